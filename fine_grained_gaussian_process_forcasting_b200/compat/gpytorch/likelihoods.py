@@ -1,0 +1,1 @@
+from fine_grained_gaussian_process_forcasting_b200.gpcompat import GaussianLikelihood  # noqa: F401

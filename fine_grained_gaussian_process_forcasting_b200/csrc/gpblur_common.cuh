@@ -1,0 +1,197 @@
+// Shared definitions for the gpblur sm_100a kernels: workspace layout, Philox, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/gpblur.h"
+
+namespace gpblur {
+
+constexpr float kJitter = 1e-4f;        // gpytorch.settings.variational_cholesky_jitter (fp32)
+constexpr float kMinVariance = 1e-6f;   // gpytorch.settings.min_variance (fp32)
+constexpr float kNoiseLower = 1e-4f;    // GaussianLikelihood GreaterThan(1e-4)
+constexpr int kThreads = 256;
+constexpr int kKS = 16;                 // K-slice depth of the staged operand tiles
+constexpr int kMaxPersist = 296;        // persistent CTAs of the backward point kernel (2 x 148 SMs)
+constexpr int kMaxSplits = 64;          // split-K factor cap of the N-reduction GEMMs
+
+// hyp (fp32) slots
+enum { H_OS = 0, H_JIT = 1, H_CWB = 2, H_KL = 3, H_COUNT = 8 };
+// per-CTA vector partial layout of the backward point kernel: [colsum MP | q DP | wbar DP | scalars 4]
+enum { VS_GMU = 0, VS_RSUM = 1, VS_GVAR = 2, VS_COUNT = 4 };
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// padded inducing count: 32, 64, or a multiple of 128
+__host__ __device__ inline int padded_m(int M) {
+  if (M <= 32) return 32;
+  if (M <= 64) return 64;
+  return round_up(M, 128);
+}
+// padded input dim: 16, 32, 64 or 128
+__host__ __device__ inline int padded_d(int D) {
+  if (D <= 16) return 16;
+  if (D <= 32) return 32;
+  if (D <= 64) return 64;
+  return 128;
+}
+
+struct WsLayout {
+  long long N;
+  int D, DP, M, MP;
+  int training;
+  int splitsS, splitsZ;     // split-K factors of the Gram / W^T X reductions
+  int nvec;                 // number of per-CTA vector partials (persistent backward CTAs)
+  int vec_len;              // floats per vector partial
+  // byte offsets
+  size_t hyp, hyp64, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
+  size_t K64, L64, Linv64, T64, U64, LinvT32, LC32;
+  size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64;
+  size_t total;
+};
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+inline int choose_splits(long long N, int ntiles) {
+  // enough CTAs to fill ~2 waves of 148 SMs, each split at least 256 rows deep
+  long long want = (2 * 148 + ntiles - 1) / ntiles;
+  long long maxs = (N + 255) / 256;
+  long long s = want < maxs ? want : maxs;
+  if (s < 1) s = 1;
+  if (s > kMaxSplits) s = kMaxSplits;
+  return (int)s;
+}
+
+inline WsLayout make_layout(long long N, int D, int M, int training) {
+  WsLayout w;
+  w.N = N; w.D = D; w.M = M; w.training = training;
+  w.DP = padded_d(D); w.MP = padded_m(M);
+  const size_t MP = w.MP, DP = w.DP;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  w.hyp = take(H_COUNT * 4);
+  w.hyp64 = take(H_COUNT * 8);
+  w.inv_ell = take(DP * 4);
+  w.ell = take(DP * 4);
+  w.center = take(DP * 4);
+  w.wl = take(DP * 4);
+  w.Zt = take(MP * DP * 4);
+  w.ZtT = take(DP * MP * 4);
+  w.zn = take(MP * 4);
+  w.mvec = take(MP * 4);
+  w.cvec = take(MP * 4);
+  w.svec = take(MP * 4);
+  w.beta = take(MP * 4);
+  w.K64 = take(MP * MP * 8);
+  w.L64 = take(MP * MP * 8);
+  w.Linv64 = take(MP * MP * 8);
+  w.T64 = take(MP * MP * 8);
+  w.U64 = take(MP * MP * 8);
+  w.LinvT32 = take(MP * MP * 4);
+  w.LC32 = take(MP * MP * 4);
+  const int tp = w.MP < 128 ? w.MP : 128;
+  const int nt = w.MP / tp;
+  w.splitsS = choose_splits(N, nt * (nt + 1) / 2);
+  w.splitsZ = choose_splits(N, nt);
+  w.nvec = kMaxPersist;
+  w.vec_len = w.MP + 2 * w.DP + VS_COUNT;
+  if (training) {
+    w.A = take((size_t)N * MP * 4);
+    w.W = take((size_t)N * MP * 4);
+    w.Spart = take((size_t)w.splitsS * MP * MP * 4);
+    w.upart = take((size_t)w.splitsS * MP * 4);
+    w.WXpart = take((size_t)w.splitsZ * MP * DP * 4);
+    w.vecpart = take((size_t)w.nvec * w.vec_len * 4);
+    w.gsc = take((size_t)2 * (N > 0 ? N : 1) * 4);   // folded upstream grads g_mu, g_var [N] each
+    w.v64 = take((size_t)(3 * MP + w.vec_len) * 8);
+    w.t64 = take((size_t)MP * DP * 8);
+  } else {
+    w.A = w.W = w.Spart = w.upart = w.WXpart = w.vecpart = w.gsc = w.v64 = w.t64 = o;
+  }
+  w.total = o;
+  return w;
+}
+
+template <typename T>
+__host__ __device__ inline T* ws_ptr(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+template <typename T>
+__host__ __device__ inline const T* ws_cptr(const void* ws, size_t off) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(ws) + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double softplus64(double x) {
+  return x > 30.0 ? x : log1p(exp(x));
+}
+__device__ __forceinline__ double sigmoid64(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// Philox4x32-10 (Random123).  Counter layout documented in oracle/gp_oracle.py::philox_bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 philox_element(uint64_t seed, uint64_t e, uint32_t stream_id) {
+  return philox4x32_10(make_uint4((uint32_t)e, (uint32_t)(e >> 32), stream_id, 0u),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t e, uint32_t stream_id) {
+  const uint4 r = philox_element(seed, e, stream_id);
+  const float u1 = ((float)(r.x >> 9) + 0.5f) * 1.1920928955078125e-07f;   // 2^-23
+  const float u2 = ((float)(r.y >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// host-side launch bookkeeping (defined in gpblur_api.cu)
+void note_launch(int n = 1);
+int check_launch(const char* what);
+int num_sms();
+
+// launchers implemented in the other translation units
+int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
+                      cudaStream_t st);
+int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
+                       float* grad_bucket, cudaStream_t st);
+int launch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var,
+                         float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                         cudaStream_t st);
+int launch_point_backward(const WsLayout& L, void* ws, const float* x, const float* g_mean,
+                          const float* g_var, const float* g_sample, const float* var, uint64_t seed,
+                          uint64_t offset, uint32_t stream_id, float* dx, cudaStream_t st);
+int launch_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st);
+
+}  // namespace gpblur

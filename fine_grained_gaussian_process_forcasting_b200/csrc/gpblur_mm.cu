@@ -1,0 +1,687 @@
+// Once-per-step M x M stage of the whitened SVGP, fp64, one cooperative launch each way.
+//
+// forward  (replaces gpytorch's B batched copies of: kernel(Z,Z) build, add_jitter, psd_safe_cholesky in
+//           float64 and the triangular solve set-up; /root/reference/denoising_model/DeepGP.py:33-38,46-49
+//           via VariationalStrategy.forward):
+//   phase 0  hyper-parameters (softplus constraints), input centre, KL(q(u) || N(0, I))
+//   phase 1  scaled/centred inducing points Zt, Kzz + jitter (fp64, direct differences)
+//   phase 2  right-looking blocked Cholesky, 32 x 32 blocks staged in shared memory
+//   phase 3  triangular inverse Linv = L^-1 by recursive doubling (all-GEMM, parallel over tiles)
+//   phase 4  fp32 operands for the per-point kernels: Linv^T, diag(c) Linv, beta = Linv^T m
+// backward (replaces LinalgCholeskyExBackward0 + kernel-matrix autograd):
+//   Gbar = beta u^T + 2 Linv^T diag(c) S ; Lbar = -tril(Gbar) ; Kbar = sym(Linv^T Phi(L^T Lbar) Linv)
+//   then the Kzz-path gradients of Z, lengthscale, outputscale and the final parameter bucket.
+//
+// All matrices are [MP, MP] row-major doubles with MP a multiple of 32 (identity padding).
+#include <cooperative_groups.h>
+
+#include "gpblur_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gpblur {
+
+namespace {
+
+constexpr int TB = 32;          // block size of the blocked algorithms
+constexpr int TLD = TB + 1;     // padded leading dimension of a shared tile
+typedef double Tile[TB][TLD];
+
+struct MatRef {
+  const double* p;
+  int ld;
+  bool trans;   // element(i, j) = trans ? p[j * ld + i] : p[i * ld + j]
+};
+
+// dst[r][c] = M(r0 + r, c0 + c), coalesced for both orientations.  256 threads.
+__device__ __forceinline__ void load_tile(Tile& dst, const MatRef& m, int r0, int c0) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i;
+    if (!m.trans) dst[r][tx] = m.p[(size_t)(r0 + r) * m.ld + c0 + tx];
+    else dst[tx][r] = m.p[(size_t)(c0 + r) * m.ld + r0 + tx];
+  }
+}
+
+// acc[i] (+)= sum_{k in [k0, k1)} A(r0 + ty + 8 i, k) * B(k, c0 + tx);  k0, k1 multiples of 32.
+__device__ __forceinline__ void tile_gemm(double acc[4], const MatRef& A, int r0, const MatRef& B, int c0,
+                                          int k0, int k1, Tile& As, Tile& Bs) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int kk = k0; kk < k1; kk += TB) {
+    __syncthreads();
+    load_tile(As, A, r0, kk);
+    load_tile(Bs, B, kk, c0);
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < TB; ++k) {
+      const double b = Bs[k][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fma(As[ty + 8 * i][k], b, acc[i]);
+    }
+  }
+}
+
+// decode t -> (i, j) with j <= i, t = i (i + 1) / 2 + j
+__device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
+  int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+  while (ii * (ii + 1) / 2 > t) --ii;
+  i = ii;
+  j = t - ii * (ii + 1) / 2;
+}
+
+struct MmFwdArgs {
+  gpblur_svgp_params p;
+  WsLayout L;
+  void* ws;
+  float* kl;
+  int* info;
+};
+
+__global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
+  Tile& As = tiles[0];
+  Tile& Bs = tiles[1];
+  Tile* Cs = tiles + 2;   // 8 per-warp tiles
+  Tile& Dg = tiles[10];   // factorised diagonal block of the current panel
+
+  const WsLayout& L = a.L;
+  const int D = L.D, DP = L.DP, M = L.M, MP = L.MP;
+  const int nb = MP / TB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int gtid = blockIdx.x * kThreads + tid, gsize = G * kThreads;
+
+  float* hyp = ws_ptr<float>(a.ws, L.hyp);
+  double* hyp64 = ws_ptr<double>(a.ws, L.hyp64);
+  float* inv_ell = ws_ptr<float>(a.ws, L.inv_ell);
+  float* ellv = ws_ptr<float>(a.ws, L.ell);
+  float* center = ws_ptr<float>(a.ws, L.center);
+  float* wl = ws_ptr<float>(a.ws, L.wl);
+  float* Zt = ws_ptr<float>(a.ws, L.Zt);
+  float* ZtT = ws_ptr<float>(a.ws, L.ZtT);
+  float* mvec = ws_ptr<float>(a.ws, L.mvec);
+  float* cvec = ws_ptr<float>(a.ws, L.cvec);
+  float* svec = ws_ptr<float>(a.ws, L.svec);
+  float* beta = ws_ptr<float>(a.ws, L.beta);
+  double* K64 = ws_ptr<double>(a.ws, L.K64);
+  double* L64 = ws_ptr<double>(a.ws, L.L64);
+  double* Li64 = ws_ptr<double>(a.ws, L.Linv64);
+  double* T64 = ws_ptr<double>(a.ws, L.T64);
+  float* LinvT32 = ws_ptr<float>(a.ws, L.LinvT32);
+  float* LC32 = ws_ptr<float>(a.ws, L.LC32);
+  const float* Z = a.p.inducing_points;
+
+  // ---------------- phase 0: per-dimension hyper-parameters, centre, KL ----------------
+  for (int d = blockIdx.x * 8 + warp; d < DP; d += G * 8) {
+    if (d < D) {
+      const double ell = softplus64((double)a.p.raw_lengthscale[d]);
+      double s = 0.0;
+      for (int m = lane; m < M; m += 32) s += (double)Z[(size_t)m * D + d];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float c = (float)(s / (double)M);
+        center[d] = c;
+        ellv[d] = (float)ell;
+        inv_ell[d] = (float)(1.0 / ell);
+        wl[d] = a.p.mean_weights ? (float)(ell * (double)a.p.mean_weights[d]) : 0.0f;
+      }
+    } else if (lane == 0) {
+      center[d] = 0.f; ellv[d] = 1.f; inv_ell[d] = 0.f; wl[d] = 0.f;
+    }
+  }
+  if (blockIdx.x == 0) {
+    // KL( N(m, diag s^2) || N(0, I) ) = 1/2 [ sum s^2 + sum m^2 - M - sum log s^2 ]
+    double part = 0.0;
+    for (int m = tid; m < M; m += kThreads) {
+      const double mm = (double)a.p.variational_mean[m];
+      const double ss = (double)a.p.variational_stddev[m];
+      part += ss * ss + mm * mm - 1.0 - log(ss * ss);
+    }
+    part = warp_sum(part);
+    __shared__ double red[8];
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      const double os = softplus64((double)a.p.raw_outputscale[0]);
+      hyp[H_OS] = (float)os;
+      hyp[H_JIT] = kJitter;
+      hyp[H_KL] = (float)(0.5 * t);
+      hyp64[H_OS] = os;
+      hyp64[H_KL] = 0.5 * t;
+      if (a.kl) a.kl[0] = (float)(0.5 * t);
+      if (a.info) a.info[0] = 0;
+    }
+  }
+  grid.sync();
+
+  // ---------------- phase 1: Zt, vectors, Kzz ----------------
+  for (int idx = gtid; idx < MP * DP; idx += gsize) {
+    const int m = idx / DP, d = idx - m * DP;
+    float v = 0.f;
+    if (m < M && d < D) v = (Z[(size_t)m * D + d] - center[d]) * inv_ell[d];
+    Zt[idx] = v;
+    ZtT[(size_t)d * MP + m] = v;
+  }
+  for (int m = gtid; m < MP; m += gsize) {
+    const float mm = m < M ? a.p.variational_mean[m] : 0.f;
+    const float ss = m < M ? a.p.variational_stddev[m] : 1.f;
+    mvec[m] = mm;
+    svec[m] = ss;
+    cvec[m] = m < M ? ss * ss - 1.0f : 0.f;
+  }
+  if (blockIdx.x == 0 && warp == 0) {
+    double s = 0.0;
+    if (a.p.mean_weights)
+      for (int d = lane; d < D; d += 32) s += (double)center[d] * (double)a.p.mean_weights[d];
+    s = warp_sum(s);
+    if (lane == 0) hyp[H_CWB] = (float)(s + (double)a.p.mean_bias[0]);
+  }
+  {
+    const double os = softplus64((double)a.p.raw_outputscale[0]);
+    const int ntiles = nb * (nb + 1) / 2;
+    const int tx = lane, ty = warp;
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+      int bi, bj;
+      tri_decode(t, bi, bj);
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int d0 = 0; d0 < D; d0 += TB) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ty + 8 * i;
+          const int d = d0 + tx;
+          double va = 0.0, vb = 0.0;
+          if (d < D) {
+            const double ie = 1.0 / softplus64((double)a.p.raw_lengthscale[d]);
+            const int ra = bi * TB + r, rb = bj * TB + r;
+            if (ra < M) va = (double)Z[(size_t)ra * D + d] * ie;
+            if (rb < M) vb = (double)Z[(size_t)rb * D + d] * ie;
+          }
+          As[r][tx] = va;
+          Bs[r][tx] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < TB; ++k) {
+          const double b = Bs[tx][k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double df = As[ty + 8 * i][k] - b;
+            acc[i] = fma(df, df, acc[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = bi * TB + ty + 8 * i, gj = bj * TB + tx;
+        double kv;
+        if (gi < M && gj < M) kv = os * exp(-0.5 * acc[i]) + (gi == gj ? (double)kJitter : 0.0);
+        else kv = (gi == gj) ? 1.0 : 0.0;
+        K64[(size_t)gi * MP + gj] = kv;
+        K64[(size_t)gj * MP + gi] = kv;
+        L64[(size_t)gi * MP + gj] = (gj <= gi) ? kv : 0.0;
+        if (bi != bj) L64[(size_t)gj * MP + gi] = 0.0;
+      }
+    }
+  }
+  grid.sync();
+
+  // ---------------- phase 2: blocked Cholesky (right-looking) ----------------
+  for (int kb = 0; kb < nb; ++kb) {
+    const int nrb = nb - kb - 1;
+    const bool has_rows = (blockIdx.x * 8) < nrb;
+    if (has_rows || blockIdx.x == 0) {
+      __syncthreads();
+      load_tile(Dg, MatRef{L64, MP, false}, kb * TB, kb * TB);
+      __syncthreads();
+      if (warp == 0) {
+        for (int c = 0; c < TB; ++c) {
+          double d = Dg[c][c];
+          if (!(d > 0.0)) {
+            if (blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + c + 1);
+          }
+          const double sd = sqrt(d);
+          __syncwarp();
+          if (lane == c) Dg[c][c] = sd;
+          if (lane > c) Dg[lane][c] = Dg[lane][c] / sd;
+          __syncwarp();
+          if (lane > c) {
+            const double l = Dg[lane][c];
+            for (int c2 = c + 1; c2 <= lane; ++c2) Dg[lane][c2] = fma(-l, Dg[c2][c], Dg[lane][c2]);
+          }
+          __syncwarp();
+        }
+        for (int c = lane + 1; c < TB; ++c) Dg[lane][c] = 0.0;
+      }
+      __syncthreads();
+      // panel: X L_kk^T = A_ik, one row block per warp, one row per lane
+      for (int rb0 = blockIdx.x * 8; rb0 < nrb; rb0 += G * 8) {
+        const int rb = rb0 + warp;
+        if (rb < nrb) {
+          Tile& C = Cs[warp];
+          const int row0 = (kb + 1 + rb) * TB;
+          for (int r = 0; r < TB; ++r) C[r][lane] = L64[(size_t)(row0 + r) * MP + kb * TB + lane];
+          __syncwarp();
+          for (int c = 0; c < TB; ++c) {
+            double x = C[lane][c];
+            for (int c2 = 0; c2 < c; ++c2) x = fma(-C[lane][c2], Dg[c][c2], x);
+            C[lane][c] = x / Dg[c][c];
+          }
+          __syncwarp();
+          for (int r = 0; r < TB; ++r) L64[(size_t)(row0 + r) * MP + kb * TB + lane] = C[r][lane];
+        }
+      }
+    }
+    grid.sync();
+    // the factorised diagonal block is published only now: other CTAs read the unfactorised one above
+    if (blockIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = warp + 8 * i;
+        L64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Dg[r][lane];
+      }
+    }
+    // trailing update: C_ij -= L_ik L_jk^T for kb < j <= i
+    const int ntr = nrb * (nrb + 1) / 2;
+    for (int t = blockIdx.x; t < ntr; t += G) {
+      int ti, tj;
+      tri_decode(t, ti, tj);
+      const int bi = kb + 1 + ti, bj = kb + 1 + tj;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
+                kb * TB + TB, As, Bs);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = warp + 8 * i;
+        if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] -= acc[i];
+      }
+    }
+    if (ntr > 0) grid.sync();
+  }
+
+  // ---------------- phase 3a: inverses of the diagonal blocks ----------------
+  for (int b = blockIdx.x; b < nb; b += G) {
+    __syncthreads();
+    load_tile(As, MatRef{L64, MP, false}, b * TB, b * TB);
+    __syncthreads();
+    if (warp == 0) {
+      const int c = lane;   // column of the inverse
+      for (int r = 0; r < TB; ++r) {
+        double x = 0.0;
+        if (r >= c) {
+          double s = (r == c) ? 1.0 : 0.0;
+          for (int k = c; k < r; ++k) s = fma(-As[r][k], Bs[k][c], s);
+          x = s / As[r][r];
+        }
+        Bs[r][c] = x;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      Li64[(size_t)(b * TB + r) * MP + b * TB + lane] = Bs[r][lane];
+    }
+  }
+  grid.sync();
+  // ---------------- phase 3b: recursive doubling  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]] ----
+  for (int s = TB; s < MP; s *= 2) {
+    const int sb = s / TB;                    // blocks per half
+    const int npairs = (MP + 2 * s - 1) / (2 * s);
+    // phase a: T = C * Ainv
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int pr = 0; pr < npairs; ++pr) {
+        const int start = pr * 2 * s, mid = start + s;
+        if (mid >= MP) continue;
+        const int end = (start + 2 * s < MP) ? start + 2 * s : MP;
+        const int rbk = (end - mid) / TB;
+        const int nt = rbk * sb;
+        for (int t = blockIdx.x; t < nt; t += G) {
+          const int tr = t / sb, tc = t - tr * sb;
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          if (pass == 0) {
+            // T[mid + r][start + c] = sum_{k >= c-tile} L[mid + r][start + k] Ainv[start + k][start + c]
+            tile_gemm(acc, MatRef{L64, MP, false}, mid + tr * TB, MatRef{Li64, MP, false},
+                      start + tc * TB, start + tc * TB, mid, As, Bs);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              T64[(size_t)(mid + tr * TB + warp + 8 * i) * MP + start + tc * TB + lane] = acc[i];
+          } else {
+            // X[mid + r][start + c] = - sum_{k <= r-tile} Binv[mid + r][mid + k] T[mid + k][start + c]
+            tile_gemm(acc, MatRef{Li64, MP, false}, mid + tr * TB, MatRef{T64, MP, false},
+                      start + tc * TB, mid, mid + (tr + 1) * TB, As, Bs);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              Li64[(size_t)(mid + tr * TB + warp + 8 * i) * MP + start + tc * TB + lane] = -acc[i];
+          }
+        }
+      }
+      grid.sync();
+    }
+  }
+
+  // ---------------- phase 4: fp32 operands ----------------
+  for (int t = blockIdx.x; t < nb * nb; t += G) {
+    const int bi = t / nb, bj = t - bi * nb;
+    __syncthreads();
+    if (bi >= bj) load_tile(As, MatRef{Li64, MP, false}, bi * TB, bj * TB);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      // LC32 tile (bi, bj): element (r, lane)
+      const int gi = bi * TB + r, gj = bj * TB + lane;
+      float v = 0.f;
+      if (bi >= bj && gj <= gi) v = (float)As[r][lane];
+      LC32[(size_t)gi * MP + gj] = v * cvec[gi];
+      // LinvT32 tile (bj, bi): element (r, lane) = Linv[bi*TB + lane][bj*TB + r]
+      const int ti = bi * TB + lane, tj = bj * TB + r;
+      float vt = 0.f;
+      if (bi >= bj && tj <= ti) vt = (float)As[lane][r];
+      LinvT32[(size_t)tj * MP + ti] = vt;
+    }
+  }
+  float* zn = ws_ptr<float>(a.ws, L.zn);
+  for (int j = gtid; j < MP; j += gsize) {
+    double s = 0.0;
+    for (int i = j; i < M; ++i) s = fma(Li64[(size_t)i * MP + j], (double)mvec[i], s);
+    beta[j] = (float)s;
+    float z2 = 0.f;
+    for (int d = 0; d < DP; ++d) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
+    zn[j] = z2;
+  }
+}
+
+// ==================================================================================================
+struct MmBwdArgs {
+  gpblur_svgp_params p;
+  WsLayout L;
+  void* ws;
+  const float* g_kl;
+  float* bucket;
+  int nvec_used;
+};
+
+__global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
+  Tile& As = tiles[0];
+  Tile& Bs = tiles[1];
+
+  const WsLayout& L = a.L;
+  const int D = L.D, DP = L.DP, M = L.M, MP = L.MP;
+  const int nb = MP / TB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int gtid = blockIdx.x * kThreads + tid, gsize = G * kThreads;
+
+  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
+  double* hyp64 = ws_ptr<double>(a.ws, L.hyp64);
+  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
+  const float* center = ws_cptr<float>(a.ws, L.center);
+  const float* Zt = ws_cptr<float>(a.ws, L.Zt);
+  const float* mvec = ws_cptr<float>(a.ws, L.mvec);
+  const float* cvec = ws_cptr<float>(a.ws, L.cvec);
+  const float* svec = ws_cptr<float>(a.ws, L.svec);
+  const float* beta = ws_cptr<float>(a.ws, L.beta);
+  const double* K64 = ws_cptr<double>(a.ws, L.K64);
+  const double* L64 = ws_cptr<double>(a.ws, L.L64);
+  const double* Li64 = ws_cptr<double>(a.ws, L.Linv64);
+  double* T64 = ws_ptr<double>(a.ws, L.T64);
+  double* U64 = ws_ptr<double>(a.ws, L.U64);
+  const float* Spart = ws_cptr<float>(a.ws, L.Spart);
+  const float* upart = ws_cptr<float>(a.ws, L.upart);
+  const float* WXpart = ws_cptr<float>(a.ws, L.WXpart);
+  const float* vecpart = ws_cptr<float>(a.ws, L.vecpart);
+  // fp64 vector scratch: [u MP | vec vec_len | diag(S) MP | rz MP]
+  double* v64 = ws_ptr<double>(a.ws, L.v64);
+  double* u64 = v64;
+  double* vec64 = v64 + MP;
+  double* sdiag = vec64 + L.vec_len;
+  double* rz64 = sdiag + MP;
+  double* t64 = ws_ptr<double>(a.ws, L.t64);   // [MP, DP] per-(i, d) terms of d lengthscale
+
+  const int tp = MP < 128 ? MP : 128;   // tile size used by the Gram reduction (lower tile triangle valid)
+
+  // ---------------- phase 0: reduce split partials ----------------
+  for (int m = gtid; m < MP; m += gsize) {
+    double s = 0.0;
+    for (int sp = 0; sp < L.splitsS; ++sp) s += (double)upart[(size_t)sp * MP + m];
+    u64[m] = s;
+  }
+  for (int e = gtid; e < L.vec_len; e += gsize) {
+    double s = 0.0;
+    for (int c = 0; c < a.nvec_used; ++c) s += (double)vecpart[(size_t)c * L.vec_len + e];
+    vec64[e] = s;
+  }
+  for (int idx = gtid; idx < MP * MP; idx += gsize) {
+    const int i = idx / MP, j = idx - i * MP;
+    // Gram partials hold the lower tile triangle (tile size tp); mirror the rest
+    const int si = (i / tp >= j / tp) ? i : j, sj = (i / tp >= j / tp) ? j : i;
+    double s = 0.0;
+    for (int sp = 0; sp < L.splitsS; ++sp) s += (double)Spart[((size_t)sp * MP + si) * MP + sj];
+    if (i == j) sdiag[i] = s;
+    T64[idx] = (double)cvec[i] * s;          // cS = diag(c) S
+  }
+  grid.sync();
+
+  // ---------------- phase 1: Lbar = -tril( beta u^T + 2 Linv^T cS ) -> U64 ----------------
+  {
+    const int ntl = nb * (nb + 1) / 2;
+    for (int t = blockIdx.x; t < nb * nb; t += G) {
+      const int bi = t / nb, bj = t - bi * nb;
+      if (bi < bj) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+        continue;
+      }
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{T64, MP, false}, bj * TB, bi * TB, MP, As, Bs);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
+        const double g = (double)beta[gi] * u64[gj] + 2.0 * acc[i];
+        U64[(size_t)gi * MP + gj] = (gj <= gi) ? -g : 0.0;
+      }
+    }
+    (void)ntl;
+  }
+  grid.sync();
+
+  // ---------------- phase 2: Phi( L^T Lbar ) -> T64 (lower) ----------------
+  for (int t = blockIdx.x; t < nb * nb; t += G) {
+    const int bi = t / nb, bj = t - bi * nb;
+    if (bi < bj) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+      continue;
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    tile_gemm(acc, MatRef{L64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, bi * TB, MP, As, Bs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
+      double v = acc[i];
+      if (gj > gi) v = 0.0;
+      else if (gj == gi) v *= 0.5;
+      T64[(size_t)gi * MP + gj] = v;
+    }
+  }
+  grid.sync();
+
+  // ---------------- phase 3: Tm = Phi Linv -> U64 (lower) ----------------
+  for (int t = blockIdx.x; t < nb * nb; t += G) {
+    const int bi = t / nb, bj = t - bi * nb;
+    if (bi < bj) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+      continue;
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // sum over k in [bj-tile, bi-tile]; operand zeros handle the ragged edges inside the diagonal tiles
+    tile_gemm(acc, MatRef{T64, MP, false}, bi * TB, MatRef{Li64, MP, false}, bj * TB, bj * TB,
+              (bi + 1) * TB, As, Bs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
+  }
+  grid.sync();
+
+  // ---------------- phase 4: Kb = Linv^T Tm -> T64 (full) ----------------
+  for (int t = blockIdx.x; t < nb * nb; t += G) {
+    const int bi = t / nb, bj = t - bi * nb;
+    const int kb0 = bi > bj ? bi : bj;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, kb0 * TB, MP, As, Bs);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
+  }
+  grid.sync();
+
+  // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
+  for (int idx = gtid; idx < MP * MP; idx += gsize) {
+    const int i = idx / MP, j = idx - i * MP;
+    double v = 0.0;
+    if (i < M && j < M) {
+      const double kb = 0.5 * (T64[idx] + T64[(size_t)j * MP + i]);
+      const double kz = K64[idx] - (i == j ? (double)kJitter : 0.0);
+      v = kb * kz;
+    }
+    U64[idx] = v;
+  }
+  grid.sync();
+
+  // ---------------- phase 6: Kzz-path + a-space gradients of Z; per-(i, d) terms of d ell -------
+  for (int idx = gtid; idx < MP * DP; idx += gsize) {
+    const int i = idx / DP, d = idx - i * DP;
+    double tval = 0.0;
+    if (i < M && d < D) {
+      double V = 0.0, rz = 0.0;
+      for (int j = 0; j < M; ++j) {
+        const double w = U64[(size_t)i * MP + j];
+        V = fma(w, (double)Zt[(size_t)j * DP + d], V);
+        rz += w;
+      }
+      if (d == 0) rz64[i] = rz;
+      double wx = 0.0;
+      for (int sp = 0; sp < L.splitsZ; ++sp) wx += (double)WXpart[((size_t)sp * MP + i) * DP + d];
+      const double ie = (double)inv_ell[d];
+      const double csum = vec64[i];
+      const double z = (double)Zt[(size_t)i * DP + d];
+      const double wxt = (wx - csum * (double)center[d]) * ie;          // (W^T Xtilde)_id
+      const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
+      a.bucket[(size_t)i * D + d] = (float)dz;
+      tval = -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
+    }
+    t64[idx] = tval;
+  }
+  grid.sync();
+
+  // ---------------- phase 7: final bucket (block 0) ----------------
+  if (blockIdx.x == 0) {
+    const double os = hyp64[H_OS];
+    const double gkl = a.g_kl ? (double)a.g_kl[0] : 0.0;
+    float* b_ell = a.bucket + (size_t)M * D;
+    float* b_os = b_ell + D;
+    float* b_m = b_os + 1;
+    float* b_s = b_m + M;
+    float* b_w = b_s + M;
+    float* b_b = b_w + D;
+    const double* q = vec64 + MP;
+    const double* wbar = vec64 + MP + DP;
+    const double* sc = vec64 + MP + 2 * DP;
+    for (int d = tid; d < D; d += kThreads) {
+      double s = q[d];
+      for (int i = 0; i < M; ++i) s += t64[(size_t)i * DP + d];
+      const double dell = s * (double)inv_ell[d];
+      b_ell[d] = (float)(dell * sigmoid64((double)a.p.raw_lengthscale[d]));
+      b_w[d] = a.p.mean_weights ? (float)wbar[d] : 0.f;
+    }
+    for (int m = tid; m < M; m += kThreads) {
+      const double mm = (double)mvec[m], ss = (double)svec[m];
+      b_m[m] = (float)(u64[m] + gkl * mm);
+      b_s[m] = (float)(2.0 * ss * sdiag[m] + gkl * (ss - 1.0 / ss));
+    }
+    if (warp == 0) {
+      double s = 0.0;
+      for (int i = lane; i < M; i += 32) s += rz64[i];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const double dos = (s + sc[VS_RSUM]) / os + sc[VS_GVAR];
+        b_os[0] = (float)(dos * sigmoid64((double)a.p.raw_outputscale[0]));
+        b_b[0] = (float)sc[VS_GMU];
+      }
+    }
+  }
+  (void)hyp;
+}
+
+int coop_grid(const void* func, int want, size_t smem) {
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, kThreads, smem);
+  if (occ < 1) occ = 1;
+  const int cap = occ * num_sms();
+  if (want < 1) want = 1;
+  return want < cap ? want : cap;
+}
+
+}  // namespace
+
+int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
+                      cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(Tile) * 11;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const int nb = L.MP / TB;
+  int want = nb * nb;
+  const int dwant = (L.MP * L.DP + kThreads * 4 - 1) / (kThreads * 4);
+  if (want < dwant) want = dwant;
+  if (want > 148) want = 148;
+  const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
+  MmFwdArgs args{p, L, ws, kl, info};
+  void* kargs[] = {&args};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_forward_kernel, dim3(grid), dim3(kThreads),
+                                              kargs, smem, st);
+  note_launch();
+  if (e != cudaSuccess) return check_launch("mm_forward");
+  return GPBLUR_OK;
+}
+
+int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
+                       float* grad_bucket, cudaStream_t st);
+
+int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
+                     float* grad_bucket, int nvec_used, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(Tile) * 2;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const int nb = L.MP / TB;
+  int want = nb * nb;
+  const int dwant = (L.MP * L.DP + kThreads - 1) / kThreads;
+  if (want < dwant) want = dwant;
+  if (want > 148) want = 148;
+  const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
+  MmBwdArgs args{p, L, ws, g_kl, grad_bucket, nvec_used};
+  void* kargs[] = {&args};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),
+                                              kargs, smem, st);
+  note_launch();
+  if (e != cudaSuccess) return check_launch("mm_backward");
+  return GPBLUR_OK;
+}
+
+}  // namespace gpblur

@@ -1,0 +1,368 @@
+"""torch-facing ops over the gpblur C ABI: thin wrappers (device pointers + current CUDA stream in,
+fresh tensors out), registered as ``torch.ops.gpblur.*`` custom ops, plus the autograd glue.
+
+There is no CPU path: every op raises on non-CUDA tensors and the loader raises if libgpblur.so is
+missing (``_cabi.lib``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "gpblur ops run only on CUDA tensors (B200 / sm_100a); there is no CPU fallback")
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _params_struct(Z, raw_ell, raw_os, m, s, w, b) -> _cabi.SvgpParams:
+    return _cabi.SvgpParams(Z.data_ptr(), raw_ell.data_ptr(), raw_os.data_ptr(), m.data_ptr(), s.data_ptr(),
+                            None if w is None else w.data_ptr(), b.data_ptr())
+
+
+def grad_bucket_floats(D: int, M: int) -> int:
+    return M * D + 2 * M + 2 * D + 2
+
+
+def workspace_bytes(N: int, D: int, M: int, training: bool) -> int:
+    n = int(_cabi.lib().gpblur_svgp_workspace_bytes(N, D, M, int(training)))
+    if n == 0:
+        raise RuntimeError(f"unsupported SVGP shape N={N} D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, "
+                           f"M <= {_cabi.GPBLUR_MAX_M})")
+    return n
+
+
+# ------------------------------------------------------------------------------------------------
+# raw calls
+# ------------------------------------------------------------------------------------------------
+def svgp_forward_raw(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: Tensor, s: Tensor,
+                     w: Optional[Tensor], b: Tensor, seed: int, offset: int, stream_id: int,
+                     want_sample: bool, training: bool):
+    """x [N, D] -> (mean [N], var [N], sample [N] | None, kl [1], info [1] int32, workspace uint8)."""
+    _need_cuda(x, Z, raw_ell, raw_os, m, s, w, b)
+    N, D = x.shape
+    M = Z.shape[0]
+    dev = x.device
+    mean = torch.empty(N, device=dev, dtype=torch.float32)
+    var = torch.empty(N, device=dev, dtype=torch.float32)
+    sample = torch.empty(N, device=dev, dtype=torch.float32) if want_sample else None
+    kl = torch.empty(1, device=dev, dtype=torch.float32)
+    info = torch.empty(1, device=dev, dtype=torch.int32)
+    ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
+    p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_forward(
+            C.byref(p), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+            _ptr(kl), _ptr(info), int(training), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_forward")
+    return mean, var, sample, kl, info, ws
+
+
+def svgp_backward_raw(x, Z, raw_ell, raw_os, m, s, w, b, g_mean, g_var, g_sample, g_kl, var, seed, offset,
+                      stream_id, ws, need_dx: bool = True):
+    """-> (dx [N, D] | None, bucket [M*D + 2M + 2D + 2])."""
+    _need_cuda(x, Z, ws, g_mean, g_var, g_sample, g_kl, var)
+    N, D = x.shape
+    M = Z.shape[0]
+    dev = x.device
+    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if need_dx else None
+    bucket = torch.empty(grad_bucket_floats(D, M), device=dev, dtype=torch.float32)
+    p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_backward(
+            C.byref(p), _ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(g_kl), _ptr(var),
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+            _ptr(dx), _ptr(bucket), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_backward")
+    return dx, bucket
+
+
+def split_bucket(bucket: Tensor, D: int, M: int, has_weights: bool):
+    """Views of the flat gradient bucket in parameter order (see include/gpblur.h)."""
+    o = 0
+    dZ = bucket[o:o + M * D].view(M, D); o += M * D
+    dell = bucket[o:o + D]; o += D
+    dos = bucket[o:o + 1]; o += 1
+    dm = bucket[o:o + M]; o += M
+    ds = bucket[o:o + M]; o += M
+    dw = bucket[o:o + D] if has_weights else None; o += D
+    db = bucket[o:o + 1]
+    return dZ, dell, dos, dm, ds, dw, db
+
+
+def elbo_forward_raw(mean, var, y, raw_noise, kl, num_data: float):
+    _need_cuda(mean, var, y, raw_noise, kl)
+    B, L = mean.shape
+    elbo = torch.empty(B, device=mean.device, dtype=torch.float32)
+    with torch.cuda.device(mean.device):
+        rc = _cabi.lib().gpblur_elbo_forward(_ptr(mean), _ptr(var), _ptr(y), _ptr(raw_noise), _ptr(kl),
+                                             float(num_data), B, L, _ptr(elbo), _stream())
+    _cabi.check(rc, "gpblur_elbo_forward")
+    return elbo
+
+
+def elbo_backward_raw(mean, var, y, raw_noise, g_elbo, num_data: float):
+    _need_cuda(mean, var, y, raw_noise, g_elbo)
+    B, L = mean.shape
+    dev = mean.device
+    g_mean = torch.empty(B, L, device=dev, dtype=torch.float32)
+    g_var = torch.empty(B, L, device=dev, dtype=torch.float32)
+    g_noise = torch.empty(1, device=dev, dtype=torch.float32)
+    g_kl = torch.empty(1, device=dev, dtype=torch.float32)
+    scratch = torch.empty(max(B, 1), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_elbo_backward(_ptr(mean), _ptr(var), _ptr(y), _ptr(raw_noise), _ptr(g_elbo),
+                                              float(num_data), B, L, _ptr(g_mean), _ptr(g_var), _ptr(g_noise),
+                                              _ptr(g_kl), _ptr(scratch), _stream())
+    _cabi.check(rc, "gpblur_elbo_backward")
+    return g_mean, g_var, g_noise, g_kl
+
+
+def philox_bits(seed: int, offset: int, n: int, stream_id: int = 0, device="cuda") -> Tensor:
+    out = torch.empty(n, 4, device=device, dtype=torch.int32)
+    _need_cuda(out)
+    with torch.cuda.device(out.device):
+        rc = _cabi.lib().gpblur_philox_bits(seed, offset, stream_id, n, _ptr(out), _stream())
+    _cabi.check(rc, "gpblur_philox_bits")
+    return out
+
+
+def philox_normal(seed: int, offset: int, n: int, stream_id: int = 0, device="cuda") -> Tensor:
+    out = torch.empty(n, device=device, dtype=torch.float32)
+    _need_cuda(out)
+    with torch.cuda.device(out.device):
+        rc = _cabi.lib().gpblur_philox_normal(seed, offset, stream_id, n, _ptr(out), _stream())
+    _cabi.check(rc, "gpblur_philox_normal")
+    return out
+
+
+def rbf_covariance(x1: Tensor, x2: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor, ard: bool) -> Tensor:
+    _need_cuda(x1, x2, raw_lengthscale, raw_outputscale)
+    x1 = _f32c(x1); x2 = _f32c(x2)
+    n1, D = x1.shape
+    n2 = x2.shape[0]
+    out = torch.empty(n1, n2, device=x1.device, dtype=torch.float32)
+    with torch.cuda.device(x1.device):
+        rc = _cabi.lib().gpblur_rbf_covariance(_ptr(x1), _ptr(x2), n1, n2, D, _ptr(_f32c(raw_lengthscale)),
+                                               int(ard), _ptr(_f32c(raw_outputscale)), _ptr(out), _stream())
+    _cabi.check(rc, "gpblur_rbf_covariance")
+    return out
+
+
+def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
+    """Test probe: 0 = L, 1 = Linv, 2 = Kzz + jitter (float64 [Mp, Mp]); 3 = A (float32 [N, Mp])."""
+    mp = C.c_int(0)
+    Mp = 32 if M <= 32 else 64 if M <= 64 else (M + 127) // 128 * 128
+    if which == 3:
+        out = torch.empty(N, Mp, device=ws.device, dtype=torch.float32)
+    else:
+        out = torch.empty(Mp, Mp, device=ws.device, dtype=torch.float64)
+    with torch.cuda.device(ws.device):
+        rc = _cabi.lib().gpblur_debug_fetch(which, N, D, M, _ptr(ws), _ptr(out), out.numel() * out.element_size(),
+                                            C.byref(mp), _stream())
+    _cabi.check(rc, "gpblur_debug_fetch")
+    assert mp.value == Mp
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------
+class _SvgpFunction(torch.autograd.Function):
+    """Whitened SVGP predictive with a hand-written backward (no autograd through the kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, Z, raw_ell, raw_os, m, s, w, b, seed, offset, stream_id, want_sample):
+        shape = x.shape
+        D = shape[-1]
+        x2 = _f32c(x).reshape(-1, D)
+        Zc, ellc, osc, mc, sc, bc = (_f32c(t) for t in (Z, raw_ell, raw_os, m, s, b))
+        ellc = ellc.reshape(-1)
+        osc = osc.reshape(-1)
+        bc = bc.reshape(-1)
+        wc = None if w is None else _f32c(w).reshape(-1)
+        training = any(ctx.needs_input_grad[:8])
+        mean, var, sample, kl, info, ws = svgp_forward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, seed, offset,
+                                                           stream_id, want_sample, training)
+        if training:
+            ctx.save_for_backward(x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws)
+        ctx.rng = (seed, offset, stream_id)
+        ctx.shapes = (shape, Z.shape, raw_ell.shape, raw_os.shape, m.shape, s.shape,
+                      None if w is None else w.shape, b.shape)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(info)
+        out_shape = shape[:-1]
+        sample_out = sample.reshape(out_shape) if sample is not None else None
+        return mean.reshape(out_shape), var.reshape(out_shape), sample_out, kl.reshape(()), info
+
+    @staticmethod
+    def backward(ctx, g_mean, g_var, g_sample, g_kl, _g_info):
+        x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws = ctx.saved_tensors
+        seed, offset, stream_id = ctx.rng
+        N, D = x2.shape
+        M = Zc.shape[0]
+        gm = None if g_mean is None else _f32c(g_mean).reshape(-1)
+        gv = None if g_var is None else _f32c(g_var).reshape(-1)
+        gs = None if g_sample is None else _f32c(g_sample).reshape(-1)
+        gk = None if g_kl is None else _f32c(g_kl).reshape(1)
+        dx, bucket = svgp_backward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, gm, gv, gs, gk, var, seed, offset,
+                                       stream_id, ws, need_dx=ctx.needs_input_grad[0])
+        dZ, dell, dos, dm, ds, dw, db = split_bucket(bucket, D, M, wc is not None)
+        shp = ctx.shapes
+        need = ctx.needs_input_grad
+        return (dx.reshape(shp[0]) if need[0] else None,
+                dZ.reshape(shp[1]) if need[1] else None,
+                dell.reshape(shp[2]) if need[2] else None,
+                dos.reshape(shp[3]) if need[3] else None,
+                dm.reshape(shp[4]) if need[4] else None,
+                ds.reshape(shp[5]) if need[5] else None,
+                dw.reshape(shp[6]) if (wc is not None and need[6]) else None,
+                db.reshape(shp[7]) if need[7] else None,
+                None, None, None, None)
+
+
+def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
+                 variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
+                 mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
+                 want_sample: bool = False):
+    """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1])."""
+    return _SvgpFunction.apply(x, inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
+                               variational_stddev, mean_weights, mean_bias, int(seed), int(offset),
+                               int(stream_id), bool(want_sample))
+
+
+class _ElboFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, var, y, raw_noise, kl, num_data):
+        L = mean.shape[-1]
+        mean2 = _f32c(mean).reshape(-1, L)
+        var2 = _f32c(var).reshape(-1, L)
+        y2 = _f32c(y).expand(mean.shape).reshape(-1, L).contiguous()
+        rn = _f32c(raw_noise).reshape(-1)
+        klc = _f32c(kl).reshape(1)
+        elbo = elbo_forward_raw(mean2, var2, y2, rn, klc, num_data)
+        ctx.save_for_backward(mean2, var2, y2, rn)
+        ctx.num_data = float(num_data)
+        ctx.shapes = (mean.shape, var.shape, raw_noise.shape, kl.shape)
+        return elbo.reshape(mean.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, g_elbo):
+        mean2, var2, y2, rn = ctx.saved_tensors
+        g = _f32c(g_elbo).reshape(-1)
+        g_mean, g_var, g_noise, g_kl = elbo_backward_raw(mean2, var2, y2, rn, g, ctx.num_data)
+        shp = ctx.shapes
+        need = ctx.needs_input_grad
+        return (g_mean.reshape(shp[0]) if need[0] else None,
+                g_var.reshape(shp[1]) if need[1] else None,
+                None,
+                g_noise.reshape(shp[2]) if need[3] else None,
+                g_kl.reshape(shp[3]) if need[4] else None,
+                None)
+
+
+def variational_elbo(mean: Tensor, var: Tensor, y: Tensor, raw_noise: Tensor, kl: Tensor,
+                     num_data: float) -> Tensor:
+    """mean, var, y [..., L] -> elbo [...] (per window)."""
+    return _ElboFunction.apply(mean, var, y, raw_noise, kl, float(num_data))
+
+
+class _RsampleFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, var, seed, offset, stream_id):
+        _need_cuda(mean, var)
+        m = _f32c(mean).reshape(-1)
+        v = _f32c(var).reshape(-1)
+        out = torch.empty_like(m)
+        with torch.cuda.device(m.device):
+            rc = _cabi.lib().gpblur_rsample_forward(_ptr(m), _ptr(v), m.numel(), seed, offset, stream_id,
+                                                    _ptr(out), _stream())
+        _cabi.check(rc, "gpblur_rsample_forward")
+        ctx.save_for_backward(v)
+        ctx.rng = (seed, offset, stream_id)
+        ctx.shape = mean.shape
+        return out.reshape(mean.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (v,) = ctx.saved_tensors
+        seed, offset, stream_id = ctx.rng
+        gc = _f32c(g).reshape(-1)
+        gm = torch.empty_like(gc)
+        gv = torch.empty_like(gc)
+        with torch.cuda.device(v.device):
+            rc = _cabi.lib().gpblur_rsample_backward(_ptr(v), _ptr(gc), gc.numel(), seed, offset, stream_id,
+                                                     _ptr(gm), _ptr(gv), _stream())
+        _cabi.check(rc, "gpblur_rsample_backward")
+        return gm.reshape(ctx.shape), gv.reshape(ctx.shape), None, None, None
+
+
+def rsample(mean: Tensor, var: Tensor, seed: int, offset: int, stream_id: int = 0) -> Tensor:
+    """Normal(mean, sqrt(var)).rsample() with explicit Philox counters (between DeepGP layers)."""
+    return _RsampleFunction.apply(mean, var, int(seed), int(offset), int(stream_id))
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.library registration (torch.ops.gpblur.*): the same raw calls behind dispatcher-visible ops
+# ------------------------------------------------------------------------------------------------
+def _register_custom_ops():
+    try:
+        from torch.library import custom_op
+    except Exception:   # pragma: no cover
+        return
+
+    @custom_op("gpblur::svgp_fwd", mutates_args=(), device_types="cuda")
+    def svgp_fwd(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: Tensor, s: Tensor, w: Optional[Tensor],
+                 b: Tensor, seed: int, offset: int, stream_id: int, want_sample: bool,
+                 training: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+        mean, var, sample, kl, info, ws = svgp_forward_raw(x, Z, raw_ell, raw_os, m, s, w, b, seed, offset,
+                                                           stream_id, want_sample, training)
+        if sample is None:
+            sample = mean.new_empty(0)
+        return mean, var, sample, kl, info, ws
+
+    @custom_op("gpblur::svgp_bwd", mutates_args=(), device_types="cuda")
+    def svgp_bwd(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: Tensor, s: Tensor, w: Optional[Tensor],
+                 b: Tensor, g_mean: Optional[Tensor], g_var: Optional[Tensor], g_sample: Optional[Tensor],
+                 g_kl: Optional[Tensor], var: Tensor, seed: int, offset: int, stream_id: int,
+                 ws: Tensor) -> Tuple[Tensor, Tensor]:
+        dx, bucket = svgp_backward_raw(x, Z, raw_ell, raw_os, m, s, w, b, g_mean, g_var, g_sample, g_kl, var,
+                                       seed, offset, stream_id, ws, True)
+        return dx, bucket
+
+    @custom_op("gpblur::elbo_fwd", mutates_args=(), device_types="cuda")
+    def elbo_fwd(mean: Tensor, var: Tensor, y: Tensor, raw_noise: Tensor, kl: Tensor, num_data: float) -> Tensor:
+        return elbo_forward_raw(mean, var, y, raw_noise, kl, num_data)
+
+    @custom_op("gpblur::elbo_bwd", mutates_args=(), device_types="cuda")
+    def elbo_bwd(mean: Tensor, var: Tensor, y: Tensor, raw_noise: Tensor, g_elbo: Tensor,
+                 num_data: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        return elbo_backward_raw(mean, var, y, raw_noise, g_elbo, num_data)
+
+
+_register_custom_ops()

@@ -1,0 +1,139 @@
+/*
+ * gpblur.h - C ABI of the B200 (sm_100a) GP blur / corruption hot path.
+ *
+ * The reference (SepKfr/Fine_grained_Gaussian_Process_Forcasting) has no FFI of its own: the path sits
+ * behind Python classes that call gpytorch.  Each entry point below replaces the gpytorch call chain
+ * cited next to it; the Python package binds them with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - all tensor arguments are DEVICE pointers to contiguous fp32 unless stated; they are borrowed,
+ *     never freed, never reallocated;  `stream` is a cudaStream_t passed as void*.
+ *   - no entry point allocates device memory or synchronises; scratch comes from the caller as
+ *     (`ws`, `ws_bytes`), sized by gpblur_svgp_workspace_bytes().  The SAME workspace must be
+ *     handed to the matching backward call (it carries the saved whitened cross-covariances).
+ *   - return value: 0 on success, negative GPBLUR_E* code on argument / launch errors.  Numerical
+ *     failure of the Cholesky (non-PD Kzz) is reported asynchronously through the device int `info`
+ *     (0 = ok, k>0 = pivot k was not positive), like LAPACK potrf.
+ *   - thread-safe and re-entrant: no global mutable state except a per-device immutable
+ *     attribute cache.
+ */
+#ifndef GPBLUR_H_
+#define GPBLUR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPBLUR_OK 0
+#define GPBLUR_EINVAL -1     /* bad shape / null pointer */
+#define GPBLUR_EWORKSPACE -2 /* workspace too small */
+#define GPBLUR_ELAUNCH -3    /* CUDA launch failure (see gpblur_last_cuda_error) */
+#define GPBLUR_EUNSUPPORTED -4
+
+#define GPBLUR_MAX_D 128
+#define GPBLUR_MAX_M 1024
+
+/* Parameters of one whitened sparse variational GP layer.
+ * Replaces the parameter set created by ToyDeepGPHiddenLayer.__init__
+ * (/root/reference/denoising_model/DeepGP.py:15-49) for output_dims=None. */
+typedef struct gpblur_svgp_params {
+  const float* inducing_points;    /* [M, D]   VariationalStrategy.inducing_points        */
+  const float* raw_lengthscale;    /* [D]      covar_module.base_kernel.raw_lengthscale   */
+  const float* raw_outputscale;    /* [1]      covar_module.raw_outputscale               */
+  const float* variational_mean;   /* [M]      _variational_distribution.variational_mean */
+  const float* variational_stddev; /* [M]      _variational_distribution._variational_stddev */
+  const float* mean_weights;       /* [D] LinearMean.weights, or NULL for ConstantMean    */
+  const float* mean_bias;          /* [1] LinearMean.bias / ConstantMean constant         */
+} gpblur_svgp_params;
+
+/* Number of floats in the flat parameter-gradient bucket written by gpblur_svgp_backward:
+ *   [ dZ (M*D) | d raw_lengthscale (D) | d raw_outputscale (1) | d variational_mean (M) |
+ *     d variational_stddev (M) | d mean_weights (D) | d mean_bias (1) ]
+ * This bucket is what data-parallel training all-reduces. */
+size_t gpblur_svgp_grad_bucket_floats(int D, int M);
+
+/* Scratch bytes for N input points.  `training` != 0 reserves room for the saved whitened
+ * cross-covariance A [N, Mp] and the backward intermediates. */
+size_t gpblur_svgp_workspace_bytes(long long N, int D, int M, int training);
+
+/* Whitened SVGP predictive.
+ * Replaces DeepGPp.forward / ToyDeepGPHiddenLayer.__call__ -> gpytorch
+ * VariationalStrategy.forward (/root/reference/denoising_model/DeepGP.py:56-73, 90-92):
+ *   Kzz build + jitter, fp64 blocked Cholesky, explicit whitening, predictive mean / variance,
+ *   optional fused Philox reparameterised sample, KL(q(u)||p(u)).
+ *   x [N, D] -> mean [N], var [N], sample [N] (nullable), kl [1], info [1].
+ * sample_n = mean_n + sqrt(var_n) * eps_n, eps_n = BoxMuller(Philox4x32-10(counter = (offset + n,
+ * stream_id), key = seed)).  With training != 0 the workspace keeps what the backward needs. */
+int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
+                        float* mean, float* var, float* sample, uint64_t seed, uint64_t offset,
+                        uint32_t stream_id, float* kl, int* info, int training, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* Backward of gpblur_svgp_forward (replaces torch autograd through gpytorch, incl.
+ * LinalgCholeskyExBackward0 / LinalgSolveTriangularBackward0).
+ * Upstream gradients g_mean, g_var, g_sample [N] (each nullable) and g_kl [1] (nullable);
+ * `var` is the forward output (needed for the variance clamp and the sample path).
+ * Writes dx [N, D] (nullable) and the flat bucket described above. */
+int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
+                         const float* g_mean, const float* g_var, const float* g_sample,
+                         const float* g_kl, const float* var, uint64_t seed, uint64_t offset,
+                         uint32_t stream_id, float* dx, float* grad_bucket, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* Expected log-likelihood part of the ELBO.
+ * Replaces DeepApproximateMLL(VariationalELBO(likelihood, model, num_data))(dist, y) built at
+ * /root/reference/forecast_denoising.py:87-89 (GaussianLikelihood.expected_log_prob, sum over the
+ * event dim / L, minus KL / num_data):
+ *   elbo[b] = (1/L) sum_l -1/2 [ ((y-mean)^2 + var)/noise + log noise + log 2pi ] - kl / num_data
+ * mean, var, y [B, L]; raw_noise [1]; kl [1] -> elbo [B]. */
+int gpblur_elbo_forward(const float* mean, const float* var, const float* y, const float* raw_noise,
+                        const float* kl, float num_data, long long B, int L, float* elbo,
+                        void* stream);
+
+/* Backward of gpblur_elbo_forward: g_elbo [B] -> g_mean, g_var [B, L], g_raw_noise [1], g_kl [1].
+ * `scratch` must hold at least B floats. */
+int gpblur_elbo_backward(const float* mean, const float* var, const float* y, const float* raw_noise,
+                         const float* g_elbo, float num_data, long long B, int L, float* g_mean,
+                         float* g_var, float* g_raw_noise, float* g_kl, float* scratch,
+                         void* stream);
+
+/* Raw Philox4x32-10 words for elements offset .. offset+n-1 (bit-exactness probe): out [n, 4]. */
+int gpblur_philox_bits(uint64_t seed, uint64_t offset, uint32_t stream_id, long long n,
+                       uint32_t* out, void* stream);
+/* Standard normals with the sampler's counter layout: out [n]. */
+int gpblur_philox_normal(uint64_t seed, uint64_t offset, uint32_t stream_id, long long n,
+                         float* out, void* stream);
+
+/* Elementwise reparameterised sample used between DeepGP layers
+ * (gpytorch DeepGPLayer: Normal(mean, var.sqrt()).rsample()): out = mean + sqrt(var) * eps. */
+int gpblur_rsample_forward(const float* mean, const float* var, long long n, uint64_t seed,
+                           uint64_t offset, uint32_t stream_id, float* out, void* stream);
+int gpblur_rsample_backward(const float* var, const float* g_out, long long n, uint64_t seed,
+                            uint64_t offset, uint32_t stream_id, float* g_mean, float* g_var,
+                            void* stream);
+
+/* Dense ScaleKernel(RBF) covariance for the exact-GP model
+ * (/root/reference/denoising_model/GPModel.py:10-13): x1 [n1, D], x2 [n2, D], one lengthscale per
+ * dimension (pass the same value D times for the isotropic kernel) -> out [n1, n2]. */
+int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long long n2, int D,
+                          const float* raw_lengthscale, int ard, const float* raw_outputscale,
+                          float* out, void* stream);
+
+/* Debug / test probes into the workspace of the last forward on (ws): copies device-to-device.
+ * which: 0 = L (fp64 [Mp,Mp]), 1 = Linv (fp64 [Mp,Mp]), 2 = Kzz+jitter (fp64 [Mp,Mp]),
+ *        3 = A (fp32 [N,Mp]).  Returns the padded inducing count Mp via *mp. */
+int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
+                       size_t out_bytes, int* mp, void* stream);
+
+/* Count of kernel launches issued by this library in this process (for bench.py's gpu_launches). */
+unsigned long long gpblur_launch_count(void);
+const char* gpblur_last_cuda_error(void);
+const char* gpblur_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPBLUR_H_ */
