@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] -= acc[i];
       }
     }
-    if (ntr > 0) grid.sync();
+    grid.sync();   // also publishes the last diagonal block before phase 3
   }
 
   // ---------------- phase 3a: inverses of the diagonal blocks ----------------

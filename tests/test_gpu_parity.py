@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): <= 1e-5 relative on mean / variance / ELBO in FP32, Philox
+words bit-exact.  "relative" is max|cuda - oracle| / max|oracle| against the float64 closed-form oracle.
+Gradients (not given a number by the north star) are held to 2e-4 of the same norm; the measured
+values are far below.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 1e-5
+TOL_GRAD = 2e-4
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-300)).item()
+
+
+def to_dev(p, dev):
+    return {k: v.to(dev) for k, v in p.items()}
+
+
+def cuda_predict(ops, pd, x, **kw):
+    return ops.svgp_predict(x, pd["inducing_points"], pd["raw_lengthscale"], pd["raw_outputscale"],
+                            pd["variational_mean"], pd["variational_stddev"], pd["weights"], pd["bias"], **kw)
+
+
+# (B, L, D, M): BASELINE configs at oracle-sized batches + ragged / edge shapes
+SHAPES = [
+    (256, 24, 64, 32),     # C1 as quoted
+    (16, 24, 64, 128),     # C3 shape, small batch
+    (8, 192, 32, 256),     # C2 encoder-side call, reference default M
+    (8, 24, 16, 256),      # reference d_model=16
+    (4, 24, 64, 512),      # C5 interior
+    (2, 24, 64, 1024),     # C5 end
+    (3, 7, 5, 3),          # ragged everything: D % 4 != 0, M < 32, N < tile
+    (1, 1, 1, 1),          # degenerate
+    (5, 13, 48, 100),      # D padded 48 -> 64, M padded 100 -> 128
+    (700, 24, 64, 64),     # enough points for the 128-point tiles, M = 64 path
+]
+
+
+def test_philox_bits_bit_exact(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    for seed, offset, stream in [(1234, 0, 0), (0xDEADBEEFCAFEF00D, (1 << 40) + 12345, 7), (0, (1 << 32) - 3, 1)]:
+        n = 4099
+        got = ops.philox_bits(seed, offset, n, stream).cpu().numpy().view(np.uint32)
+        want = O.philox_bits(seed, offset, n, stream)
+        assert np.array_equal(got, want)
+
+
+def test_philox_normal(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    n = 1 << 16
+    got = ops.philox_normal(1234, 77, n, 3).cpu().numpy()
+    want = O.philox_normal(1234, 77, n, 3)
+    assert np.max(np.abs(got - want)) <= 2e-6 * max(1.0, np.max(np.abs(want)))
+    assert abs(got.mean()) < 0.02 and abs(got.std() - 1) < 0.02
+
+
+@pytest.mark.parametrize("B,L,D,M", SHAPES)
+def test_mm_stage_and_forward(cuda, B, L, D, M):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    p32 = O.init_params_exercise(D, M, seed=11)
+    x32, _, _, _ = O.make_inputs(B, L, D, seed=12)
+    p64 = O.clone_params(p32, torch.float64)
+    mean_o, var_o = O.svgp_predict_closed_form(p64, x32.double())
+    pd = to_dev(p32, cuda)
+    xd = x32.to(cuda)
+    # raw call so that the workspace can be probed
+    mean, var, sample, kl, info, ws = ops.svgp_forward_raw(
+        xd.reshape(-1, D), pd["inducing_points"], pd["raw_lengthscale"].reshape(-1), pd["raw_outputscale"].reshape(1),
+        pd["variational_mean"], pd["variational_stddev"], pd["weights"].reshape(-1), pd["bias"], 1234, 5, 0, True, True)
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    # M x M stage
+    ell = O.softplus(p64["raw_lengthscale"]).reshape(D)
+    os_ = O.softplus(p64["raw_outputscale"])
+    Kzz = O.rbf_scale_direct(p64["inducing_points"], p64["inducing_points"], ell, os_) + O.JITTER * torch.eye(M, dtype=torch.float64)
+    Lc = torch.linalg.cholesky(Kzz)
+    Linv = torch.linalg.solve_triangular(Lc, torch.eye(M, dtype=torch.float64), upper=False)
+    Kd = ops.debug_fetch(2, B * L, D, M, ws).cpu()[:M, :M]
+    Ld = ops.debug_fetch(0, B * L, D, M, ws).cpu()[:M, :M]
+    Lid = ops.debug_fetch(1, B * L, D, M, ws).cpu()[:M, :M]
+    assert rel(Kd, Kzz) < 1e-6          # fp32 inputs, fp64 arithmetic (float lengthscale rounding)
+    assert rel(torch.tril(Ld), Lc) < 1e-6
+    assert rel(torch.tril(Lid), Linv) < 1e-5
+    # predictive
+    e_mean, e_var = rel(mean.reshape(B, L), mean_o), rel(var.reshape(B, L), var_o)
+    print(f"fwd B={B} L={L} D={D} M={M}: mean {e_mean:.2e} var {e_var:.2e}")
+    assert e_mean < TOL_FWD and e_var < TOL_FWD
+    assert abs(kl.item() - O.kl_meanfield(p64).item()) <= 1e-5 * max(1.0, abs(O.kl_meanfield(p64).item()))
+    # fused sample = mean + sqrt(var) * eps with the documented counters
+    eps = torch.from_numpy(O.philox_normal(1234, 5, B * L, 0))
+    want = mean.cpu() + var.cpu().sqrt() * eps
+    assert (sample.cpu() - want).abs().max() <= 1e-5 * (1 + want.abs().max())
+
+
+@pytest.mark.parametrize("B,L,D,M", SHAPES)
+def test_backward(cuda, B, L, D, M):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    p32 = O.init_params_exercise(D, M, seed=21)
+    x32, y32, gm32, gv32 = O.make_inputs(B, L, D, seed=22)
+    gs32 = torch.randn(B, L, generator=torch.Generator().manual_seed(23))
+    gkl = 0.37
+    seed, offset, stream = 99, 1000, 2
+    # oracle: float64 autograd through the closed form
+    p64 = O.clone_params(p32, torch.float64, requires_grad=True)
+    x64 = x32.double().requires_grad_(True)
+    mo, vo = O.svgp_predict_closed_form(p64, x64)
+    eps = torch.from_numpy(O.philox_normal(seed, offset, B * L, stream)).double().reshape(B, L)
+    so = O.rsample(mo, vo, eps)
+    loss = (gm32.double() * mo).sum() + (gv32.double() * vo).sum() + (gs32.double() * so).sum() + gkl * O.kl_meanfield(p64)
+    loss.backward()
+    # cuda
+    pd = {k: v.to(cuda).requires_grad_(True) for k, v in p32.items()}
+    xd = x32.to(cuda).requires_grad_(True)
+    mean, var, sample, kl, info = cuda_predict(ops, pd, xd, seed=seed, offset=offset, stream_id=stream, want_sample=True)
+    lc = (gm32.to(cuda) * mean).sum() + (gv32.to(cuda) * var).sum() + (gs32.to(cuda) * sample).sum() + gkl * kl
+    lc.backward()
+    torch.cuda.synchronize()
+    errs = {"dx": rel(xd.grad, x64.grad)}
+    for k in ["inducing_points", "raw_lengthscale", "raw_outputscale", "variational_mean", "variational_stddev", "weights", "bias"]:
+        errs[k] = rel(pd[k].grad, p64[k].grad)
+    print(f"bwd B={B} L={L} D={D} M={M}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < TOL_GRAD, (k, v)
+
+
+def test_backward_without_sample_and_partial_upstream(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L, D, M = 6, 24, 32, 64
+    p32 = O.init_params_exercise(D, M, seed=31)
+    x32, _, gm32, _ = O.make_inputs(B, L, D, seed=32)
+    p64 = O.clone_params(p32, torch.float64, requires_grad=True)
+    x64 = x32.double().requires_grad_(True)
+    mo, _ = O.svgp_predict_closed_form(p64, x64)
+    (gm32.double() * mo).sum().backward()
+    pd = {k: v.to(cuda).requires_grad_(True) for k, v in p32.items()}
+    xd = x32.to(cuda).requires_grad_(True)
+    mean, var, sample, kl, info = cuda_predict(ops, pd, xd)
+    assert sample is None
+    (gm32.to(cuda) * mean).sum().backward()
+    assert rel(xd.grad, x64.grad) < TOL_GRAD
+    assert rel(pd["inducing_points"].grad, p64["inducing_points"].grad) < TOL_GRAD
+    assert rel(pd["variational_mean"].grad, p64["variational_mean"].grad) < TOL_GRAD
+    assert pd["variational_stddev"].grad.abs().max().item() == 0.0
+
+
+def test_elbo_forward_backward(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L = 37, 24
+    g = torch.Generator().manual_seed(5)
+    mean = torch.randn(B, L, generator=g)
+    var = torch.rand(B, L, generator=g) + 0.1
+    y = torch.randn(B, L, generator=g)
+    raw_noise = torch.tensor([0.3])
+    kl = torch.tensor(2.5)
+    ge = torch.randn(B, generator=g)
+    t64 = [t.double().requires_grad_(True) for t in (mean, var, raw_noise, kl)]
+    noise = O.softplus(t64[2]).reshape(()) + O.NOISE_LOWER
+    eo = O.elbo_per_window(t64[0], t64[1], y.double(), noise, t64[3], 64.0)
+    (eo * ge.double()).sum().backward()
+    td = [t.to(cuda).requires_grad_(True) for t in (mean, var, raw_noise, kl)]
+    ec = ops.variational_elbo(td[0], td[1], y.to(cuda), td[2], td[3], 64.0)
+    (ec * ge.to(cuda)).sum().backward()
+    assert rel(ec, eo) < TOL_FWD
+    for a, b in zip(td, t64):
+        assert rel(a.grad, b.grad) < 1e-5
+
+
+def test_reference_regime_underflow(cuda):
+    """R-reference regime: parameters exactly as DeepGPp(D, seed) initialises them, LayerNorm-ed inputs.
+    K(x, Z) underflows, so the predictive is the linear mean and var = outputscale + jitter."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L, D, M = 32, 24, 64, 256
+    p32 = O.init_params_reference(D, seed=1234, M=M)
+    x32, _, _, _ = O.make_inputs(B, L, D, seed=3, layernorm=True)
+    pd = to_dev(p32, cuda)
+    mean, var, _, kl, info = cuda_predict(ops, pd, x32.to(cuda))
+    want_mean = (x32.double() @ p32["weights"].double()).squeeze(-1) + p32["bias"].double()
+    assert rel(mean, want_mean) < TOL_FWD
+    assert torch.allclose(var.cpu(), torch.full((B, L), math.log(2.0) + 1e-4), rtol=1e-6, atol=0)
+    assert kl.item() == 0.0 and int(info.item()) == 0
+    mo, vo = O.svgp_predict_reference_order(p32, x32)
+    assert rel(mean, mo) < TOL_FWD and rel(var, vo) < TOL_FWD
+
+
+def test_empty_batch(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    D, M = 16, 32
+    p32 = O.init_params_exercise(D, M, seed=1)
+    pd = {k: v.to(cuda).requires_grad_(True) for k, v in p32.items()}
+    x = torch.empty(0, 24, D, device=cuda, requires_grad=True)
+    mean, var, sample, kl, info = cuda_predict(ops, pd, x)
+    assert mean.shape == (0, 24)
+    (kl * 2.0).backward()
+    p64 = O.clone_params(p32, torch.float64, requires_grad=True)
+    (O.kl_meanfield(p64) * 2.0).backward()
+    assert rel(pd["variational_stddev"].grad, p64["variational_stddev"].grad) < 1e-5
+    assert pd["inducing_points"].grad.abs().max().item() == 0.0
+
+
+def test_non_psd_reports_info(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    D, M = 8, 40
+    p32 = O.init_params_exercise(D, M, seed=1)
+    p32["inducing_points"][5] = float("nan")
+    pd = to_dev(p32, cuda)
+    x = torch.randn(4, 3, D, device=cuda)
+    _, _, _, _, info = cuda_predict(ops, pd, x)
+    assert int(info.item()) != 0
+
+
+def test_rbf_covariance(cuda):
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x1 = torch.randn(37, 5, generator=g)
+    x2 = torch.randn(21, 5, generator=g)
+    raw_ell = torch.tensor([0.4])
+    raw_os = torch.tensor([-0.2])
+    want = O.rbf_scale_direct(x1.double(), x2.double(), O.softplus(raw_ell.double()), O.softplus(raw_os.double()))
+    got = ops.rbf_covariance(x1.to(cuda), x2.to(cuda), raw_ell.to(cuda), raw_os.to(cuda), ard=False)
+    assert rel(got, want) < 1e-5
