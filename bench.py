@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""GP-blur fwd+bwd throughput (windows/s) on B200 - the metric of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic forecast windows per GPU:
+whitened-SVGP predictive (mean, variance, fused Philox sample) of every GP call of the workload, the
+ELBO on the decoder-side call, and the full hand-written backward (dX + every GP parameter gradient);
+for N > 1 the flat GP-gradient bucket is all-reduced over NCCL inside the step.
+
+Workloads (BASELINE.json `configs`; per-GPU batch is fixed => weak scaling):
+  c2      configs[1]: the two GP-blur calls of the traffic-shape train step, enc [256,192,64] and
+          dec [256,24,64], M=256 (reference default), ELBO on the decoder call.   <- default
+          (the forecaster / denoiser around them are outside the hot path)
+  c1      configs[0]: B=256, L=24, D=64, M=32
+  c3      configs[2]: B=1024, L=24, D=64, M=128
+  c5_mM   configs[4]: B=8192, L=24, D=64, M in {64,128,256,512,1024}
+
+The JSON line carries `value` (inputs resident in HBM), `e2e` (host buffers, H2D/D2H inside the timed
+region, through the public module API), `roofline` of the dominant kernel (per-stage CUDA-event times
+measured live by the library's profile hooks) and `cpu_baseline` (the oracle's reference-order
+restatement of the gpytorch path on the host cores: gpytorch itself is not installable here).
+`--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "c1": dict(B=256, calls=[24], D=64, M=32, desc="configs[0]: GPModel blur B=256 L=24 D=64 M=32"),
+    "c2": dict(B=256, calls=[192, 24], D=64, M=256,
+               desc="configs[1] GP-blur calls of the traffic-shape step: enc [256,192,64] + dec [256,24,64], M=256"),
+    "c3": dict(B=1024, calls=[24], D=64, M=128, desc="configs[2]: electricity shape B=1024 L=24 D=64 M=128"),
+}
+for _m in (64, 128, 256, 512, 1024):
+    WORKLOADS[f"c5_m{_m}"] = dict(B=8192, calls=[24], D=64, M=_m,
+                                  desc=f"configs[4]: inducing sweep point B=8192 L=24 D=64 M={_m}")
+DEFAULT_WORKLOAD = "c2"
+METRIC = "gp_blur_fwd_bwd_windows_per_sec"
+UNIT = "windows/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithmic work model
+# --------------------------------------------------------------------------------------------------
+def stage_work(stage: str, N: int, D: int, M: int):
+    """(algorithmic bytes, algorithmic flops) of one launch of `stage` over N points."""
+    if stage == "point_fwd":
+        return N * (4 * D + 12), N * (2 * M * D + M * M)
+    if stage == "point_bwd":
+        return N * (8 * D + 16), N * (4 * M * D + M * M)
+    if stage == "gram":
+        return 0, N * M * M
+    if stage == "wx":
+        return 0, 2 * N * M * D
+    if stage == "mm_fwd":
+        return 4 * M * D, 2 * M * M * D + M ** 3 // 3 + M ** 3 // 3
+    if stage == "mm_bwd":
+        return 4 * M * D, 4 * M ** 3
+    return 0, 0
+
+
+def bytes_per_window(L, D):
+    return 12 * L * D + 32 * L + 4
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = sorted(float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit())
+            mx = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = set()
+            for r in rows:
+                for i, nm in enumerate(names):
+                    if len(r) > 3 + i and r[3 + i].strip().lower() == "active":
+                        reasons.add(nm)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+            if mx:
+                out["sm_max_mhz"] = max(mx)
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(rows)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm on the host cores (oracle restatement; gpytorch is absent)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(wl, B_cpu, seed=1234):
+    from oracle import gp_oracle as O
+    D, M = wl["D"], wl["M"]
+    p = O.clone_params(O.init_params_exercise(D, M, seed), requires_grad=True)
+    calls = []
+    for i, L in enumerate(wl["calls"]):
+        x, y, gm, gv = O.make_inputs(B_cpu, L, D, seed + 1 + i)
+        calls.append((x.requires_grad_(True), y, gm, gv))
+
+    def step():
+        for q in p.values():
+            q.grad = None
+        loss = 0.0
+        for i, (x, y, gm, gv) in enumerate(calls):
+            x.grad = None
+            mean, var = O.svgp_predict_reference_order(p, x)
+            loss = loss + (gm * mean).sum()
+            if i == len(calls) - 1:
+                e = O.elbo_per_window(mean, var, y, O.noise_variance(p), O.kl_meanfield(p), float(D))
+                loss = loss - e.mean()
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
+def time_cpu_reference(wl, steps, warmup, budget_s=25.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    # bounded sample: pick B_cpu so that one step costs a few seconds at most
+    N_per_window = sum(wl["calls"])
+    M = wl["M"]
+    cost = N_per_window * (M + max(wl["calls"])) ** 2 / 1e9 + M ** 3 / 1e9 * 4   # rough Gflop-ish per window
+    B_cpu = int(max(2, min(wl["B"], 6.0 / max(cost, 1e-3))))
+    B_cpu = int(os.environ.get("GPBLUR_CPU_SAMPLE_B", B_cpu))
+    step = cpu_reference_step_fn(wl, B_cpu)
+    for _ in range(max(1, warmup)):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return dict(value=B_cpu / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{done} steps of B={B_cpu} windows (of the workload's B={wl['B']}), calls L={wl['calls']}, "
+                       f"oracle reference-order restatement of the gpytorch path (fp32 kernels, fp64 batched "
+                       f"Cholesky/solve, autograd backward), torch {torch.__version__} CPU"), dt
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    cb, dt = time_cpu_reference(wl, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "desc": wl["desc"], "B": wl["B"], "L": wl["calls"], "D": wl["D"], "M": wl["M"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def make_model(wl, device, seed=1234):
+    import math
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    gpcompat.num_likelihood_samples._set_value(1)       # train.py:20
+    model = DeepGPp(wl["D"], seed, num_inducing=wl["M"]).to(device)
+    # "R-exercise" parameter regime of SURVEY 8(d): lengthscales ~ sqrt(D) so K(x, Z) is O(0.1..1)
+    Dd, Mm = wl["D"], wl["M"]
+    g = torch.Generator().manual_seed(seed)
+    ell = math.sqrt(Dd) * (0.75 + 0.5 * torch.rand(1, Dd, generator=g))
+    p = {"inducing_points": torch.randn(Mm, Dd, generator=g),
+         "raw_lengthscale": torch.log(torch.expm1(ell)),
+         "variational_mean": 0.5 * torch.randn(Mm, generator=g),
+         "variational_stddev": 0.5 + torch.rand(Mm, generator=g),
+         "weights": torch.randn(Dd, 1, generator=g) / math.sqrt(Dd),
+         "bias": torch.randn(1, generator=g)}
+    hl = model.hidden_layer
+    with torch.no_grad():
+        hl.variational_strategy.inducing_points.copy_(p["inducing_points"])
+        hl.covar_module.base_kernel.raw_lengthscale.copy_(p["raw_lengthscale"])
+        hl.variational_strategy._variational_distribution.variational_mean.copy_(p["variational_mean"])
+        hl.variational_strategy._variational_distribution._variational_stddev.copy_(p["variational_stddev"])
+        hl.mean_module.weights.copy_(p["weights"])
+        hl.mean_module.bias.copy_(p["bias"])
+        hl.variational_strategy.variational_params_initialized.fill_(1)
+    return model
+
+
+def run_ours(args, wl, name):
+    from fine_grained_gaussian_process_forcasting_b200 import _cabi
+    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the GP blur path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    _cabi.lib()
+
+    B, D, M, calls = wl["B"], wl["D"], wl["M"], wl["calls"]
+    model = make_model(wl, device)
+    model.train()
+    bucket = FlatGradBucket(gp_parameters(model))
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    nbuf = 3   # rotate inputs; an L2 flush is also issued between timed steps
+    xs = [[torch.randn(B, L, D, device=device, generator=g) for L in calls] for _ in range(nbuf)]
+    ys = [torch.randn(1, B, calls[-1], device=device, generator=g) for _ in range(nbuf)]
+    gms = [torch.randn(1, B, L, device=device, generator=g) for L in calls]
+    gss = [torch.randn(1, B, L, device=device, generator=g) for L in calls]
+    g_elbo = torch.full((1, B), -1.0 / B, device=device)
+    xh = [[x.cpu().pin_memory() for x in xs[0]]]
+    yh = ys[0].cpu().pin_memory()
+    elbo_h = torch.empty(1, B).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES // 4, device=device)
+    hl = model.hidden_layer
+
+    def step(i, xin, yin):
+        bucket.zero()
+        outs, grads = [], []
+        elbo = None
+        for c, L in enumerate(calls):
+            x = xin[c].detach().requires_grad_(True)      # fresh leaf: dX flows back to the forecaster
+            hl._rng_offset = (i * world + rank) * B * L       # global window index -> Philox counter
+            last = c == len(calls) - 1
+            out = model.blur(x, yin if last else None, num_data=D)
+            outs += [out.mean, out.sample]
+            grads += [gms[c], gss[c]]
+            if last:
+                elbo = out.elbo
+                outs.append(elbo)
+                grads.append(g_elbo)
+        torch.autograd.backward(outs, grads)
+        if world > 1:
+            bucket.all_reduce(average=True)
+        return elbo
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for i in range(max(3, args.warmup)):
+        step(i, xs[i % nbuf], ys[i % nbuf])
+    sync_all()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the events)
+        evs[i][0].record()
+        step(i, xs[i % nbuf], ys[i % nbuf])
+        evs[i][1].record()
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _cabi.launch_count() - launches0
+    ms_dev = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_dev], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- timed region 2: end to end through the module API with host buffers ----
+    xdev = [torch.empty_like(x) for x in xs[0]]
+    ydev = torch.empty_like(ys[0])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        for c in range(len(calls)):
+            xdev[c].copy_(xh[0][c], non_blocking=True)
+        ydev.copy_(yh, non_blocking=True)
+        elbo = step(i, xdev, ydev)
+        elbo_h.copy_(elbo.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the step's result on the host
+    e1.record()
+    sync_all()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t2.item()) * 1e-3)
+    h2d = sum(x.numel() for x in xh[0]) * 4 + yh.numel() * 4
+    d2h = elbo_h.numel() * 4
+
+    # ---- per-stage device times (library profile hooks: CUDA events on the launching stream) ----
+    stage_ms = {}
+    if rank == 0 or True:
+        _cabi.profile_enable(True)
+        nprof = max(3, min(args.steps, 10))
+        for i in range(nprof):
+            flush.zero_()
+            step(i, xs[i % nbuf], ys[i % nbuf])
+        torch.cuda.synchronize()
+        prof = _cabi.profile_collect()
+        _cabi.profile_enable(False)
+        stage_ms = {k: (ms / nprof, cnt / nprof) for k, (ms, cnt) in prof.items() if cnt}
+    sync_all()
+
+    if rank == 0:
+        peaks = load_peaks()
+        N_total = B * sum(calls)
+        # dominant kernel and its roofline
+        dom = max(stage_ms.items(), key=lambda kv: kv[1][0])[0] if stage_ms else None
+        roof = None
+        if dom is not None:
+            ms_dom, launches_dom = stage_ms[dom]
+            per_launch_s = ms_dom * 1e-3 / max(launches_dom, 1)
+            n_per_launch = N_total / max(launches_dom, 1)
+            by, fl = stage_work(dom, int(n_per_launch), D, M)
+            tf32_peak = peaks["bf16_tflops"] / 2.0
+            intensity = fl / max(by, 1)
+            if by > 0 and intensity < tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9):
+                roof = {"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+            else:
+                roof = {"bound": "tensor", "achieved": fl / per_launch_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "peak_note": "TF32 dense rate taken as 1/2 of the measured cuBLAS bf16 burst peak; the "
+                                     "kernel itself still runs FP32 FFMA (round 1), FFMA peak ~74 TFLOP/s"}
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            roof["traffic"] = None
+            roof["kernel"] = dom
+            roof["kernel_ms_per_launch"] = per_launch_s * 1e3
+            roof["peak_source"] = peaks["source"]
+            roof["hbm_frac_whole_step"] = (B * sum(bytes_per_window(L, D) for L in calls) / (ms_per_step * 1e-3) / 1e9
+                                           / peaks["hbm_gbs"])
+        cb, _ = time_cpu_reference(wl, 3, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "desc": wl["desc"], "B_per_gpu": B, "L": calls, "D": D, "M": M,
+                       "parallelism": f"dp{world}", "l2": f"flush ({L2_FLUSH_BYTES >> 20} MiB write) between timed steps "
+                       "+ 3 rotating input sets", "timing": "per-step CUDA events, max over ranks",
+                       "regime": "R-exercise (SURVEY 8d)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cb,
+            "stage_ms_per_step": {k: round(v[0], 5) for k, v in stage_ms.items()},
+            "wall_ms_per_step": t_wall * 1e3 / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=os.environ.get("GPBLUR_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

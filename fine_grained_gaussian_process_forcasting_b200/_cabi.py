@@ -68,6 +68,8 @@ SIGNATURES = {
     "gpblur_debug_fetch": (C.c_int, [
         C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
         C.POINTER(C.c_int), C.c_void_p]),
+    "gpblur_profile_enable": (C.c_int, [C.c_int]),
+    "gpblur_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.c_int]),
     "gpblur_launch_count": (C.c_ulonglong, []),
     "gpblur_last_cuda_error": (C.c_char_p, []),
     "gpblur_version": (C.c_char_p, []),
@@ -107,6 +109,22 @@ def check(rc: int, what: str) -> None:
     if rc == -3:
         detail = " : " + (lib().gpblur_last_cuda_error() or b"").decode()
     raise RuntimeError(f"{what} failed with {ERRORS.get(rc, rc)}{detail}")
+
+
+STAGES = ("mm_fwd", "point_fwd", "point_bwd", "gram", "wx", "mm_bwd", "elbo_fwd", "elbo_bwd", "other")
+
+
+def profile_enable(on: bool) -> None:
+    lib().gpblur_profile_enable(int(on))
+
+
+def profile_collect() -> dict:
+    """{stage: (total_ms, launches)} since the last collect (synchronises on the recorded events)."""
+    n = len(STAGES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_ulonglong * n)()
+    check(lib().gpblur_profile_collect(ms, cnt, n), "gpblur_profile_collect")
+    return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(STAGES)}
 
 
 def launch_count() -> int:

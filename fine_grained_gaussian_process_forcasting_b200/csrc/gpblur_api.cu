@@ -1,6 +1,8 @@
 // extern "C" entry points (see include/gpblur.h) + the small elementwise kernels: ELBO, Philox probes,
 // reparameterised sample, dense RBF covariance.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 
@@ -10,6 +12,28 @@ namespace gpblur {
 
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_err[256] = "";
+
+// ---- optional per-stage timing (bench.py roofline): events are recorded on the launching stream ----
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof_recs;
+
+ProfScope::ProfScope(int stage_, cudaStream_t st_) : stage(stage_), st(st_), rec(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec{stage, nullptr, nullptr};
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(r);
+}
 
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
@@ -256,6 +280,7 @@ int gpblur_elbo_forward(const float* mean, const float* var, const float* y, con
   if (B < 0 || L < 1 || !raw_noise || !kl) return GPBLUR_EINVAL;
   if (B == 0) return GPBLUR_OK;
   if (!mean || !var || !y || !elbo) return GPBLUR_EINVAL;
+  ProfScope ps(ST_ELBO_FWD, (cudaStream_t)stream);
   elbo_fwd_kernel<<<ew_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(mean, var, y, raw_noise, kl, num_data, B, L,
                                                                    elbo);
   note_launch();
@@ -267,6 +292,7 @@ int gpblur_elbo_backward(const float* mean, const float* var, const float* y, co
                          float* g_raw_noise, float* g_kl, float* scratch, void* stream) {
   if (B < 0 || L < 1 || !raw_noise) return GPBLUR_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(ST_ELBO_BWD, st);
   if (B > 0) {
     if (!mean || !var || !y || !g_elbo || !g_mean || !g_var || !scratch) return GPBLUR_EINVAL;
     elbo_bwd_kernel<<<ew_grid(B, 8), 256, 0, st>>>(mean, var, y, raw_noise, g_elbo, B, L, g_mean, g_var,
@@ -346,6 +372,27 @@ int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, voi
   if (out_bytes < bytes) return GPBLUR_EWORKSPACE;
   cudaMemcpyAsync(out, ws_cptr<char>(ws, off), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return check_launch("debug_fetch");
+}
+
+int gpblur_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return GPBLUR_OK;
+}
+
+int gpblur_profile_collect(double* ms, unsigned long long* counts, int n) {
+  if (!ms || !counts || n < ST_COUNT) return GPBLUR_EINVAL;
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (ProfRec* r : g_prof_recs) {
+    cudaEventSynchronize(r->b);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->a, r->b) == cudaSuccess) { ms[r->stage] += (double)t; counts[r->stage] += 1; }
+    cudaEventDestroy(r->a);
+    cudaEventDestroy(r->b);
+    delete r;
+  }
+  g_prof_recs.clear();
+  return GPBLUR_OK;
 }
 
 unsigned long long gpblur_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -177,6 +177,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // host-side launch bookkeeping (defined in gpblur_api.cu)
+enum Stage { ST_MM_FWD = 0, ST_POINT_FWD, ST_POINT_BWD, ST_GRAM, ST_WX, ST_MM_BWD, ST_ELBO_FWD, ST_ELBO_BWD,
+             ST_OTHER, ST_COUNT };
+// RAII: when profiling is enabled, brackets the launches issued in its scope with CUDA events on `st`
+struct ProfScope {
+  int stage; cudaStream_t st; void* rec;
+  ProfScope(int stage, cudaStream_t st);
+  ~ProfScope();
+};
 void note_launch(int n = 1);
 int check_launch(const char* what);
 int num_sms();

@@ -651,6 +651,7 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
   MmFwdArgs args{p, L, ws, kl, info};
   void* kargs[] = {&args};
+  ProfScope ps(ST_MM_FWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_forward_kernel, dim3(grid), dim3(kThreads),
                                               kargs, smem, st);
   note_launch();
@@ -677,6 +678,7 @@ int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, c
   const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
   MmBwdArgs args{p, L, ws, g_kl, grad_bucket, nvec_used};
   void* kargs[] = {&args};
+  ProfScope ps(ST_MM_BWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),
                                               kargs, smem, st);
   note_launch();

@@ -372,6 +372,7 @@ int launch_bwd_cfg(const PointBwdArgs& a0, cudaStream_t st) {
   }
   a.ntiles = (int)((a.L.N + Cfg::TN - 1) / Cfg::TN);
   const int grid = bwd_persistent_grid(a.L, Cfg::TN);
+  ProfScope ps(ST_POINT_BWD, st);
   point_bwd_kernel<Cfg, DP><<<grid, kThreads, smem, st>>>(a);
   note_launch();
   return check_launch("point_bwd");

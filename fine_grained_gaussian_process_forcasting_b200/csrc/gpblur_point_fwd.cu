@@ -177,6 +177,7 @@ int launch_fwd_cfg(const PointFwdArgs& a0, cudaStream_t st) {
   int grid = occ * num_sms();
   if (grid > a.ntiles) grid = a.ntiles;
   if (grid < 1) grid = 1;
+  ProfScope ps(ST_POINT_FWD, st);
   point_fwd_kernel<Cfg><<<grid, kThreads, smem, st>>>(a);
   note_launch();
   return check_launch("point_fwd");

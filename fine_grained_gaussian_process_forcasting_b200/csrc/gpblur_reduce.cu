@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kThreads) reduce_gemm_kernel(ReduceArgs a) {
 template <int TP, int TQ, bool GRAM>
 int launch_reduce(const ReduceArgs& a, int ntiles, int splits, cudaStream_t st) {
   dim3 grid(ntiles, splits);
+  ProfScope ps(GRAM ? ST_GRAM : ST_WX, st);
   reduce_gemm_kernel<TP, TQ, GRAM><<<grid, kThreads, 0, st>>>(a);
   note_launch();
   return check_launch("reduce_gemm");

@@ -128,6 +128,13 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
 int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
                        size_t out_bytes, int* mp, void* stream);
 
+/* Optional per-stage timing for bench.py's roofline: while enabled, every launch is bracketed with CUDA
+ * events on its own stream.  gpblur_profile_collect synchronises on the recorded events, writes the
+ * accumulated milliseconds / launch counts per stage (order: mm_fwd, point_fwd, point_bwd, gram, wx,
+ * mm_bwd, elbo_fwd, elbo_bwd, other; n >= 9) and clears the records. */
+int gpblur_profile_enable(int on);
+int gpblur_profile_collect(double* ms, unsigned long long* counts, int n);
+
 /* Count of kernel launches issued by this library in this process (for bench.py's gpu_launches). */
 unsigned long long gpblur_launch_count(void);
 const char* gpblur_last_cuda_error(void);

@@ -1,0 +1,258 @@
+"""GPU tests at the module boundary (the calls the reference's forecast_denoising.py / denoise_model_2.py make),
+against the oracle and the committed golden fixtures, plus size-independent properties at BASELINE sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-300)).item()
+
+
+def load_params(model, p):
+    hl = model.hidden_layer
+    with torch.no_grad():
+        hl.variational_strategy.inducing_points.copy_(p["inducing_points"])
+        hl.covar_module.base_kernel.raw_lengthscale.copy_(p["raw_lengthscale"].reshape(1, -1))
+        hl.covar_module.raw_outputscale.copy_(p["raw_outputscale"].reshape(()))
+        hl.variational_strategy._variational_distribution.variational_mean.copy_(p["variational_mean"])
+        hl.variational_strategy._variational_distribution._variational_stddev.copy_(p["variational_stddev"])
+        hl.mean_module.weights.copy_(p["weights"].reshape(-1, 1))
+        hl.mean_module.bias.copy_(p["bias"].reshape(1))
+        if "raw_noise" in p:
+            model.likelihood.noise_covar.raw_noise.copy_(p["raw_noise"].reshape(1))
+        hl.variational_strategy.variational_params_initialized.fill_(1)
+
+
+def test_predict_and_mll_protocol_like_the_reference(cuda):
+    """denoise_model_2.add_gp_noise + forecast_denoising.py:87-89, verbatim call sequence."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat as gpytorch_like
+    B, L, D, M = 16, 24, 32, 64
+    p = O.init_params_exercise(D, M, 3)
+    x, y, _, _ = O.make_inputs(B, L, D, 4)
+    with gpytorch_like.num_likelihood_samples(1):
+        deep_gp = DeepGPp(D, 1234, num_inducing=M).to(cuda)
+        load_params(deep_gp, p)
+        proj_up = torch.nn.Linear(1, D).to(cuda)
+        xd = x.to(cuda).requires_grad_(True)
+        eps_gp, dist = deep_gp.predict(xd)                       # denoise_model_2.py:36
+        assert eps_gp.shape == (1, B, L) and dist.mean.shape == (1, B, L) and dist.event_shape == (L,)
+        x_noisy = xd + proj_up(eps_gp.permute(1, 2, 0))          # :37-38
+        y_true = y.to(cuda).unsqueeze(-1)                        # [B, L, 1]
+        mll = gpytorch_like.DeepApproximateMLL(
+            gpytorch_like.VariationalELBO(deep_gp.likelihood, deep_gp, D))
+        mll_error = -mll(dist, y_true.permute(2, 0, 1)).mean()   # forecast_denoising.py:89
+        loss = x_noisy.pow(2).mean() + 0.005 * mll_error
+        loss.backward()
+    p64 = O.clone_params(p, torch.float64, requires_grad=True)
+    x64 = x.double().requires_grad_(True)
+    mo, vo = O.svgp_predict_closed_form(p64, x64)
+    w64, b64 = proj_up.weight.detach().double().cpu(), proj_up.bias.detach().double().cpu()
+    xn = x64 + mo.unsqueeze(-1) * w64.reshape(1, 1, D) + b64
+    eo = O.elbo_per_window(mo, vo, y.double(), O.noise_variance(p64), O.kl_meanfield(p64), float(D))
+    lo = xn.pow(2).mean() + 0.005 * (-eo.mean())
+    lo.backward()
+    assert rel(eps_gp[0], mo) < 1e-5 and rel(dist.variance[0], vo) < 1e-5
+    assert abs(mll_error.item() + eo.mean().item()) < 1e-5 * abs(eo.mean().item())
+    assert rel(xd.grad, x64.grad) < 2e-4
+    hl = deep_gp.hidden_layer
+    assert rel(hl.variational_strategy.inducing_points.grad, p64["inducing_points"].grad) < 2e-4
+    assert rel(hl.covar_module.base_kernel.raw_lengthscale.grad, p64["raw_lengthscale"].grad) < 2e-4
+    assert rel(hl.variational_strategy._variational_distribution._variational_stddev.grad,
+               p64["variational_stddev"].grad) < 2e-4
+    assert rel(deep_gp.likelihood.noise_covar.raw_noise.grad, p64["raw_noise"].grad) < 2e-4
+    # default sample count outside the context is 10 (gpytorch default)
+    _, d10 = deep_gp.predict(x.to(cuda))
+    assert d10.mean.shape == (10, B, L)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "svgp_*.npz"))))
+def test_cuda_matches_golden_fixtures(cuda, path):
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    g = np.load(path)
+    p = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p_")}
+    x = torch.from_numpy(g["x"])
+    B, L, D = x.shape
+    M = p["inducing_points"].shape[0]
+    seed, off, stream = (int(v) for v in g["philox_seed_offset_stream"])
+    with gpcompat.num_likelihood_samples(1):
+        model = DeepGPp(D, 0, num_inducing=M).to(cuda)
+        load_params(model, p)
+        model.hidden_layer.set_rng(seed, off, stream)
+        xd = x.to(cuda).requires_grad_(True)
+        out = model.blur(xd, torch.from_numpy(g["y"]).to(cuda), num_data=D)
+        loss = -out.elbo.mean() + (torch.from_numpy(g["g_mean"]).to(cuda) * out.mean[0]).sum() + \
+            (torch.from_numpy(g["g_sample"]).to(cuda) * out.sample[0]).sum()
+        loss.backward()
+    assert rel(out.mean[0], g["mean"]) < 1e-5 and rel(out.variance[0], g["var"]) < 1e-5
+    assert rel(out.elbo[0], g["elbo"]) < 1e-5 and rel(out.kl, g["kl"]) < 1e-5
+    assert rel(out.sample[0], g["sample"]) < 1e-5
+    # the scalar is a sum of cancelling fp32 terms: compare against the magnitude of what was summed
+    scale = float(np.abs(g["g_mean"] * g["mean"]).sum() + np.abs(g["g_sample"] * g["sample"]).sum() + abs(g["elbo"]).mean())
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * scale
+    assert rel(xd.grad, g["dx"]) < 2e-4
+    hl = model.hidden_layer
+    got = {"inducing_points": hl.variational_strategy.inducing_points.grad,
+           "raw_lengthscale": hl.covar_module.base_kernel.raw_lengthscale.grad,
+           "raw_outputscale": hl.covar_module.raw_outputscale.grad,
+           "variational_mean": hl.variational_strategy._variational_distribution.variational_mean.grad,
+           "variational_stddev": hl.variational_strategy._variational_distribution._variational_stddev.grad,
+           "weights": hl.mean_module.weights.grad, "bias": hl.mean_module.bias.grad,
+           "raw_noise": model.likelihood.noise_covar.raw_noise.grad}
+    for k, v in got.items():
+        assert rel(v.reshape(-1), g["d_" + k].reshape(-1)) < 2e-4, k
+
+
+def test_eval_mode_and_no_grad(cuda):
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    D, M = 16, 32
+    p = O.init_params_exercise(D, M, 3)
+    x, _, _, _ = O.make_inputs(5, 24, D, 4)
+    with gpcompat.num_likelihood_samples(1):
+        m = DeepGPp(D, 1, num_inducing=M).to(cuda).eval()
+        load_params(m, p)
+        with torch.no_grad():
+            mean, dist = m.predict(x.to(cuda))
+    mo, vo = O.svgp_predict_closed_form(O.clone_params(p, torch.float64), x.double())
+    assert rel(mean[0], mo) < 1e-5 and rel(dist.variance[0], vo) < 1e-5 and not mean.requires_grad
+
+
+def test_two_layer_deepgp_matches_oracle(cuda):
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGP2
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    B, L, D, H, M = 6, 24, 16, 4, 32
+    p1 = O.init_params_hidden_layer(D, H, M, 5)
+    p2 = O.init_params_exercise(H, M, 6)
+    x, y, _, _ = O.make_inputs(B, L, D, 7)
+    with gpcompat.num_likelihood_samples(1):
+        net = DeepGP2(D, 11, hidden_dims=H, num_inducing=M).to(cuda)
+        l1, l2 = net.hidden_layer, net.last_layer
+        with torch.no_grad():
+            l1.variational_strategy.inducing_points.copy_(p1["inducing_points"])
+            l1.covar_module.base_kernel.raw_lengthscale.copy_(p1["raw_lengthscale"])
+            l1.covar_module.raw_outputscale.copy_(p1["raw_outputscale"])
+            l1.variational_strategy._variational_distribution.variational_mean.copy_(p1["variational_mean"])
+            l1.variational_strategy._variational_distribution._variational_stddev.copy_(p1["variational_stddev"])
+            l1.mean_module.weights.copy_(p1["weights"]); l1.mean_module.bias.copy_(p1["bias"])
+            l1.variational_strategy.variational_params_initialized.fill_(1)
+            l2.variational_strategy.inducing_points.copy_(p2["inducing_points"])
+            l2.covar_module.base_kernel.raw_lengthscale.copy_(p2["raw_lengthscale"])
+            l2.variational_strategy._variational_distribution.variational_mean.copy_(p2["variational_mean"])
+            l2.variational_strategy._variational_distribution._variational_stddev.copy_(p2["variational_stddev"])
+            l2.mean_module.weights.copy_(p2["weights"]); l2.mean_module.bias.copy_(p2["bias"])
+            l2.variational_strategy.variational_params_initialized.fill_(1)
+        l1.set_rng(77, 0, stream=1)
+        xd = x.to(cuda).requires_grad_(True)
+        mean, dist = net.predict(xd)
+        mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(net.likelihood, net, D))
+        loss = -mll(dist, y.to(cuda).unsqueeze(0)).mean()
+        loss.backward()
+    # oracle with the same Philox draws: layer 1 output h uses counters offset = h * N + n, stream 1
+    N = B * L
+    eps = torch.stack([torch.from_numpy(O.philox_normal(77, h * N, N, 1)).reshape(B, L) for h in range(H)], -1).double()
+    p1_64 = O.clone_params(p1, torch.float64, requires_grad=True)
+    p2_64 = O.clone_params(p2, torch.float64, requires_grad=True)
+    x64 = x.double().requires_grad_(True)
+    mo, vo, ho = O.deepgp2_predict(p1_64, p2_64, x64, eps)
+    kl = O.kl_hidden_layer(p1_64) + O.kl_meanfield(p2_64)
+    noise = O.softplus(torch.zeros((), dtype=torch.float64)) + O.NOISE_LOWER
+    lo = -O.elbo_per_window(mo, vo, y.double(), noise, kl, float(D)).mean()
+    lo.backward()
+    assert rel(mean[0], mo) < 2e-5 and rel(dist.variance[0], vo) < 2e-5
+    assert abs(loss.item() - lo.item()) < 2e-5 * abs(lo.item())
+    assert rel(xd.grad, x64.grad) < 5e-4
+    assert rel(l1.variational_strategy.inducing_points.grad, p1_64["inducing_points"].grad) < 5e-4
+    assert rel(l2.variational_strategy.inducing_points.grad, p2_64["inducing_points"].grad) < 5e-4
+    assert rel(l1.mean_module.weights.grad, p1_64["weights"].grad) < 5e-4
+
+
+def test_exact_gp_model(cuda):
+    from fine_grained_gaussian_process_forcasting_b200.GPModel import ExactGPModel
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    g = torch.Generator().manual_seed(0)
+    tx, ty, sx = torch.randn(20, 3, generator=g), torch.randn(20, generator=g), torch.randn(7, 3, generator=g)
+    lik = gpcompat.GaussianLikelihood().to(cuda)
+    m = ExactGPModel(tx.to(cuda), ty.to(cuda), lik).to(cuda)
+    prior = m(tx.to(cuda))                                       # train mode: prior at the inputs
+    z = torch.zeros((), dtype=torch.float64)
+    mean_o, cov_o = O.exact_gp_prior(tx.double(), z, z, z)
+    assert rel(prior.covariance_matrix, cov_o) < 1e-5 and rel(prior.mean + 1.0, mean_o + 1.0) < 1e-6
+    m.eval()
+    post = m(sx.to(cuda))
+    pm, pc = O.exact_gp_posterior(tx.double(), ty.double(), sx.double(), z, z, z, z)
+    assert rel(post.mean, pm) < 1e-4 and rel(post.covariance_matrix, pc) < 1e-4
+
+
+def test_shard_invariance_and_bit_exact_samples(cuda):
+    """Size-independent property at a BASELINE size (C3: B=1024, L=24, D=64, M=128): running the batch in
+    two shards with global Philox offsets reproduces the single-shot per-window outputs BIT-exactly."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L, D, M = 1024, 24, 64, 128
+    p = {k: v.to(cuda) for k, v in O.init_params_exercise(D, M, 9).items()}
+    x = torch.randn(B, L, D, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+
+    def run(xs, off):
+        return ops.svgp_predict(xs, p["inducing_points"], p["raw_lengthscale"], p["raw_outputscale"],
+                                p["variational_mean"], p["variational_stddev"], p["weights"], p["bias"],
+                                seed=5, offset=off, stream_id=0, want_sample=True)
+    m_all, v_all, s_all, _, _ = run(x, 0)
+    h = 384
+    m_a, v_a, s_a, _, _ = run(x[:h], 0)
+    m_b, v_b, s_b, _, _ = run(x[h:], h * L)
+    assert torch.equal(torch.cat([m_a, m_b]), m_all)
+    assert torch.equal(torch.cat([v_a, v_b]), v_all)
+    assert torch.equal(torch.cat([s_a, s_b]), s_all)
+
+
+def test_backward_linearity_at_full_size(cuda):
+    """Property at C5 size (B=8192, L=24, D=64, M=64): the backward is linear in the upstream gradients,
+    grads(g1 + 2 g2) == grads(g1) + 2 grads(g2), and deterministic run to run."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L, D, M = 8192, 24, 64, 64
+    gen = torch.Generator(device=cuda).manual_seed(2)
+    p = {k: v.to(cuda).requires_grad_(True) for k, v in O.init_params_exercise(D, M, 9).items()}
+    x = torch.randn(B, L, D, device=cuda, generator=gen).requires_grad_(True)
+    g1m, g2m = (torch.randn(B, L, device=cuda, generator=gen) for _ in range(2))
+    g1v, g2v = (torch.randn(B, L, device=cuda, generator=gen) for _ in range(2))
+    names = ["inducing_points", "raw_lengthscale", "raw_outputscale", "variational_mean", "variational_stddev",
+             "weights", "bias"]
+
+    def grads(gm, gv):
+        mean, var, _, kl, _ = ops.svgp_predict(x, *(p[k] for k in names))
+        return torch.autograd.grad([mean, var], [x] + [p[k] for k in names], [gm, gv])
+    ga, gb = grads(g1m, g1v), grads(g2m, g2v)
+    gc = grads(g1m + 2 * g2m, g1v + 2 * g2v)
+    gc2 = grads(g1m + 2 * g2m, g1v + 2 * g2v)
+    for a, b, c, c2 in zip(ga, gb, gc, gc2):
+        assert torch.equal(c, c2)                                     # deterministic reductions
+        assert rel(a + 2 * b, c) < 2e-4
+
+
+def test_sharded_wrapper_single_process(cuda):
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200.distributed import ShardedGPBlur
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    D, M, B, L = 16, 32, 8, 24
+    with gpcompat.num_likelihood_samples(1):
+        model = DeepGPp(D, 3, num_inducing=M).to(cuda)
+        load_params(model, O.init_params_exercise(D, M, 3))
+        dp = ShardedGPBlur(model)
+        x, y, _, _ = O.make_inputs(B, L, D, 4)
+        out = dp(x.to(cuda).requires_grad_(True), y.to(cuda), first_global_window=0, global_windows=B)
+        (-out.elbo.mean()).backward()
+        dp.sync_grads()
+    assert dp.bucket.flat.abs().sum().item() > 0
+    assert model.hidden_layer.variational_strategy.inducing_points.grad.data_ptr() >= dp.bucket.flat.data_ptr()
