@@ -393,7 +393,7 @@ def run_ours(args, wl, name):
             roof["peak_source"] = peaks["source"]
             roof["hbm_frac_whole_step"] = (B * sum(bytes_per_window(L, D) for L in calls) / (ms_per_step * 1e-3) / 1e9
                                            / peaks["hbm_gbs"])
-        cb, _ = time_cpu_reference(wl, 3, 1)
+        cb = None if args.no_cpu_baseline else time_cpu_reference(wl, 3, 1)[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -423,6 +423,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("GPBLUR_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
