@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "gpblur_common.cuh"
 
@@ -55,6 +56,11 @@ int num_sms() {
     cache[dev] = n > 0 ? n : 148;
   }
   return cache[dev];
+}
+
+int tile_override(const char* env) {
+  const char* v = getenv(env);
+  return v ? atoi(v) : 0;
 }
 
 int bwd_vector_partials(const WsLayout& L);

@@ -15,7 +15,7 @@ constexpr float kNoiseLower = 1e-4f;    // GaussianLikelihood GreaterThan(1e-4)
 constexpr int kThreads = 256;
 constexpr int kKS = 16;                 // K-slice depth of the staged operand tiles
 constexpr int kMaxPersist = 296;        // persistent CTAs of the backward point kernel (2 x 148 SMs)
-constexpr int kMaxSplits = 64;          // split-K factor cap of the N-reduction GEMMs
+constexpr int kMaxSplits = 148;          // split-K factor cap of the N-reduction GEMMs
 
 // hyp (fp32) slots
 enum { H_OS = 0, H_JIT = 1, H_CWB = 2, H_KL = 3, H_COUNT = 8 };
@@ -96,6 +96,14 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   const int nt = w.MP / tp;
   w.splitsS = choose_splits(N, nt * (nt + 1) / 2);
   w.splitsZ = choose_splits(N, nt);
+  if (w.MP == 128 || w.MP == 256) {
+    // tensor-core reductions: (MP / 128) row tiles x splits CTAs, one wave of 148 SMs, >= 128 rows per split
+    long long s = 148 / (w.MP / 128);
+    const long long maxs = (N + 127) / 128;
+    if (s > maxs) s = maxs;
+    if (s < 1) s = 1;
+    w.splitsS = w.splitsZ = (int)s;
+  }
   w.nvec = kMaxPersist;
   w.vec_len = w.MP + 2 * w.DP + VS_COUNT;
   if (training) {
@@ -188,6 +196,7 @@ struct ProfScope {
 void note_launch(int n = 1);
 int check_launch(const char* what);
 int num_sms();
+int tile_override(const char* env);   // 0 = heuristic, else forced tile height (tuning knob)
 
 // launchers implemented in the other translation units
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,

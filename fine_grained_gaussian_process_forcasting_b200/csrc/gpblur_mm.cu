@@ -71,6 +71,42 @@ __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
   j = t - ii * (ii + 1) / 2;
 }
 
+// Cholesky of a 32 x 32 block held one row per lane in registers (warp-shuffle pivot / column broadcasts).
+// On exit a[c] = L[lane][c] (0 above the diagonal), rinv = 1 / L[lane][lane]; returns the first bad pivot (1-based).
+__device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int lane) {
+  int bad = 0;
+#pragma unroll
+  for (int c = 0; c < TB; ++c) {
+    const double d = __shfl_sync(0xffffffffu, a[c], c);
+    if (!(d > 0.0) && bad == 0) bad = c + 1;
+    const double rs = rsqrt(d);
+    const double l = a[c] * rs;
+    if (lane == c) rinv = rs;
+    a[c] = (lane >= c) ? l : 0.0;
+#pragma unroll
+    for (int c2 = c + 1; c2 < TB; ++c2) {
+      const double lc2 = __shfl_sync(0xffffffffu, l, c2);
+      if (lane >= c2) a[c2] = fma(-l, lc2, a[c2]);
+    }
+  }
+  return bad;
+}
+
+// Inverse of the lower-triangular block Lb (shared memory, row-major) with reciprocal diagonal rd:
+// lane = column of the inverse, result X[r][lane] written to Xb.
+__device__ __forceinline__ void trinv32_warp(const Tile& Lb, const double* rd, Tile& Xb, int lane) {
+  double x[TB];
+#pragma unroll
+  for (int r = 0; r < TB; ++r) {
+    double s = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) s = fma(-Lb[r][k], x[k], s);
+    x[r] = (r >= lane) ? s * rd[r] : 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < TB; ++r) Xb[r][lane] = x[r];
+}
+
 struct MmFwdArgs {
   gpblur_svgp_params p;
   WsLayout L;
@@ -127,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         center[d] = c;
         ellv[d] = (float)ell;
         inv_ell[d] = (float)(1.0 / ell);
+        T64[d] = 1.0 / ell;                 // fp64 copy for the Kzz build (T64 is free until phase 3b)
         wl[d] = a.p.mean_weights ? (float)(ell * (double)a.p.mean_weights[d]) : 0.0f;
       }
     } else if (lane == 0) {
@@ -198,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
           const int d = d0 + tx;
           double va = 0.0, vb = 0.0;
           if (d < D) {
-            const double ie = 1.0 / softplus64((double)a.p.raw_lengthscale[d]);
+            const double ie = T64[d];
             const int ra = bi * TB + r, rb = bj * TB + r;
             if (ra < M) va = (double)Z[(size_t)ra * D + d] * ie;
             if (rb < M) vb = (double)Z[(size_t)rb * D + d] * ie;
@@ -233,58 +270,56 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   grid.sync();
 
   // ---------------- phase 2: blocked Cholesky (right-looking) ----------------
+  // per block column kb: every participating CTA factorises the diagonal block in registers (one warp, shuffle
+  // broadcasts) and inverts it, so the panel solve X L_kk^T = A_ik becomes the GEMM X = A_ik Dinv^T.
+  __shared__ double rdiag[TB];
+  Tile& Di = Cs[0];   // inverse of the diagonal block
   for (int kb = 0; kb < nb; ++kb) {
     const int nrb = nb - kb - 1;
-    const bool has_rows = (blockIdx.x * 8) < nrb;
+    const bool has_rows = (int)blockIdx.x < nrb;
     if (has_rows || blockIdx.x == 0) {
       __syncthreads();
-      load_tile(Dg, MatRef{L64, MP, false}, kb * TB, kb * TB);
-      __syncthreads();
       if (warp == 0) {
-        for (int c = 0; c < TB; ++c) {
-          double d = Dg[c][c];
-          if (!(d > 0.0)) {
-            if (blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + c + 1);
-          }
-          const double sd = sqrt(d);
-          __syncwarp();
-          if (lane == c) Dg[c][c] = sd;
-          if (lane > c) Dg[lane][c] = Dg[lane][c] / sd;
-          __syncwarp();
-          if (lane > c) {
-            const double l = Dg[lane][c];
-            for (int c2 = c + 1; c2 <= lane; ++c2) Dg[lane][c2] = fma(-l, Dg[c2][c], Dg[lane][c2]);
-          }
-          __syncwarp();
-        }
-        for (int c = lane + 1; c < TB; ++c) Dg[lane][c] = 0.0;
+        double arow[TB];
+        const double* src = L64 + (size_t)(kb * TB + lane) * MP + kb * TB;
+#pragma unroll
+        for (int c = 0; c < TB; ++c) arow[c] = src[c];
+        double rinv = 0.0;
+        const int bad = chol32_warp(arow, rinv, lane);
+        if (bad && blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + bad);
+#pragma unroll
+        for (int c = 0; c < TB; ++c) Dg[lane][c] = arow[c];
+        rdiag[lane] = rinv;
+        __syncwarp();
+        trinv32_warp(Dg, rdiag, Di, lane);
       }
       __syncthreads();
-      // panel: X L_kk^T = A_ik, one row block per warp, one row per lane
-      for (int rb0 = blockIdx.x * 8; rb0 < nrb; rb0 += G * 8) {
-        const int rb = rb0 + warp;
-        if (rb < nrb) {
-          Tile& C = Cs[warp];
-          const int row0 = (kb + 1 + rb) * TB;
-          for (int r = 0; r < TB; ++r) C[r][lane] = L64[(size_t)(row0 + r) * MP + kb * TB + lane];
-          __syncwarp();
-          for (int c = 0; c < TB; ++c) {
-            double x = C[lane][c];
-            for (int c2 = 0; c2 < c; ++c2) x = fma(-C[lane][c2], Dg[c][c2], x);
-            C[lane][c] = x / Dg[c][c];
-          }
-          __syncwarp();
-          for (int r = 0; r < TB; ++r) L64[(size_t)(row0 + r) * MP + kb * TB + lane] = C[r][lane];
+      // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
+      for (int rb = blockIdx.x; rb < nrb; rb += G) {
+        const int row0 = (kb + 1 + rb) * TB;
+        __syncthreads();
+        load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
+        __syncthreads();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+        for (int k = 0; k < TB; ++k) {
+          const double b = Di[lane][k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fma(As[warp + 8 * i][k], b, acc[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) L64[(size_t)(row0 + warp + 8 * i) * MP + kb * TB + lane] = acc[i];
       }
     }
     grid.sync();
-    // the factorised diagonal block is published only now: other CTAs read the unfactorised one above
+    // the factorised diagonal block (and its inverse, which seeds phase 3) are published only now: other
+    // CTAs read the unfactorised block above
     if (blockIdx.x == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = warp + 8 * i;
         L64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Dg[r][lane];
+        Li64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Di[r][lane];
       }
     }
     // trailing update: C_ij -= L_ik L_jk^T for kb < j <= i
@@ -305,31 +340,6 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     grid.sync();   // also publishes the last diagonal block before phase 3
   }
 
-  // ---------------- phase 3a: inverses of the diagonal blocks ----------------
-  for (int b = blockIdx.x; b < nb; b += G) {
-    __syncthreads();
-    load_tile(As, MatRef{L64, MP, false}, b * TB, b * TB);
-    __syncthreads();
-    if (warp == 0) {
-      const int c = lane;   // column of the inverse
-      for (int r = 0; r < TB; ++r) {
-        double x = 0.0;
-        if (r >= c) {
-          double s = (r == c) ? 1.0 : 0.0;
-          for (int k = c; k < r; ++k) s = fma(-As[r][k], Bs[k][c], s);
-          x = s / As[r][r];
-        }
-        Bs[r][c] = x;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = warp + 8 * i;
-      Li64[(size_t)(b * TB + r) * MP + b * TB + lane] = Bs[r][lane];
-    }
-  }
-  grid.sync();
   // ---------------- phase 3b: recursive doubling  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]] ----
   for (int s = TB; s < MP; s *= 2) {
     const int sb = s / TB;                    // blocks per half
@@ -598,12 +608,22 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     const double* q = vec64 + MP;
     const double* wbar = vec64 + MP + DP;
     const double* sc = vec64 + MP + 2 * DP;
-    for (int d = tid; d < D; d += kThreads) {
-      double s = q[d];
-      for (int i = 0; i < M; ++i) s += t64[(size_t)i * DP + d];
-      const double dell = s * (double)inv_ell[d];
-      b_ell[d] = (float)(dell * sigmoid64((double)a.p.raw_lengthscale[d]));
-      b_w[d] = a.p.mean_weights ? (float)wbar[d] : 0.f;
+    // column sums of the per-(i, d) terms: NPART row partitions per column, combined in fixed order
+    {
+      __shared__ double colred[kThreads];
+      const int npart = kThreads / DP;           // DP in {16, 32, 64, 128}
+      const int d = tid % DP, part = tid / DP;
+      double s = 0.0;
+      for (int i = part; i < M; i += npart) s += t64[(size_t)i * DP + d];
+      colred[tid] = s;
+      __syncthreads();
+      if (part == 0 && d < D) {
+        double tot = q[d];
+        for (int p2 = 0; p2 < npart; ++p2) tot += colred[p2 * DP + d];
+        const double dell = tot * (double)inv_ell[d];
+        b_ell[d] = (float)(dell * sigmoid64((double)a.p.raw_lengthscale[d]));
+        b_w[d] = a.p.mean_weights ? (float)wbar[d] : 0.f;
+      }
     }
     for (int m = tid; m < M; m += kThreads) {
       const double mm = (double)mvec[m], ss = (double)svec[m];

@@ -25,7 +25,7 @@ struct BwdSmem {
 };
 
 template <class Cfg, int DP>
-__global__ void __launch_bounds__(kThreads) point_bwd_kernel(PointBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, Cfg::TN <= 64 ? 2 : 1) point_bwd_kernel(PointBwdArgs a) {
   constexpr int PT = Cfg::PT, CT = Cfg::CT, CW = Cfg::CW, TN = Cfg::TN, TXN = Cfg::TXN, TYN = Cfg::TYN;
   using S = BwdSmem<Cfg, DP>;
   constexpr int ldx = S::ldx, lda = S::lda, ldw = S::ldw, BZ = S::BZ;
@@ -350,9 +350,10 @@ __global__ void __launch_bounds__(kThreads) point_bwd_kernel(PointBwdArgs a) {
 // tile height used by the backward for a given problem (shared with the M x M stage, which needs the
 // number of vector partials)
 inline int bwd_tile_points(const WsLayout& L) {
-  const long long N = L.N;
-  if (L.DP == 128) return 64;
-  if (N >= (long long)128 * 2 * 148) return 128;
+  const int force = tile_override("GPBLUR_BWD_TN");
+  if (force == 128 && L.DP != 128) return 128;
+  if (force == 64) return 64;
+  // 64-point tiles: <= 128 registers and ~90 KB shared memory -> two CTAs (16 warps) per SM
   return 64;
 }
 

@@ -14,7 +14,7 @@ namespace gpblur {
 namespace {
 
 template <class Cfg>
-__global__ void __launch_bounds__(kThreads) point_fwd_kernel(PointFwdArgs a) {
+__global__ void __launch_bounds__(kThreads, Cfg::PT <= 4 ? 2 : 1) point_fwd_kernel(PointFwdArgs a) {
   constexpr int PT = Cfg::PT, CT = Cfg::CT, CW = Cfg::CW, TN = Cfg::TN;
   extern __shared__ __align__(16) float smem[];
   const WsLayout& L = a.L;
@@ -193,6 +193,13 @@ int dispatch_fwd_tn(const PointFwdArgs& a, cudaStream_t st) {
   using C32 = TileCfg<32 / TYN, CT, CW>;
   const long long N = a.L.N;
   const int sms = num_sms();
+  const int force = tile_override("GPBLUR_FWD_TN");
+  if (force == 128 && fwd_smem_bytes<C128>(a.L) <= kSmemCap) return launch_fwd_cfg<C128>(a, st);
+  if (force == 64 && fwd_smem_bytes<C64>(a.L) <= kSmemCap) return launch_fwd_cfg<C64>(a, st);
+  if (force == 32 && fwd_smem_bytes<C32>(a.L) <= kSmemCap) return launch_fwd_cfg<C32>(a, st);
+  // 64-point tiles with two CTAs per SM (16 warps) hide the shared-memory / barrier latency better than one
+  // 128-point CTA (ncu r01a: 8 warps/SM, issue slots 61 % busy); fall back to whatever fits in shared memory.
+  if (2 * fwd_smem_bytes<C64>(a.L) <= kSmemCap && N >= (long long)64 * sms) return launch_fwd_cfg<C64>(a, st);
   if (fwd_smem_bytes<C128>(a.L) <= kSmemCap && N >= (long long)128 * 2 * sms) return launch_fwd_cfg<C128>(a, st);
   if (fwd_smem_bytes<C64>(a.L) <= kSmemCap && N >= (long long)64 * sms) return launch_fwd_cfg<C64>(a, st);
   if (fwd_smem_bytes<C32>(a.L) <= kSmemCap) return launch_fwd_cfg<C32>(a, st);

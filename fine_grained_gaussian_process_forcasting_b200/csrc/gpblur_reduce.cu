@@ -48,7 +48,7 @@ struct ReduceArgs {
 };
 
 template <int TP, int TQ, bool GRAM>
-__global__ void __launch_bounds__(kThreads) reduce_gemm_kernel(ReduceArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) reduce_gemm_kernel(ReduceArgs a) {
   constexpr int RP = TP / 16, RQ = TQ / 16;
   __shared__ __align__(16) float Us[2][kKS][TP];
   __shared__ __align__(16) float Vs[2][kKS][TQ];
@@ -183,8 +183,12 @@ int launch_wx(const ReduceArgs& a, int DP, int ntiles, int splits, cudaStream_t 
 
 }  // namespace
 
+bool tc_reductions_supported(const WsLayout& L);
+int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st);
+
 int launch_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st) {
   if (L.N <= 0) return GPBLUR_OK;
+  if (tc_reductions_supported(L)) return launch_tc_reductions(L, ws, x, st);   // tcgen05 3xTF32 path
   const int MP = L.MP;
   const int tp = MP < 128 ? MP : 128;
   const int nt = MP / tp;

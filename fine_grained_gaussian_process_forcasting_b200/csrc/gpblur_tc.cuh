@@ -1,0 +1,140 @@
+// tcgen05 (5th-gen tensor core) building blocks for the 3xTF32 GEMMs: TMEM allocation, mbarrier, UMMA shared
+// memory / instruction descriptors, the error-compensated operand split and TMEM -> register loads.
+//
+// Operand tiles are written by CUDA cores (they have to be: every fp32 operand is split into a TF32 "hi" and a
+// TF32 "lo" plane, D += Ahi*Bhi + Ahi*Blo + Alo*Bhi), in the canonical K-major NO-SWIZZLE UMMA layout
+//   byte offset(row r, 16-byte k-chunk c) = c * (ROWS * 16) + r * 16
+// i.e. per k-chunk (4 fp32) a dense [ROWS][16 B] plane: core matrices (8 rows x 16 B) are contiguous along the
+// rows (SBO = 128 B) and ROWS*16 B apart along K (LBO).  One tcgen05.mma.kind::tf32 consumes K = 8 = two chunks.
+#pragma once
+#include "gpblur_common.cuh"
+
+namespace gpblur {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::); }
+// spin on the phase parity; traps instead of hanging the GPU if the phase never completes
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t tries = 0; !ok; ++tries) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (tries > (1u << 24)) asm volatile("trap;");
+  }
+}
+
+// ---- fences ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------------------
+// one full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols));
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (lane = row of the tile)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------------
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//   [46,48) version = 1 (sm_100) | [61,64) layout type = 0
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor):
+//   [4,6) c_format = 1 (F32) | [7,10) a_format = 2 (TF32) | [10,13) b_format = 2 | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrive on `bar` when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- 3xTF32 split ---------------------------------------------------------------------------------------
+// hi = round-to-nearest TF32 of a (low 13 mantissa bits zero), lo = a - hi (exact in fp32; the tensor core
+// truncates it to TF32 at 2^-22 |a|).  a*b ~= hi_a*hi_b + hi_a*lo_b + lo_a*hi_b, relative error ~2^-21.
+__device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
+  hi = __uint_as_float(h);
+  lo = a - hi;
+}
+__device__ __forceinline__ void store_split(float* hi_plane, float* lo_plane, int off_floats, const float4& v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi_plane + off_floats) = h;
+  *reinterpret_cast<float4*>(lo_plane + off_floats) = l;
+}
+
+// byte layout helper: float offset of (row r, k-chunk c) in a [KCH chunks][ROWS][4 floats] operand plane
+template <int ROWS>
+__device__ __forceinline__ int op_off(int r, int c) { return (c * ROWS + r) * 4; }
+
+// issue the 3 x (KT / 8) MMAs of one K slab: A planes [KT/4 chunks][128 rows], B planes [KT/4][NROWS]
+template <int KT, int NROWS>
+__device__ __forceinline__ void issue_slab_3xtf32(uint32_t tmem_d, const float* a_hi, const float* a_lo,
+                                                  const float* b_hi, const float* b_lo, uint32_t idesc, bool first) {
+  constexpr uint32_t A_LBO = 128 * 16, B_LBO = NROWS * 16, SBO = 128;
+  const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+  for (int j = 0; j < KT / 8; ++j) {
+    const uint32_t ao = 2 * j * A_LBO, bo = 2 * j * B_LBO;
+    const uint64_t dah = make_smem_desc(ah + ao, A_LBO, SBO), dal = make_smem_desc(al + ao, A_LBO, SBO);
+    const uint64_t dbh = make_smem_desc(bh + bo, B_LBO, SBO), dbl = make_smem_desc(bl + bo, B_LBO, SBO);
+    umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
+    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+    umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+  }
+}
+
+}  // namespace tc
+}  // namespace gpblur

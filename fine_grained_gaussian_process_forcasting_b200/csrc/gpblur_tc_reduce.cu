@@ -1,0 +1,246 @@
+// tcgen05 3xTF32 N-reduction GEMMs of the backward (tensor-core replacement of reduce_gemm_kernel for M >= 128):
+//   Gram  : S[p][q]  = sum_n A[n][p] * (g_var[n] A[n][q])      (+ u[p] = sum_n g_mu[n] A[n][p], for free in the loader)
+//   W^T X : WX[m][d] = sum_n W[n][m] * X[n][d]
+// Both operands are "MN-major" in memory (the reduction index n is the slow one), so the producer threads gather
+// 4 consecutive n per 16-byte k-chunk, split every value into TF32 hi/lo planes and write the canonical K-major
+// no-swizzle UMMA tiles; one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = TQ, K = 8) into a TMEM
+// accumulator, completion is tracked with tcgen05.commit -> mbarrier, and the epilogue reads TMEM with tcgen05.ld.
+// Split over N across CTAs (grid.y); partials are reduced in fixed order by the M x M backward stage.
+#include "gpblur_tc.cuh"
+
+namespace gpblur {
+
+namespace {
+
+constexpr int KT = 32;   // reduction rows per pipeline slab (4 UMMA k-steps)
+
+struct TcReduceArgs {
+  const float* U;   // [N][ldu]   A-operand source (rows of the output = columns p of U)
+  const float* V;   // [N][ldv]   B-operand source (columns q)
+  const float* sc;  // [N] scale applied to V rows, or null
+  const float* gm;  // [N] weights of the fused column sum u (Gram only), or null
+  float* C;         // [splits][P][ldc]
+  float* uvec;      // [splits][P]
+  long long N;
+  int ldu, ldv, vcols, P, ldc, rows_per_split;
+};
+
+template <int TQ>
+struct TcSmem {
+  static constexpr int A_PLANE = (KT / 4) * 128 * 4;   // floats
+  static constexpr int B_PLANE = (KT / 4) * TQ * 4;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr size_t bytes = (size_t)2 * STAGE * 4 + 1024;
+};
+
+template <int TQ, bool GRAM>
+__global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) {
+  using S = TcSmem<TQ>;
+  constexpr int BG0 = kThreads / TQ > 0 ? kThreads / TQ : 1;
+  constexpr int BG = BG0 > KT / 4 ? KT / 4 : BG0;             // thread groups along the B chunks (1, 2, 4, 8)
+  constexpr int BCH = (KT / 4) / BG;                          // B chunks per thread
+  constexpr uint32_t TMEM_COLS = TQ < 32 ? 32 : TQ;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float scs[2][KT], gms[2][KT];
+  __shared__ float ured[2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p0 = blockIdx.x * 128;
+  const long long r0 = (long long)blockIdx.y * a.rows_per_split;
+  long long r1 = r0 + a.rows_per_split;
+  if (r1 > a.N) r1 = a.N;
+  const int nsl = r1 > r0 ? (int)((r1 - r0 + KT - 1) / KT) : 0;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  constexpr uint32_t idesc = tc::make_idesc_tf32(128, TQ);
+
+  // ---- loader thread mapping ----
+  const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk parity (chunks acg, acg+2, acg+4, acg+6)
+  const int bq = tid % TQ, bcg = (tid / TQ) % BG;      // B: row, chunk group
+  float4 areg[4], breg[BCH];
+  float usum = 0.f;
+
+  auto prefetch = [&](int s) {
+    const long long n0 = r0 + (long long)s * KT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = acg + 2 * i;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long n = n0 + 4 * c + e;
+        v[e] = (n < r1) ? a.U[(size_t)n * a.ldu + p0 + ar] : 0.f;
+      }
+      areg[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (TQ >= kThreads || tid < TQ * BG) {
+#pragma unroll
+      for (int i = 0; i < BCH; ++i) {
+        const int c = bcg + BG * i;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long n = n0 + 4 * c + e;
+          v[e] = (n < r1 && bq < a.vcols) ? a.V[(size_t)n * a.ldv + bq] : 0.f;
+        }
+        breg[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  };
+  // per-row scales of slab s go through shared memory; they are staged one iteration ahead, BEFORE that
+  // iteration's __syncthreads, so the barrier orders the write against the reads of the next iteration
+  auto stage_scales = [&](int s) {
+    if (tid < KT) {
+      const long long n = r0 + (long long)s * KT + tid;
+      scs[s & 1][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
+      if (GRAM) gms[s & 1][tid] = (n < r1) ? a.gm[n] : 0.f;
+    }
+  };
+
+  uint32_t uses[2] = {0, 0};
+  if (nsl > 0) { prefetch(0); stage_scales(0); }
+  __syncthreads();
+  for (int s = 0; s < nsl; ++s) {
+    const int st = s & 1;
+    if (s + 1 < nsl) stage_scales(s + 1);
+    float* a_hi = stage_base + st * S::STAGE;
+    float* a_lo = a_hi + S::A_PLANE;
+    float* b_hi = a_lo + S::A_PLANE;
+    float* b_lo = b_hi + S::B_PLANE;
+    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);   // MMAs of slab s-2 are done with this stage
+    // ---- transform: split into TF32 hi / lo planes in the UMMA layout ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = acg + 2 * i;
+      tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), areg[i]);
+      if (GRAM) {
+        usum = fmaf(gms[st][4 * c + 0], areg[i].x, usum);
+        usum = fmaf(gms[st][4 * c + 1], areg[i].y, usum);
+        usum = fmaf(gms[st][4 * c + 2], areg[i].z, usum);
+        usum = fmaf(gms[st][4 * c + 3], areg[i].w, usum);
+      }
+    }
+    if (TQ >= kThreads || tid < TQ * BG) {
+#pragma unroll
+      for (int i = 0; i < BCH; ++i) {
+        const int c = bcg + BG * i;
+        float4 v = breg[i];
+        v.x *= scs[st][4 * c + 0]; v.y *= scs[st][4 * c + 1];
+        v.z *= scs[st][4 * c + 2]; v.w *= scs[st][4 * c + 3];
+        tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
+      }
+    }
+    tc::fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      tc::issue_slab_3xtf32<KT, TQ>(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, s == 0);
+      tc::umma_commit(&bars[st]);
+    }
+    uses[st] += 1;
+    if (s + 1 < nsl) prefetch(s + 1);   // global loads of the next slab fly while the tensor core works
+  }
+
+  // ---- epilogue ----
+  float* Cs = a.C + (size_t)blockIdx.y * a.P * a.ldc;
+  const int row = (warp & 3) * 32 + lane;
+  constexpr int CHUNKS = TQ / 32;                 // 32-column chunks of the tile
+  constexpr int CPW = CHUNKS >= 2 ? CHUNKS / 2 : 1;   // chunks per warp (two column halves when possible)
+  const int c_begin = CHUNKS >= 2 ? (warp >> 2) * CPW : 0;
+  const bool active = CHUNKS >= 2 || warp < 4;
+  if (nsl > 0) {
+    const int last = (nsl - 1) & 1;
+    tc::mbar_wait(&bars[last], (uses[last] - 1) & 1);
+    tc::tc_fence_after();
+  }
+  if (active) {
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+      const int col = (c_begin + cc) * 32;
+      float v[32];
+      if (nsl > 0) {
+        tc::tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      float* dst = Cs + (size_t)(p0 + row) * a.ldc + col;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  if (GRAM) {
+    ured[acg][ar] = usum;
+    __syncthreads();
+    if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int TQ, bool GRAM>
+int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = TcSmem<TQ>::bytes;
+  if (!configured) {
+    cudaFuncSetAttribute(tc_reduce_kernel<TQ, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  ProfScope ps(GRAM ? ST_GRAM : ST_WX, st);
+  tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits), kThreads, smem, st>>>(a);
+  note_launch();
+  return check_launch("tc_reduce");
+}
+
+}  // namespace
+
+bool tc_reductions_supported(const WsLayout& L) {
+  const int off = tile_override("GPBLUR_TC");   // GPBLUR_TC=-1 disables the tensor-core path
+  if (off < 0) return false;
+  return (L.MP == 128 || L.MP == 256) && (L.DP == 64 || L.DP == 32 || L.DP == 128 || L.DP == 16) && L.N >= 1;
+}
+
+int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st) {
+  const int MP = L.MP;
+  const float* gsc = ws_cptr<float>(ws, L.gsc);
+  auto rows = [&](int splits) {
+    long long r = (L.N + splits - 1) / splits;
+    return (int)round_up_ll(r, KT);
+  };
+  TcReduceArgs g{};
+  g.U = ws_cptr<float>(ws, L.A); g.V = g.U; g.sc = gsc + L.N; g.gm = gsc;
+  g.C = ws_ptr<float>(ws, L.Spart); g.uvec = ws_ptr<float>(ws, L.upart);
+  g.N = L.N; g.ldu = MP; g.ldv = MP; g.vcols = MP; g.P = MP; g.ldc = MP;
+  g.rows_per_split = rows(L.splitsS);
+  int rc = (MP == 128) ? launch_tc_reduce<128, true>(g, 1, L.splitsS, st)
+                       : launch_tc_reduce<256, true>(g, 2, L.splitsS, st);
+  if (rc) return rc;
+  TcReduceArgs w{};
+  w.U = ws_cptr<float>(ws, L.W); w.V = x; w.sc = nullptr; w.gm = nullptr;
+  w.C = ws_ptr<float>(ws, L.WXpart); w.uvec = nullptr;
+  w.N = L.N; w.ldu = MP; w.ldv = L.D; w.vcols = L.D; w.P = MP; w.ldc = L.DP;
+  w.rows_per_split = rows(L.splitsZ);
+  const int pt = MP / 128;
+  switch (L.DP) {
+    case 16:   // N = 32 MMA with the upper 16 columns zero (vcols = D), only ldc = 16 columns are stored
+    case 32: return launch_tc_reduce<32, false>(w, pt, L.splitsZ, st);
+    case 64: return launch_tc_reduce<64, false>(w, pt, L.splitsZ, st);
+    default: return launch_tc_reduce<128, false>(w, pt, L.splitsZ, st);
+  }
+}
+
+}  // namespace gpblur
