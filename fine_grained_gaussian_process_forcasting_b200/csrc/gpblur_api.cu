@@ -65,7 +65,7 @@ int tile_override(const char* env) {
 
 int bwd_vector_partials(const WsLayout& L);
 int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                     float* grad_bucket, int nvec_used, cudaStream_t st);
+                     float* grad_bucket, int nvec_used, int ncpart, cudaStream_t st);
 
 namespace {
 
@@ -219,7 +219,8 @@ inline int ew_grid(long long n, int block) { return (int)((n + block - 1) / bloc
 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
                        float* grad_bucket, cudaStream_t st) {
-  return mm_backward_impl(p, L, ws, g_kl, grad_bucket, bwd_vector_partials(L), st);
+  if (tc_point_supported(L)) return mm_backward_impl(p, L, ws, g_kl, grad_bucket, tc_vector_partials(L), L.splitsZ, st);
+  return mm_backward_impl(p, L, ws, g_kl, grad_bucket, bwd_vector_partials(L), 0, st);
 }
 
 }  // namespace gpblur
@@ -256,6 +257,7 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_mm_forward(*p, L, ws, kl, info, st);
   if (rc) return rc;
+  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
   return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
@@ -273,7 +275,10 @@ int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long 
   if (N == 0) {
     cudaMemsetAsync(ws_ptr<char>(ws, L.Spart), 0, L.total - L.Spart, st);
   } else {
-    rc = launch_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
+    if (tc_point_supported(L))
+      rc = launch_tc_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
+    else
+      rc = launch_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
     if (rc) return rc;
     rc = launch_reductions(L, ws, x, st);
     if (rc) return rc;

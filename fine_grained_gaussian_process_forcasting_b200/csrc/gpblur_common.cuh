@@ -48,8 +48,8 @@ struct WsLayout {
   int vec_len;              // floats per vector partial
   // byte offsets
   size_t hyp, hyp64, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
-  size_t K64, L64, Linv64, T64, U64, LinvT32, LC32;
-  size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64;
+  size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
+  size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64, rrow, cpart;
   size_t total;
 };
 
@@ -92,6 +92,8 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.U64 = take(MP * MP * 8);
   w.LinvT32 = take(MP * MP * 4);
   w.LC32 = take(MP * MP * 4);
+  w.Linv32 = take(MP * MP * 4);   // row-major Linv (tensor-core forward B operand)
+  w.LCT32 = take(MP * MP * 4);    // (diag(c) Linv)^T (tensor-core backward B operand)
   const int tp = w.MP < 128 ? w.MP : 128;
   const int nt = w.MP / tp;
   w.splitsS = choose_splits(N, nt * (nt + 1) / 2);
@@ -116,8 +118,10 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     w.gsc = take((size_t)2 * (N > 0 ? N : 1) * 4);   // folded upstream grads g_mu, g_var [N] each
     w.v64 = take((size_t)(3 * MP + w.vec_len) * 8);
     w.t64 = take((size_t)MP * DP * 8);
+    w.rrow = take((size_t)(N > 0 ? N : 1) * 4);           // row sums r[n] of W (tensor-core backward)
+    w.cpart = take((size_t)w.splitsZ * MP * 4);           // column sums of W per split (tensor-core W^T X)
   } else {
-    w.A = w.W = w.Spart = w.upart = w.WXpart = w.vecpart = w.gsc = w.v64 = w.t64 = o;
+    w.A = w.W = w.Spart = w.upart = w.WXpart = w.vecpart = w.gsc = w.v64 = w.t64 = w.rrow = w.cpart = o;
   }
   w.total = o;
   return w;
@@ -210,5 +214,13 @@ int launch_point_backward(const WsLayout& L, void* ws, const float* x, const flo
                           const float* g_var, const float* g_sample, const float* var, uint64_t seed,
                           uint64_t offset, uint32_t stream_id, float* dx, cudaStream_t st);
 int launch_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st);
+// tensor-core (tcgen05 3xTF32) variants; *_supported() decides per problem shape
+bool tc_point_supported(const WsLayout& L);
+int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
+                            uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st);
+int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const float* g_mean, const float* g_var,
+                             const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
+                             uint32_t stream_id, float* dx, cudaStream_t st);
+int tc_vector_partials(const WsLayout& L);
 
 }  // namespace gpblur

@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   double* T64 = ws_ptr<double>(a.ws, L.T64);
   float* LinvT32 = ws_ptr<float>(a.ws, L.LinvT32);
   float* LC32 = ws_ptr<float>(a.ws, L.LC32);
+  float* Linv32 = ws_ptr<float>(a.ws, L.Linv32);
+  float* LCT32 = ws_ptr<float>(a.ws, L.LCT32);
   const float* Z = a.p.inducing_points;
 
   // ---------------- phase 0: per-dimension hyper-parameters, centre, KL ----------------
@@ -390,11 +392,13 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       float v = 0.f;
       if (bi >= bj && gj <= gi) v = (float)As[r][lane];
       LC32[(size_t)gi * MP + gj] = v * cvec[gi];
+      Linv32[(size_t)gi * MP + gj] = v;
       // LinvT32 tile (bj, bi): element (r, lane) = Linv[bi*TB + lane][bj*TB + r]
       const int ti = bi * TB + lane, tj = bj * TB + r;
       float vt = 0.f;
       if (bi >= bj && tj <= ti) vt = (float)As[lane][r];
       LinvT32[(size_t)tj * MP + ti] = vt;
+      LCT32[(size_t)tj * MP + ti] = vt * cvec[ti];
     }
   }
   float* zn = ws_ptr<float>(a.ws, L.zn);
@@ -416,6 +420,7 @@ struct MmBwdArgs {
   const float* g_kl;
   float* bucket;
   int nvec_used;
+  int ncpart;   // > 0: column sums of W come as [ncpart][MP] partials from the tensor-core W^T X kernel
 };
 
 __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
@@ -466,9 +471,12 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     for (int sp = 0; sp < L.splitsS; ++sp) s += (double)upart[(size_t)sp * MP + m];
     u64[m] = s;
   }
+  const float* cpart = ws_cptr<float>(a.ws, L.cpart);
   for (int e = gtid; e < L.vec_len; e += gsize) {
     double s = 0.0;
     for (int c = 0; c < a.nvec_used; ++c) s += (double)vecpart[(size_t)c * L.vec_len + e];
+    if (a.ncpart > 0 && e < MP)
+      for (int c = 0; c < a.ncpart; ++c) s += (double)cpart[(size_t)c * MP + e];
     vec64[e] = s;
   }
   for (int idx = gtid; idx < MP * MP; idx += gsize) {
@@ -683,7 +691,7 @@ int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws,
                        float* grad_bucket, cudaStream_t st);
 
 int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                     float* grad_bucket, int nvec_used, cudaStream_t st) {
+                     float* grad_bucket, int nvec_used, int ncpart, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = sizeof(Tile) * 2;
   if (!attr_set) {
@@ -696,7 +704,7 @@ int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, c
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
-  MmBwdArgs args{p, L, ws, g_kl, grad_bucket, nvec_used};
+  MmBwdArgs args{p, L, ws, g_kl, grad_bucket, nvec_used, ncpart};
   void* kargs[] = {&args};
   ProfScope ps(ST_MM_BWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),

@@ -1,0 +1,694 @@
+// Per-point forward / backward of the whitened SVGP on the 5th-gen tensor cores (tcgen05, 3xTF32) for
+// padded inducing counts MP in {128, 256}.  One CTA owns a tile of 128 points = the M dimension of the MMA; the
+// accumulators live in TMEM (S = x~ z~^T in columns [0, MP), the whitened / back-substituted product in columns
+// [MP, 2 MP)); in every epilogue a thread owns ONE point (TMEM lane), so mean / variance / row sums need no
+// cross-thread reduction, and the exp()'d cross-covariance goes straight from TMEM registers into the next MMA's
+// shared-memory operand planes: it never touches HBM.
+//
+//   forward  : S = X~ Z~^T -> k = os exp(-1/2 d^2) -> A = k Linv^T (block-triangular: slab s only feeds columns
+//              >= 32 s) -> mean, var, sample; A saved for the backward.
+//   backward : S again, T = a (diag(c) Linv) (slabs in decreasing order so the first MMA initialises every column)
+//              -> kbar = g_mu beta + 2 g_var T, W = kbar o k, r = rowsum(W); W and r go to HBM once.
+//   dx       : dx = (W Z~ - r x~) / ell + g_mu w as a third small GEMM (N = Dp) + the per-dimension reductions.
+// Operand tiles are produced by all 256 threads (coalesced 16-byte loads, TF32 hi/lo split, canonical K-major
+// no-swizzle UMMA layout), one elected thread issues the MMAs, tcgen05.commit -> mbarrier tracks completion.
+#include "gpblur_tc.cuh"
+
+namespace gpblur {
+
+namespace {
+
+constexpr int KT = 32;
+constexpr int TNP = 128;   // points per tile (MMA M)
+
+struct TcPointArgs {
+  WsLayout L;
+  void* ws;
+  const float* x;
+  float* mean;
+  float* var;
+  float* sample;
+  const float* g_mean;
+  const float* g_var;
+  const float* g_sample;
+  const float* var_in;
+  float* dx;
+  uint64_t seed, offset;
+  uint32_t stream_id;
+  int ntiles;
+};
+
+template <int NB>   // NB = row capacity of the B operand planes
+struct Stage {
+  static constexpr int A_PLANE = (KT / 4) * TNP * 4;   // floats
+  static constexpr int B_PLANE = (KT / 4) * NB * 4;
+  static constexpr int FLOATS = 2 * A_PLANE + 2 * B_PLANE;
+};
+
+// two-stage operand ring + completion barriers
+template <int NB>
+struct Pipe {
+  float* base;
+  uint64_t* bars;
+  uint32_t uses[2];
+  int slab;
+  __device__ __forceinline__ void init(float* b, uint64_t* br) { base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; }
+  // wait until the MMAs that last read this stage are done, return its planes
+  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) {
+    const int st = slab & 1;
+    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+    a_hi = base + st * Stage<NB>::FLOATS;
+    a_lo = a_hi + Stage<NB>::A_PLANE;
+    b_hi = a_lo + Stage<NB>::A_PLANE;
+    b_lo = b_hi + Stage<NB>::B_PLANE;
+  }
+  // publish the stage to the tensor core and issue N-column MMAs into tmem_d
+  __device__ __forceinline__ void commit(uint32_t tmem_d, int ncols, bool first) {
+    const int st = slab & 1;
+    tc::fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::tc_fence_after();
+      float* a_hi = base + st * Stage<NB>::FLOATS;
+      float* a_lo = a_hi + Stage<NB>::A_PLANE;
+      float* b_hi = a_lo + Stage<NB>::A_PLANE;
+      float* b_lo = b_hi + Stage<NB>::B_PLANE;
+      tc::issue_slab_3xtf32<KT, NB>(tmem_d, a_hi, a_lo, b_hi, b_lo, tc::make_idesc_tf32(TNP, ncols), first);
+      tc::umma_commit(&bars[st]);
+    }
+    uses[st] += 1;
+    slab += 1;
+  }
+  // block until every MMA issued so far has completed
+  __device__ __forceinline__ void drain() {
+    if (slab == 0) return;
+    const int st = (slab - 1) & 1;
+    tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+    tc::tc_fence_after();
+  }
+};
+
+// Produce `nrows` (multiple of 8) rows x 32 k of a K-major operand slab from a row-major source:
+// load4(row, chunk) returns the 4 values k = 4 chunk .. 4 chunk + 3 of `row`.  A warp covers 8 rows x 4 chunks per
+// pass (64 contiguous bytes per row), stores are conflict-free (8 consecutive rows per quarter warp).
+template <int PLANE_ROWS, class F>
+__device__ __forceinline__ void produce_kmajor(float* hi, float* lo, int nrows, F&& load4) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rr = lane & 7, cq = lane >> 3;
+  const int ntiles = (nrows >> 3) * 2;   // warp tiles: (8-row block, 4-chunk group)
+  for (int wt = warp; wt < ntiles; wt += kThreads / 32) {
+    const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
+    const float4 v = load4(row, c);
+    tc::store_split(hi, lo, tc::op_off<PLANE_ROWS>(row, c), v);
+  }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// x tile row (point) -> centred / scaled float4 of k-chunk `dchunk`
+struct XLoader {
+  const float* x; long long n0, N; int D; const float* center; const float* inv_ell; bool vec;
+  __device__ __forceinline__ float4 operator()(int row, int dchunk) const {
+    const long long gn = n0 + row;
+    const int d = dchunk * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gn < N && d < D) {
+      const float* r = x + (size_t)gn * D;
+      if (vec) v = ldg4(r + d);
+      else {
+        v.x = r[d];
+        if (d + 1 < D) v.y = r[d + 1];
+        if (d + 2 < D) v.z = r[d + 2];
+        if (d + 3 < D) v.w = r[d + 3];
+      }
+      const float4 c = ldg4(center + d), ie = ldg4(inv_ell + d);
+      v.x = (v.x - c.x) * ie.x; v.y = (v.y - c.y) * ie.y; v.z = (v.z - c.z) * ie.z; v.w = (v.w - c.w) * ie.w;
+    }
+    return v;
+  }
+};
+
+__device__ __forceinline__ XLoader make_xloader(const TcPointArgs& a, long long n0) {
+  const WsLayout& L = a.L;
+  return XLoader{a.x, n0, L.N, L.D, ws_cptr<float>(a.ws, L.center), ws_cptr<float>(a.ws, L.inv_ell),
+                 (L.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0)};
+}
+
+// per-row |x~|^2 and linear mean x~ . (ell w): one thread per point of the tile (threads 0..127)
+__device__ __forceinline__ void row_stats(const TcPointArgs& a, const XLoader& xl, float* xn_s, float* xw_s) {
+  if (threadIdx.x < TNP) {
+    const float* wl = ws_cptr<float>(a.ws, a.L.wl);
+    float n2 = 0.f, xw = 0.f;
+    for (int dc = 0; dc * 4 < a.L.DP; ++dc) {
+      const float4 v = xl(threadIdx.x, dc);
+      const float4 w4 = ldg4(wl + dc * 4);
+      n2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      xw += v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+    }
+    xn_s[threadIdx.x] = n2;
+    xw_s[threadIdx.x] = xw;
+  }
+}
+
+// phase A of both kernels: S[128, MP] = X~ Z~^T into TMEM columns [0, MP)
+template <int MP>
+__device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl) {
+  const WsLayout& L = a.L;
+  const float* Zt = ws_cptr<float>(a.ws, L.Zt);
+  const int DP = L.DP;
+  const int nds = DP >= KT ? DP / KT : 1;
+  for (int ds = 0; ds < nds; ++ds) {
+    float *a_hi, *a_lo, *b_hi, *b_lo;
+    pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+    produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int row, int c) {
+      const int dchunk = ds * (KT / 4) + c;
+      return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    produce_kmajor<MP>(b_hi, b_lo, MP, [&](int row, int c) {
+      const int d = ds * KT + c * 4;
+      return d < DP ? ldg4(Zt + (size_t)row * DP + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    pipe.commit(tmem_s, MP, ds == 0);
+  }
+}
+
+// cross-covariance values of one 32-column chunk from the S accumulators: k = os exp(-1/2 max(|x|^2 + |z|^2 - 2 s, 0))
+__device__ __forceinline__ void kernel_values(float (&v)[32], float xn, const float* zn_s, int col0, int M, float os) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int m = col0 + i;
+    const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
+    v[i] = (m < M) ? os * expf(-0.5f * d2) : 0.f;
+  }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int MP>
+__global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float zn_s[MP], m_s[MP], c_s[MP];
+  __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
+
+  const WsLayout& L = a.L;
+  const int M = L.M;
+  const long long N = L.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
+  const float* Linv = ws_cptr<float>(a.ws, L.Linv32);
+  float* Ag = ws_ptr<float>(a.ws, L.A);
+  const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
+
+  constexpr uint32_t TMEM_COLS = 2 * MP;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < MP; i += kThreads) {
+    zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+    m_s[i] = ws_cptr<float>(a.ws, L.mvec)[i];
+    c_s[i] = ws_cptr<float>(a.ws, L.cvec)[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + MP;
+  Pipe<MP> pipe;
+  pipe.init(stage_base, bars);
+
+  const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
+  const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const long long n0 = (long long)tile * TNP;
+    const XLoader xl = make_xloader(a, n0);
+    row_stats(a, xl, xn_s, xw_s);
+    phase_a<MP>(pipe, tmem_s, a, xl);
+    pipe.drain();                                   // S complete (also makes xn_s visible: commit() synchronised)
+    const float xn = xn_s[row];
+
+    // ---- phase B: A[:, i >= 32 s] += k[:, slab s] Linv[i, slab s]^T ----
+    for (int s = 0; s < MP / KT; ++s) {
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      {
+        // epilogue A of this 32-column chunk: the two column halves of a lane quadrant take 16 columns each
+        float v[32];
+        tc::tmem_ld32(tmem_s + lane_base + (uint32_t)(s * KT), v);
+        kernel_values(v, xn, zn_s, s * KT, M, os);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cc = half * 4 + c;              // k-chunk of the slab written by this thread
+          tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, cc),
+                          make_float4(v[cc * 4 + 0], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
+        }
+      }
+      const int i0 = s * KT;                        // only rows i >= 32 s of Linv see this slab (lower triangular)
+      produce_kmajor<MP>(b_hi, b_lo, MP - i0, [&](int r, int c) {
+        return ldg4(Linv + (size_t)(i0 + r) * MP + i0 + c * 4);
+      });
+      tc::tc_fence_before();
+      pipe.commit(tmem_a + i0, MP - i0, s == 0);
+    }
+    pipe.drain();
+
+    // ---- epilogue B: mean / variance of the own point from its half of the columns; save A ----
+    float mu = 0.f, vv = 0.f;
+    const long long gn = n0 + row;
+#pragma unroll 1
+    for (int ch = 0; ch < MP / 64; ++ch) {
+      const int col = half * (MP / 2) + ch * 32;
+      float v[32];
+      tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mu = fmaf(v[i], m_s[col + i], mu);
+        vv = fmaf(c_s[col + i] * v[i], v[i], vv);
+      }
+      if (L.training && gn < N) {
+        float* dst = Ag + (size_t)gn * MP + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+    if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (half == 0 && gn < N) {
+      const float mean = mu + mu_s[row] + xw_s[row] + cwb;
+      const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
+      a.mean[gn] = mean;
+      a.var[gn] = var;
+      if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
+    }
+    __syncthreads();
+    tc::tc_fence_after();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
+}
+
+// =================================================================================================
+// backward: W = kbar o k and its row sums
+// =================================================================================================
+template <int MP>
+__global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float zn_s[MP], beta_s[MP];
+  __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
+
+  const WsLayout& L = a.L;
+  const int M = L.M;
+  const long long N = L.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
+  const float* LCT = ws_cptr<float>(a.ws, L.LCT32);
+  const float* Ag = ws_cptr<float>(a.ws, L.A);
+  float* Wg = ws_ptr<float>(a.ws, L.W);
+  float* gsc = ws_ptr<float>(a.ws, L.gsc);
+  float* rrow = ws_ptr<float>(a.ws, L.rrow);
+  const float os = hyp[H_OS];
+
+  constexpr uint32_t TMEM_COLS = 2 * MP;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < MP; i += kThreads) {
+    zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+    beta_s[i] = ws_cptr<float>(a.ws, L.beta)[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + MP;
+  Pipe<MP> pipe;
+  pipe.init(stage_base, bars);
+
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const long long n0 = (long long)tile * TNP;
+    const XLoader xl = make_xloader(a, n0);
+    row_stats(a, xl, xn_s, xw_s);
+    phase_a<MP>(pipe, tmem_s, a, xl);
+
+    // ---- phase B': T[:, j < 32 (s + 1)] += a[:, slab s] (diag(c) Linv)[slab s, j], slabs in DEcreasing order ----
+    for (int s = MP / KT - 1; s >= 0; --s) {
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      const int i0 = s * KT;
+      produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int r, int c) {
+        long long gn = n0 + r;
+        if (gn >= N) gn = N - 1;                       // clamped rows carry g = 0 below
+        return ldg4(Ag + (size_t)gn * MP + i0 + c * 4);
+      });
+      produce_kmajor<MP>(b_hi, b_lo, i0 + KT, [&](int r, int c) {
+        return ldg4(LCT + (size_t)r * MP + i0 + c * 4);
+      });
+      pipe.commit(tmem_t, i0 + KT, s == MP / KT - 1);
+    }
+    pipe.drain();
+
+    // ---- fold the upstream gradients of this thread's point ----
+    const long long gn = n0 + row;
+    float gm = 0.f, gv = 0.f;
+    if (gn < N) {
+      if (a.g_mean) gm = a.g_mean[gn];
+      if (a.g_var) gv = a.g_var[gn];
+      const float v = a.var_in[gn];
+      if (a.g_sample) {
+        const float gs = a.g_sample[gn];
+        const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
+        gm += gs;
+        gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
+      }
+      if (v <= kMinVariance) gv = 0.f;
+      if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
+    }
+    const float xn = xn_s[row];
+    float rsum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < MP / 64; ++ch) {
+      const int col = half * (MP / 2) + ch * 32;
+      float k[32], t[32];
+      tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
+      tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
+      kernel_values(k, xn, zn_s, col, M, os);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[col + i]);
+        t[i] = kb * k[i];
+        rsum += t[i];
+      }
+      if (gn < N) {
+        float* dst = Wg + (size_t)gn * MP + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+      }
+    }
+    if (half == 1) r_s[row] = rsum;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
+    __syncthreads();
+    tc::tc_fence_after();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
+}
+
+// =================================================================================================
+// dx = (W Z~ - r x~) / ell + g_mu w  and the per-dimension reductions q, wbar + scalar sums
+// =================================================================================================
+template <int DPT>   // DPT = MMA N = padded input dim (32, 64 or 128)
+__global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[8][32][33];
+  __shared__ float part_q[8][32], part_t[8][32], part_sc[8][4];
+  __shared__ float q_s[DPT], t1_s[DPT], sc_s[4];
+
+  const WsLayout& L = a.L;
+  const int D = L.D, DP = L.DP, MP = L.MP;
+  const long long N = L.N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
+  const float* ellv = ws_cptr<float>(a.ws, L.ell);
+  const float* center = ws_cptr<float>(a.ws, L.center);
+  const float* wl = ws_cptr<float>(a.ws, L.wl);
+  const float* ZtT = ws_cptr<float>(a.ws, L.ZtT);
+  const float* Wg = ws_cptr<float>(a.ws, L.W);
+  const float* gsc = ws_cptr<float>(a.ws, L.gsc);
+  const float* rrow = ws_cptr<float>(a.ws, L.rrow);
+  float* vecpart = ws_ptr<float>(a.ws, L.vecpart);
+
+  constexpr uint32_t TMEM_COLS = DPT;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
+  if (tid < 4) sc_s[tid] = 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  Pipe<DPT> pipe;
+  pipe.init(stage_base, bars);
+
+  // epilogue mapping: the 8 warps cover 4 lane quadrants x 2 column halves of the [128, DPT] tile; with DPT = 32
+  // only the first 4 warps have columns.
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+  constexpr int CH_PER_HALF = DPT >= 64 ? DPT / 64 : 1;
+  const bool has_cols = DPT >= 64 || half == 0;
+  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a.dx) & 15) == 0);
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const long long n0 = (long long)tile * TNP;
+    for (int s = 0; s < MP / KT; ++s) {
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      const int m0 = s * KT;
+      produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int r, int c) {
+        const long long gn = n0 + r;
+        return gn < N ? ldg4(Wg + (size_t)gn * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      });
+      produce_kmajor<DPT>(b_hi, b_lo, DPT, [&](int r, int c) {
+        return r < DP ? ldg4(ZtT + (size_t)r * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      });
+      pipe.commit(tmem_d, DPT, s == 0);
+    }
+    pipe.drain();
+
+    const long long gn = n0 + row;
+    const bool live = gn < N;
+    const float r = live ? rrow[gn] : 0.f;
+    const float gm = live ? gsc[gn] : 0.f;
+    const float gv = live ? gsc[N + gn] : 0.f;
+    if (has_cols) {
+#pragma unroll 1
+      for (int ch = 0; ch < CH_PER_HALF; ++ch) {
+        const int col = (DPT >= 64 ? half * (DPT / 2) : 0) + ch * 32;
+        float v[32];
+        tc::tmem_ld32(tmem_d + lane_base + (uint32_t)col, v);
+        float xs[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int d = col + i;
+          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && d < D) {
+            const float* xr = a.x + (size_t)gn * D;
+            if (vec) xv = ldg4(xr + d);
+            else {
+              xv.x = xr[d];
+              if (d + 1 < D) xv.y = xr[d + 1];
+              if (d + 2 < D) xv.z = xr[d + 2];
+              if (d + 3 < D) xv.w = xr[d + 3];
+            }
+          }
+          const float4 c4 = d < DP ? ldg4(center + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 ie = d < DP ? ldg4(inv_ell + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xs[i + 0] = (xv.x - c4.x) * ie.x; xs[i + 1] = (xv.y - c4.y) * ie.y;
+          xs[i + 2] = (xv.z - c4.z) * ie.z; xs[i + 3] = (xv.w - c4.w) * ie.w;
+        }
+        // dx
+        if (a.dx && live) {
+          float* dst = a.dx + (size_t)gn * D + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int d = col + i;
+            if (d < D) {
+              const float4 ie = ldg4(inv_ell + d), w4 = ldg4(wl + d);
+              float4 o;
+              o.x = (v[i + 0] - r * xs[i + 0]) * ie.x + gm * (w4.x * ie.x);
+              o.y = (v[i + 1] - r * xs[i + 1]) * ie.y + gm * (w4.y * ie.y);
+              o.z = (v[i + 2] - r * xs[i + 2]) * ie.z + gm * (w4.z * ie.z);
+              o.w = (v[i + 3] - r * xs[i + 3]) * ie.w + gm * (w4.w * ie.w);
+              if (vec) *reinterpret_cast<float4*>(dst + i) = o;
+              else {
+                dst[i] = o.x;
+                if (d + 1 < D) dst[i + 1] = o.y;
+                if (d + 2 < D) dst[i + 2] = o.z;
+                if (d + 3 < D) dst[i + 3] = o.w;
+              }
+            }
+          }
+        }
+        // per-dimension reductions over the 32 points of this warp: q_d = sum r x~^2, t1_d = sum g_mu x~
+#pragma unroll
+        for (int i = 0; i < 32; ++i) red[warp][lane][i] = live ? r * xs[i] * xs[i] : 0.f;
+        __syncwarp();
+        float sq = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) sq += red[warp][rr][lane];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) red[warp][lane][i] = live ? gm * xs[i] : 0.f;
+        __syncwarp();
+        float st = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) st += red[warp][rr][lane];
+        __syncwarp();
+        // this warp's partial for dimension col + lane; (quad, half, ch) -> combined below in fixed order
+        if (CH_PER_HALF == 1) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
+        else {
+          // DPT = 128: two chunks per half; accumulate the second chunk into a second slot of the same warp
+          if (ch == 0) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
+          else { red[warp][0][lane] = sq; red[warp][1][lane] = st; }
+        }
+      }
+    }
+    {
+      const float sg = warp_sum(live && half == 0 ? gm : 0.f);
+      const float sr = warp_sum(live && half == 0 ? r : 0.f);
+      const float sv = warp_sum(live && half == 0 ? gv : 0.f);
+      if (lane == 0) { part_sc[warp][VS_GMU] = sg; part_sc[warp][VS_RSUM] = sr; part_sc[warp][VS_GVAR] = sv; }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // combine the 4 lane quadrants in fixed order: dimension d = half * (DPT / 2) + ch * 32 + lane
+    if (tid < DPT) {
+      const int d = tid;
+      const int hf = DPT >= 64 ? d / (DPT / 2) : 0;
+      const int within = DPT >= 64 ? d % (DPT / 2) : d;
+      const int ch = within / 32, ln = within % 32;
+      float sq = 0.f, st = 0.f;
+      for (int qd = 0; qd < 4; ++qd) {
+        const int w = hf * 4 + qd;
+        if (ch == 0) { sq += part_q[w][ln]; st += part_t[w][ln]; }
+        else { sq += red[w][0][ln]; st += red[w][1][ln]; }
+      }
+      q_s[d] += sq;
+      t1_s[d] += st;
+    }
+    if (tid < 3) {
+      float s = 0.f;
+      for (int w = 0; w < 4; ++w) s += part_sc[w][tid];
+      sc_s[tid] += s;
+    }
+    __syncthreads();
+    tc::tc_fence_after();
+  }
+  __syncthreads();
+  float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
+  for (int i = tid; i < MP; i += kThreads) vp[i] = 0.f;          // column sums come from the W^T X kernel
+  for (int d = tid; d < DP; d += kThreads) {
+    vp[MP + d] = d < DPT ? q_s[d] : 0.f;
+    vp[MP + DP + d] = (d < D && d < DPT) ? ellv[d] * t1_s[d] + center[d] * sc_s[VS_GMU] : 0.f;
+  }
+  if (tid < VS_COUNT) vp[MP + 2 * DP + tid] = tid < 3 ? sc_s[tid] : 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
+}
+
+template <int NB>
+constexpr size_t tc_smem_bytes() { return (size_t)2 * Stage<NB>::FLOATS * 4 + 1024; }
+
+int tc_grid(const WsLayout& L) {
+  const long long nt = (L.N + TNP - 1) / TNP;
+  const int sms = num_sms();
+  return (int)(nt < sms ? (nt < 1 ? 1 : nt) : sms);
+}
+
+template <class K>
+void set_smem(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+bool tc_point_supported(const WsLayout& L) {
+  if (tile_override("GPBLUR_TC") < 0) return false;       // GPBLUR_TC=-1 forces the FP32 FFMA kernels
+  return (L.MP == 128 || L.MP == 256) && L.N >= 1;
+}
+
+int tc_vector_partials(const WsLayout& L) { return tc_grid(L); }
+
+int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
+                            uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
+  TcPointArgs a{};
+  a.L = L; a.ws = ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
+  a.seed = seed; a.offset = offset; a.stream_id = stream_id;
+  a.ntiles = (int)((L.N + TNP - 1) / TNP);
+  const int grid = tc_grid(L);
+  ProfScope ps(ST_POINT_FWD, st);
+  if (L.MP == 128) {
+    static bool cfg = false;
+    if (!cfg) { set_smem(tc_point_fwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
+    tc_point_fwd_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { set_smem(tc_point_fwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
+    tc_point_fwd_kernel<256><<<grid, kThreads, tc_smem_bytes<256>(), st>>>(a);
+  }
+  note_launch();
+  return check_launch("tc_point_fwd");
+}
+
+int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const float* g_mean, const float* g_var,
+                             const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
+                             uint32_t stream_id, float* dx, cudaStream_t st) {
+  TcPointArgs a{};
+  a.L = L; a.ws = ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
+  a.seed = seed; a.offset = offset; a.stream_id = stream_id;
+  a.ntiles = (int)((L.N + TNP - 1) / TNP);
+  const int grid = tc_grid(L);
+  {
+    ProfScope ps(ST_POINT_BWD, st);
+    if (L.MP == 128) {
+      static bool cfg = false;
+      if (!cfg) { set_smem(tc_point_bwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
+      tc_point_bwd_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+    } else {
+      static bool cfg = false;
+      if (!cfg) { set_smem(tc_point_bwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
+      tc_point_bwd_kernel<256><<<grid, kThreads, tc_smem_bytes<256>(), st>>>(a);
+    }
+    note_launch();
+    int rc = check_launch("tc_point_bwd");
+    if (rc) return rc;
+  }
+  ProfScope ps(ST_OTHER, st);
+  if (L.DP <= 32) {
+    static bool cfg = false;
+    if (!cfg) { set_smem(tc_dx_kernel<32>, tc_smem_bytes<32>()); cfg = true; }
+    tc_dx_kernel<32><<<grid, kThreads, tc_smem_bytes<32>(), st>>>(a);
+  } else if (L.DP == 64) {
+    static bool cfg = false;
+    if (!cfg) { set_smem(tc_dx_kernel<64>, tc_smem_bytes<64>()); cfg = true; }
+    tc_dx_kernel<64><<<grid, kThreads, tc_smem_bytes<64>(), st>>>(a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { set_smem(tc_dx_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
+    tc_dx_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+  }
+  note_launch();
+  return check_launch("tc_dx");
+}
+
+}  // namespace gpblur

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
     if (tid < KT) {
       const long long n = r0 + (long long)s * KT + tid;
       scs[s & 1][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
-      if (GRAM) gms[s & 1][tid] = (n < r1) ? a.gm[n] : 0.f;
+      gms[s & 1][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
     }
   };
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
     for (int i = 0; i < 4; ++i) {
       const int c = acg + 2 * i;
       tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), areg[i]);
-      if (GRAM) {
+      {
         usum = fmaf(gms[st][4 * c + 0], areg[i].x, usum);
         usum = fmaf(gms[st][4 * c + 1], areg[i].y, usum);
         usum = fmaf(gms[st][4 * c + 2], areg[i].z, usum);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
         if (col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
   }
-  if (GRAM) {
+  if (a.uvec) {
     ured[acg][ar] = usum;
     __syncthreads();
     if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
@@ -208,11 +208,7 @@ int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t
 
 }  // namespace
 
-bool tc_reductions_supported(const WsLayout& L) {
-  const int off = tile_override("GPBLUR_TC");   // GPBLUR_TC=-1 disables the tensor-core path
-  if (off < 0) return false;
-  return (L.MP == 128 || L.MP == 256) && (L.DP == 64 || L.DP == 32 || L.DP == 128 || L.DP == 16) && L.N >= 1;
-}
+bool tc_reductions_supported(const WsLayout& L) { return tc_point_supported(L); }
 
 int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream_t st) {
   const int MP = L.MP;
@@ -231,7 +227,7 @@ int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream
   if (rc) return rc;
   TcReduceArgs w{};
   w.U = ws_cptr<float>(ws, L.W); w.V = x; w.sc = nullptr; w.gm = nullptr;
-  w.C = ws_ptr<float>(ws, L.WXpart); w.uvec = nullptr;
+  w.C = ws_ptr<float>(ws, L.WXpart); w.uvec = ws_ptr<float>(ws, L.cpart);   // + column sums of W
   w.N = L.N; w.ldu = MP; w.ldv = L.D; w.vcols = L.D; w.P = MP; w.ldc = L.DP;
   w.rows_per_split = rows(L.splitsZ);
   const int pt = MP / 128;
