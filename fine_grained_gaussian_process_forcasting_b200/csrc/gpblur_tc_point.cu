@@ -88,18 +88,38 @@ struct Pipe {
   }
 };
 
-// Produce `nrows` (multiple of 8) rows x 32 k of a K-major operand slab from a row-major source:
-// load4(row, chunk) returns the 4 values k = 4 chunk .. 4 chunk + 3 of `row`.  A warp covers 8 rows x 4 chunks per
-// pass (64 contiguous bytes per row), stores are conflict-free (8 consecutive rows per quarter warp).
+// A [rows x 32 k] K-major operand slab is produced in two steps so that every global load of a slab is in flight
+// before the first one is consumed: load_kmajor() fills registers (load4(row, chunk) returns the 4 values
+// k = 4 chunk .. 4 chunk + 3 of `row`), store_kmajor() splits them into the TF32 hi / lo planes.  A warp covers
+// 8 rows x 4 chunks per pass (64 contiguous bytes per row); stores are conflict-free (8 consecutive rows per
+// quarter warp).  `nrows` is a runtime multiple of 8, PLANE_ROWS the plane capacity.
+template <int PLANE_ROWS>
+struct OpRegs {
+  static constexpr int PASSES = (PLANE_ROWS / 8 * 2 + 7) / 8;
+  float4 v[PASSES];
+};
+
 template <int PLANE_ROWS, class F>
-__device__ __forceinline__ void produce_kmajor(float* hi, float* lo, int nrows, F&& load4) {
+__device__ __forceinline__ void load_kmajor(OpRegs<PLANE_ROWS>& regs, int nrows, F&& load4) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rr = lane & 7, cq = lane >> 3;
   const int ntiles = (nrows >> 3) * 2;   // warp tiles: (8-row block, 4-chunk group)
-  for (int wt = warp; wt < ntiles; wt += kThreads / 32) {
-    const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
-    const float4 v = load4(row, c);
-    tc::store_split(hi, lo, tc::op_off<PLANE_ROWS>(row, c), v);
+#pragma unroll
+  for (int p = 0; p < OpRegs<PLANE_ROWS>::PASSES; ++p) {
+    const int wt = warp + 8 * p;
+    if (wt < ntiles) regs.v[p] = load4((wt >> 1) * 8 + rr, (wt & 1) * 4 + cq);
+  }
+}
+
+template <int PLANE_ROWS>
+__device__ __forceinline__ void store_kmajor(float* hi, float* lo, const OpRegs<PLANE_ROWS>& regs, int nrows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rr = lane & 7, cq = lane >> 3;
+  const int ntiles = (nrows >> 3) * 2;
+#pragma unroll
+  for (int p = 0; p < OpRegs<PLANE_ROWS>::PASSES; ++p) {
+    const int wt = warp + 8 * p;
+    if (wt < ntiles) tc::store_split(hi, lo, tc::op_off<PLANE_ROWS>((wt >> 1) * 8 + rr, (wt & 1) * 4 + cq), regs.v[p]);
   }
 }
 
@@ -158,16 +178,20 @@ __device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const T
   const int DP = L.DP;
   const int nds = DP >= KT ? DP / KT : 1;
   for (int ds = 0; ds < nds; ++ds) {
-    float *a_hi, *a_lo, *b_hi, *b_lo;
-    pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-    produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int row, int c) {
+    OpRegs<TNP> ra;
+    OpRegs<MP> rb;
+    load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
       const int dchunk = ds * (KT / 4) + c;
       return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
     });
-    produce_kmajor<MP>(b_hi, b_lo, MP, [&](int row, int c) {
+    load_kmajor<MP>(rb, MP, [&](int row, int c) {
       const int d = ds * KT + c * 4;
       return d < DP ? ldg4(Zt + (size_t)row * DP + d) : make_float4(0.f, 0.f, 0.f, 0.f);
     });
+    float *a_hi, *a_lo, *b_hi, *b_lo;
+    pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+    store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+    store_kmajor<MP>(b_hi, b_lo, rb, MP);
     pipe.commit(tmem_s, MP, ds == 0);
   }
 }
@@ -236,24 +260,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
 
     // ---- phase B: A[:, i >= 32 s] += k[:, slab s] Linv[i, slab s]^T ----
     for (int s = 0; s < MP / KT; ++s) {
+      const int i0 = s * KT;                        // only rows i >= 32 s of Linv see this slab (lower triangular)
+      OpRegs<MP> rb;
+      load_kmajor<MP>(rb, MP - i0, [&](int r, int c) { return ldg4(Linv + (size_t)(i0 + r) * MP + i0 + c * 4); });
       float *a_hi, *a_lo, *b_hi, *b_lo;
       pipe.acquire(a_hi, a_lo, b_hi, b_lo);
       {
         // epilogue A of this 32-column chunk: the two column halves of a lane quadrant take 16 columns each
-        float v[32];
-        tc::tmem_ld32(tmem_s + lane_base + (uint32_t)(s * KT), v);
-        kernel_values(v, xn, zn_s, s * KT, M, os);
+        float v[16];
+        const int col0 = s * KT + half * 16;
+        tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int cc = half * 4 + c;              // k-chunk of the slab written by this thread
-          tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, cc),
-                          make_float4(v[cc * 4 + 0], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
+        for (int i = 0; i < 16; ++i) {
+          const int m = col0 + i;
+          const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
+          v[i] = (m < M) ? os * expf(-0.5f * d2) : 0.f;
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)                 // k-chunks half * 4 + c of the slab
+          tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
+                          make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
       }
-      const int i0 = s * KT;                        // only rows i >= 32 s of Linv see this slab (lower triangular)
-      produce_kmajor<MP>(b_hi, b_lo, MP - i0, [&](int r, int c) {
-        return ldg4(Linv + (size_t)(i0 + r) * MP + i0 + c * 4);
-      });
+      store_kmajor<MP>(b_hi, b_lo, rb, MP - i0);
       tc::tc_fence_before();
       pipe.commit(tmem_a + i0, MP - i0, s == 0);
     }
@@ -350,17 +378,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
 
     // ---- phase B': T[:, j < 32 (s + 1)] += a[:, slab s] (diag(c) Linv)[slab s, j], slabs in DEcreasing order ----
     for (int s = MP / KT - 1; s >= 0; --s) {
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
       const int i0 = s * KT;
-      produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int r, int c) {
+      OpRegs<TNP> ra;
+      OpRegs<MP> rb;
+      load_kmajor<TNP>(ra, TNP, [&](int r, int c) {
         long long gn = n0 + r;
         if (gn >= N) gn = N - 1;                       // clamped rows carry g = 0 below
         return ldg4(Ag + (size_t)gn * MP + i0 + c * 4);
       });
-      produce_kmajor<MP>(b_hi, b_lo, i0 + KT, [&](int r, int c) {
-        return ldg4(LCT + (size_t)r * MP + i0 + c * 4);
-      });
+      load_kmajor<MP>(rb, i0 + KT, [&](int r, int c) { return ldg4(LCT + (size_t)r * MP + i0 + c * 4); });
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+      store_kmajor<MP>(b_hi, b_lo, rb, i0 + KT);
       pipe.commit(tmem_t, i0 + KT, s == MP / KT - 1);
     }
     pipe.drain();
@@ -470,16 +500,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
     for (int s = 0; s < MP / KT; ++s) {
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
       const int m0 = s * KT;
-      produce_kmajor<TNP>(a_hi, a_lo, TNP, [&](int r, int c) {
+      OpRegs<TNP> ra;
+      OpRegs<DPT> rb;
+      load_kmajor<TNP>(ra, TNP, [&](int r, int c) {
         const long long gn = n0 + r;
         return gn < N ? ldg4(Wg + (size_t)gn * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
-      produce_kmajor<DPT>(b_hi, b_lo, DPT, [&](int r, int c) {
+      load_kmajor<DPT>(rb, DPT, [&](int r, int c) {
         return r < DP ? ldg4(ZtT + (size_t)r * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+      store_kmajor<DPT>(b_hi, b_lo, rb, DPT);
       pipe.commit(tmem_d, DPT, s == 0);
     }
     pipe.drain();
