@@ -277,6 +277,7 @@ def run_ours(args, wl, name):
 
     def step(i, xin, yin):
         bucket.zero()
+        hl.invalidate_param_stage()     # a real training step changes the parameters: recompute Kzz / Cholesky once
         outs, grads = [], []
         elbo = None
         for c, L in enumerate(calls):

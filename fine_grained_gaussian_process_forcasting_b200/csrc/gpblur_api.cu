@@ -261,6 +261,35 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
   return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
+size_t gpblur_svgp_param_stage_bytes(int D, int M) {
+  if (D < 1 || M < 1 || D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return 0;
+  return make_layout(0, D, M, 0).total;   // the inference layout is exactly the parameter stage
+}
+
+int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long long N, int D, int M, float* mean,
+                               float* var, float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                               float* kl, int* info, int training, void* ws, size_t ws_bytes,
+                               const void* param_stage, void* stream) {
+  if (!param_stage)
+    return gpblur_svgp_forward(p, x, N, D, M, mean, var, sample, seed, offset, stream_id, kl, info, training, ws,
+                               ws_bytes, stream);
+  int rc = validate(p, N, D, M);
+  if (rc) return rc;
+  if (N > 0 && (!x || !mean || !var)) return GPBLUR_EINVAL;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(N, D, M, training ? 1 : 0);
+  if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pbytes = make_layout(0, D, M, 0).total;
+  cudaMemcpyAsync(ws, param_stage, pbytes, cudaMemcpyDeviceToDevice, st);
+  if (kl) cudaMemcpyAsync(kl, ws_cptr<float>(param_stage, L.hyp) + H_KL, sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+  rc = check_launch("param_stage_copy");
+  if (rc) return rc;
+  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+}
+
 int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
                          const float* g_mean, const float* g_var, const float* g_sample, const float* g_kl,
                          const float* var, uint64_t seed, uint64_t offset, uint32_t stream_id, float* dx,

@@ -462,10 +462,17 @@ class DeepGPLayer(ApproximateGP):
         self._rng_stream = 0
         self.fused_sample = True
         self.last_info = None
+        self.share_param_stage = True      # reuse Kzz / Cholesky / Linv between calls with unchanged parameters
+        self._stage_caches = {}
 
     # ---- RNG counters of the fused sampler (Philox key = seed, counter = (offset + point, stream)) ----
     def set_rng(self, seed: int, offset: int = 0, stream: int = 0):
         self._rng_seed, self._rng_offset, self._rng_stream = int(seed), int(offset), int(stream)
+
+    def invalidate_param_stage(self):
+        """Drop the cached M x M stage (parameters are also tracked by tensor version, so an optimizer step
+        invalidates it automatically; benchmarks that never step call this to stay honest)."""
+        self._stage_caches = {}
 
     def _next_counters(self, n: int):
         seed, off, stream = self._rng_seed, self._rng_offset, self._rng_stream
@@ -522,8 +529,9 @@ class DeepGPLayer(ApproximateGP):
         for h in ([None] if H is None else range(H)):
             Z, raw_ell, raw_os, m, s, w, b = self._layer_params(h)
             seed, off, stream = self._next_counters(n_pts) if self.fused_sample else (0, 0, 0)
+            cache = self._stage_caches.setdefault(h, {}) if self.share_param_stage else None
             mean, var, sample, kl, info = ops.svgp_predict(inputs, Z, raw_ell, raw_os, m, s, w, b, seed, off, stream,
-                                                           want_sample=self.fused_sample)
+                                                           want_sample=self.fused_sample, stage_cache=cache)
             self.last_info = info
             means.append(mean); vars_.append(var); samples.append(sample); kls.append(kl)
         if check_cholesky.value():

@@ -59,10 +59,16 @@ def workspace_bytes(N: int, D: int, M: int, training: bool) -> int:
 # ------------------------------------------------------------------------------------------------
 # raw calls
 # ------------------------------------------------------------------------------------------------
+def param_stage_bytes(D: int, M: int) -> int:
+    return int(_cabi.lib().gpblur_svgp_param_stage_bytes(D, M))
+
+
 def svgp_forward_raw(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: Tensor, s: Tensor,
                      w: Optional[Tensor], b: Tensor, seed: int, offset: int, stream_id: int,
-                     want_sample: bool, training: bool):
-    """x [N, D] -> (mean [N], var [N], sample [N] | None, kl [1], info [1] int32, workspace uint8)."""
+                     want_sample: bool, training: bool, param_stage: Optional[Tensor] = None):
+    """x [N, D] -> (mean [N], var [N], sample [N] | None, kl [1], info [1] int32, workspace uint8).
+    `param_stage`: the leading param_stage_bytes(D, M) bytes of the workspace of an earlier forward with the same
+    parameter values; if given, the M x M stage is copied instead of recomputed."""
     _need_cuda(x, Z, raw_ell, raw_os, m, s, w, b)
     N, D = x.shape
     M = Z.shape[0]
@@ -75,10 +81,10 @@ def svgp_forward_raw(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: T
     ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().gpblur_svgp_forward(
+        rc = _cabi.lib().gpblur_svgp_forward_cached(
             C.byref(p), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
-            _ptr(kl), _ptr(info), int(training), _ptr(ws), ws.numel(), _stream())
+            _ptr(kl), _ptr(info), int(training), _ptr(ws), ws.numel(), _ptr(param_stage), _stream())
     _cabi.check(rc, "gpblur_svgp_forward")
     return mean, var, sample, kl, info, ws
 
@@ -197,7 +203,7 @@ class _SvgpFunction(torch.autograd.Function):
     """Whitened SVGP predictive with a hand-written backward (no autograd through the kernels)."""
 
     @staticmethod
-    def forward(ctx, x, Z, raw_ell, raw_os, m, s, w, b, seed, offset, stream_id, want_sample):
+    def forward(ctx, x, Z, raw_ell, raw_os, m, s, w, b, seed, offset, stream_id, want_sample, stage_cache):
         shape = x.shape
         D = shape[-1]
         x2 = _f32c(x).reshape(-1, D)
@@ -207,8 +213,19 @@ class _SvgpFunction(torch.autograd.Function):
         bc = bc.reshape(-1)
         wc = None if w is None else _f32c(w).reshape(-1)
         training = any(ctx.needs_input_grad[:8])
+        # share the M x M stage between calls whose parameters are unchanged (enc / dec call of one step)
+        stage = None
+        key = None
+        if stage_cache is not None:
+            key = tuple((t._version, t.data_ptr()) for t in (Z, raw_ell, raw_os, m, s, b) if t is not None) + \
+                ((w._version, w.data_ptr()) if w is not None else (), D, Zc.shape[0])
+            if stage_cache.get("key") == key:
+                stage = stage_cache["stage"]
         mean, var, sample, kl, info, ws = svgp_forward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, seed, offset,
-                                                           stream_id, want_sample, training)
+                                                           stream_id, want_sample, training, stage)
+        if stage_cache is not None and stage is None:
+            stage_cache["key"] = key
+            stage_cache["stage"] = ws[:param_stage_bytes(D, Zc.shape[0])].clone()
         if training:
             ctx.save_for_backward(x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws)
         ctx.rng = (seed, offset, stream_id)
@@ -243,17 +260,19 @@ class _SvgpFunction(torch.autograd.Function):
                 ds.reshape(shp[5]) if need[5] else None,
                 dw.reshape(shp[6]) if (wc is not None and need[6]) else None,
                 db.reshape(shp[7]) if need[7] else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
-                 want_sample: bool = False):
-    """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1])."""
+                 want_sample: bool = False, stage_cache: Optional[dict] = None):
+    """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]).
+    `stage_cache`: a dict owned by the caller (one per GP) that lets consecutive calls with unchanged parameter
+    tensors (same `_version`) share the once-per-update M x M stage."""
     return _SvgpFunction.apply(x, inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
                                variational_stddev, mean_weights, mean_bias, int(seed), int(offset),
-                               int(stream_id), bool(want_sample))
+                               int(stream_id), bool(want_sample), stage_cache)
 
 
 class _ElboFunction(torch.autograd.Function):

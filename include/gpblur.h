@@ -72,6 +72,20 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
                         uint32_t stream_id, float* kl, int* info, int training, void* ws,
                         size_t ws_bytes, void* stream);
 
+/* Bytes at the start of a workspace that hold the once-per-parameter-update M x M stage (Kzz, L, Linv and the
+ * fp32 operands derived from them).  They depend only on the parameters, not on x. */
+size_t gpblur_svgp_param_stage_bytes(int D, int M);
+
+/* Same as gpblur_svgp_forward, but the M x M stage is COPIED from `param_stage` (the first
+ * gpblur_svgp_param_stage_bytes() bytes of the workspace of an earlier forward with the SAME parameter values)
+ * instead of being recomputed.  The reference evaluates the GP twice per training step with unchanged parameters
+ * (/root/reference/denoising_model/denoise_model_2.py:50-51, encoder and decoder side) and gpytorch re-factorises
+ * Kzz both times; this entry point shares one factorisation between the two calls. */
+int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
+                               float* mean, float* var, float* sample, uint64_t seed, uint64_t offset,
+                               uint32_t stream_id, float* kl, int* info, int training, void* ws,
+                               size_t ws_bytes, const void* param_stage, void* stream);
+
 /* Backward of gpblur_svgp_forward (replaces torch autograd through gpytorch, incl.
  * LinalgCholeskyExBackward0 / LinalgSolveTriangularBackward0).
  * Upstream gradients g_mean, g_var, g_sample [N] (each nullable) and g_kl [1] (nullable);

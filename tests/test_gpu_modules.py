@@ -256,3 +256,41 @@ def test_sharded_wrapper_single_process(cuda):
         dp.sync_grads()
     assert dp.bucket.flat.abs().sum().item() > 0
     assert model.hidden_layer.variational_strategy.inducing_points.grad.data_ptr() >= dp.bucket.flat.data_ptr()
+
+
+def test_param_stage_is_shared_between_calls_and_invalidated_by_updates(cuda):
+    """The enc / dec calls of one step share the M x M stage (gpblur_svgp_forward_cached); an in-place parameter
+    update (optimizer step) bumps the tensor version and forces a recompute."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat, _cabi
+    D, M = 32, 256
+    p = O.init_params_exercise(D, M, 3)
+    x_enc, _, _, _ = O.make_inputs(4, 48, D, 4)
+    x_dec, y, _, _ = O.make_inputs(4, 24, D, 5)
+    with gpcompat.num_likelihood_samples(1):
+        model = DeepGPp(D, 1, num_inducing=M).to(cuda)
+        load_params(model, p)
+        hl = model.hidden_layer
+        _cabi.profile_enable(True)
+        m1, _ = model.predict(x_enc.to(cuda).requires_grad_(True))
+        m2, d2 = model.predict(x_dec.to(cuda).requires_grad_(True))
+        torch.cuda.synchronize()
+        prof = _cabi.profile_collect()
+        assert prof["mm_fwd"][1] == 1 and prof["point_fwd"][1] == 2          # one factorisation, two point passes
+        hl.share_param_stage = False
+        m2_ref, d2_ref = model.predict(x_dec.to(cuda))
+        assert torch.equal(m2, m2_ref) and torch.equal(d2.variance, d2_ref.variance)
+        hl.share_param_stage = True
+        # gradients through the cached call
+        mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
+        (-mll(d2, y.to(cuda).unsqueeze(0)).mean() + m1.sum()).backward()
+        with torch.no_grad():
+            hl.variational_strategy.inducing_points.add_(0.01)                # "optimizer step"
+        m3, _ = model.predict(x_dec.to(cuda))
+        torch.cuda.synchronize()
+        prof = _cabi.profile_collect()
+        _cabi.profile_enable(False)
+        assert prof["mm_fwd"][1] >= 2                                          # uncached call + recompute after update
+    p2 = dict(p, inducing_points=p["inducing_points"] + 0.01)
+    mo, _ = O.svgp_predict_closed_form(O.clone_params(p2, torch.float64), x_dec.double())
+    assert rel(m3[0], mo) < 1e-4

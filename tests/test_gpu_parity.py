@@ -15,8 +15,13 @@ from oracle import gp_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL_FWD = 1e-5
+TOL_FWD = 1e-5        # FP32 FFMA path (M <= 64 or M > 256)
+TOL_FWD_TC = 1e-4     # tcgen05 3xTF32 path (64 < M <= 256); the north star allows 1e-3 there, measured <= 7e-6
 TOL_GRAD = 2e-4
+
+
+def fwd_tol(M):
+    return TOL_FWD_TC if 64 < M <= 256 else TOL_FWD
 
 
 def rel(a, b):
@@ -97,7 +102,7 @@ def test_mm_stage_and_forward(cuda, B, L, D, M):
     # predictive
     e_mean, e_var = rel(mean.reshape(B, L), mean_o), rel(var.reshape(B, L), var_o)
     print(f"fwd B={B} L={L} D={D} M={M}: mean {e_mean:.2e} var {e_var:.2e}")
-    assert e_mean < TOL_FWD and e_var < TOL_FWD
+    assert e_mean < fwd_tol(M) and e_var < fwd_tol(M)
     assert abs(kl.item() - O.kl_meanfield(p64).item()) <= 1e-5 * max(1.0, abs(O.kl_meanfield(p64).item()))
     # fused sample = mean + sqrt(var) * eps with the documented counters
     eps = torch.from_numpy(O.philox_normal(1234, 5, B * L, 0))
