@@ -70,7 +70,9 @@ def stage_work(stage: str, N: int, D: int, M: int):
     if stage == "point_fwd":
         return N * (4 * D + 12), N * (2 * M * D + M * M)
     if stage == "point_bwd":
-        return N * (8 * D + 16), N * (4 * M * D + M * M)
+        return N * (4 * D + 16), N * (2 * M * D + M * M)
+    if stage == "dx":
+        return N * 8 * D, 2 * N * M * D
     if stage == "gram":
         return 0, N * M * M
     if stage == "wx":
@@ -88,52 +90,59 @@ def bytes_per_window(L, D):
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock + throttle reasons DURING the timed region (NVML from a background thread, ~2 ms period;
+    falls back to one `nvidia-smi` query)."""
+
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                for nm, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
-            os.close(fd)
-            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
-            sm = sorted(float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit())
-            mx = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = set()
-            for r in rows:
-                for i, nm in enumerate(names):
-                    if len(r) > 3 + i and r[3 + i].strip().lower() == "active":
-                        reasons.add(nm)
-            if sm:
-                out["sm_mhz"] = sm[len(sm) // 2]
-            if mx:
-                out["sm_max_mhz"] = max(mx)
-            out["reasons"] = sorted(reasons)
-            out["samples"] = len(rows)
-            os.unlink(self.path)
-        except Exception:
-            pass
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.samples:
+            sm = sorted(self.samples)
+            out["sm_mhz"] = sm[len(sm) // 2]
+        else:
+            try:
+                r = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout.split(",")
+                out["sm_mhz"], out["sm_max_mhz"] = float(r[0]), float(r[1])
+            except Exception:
+                pass
         return out
 
 
@@ -335,6 +344,9 @@ def run_ours(args, wl, name):
     # ---- timed region 2: end to end through the module API with host buffers ----
     xdev = [torch.empty_like(x) for x in xs[0]]
     ydev = torch.empty_like(ys[0])
+    for c in range(len(calls)):                          # untimed warm-up of the pinned-copy path
+        xdev[c].copy_(xh[0][c], non_blocking=True)
+    step(0, xdev, ydev)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -385,8 +397,9 @@ def run_ours(args, wl, name):
                 roof = {"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
             else:
                 roof = {"bound": "tensor", "achieved": fl / per_launch_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "peak_note": "TF32 dense rate taken as 1/2 of the measured cuBLAS bf16 burst peak; the "
-                                     "kernel itself still runs FP32 FFMA (round 1), FFMA peak ~74 TFLOP/s"}
+                        "peak_note": "TF32 dense rate = 1/2 of the measured cuBLAS bf16 burst peak; 'achieved' counts "
+                                     "ALGORITHMIC flops (a 3xTF32 kernel issues 3 MMAs per product; M <= 64 and "
+                                     "M > 256 still run FP32 FFMA, peak ~74 TFLOP/s)"}
             roof["frac"] = roof["achieved"] / roof["peak"]
             roof["traffic"] = None
             roof["kernel"] = dom

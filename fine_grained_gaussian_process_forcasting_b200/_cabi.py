@@ -116,7 +116,7 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(f"{what} failed with {ERRORS.get(rc, rc)}{detail}")
 
 
-STAGES = ("mm_fwd", "point_fwd", "point_bwd", "gram", "wx", "mm_bwd", "elbo_fwd", "elbo_bwd", "other")
+STAGES = ("mm_fwd", "point_fwd", "point_bwd", "gram", "wx", "mm_bwd", "elbo_fwd", "elbo_bwd", "dx")
 
 
 def profile_enable(on: bool) -> None:

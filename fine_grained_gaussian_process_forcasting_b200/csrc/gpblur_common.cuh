@@ -49,6 +49,7 @@ struct WsLayout {
   // byte offsets
   size_t hyp, hyp64, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
+  size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
   size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64, rrow, cpart;
   size_t total;
 };
@@ -94,6 +95,14 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.LC32 = take(MP * MP * 4);
   w.Linv32 = take(MP * MP * 4);   // row-major Linv (tensor-core forward B operand)
   w.LCT32 = take(MP * MP * 4);    // (diag(c) Linv)^T (tensor-core backward B operand)
+  {
+    // UMMA slab images, see tc_slab_* helpers below.  Sizes in floats (hi + lo planes).
+    const size_t nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
+    w.ZtU = take(nds * 64 * MP * 4);
+    w.LinvU = take((64 * nsl * MP - 1024 * nsl * (nsl - 1)) * 4);
+    w.LCTU = take(1024 * nsl * (nsl + 1) * 4);
+    w.ZtTU = take(nsl * 64 * dpt * 4);
+  }
   const int tp = w.MP < 128 ? w.MP : 128;
   const int nt = w.MP / tp;
   w.splitsS = choose_splits(N, nt * (nt + 1) / 2);
@@ -126,6 +135,14 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.total = o;
   return w;
 }
+
+// float offsets of slab s inside the UMMA slab images (each slab: hi plane [8 chunks][rows][4], then lo plane)
+__host__ __device__ inline size_t tc_slab_zt(int MP, int ds) { return (size_t)ds * 64 * MP; }
+__host__ __device__ inline int tc_rows_linv(int MP, int s) { return MP - 32 * s; }
+__host__ __device__ inline size_t tc_slab_linv(int MP, int s) { return (size_t)64 * s * MP - (size_t)1024 * s * (s - 1); }
+__host__ __device__ inline int tc_rows_lct(int s) { return 32 * (s + 1); }
+__host__ __device__ inline size_t tc_slab_lct(int s) { return (size_t)1024 * s * (s + 1); }
+__host__ __device__ inline size_t tc_slab_ztt(int dpt, int s) { return (size_t)s * 64 * dpt; }
 
 template <typename T>
 __host__ __device__ inline T* ws_ptr(void* ws, size_t off) {

@@ -401,6 +401,70 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       LCT32[(size_t)tj * MP + ti] = vt * cvec[ti];
     }
   }
+  // ---- constant operands of the tensor-core kernels, pre-split into TF32 hi / lo UMMA slab images ----
+  if (MP == 128 || MP == 256) {
+    auto split = [](float v, float& hi, float& lo) {
+      uint32_t h;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+      hi = __uint_as_float(h);
+      lo = v - hi;
+    };
+    const int nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
+    float* ZtU = ws_ptr<float>(a.ws, L.ZtU);
+    float* LinvU = ws_ptr<float>(a.ws, L.LinvU);
+    float* LCTU = ws_ptr<float>(a.ws, L.LCTU);
+    float* ZtTU = ws_ptr<float>(a.ws, L.ZtTU);
+    // Z~ slabs (rows m, k = d):   element (c, r, e) of slab ds = Zt[r][32 ds + 4 c + e]
+    for (int idx = gtid; idx < nds * 8 * MP * 4; idx += gsize) {
+      const int e = idx & 3, r = (idx >> 2) % MP, c = ((idx >> 2) / MP) & 7, ds = (idx >> 2) / (MP * 8);
+      const int d = ds * 32 + c * 4 + e;
+      const float v = (d < DP) ? Zt[(size_t)r * DP + d] : 0.f;
+      float hi, lo;
+      split(v, hi, lo);
+      float* base = ZtU + tc_slab_zt(MP, ds);
+      base[(c * MP + r) * 4 + e] = hi;
+      base[32 * MP + (c * MP + r) * 4 + e] = lo;
+    }
+    // Z~^T slabs (rows d, k = m): element (c, r, e) of slab s = Zt[32 s + 4 c + e][r]
+    for (int idx = gtid; idx < nsl * 8 * dpt * 4; idx += gsize) {
+      const int e = idx & 3, r = (idx >> 2) % dpt, c = ((idx >> 2) / dpt) & 7, sl = (idx >> 2) / (dpt * 8);
+      const int m = sl * 32 + c * 4 + e;
+      const float v = (r < DP) ? Zt[(size_t)m * DP + r] : 0.f;
+      float hi, lo;
+      split(v, hi, lo);
+      float* base = ZtTU + tc_slab_ztt(dpt, sl);
+      base[(c * dpt + r) * 4 + e] = hi;
+      base[32 * dpt + (c * dpt + r) * 4 + e] = lo;
+    }
+    // Linv slabs (forward): slab s holds rows i = 32 s + r (r < MP - 32 s), k = j = 32 s + 4 c + e
+    for (int sl = 0; sl < nsl; ++sl) {
+      const int nr = tc_rows_linv(MP, sl);
+      float* base = LinvU + tc_slab_linv(MP, sl);
+      for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
+        const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
+        const int i = 32 * sl + r, j = 32 * sl + 4 * c + e;
+        const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] : 0.f;
+        float hi, lo;
+        split(v, hi, lo);
+        base[(c * nr + r) * 4 + e] = hi;
+        base[32 * nr + (c * nr + r) * 4 + e] = lo;
+      }
+    }
+    // (diag(c) Linv)^T slabs (backward): slab s holds rows j = r (r < 32 (s + 1)), k = i = 32 s + 4 c + e
+    for (int sl = 0; sl < nsl; ++sl) {
+      const int nr = tc_rows_lct(sl);
+      float* base = LCTU + tc_slab_lct(sl);
+      for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
+        const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
+        const int i = 32 * sl + 4 * c + e, j = r;
+        const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] * cvec[i] : 0.f;
+        float hi, lo;
+        split(v, hi, lo);
+        base[(c * nr + r) * 4 + e] = hi;
+        base[32 * nr + (c * nr + r) * 4 + e] = lo;
+      }
+    }
+  }
   float* zn = ws_ptr<float>(a.ws, L.zn);
   for (int j = gtid; j < MP; j += gsize) {
     double s = 0.0;

@@ -35,6 +35,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// transaction barrier for cp.async.bulk: one arrival + `bytes` expected
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared (size multiple of 16 B), completion signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- fences ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -112,6 +124,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// exp(x) for x <= 0 via ex2.approx with a compensated x * log2(e) (relative error ~2^-22, ~5 instructions)
+__device__ __forceinline__ float fast_exp(float x) {
+  const float t = x * 1.4426950408889634f;
+  const float r = fmaf(x, 1.4426950408889634f, -t);            // rounding error of the product
+  const float t2 = fmaf(x, 1.9259629911266175e-08f, r) + t;     // + x * (log2e - fl(log2e))
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t2));
+  return y;
+}
+
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------
 // hi = round-to-nearest TF32 of a (low 13 mantissa bits zero), lo = a - hi (exact in fp32; the tensor core
 // truncates it to TF32 at 2^-22 |a|).  a*b ~= hi_a*hi_b + hi_a*lo_b + lo_a*hi_b, relative error ~2^-21.
@@ -135,8 +157,10 @@ __device__ __forceinline__ int op_off(int r, int c) { return (c * ROWS + r) * 4;
 // issue the 3 x (KT / 8) MMAs of one K slab: A planes [KT/4 chunks][128 rows], B planes [KT/4][NROWS]
 template <int KT, int NROWS>
 __device__ __forceinline__ void issue_slab_3xtf32(uint32_t tmem_d, const float* a_hi, const float* a_lo,
-                                                  const float* b_hi, const float* b_lo, uint32_t idesc, bool first) {
-  constexpr uint32_t A_LBO = 128 * 16, B_LBO = NROWS * 16, SBO = 128;
+                                                  const float* b_hi, const float* b_lo, uint32_t idesc, bool first,
+                                                  int b_rows = NROWS) {
+  constexpr uint32_t A_LBO = 128 * 16, SBO = 128;
+  const uint32_t B_LBO = (uint32_t)b_rows * 16;
   const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll
   for (int j = 0; j < KT / 8; ++j) {

@@ -45,39 +45,68 @@ struct Stage {
   static constexpr int FLOATS = 2 * A_PLANE + 2 * B_PLANE;
 };
 
-// two-stage operand ring + completion barriers
+// two-stage operand ring.  bars[0..1]: "MMAs that read this stage are done" (tcgen05.commit);
+// bars[2..3]: "the TMA bulk copy of this stage's B planes has landed" (mbarrier complete_tx).
 template <int NB>
 struct Pipe {
   float* base;
   uint64_t* bars;
-  uint32_t uses[2];
+  uint32_t uses[2], fulls[2];
   int slab;
-  __device__ __forceinline__ void init(float* b, uint64_t* br) { base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; }
-  // wait until the MMAs that last read this stage are done, return its planes
-  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) {
-    const int st = slab & 1;
-    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+  bool prefetched;
+  __device__ __forceinline__ void init(float* b, uint64_t* br) {
+    base = b; bars = br; uses[0] = uses[1] = 0; fulls[0] = fulls[1] = 0; slab = 0; prefetched = false;
+  }
+  __device__ __forceinline__ void planes(int st, float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) const {
     a_hi = base + st * Stage<NB>::FLOATS;
     a_lo = a_hi + Stage<NB>::A_PLANE;
     b_hi = a_lo + Stage<NB>::A_PLANE;
     b_lo = b_hi + Stage<NB>::B_PLANE;
   }
-  // publish the stage to the tensor core and issue N-column MMAs into tmem_d
-  __device__ __forceinline__ void commit(uint32_t tmem_d, int ncols, bool first) {
+  // wait until the MMAs that last read this stage are done, return its planes
+  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) {
+    const int st = slab & 1;
+    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+    planes(st, a_hi, a_lo, b_hi, b_lo);
+  }
+  // thread 0: pull a pre-split B slab image (hi plane then lo plane, `rows` rows each) into stage `st`
+  __device__ __forceinline__ void issue_bulk(int st, const float* image, int rows) {
+    float *a_hi, *a_lo, *b_hi, *b_lo;
+    planes(st, a_hi, a_lo, b_hi, b_lo);
+    const uint32_t bytes = (uint32_t)rows * 128u;          // 8 k-chunks x rows x 16 B
+    tc::mbar_expect_tx(&bars[2 + st], 2 * bytes);
+    tc::bulk_g2s(b_hi, image, bytes, &bars[2 + st]);
+    tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
+  }
+  // B operand of the CURRENT slab; a no-op when the previous commit() already prefetched it
+  __device__ __forceinline__ void bulk_b(const float* image, int rows) {
+    if (threadIdx.x == 0 && !prefetched) issue_bulk(slab & 1, image, rows);
+  }
+  // publish the stage to the tensor core, issue N-column MMAs into tmem_d, then (thread 0) start the TMA copy of the
+  // NEXT slab's B image into the other stage as soon as the MMAs that still read it have retired, so that its
+  // latency hides behind the production of the next A operand.
+  __device__ __forceinline__ void commit(uint32_t tmem_d, int ncols, bool first, int b_rows, const float* next_image,
+                                         int next_rows) {
     const int st = slab & 1;
     tc::fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
+      tc::mbar_wait(&bars[2 + st], fulls[st] & 1);
       tc::tc_fence_after();
-      float* a_hi = base + st * Stage<NB>::FLOATS;
-      float* a_lo = a_hi + Stage<NB>::A_PLANE;
-      float* b_hi = a_lo + Stage<NB>::A_PLANE;
-      float* b_lo = b_hi + Stage<NB>::B_PLANE;
-      tc::issue_slab_3xtf32<KT, NB>(tmem_d, a_hi, a_lo, b_hi, b_lo, tc::make_idesc_tf32(TNP, ncols), first);
+      float *a_hi, *a_lo, *b_hi, *b_lo;
+      planes(st, a_hi, a_lo, b_hi, b_lo);
+      tc::issue_slab_3xtf32<KT, NB>(tmem_d, a_hi, a_lo, b_hi, b_lo, tc::make_idesc_tf32(TNP, ncols), first, b_rows);
       tc::umma_commit(&bars[st]);
+      if (next_image) {
+        const int nst = st ^ 1;
+        if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
+        issue_bulk(nst, next_image, next_rows);
+      }
     }
     uses[st] += 1;
+    fulls[st] += 1;
     slab += 1;
+    prefetched = next_image != nullptr;
   }
   // block until every MMA issued so far has completed
   __device__ __forceinline__ void drain() {
@@ -172,27 +201,24 @@ __device__ __forceinline__ void row_stats(const TcPointArgs& a, const XLoader& x
 
 // phase A of both kernels: S[128, MP] = X~ Z~^T into TMEM columns [0, MP)
 template <int MP>
-__device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl) {
+__device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl,
+                                        const float* after_image, int after_rows) {
   const WsLayout& L = a.L;
-  const float* Zt = ws_cptr<float>(a.ws, L.Zt);
+  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   const int DP = L.DP;
   const int nds = DP >= KT ? DP / KT : 1;
   for (int ds = 0; ds < nds; ++ds) {
     OpRegs<TNP> ra;
-    OpRegs<MP> rb;
     load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
       const int dchunk = ds * (KT / 4) + c;
       return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
     });
-    load_kmajor<MP>(rb, MP, [&](int row, int c) {
-      const int d = ds * KT + c * 4;
-      return d < DP ? ldg4(Zt + (size_t)row * DP + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-    });
     float *a_hi, *a_lo, *b_hi, *b_lo;
     pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+    pipe.bulk_b(ZtU + tc_slab_zt(MP, ds), MP);        // Z~ slab: TMA bulk copy of the pre-split image
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-    store_kmajor<MP>(b_hi, b_lo, rb, MP);
-    pipe.commit(tmem_s, MP, ds == 0);
+    const bool last = ds + 1 == nds;
+    pipe.commit(tmem_s, MP, ds == 0, MP, last ? after_image : ZtU + tc_slab_zt(MP, ds + 1), last ? after_rows : MP);
   }
 }
 
@@ -202,7 +228,7 @@ __device__ __forceinline__ void kernel_values(float (&v)[32], float xn, const fl
   for (int i = 0; i < 32; ++i) {
     const int m = col0 + i;
     const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-    v[i] = (m < M) ? os * expf(-0.5f * d2) : 0.f;
+    v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
   }
 }
 
@@ -213,7 +239,7 @@ template <int MP>
 __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[MP], m_s[MP], c_s[MP];
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
@@ -223,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* Linv = ws_cptr<float>(a.ws, L.Linv32);
+  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
   float* Ag = ws_ptr<float>(a.ws, L.A);
   const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
 
@@ -232,6 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init(&bars[3], 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < MP; i += kThreads) {
@@ -254,36 +282,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
     const long long n0 = (long long)tile * TNP;
     const XLoader xl = make_xloader(a, n0);
     row_stats(a, xl, xn_s, xw_s);
-    phase_a<MP>(pipe, tmem_s, a, xl);
+    phase_a<MP>(pipe, tmem_s, a, xl, LinvU, MP);    // prefetches the first Linv slab
     pipe.drain();                                   // S complete (also makes xn_s visible: commit() synchronised)
     const float xn = xn_s[row];
 
     // ---- phase B: A[:, i >= 32 s] += k[:, slab s] Linv[i, slab s]^T ----
     for (int s = 0; s < MP / KT; ++s) {
       const int i0 = s * KT;                        // only rows i >= 32 s of Linv see this slab (lower triangular)
-      OpRegs<MP> rb;
-      load_kmajor<MP>(rb, MP - i0, [&](int r, int c) { return ldg4(Linv + (size_t)(i0 + r) * MP + i0 + c * 4); });
+      // epilogue A of this 32-column chunk: the two column halves of a lane quadrant take 16 columns each
+      float v[16];
+      const int col0 = s * KT + half * 16;
+      tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int m = col0 + i;
+        const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
+        v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
+      }
       float *a_hi, *a_lo, *b_hi, *b_lo;
       pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-      {
-        // epilogue A of this 32-column chunk: the two column halves of a lane quadrant take 16 columns each
-        float v[16];
-        const int col0 = s * KT + half * 16;
-        tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
+      pipe.bulk_b(LinvU + tc_slab_linv(MP, s), MP - i0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int m = col0 + i;
-          const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-          v[i] = (m < M) ? os * expf(-0.5f * d2) : 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)                 // k-chunks half * 4 + c of the slab
-          tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
-                          make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
-      }
-      store_kmajor<MP>(b_hi, b_lo, rb, MP - i0);
+      for (int c = 0; c < 4; ++c)                   // k-chunks half * 4 + c of the slab
+        tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
+                        make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
       tc::tc_fence_before();
-      pipe.commit(tmem_a + i0, MP - i0, s == 0);
+      const bool last = s + 1 == MP / KT;
+      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      const float* nxt = last ? (more_tiles ? ws_cptr<float>(a.ws, L.ZtU) : nullptr) : LinvU + tc_slab_linv(MP, s + 1);
+      pipe.commit(tmem_a + i0, MP - i0, s == 0, MP - i0, nxt, last ? MP : MP - i0 - KT);
     }
     pipe.drain();
 
@@ -331,7 +358,7 @@ template <int MP>
 __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[MP], beta_s[MP];
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
@@ -341,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* LCT = ws_cptr<float>(a.ws, L.LCT32);
+  const float* LCTU = ws_cptr<float>(a.ws, L.LCTU);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
@@ -353,6 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init(&bars[3], 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < MP; i += kThreads) {
@@ -374,24 +403,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
     const long long n0 = (long long)tile * TNP;
     const XLoader xl = make_xloader(a, n0);
     row_stats(a, xl, xn_s, xw_s);
-    phase_a<MP>(pipe, tmem_s, a, xl);
+    phase_a<MP>(pipe, tmem_s, a, xl, LCTU + tc_slab_lct(MP / KT - 1), MP);
 
     // ---- phase B': T[:, j < 32 (s + 1)] += a[:, slab s] (diag(c) Linv)[slab s, j], slabs in DEcreasing order ----
-    for (int s = MP / KT - 1; s >= 0; --s) {
-      const int i0 = s * KT;
-      OpRegs<TNP> ra;
-      OpRegs<MP> rb;
-      load_kmajor<TNP>(ra, TNP, [&](int r, int c) {
+    auto load_a = [&](OpRegs<TNP>& regs, int sl) {
+      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
         long long gn = n0 + r;
         if (gn >= N) gn = N - 1;                       // clamped rows carry g = 0 below
-        return ldg4(Ag + (size_t)gn * MP + i0 + c * 4);
+        return ldg4(Ag + (size_t)gn * MP + sl * KT + c * 4);
       });
-      load_kmajor<MP>(rb, i0 + KT, [&](int r, int c) { return ldg4(LCT + (size_t)r * MP + i0 + c * 4); });
+    };
+    OpRegs<TNP> ra;
+    load_a(ra, MP / KT - 1);
+    for (int s = MP / KT - 1; s >= 0; --s) {
+      const int i0 = s * KT;
       float *a_hi, *a_lo, *b_hi, *b_lo;
       pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      pipe.bulk_b(LCTU + tc_slab_lct(s), i0 + KT);
       store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      store_kmajor<MP>(b_hi, b_lo, rb, i0 + KT);
-      pipe.commit(tmem_t, i0 + KT, s == MP / KT - 1);
+      if (s > 0) load_a(ra, s - 1);                   // next slab's saved-A tile flies during the MMAs
+      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      const float* nxt = s > 0 ? LCTU + tc_slab_lct(s - 1) : (more_tiles ? ws_cptr<float>(a.ws, L.ZtU) : nullptr);
+      pipe.commit(tmem_t, i0 + KT, s == MP / KT - 1, i0 + KT, nxt, s > 0 ? i0 : MP);
     }
     pipe.drain();
 
@@ -451,7 +484,7 @@ template <int DPT>   // DPT = MMA N = padded input dim (32, 64 or 128)
 __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8][32][33];
   __shared__ float part_q[8][32], part_t[8][32], part_sc[8][4];
@@ -465,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
   const float* ellv = ws_cptr<float>(a.ws, L.ell);
   const float* center = ws_cptr<float>(a.ws, L.center);
   const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const float* ZtT = ws_cptr<float>(a.ws, L.ZtT);
+  const float* ZtTU = ws_cptr<float>(a.ws, L.ZtTU);
   const float* Wg = ws_cptr<float>(a.ws, L.W);
   const float* gsc = ws_cptr<float>(a.ws, L.gsc);
   const float* rrow = ws_cptr<float>(a.ws, L.rrow);
@@ -476,6 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init(&bars[3], 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
@@ -499,22 +534,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
 
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
-    for (int s = 0; s < MP / KT; ++s) {
-      const int m0 = s * KT;
-      OpRegs<TNP> ra;
-      OpRegs<DPT> rb;
-      load_kmajor<TNP>(ra, TNP, [&](int r, int c) {
+    auto load_w = [&](OpRegs<TNP>& regs, int sl) {
+      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
         const long long gn = n0 + r;
-        return gn < N ? ldg4(Wg + (size_t)gn * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return gn < N ? ldg4(Wg + (size_t)gn * MP + sl * KT + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
-      load_kmajor<DPT>(rb, DPT, [&](int r, int c) {
-        return r < DP ? ldg4(ZtT + (size_t)r * MP + m0 + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      });
+    };
+    OpRegs<TNP> ra;
+    load_w(ra, 0);
+    for (int s = 0; s < MP / KT; ++s) {
       float *a_hi, *a_lo, *b_hi, *b_lo;
       pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+      pipe.bulk_b(ZtTU + tc_slab_ztt(DPT, s), DPT);
       store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      store_kmajor<DPT>(b_hi, b_lo, rb, DPT);
-      pipe.commit(tmem_d, DPT, s == 0);
+      if (s + 1 < MP / KT) load_w(ra, s + 1);
+      const bool last = s + 1 == MP / KT;
+      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      const float* nxt = last ? (more_tiles ? ZtTU : nullptr) : ZtTU + tc_slab_ztt(DPT, s + 1);
+      pipe.commit(tmem_d, DPT, s == 0, DPT, nxt, DPT);
     }
     pipe.drain();
 
