@@ -183,42 +183,64 @@ __device__ __forceinline__ XLoader make_xloader(const TcPointArgs& a, long long 
                  (L.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0)};
 }
 
-// per-row |x~|^2 and linear mean x~ . (ell w): one thread per point of the tile (threads 0..127)
-__device__ __forceinline__ void row_stats(const TcPointArgs& a, const XLoader& xl, float* xn_s, float* xw_s) {
-  if (threadIdx.x < TNP) {
-    const float* wl = ws_cptr<float>(a.ws, a.L.wl);
-    float n2 = 0.f, xw = 0.f;
-    for (int dc = 0; dc * 4 < a.L.DP; ++dc) {
-      const float4 v = xl(threadIdx.x, dc);
-      const float4 w4 = ldg4(wl + dc * 4);
-      n2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      xw += v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
-    }
-    xn_s[threadIdx.x] = n2;
-    xw_s[threadIdx.x] = xw;
-  }
+// phase A of both kernels: S[128, MP] = X~ Z~^T into TMEM columns [0, MP)
+// registers of one 32-wide d-slab of the x tile (centred / scaled)
+__device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
+  load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
+    const int dchunk = ds * (KT / 4) + c;
+    return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+  });
 }
 
-// phase A of both kernels: S[128, MP] = X~ Z~^T into TMEM columns [0, MP)
+// xr0 / xr1: the first two d-slabs of this tile's x, already in registers (loaded one tile ahead so that the HBM
+// latency hides behind the previous tile's MMAs and epilogue)
 template <int MP>
 __device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl,
-                                        const float* after_image, int after_rows) {
+                                        const float* after_image, int after_rows, float* part_n, float* part_w,
+                                        float* xn_s, float* xw_s, const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1) {
   const WsLayout& L = a.L;
   const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
+  const float* wl = ws_cptr<float>(a.ws, L.wl);
   const int DP = L.DP;
   const int nds = DP >= KT ? DP / KT : 1;
   for (int ds = 0; ds < nds; ++ds) {
     OpRegs<TNP> ra;
-    load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
-      const int dchunk = ds * (KT / 4) + c;
-      return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-    });
+    if (ds == 0) ra = xr0;
+    else if (ds == 1) ra = xr1;
+    else load_x_slab(ra, xl, ds, DP);
+    {
+      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int rr = lane & 7, cq = lane >> 3;
+#pragma unroll
+      for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
+        const int wt = warp + 8 * p;
+        const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
+        const int dchunk = ds * (KT / 4) + c;
+        const float4 v = ra.v[p];
+        const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        part_n[c * TNP + row] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        part_w[c * TNP + row] = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+      }
+    }
     float *a_hi, *a_lo, *b_hi, *b_lo;
     pipe.acquire(a_hi, a_lo, b_hi, b_lo);
     pipe.bulk_b(ZtU + tc_slab_zt(MP, ds), MP);        // Z~ slab: TMA bulk copy of the pre-split image
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
     const bool last = ds + 1 == nds;
     pipe.commit(tmem_s, MP, ds == 0, MP, last ? after_image : ZtU + tc_slab_zt(MP, ds + 1), last ? after_rows : MP);
+    // commit() synchronised the CTA: fold this slab's 8 chunk partials in fixed order (bit-deterministic)
+    if (threadIdx.x < TNP) {
+      float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
+#pragma unroll
+      for (int c = 0; c < KT / 4; ++c) {
+        n2 += part_n[c * TNP + threadIdx.x];
+        xw += part_w[c * TNP + threadIdx.x];
+      }
+      xn_s[threadIdx.x] = n2;
+      xw_s[threadIdx.x] = xw;
+    }
+    __syncthreads();
   }
 }
 
@@ -243,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[MP], m_s[MP], c_s[MP];
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
+  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];   // per-slab row-statistic partials
 
   const WsLayout& L = a.L;
   const int M = L.M;
@@ -278,12 +301,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
   const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
+  OpRegs<TNP> xr0, xr1;
+  {
+    const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
+    load_x_slab(xr0, xl0, 0, L.DP);
+    if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
+  }
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
     const XLoader xl = make_xloader(a, n0);
-    row_stats(a, xl, xn_s, xw_s);
-    phase_a<MP>(pipe, tmem_s, a, xl, LinvU, MP);    // prefetches the first Linv slab
-    pipe.drain();                                   // S complete (also makes xn_s visible: commit() synchronised)
+    phase_a<MP>(pipe, tmem_s, a, xl, LinvU, MP, part_n, part_w, xn_s, xw_s, xr0, xr1);    // prefetches the first Linv slab
+    if (tile + (int)gridDim.x < a.ntiles) {        // next tile's x: in flight during phase B and the epilogue
+      const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+      load_x_slab(xr0, xln, 0, L.DP);
+      if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+    }
+    pipe.drain();                                   // S complete
     const float xn = xn_s[row];
 
     // ---- phase B: A[:, i >= 32 s] += k[:, slab s] Linv[i, slab s]^T ----
@@ -362,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[MP], beta_s[MP];
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
+  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];
 
   const WsLayout& L = a.L;
   const int M = L.M;
@@ -399,11 +433,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   const int row = quad * 32 + lane;
   const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
+  OpRegs<TNP> xr0, xr1;
+  {
+    const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
+    load_x_slab(xr0, xl0, 0, L.DP);
+    if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
+  }
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
     const XLoader xl = make_xloader(a, n0);
-    row_stats(a, xl, xn_s, xw_s);
-    phase_a<MP>(pipe, tmem_s, a, xl, LCTU + tc_slab_lct(MP / KT - 1), MP);
+    phase_a<MP>(pipe, tmem_s, a, xl, LCTU + tc_slab_lct(MP / KT - 1), MP, part_n, part_w, xn_s, xw_s, xr0, xr1);
+    if (tile + (int)gridDim.x < a.ntiles) {
+      const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+      load_x_slab(xr0, xln, 0, L.DP);
+      if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+    }
 
     // ---- phase B': T[:, j < 32 (s + 1)] += a[:, slab s] (diag(c) Linv)[slab s, j], slabs in DEcreasing order ----
     auto load_a = [&](OpRegs<TNP>& regs, int sl) {
