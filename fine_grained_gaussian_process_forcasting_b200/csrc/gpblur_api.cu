@@ -407,6 +407,7 @@ int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, voi
     case 1: off = L.Linv64; bytes = mm8; break;
     case 2: off = L.K64; bytes = mm8; break;
     case 3: off = L.A; bytes = (size_t)N * L.MP * 4; break;
+    case 4: off = L.stamps; bytes = kStampSlots * 8; break;
     default: return GPBLUR_EINVAL;
   }
   if (out_bytes < bytes) return GPBLUR_EWORKSPACE;

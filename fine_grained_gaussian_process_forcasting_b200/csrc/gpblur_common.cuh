@@ -19,6 +19,7 @@ constexpr int kMaxSplits = 148;          // split-K factor cap of the N-reductio
 
 // hyp (fp32) slots
 enum { H_OS = 0, H_JIT = 1, H_CWB = 2, H_KL = 3, H_COUNT = 8 };
+constexpr int kStampSlots = 32;   // phase timestamps (globaltimer ns) of the M x M kernels: [0,16) forward, [16,32) backward
 // per-CTA vector partial layout of the backward point kernel: [colsum MP | q DP | wbar DP | scalars 4]
 enum { VS_GMU = 0, VS_RSUM = 1, VS_GVAR = 2, VS_COUNT = 4 };
 
@@ -47,7 +48,7 @@ struct WsLayout {
   int nvec;                 // number of per-CTA vector partials (persistent backward CTAs)
   int vec_len;              // floats per vector partial
   // byte offsets
-  size_t hyp, hyp64, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
+  size_t hyp, hyp64, stamps, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
   size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
   size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64, rrow, cpart;
@@ -75,6 +76,7 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   w.hyp = take(H_COUNT * 4);
   w.hyp64 = take(H_COUNT * 8);
+  w.stamps = take(kStampSlots * 8);
   w.inv_ell = take(DP * 4);
   w.ell = take(DP * 4);
   w.center = take(DP * 4);
@@ -156,6 +158,11 @@ __host__ __device__ inline const T* ws_cptr(const void* ws, size_t off) {
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ double softplus64(double x) {
   return x > 30.0 ? x : log1p(exp(x));
 }

@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   float* Linv32 = ws_ptr<float>(a.ws, L.Linv32);
   float* LCT32 = ws_ptr<float>(a.ws, L.LCT32);
   const float* Z = a.p.inducing_points;
+  unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps);
+  int stamp_i = 0;
+#define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
+  GPBLUR_STAMP();
 
   // ---------------- phase 0: per-dimension hyper-parameters, centre, KL ----------------
   for (int d = blockIdx.x * 8 + warp; d < DP; d += G * 8) {
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     }
   }
   grid.sync();
+  GPBLUR_STAMP();
 
   // ---------------- phase 1: Zt, vectors, Kzz ----------------
   for (int idx = gtid; idx < MP * DP; idx += gsize) {
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     }
   }
   grid.sync();
+  GPBLUR_STAMP();
 
   // ---------------- phase 2: blocked Cholesky (right-looking) ----------------
   // per block column kb: every participating CTA factorises the diagonal block in registers (one warp, shuffle
@@ -342,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     grid.sync();   // also publishes the last diagonal block before phase 3
   }
 
+  GPBLUR_STAMP();
   // ---------------- phase 3b: recursive doubling  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]] ----
   for (int s = TB; s < MP; s *= 2) {
     const int sb = s / TB;                    // blocks per half
@@ -378,6 +385,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     }
   }
 
+  GPBLUR_STAMP();
   // ---------------- phase 4: fp32 operands ----------------
   for (int t = blockIdx.x; t < nb * nb; t += G) {
     const int bi = t / nb, bj = t - bi * nb;
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       LCT32[(size_t)tj * MP + ti] = vt * cvec[ti];
     }
   }
+  GPBLUR_STAMP();
   // ---- constant operands of the tensor-core kernels, pre-split into TF32 hi / lo UMMA slab images ----
   if (MP == 128 || MP == 256) {
     auto split = [](float v, float& hi, float& lo) {
@@ -465,6 +474,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       }
     }
   }
+  GPBLUR_STAMP();
   float* zn = ws_ptr<float>(a.ws, L.zn);
   for (int j = gtid; j < MP; j += gsize) {
     double s = 0.0;
@@ -474,6 +484,8 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     for (int d = 0; d < DP; ++d) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
     zn[j] = z2;
   }
+  GPBLUR_STAMP();
+#undef GPBLUR_STAMP
 }
 
 // ==================================================================================================
@@ -528,6 +540,10 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   double* t64 = ws_ptr<double>(a.ws, L.t64);   // [MP, DP] per-(i, d) terms of d lengthscale
 
   const int tp = MP < 128 ? MP : 128;   // tile size used by the Gram reduction (lower tile triangle valid)
+  unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps) + 16;
+  int stamp_i = 0;
+#define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
+  GPBLUR_STAMP();
 
   // ---------------- phase 0: reduce split partials ----------------
   for (int m = gtid; m < MP; m += gsize) {
@@ -554,6 +570,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 1: Lbar = -tril( beta u^T + 2 Linv^T cS ) -> U64 ----------------
   {
     const int ntl = nb * (nb + 1) / 2;
@@ -577,6 +594,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 2: Phi( L^T Lbar ) -> T64 (lower) ----------------
   for (int t = blockIdx.x; t < nb * nb; t += G) {
     const int bi = t / nb, bj = t - bi * nb;
@@ -598,6 +616,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 3: Tm = Phi Linv -> U64 (lower) ----------------
   for (int t = blockIdx.x; t < nb * nb; t += G) {
     const int bi = t / nb, bj = t - bi * nb;
@@ -616,6 +635,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 4: Kb = Linv^T Tm -> T64 (full) ----------------
   for (int t = blockIdx.x; t < nb * nb; t += G) {
     const int bi = t / nb, bj = t - bi * nb;
@@ -628,6 +648,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
   for (int idx = gtid; idx < MP * MP; idx += gsize) {
     const int i = idx / MP, j = idx - i * MP;
@@ -641,6 +662,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 6: Kzz-path + a-space gradients of Z; per-(i, d) terms of d ell -------
   for (int idx = gtid; idx < MP * DP; idx += gsize) {
     const int i = idx / DP, d = idx - i * DP;
@@ -667,6 +689,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   }
   grid.sync();
 
+  GPBLUR_STAMP();
   // ---------------- phase 7: final bucket (block 0) ----------------
   if (blockIdx.x == 0) {
     const double os = hyp64[H_OS];
@@ -713,6 +736,8 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       }
     }
   }
+  GPBLUR_STAMP();
+#undef GPBLUR_STAMP
   (void)hyp;
 }
 

@@ -184,7 +184,9 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
     """Test probe: 0 = L, 1 = Linv, 2 = Kzz + jitter (float64 [Mp, Mp]); 3 = A (float32 [N, Mp])."""
     mp = C.c_int(0)
     Mp = 32 if M <= 32 else 64 if M <= 64 else (M + 127) // 128 * 128
-    if which == 3:
+    if which == 4:
+        out = torch.empty(32, device=ws.device, dtype=torch.int64)
+    elif which == 3:
         out = torch.empty(N, Mp, device=ws.device, dtype=torch.float32)
     else:
         out = torch.empty(Mp, Mp, device=ws.device, dtype=torch.float64)

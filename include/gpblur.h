@@ -138,7 +138,8 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
 
 /* Debug / test probes into the workspace of the last forward on (ws): copies device-to-device.
  * which: 0 = L (fp64 [Mp,Mp]), 1 = Linv (fp64 [Mp,Mp]), 2 = Kzz+jitter (fp64 [Mp,Mp]),
- *        3 = A (fp32 [N,Mp]).  Returns the padded inducing count Mp via *mp. */
+ *        3 = A (fp32 [N,Mp]), 4 = phase timestamps of the M x M kernels (uint64 ns [32]).
+ *        Returns the padded inducing count Mp via *mp. */
 int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
                        size_t out_bytes, int* mp, void* stream);
 
