@@ -26,11 +26,12 @@ enum { VS_GMU = 0, VS_RSUM = 1, VS_GVAR = 2, VS_COUNT = 4 };
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
-// padded inducing count: 32, 64, or a multiple of 128
+// padded inducing count: 32, 64, 128, or a multiple of 256 (the column-block width of the tensor-core kernels)
 __host__ __device__ inline int padded_m(int M) {
   if (M <= 32) return 32;
   if (M <= 64) return 64;
-  return round_up(M, 128);
+  if (M <= 128) return 128;
+  return round_up(M, 256);
 }
 // padded input dim: 16, 32, 64 or 128
 __host__ __device__ inline int padded_d(int D) {
@@ -54,6 +55,49 @@ struct WsLayout {
   size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64, rrow, cpart;
   size_t total;
 };
+
+// ---- UMMA slab images of the constant operands (tensor-core path) -------------------------------------------
+// Every image is [hi plane | lo plane], a plane is [8 k-chunks][rows][4 floats] (64 * rows floats per image).
+// The inducing dimension is processed in column blocks of width BW = min(MP, 256).
+__host__ __device__ inline int tc_bw(int MP) { return MP >= 256 ? 256 : MP; }
+// Z~ images: block q (rows m = q BW + r, r < BW), d-slab ds (k = d)
+__host__ __device__ inline size_t tc_zt_image(int MP, int nds, int q, int ds) {
+  return (size_t)(q * nds + ds) * 64 * tc_bw(MP);
+}
+// forward Linv images: output block p (rows i in block p), global k-slab s (k = j in [32 s, 32 s + 32)), s < (p + 1) BW / 32.
+// rows i run from max(p BW, 32 s) to (p + 1) BW.  Returns the float offset, *rows the row count.
+__host__ __device__ inline size_t tc_linv_image(int MP, int p, int s, int* rows) {
+  const int BW = tc_bw(MP), spb = BW / 32;
+  size_t off = 0;
+  for (int pp = 0; pp < p; ++pp)
+    off += (size_t)64 * ((size_t)pp * spb * BW + (size_t)BW * spb - (size_t)16 * spb * (spb - 1));
+  for (int ss = 0; ss < s; ++ss) {
+    const int lo = ss * 32 > p * BW ? ss * 32 : p * BW;
+    off += (size_t)64 * ((p + 1) * BW - lo);
+  }
+  const int lo = s * 32 > p * BW ? s * 32 : p * BW;
+  if (rows) *rows = (p + 1) * BW - lo;
+  return off;
+}
+__host__ __device__ inline size_t tc_linv_total(int MP) { return tc_linv_image(MP, MP / tc_bw(MP), 0, nullptr); }
+// backward (diag(c) Linv)^T images: column block p (rows j in [p BW, min((p + 1) BW, 32 (s + 1)))), k-slab s >= p BW / 32
+__host__ __device__ inline size_t tc_lct_image(int MP, int p, int s, int* rows) {
+  const int BW = tc_bw(MP), spb = BW / 32, nsl = MP / 32;
+  size_t off = 0;
+  for (int pp = 0; pp < p; ++pp) {
+    // slabs of block pp itself: rows 32, 64, ..., BW ; slabs above it: BW rows each
+    off += (size_t)64 * ((size_t)16 * spb * (spb + 1) + (size_t)(nsl - (pp + 1) * spb) * BW);
+  }
+  for (int ss = p * spb; ss < s; ++ss) {
+    const int r = 32 * (ss + 1) - p * BW;
+    off += (size_t)64 * (r < BW ? r : BW);
+  }
+  const int r = 32 * (s + 1) - p * BW;
+  if (rows) *rows = r < BW ? r : BW;
+  return off;
+}
+__host__ __device__ inline size_t tc_lct_total(int MP) { return tc_lct_image(MP, MP / tc_bw(MP), MP / 32, nullptr); }
+__host__ __device__ inline size_t tc_slab_ztt(int dpt, int s) { return (size_t)s * 64 * dpt; }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -101,21 +145,24 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     // UMMA slab images, see tc_slab_* helpers below.  Sizes in floats (hi + lo planes).
     const size_t nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
     w.ZtU = take(nds * 64 * MP * 4);
-    w.LinvU = take((64 * nsl * MP - 1024 * nsl * (nsl - 1)) * 4);
-    w.LCTU = take(1024 * nsl * (nsl + 1) * 4);
+    w.LinvU = take(tc_linv_total(w.MP) * 4);
+    w.LCTU = take(tc_lct_total(w.MP) * 4);
     w.ZtTU = take(nsl * 64 * dpt * 4);
   }
   const int tp = w.MP < 128 ? w.MP : 128;
   const int nt = w.MP / tp;
   w.splitsS = choose_splits(N, nt * (nt + 1) / 2);
   w.splitsZ = choose_splits(N, nt);
-  if (w.MP == 128 || w.MP == 256) {
-    // tensor-core reductions: (MP / 128) row tiles x splits CTAs, one wave of 148 SMs, >= 128 rows per split
-    long long s = 148 / (w.MP / 128);
+  if (w.MP >= 128) {
+    // tensor-core reductions: Gram = (MP / 128) row tiles x (MP / 256) column tiles x splitsS CTAs, W^T X =
+    // (MP / 128) row tiles x splitsZ CTAs: about one wave of 148 SMs each, >= 128 rows per split
+    const int qt = w.MP >= 256 ? w.MP / 256 : 1;
     const long long maxs = (N + 127) / 128;
-    if (s > maxs) s = maxs;
-    if (s < 1) s = 1;
-    w.splitsS = w.splitsZ = (int)s;
+    long long sS = 148 / ((w.MP / 128) * qt), sZ = 148 / (w.MP / 128);
+    if (sS > maxs) sS = maxs;
+    if (sZ > maxs) sZ = maxs;
+    w.splitsS = (int)(sS < 1 ? 1 : sS);
+    w.splitsZ = (int)(sZ < 1 ? 1 : sZ);
   }
   w.nvec = kMaxPersist;
   w.vec_len = w.MP + 2 * w.DP + VS_COUNT;
@@ -137,14 +184,6 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.total = o;
   return w;
 }
-
-// float offsets of slab s inside the UMMA slab images (each slab: hi plane [8 chunks][rows][4], then lo plane)
-__host__ __device__ inline size_t tc_slab_zt(int MP, int ds) { return (size_t)ds * 64 * MP; }
-__host__ __device__ inline int tc_rows_linv(int MP, int s) { return MP - 32 * s; }
-__host__ __device__ inline size_t tc_slab_linv(int MP, int s) { return (size_t)64 * s * MP - (size_t)1024 * s * (s - 1); }
-__host__ __device__ inline int tc_rows_lct(int s) { return 32 * (s + 1); }
-__host__ __device__ inline size_t tc_slab_lct(int s) { return (size_t)1024 * s * (s + 1); }
-__host__ __device__ inline size_t tc_slab_ztt(int dpt, int s) { return (size_t)s * 64 * dpt; }
 
 template <typename T>
 __host__ __device__ inline T* ws_ptr(void* ws, size_t off) {

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   }
   GPBLUR_STAMP();
   // ---- constant operands of the tensor-core kernels, pre-split into TF32 hi / lo UMMA slab images ----
-  if (MP == 128 || MP == 256) {
+  if (MP >= 128) {
     auto split = [](float v, float& hi, float& lo) {
       uint32_t h;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
@@ -419,20 +419,22 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       lo = v - hi;
     };
     const int nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
+    const int BW = tc_bw(MP), NP = MP / BW, spb = BW / 32;
     float* ZtU = ws_ptr<float>(a.ws, L.ZtU);
     float* LinvU = ws_ptr<float>(a.ws, L.LinvU);
     float* LCTU = ws_ptr<float>(a.ws, L.LCTU);
     float* ZtTU = ws_ptr<float>(a.ws, L.ZtTU);
-    // Z~ slabs (rows m, k = d):   element (c, r, e) of slab ds = Zt[r][32 ds + 4 c + e]
-    for (int idx = gtid; idx < nds * 8 * MP * 4; idx += gsize) {
-      const int e = idx & 3, r = (idx >> 2) % MP, c = ((idx >> 2) / MP) & 7, ds = (idx >> 2) / (MP * 8);
+    // Z~ images (rows m of block q, k = d):   element (c, r, e) of image (q, ds) = Zt[q BW + r][32 ds + 4 c + e]
+    for (int idx = gtid; idx < NP * nds * 8 * BW * 4; idx += gsize) {
+      const int e = idx & 3, r = (idx >> 2) % BW, c = ((idx >> 2) / BW) & 7, img = (idx >> 2) / (BW * 8);
+      const int q = img / nds, ds = img - q * nds;
       const int d = ds * 32 + c * 4 + e;
-      const float v = (d < DP) ? Zt[(size_t)r * DP + d] : 0.f;
+      const float v = (d < DP) ? Zt[(size_t)(q * BW + r) * DP + d] : 0.f;
       float hi, lo;
       split(v, hi, lo);
-      float* base = ZtU + tc_slab_zt(MP, ds);
-      base[(c * MP + r) * 4 + e] = hi;
-      base[32 * MP + (c * MP + r) * 4 + e] = lo;
+      float* base = ZtU + tc_zt_image(MP, nds, q, ds);
+      base[(c * BW + r) * 4 + e] = hi;
+      base[32 * BW + (c * BW + r) * 4 + e] = lo;
     }
     // Z~^T slabs (rows d, k = m): element (c, r, e) of slab s = Zt[32 s + 4 c + e][r]
     for (int idx = gtid; idx < nsl * 8 * dpt * 4; idx += gsize) {
@@ -445,32 +447,37 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       base[(c * dpt + r) * 4 + e] = hi;
       base[32 * dpt + (c * dpt + r) * 4 + e] = lo;
     }
-    // Linv slabs (forward): slab s holds rows i = 32 s + r (r < MP - 32 s), k = j = 32 s + 4 c + e
-    for (int sl = 0; sl < nsl; ++sl) {
-      const int nr = tc_rows_linv(MP, sl);
-      float* base = LinvU + tc_slab_linv(MP, sl);
-      for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
-        const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
-        const int i = 32 * sl + r, j = 32 * sl + 4 * c + e;
-        const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] : 0.f;
-        float hi, lo;
-        split(v, hi, lo);
-        base[(c * nr + r) * 4 + e] = hi;
-        base[32 * nr + (c * nr + r) * 4 + e] = lo;
+    // Linv images (forward): image (p, s) holds rows i = ilo + r, ilo = max(p BW, 32 s), k = j = 32 s + 4 c + e
+    for (int pp = 0; pp < NP; ++pp) {
+      for (int sl = 0; sl < (pp + 1) * spb; ++sl) {
+        int nr;
+        float* base = LinvU + tc_linv_image(MP, pp, sl, &nr);
+        const int ilo = (pp + 1) * BW - nr;
+        for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
+          const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
+          const int i = ilo + r, j = 32 * sl + 4 * c + e;
+          const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] : 0.f;
+          float hi, lo;
+          split(v, hi, lo);
+          base[(c * nr + r) * 4 + e] = hi;
+          base[32 * nr + (c * nr + r) * 4 + e] = lo;
+        }
       }
     }
-    // (diag(c) Linv)^T slabs (backward): slab s holds rows j = r (r < 32 (s + 1)), k = i = 32 s + 4 c + e
-    for (int sl = 0; sl < nsl; ++sl) {
-      const int nr = tc_rows_lct(sl);
-      float* base = LCTU + tc_slab_lct(sl);
-      for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
-        const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
-        const int i = 32 * sl + 4 * c + e, j = r;
-        const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] * cvec[i] : 0.f;
-        float hi, lo;
-        split(v, hi, lo);
-        base[(c * nr + r) * 4 + e] = hi;
-        base[32 * nr + (c * nr + r) * 4 + e] = lo;
+    // (diag(c) Linv)^T images (backward): image (p, s) holds rows j = p BW + r, k = i = 32 s + 4 c + e
+    for (int pp = 0; pp < NP; ++pp) {
+      for (int sl = pp * spb; sl < nsl; ++sl) {
+        int nr;
+        float* base = LCTU + tc_lct_image(MP, pp, sl, &nr);
+        for (int idx = gtid; idx < 8 * nr * 4; idx += gsize) {
+          const int e = idx & 3, r = (idx >> 2) % nr, c = (idx >> 2) / nr;
+          const int i = 32 * sl + 4 * c + e, j = pp * BW + r;
+          const float v = (j <= i) ? (float)Li64[(size_t)i * MP + j] * cvec[i] : 0.f;
+          float hi, lo;
+          split(v, hi, lo);
+          base[(c * nr + r) * 4 + e] = hi;
+          base[32 * nr + (c * nr + r) * 4 + e] = lo;
+        }
       }
     }
   }

@@ -192,23 +192,25 @@ __device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, 
   });
 }
 
-// xr0 / xr1: the first two d-slabs of this tile's x, already in registers (loaded one tile ahead so that the HBM
-// latency hides behind the previous tile's MMAs and epilogue)
-template <int MP>
-__device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl,
-                                        const float* after_image, int after_rows, float* part_n, float* part_w,
-                                        float* xn_s, float* xw_s, const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1) {
+// S[128, BW] = X~ Z~[block q]^T into TMEM columns [0, BW).  xr0 / xr1: the first two d-slabs of this tile's x when
+// `preloaded` (loaded one tile ahead so that the HBM latency hides behind the previous tile's MMAs and epilogue).
+// With `stats`, per-row |x~|^2 and x~ . (ell w) are folded from per-slab partials in fixed order (deterministic).
+template <int BW>
+__device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl, int q,
+                                        const float* after_image, int after_rows, bool stats, float* part_n,
+                                        float* part_w, float* xn_s, float* xw_s, bool preloaded,
+                                        const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1) {
   const WsLayout& L = a.L;
   const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const int DP = L.DP;
+  const int DP = L.DP, MP = L.MP;
   const int nds = DP >= KT ? DP / KT : 1;
   for (int ds = 0; ds < nds; ++ds) {
     OpRegs<TNP> ra;
-    if (ds == 0) ra = xr0;
-    else if (ds == 1) ra = xr1;
+    if (preloaded && ds == 0) ra = xr0;
+    else if (preloaded && ds == 1) ra = xr1;
     else load_x_slab(ra, xl, ds, DP);
-    {
+    if (stats) {
       // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       const int rr = lane & 7, cq = lane >> 3;
@@ -225,22 +227,25 @@ __device__ __forceinline__ void phase_a(Pipe<MP>& pipe, uint32_t tmem_s, const T
     }
     float *a_hi, *a_lo, *b_hi, *b_lo;
     pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-    pipe.bulk_b(ZtU + tc_slab_zt(MP, ds), MP);        // Z~ slab: TMA bulk copy of the pre-split image
+    pipe.bulk_b(ZtU + tc_zt_image(MP, nds, q, ds), BW);   // Z~ image: TMA bulk copy of the pre-split block
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
     const bool last = ds + 1 == nds;
-    pipe.commit(tmem_s, MP, ds == 0, MP, last ? after_image : ZtU + tc_slab_zt(MP, ds + 1), last ? after_rows : MP);
-    // commit() synchronised the CTA: fold this slab's 8 chunk partials in fixed order (bit-deterministic)
-    if (threadIdx.x < TNP) {
-      float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
+    pipe.commit(tmem_s, BW, ds == 0, BW, last ? after_image : ZtU + tc_zt_image(MP, nds, q, ds + 1),
+                last ? after_rows : BW);
+    if (stats) {
+      // commit() synchronised the CTA: fold this slab's 8 chunk partials in fixed order (bit-deterministic)
+      if (threadIdx.x < TNP) {
+        float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
 #pragma unroll
-      for (int c = 0; c < KT / 4; ++c) {
-        n2 += part_n[c * TNP + threadIdx.x];
-        xw += part_w[c * TNP + threadIdx.x];
+        for (int c = 0; c < KT / 4; ++c) {
+          n2 += part_n[c * TNP + threadIdx.x];
+          xw += part_w[c * TNP + threadIdx.x];
+        }
+        xn_s[threadIdx.x] = n2;
+        xw_s[threadIdx.x] = xw;
       }
-      xn_s[threadIdx.x] = n2;
-      xw_s[threadIdx.x] = xw;
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -255,28 +260,33 @@ __device__ __forceinline__ void kernel_values(float (&v)[32], float xn, const fl
 }
 
 // =================================================================================================
-// forward
+// forward.  The inducing dimension is processed in column blocks of width BW (= min(MP, 256), the TMEM budget:
+// S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
+// cross-covariance blocks q <= p (Linv is lower triangular); for MP > 256 block q is recomputed for every p >= q.
 // =================================================================================================
-template <int MP>
+template <int BW>
 __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float zn_s[MP], m_s[MP], c_s[MP];
+  __shared__ float zn_s[GPBLUR_MAX_M], m_s[GPBLUR_MAX_M], c_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
   __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];   // per-slab row-statistic partials
 
   const WsLayout& L = a.L;
-  const int M = L.M;
+  const int M = L.M, MP = L.MP;
+  const int NP = MP / BW, SPB = BW / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
   const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
+  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   float* Ag = ws_ptr<float>(a.ws, L.A);
   const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
 
-  constexpr uint32_t TMEM_COLS = 2 * MP;
+  constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
@@ -293,8 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + MP;
-  Pipe<MP> pipe;
+  const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
+  Pipe<BW> pipe;
   pipe.init(stage_base, bars);
 
   const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
@@ -309,65 +319,80 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
   }
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
-    const XLoader xl = make_xloader(a, n0);
-    phase_a<MP>(pipe, tmem_s, a, xl, LinvU, MP, part_n, part_w, xn_s, xw_s, xr0, xr1);    // prefetches the first Linv slab
-    if (tile + (int)gridDim.x < a.ntiles) {        // next tile's x: in flight during phase B and the epilogue
-      const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-      load_x_slab(xr0, xln, 0, L.DP);
-      if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
-    }
-    pipe.drain();                                   // S complete
-    const float xn = xn_s[row];
-
-    // ---- phase B: A[:, i >= 32 s] += k[:, slab s] Linv[i, slab s]^T ----
-    for (int s = 0; s < MP / KT; ++s) {
-      const int i0 = s * KT;                        // only rows i >= 32 s of Linv see this slab (lower triangular)
-      // epilogue A of this 32-column chunk: the two column halves of a lane quadrant take 16 columns each
-      float v[16];
-      const int col0 = s * KT + half * 16;
-      tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int m = col0 + i;
-        const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-        v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
-      }
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-      pipe.bulk_b(LinvU + tc_slab_linv(MP, s), MP - i0);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)                   // k-chunks half * 4 + c of the slab
-        tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
-                        make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
-      tc::tc_fence_before();
-      const bool last = s + 1 == MP / KT;
-      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      const float* nxt = last ? (more_tiles ? ws_cptr<float>(a.ws, L.ZtU) : nullptr) : LinvU + tc_slab_linv(MP, s + 1);
-      pipe.commit(tmem_a + i0, MP - i0, s == 0, MP - i0, nxt, last ? MP : MP - i0 - KT);
-    }
-    pipe.drain();
-
-    // ---- epilogue B: mean / variance of the own point from its half of the columns; save A ----
-    float mu = 0.f, vv = 0.f;
     const long long gn = n0 + row;
+    const XLoader xl = make_xloader(a, n0);
+    const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+    float mu = 0.f, vv = 0.f;
+    for (int p = 0; p < NP; ++p) {
+      for (int q = 0; q <= p; ++q) {
+        int rows0;
+        const float* first_linv = LinvU + tc_linv_image(MP, p, q * SPB, &rows0);
+        const bool first_pass = p == 0 && q == 0;
+        phase_a<BW>(pipe, tmem_s, a, xl, q, first_linv, rows0, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0,
+                    xr1);
+        if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
+          const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+          load_x_slab(xr0, xln, 0, L.DP);
+          if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+        }
+        pipe.drain();                               // S of block q complete
+        const float xn = xn_s[row];
+        // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
+        for (int sl = 0; sl < SPB; ++sl) {
+          const int s = q * SPB + sl;               // global k-slab
+          // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
+          float v[16];
+          const int col0 = sl * KT + half * 16;
+          tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int m = q * BW + col0 + i;
+            const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
+            v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
+          }
+          int rows;
+          const float* img = LinvU + tc_linv_image(MP, p, s, &rows);
+          float *a_hi, *a_lo, *b_hi, *b_lo;
+          pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+          pipe.bulk_b(img, rows);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)               // k-chunks half * 4 + c of the slab
+            tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
+                            make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+          tc::tc_fence_before();
+          // what to prefetch next: the next Linv slab of this block, else the Z~ image of the next (p, q) / tile
+          const float* nxt = nullptr;
+          int nxt_rows = BW;
+          if (sl + 1 < SPB) nxt = LinvU + tc_linv_image(MP, p, s + 1, &nxt_rows);
+          else if (q < p) nxt = ZtU + tc_zt_image(MP, nds, q + 1, 0);
+          else if (p + 1 < NP || more_tiles) nxt = ZtU + tc_zt_image(MP, nds, 0, 0);
+          pipe.commit(tmem_a + (uint32_t)(BW - rows), rows, q == 0 && sl == 0, rows, nxt, nxt_rows);
+        }
+      }
+      pipe.drain();
+      // ---- epilogue of output block p: mean / variance partials of the own point; save A ----
 #pragma unroll 1
-    for (int ch = 0; ch < MP / 64; ++ch) {
-      const int col = half * (MP / 2) + ch * 32;
-      float v[32];
-      tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
+      for (int ch = 0; ch < BW / 64; ++ch) {
+        const int col = half * (BW / 2) + ch * 32;
+        float v[32];
+        tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
+        const int gcol = p * BW + col;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mu = fmaf(v[i], m_s[col + i], mu);
-        vv = fmaf(c_s[col + i] * v[i], v[i], vv);
-      }
-      if (L.training && gn < N) {
-        float* dst = Ag + (size_t)gn * MP + col;
+        for (int i = 0; i < 32; ++i) {
+          mu = fmaf(v[i], m_s[gcol + i], mu);
+          vv = fmaf(c_s[gcol + i] * v[i], v[i], vv);
+        }
+        if (L.training && gn < N) {
+          float* dst = Ag + (size_t)gn * MP + gcol;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
       }
+      tc::tc_fence_before();
+      __syncthreads();                              // TMEM reads done before the next block's MMAs overwrite
+      tc::tc_fence_after();
     }
     if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
-    tc::tc_fence_before();
     __syncthreads();
     if (half == 0 && gn < N) {
       const float mean = mu + mu_s[row] + xw_s[row] + cwb;
@@ -377,7 +402,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
       if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
     }
     __syncthreads();
-    tc::tc_fence_after();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -385,31 +409,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
 }
 
 // =================================================================================================
-// backward: W = kbar o k and its row sums
+// backward: W = kbar o k and its row sums, one column block p of width BW at a time
 // =================================================================================================
-template <int MP>
+template <int BW>
 __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float zn_s[MP], beta_s[MP];
+  __shared__ float zn_s[GPBLUR_MAX_M], beta_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
   __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];
 
   const WsLayout& L = a.L;
-  const int M = L.M;
+  const int M = L.M, MP = L.MP;
+  const int NP = MP / BW, SPB = BW / KT, NSL = MP / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
   const float* LCTU = ws_cptr<float>(a.ws, L.LCTU);
+  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
   float* rrow = ws_ptr<float>(a.ws, L.rrow);
   const float os = hyp[H_OS];
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
 
-  constexpr uint32_t TMEM_COLS = 2 * MP;
+  constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
@@ -425,8 +452,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + MP;
-  Pipe<MP> pipe;
+  const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + BW;
+  Pipe<BW> pipe;
   pipe.init(stage_base, bars);
 
   const int quad = warp & 3, half = warp >> 2;
@@ -441,39 +468,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
   }
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
-    const XLoader xl = make_xloader(a, n0);
-    phase_a<MP>(pipe, tmem_s, a, xl, LCTU + tc_slab_lct(MP / KT - 1), MP, part_n, part_w, xn_s, xw_s, xr0, xr1);
-    if (tile + (int)gridDim.x < a.ntiles) {
-      const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-      load_x_slab(xr0, xln, 0, L.DP);
-      if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
-    }
-
-    // ---- phase B': T[:, j < 32 (s + 1)] += a[:, slab s] (diag(c) Linv)[slab s, j], slabs in DEcreasing order ----
-    auto load_a = [&](OpRegs<TNP>& regs, int sl) {
-      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-        long long gn = n0 + r;
-        if (gn >= N) gn = N - 1;                       // clamped rows carry g = 0 below
-        return ldg4(Ag + (size_t)gn * MP + sl * KT + c * 4);
-      });
-    };
-    OpRegs<TNP> ra;
-    load_a(ra, MP / KT - 1);
-    for (int s = MP / KT - 1; s >= 0; --s) {
-      const int i0 = s * KT;
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-      pipe.bulk_b(LCTU + tc_slab_lct(s), i0 + KT);
-      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      if (s > 0) load_a(ra, s - 1);                   // next slab's saved-A tile flies during the MMAs
-      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      const float* nxt = s > 0 ? LCTU + tc_slab_lct(s - 1) : (more_tiles ? ws_cptr<float>(a.ws, L.ZtU) : nullptr);
-      pipe.commit(tmem_t, i0 + KT, s == MP / KT - 1, i0 + KT, nxt, s > 0 ? i0 : MP);
-    }
-    pipe.drain();
-
-    // ---- fold the upstream gradients of this thread's point ----
     const long long gn = n0 + row;
+    const XLoader xl = make_xloader(a, n0);
+    const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+    // ---- fold the upstream gradients of this thread's point ----
     float gm = 0.f, gv = 0.f;
     if (gn < N) {
       if (a.g_mean) gm = a.g_mean[gn];
@@ -488,33 +486,75 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
       if (v <= kMinVariance) gv = 0.f;
       if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
     }
-    const float xn = xn_s[row];
+    auto load_a = [&](OpRegs<TNP>& regs, int sl) {
+      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
+        long long g2 = n0 + r;
+        if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
+        return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
+      });
+    };
     float rsum = 0.f;
+    for (int p = 0; p < NP; ++p) {
+      int rows_top;
+      const float* top_img = LCTU + tc_lct_image(MP, p, NSL - 1, &rows_top);
+      phase_a<BW>(pipe, tmem_s, a, xl, p, top_img, rows_top, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
+      if (p == 0 && more_tiles) {
+        const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+        load_x_slab(xr0, xln, 0, L.DP);
+        if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+      }
+      // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
+      OpRegs<TNP> ra;
+      load_a(ra, NSL - 1);
+      for (int s = NSL - 1; s >= p * SPB; --s) {
+        int rows;
+        const float* img = LCTU + tc_lct_image(MP, p, s, &rows);
+        float *a_hi, *a_lo, *b_hi, *b_lo;
+        pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+        pipe.bulk_b(img, rows);
+        store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+        const float* nxt = nullptr;
+        int nxt_rows = BW;
+        if (s > p * SPB) {
+          load_a(ra, s - 1);                          // next slab's saved-A tile flies during the MMAs
+          nxt = LCTU + tc_lct_image(MP, p, s - 1, &nxt_rows);
+        } else if (p + 1 < NP) {
+          nxt = ZtU + tc_zt_image(MP, nds, p + 1, 0);
+        } else if (more_tiles) {
+          nxt = ZtU + tc_zt_image(MP, nds, 0, 0);
+        }
+        pipe.commit(tmem_t, rows, s == NSL - 1, rows, nxt, nxt_rows);
+      }
+      pipe.drain();
+      const float xn = xn_s[row];
 #pragma unroll 1
-    for (int ch = 0; ch < MP / 64; ++ch) {
-      const int col = half * (MP / 2) + ch * 32;
-      float k[32], t[32];
-      tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
-      tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
-      kernel_values(k, xn, zn_s, col, M, os);
+      for (int ch = 0; ch < BW / 64; ++ch) {
+        const int col = half * (BW / 2) + ch * 32;
+        const int gcol = p * BW + col;
+        float k[32], t[32];
+        tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
+        tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
+        kernel_values(k, xn, zn_s, gcol, M, os);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[col + i]);
-        t[i] = kb * k[i];
-        rsum += t[i];
-      }
-      if (gn < N) {
-        float* dst = Wg + (size_t)gn * MP + col;
+        for (int i = 0; i < 32; ++i) {
+          const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[gcol + i]);
+          t[i] = kb * k[i];
+          rsum += t[i];
+        }
+        if (gn < N) {
+          float* dst = Wg + (size_t)gn * MP + gcol;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+        }
       }
+      tc::tc_fence_before();
+      __syncthreads();
+      tc::tc_fence_after();
     }
     if (half == 1) r_s[row] = rsum;
-    tc::tc_fence_before();
     __syncthreads();
     if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
     __syncthreads();
-    tc::tc_fence_after();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -739,7 +779,7 @@ void set_smem(K kernel, size_t bytes) {
 
 bool tc_point_supported(const WsLayout& L) {
   if (tile_override("GPBLUR_TC") < 0) return false;       // GPBLUR_TC=-1 forces the FP32 FFMA kernels
-  return (L.MP == 128 || L.MP == 256) && L.N >= 1;
+  return (L.MP == 128 || (L.MP >= 256 && L.MP % 256 == 0)) && L.N >= 1;
 }
 
 int tc_vector_partials(const WsLayout& L) { return tc_grid(L); }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int p0 = blockIdx.x * 128;
+  const int q0 = blockIdx.z * TQ;               // column tile (Gram with MP > 256)
   const long long r0 = (long long)blockIdx.y * a.rows_per_split;
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.N) r1 = a.N;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const long long n = n0 + 4 * c + e;
-          v[e] = (n < r1 && bq < a.vcols) ? a.V[(size_t)n * a.ldv + bq] : 0.f;
+          v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
         }
         breg[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
@@ -176,13 +177,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      float* dst = Cs + (size_t)(p0 + row) * a.ldc + col;
+      float* dst = Cs + (size_t)(p0 + row) * a.ldc + q0 + col;
 #pragma unroll
       for (int i = 0; i < 32; i += 4)
-        if (col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (q0 + col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
   }
-  if (a.uvec) {
+  if (a.uvec && blockIdx.z == 0) {
     ured[acg][ar] = usum;
     __syncthreads();
     if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
 }
 
 template <int TQ, bool GRAM>
-int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t st) {
+int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t st, int qtiles = 1) {
   static bool configured = false;
   const size_t smem = TcSmem<TQ>::bytes;
   if (!configured) {
@@ -201,7 +202,7 @@ int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t
     configured = true;
   }
   ProfScope ps(GRAM ? ST_GRAM : ST_WX, st);
-  tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits), kThreads, smem, st>>>(a);
+  tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits, qtiles), kThreads, smem, st>>>(a);
   note_launch();
   return check_launch("tc_reduce");
 }
@@ -223,7 +224,7 @@ int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream
   g.N = L.N; g.ldu = MP; g.ldv = MP; g.vcols = MP; g.P = MP; g.ldc = MP;
   g.rows_per_split = rows(L.splitsS);
   int rc = (MP == 128) ? launch_tc_reduce<128, true>(g, 1, L.splitsS, st)
-                       : launch_tc_reduce<256, true>(g, 2, L.splitsS, st);
+                       : launch_tc_reduce<256, true>(g, MP / 128, L.splitsS, st, MP / 256);
   if (rc) return rc;
   TcReduceArgs w{};
   w.U = ws_cptr<float>(ws, L.W); w.V = x; w.sc = nullptr; w.gm = nullptr;
