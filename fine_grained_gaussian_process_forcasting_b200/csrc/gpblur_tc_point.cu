@@ -36,6 +36,7 @@ struct TcPointArgs {
   uint64_t seed, offset;
   uint32_t stream_id;
   int ntiles;
+  long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
 };
 
 template <int NB>   // NB = row capacity of the B operand planes
@@ -45,17 +46,35 @@ struct Stage {
   static constexpr int FLOATS = 2 * A_PLANE + 2 * B_PLANE;
 };
 
-// two-stage operand ring.  bars[0..1]: "MMAs that read this stage are done" (tcgen05.commit);
-// bars[2..3]: "the TMA bulk copy of this stage's B planes has landed" (mbarrier complete_tx).
+constexpr int kIssuerWarp = kThreads / 32;         // warp 8: the dedicated TMA / MMA issuer
+constexpr int kBlockThreads = kThreads + 32;       // 8 producer / epilogue warps + the issuer warp
+
+// named barrier among the 256 producer threads only (the issuer warp never joins it)
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// Two-stage operand ring shared by the producer warps (0..7) and the issuer warp (8).  Both roles run the SAME slab
+// schedule (same loops, same counters); producers never wait for the issuer except through the barriers below:
+//   bars[0..1] mma_done : tcgen05.commit - the MMAs that read stage st have retired (stage reusable)
+//   bars[2..3] b_full   : the TMA bulk copy of stage st's B planes has landed (complete_tx)
+//   bars[4..5] a_ready  : all 256 producers have written (and proxy-fenced) stage st's A planes
 template <int NB>
 struct Pipe {
   float* base;
   uint64_t* bars;
-  uint32_t uses[2], fulls[2];
+  uint32_t uses[2];
   int slab;
   bool prefetched;
+  bool issuer;     // role of the calling warp
+  bool elect;      // the one issuing thread (lane 0 of the issuer warp)
+  long long iseg[6];   // issuer cycle accounting (debug)
   __device__ __forceinline__ void init(float* b, uint64_t* br) {
-    base = b; bars = br; uses[0] = uses[1] = 0; fulls[0] = fulls[1] = 0; slab = 0; prefetched = false;
+    base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; prefetched = false;
+    issuer = (threadIdx.x >> 5) == kIssuerWarp;
+    elect = threadIdx.x == kThreads;
+    for (int i = 0; i < 6; ++i) iseg[i] = 0;
   }
   __device__ __forceinline__ void planes(int st, float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) const {
     a_hi = base + st * Stage<NB>::FLOATS;
@@ -63,13 +82,12 @@ struct Pipe {
     b_hi = a_lo + Stage<NB>::A_PLANE;
     b_lo = b_hi + Stage<NB>::B_PLANE;
   }
-  // wait until the MMAs that last read this stage are done, return its planes
+  // producers: wait until the MMAs that last read this stage have retired, return its planes
   __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) {
     const int st = slab & 1;
-    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+    if (!issuer && uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
     planes(st, a_hi, a_lo, b_hi, b_lo);
   }
-  // thread 0: pull a pre-split B slab image (hi plane then lo plane, `rows` rows each) into stage `st`
   __device__ __forceinline__ void issue_bulk(int st, const float* image, int rows) {
     float *a_hi, *a_lo, *b_hi, *b_lo;
     planes(st, a_hi, a_lo, b_hi, b_lo);
@@ -78,42 +96,61 @@ struct Pipe {
     tc::bulk_g2s(b_hi, image, bytes, &bars[2 + st]);
     tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
   }
-  // B operand of the CURRENT slab; a no-op when the previous commit() already prefetched it
+  // issuer: B operand of the CURRENT slab (a no-op when the previous commit() already prefetched it)
   __device__ __forceinline__ void bulk_b(const float* image, int rows) {
-    if (threadIdx.x == 0 && !prefetched) issue_bulk(slab & 1, image, rows);
+    if (elect && !prefetched) {
+      const int st = slab & 1;
+      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+      issue_bulk(st, image, rows);
+    }
   }
-  // publish the stage to the tensor core, issue N-column MMAs into tmem_d, then (thread 0) start the TMA copy of the
-  // NEXT slab's B image into the other stage as soon as the MMAs that still read it have retired, so that its
-  // latency hides behind the production of the next A operand.
+  // producers: publish this stage's A planes (no CTA barrier).  issuer: wait for A and B, issue the N-column MMAs
+  // into tmem_d, commit, then start the TMA copy of the NEXT slab's B image into the other stage as soon as the
+  // MMAs that still read it have retired.
   __device__ __forceinline__ void commit(uint32_t tmem_d, int ncols, bool first, int b_rows, const float* next_image,
                                          int next_rows) {
     const int st = slab & 1;
-    tc::fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tc::mbar_wait(&bars[2 + st], fulls[st] & 1);
+    const uint32_t phase = uses[st] & 1;
+    if (!issuer) {
+      tc::tc_fence_before();
+      tc::fence_async_smem();
+      mbar_arrive(&bars[4 + st]);
+    } else if (elect) {
+      long long t0 = clock64(), t1;
+      tc::mbar_wait(&bars[4 + st], phase);
+      t1 = clock64(); iseg[0] += t1 - t0; t0 = t1;
+      tc::mbar_wait(&bars[2 + st], phase);
+      t1 = clock64(); iseg[1] += t1 - t0; t0 = t1;
       tc::tc_fence_after();
       float *a_hi, *a_lo, *b_hi, *b_lo;
       planes(st, a_hi, a_lo, b_hi, b_lo);
       tc::issue_slab_3xtf32<KT, NB>(tmem_d, a_hi, a_lo, b_hi, b_lo, tc::make_idesc_tf32(TNP, ncols), first, b_rows);
       tc::umma_commit(&bars[st]);
+      t1 = clock64(); iseg[2] += t1 - t0; t0 = t1;
       if (next_image) {
         const int nst = st ^ 1;
         if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
+        t1 = clock64(); iseg[3] += t1 - t0; t0 = t1;
         issue_bulk(nst, next_image, next_rows);
+        t1 = clock64(); iseg[4] += t1 - t0; t0 = t1;
       }
     }
     uses[st] += 1;
-    fulls[st] += 1;
     slab += 1;
     prefetched = next_image != nullptr;
   }
-  // block until every MMA issued so far has completed
+  // producers: block until every MMA issued so far has completed
   __device__ __forceinline__ void drain() {
-    if (slab == 0) return;
+    if (issuer || slab == 0) return;
     const int st = (slab - 1) & 1;
     tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
     tc::tc_fence_after();
+  }
+  __device__ __forceinline__ static void init_barriers(uint64_t* br) {
+    tc::mbar_init(&br[0], 1); tc::mbar_init(&br[1], 1);
+    tc::mbar_init(&br[2], 1); tc::mbar_init(&br[3], 1);
+    tc::mbar_init(&br[4], kThreads); tc::mbar_init(&br[5], kThreads);
+    tc::fence_barrier_init();
   }
 };
 
@@ -205,12 +242,15 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const T
   const float* wl = ws_cptr<float>(a.ws, L.wl);
   const int DP = L.DP, MP = L.MP;
   const int nds = DP >= KT ? DP / KT : 1;
+  const bool prod = !pipe.issuer;
   for (int ds = 0; ds < nds; ++ds) {
     OpRegs<TNP> ra;
-    if (preloaded && ds == 0) ra = xr0;
-    else if (preloaded && ds == 1) ra = xr1;
-    else load_x_slab(ra, xl, ds, DP);
-    if (stats) {
+    if (prod) {
+      if (preloaded && ds == 0) ra = xr0;
+      else if (preloaded && ds == 1) ra = xr1;
+      else load_x_slab(ra, xl, ds, DP);
+    }
+    if (prod && stats) {
       // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       const int rr = lane & 7, cq = lane >> 3;
@@ -228,12 +268,13 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const T
     float *a_hi, *a_lo, *b_hi, *b_lo;
     pipe.acquire(a_hi, a_lo, b_hi, b_lo);
     pipe.bulk_b(ZtU + tc_zt_image(MP, nds, q, ds), BW);   // Z~ image: TMA bulk copy of the pre-split block
-    store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+    if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
     const bool last = ds + 1 == nds;
     pipe.commit(tmem_s, BW, ds == 0, BW, last ? after_image : ZtU + tc_zt_image(MP, nds, q, ds + 1),
                 last ? after_rows : BW);
-    if (stats) {
-      // commit() synchronised the CTA: fold this slab's 8 chunk partials in fixed order (bit-deterministic)
+    if (prod && stats) {
+      // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
+      prod_sync();
       if (threadIdx.x < TNP) {
         float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
 #pragma unroll
@@ -244,7 +285,7 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const T
         xn_s[threadIdx.x] = n2;
         xw_s[threadIdx.x] = xw;
       }
-      __syncthreads();
+      prod_sync();
     }
   }
 }
@@ -265,10 +306,10 @@ __device__ __forceinline__ void kernel_values(float (&v)[32], float xn, const fl
 // cross-covariance blocks q <= p (Linv is lower triangular); for MP > 256 block q is recomputed for every p >= q.
 // =================================================================================================
 template <int BW>
-__global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[GPBLUR_MAX_M], m_s[GPBLUR_MAX_M], c_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
@@ -288,31 +329,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], 1);
-    tc::mbar_init(&bars[3], 1);
-    tc::fence_barrier_init();
-  }
-  for (int i = tid; i < MP; i += kThreads) {
-    zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
-    m_s[i] = ws_cptr<float>(a.ws, L.mvec)[i];
-    c_s[i] = ws_cptr<float>(a.ws, L.cvec)[i];
-  }
+  if (tid == 0) Pipe<1>::init_barriers(bars);
+  if (tid < kThreads)
+    for (int i = tid; i < MP; i += kThreads) {
+      zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+      m_s[i] = ws_cptr<float>(a.ws, L.mvec)[i];
+      c_s[i] = ws_cptr<float>(a.ws, L.cvec)[i];
+    }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
   Pipe<BW> pipe;
   pipe.init(stage_base, bars);
+  const bool prod = !pipe.issuer;                   // warps 0..7 produce operands and run the epilogues
 
   const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
   const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
   const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
+  long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define SEG(i) do { if (a.dbg) { const long long tnow = clock64(); seg[i] += tnow - tlast; tlast = tnow; } } while (0)
   OpRegs<TNP> xr0, xr1;
-  {
+  if (prod) {
     const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
     load_x_slab(xr0, xl0, 0, L.DP);
     if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
@@ -323,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
     const XLoader xl = make_xloader(a, n0);
     const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
     float mu = 0.f, vv = 0.f;
+    SEG(7);
     for (int p = 0; p < NP; ++p) {
       for (int q = 0; q <= p; ++q) {
         int rows0;
@@ -330,47 +371,58 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
         const bool first_pass = p == 0 && q == 0;
         phase_a<BW>(pipe, tmem_s, a, xl, q, first_linv, rows0, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0,
                     xr1);
-        if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
+        if (prod && first_pass && more_tiles) {     // next tile's x: in flight during the MMAs and epilogues
           const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
           load_x_slab(xr0, xln, 0, L.DP);
           if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
         }
+        SEG(0);                                     // phase A (x split, Z~ bulk, S MMAs issued)
         pipe.drain();                               // S of block q complete
-        const float xn = xn_s[row];
+        SEG(1);
+        const float xn = prod ? xn_s[row] : 0.f;
         // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
         for (int sl = 0; sl < SPB; ++sl) {
           const int s = q * SPB + sl;               // global k-slab
           // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
           float v[16];
           const int col0 = sl * KT + half * 16;
-          tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
+          if (prod) {
+            tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int m = q * BW + col0 + i;
-            const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-            v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
+            for (int i = 0; i < 16; ++i) {
+              const int m = q * BW + col0 + i;
+              const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
+              v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
+            }
           }
+          SEG(2);                                   // TMEM load + exp
           int rows;
           const float* img = LinvU + tc_linv_image(MP, p, s, &rows);
           float *a_hi, *a_lo, *b_hi, *b_lo;
           pipe.acquire(a_hi, a_lo, b_hi, b_lo);
+          SEG(3);                                   // stage acquire (MMA s-2 retired)
           pipe.bulk_b(img, rows);
+          if (prod) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)               // k-chunks half * 4 + c of the slab
-            tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
-                            make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
-          tc::tc_fence_before();
+            for (int c = 0; c < 4; ++c)             // k-chunks half * 4 + c of the slab
+              tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
+                              make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+          }
           // what to prefetch next: the next Linv slab of this block, else the Z~ image of the next (p, q) / tile
           const float* nxt = nullptr;
           int nxt_rows = BW;
           if (sl + 1 < SPB) nxt = LinvU + tc_linv_image(MP, p, s + 1, &nxt_rows);
           else if (q < p) nxt = ZtU + tc_zt_image(MP, nds, q + 1, 0);
           else if (p + 1 < NP || more_tiles) nxt = ZtU + tc_zt_image(MP, nds, 0, 0);
+          SEG(4);                                   // split + store of the k slab
           pipe.commit(tmem_a + (uint32_t)(BW - rows), rows, q == 0 && sl == 0, rows, nxt, nxt_rows);
+          SEG(5);                                   // fence + barrier (+ thread 0: wait B, issue MMAs, prefetch)
         }
       }
       pipe.drain();
+      SEG(1);
       // ---- epilogue of output block p: mean / variance partials of the own point; save A ----
+      if (prod) {
 #pragma unroll 1
       for (int ch = 0; ch < BW / 64; ++ch) {
         const int col = half * (BW / 2) + ch * 32;
@@ -388,12 +440,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
       }
-      tc::tc_fence_before();
-      __syncthreads();                              // TMEM reads done before the next block's MMAs overwrite
-      tc::tc_fence_after();
+      }   // the next MMAs into these columns are issued only after every producer's next commit(), which fences
+      SEG(6);                                       // block epilogue
     }
+    if (prod) {
     if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
-    __syncthreads();
+    prod_sync();
     if (half == 0 && gn < N) {
       const float mean = mu + mu_s[row] + xw_s[row] + cwb;
       const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
@@ -401,8 +453,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
       a.var[gn] = var;
       if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
     }
-    __syncthreads();
+    prod_sync();
+    }
   }
+  if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
+    for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
+  if (a.dbg && blockIdx.x == 0 && pipe.elect)
+    for (int i = 0; i < 6; ++i) a.dbg[16 + i] = pipe.iseg[i];
+#undef SEG
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
@@ -412,10 +470,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_fwd_kernel(TcPointArgs a
 // backward: W = kbar o k and its row sums, one column block p of width BW at a time
 // =================================================================================================
 template <int BW>
-__global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   __shared__ float zn_s[GPBLUR_MAX_M], beta_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
@@ -438,30 +496,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], 1);
-    tc::mbar_init(&bars[3], 1);
-    tc::fence_barrier_init();
-  }
-  for (int i = tid; i < MP; i += kThreads) {
-    zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
-    beta_s[i] = ws_cptr<float>(a.ws, L.beta)[i];
-  }
+  if (tid == 0) Pipe<1>::init_barriers(bars);
+  if (tid < kThreads)
+    for (int i = tid; i < MP; i += kThreads) {
+      zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+      beta_s[i] = ws_cptr<float>(a.ws, L.beta)[i];
+    }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + BW;
   Pipe<BW> pipe;
   pipe.init(stage_base, bars);
+  const bool prod = !pipe.issuer;
 
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
   const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
   OpRegs<TNP> xr0, xr1;
-  {
+  if (prod) {
     const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
     load_x_slab(xr0, xl0, 0, L.DP);
     if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
@@ -473,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
     const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
     // ---- fold the upstream gradients of this thread's point ----
     float gm = 0.f, gv = 0.f;
-    if (gn < N) {
+    if (prod && gn < N) {
       if (a.g_mean) gm = a.g_mean[gn];
       if (a.g_var) gv = a.g_var[gn];
       const float v = a.var_in[gn];
@@ -498,25 +552,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
       int rows_top;
       const float* top_img = LCTU + tc_lct_image(MP, p, NSL - 1, &rows_top);
       phase_a<BW>(pipe, tmem_s, a, xl, p, top_img, rows_top, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
-      if (p == 0 && more_tiles) {
+      if (prod && p == 0 && more_tiles) {
         const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
         load_x_slab(xr0, xln, 0, L.DP);
         if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
       }
       // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
       OpRegs<TNP> ra;
-      load_a(ra, NSL - 1);
+      if (prod) load_a(ra, NSL - 1);
       for (int s = NSL - 1; s >= p * SPB; --s) {
         int rows;
         const float* img = LCTU + tc_lct_image(MP, p, s, &rows);
         float *a_hi, *a_lo, *b_hi, *b_lo;
         pipe.acquire(a_hi, a_lo, b_hi, b_lo);
         pipe.bulk_b(img, rows);
-        store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+        if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
         const float* nxt = nullptr;
         int nxt_rows = BW;
         if (s > p * SPB) {
-          load_a(ra, s - 1);                          // next slab's saved-A tile flies during the MMAs
+          if (prod) load_a(ra, s - 1);                // next slab's saved-A tile flies during the MMAs
           nxt = LCTU + tc_lct_image(MP, p, s - 1, &nxt_rows);
         } else if (p + 1 < NP) {
           nxt = ZtU + tc_zt_image(MP, nds, p + 1, 0);
@@ -526,6 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
         pipe.commit(tmem_t, rows, s == NSL - 1, rows, nxt, nxt_rows);
       }
       pipe.drain();
+      if (prod) {
       const float xn = xn_s[row];
 #pragma unroll 1
       for (int ch = 0; ch < BW / 64; ++ch) {
@@ -547,14 +602,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
           for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
         }
       }
-      tc::tc_fence_before();
-      __syncthreads();
-      tc::tc_fence_after();
+      }
     }
-    if (half == 1) r_s[row] = rsum;
-    __syncthreads();
-    if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
-    __syncthreads();
+    if (prod) {
+      if (half == 1) r_s[row] = rsum;
+      prod_sync();
+      if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
+      prod_sync();
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -565,10 +620,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_point_bwd_kernel(TcPointArgs a
 // dx = (W Z~ - r x~) / ell + g_mu w  and the per-dimension reductions q, wbar + scalar sums
 // =================================================================================================
 template <int DPT>   // DPT = MMA N = padded input dim (32, 64 or 128)
-__global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[4];
+  __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8][32][33];
   __shared__ float part_q[8][32], part_t[8][32], part_sc[8][4];
@@ -590,14 +645,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
 
   constexpr uint32_t TMEM_COLS = DPT;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], 1);
-    tc::mbar_init(&bars[3], 1);
-    tc::fence_barrier_init();
-  }
-  for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
+  if (tid == 0) Pipe<1>::init_barriers(bars);
+  if (tid < kThreads)
+    for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
   if (tid < 4) sc_s[tid] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
@@ -605,6 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
   const uint32_t tmem_d = tmem_slot;
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
+  const bool prod = !pipe.issuer;
 
   // epilogue mapping: the 8 warps cover 4 lane quadrants x 2 column halves of the [128, DPT] tile; with DPT = 32
   // only the first 4 warps have columns.
@@ -625,19 +676,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
       });
     };
     OpRegs<TNP> ra;
-    load_w(ra, 0);
+    if (prod) load_w(ra, 0);
     for (int s = 0; s < MP / KT; ++s) {
       float *a_hi, *a_lo, *b_hi, *b_lo;
       pipe.acquire(a_hi, a_lo, b_hi, b_lo);
       pipe.bulk_b(ZtTU + tc_slab_ztt(DPT, s), DPT);
-      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      if (s + 1 < MP / KT) load_w(ra, s + 1);
+      if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+      if (prod && s + 1 < MP / KT) load_w(ra, s + 1);
       const bool last = s + 1 == MP / KT;
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
       const float* nxt = last ? (more_tiles ? ZtTU : nullptr) : ZtTU + tc_slab_ztt(DPT, s + 1);
       pipe.commit(tmem_d, DPT, s == 0, DPT, nxt, DPT);
     }
     pipe.drain();
+    if (!prod) continue;                            // the issuer warp only runs the slab schedule
 
     const long long gn = n0 + row;
     const bool live = gn < N;
@@ -723,8 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
       const float sv = warp_sum(live && half == 0 ? gv : 0.f);
       if (lane == 0) { part_sc[warp][VS_GMU] = sg; part_sc[warp][VS_RSUM] = sr; part_sc[warp][VS_GVAR] = sv; }
     }
-    tc::tc_fence_before();
-    __syncthreads();
+    prod_sync();
     // combine the 4 lane quadrants in fixed order: dimension d = half * (DPT / 2) + ch * 32 + lane
     if (tid < DPT) {
       const int d = tid;
@@ -745,17 +796,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dx_kernel(TcPointArgs a) {
       for (int w = 0; w < 4; ++w) s += part_sc[w][tid];
       sc_s[tid] += s;
     }
-    __syncthreads();
-    tc::tc_fence_after();
+    prod_sync();
   }
   __syncthreads();
   float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
-  for (int i = tid; i < MP; i += kThreads) vp[i] = 0.f;          // column sums come from the W^T X kernel
-  for (int d = tid; d < DP; d += kThreads) {
-    vp[MP + d] = d < DPT ? q_s[d] : 0.f;
-    vp[MP + DP + d] = (d < D && d < DPT) ? ellv[d] * t1_s[d] + center[d] * sc_s[VS_GMU] : 0.f;
+  if (tid < kThreads) {
+    for (int i = tid; i < MP; i += kThreads) vp[i] = 0.f;        // column sums come from the W^T X kernel
+    for (int d = tid; d < DP; d += kThreads) {
+      vp[MP + d] = d < DPT ? q_s[d] : 0.f;
+      vp[MP + DP + d] = (d < D && d < DPT) ? ellv[d] * t1_s[d] + center[d] * sc_s[VS_GMU] : 0.f;
+    }
+    if (tid < VS_COUNT) vp[MP + 2 * DP + tid] = tid < 3 ? sc_s[tid] : 0.f;
   }
-  if (tid < VS_COUNT) vp[MP + 2 * DP + tid] = tid < 3 ? sc_s[tid] : 0.f;
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
@@ -790,16 +842,17 @@ int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* 
   a.L = L; a.ws = ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
   a.seed = seed; a.offset = offset; a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
+  a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
   const int grid = tc_grid(L);
   ProfScope ps(ST_POINT_FWD, st);
   if (L.MP == 128) {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_point_fwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-    tc_point_fwd_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+    tc_point_fwd_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
   } else {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_point_fwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-    tc_point_fwd_kernel<256><<<grid, kThreads, tc_smem_bytes<256>(), st>>>(a);
+    tc_point_fwd_kernel<256><<<grid, kBlockThreads, tc_smem_bytes<256>(), st>>>(a);
   }
   note_launch();
   return check_launch("tc_point_fwd");
@@ -818,11 +871,11 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
     if (L.MP == 128) {
       static bool cfg = false;
       if (!cfg) { set_smem(tc_point_bwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-      tc_point_bwd_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+      tc_point_bwd_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
     } else {
       static bool cfg = false;
       if (!cfg) { set_smem(tc_point_bwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-      tc_point_bwd_kernel<256><<<grid, kThreads, tc_smem_bytes<256>(), st>>>(a);
+      tc_point_bwd_kernel<256><<<grid, kBlockThreads, tc_smem_bytes<256>(), st>>>(a);
     }
     note_launch();
     int rc = check_launch("tc_point_bwd");
@@ -832,15 +885,15 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
   if (L.DP <= 32) {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_dx_kernel<32>, tc_smem_bytes<32>()); cfg = true; }
-    tc_dx_kernel<32><<<grid, kThreads, tc_smem_bytes<32>(), st>>>(a);
+    tc_dx_kernel<32><<<grid, kBlockThreads, tc_smem_bytes<32>(), st>>>(a);
   } else if (L.DP == 64) {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_dx_kernel<64>, tc_smem_bytes<64>()); cfg = true; }
-    tc_dx_kernel<64><<<grid, kThreads, tc_smem_bytes<64>(), st>>>(a);
+    tc_dx_kernel<64><<<grid, kBlockThreads, tc_smem_bytes<64>(), st>>>(a);
   } else {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_dx_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-    tc_dx_kernel<128><<<grid, kThreads, tc_smem_bytes<128>(), st>>>(a);
+    tc_dx_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
   }
   note_launch();
   return check_launch("tc_dx");
