@@ -81,12 +81,14 @@ __device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int la
     if (!(d > 0.0) && bad == 0) bad = c + 1;
     const double rs = rsqrt(d);
     const double l = a[c] * rs;
-    if (lane == c) rinv = rs;
+    rinv = (lane == c) ? rs : rinv;
     a[c] = (lane >= c) ? l : 0.0;
+    // branch-free trailing update: lanes above the diagonal (lane < c2) update entries that are never read
+    // (they are overwritten with 0 when their column is processed), so no predicate is needed
 #pragma unroll
     for (int c2 = c + 1; c2 < TB; ++c2) {
       const double lc2 = __shfl_sync(0xffffffffu, l, c2);
-      if (lane >= c2) a[c2] = fma(-l, lc2, a[c2]);
+      a[c2] = fma(-l, lc2, a[c2]);
     }
   }
   return bad;
@@ -287,19 +289,23 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     const bool has_rows = (int)blockIdx.x < nrb;
     if (has_rows || blockIdx.x == 0) {
       __syncthreads();
+      if (kb == 0 && blockIdx.x == 0 && tid == 0) stamps[9] = global_ns();
       if (warp == 0) {
         double arow[TB];
         const double* src = L64 + (size_t)(kb * TB + lane) * MP + kb * TB;
 #pragma unroll
         for (int c = 0; c < TB; ++c) arow[c] = src[c];
+        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[10] = global_ns() + (unsigned long long)(arow[0] == 12345.678);
         double rinv = 0.0;
         const int bad = chol32_warp(arow, rinv, lane);
         if (bad && blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + bad);
+        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(rinv == 12345.678);
 #pragma unroll
         for (int c = 0; c < TB; ++c) Dg[lane][c] = arow[c];
         rdiag[lane] = rinv;
         __syncwarp();
         trinv32_warp(Dg, rdiag, Di, lane);
+        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(Di[31][0] == 12345.678);
       }
       __syncthreads();
       // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
@@ -483,13 +489,31 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   }
   GPBLUR_STAMP();
   float* zn = ws_ptr<float>(a.ws, L.zn);
-  for (int j = gtid; j < MP; j += gsize) {
-    double s = 0.0;
-    for (int i = j; i < M; ++i) s = fma(Li64[(size_t)i * MP + j], (double)mvec[i], s);
-    beta[j] = (float)s;
+  // beta = Linv^T m : one CTA per 32-column chunk, lanes = columns (coalesced rows), the 8 warps split the rows
+  {
+    __shared__ double bred[8][32];
+    for (int cj = blockIdx.x; cj < MP / 32; cj += G) {
+      const int j = cj * 32 + lane;
+      double sacc = 0.0;
+      for (int i = cj * 32 + warp; i < M; i += 8)
+        if (i >= j) sacc = fma(Li64[(size_t)i * MP + j], (double)mvec[i], sacc);
+      __syncthreads();
+      bred[warp][lane] = sacc;
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += bred[w][lane];
+        beta[j] = (float)t;
+      }
+    }
+  }
+  // |z~_j|^2 : one warp per inducing point
+  for (int j = blockIdx.x * 8 + warp; j < MP; j += G * 8) {
     float z2 = 0.f;
-    for (int d = 0; d < DP; ++d) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
-    zn[j] = z2;
+    for (int d = lane; d < DP; d += 32) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
+    z2 = warp_sum(z2);
+    if (lane == 0) zn[j] = z2;
   }
   GPBLUR_STAMP();
 #undef GPBLUR_STAMP
