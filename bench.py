@@ -401,7 +401,18 @@ def run_ours(args, wl, name):
                                      "ALGORITHMIC flops (a 3xTF32 kernel issues 3 MMAs per product; M <= 64 and "
                                      "M > 256 still run FP32 FFMA, peak ~74 TFLOP/s)"}
             roof["frac"] = roof["achieved"] / roof["peak"]
+            # measured DRAM traffic of that kernel (ncu --set full capture of this same command, per launch)
             roof["traffic"] = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                ent = tj.get(name, {}).get(dom)
+                if ent:
+                    roof["traffic"] = ent["bytes_per_launch"]
+                    roof["traffic_source"] = "profiles/ncu_traffic.json (dram__bytes_read+write per launch, ncu --set full)"
+            except Exception:
+                pass
+            roof["algorithmic_bytes_per_launch"] = by
+            roof["algorithmic_flops_per_launch"] = fl
             roof["kernel"] = dom
             roof["kernel_ms_per_launch"] = per_launch_s * 1e3
             roof["peak_source"] = peaks["source"]

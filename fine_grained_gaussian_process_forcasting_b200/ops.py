@@ -48,19 +48,33 @@ def grad_bucket_floats(D: int, M: int) -> int:
     return M * D + 2 * M + 2 * D + 2
 
 
+_WS_BYTES_CACHE = {}
+
+
 def workspace_bytes(N: int, D: int, M: int, training: bool) -> int:
-    n = int(_cabi.lib().gpblur_svgp_workspace_bytes(N, D, M, int(training)))
-    if n == 0:
-        raise RuntimeError(f"unsupported SVGP shape N={N} D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, "
-                           f"M <= {_cabi.GPBLUR_MAX_M})")
+    key = (N, D, M, bool(training))
+    n = _WS_BYTES_CACHE.get(key)
+    if n is None:
+        n = int(_cabi.lib().gpblur_svgp_workspace_bytes(N, D, M, int(training)))
+        if n == 0:
+            raise RuntimeError(f"unsupported SVGP shape N={N} D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, "
+                               f"M <= {_cabi.GPBLUR_MAX_M})")
+        if len(_WS_BYTES_CACHE) < 4096:
+            _WS_BYTES_CACHE[key] = n
     return n
 
 
 # ------------------------------------------------------------------------------------------------
 # raw calls
 # ------------------------------------------------------------------------------------------------
+_STAGE_BYTES_CACHE = {}
+
+
 def param_stage_bytes(D: int, M: int) -> int:
-    return int(_cabi.lib().gpblur_svgp_param_stage_bytes(D, M))
+    n = _STAGE_BYTES_CACHE.get((D, M))
+    if n is None:
+        n = _STAGE_BYTES_CACHE[(D, M)] = int(_cabi.lib().gpblur_svgp_param_stage_bytes(D, M))
+    return n
 
 
 def svgp_forward_raw(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: Tensor, s: Tensor,
@@ -73,10 +87,10 @@ def svgp_forward_raw(x: Tensor, Z: Tensor, raw_ell: Tensor, raw_os: Tensor, m: T
     N, D = x.shape
     M = Z.shape[0]
     dev = x.device
-    mean = torch.empty(N, device=dev, dtype=torch.float32)
-    var = torch.empty(N, device=dev, dtype=torch.float32)
-    sample = torch.empty(N, device=dev, dtype=torch.float32) if want_sample else None
-    kl = torch.empty(1, device=dev, dtype=torch.float32)
+    out = torch.empty((3 if want_sample else 2) * N + 1, device=dev, dtype=torch.float32)   # one allocation
+    mean, var = out[:N], out[N:2 * N]
+    sample = out[2 * N:3 * N] if want_sample else None
+    kl = out[-1:]
     info = torch.empty(1, device=dev, dtype=torch.int32)
     ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
@@ -226,8 +240,10 @@ class _SvgpFunction(torch.autograd.Function):
         mean, var, sample, kl, info, ws = svgp_forward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, seed, offset,
                                                            stream_id, want_sample, training, stage)
         if stage_cache is not None and stage is None:
+            # keep a reference to this workspace: its leading param_stage_bytes() are immutable after the forward
+            # (the backward only touches scratch regions), so later calls can copy the stage straight from it
             stage_cache["key"] = key
-            stage_cache["stage"] = ws[:param_stage_bytes(D, Zc.shape[0])].clone()
+            stage_cache["stage"] = ws
         if training:
             ctx.save_for_backward(x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws)
         ctx.rng = (seed, offset, stream_id)
