@@ -14,6 +14,7 @@ Workloads (BASELINE.json `configs`; per-GPU batch is fixed => weak scaling):
           (the forecaster / denoiser around them are outside the hot path)
   c1      configs[0]: B=256, L=24, D=64, M=32
   c3      configs[2]: B=1024, L=24, D=64, M=128
+  c4      configs[3]: two-layer DeepGP, B=2048, L=24, D=64, M=256, hidden width H=10
   c5_mM   configs[4]: B=8192, L=24, D=64, M in {64,128,256,512,1024}
 
 The JSON line carries `value` (inputs resident in HBM), `e2e` (host buffers, H2D/D2H inside the timed
@@ -47,6 +48,9 @@ WORKLOADS = {
 for _m in (64, 128, 256, 512, 1024):
     WORKLOADS[f"c5_m{_m}"] = dict(B=8192, calls=[24], D=64, M=_m,
                                   desc=f"configs[4]: inducing sweep point B=8192 L=24 D=64 M={_m}")
+WORKLOADS["c4"] = dict(B=2048, calls=[24], D=64, M=256, H=10,
+                       desc="configs[3]: two-layer DeepGP blur B=2048 L=24 D=64 M=256, hidden width H=10 "
+                            "(H independent GPs D->H, reparameterised sample, one GP H->1)")
 DEFAULT_WORKLOAD = "c2"
 METRIC = "gp_blur_fwd_bwd_windows_per_sec"
 UNIT = "windows/s"
@@ -152,6 +156,8 @@ class ClockSampler:
 def cpu_reference_step_fn(wl, B_cpu, seed=1234):
     from oracle import gp_oracle as O
     D, M = wl["D"], wl["M"]
+    if "H" in wl:
+        return cpu_reference_step_fn_two_layer(wl, B_cpu, seed)
     p = O.clone_params(O.init_params_exercise(D, M, seed), requires_grad=True)
     calls = []
     for i, L in enumerate(wl["calls"]):
@@ -174,6 +180,28 @@ def cpu_reference_step_fn(wl, B_cpu, seed=1234):
     return step
 
 
+def cpu_reference_step_fn_two_layer(wl, B_cpu, seed=1234):
+    from oracle import gp_oracle as O
+    D, M, H, L = wl["D"], wl["M"], wl["H"], wl["calls"][0]
+    p1 = O.clone_params(O.init_params_hidden_layer(D, H, M, seed), requires_grad=True)
+    p2 = O.clone_params(O.init_params_exercise(H, M, seed + 1), requires_grad=True)
+    x, y, gm, gv = O.make_inputs(B_cpu, L, D, seed + 2)
+    x.requires_grad_(True)
+    eps = torch.randn(B_cpu, L, H, generator=torch.Generator().manual_seed(seed + 3))
+
+    def step():
+        for q in list(p1.values()) + list(p2.values()):
+            q.grad = None
+        x.grad = None
+        mean, var, _ = O.deepgp2_predict(p1, p2, x, eps, closed_form=False)
+        kl = O.kl_hidden_layer(p1) + O.kl_meanfield(p2)
+        e = O.elbo_per_window(mean, var, y, O.noise_variance(p2), kl, float(D))
+        loss = (gm * mean).sum() - e.mean()
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
 def time_cpu_reference(wl, steps, warmup, budget_s=25.0):
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
@@ -181,6 +209,7 @@ def time_cpu_reference(wl, steps, warmup, budget_s=25.0):
     N_per_window = sum(wl["calls"])
     M = wl["M"]
     cost = N_per_window * (M + max(wl["calls"])) ** 2 / 1e9 + M ** 3 / 1e9 * 4   # rough Gflop-ish per window
+    cost *= wl.get("H", 0) + 1
     B_cpu = int(max(2, min(wl["B"], 6.0 / max(cost, 1e-3))))
     B_cpu = int(os.environ.get("GPBLUR_CPU_SAMPLE_B", B_cpu))
     step = cpu_reference_step_fn(wl, B_cpu)
@@ -221,32 +250,39 @@ def run_reference(args, wl, name):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def make_model(wl, device, seed=1234):
+def exercise_init(layer, seed):
+    """"R-exercise" parameter regime of SURVEY 8(d) for one (possibly multi-output) whitened SVGP layer:
+    lengthscales ~ sqrt(D) so that K(x, Z) is O(0.1..1) instead of underflowing, non-trivial q(u)."""
     import math
-    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    vs = layer.variational_strategy
+    vd = vs._variational_distribution
+    Z = vs.inducing_points
+    Dd = Z.shape[-1]
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        Z.copy_(torch.randn(Z.shape, generator=g))
+        rl = layer.covar_module.base_kernel.raw_lengthscale
+        ell = math.sqrt(Dd) * (0.75 + 0.5 * torch.rand(rl.shape, generator=g))
+        rl.copy_(torch.log(torch.expm1(ell)))
+        vd.variational_mean.copy_(0.5 * torch.randn(vd.variational_mean.shape, generator=g))
+        vd._variational_stddev.copy_(0.5 + torch.rand(vd._variational_stddev.shape, generator=g))
+        layer.mean_module.weights.copy_(torch.randn(layer.mean_module.weights.shape, generator=g) / math.sqrt(Dd))
+        layer.mean_module.bias.copy_(torch.randn(layer.mean_module.bias.shape, generator=g))
+        vs.variational_params_initialized.fill_(1)
+
+
+def make_model(wl, device, seed=1234):
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp, DeepGP2
     from fine_grained_gaussian_process_forcasting_b200 import gpcompat
     gpcompat.num_likelihood_samples._set_value(1)       # train.py:20
-    model = DeepGPp(wl["D"], seed, num_inducing=wl["M"]).to(device)
-    # "R-exercise" parameter regime of SURVEY 8(d): lengthscales ~ sqrt(D) so K(x, Z) is O(0.1..1)
-    Dd, Mm = wl["D"], wl["M"]
-    g = torch.Generator().manual_seed(seed)
-    ell = math.sqrt(Dd) * (0.75 + 0.5 * torch.rand(1, Dd, generator=g))
-    p = {"inducing_points": torch.randn(Mm, Dd, generator=g),
-         "raw_lengthscale": torch.log(torch.expm1(ell)),
-         "variational_mean": 0.5 * torch.randn(Mm, generator=g),
-         "variational_stddev": 0.5 + torch.rand(Mm, generator=g),
-         "weights": torch.randn(Dd, 1, generator=g) / math.sqrt(Dd),
-         "bias": torch.randn(1, generator=g)}
-    hl = model.hidden_layer
-    with torch.no_grad():
-        hl.variational_strategy.inducing_points.copy_(p["inducing_points"])
-        hl.covar_module.base_kernel.raw_lengthscale.copy_(p["raw_lengthscale"])
-        hl.variational_strategy._variational_distribution.variational_mean.copy_(p["variational_mean"])
-        hl.variational_strategy._variational_distribution._variational_stddev.copy_(p["variational_stddev"])
-        hl.mean_module.weights.copy_(p["weights"])
-        hl.mean_module.bias.copy_(p["bias"])
-        hl.variational_strategy.variational_params_initialized.fill_(1)
-    return model
+    if "H" in wl:
+        model = DeepGP2(wl["D"], seed, hidden_dims=wl["H"], num_inducing=wl["M"])
+        exercise_init(model.hidden_layer, seed)
+        exercise_init(model.last_layer, seed + 1)
+    else:
+        model = DeepGPp(wl["D"], seed, num_inducing=wl["M"])
+        exercise_init(model.hidden_layer, seed)
+    return model.to(device)
 
 
 def run_ours(args, wl, name):
@@ -282,16 +318,19 @@ def run_ours(args, wl, name):
     yh = ys[0].cpu().pin_memory()
     elbo_h = torch.empty(1, B).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES // 4, device=device)
-    hl = model.hidden_layer
+    from fine_grained_gaussian_process_forcasting_b200.gpcompat import DeepGPLayer
+    layers = [m for m in model.modules() if isinstance(m, DeepGPLayer)]
 
     def step(i, xin, yin):
         bucket.zero()
-        hl.invalidate_param_stage()     # a real training step changes the parameters: recompute Kzz / Cholesky once
+        for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
+            ly.invalidate_param_stage()
         outs, grads = [], []
         elbo = None
         for c, L in enumerate(calls):
             x = xin[c].detach().requires_grad_(True)      # fresh leaf: dX flows back to the forecaster
-            hl._rng_offset = (i * world + rank) * B * L       # global window index -> Philox counter
+            for ly in layers:                                 # global window index -> Philox counter
+                ly._rng_offset = (i * world + rank) * B * L * max(1, ly.output_dims or 1)
             last = c == len(calls) - 1
             out = model.blur(x, yin if last else None, num_data=D)
             outs += [out.mean, out.sample]
@@ -390,6 +429,8 @@ def run_ours(args, wl, name):
             ms_dom, launches_dom = stage_ms[dom]
             per_launch_s = ms_dom * 1e-3 / max(launches_dom, 1)
             n_per_launch = N_total / max(launches_dom, 1)
+            if "H" in wl:                       # two-layer stack: H + 1 launches per stage, each over all N points
+                n_per_launch = N_total          # (work model uses the layer-1 dims D, M: H of the H + 1 launches)
             by, fl = stage_work(dom, int(n_per_launch), D, M)
             tf32_peak = peaks["bf16_tflops"] / 2.0
             intensity = fl / max(by, 1)

@@ -88,14 +88,21 @@ class DeepGPp(gp.DeepGP):
         """One call for the whole hot path: predictive mean / variance, fused reparameterised sample and,
         when targets ``y [B, L]`` (or ``[1, B, L]``) are given, the per-window ELBO with
         ``num_data`` defaulting to the input width (forecast_denoising.py:88 passes d_model)."""
-        dist = self(x)
-        elbo = None
-        if y is not None:
-            nd = float(num_data if num_data is not None else x.shape[-1])
-            tgt = y if y.dim() == dist.mean.dim() else y.unsqueeze(0)
-            elbo = ops.variational_elbo(dist.mean, dist.variance, tgt.expand(dist.mean.shape),
-                                        self.likelihood.raw_noise, dist.kl, nd)
-        return BlurOutput(dist.mean, dist.variance, dist.sample_value, elbo, dist.kl, dist)
+        return _blur(self, x, y, num_data)
+
+
+def _blur(model, x, y=None, num_data=None) -> BlurOutput:
+    dist = model(x)
+    elbo = None
+    if y is not None:
+        nd = float(num_data if num_data is not None else x.shape[-1])
+        tgt = y if y.dim() == dist.mean.dim() else y.unsqueeze(0)
+        kl = model.variational_strategy.kl_divergence()      # summed over every GP of the stack
+        elbo = ops.variational_elbo(dist.mean, dist.variance, tgt.expand(dist.mean.shape),
+                                    model.likelihood.raw_noise, kl, nd)
+    else:
+        kl = dist.kl
+    return BlurOutput(dist.mean, dist.variance, dist.sample_value, elbo, kl, dist)
 
 
 class DeepGP2(gp.DeepGP):
@@ -128,3 +135,7 @@ class DeepGP2(gp.DeepGP):
         dist = self(x)
         preds = self.likelihood(dist)
         return preds.mean, dist
+
+    def blur(self, x, y=None, num_data=None) -> BlurOutput:
+        """Same contract as ``DeepGPp.blur``; ``kl`` is the sum over both layers (all H + 1 GPs)."""
+        return _blur(self, x, y, num_data)

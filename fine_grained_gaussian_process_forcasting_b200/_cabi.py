@@ -54,6 +54,18 @@ SIGNATURES = {
         C.POINTER(SvgpParams), C.c_void_p, C.c_longlong, C.c_int, C.c_int,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gpblur_svgp_stage_grad_doubles": (C.c_size_t, [C.c_int, C.c_int]),
+    "gpblur_svgp_param_stage": (C.c_int, [
+        C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gpblur_svgp_point_forward": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gpblur_svgp_point_backward": (C.c_int, [
+        C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gpblur_svgp_param_stage_backward": (C.c_int, [
+        C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+        C.c_void_p]),
     "gpblur_elbo_forward": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
         C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
@@ -116,7 +128,7 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(f"{what} failed with {ERRORS.get(rc, rc)}{detail}")
 
 
-STAGES = ("mm_fwd", "point_fwd", "point_bwd", "gram", "wx", "mm_bwd", "elbo_fwd", "elbo_bwd", "dx")
+STAGES = ("mm_fwd", "point_fwd", "point_bwd", "gram", "wx", "mm_bwd", "elbo_fwd", "elbo_bwd", "dx", "sg_reduce")
 
 
 def profile_enable(on: bool) -> None:

@@ -64,8 +64,8 @@ int tile_override(const char* env) {
 }
 
 int bwd_vector_partials(const WsLayout& L);
-int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                     float* grad_bucket, int nvec_used, int ncpart, cudaStream_t st);
+int stage_grad_reduce_impl(const WsLayout& L, const void* ws, double* sgrad, int nvec_used, int ncpart,
+                           cudaStream_t st);
 
 namespace {
 
@@ -217,10 +217,9 @@ inline int ew_grid(long long n, int block) { return (int)((n + block - 1) / bloc
 
 }  // namespace
 
-int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                       float* grad_bucket, cudaStream_t st) {
-  if (tc_point_supported(L)) return mm_backward_impl(p, L, ws, g_kl, grad_bucket, tc_vector_partials(L), L.splitsZ, st);
-  return mm_backward_impl(p, L, ws, g_kl, grad_bucket, bwd_vector_partials(L), 0, st);
+int launch_stage_grad_reduce(const WsLayout& L, const void* ws, double* sgrad, cudaStream_t st) {
+  if (tc_point_supported(L)) return stage_grad_reduce_impl(L, ws, sgrad, tc_vector_partials(L), L.splitsZ, st);
+  return stage_grad_reduce_impl(L, ws, sgrad, bwd_vector_partials(L), 0, st);
 }
 
 }  // namespace gpblur
@@ -257,6 +256,7 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_mm_forward(*p, L, ws, kl, info, st);
   if (rc) return rc;
+  if (N == 0) return GPBLUR_OK;
   if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
   return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
@@ -264,6 +264,39 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
 size_t gpblur_svgp_param_stage_bytes(int D, int M) {
   if (D < 1 || M < 1 || D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return 0;
   return make_layout(0, D, M, 0).total;   // the inference layout is exactly the parameter stage
+}
+
+size_t gpblur_svgp_stage_grad_doubles(int D, int M) {
+  if (D < 1 || M < 1 || D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return 0;
+  return stage_grad_doubles(padded_m(M), padded_d(D));
+}
+
+int gpblur_svgp_param_stage(const gpblur_svgp_params* p, int D, int M, float* kl, int* info, void* stage,
+                            size_t stage_bytes, void* stream) {
+  int rc = validate(p, 0, D, M);
+  if (rc) return rc;
+  if (!stage || (reinterpret_cast<uintptr_t>(stage) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(0, D, M, 0);
+  if (stage_bytes < L.total) return GPBLUR_EWORKSPACE;
+  return launch_mm_forward(*p, L, stage, kl, info, (cudaStream_t)stream);
+}
+
+int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long N, int D, int M, float* mean,
+                              float* var, float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                              int training, void* ws, size_t ws_bytes, void* stream) {
+  if (!param_stage || N < 0 || D < 1 || M < 1) return GPBLUR_EINVAL;
+  if (D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return GPBLUR_EUNSUPPORTED;
+  if (N > 0 && (!x || !mean || !var)) return GPBLUR_EINVAL;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(N, D, M, training ? 1 : 0);
+  if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pbytes = make_layout(0, D, M, 0).total;
+  if (param_stage != ws) cudaMemcpyAsync(ws, param_stage, pbytes, cudaMemcpyDeviceToDevice, st);
+  int rc = check_launch("param_stage_copy");
+  if (rc || N == 0) return rc;
+  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
 int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long long N, int D, int M, float* mean,
@@ -275,19 +308,47 @@ int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long
                                ws_bytes, stream);
   int rc = validate(p, N, D, M);
   if (rc) return rc;
-  if (N > 0 && (!x || !mean || !var)) return GPBLUR_EINVAL;
-  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
-  const WsLayout L = make_layout(N, D, M, training ? 1 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout L0 = make_layout(0, D, M, 0);
+  if (kl) cudaMemcpyAsync(kl, ws_cptr<float>(param_stage, L0.hyp) + H_KL, sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+  return gpblur_svgp_point_forward(param_stage, x, N, D, M, mean, var, sample, seed, offset, stream_id, training, ws,
+                                   ws_bytes, stream);
+}
+
+int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const float* g_mean, const float* g_var,
+                               const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
+                               uint32_t stream_id, float* dx, double* stage_grad, void* ws, size_t ws_bytes,
+                               void* stream) {
+  if (N < 0 || D < 1 || M < 1) return GPBLUR_EINVAL;
+  if (D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return GPBLUR_EUNSUPPORTED;
+  if (!stage_grad || !ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
+  if (N > 0 && (!x || !var)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(N, D, M, 1);
   if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t pbytes = make_layout(0, D, M, 0).total;
-  cudaMemcpyAsync(ws, param_stage, pbytes, cudaMemcpyDeviceToDevice, st);
-  if (kl) cudaMemcpyAsync(kl, ws_cptr<float>(param_stage, L.hyp) + H_KL, sizeof(float), cudaMemcpyDeviceToDevice, st);
-  if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
-  rc = check_launch("param_stage_copy");
+  int rc = GPBLUR_OK;
+  if (N > 0) {
+    if (tc_point_supported(L))
+      rc = launch_tc_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
+    else
+      rc = launch_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
+    if (rc) return rc;
+    rc = launch_reductions(L, ws, x, st);
+    if (rc) return rc;
+  }
+  return launch_stage_grad_reduce(L, ws, stage_grad, st);
+}
+
+int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,
+                                     const float* g_kl, float* grad_bucket, void* stage, size_t stage_bytes,
+                                     void* stream) {
+  int rc = validate(p, 0, D, M);
   if (rc) return rc;
-  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
-  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  if (!stage_grad || !grad_bucket || !stage || (reinterpret_cast<uintptr_t>(stage) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(0, D, M, 0);
+  if (stage_bytes < L.total) return GPBLUR_EWORKSPACE;
+  return launch_mm_backward(*p, L, stage, stage_grad, g_kl, grad_bucket, (cudaStream_t)stream);
 }
 
 int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
@@ -297,22 +358,13 @@ int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long 
   int rc = validate(p, N, D, M);
   if (rc) return rc;
   if (!grad_bucket || !ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
-  if (N > 0 && (!x || !var)) return GPBLUR_EINVAL;
   const WsLayout L = make_layout(N, D, M, 1);
   if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (N == 0) {
-    cudaMemsetAsync(ws_ptr<char>(ws, L.Spart), 0, L.total - L.Spart, st);
-  } else {
-    if (tc_point_supported(L))
-      rc = launch_tc_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
-    else
-      rc = launch_point_backward(L, ws, x, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, st);
-    if (rc) return rc;
-    rc = launch_reductions(L, ws, x, st);
-    if (rc) return rc;
-  }
-  return launch_mm_backward(*p, L, ws, g_kl, grad_bucket, st);
+  double* sgrad = ws_ptr<double>(ws, L.sgrad);
+  rc = gpblur_svgp_point_backward(x, N, D, M, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, sgrad, ws,
+                                  ws_bytes, stream);
+  if (rc) return rc;
+  return launch_mm_backward(*p, L, ws, sgrad, g_kl, grad_bucket, (cudaStream_t)stream);
 }
 
 int gpblur_elbo_forward(const float* mean, const float* var, const float* y, const float* raw_noise,

@@ -52,7 +52,8 @@ struct WsLayout {
   size_t hyp, hyp64, stamps, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
   size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
-  size_t A, W, Spart, upart, WXpart, vecpart, gsc, v64, t64, rrow, cpart;
+  size_t v64, t64;                 // fp64 scratch of the M x M backward (part of the parameter stage)
+  size_t A, W, Spart, upart, WXpart, vecpart, gsc, rrow, cpart, sgrad;
   size_t total;
 };
 
@@ -166,6 +167,8 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   }
   w.nvec = kMaxPersist;
   w.vec_len = w.MP + 2 * w.DP + VS_COUNT;
+  w.v64 = take((size_t)(3 * MP + w.vec_len) * 8);
+  w.t64 = take((size_t)MP * DP * 8);
   if (training) {
     w.A = take((size_t)N * MP * 4);
     w.W = take((size_t)N * MP * 4);
@@ -174,15 +177,22 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     w.WXpart = take((size_t)w.splitsZ * MP * DP * 4);
     w.vecpart = take((size_t)w.nvec * w.vec_len * 4);
     w.gsc = take((size_t)2 * (N > 0 ? N : 1) * 4);   // folded upstream grads g_mu, g_var [N] each
-    w.v64 = take((size_t)(3 * MP + w.vec_len) * 8);
-    w.t64 = take((size_t)MP * DP * 8);
     w.rrow = take((size_t)(N > 0 ? N : 1) * 4);           // row sums r[n] of W (tensor-core backward)
     w.cpart = take((size_t)w.splitsZ * MP * 4);           // column sums of W per split (tensor-core W^T X)
+    w.sgrad = take(((size_t)MP + w.vec_len + (size_t)MP * MP + (size_t)MP * DP) * 8);   // see stage_grad_doubles()
   } else {
-    w.A = w.W = w.Spart = w.upart = w.WXpart = w.vecpart = w.gsc = w.v64 = w.t64 = w.rrow = w.cpart = o;
+    w.A = w.W = w.Spart = w.upart = w.WXpart = w.vecpart = w.gsc = w.rrow = w.cpart = w.sgrad = o;
   }
   w.total = o;
   return w;
+}
+
+// "Stage gradient": everything the per-point backward of ONE call contributes to the parameter gradients, reduced
+// over that call's points (fp64, fixed summation order).  It is linear in the upstream gradients, so the stage
+// gradients of several calls that share one parameter stage are simply added before the M x M backward runs once.
+//   [ u MP | vec vec_len (colsum MP, q DP, wbar DP, scalars) | S MP x MP (full, symmetric) | W^T X  MP x DP ]
+__host__ __device__ inline size_t stage_grad_doubles(int MP, int DP) {
+  return (size_t)MP + (size_t)(MP + 2 * DP + VS_COUNT) + (size_t)MP * MP + (size_t)MP * DP;
 }
 
 template <typename T>
@@ -253,7 +263,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // host-side launch bookkeeping (defined in gpblur_api.cu)
 enum Stage { ST_MM_FWD = 0, ST_POINT_FWD, ST_POINT_BWD, ST_GRAM, ST_WX, ST_MM_BWD, ST_ELBO_FWD, ST_ELBO_BWD,
-             ST_OTHER, ST_COUNT };
+             ST_OTHER, ST_SG_REDUCE, ST_COUNT };
 // RAII: when profiling is enabled, brackets the launches issued in its scope with CUDA events on `st`
 struct ProfScope {
   int stage; cudaStream_t st; void* rec;
@@ -268,8 +278,11 @@ int tile_override(const char* env);   // 0 = heuristic, else forced tile height 
 // launchers implemented in the other translation units
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
                       cudaStream_t st);
-int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                       float* grad_bucket, cudaStream_t st);
+// stage: the parameter stage of the forward (its fp64 scratch regions are overwritten); sgrad: summed stage gradient
+int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
+                       const float* g_kl, float* grad_bucket, cudaStream_t st);
+// reduces the split partials left in `ws` by the point backward + N-reduction GEMMs into sgrad (fixed order, fp64)
+int launch_stage_grad_reduce(const WsLayout& L, const void* ws, double* sgrad, cudaStream_t st);
 int launch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var,
                          float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
                          cudaStream_t st);

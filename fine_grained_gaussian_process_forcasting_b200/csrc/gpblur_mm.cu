@@ -523,12 +523,78 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
 struct MmBwdArgs {
   gpblur_svgp_params p;
   WsLayout L;
-  void* ws;
+  void* ws;               // parameter stage (fp64 scratch regions T64 / U64 / v64 / t64 are overwritten)
+  const double* sgrad;    // summed stage gradient [u | vec | S | W^T X], see stage_grad_doubles()
   const float* g_kl;
   float* bucket;
+};
+
+// Per-call reduction of the split partials into the stage gradient (fixed order => bit-deterministic).
+struct SgReduceArgs {
+  WsLayout L;
+  const void* ws;
+  double* sgrad;
   int nvec_used;
   int ncpart;   // > 0: column sums of W come as [ncpart][MP] partials from the tensor-core W^T X kernel
 };
+
+__global__ void __launch_bounds__(kThreads) stage_grad_reduce_kernel(SgReduceArgs a) {
+  const WsLayout& L = a.L;
+  const int MP = L.MP, DP = L.DP;
+  const float* Spart = ws_cptr<float>(a.ws, L.Spart);
+  const float* upart = ws_cptr<float>(a.ws, L.upart);
+  const float* WXpart = ws_cptr<float>(a.ws, L.WXpart);
+  const float* vecpart = ws_cptr<float>(a.ws, L.vecpart);
+  const float* cpart = ws_cptr<float>(a.ws, L.cpart);
+  const int tp = MP < 128 ? MP : 128;   // tile size used by the Gram reduction (lower tile triangle valid)
+  double* g_u = a.sgrad;
+  double* g_vec = g_u + MP;
+  double* g_S = g_vec + L.vec_len;
+  double* g_WX = g_S + (size_t)MP * MP;
+  const size_t n_u = MP, n_vec = L.vec_len, n_S = (size_t)MP * MP, n_WX = (size_t)MP * DP;
+  const size_t total = n_u + n_vec + n_S + n_WX;
+  // A CTA owns 32 consecutive output elements per iteration (lanes, coalesced); warp g sums partials g, g + 8, ...
+  // and the 8 warp sums are folded in fixed order through shared memory (bit-deterministic), which keeps 8x more
+  // loads in flight than one thread per element.
+  __shared__ double red[8][32];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t nchunks = (total + 31) / 32;
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const size_t e = ch * 32 + lane;
+    double s = 0.0;
+    if (e < total && L.N > 0) {
+      if (e < n_u) {
+        for (int sp = g; sp < L.splitsS; sp += 8) s += (double)upart[(size_t)sp * MP + e];
+      } else if (e < n_u + n_vec) {
+        const size_t k = e - n_u;
+        for (int c = g; c < a.nvec_used; c += 8) s += (double)vecpart[(size_t)c * L.vec_len + k];
+        if (a.ncpart > 0 && k < (size_t)MP)
+          for (int c = g; c < a.ncpart; c += 8) s += (double)cpart[(size_t)c * MP + k];
+      } else if (e < n_u + n_vec + n_S) {
+        const size_t idx = e - n_u - n_vec;
+        const int i = (int)(idx / MP), j = (int)(idx - (size_t)i * MP);
+        // the FFMA Gram holds only the lower tile triangle (tile size tp): mirror the rest; the tensor-core Gram
+        // (ncpart > 0) writes every tile
+        const bool lower = a.ncpart > 0 || (i / tp >= j / tp);
+        const int si = lower ? i : j, sj = lower ? j : i;
+        for (int sp = g; sp < L.splitsS; sp += 8) s += (double)Spart[((size_t)sp * MP + si) * MP + sj];
+      } else {
+        const size_t idx = e - n_u - n_vec - n_S;
+        for (int sp = g; sp < L.splitsZ; sp += 8) s += (double)WXpart[(size_t)sp * MP * DP + idx];
+      }
+    }
+    __syncthreads();
+    red[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && e < total) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][lane];
+      a.sgrad[e] = t;
+    }
+  }
+  (void)g_u; (void)g_vec; (void)g_S; (void)g_WX;
+}
 
 __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -558,46 +624,28 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   const double* Li64 = ws_cptr<double>(a.ws, L.Linv64);
   double* T64 = ws_ptr<double>(a.ws, L.T64);
   double* U64 = ws_ptr<double>(a.ws, L.U64);
-  const float* Spart = ws_cptr<float>(a.ws, L.Spart);
-  const float* upart = ws_cptr<float>(a.ws, L.upart);
-  const float* WXpart = ws_cptr<float>(a.ws, L.WXpart);
-  const float* vecpart = ws_cptr<float>(a.ws, L.vecpart);
-  // fp64 vector scratch: [u MP | vec vec_len | diag(S) MP | rz MP]
+  // stage gradient (read-only): [u MP | vec vec_len | S MP x MP | W^T X MP x DP]
+  const double* u64 = a.sgrad;
+  const double* vec64 = a.sgrad + MP;
+  const double* S64 = vec64 + L.vec_len;
+  const double* WX64 = S64 + (size_t)MP * MP;
+  // fp64 vector scratch: [unused MP | unused vec_len | diag(S) MP | rz MP]
   double* v64 = ws_ptr<double>(a.ws, L.v64);
-  double* u64 = v64;
-  double* vec64 = v64 + MP;
-  double* sdiag = vec64 + L.vec_len;
+  double* sdiag = v64 + MP + L.vec_len;
   double* rz64 = sdiag + MP;
   double* t64 = ws_ptr<double>(a.ws, L.t64);   // [MP, DP] per-(i, d) terms of d lengthscale
 
-  const int tp = MP < 128 ? MP : 128;   // tile size used by the Gram reduction (lower tile triangle valid)
   unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps) + 16;
   int stamp_i = 0;
 #define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
   GPBLUR_STAMP();
 
-  // ---------------- phase 0: reduce split partials ----------------
-  for (int m = gtid; m < MP; m += gsize) {
-    double s = 0.0;
-    for (int sp = 0; sp < L.splitsS; ++sp) s += (double)upart[(size_t)sp * MP + m];
-    u64[m] = s;
-  }
-  const float* cpart = ws_cptr<float>(a.ws, L.cpart);
-  for (int e = gtid; e < L.vec_len; e += gsize) {
-    double s = 0.0;
-    for (int c = 0; c < a.nvec_used; ++c) s += (double)vecpart[(size_t)c * L.vec_len + e];
-    if (a.ncpart > 0 && e < MP)
-      for (int c = 0; c < a.ncpart; ++c) s += (double)cpart[(size_t)c * MP + e];
-    vec64[e] = s;
-  }
+  // ---------------- phase 0: cS = diag(c) S, diag(S) ----------------
   for (int idx = gtid; idx < MP * MP; idx += gsize) {
     const int i = idx / MP, j = idx - i * MP;
-    // Gram partials hold the lower tile triangle (tile size tp); mirror the rest
-    const int si = (i / tp >= j / tp) ? i : j, sj = (i / tp >= j / tp) ? j : i;
-    double s = 0.0;
-    for (int sp = 0; sp < L.splitsS; ++sp) s += (double)Spart[((size_t)sp * MP + si) * MP + sj];
+    const double s = S64[idx];
     if (i == j) sdiag[i] = s;
-    T64[idx] = (double)cvec[i] * s;          // cS = diag(c) S
+    T64[idx] = (double)cvec[i] * s;
   }
   grid.sync();
 
@@ -706,8 +754,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
         rz += w;
       }
       if (d == 0) rz64[i] = rz;
-      double wx = 0.0;
-      for (int sp = 0; sp < L.splitsZ; ++sp) wx += (double)WXpart[((size_t)sp * MP + i) * DP + d];
+      const double wx = WX64[(size_t)i * DP + d];
       const double ie = (double)inv_ell[d];
       const double csum = vec64[i];
       const double z = (double)Zt[(size_t)i * DP + d];
@@ -807,11 +854,8 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   return GPBLUR_OK;
 }
 
-int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                       float* grad_bucket, cudaStream_t st);
-
-int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, const float* g_kl,
-                     float* grad_bucket, int nvec_used, int ncpart, cudaStream_t st) {
+int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
+                       const float* g_kl, float* grad_bucket, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = sizeof(Tile) * 2;
   if (!attr_set) {
@@ -824,7 +868,7 @@ int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, c
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
-  MmBwdArgs args{p, L, ws, g_kl, grad_bucket, nvec_used, ncpart};
+  MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket};
   void* kargs[] = {&args};
   ProfScope ps(ST_MM_BWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),
@@ -832,6 +876,18 @@ int mm_backward_impl(const gpblur_svgp_params& p, const WsLayout& L, void* ws, c
   note_launch();
   if (e != cudaSuccess) return check_launch("mm_backward");
   return GPBLUR_OK;
+}
+
+int stage_grad_reduce_impl(const WsLayout& L, const void* ws, double* sgrad, int nvec_used, int ncpart,
+                           cudaStream_t st) {
+  const size_t total = stage_grad_doubles(L.MP, L.DP);
+  int grid = (int)((total + 31) / 32);
+  if (grid > 16 * 148) grid = 16 * 148;
+  SgReduceArgs args{L, ws, sgrad, nvec_used, ncpart};
+  ProfScope ps(ST_SG_REDUCE, st);
+  stage_grad_reduce_kernel<<<grid, kThreads, 0, st>>>(args);
+  note_launch();
+  return check_launch("stage_grad_reduce");
 }
 
 }  // namespace gpblur

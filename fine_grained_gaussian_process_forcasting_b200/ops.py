@@ -215,70 +215,191 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 # autograd
 # ------------------------------------------------------------------------------------------------
-class _SvgpFunction(torch.autograd.Function):
-    """Whitened SVGP predictive with a hand-written backward (no autograd through the kernels)."""
+def stage_grad_doubles(D: int, M: int) -> int:
+    return int(_cabi.lib().gpblur_svgp_stage_grad_doubles(D, M))
+
+
+def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b):
+    """Once-per-parameter-update M x M stage: -> (stage uint8 [param_stage_bytes], kl [1], info [1] int32)."""
+    _need_cuda(Z, raw_ell, raw_os, m, s, w, b)
+    M, D = Z.shape
+    dev = Z.device
+    nbytes = param_stage_bytes(D, M)
+    if nbytes == 0:
+        raise RuntimeError(f"unsupported SVGP shape D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, M <= {_cabi.GPBLUR_MAX_M})")
+    stage = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    kl = torch.empty(1, device=dev, dtype=torch.float32)
+    info = torch.empty(1, device=dev, dtype=torch.int32)
+    p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_param_stage(C.byref(p), D, M, _ptr(kl), _ptr(info), _ptr(stage), stage.numel(),
+                                                 _stream())
+    _cabi.check(rc, "gpblur_svgp_param_stage")
+    return stage, kl, info
+
+
+def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, stream_id: int, want_sample: bool,
+                      training: bool):
+    """x [N, D] + parameter stage -> (mean [N], var [N], sample [N] | None, workspace uint8)."""
+    _need_cuda(x, stage)
+    N, D = x.shape
+    dev = x.device
+    out = torch.empty((3 if want_sample else 2) * N, device=dev, dtype=torch.float32)   # one allocation
+    mean, var = out[:N], out[N:2 * N]
+    sample = out[2 * N:3 * N] if want_sample else None
+    ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_point_forward(
+            _ptr(stage), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, int(training),
+            _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_point_forward")
+    return mean, var, sample, ws
+
+
+def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, offset, stream_id, ws,
+                       need_dx: bool = True):
+    """-> (dx [N, D] | None, stage_grad float64 [stage_grad_doubles(D, M)])."""
+    _need_cuda(x, ws, g_mean, g_var, g_sample, var)
+    N, D = x.shape
+    dev = x.device
+    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if need_dx else None
+    sgrad = torch.empty(stage_grad_doubles(D, M), device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_point_backward(
+            _ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(var),
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+            _ptr(dx), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_point_backward")
+    return dx, sgrad
+
+
+def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor):
+    """Summed stage gradient (+ g_kl) -> flat parameter-gradient bucket [M*D + 2M + 2D + 2]."""
+    _need_cuda(Z, sgrad, stage, g_kl)
+    M, D = Z.shape
+    bucket = torch.empty(grad_bucket_floats(D, M), device=Z.device, dtype=torch.float32)
+    p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
+    with torch.cuda.device(Z.device):
+        rc = _cabi.lib().gpblur_svgp_param_stage_backward(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
+                                                          _ptr(stage), stage.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_param_stage_backward")
+    return bucket
+
+
+class _ParamStageFunction(torch.autograd.Function):
+    """Parameters -> (token, kl, info).  `token` is a float64 carrier whose GRADIENT is the stage gradient
+    (include/gpblur.h): every per-point call that uses this stage returns its contribution as d/d token, autograd
+    adds them up, and the M x M backward (Cholesky backward, Kzz-path gradients) runs ONCE per parameter update no
+    matter how many times the GP was evaluated (the reference evaluates it twice per step,
+    denoise_model_2.py:50-51).  The stage buffer itself travels in `holder` (not differentiable)."""
 
     @staticmethod
-    def forward(ctx, x, Z, raw_ell, raw_os, m, s, w, b, seed, offset, stream_id, want_sample, stage_cache):
-        shape = x.shape
-        D = shape[-1]
-        x2 = _f32c(x).reshape(-1, D)
+    def forward(ctx, Z, raw_ell, raw_os, m, s, w, b, holder):
         Zc, ellc, osc, mc, sc, bc = (_f32c(t) for t in (Z, raw_ell, raw_os, m, s, b))
         ellc = ellc.reshape(-1)
         osc = osc.reshape(-1)
         bc = bc.reshape(-1)
         wc = None if w is None else _f32c(w).reshape(-1)
-        training = any(ctx.needs_input_grad[:8])
-        # share the M x M stage between calls whose parameters are unchanged (enc / dec call of one step)
-        stage = None
-        key = None
-        if stage_cache is not None:
-            key = tuple((t._version, t.data_ptr()) for t in (Z, raw_ell, raw_os, m, s, b) if t is not None) + \
-                ((w._version, w.data_ptr()) if w is not None else (), D, Zc.shape[0])
-            if stage_cache.get("key") == key:
-                stage = stage_cache["stage"]
-        mean, var, sample, kl, info, ws = svgp_forward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, seed, offset,
-                                                           stream_id, want_sample, training, stage)
-        if stage_cache is not None and stage is None:
-            # keep a reference to this workspace: its leading param_stage_bytes() are immutable after the forward
-            # (the backward only touches scratch regions), so later calls can copy the stage straight from it
-            stage_cache["key"] = key
-            stage_cache["stage"] = ws
-        if training:
-            ctx.save_for_backward(x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws)
-        ctx.rng = (seed, offset, stream_id)
-        ctx.shapes = (shape, Z.shape, raw_ell.shape, raw_os.shape, m.shape, s.shape,
-                      None if w is None else w.shape, b.shape)
+        stage, kl, info = param_stage_raw(Zc, ellc, osc, mc, sc, wc, bc)
+        holder["stage"] = stage
+        holder["consumed"] = False
+        M, D = Zc.shape
+        ctx.holder = holder
+        ctx.save_for_backward(Zc, ellc, osc, mc, sc, wc, bc)
+        ctx.shapes = (Z.shape, raw_ell.shape, raw_os.shape, m.shape, s.shape, None if w is None else w.shape, b.shape)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(info)
-        out_shape = shape[:-1]
-        sample_out = sample.reshape(out_shape) if sample is not None else None
-        return mean.reshape(out_shape), var.reshape(out_shape), sample_out, kl.reshape(()), info
+        token = torch.zeros((), device=Zc.device, dtype=torch.float64).expand(stage_grad_doubles(D, M))
+        return token, kl.reshape(()), info
 
     @staticmethod
-    def backward(ctx, g_mean, g_var, g_sample, g_kl, _g_info):
-        x2, Zc, ellc, osc, mc, sc, wc, bc, var, ws = ctx.saved_tensors
-        seed, offset, stream_id = ctx.rng
-        N, D = x2.shape
-        M = Zc.shape[0]
-        gm = None if g_mean is None else _f32c(g_mean).reshape(-1)
-        gv = None if g_var is None else _f32c(g_var).reshape(-1)
-        gs = None if g_sample is None else _f32c(g_sample).reshape(-1)
+    def backward(ctx, g_token, g_kl, _g_info):
+        Zc, ellc, osc, mc, sc, wc, bc = ctx.saved_tensors
+        holder = ctx.holder
+        M, D = Zc.shape
+        if g_token is None:
+            sgrad = torch.zeros(stage_grad_doubles(D, M), device=Zc.device, dtype=torch.float64)
+        else:
+            sgrad = g_token.to(torch.float64).contiguous()
         gk = None if g_kl is None else _f32c(g_kl).reshape(1)
-        dx, bucket = svgp_backward_raw(x2, Zc, ellc, osc, mc, sc, wc, bc, gm, gv, gs, gk, var, seed, offset,
-                                       stream_id, ws, need_dx=ctx.needs_input_grad[0])
+        bucket = param_stage_backward_raw(Zc, ellc, osc, mc, sc, wc, bc, sgrad, gk, holder["stage"])
+        holder["consumed"] = True        # the graph behind this token is gone: the next forward rebuilds the stage
         dZ, dell, dos, dm, ds, dw, db = split_bucket(bucket, D, M, wc is not None)
         shp = ctx.shapes
         need = ctx.needs_input_grad
-        return (dx.reshape(shp[0]) if need[0] else None,
-                dZ.reshape(shp[1]) if need[1] else None,
-                dell.reshape(shp[2]) if need[2] else None,
-                dos.reshape(shp[3]) if need[3] else None,
-                dm.reshape(shp[4]) if need[4] else None,
-                ds.reshape(shp[5]) if need[5] else None,
-                dw.reshape(shp[6]) if (wc is not None and need[6]) else None,
-                db.reshape(shp[7]) if need[7] else None,
-                None, None, None, None, None)
+        return (dZ.reshape(shp[0]) if need[0] else None,
+                dell.reshape(shp[1]) if need[1] else None,
+                dos.reshape(shp[2]) if need[2] else None,
+                dm.reshape(shp[3]) if need[3] else None,
+                ds.reshape(shp[4]) if need[4] else None,
+                dw.reshape(shp[5]) if (wc is not None and need[5]) else None,
+                db.reshape(shp[6]) if need[6] else None,
+                None)
+
+
+class _PointFunction(torch.autograd.Function):
+    """Per-point part of the whitened SVGP predictive on a given parameter stage, hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample):
+        shape = x.shape
+        D = shape[-1]
+        x2 = _f32c(x).reshape(-1, D)
+        training = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        mean, var, sample, ws = point_forward_raw(holder["stage"], x2, M, seed, offset, stream_id, want_sample,
+                                                  training)
+        if training:
+            ctx.save_for_backward(x2, var, ws)
+        ctx.meta = (seed, offset, stream_id, M, shape)
+        ctx.set_materialize_grads(False)
+        out_shape = shape[:-1]
+        sample_out = sample.reshape(out_shape) if sample is not None else None
+        return mean.reshape(out_shape), var.reshape(out_shape), sample_out
+
+    @staticmethod
+    def backward(ctx, g_mean, g_var, g_sample):
+        x2, var, ws = ctx.saved_tensors
+        seed, offset, stream_id, M, shape = ctx.meta
+        gm = None if g_mean is None else _f32c(g_mean).reshape(-1)
+        gv = None if g_var is None else _f32c(g_var).reshape(-1)
+        gs = None if g_sample is None else _f32c(g_sample).reshape(-1)
+        need = ctx.needs_input_grad
+        dx, sgrad = point_backward_raw(x2, M, gm, gv, gs, var, seed, offset, stream_id, ws, need_dx=need[0])
+        return (dx.reshape(shape) if need[0] else None, sgrad if need[1] else None,
+                None, None, None, None, None, None)
+
+
+def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
+    key = tuple((t._version, t.data_ptr()) for t in (Z, raw_ell, raw_os, m, s, b))
+    if w is not None:
+        key += ((w._version, w.data_ptr()),)
+    return key + (tuple(Z.shape),)
+
+
+def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
+                     variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
+                     mean_bias: Tensor, stage_cache: Optional[dict] = None):
+    """-> (token, kl [], info [1], holder).  With `stage_cache` (a dict owned by the caller, one per GP) consecutive
+    calls with unchanged parameter tensors (same `_version`) share one stage - and therefore one M x M backward -
+    until a backward pass has consumed it."""
+    params = (inducing_points, raw_lengthscale, raw_outputscale, variational_mean, variational_stddev, mean_weights,
+              mean_bias)
+    want_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params)
+    key = None
+    if stage_cache is not None:
+        key = _stage_key(*params)
+        ent = stage_cache.get("entry")
+        if ent is not None and stage_cache.get("key") == key and not ent[3]["consumed"] \
+                and ent[0].requires_grad == want_grad:
+            return ent
+    holder = {}
+    token, kl, info = _ParamStageFunction.apply(*params, holder)
+    ent = (token, kl, info, holder)
+    if stage_cache is not None:
+        stage_cache["key"] = key
+        stage_cache["entry"] = ent
+    return ent
 
 
 def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
@@ -286,11 +407,15 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
                  want_sample: bool = False, stage_cache: Optional[dict] = None):
     """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]).
-    `stage_cache`: a dict owned by the caller (one per GP) that lets consecutive calls with unchanged parameter
-    tensors (same `_version`) share the once-per-update M x M stage."""
-    return _SvgpFunction.apply(x, inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
-                               variational_stddev, mean_weights, mean_bias, int(seed), int(offset),
-                               int(stream_id), bool(want_sample), stage_cache)
+    `stage_cache`: see svgp_param_stage."""
+    token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
+                                               variational_stddev, mean_weights, mean_bias, stage_cache)
+    if x.numel() == 0:
+        e = x.new_empty(x.shape[:-1], dtype=torch.float32)
+        return e, e.clone(), (e.clone() if want_sample else None), kl, info
+    mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[0]), int(seed), int(offset),
+                                             int(stream_id), bool(want_sample))
+    return mean, var, sample, kl, info
 
 
 class _ElboFunction(torch.autograd.Function):

@@ -97,6 +97,39 @@ int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long 
                          uint32_t stream_id, float* dx, float* grad_bucket, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* ---- split form: one parameter stage shared by several calls -------------------------------------------
+ * The reference evaluates the SAME GP on the encoder and on the decoder activations of one training step
+ * (/root/reference/denoising_model/denoise_model_2.py:50-51) and gpytorch factorises Kzz (and differentiates the
+ * factorisation) once per call and per batch element.  Here the once-per-parameter-update M x M work is its own
+ * pair of entry points, and each call contributes a "stage gradient" that is LINEAR in its upstream gradients:
+ *
+ *   gpblur_svgp_param_stage          params -> stage (Kzz, L, Linv, fp32 / UMMA operand images), kl, info
+ *   gpblur_svgp_point_forward        (stage, x) -> mean, var, sample              [any number of calls]
+ *   gpblur_svgp_point_backward       upstream grads -> dx, stage_grad (fp64)      [one per forward call]
+ *   gpblur_svgp_param_stage_backward (stage, SUM of the stage_grads, g_kl) -> flat parameter-gradient bucket
+ *
+ * stage_grad holds gpblur_svgp_stage_grad_doubles(D, M) doubles:
+ *   [ u (Mp) | colsum(W) (Mp), q (Dp), wbar (Dp), scalars (4) | S = sum g_var a a^T (Mp x Mp) | W^T X (Mp x Dp) ]
+ * gpblur_svgp_forward / gpblur_svgp_backward below are the single-call compositions of these four. */
+size_t gpblur_svgp_stage_grad_doubles(int D, int M);
+int gpblur_svgp_param_stage(const gpblur_svgp_params* p, int D, int M, float* kl, int* info,
+                            void* stage, size_t stage_bytes, void* stream);
+/* `ws` (gpblur_svgp_workspace_bytes(N, D, M, training)) receives a copy of the stage and, when training, the
+ * saved whitened cross-covariance; hand the same `ws` to gpblur_svgp_point_backward. */
+int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long N, int D, int M,
+                              float* mean, float* var, float* sample, uint64_t seed, uint64_t offset,
+                              uint32_t stream_id, int training, void* ws, size_t ws_bytes,
+                              void* stream);
+int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const float* g_mean,
+                               const float* g_var, const float* g_sample, const float* var,
+                               uint64_t seed, uint64_t offset, uint32_t stream_id, float* dx,
+                               double* stage_grad, void* ws, size_t ws_bytes, void* stream);
+/* `stage` is the buffer filled by gpblur_svgp_param_stage; its fp64 scratch regions are overwritten. */
+int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M,
+                                     const double* stage_grad, const float* g_kl,
+                                     float* grad_bucket, void* stage, size_t stage_bytes,
+                                     void* stream);
+
 /* Expected log-likelihood part of the ELBO.
  * Replaces DeepApproximateMLL(VariationalELBO(likelihood, model, num_data))(dist, y) built at
  * /root/reference/forecast_denoising.py:87-89 (GaussianLikelihood.expected_log_prob, sum over the
@@ -146,7 +179,7 @@ int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, voi
 /* Optional per-stage timing for bench.py's roofline: while enabled, every launch is bracketed with CUDA
  * events on its own stream.  gpblur_profile_collect synchronises on the recorded events, writes the
  * accumulated milliseconds / launch counts per stage (order: mm_fwd, point_fwd, point_bwd, gram, wx,
- * mm_bwd, elbo_fwd, elbo_bwd, other; n >= 9) and clears the records. */
+ * mm_bwd, elbo_fwd, elbo_bwd, dx, sg_reduce; n >= 10) and clears the records. */
 int gpblur_profile_enable(int on);
 int gpblur_profile_collect(double* ms, unsigned long long* counts, int n);
 

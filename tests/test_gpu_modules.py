@@ -277,20 +277,60 @@ def test_param_stage_is_shared_between_calls_and_invalidated_by_updates(cuda):
         torch.cuda.synchronize()
         prof = _cabi.profile_collect()
         assert prof["mm_fwd"][1] == 1 and prof["point_fwd"][1] == 2          # one factorisation, two point passes
+        # gradients through the cached call
+        mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
+        (-mll(d2, y.to(cuda).unsqueeze(0)).mean() + m1.sum()).backward()
+        torch.cuda.synchronize()
+        prof_b = _cabi.profile_collect()
+        # two per-point backward passes, ONE M x M backward (the stage gradients of both calls are summed first)
+        assert prof_b["point_bwd"][1] == 2 and prof_b["mm_bwd"][1] == 1 and prof_b["sg_reduce"][1] == 2
         hl.share_param_stage = False
         m2_ref, d2_ref = model.predict(x_dec.to(cuda))
         assert torch.equal(m2, m2_ref) and torch.equal(d2.variance, d2_ref.variance)
         hl.share_param_stage = True
-        # gradients through the cached call
-        mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
-        (-mll(d2, y.to(cuda).unsqueeze(0)).mean() + m1.sum()).backward()
+        torch.cuda.synchronize()
+        _cabi.profile_collect()
         with torch.no_grad():
             hl.variational_strategy.inducing_points.add_(0.01)                # "optimizer step"
         m3, _ = model.predict(x_dec.to(cuda))
         torch.cuda.synchronize()
         prof = _cabi.profile_collect()
         _cabi.profile_enable(False)
-        assert prof["mm_fwd"][1] >= 2                                          # uncached call + recompute after update
+        assert prof["mm_fwd"][1] == 1                                          # recompute after the update
     p2 = dict(p, inducing_points=p["inducing_points"] + 0.01)
     mo, _ = O.svgp_predict_closed_form(O.clone_params(p2, torch.float64), x_dec.double())
     assert rel(m3[0], mo) < 1e-4
+
+
+def test_two_calls_on_one_stage_match_the_oracle_gradients(cuda):
+    """enc + dec call of one step (denoise_model_2.py:50-51) on ONE parameter stage: every parameter gradient is
+    the sum over both calls, computed by a single M x M backward."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    for (D, M) in ((16, 32), (32, 256)):
+        p = O.init_params_exercise(D, M, 11)
+        x1, _, gm1, gv1 = O.make_inputs(3, 40, D, 12)
+        x2, _, gm2, gv2 = O.make_inputs(5, 24, D, 13)
+        names = ("inducing_points", "raw_lengthscale", "raw_outputscale", "variational_mean", "variational_stddev",
+                 "weights", "bias")
+        pd = {k: p[k].to(cuda).clone().requires_grad_(True) for k in names}
+        cache = {}
+        xs = [x1.to(cuda).requires_grad_(True), x2.to(cuda).requires_grad_(True)]
+        outs, grads = [], []
+        kl = None
+        for x, gm, gv in zip(xs, (gm1, gm2), (gv1, gv2)):
+            mean, var, _, kl, _ = ops.svgp_predict(x, *(pd[k] for k in names), stage_cache=cache)
+            outs += [mean, var]
+            grads += [gm.to(cuda), gv.to(cuda)]
+        torch.autograd.backward(outs + [kl], grads + [torch.tensor(0.3, device=cuda)])
+        p64 = O.clone_params(p, torch.float64, requires_grad=True)
+        xo = [x1.double().requires_grad_(True), x2.double().requires_grad_(True)]
+        loss = 0.3 * O.kl_meanfield(p64)
+        for x, gm, gv in zip(xo, (gm1, gm2), (gv1, gv2)):
+            mo, vo = O.svgp_predict_closed_form(p64, x)
+            loss = loss + (gm.double() * mo).sum() + (gv.double() * vo).sum()
+        loss.backward()
+        tol = 2e-4
+        for k in names:
+            assert rel(pd[k].grad.reshape(-1), p64[k].grad.reshape(-1)) < tol, (D, M, k)
+        for xg, xr in zip(xs, xo):
+            assert rel(xg.grad, xr.grad) < tol
