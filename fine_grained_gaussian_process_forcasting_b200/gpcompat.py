@@ -482,32 +482,28 @@ class DeepGPLayer(ApproximateGP):
     def forward(self, x):   # pragma: no cover - subclasses define the prior
         raise NotImplementedError
 
-    def _layer_params(self, h: Optional[int]):
+    def _layer_params(self):
+        """Parameter tensors of the layer as the fused ops take them; a multi-output layer (output_dims = H) passes
+        its batched parameters ([H, M, D] inducing points ...) and is evaluated by ONE batched op."""
         vs = self.variational_strategy
         vd = vs._variational_distribution
         raw_ell, raw_os = _kernel_raw_params(self.covar_module)
         Z, m, s = vs.inducing_points, vd.variational_mean, vd._variational_stddev
-        if h is not None:
-            Z, m, s, raw_ell, raw_os = Z[h], m[h], s[h], raw_ell[h], raw_os[h]
         mm = self.mean_module
         if isinstance(mm, LinearMean):
             w, b = mm.weights, (mm.bias if mm.bias is not None else torch.zeros(1, device=Z.device))
         elif isinstance(mm, ConstantMean):
-            w = None
-            b = mm.raw_constant if h is None or mm.raw_constant.dim() == 0 else mm.raw_constant[h]
+            w, b = None, mm.raw_constant
         else:
             raise NotImplementedError("mean module %r" % type(mm).__name__)
         return Z, raw_ell, raw_os, m, s, w, b
 
+    def _stage_cache(self):
+        return self._stage_caches.setdefault(None, {}) if self.share_param_stage else None
+
     def _kl_only(self):
-        H = self.output_dims
-        kls = []
-        for h in ([None] if H is None else range(H)):
-            Z, raw_ell, raw_os, m, s, w, b = self._layer_params(h)
-            x0 = torch.empty(0, Z.shape[-1], device=Z.device, dtype=torch.float32)
-            _, _, _, kl, _ = ops.svgp_predict(x0, Z, raw_ell, raw_os, m, s, w, b)
-            kls.append(kl)
-        return torch.stack(kls).sum() if H is not None else kls[0]
+        _, kl, _, _ = ops.svgp_param_stage(*self._layer_params(), stage_cache=self._stage_cache())
+        return kl.sum() if kl.dim() else kl
 
     def __call__(self, inputs, are_samples=False, **kwargs):
         vs = self.variational_strategy
@@ -525,28 +521,21 @@ class DeepGPLayer(ApproximateGP):
                                f"[{inputs.shape[-1]}], expected [{self.input_dims}]")
         H = self.output_dims
         n_pts = inputs.numel() // inputs.shape[-1]
-        means, vars_, samples, kls = [], [], [], []
-        for h in ([None] if H is None else range(H)):
-            Z, raw_ell, raw_os, m, s, w, b = self._layer_params(h)
-            seed, off, stream = self._next_counters(n_pts) if self.fused_sample else (0, 0, 0)
-            cache = self._stage_caches.setdefault(h, {}) if self.share_param_stage else None
-            mean, var, sample, kl, info = ops.svgp_predict(inputs, Z, raw_ell, raw_os, m, s, w, b, seed, off, stream,
-                                                           want_sample=self.fused_sample, stage_cache=cache)
-            self.last_info = info
-            means.append(mean); vars_.append(var); samples.append(sample); kls.append(kl)
+        # GP h of a multi-output layer draws its sample with counters offset + h * n_pts + n
+        seed, off, stream = self._next_counters(n_pts * (H or 1)) if self.fused_sample else (0, 0, 0)
+        mean, var, sample, kl, info = ops.svgp_predict(inputs, *self._layer_params(), seed, off, stream,
+                                                       want_sample=self.fused_sample,
+                                                       stage_cache=self._stage_cache())
+        self.last_info = info
         if check_cholesky.value():
-            k = int(self.last_info.item())
+            k = int(info.max().item())
             if k != 0:
                 raise NotPSDError(f"Kzz + jitter is not positive definite (pivot {k}); gpytorch would retry "
                                   f"with more jitter")
         if H is None:
-            mean, var, sample, kl = means[0], vars_[0], samples[0], kls[0]
             cls = MultivariateNormal
         else:
-            mean = torch.stack(means, -1)
-            var = torch.stack(vars_, -1)
-            sample = torch.stack(samples, -1) if self.fused_sample else None
-            kl = torch.stack(kls).sum()
+            kl = kl.sum()
             cls = MultitaskMultivariateNormal
         vs._cache_kl(kl)
         dist = cls(mean, None, variance=var, sample=sample, kl=kl, layer=self)

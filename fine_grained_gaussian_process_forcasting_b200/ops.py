@@ -21,7 +21,9 @@ def _ptr(t: Optional[Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of the current stream of the current device.  NOT torch.cuda.current_stream(): with device=None
+    # that goes through torch.cuda.is_available() -> cudaGetDeviceCount on every call (~0.1 ms each here).
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _need_cuda(*tensors):
@@ -219,17 +221,22 @@ def stage_grad_doubles(D: int, M: int) -> int:
     return int(_cabi.lib().gpblur_svgp_stage_grad_doubles(D, M))
 
 
-def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b):
-    """Once-per-parameter-update M x M stage: -> (stage uint8 [param_stage_bytes], kl [1], info [1] int32)."""
+def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None):
+    """Once-per-parameter-update M x M stage: -> (stage uint8 [param_stage_bytes], kl [1], info [1] int32).
+    `out` = preallocated (stage, kl, info) (the call then only launches on the current stream)."""
     _need_cuda(Z, raw_ell, raw_os, m, s, w, b)
     M, D = Z.shape
     dev = Z.device
-    nbytes = param_stage_bytes(D, M)
-    if nbytes == 0:
-        raise RuntimeError(f"unsupported SVGP shape D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, M <= {_cabi.GPBLUR_MAX_M})")
-    stage = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    kl = torch.empty(1, device=dev, dtype=torch.float32)
-    info = torch.empty(1, device=dev, dtype=torch.int32)
+    if out is None:
+        nbytes = param_stage_bytes(D, M)
+        if nbytes == 0:
+            raise RuntimeError(f"unsupported SVGP shape D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, "
+                               f"M <= {_cabi.GPBLUR_MAX_M})")
+        stage = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        kl = torch.empty(1, device=dev, dtype=torch.float32)
+        info = torch.empty(1, device=dev, dtype=torch.int32)
+    else:
+        stage, kl, info = out
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(dev):
         rc = _cabi.lib().gpblur_svgp_param_stage(C.byref(p), D, M, _ptr(kl), _ptr(info), _ptr(stage), stage.numel(),
@@ -239,12 +246,14 @@ def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b):
 
 
 def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, stream_id: int, want_sample: bool,
-                      training: bool):
-    """x [N, D] + parameter stage -> (mean [N], var [N], sample [N] | None, workspace uint8)."""
+                      training: bool, out: Optional[Tensor] = None):
+    """x [N, D] + parameter stage -> (mean [N], var [N], sample [N] | None, workspace uint8).
+    `out`: preallocated float32 [(3 | 2) * N] receiving mean | var | sample."""
     _need_cuda(x, stage)
     N, D = x.shape
     dev = x.device
-    out = torch.empty((3 if want_sample else 2) * N, device=dev, dtype=torch.float32)   # one allocation
+    if out is None:
+        out = torch.empty((3 if want_sample else 2) * N, device=dev, dtype=torch.float32)   # one allocation
     mean, var = out[:N], out[N:2 * N]
     sample = out[2 * N:3 * N] if want_sample else None
     ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
@@ -258,27 +267,31 @@ def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, 
 
 
 def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, offset, stream_id, ws,
-                       need_dx: bool = True):
+                       need_dx: bool = True, dx: Optional[Tensor] = None, sgrad: Optional[Tensor] = None):
     """-> (dx [N, D] | None, stage_grad float64 [stage_grad_doubles(D, M)])."""
     _need_cuda(x, ws, g_mean, g_var, g_sample, var)
     N, D = x.shape
     dev = x.device
-    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if need_dx else None
-    sgrad = torch.empty(stage_grad_doubles(D, M), device=dev, dtype=torch.float64)
+    if dx is None and need_dx:
+        dx = torch.empty(N, D, device=dev, dtype=torch.float32)
+    if sgrad is None:
+        sgrad = torch.empty(stage_grad_doubles(D, M), device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
         rc = _cabi.lib().gpblur_svgp_point_backward(
             _ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(var),
             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
-            _ptr(dx), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
+            _ptr(dx if need_dx else None), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
     _cabi.check(rc, "gpblur_svgp_point_backward")
-    return dx, sgrad
+    return (dx if need_dx else None), sgrad
 
 
-def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor):
+def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor,
+                             bucket: Optional[Tensor] = None):
     """Summed stage gradient (+ g_kl) -> flat parameter-gradient bucket [M*D + 2M + 2D + 2]."""
     _need_cuda(Z, sgrad, stage, g_kl)
     M, D = Z.shape
-    bucket = torch.empty(grad_bucket_floats(D, M), device=Z.device, dtype=torch.float32)
+    if bucket is None:
+        bucket = torch.empty(grad_bucket_floats(D, M), device=Z.device, dtype=torch.float32)
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(Z.device):
         rc = _cabi.lib().gpblur_svgp_param_stage_backward(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
@@ -287,87 +300,209 @@ def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl
     return bucket
 
 
+# ---- side streams: the M x M stages of the H independent GPs of a multi-output layer run concurrently ----
+_SIDE_STREAMS = {}
+N_SIDE_STREAMS = 4
+
+
+def _side_streams(dev):
+    key = (dev.type, dev.index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(N_SIDE_STREAMS)]
+    return st
+
+
+class _Fork:
+    """Round-robin fork of H independent launches onto side streams, joined back into the current stream.
+    All buffers are allocated by the caller on the CURRENT stream before the fork; only launches happen inside.
+    (Uses the raw set-stream call: torch.cuda.stream() / current_stream(None) cost ~0.1 ms each here because they
+    go through torch.cuda.is_available().)"""
+
+    def __init__(self, dev, H):
+        self.H = H
+        if H <= 1:
+            return
+        self.dev = dev
+        self.cur = torch.cuda.current_stream(dev)
+        self.side = _side_streams(dev)
+        self.ev = torch.cuda.Event()
+        self.ev.record(self.cur)
+        for st in self.side[:H]:
+            st.wait_event(self.ev)
+
+    def enter(self, h):
+        if self.H > 1:
+            torch.cuda.set_stream(self.side[h % len(self.side)])
+
+    def join(self):
+        if self.H <= 1:
+            return
+        torch.cuda.set_stream(self.cur)
+        for st in self.side[:self.H]:
+            self.cur.wait_stream(st)
+
+
 class _ParamStageFunction(torch.autograd.Function):
     """Parameters -> (token, kl, info).  `token` is a float64 carrier whose GRADIENT is the stage gradient
     (include/gpblur.h): every per-point call that uses this stage returns its contribution as d/d token, autograd
     adds them up, and the M x M backward (Cholesky backward, Kzz-path gradients) runs ONCE per parameter update no
     matter how many times the GP was evaluated (the reference evaluates it twice per step,
-    denoise_model_2.py:50-51).  The stage buffer itself travels in `holder` (not differentiable)."""
+    denoise_model_2.py:50-51).  The stage buffer itself travels in `holder` (not differentiable).
+
+    Multi-output layers (DeepGP.py:21-26: inducing points [H, M, D], H independent GPs) are handled in ONE node:
+    parameters carry a leading H, token is [H, G], and the H M x M stages (forward and backward) are launched on
+    side streams so that they overlap on the GPU."""
 
     @staticmethod
     def forward(ctx, Z, raw_ell, raw_os, m, s, w, b, holder):
-        Zc, ellc, osc, mc, sc, bc = (_f32c(t) for t in (Z, raw_ell, raw_os, m, s, b))
-        ellc = ellc.reshape(-1)
-        osc = osc.reshape(-1)
-        bc = bc.reshape(-1)
-        wc = None if w is None else _f32c(w).reshape(-1)
-        stage, kl, info = param_stage_raw(Zc, ellc, osc, mc, sc, wc, bc)
+        batched = Z.dim() == 3
+        H = Z.shape[0] if batched else 1
+        M, D = Z.shape[-2], Z.shape[-1]
+        Zc = _f32c(Z).reshape(H, M, D)
+        ellc = _f32c(raw_ell).reshape(H, D)
+        osc = _f32c(raw_os).reshape(H, 1)
+        mc = _f32c(m).reshape(H, M)
+        sc = _f32c(s).reshape(H, M)
+        wc = None if w is None else _f32c(w).reshape(-1, D)           # [1, D] shared or [H, D]
+        bc = _f32c(b).reshape(-1, 1)                                  # [1, 1] shared or [H, 1]
+        dev = Zc.device
+        _need_cuda(Zc)
+        nbytes = param_stage_bytes(D, M)
+        if nbytes == 0:
+            raise RuntimeError(f"unsupported SVGP shape D={D} M={M} (D <= {_cabi.GPBLUR_MAX_D}, "
+                               f"M <= {_cabi.GPBLUR_MAX_M})")
+        stage = torch.empty(H, nbytes, device=dev, dtype=torch.uint8)
+        kl = torch.empty(H, device=dev, dtype=torch.float32)
+        info = torch.empty(H, device=dev, dtype=torch.int32)
+        fork = _Fork(dev, H)
+        try:
+            for h in range(H):
+                fork.enter(h)
+                param_stage_raw(Zc[h], ellc[h], osc[h], mc[h], sc[h], None if wc is None else wc[h % wc.shape[0]],
+                                bc[h % bc.shape[0]], out=(stage[h], kl[h:h + 1], info[h:h + 1]))
+        finally:
+            fork.join()
         holder["stage"] = stage
         holder["consumed"] = False
-        M, D = Zc.shape
         ctx.holder = holder
+        ctx.batched = batched
         ctx.save_for_backward(Zc, ellc, osc, mc, sc, wc, bc)
         ctx.shapes = (Z.shape, raw_ell.shape, raw_os.shape, m.shape, s.shape, None if w is None else w.shape, b.shape)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(info)
-        token = torch.zeros((), device=Zc.device, dtype=torch.float64).expand(stage_grad_doubles(D, M))
-        return token, kl.reshape(()), info
+        G = stage_grad_doubles(D, M)
+        token = torch.zeros((), device=dev, dtype=torch.float64).expand((H, G) if batched else (G,))
+        return token, (kl if batched else kl.reshape(())), info
 
     @staticmethod
     def backward(ctx, g_token, g_kl, _g_info):
         Zc, ellc, osc, mc, sc, wc, bc = ctx.saved_tensors
         holder = ctx.holder
-        M, D = Zc.shape
+        H, M, D = Zc.shape
+        dev = Zc.device
+        G = stage_grad_doubles(D, M)
         if g_token is None:
-            sgrad = torch.zeros(stage_grad_doubles(D, M), device=Zc.device, dtype=torch.float64)
+            sgrad = torch.zeros(H, G, device=dev, dtype=torch.float64)
         else:
-            sgrad = g_token.to(torch.float64).contiguous()
-        gk = None if g_kl is None else _f32c(g_kl).reshape(1)
-        bucket = param_stage_backward_raw(Zc, ellc, osc, mc, sc, wc, bc, sgrad, gk, holder["stage"])
+            sgrad = g_token.to(torch.float64).reshape(H, G).contiguous()
+        gk = None if g_kl is None else _f32c(g_kl).reshape(-1).expand(H).contiguous()
+        nb = grad_bucket_floats(D, M)
+        bucket = torch.empty(H, nb, device=dev, dtype=torch.float32)
+        stage = holder["stage"]
+        fork = _Fork(dev, H)
+        try:
+            for h in range(H):
+                fork.enter(h)
+                param_stage_backward_raw(Zc[h], ellc[h], osc[h], mc[h], sc[h],
+                                         None if wc is None else wc[h % wc.shape[0]], bc[h % bc.shape[0]], sgrad[h],
+                                         None if gk is None else gk[h:h + 1], stage[h], bucket=bucket[h])
+        finally:
+            fork.join()
         holder["consumed"] = True        # the graph behind this token is gone: the next forward rebuilds the stage
-        dZ, dell, dos, dm, ds, dw, db = split_bucket(bucket, D, M, wc is not None)
+        o = 0
+        dZ = bucket[:, o:o + M * D]; o += M * D
+        dell = bucket[:, o:o + D]; o += D
+        dos = bucket[:, o:o + 1]; o += 1
+        dm = bucket[:, o:o + M]; o += M
+        ds = bucket[:, o:o + M]; o += M
+        dw = bucket[:, o:o + D]; o += D
+        db = bucket[:, o:o + 1]
         shp = ctx.shapes
         need = ctx.needs_input_grad
+
+        def shared(t, shape, n_rows):
+            # a parameter shared by the H GPs (LinearMean of a multi-output layer) receives the sum over h
+            return (t.sum(0) if (H > 1 and n_rows == 1) else t).reshape(shape)
+
         return (dZ.reshape(shp[0]) if need[0] else None,
                 dell.reshape(shp[1]) if need[1] else None,
                 dos.reshape(shp[2]) if need[2] else None,
                 dm.reshape(shp[3]) if need[3] else None,
                 ds.reshape(shp[4]) if need[4] else None,
-                dw.reshape(shp[5]) if (wc is not None and need[5]) else None,
-                db.reshape(shp[6]) if need[6] else None,
+                shared(dw, shp[5], wc.shape[0]) if (wc is not None and need[5]) else None,
+                shared(db, shp[6], bc.shape[0]) if need[6] else None,
                 None)
 
 
 class _PointFunction(torch.autograd.Function):
-    """Per-point part of the whitened SVGP predictive on a given parameter stage, hand-written backward."""
+    """Per-point part of the whitened SVGP predictive on a given parameter stage, hand-written backward.
+    With an [H, G] token (multi-output layer) every output gains a trailing H: mean [..., H]."""
 
     @staticmethod
     def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample):
         shape = x.shape
         D = shape[-1]
         x2 = _f32c(x).reshape(-1, D)
+        N = x2.shape[0]
+        batched = token.dim() == 2
+        H = token.shape[0] if batched else 1
         training = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        mean, var, sample, ws = point_forward_raw(holder["stage"], x2, M, seed, offset, stream_id, want_sample,
-                                                  training)
+        nout = 3 if want_sample else 2
+        out = torch.empty(H, nout * N, device=x2.device, dtype=torch.float32)
+        stage = holder["stage"]
+        wss = []
+        for h in range(H):
+            _, _, _, ws = point_forward_raw(stage[h], x2, M, seed, offset + h * N, stream_id, want_sample, training,
+                                            out=out[h])
+            wss.append(ws)
         if training:
-            ctx.save_for_backward(x2, var, ws)
-        ctx.meta = (seed, offset, stream_id, M, shape)
+            ctx.save_for_backward(x2, out, *wss)
+        ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout)
         ctx.set_materialize_grads(False)
-        out_shape = shape[:-1]
-        sample_out = sample.reshape(out_shape) if sample is not None else None
-        return mean.reshape(out_shape), var.reshape(out_shape), sample_out
+        out_shape = tuple(shape[:-1]) + ((H,) if batched else ())
+
+        def view(i):
+            t = out[:, i * N:(i + 1) * N]                      # [H, N]
+            return (t.t() if batched else t[0]).reshape(out_shape)
+
+        return view(0), view(1), (view(2) if want_sample else None)
 
     @staticmethod
     def backward(ctx, g_mean, g_var, g_sample):
-        x2, var, ws = ctx.saved_tensors
-        seed, offset, stream_id, M, shape = ctx.meta
-        gm = None if g_mean is None else _f32c(g_mean).reshape(-1)
-        gv = None if g_var is None else _f32c(g_var).reshape(-1)
-        gs = None if g_sample is None else _f32c(g_sample).reshape(-1)
+        x2, out, *wss = ctx.saved_tensors
+        seed, offset, stream_id, M, shape, H, batched, nout = ctx.meta
+        N, D = x2.shape
+        dev = x2.device
+
+        def prep(g):
+            if g is None:
+                return None
+            g = _f32c(g)
+            return g.reshape(N, H).t().contiguous() if batched else g.reshape(1, N)
+
+        gm, gv, gs = prep(g_mean), prep(g_var), prep(g_sample)
         need = ctx.needs_input_grad
-        dx, sgrad = point_backward_raw(x2, M, gm, gv, gs, var, seed, offset, stream_id, ws, need_dx=need[0])
-        return (dx.reshape(shape) if need[0] else None, sgrad if need[1] else None,
-                None, None, None, None, None, None)
+        G = stage_grad_doubles(D, M)
+        sgrad = torch.empty(H, G, device=dev, dtype=torch.float64)
+        dx = torch.empty(H, N, D, device=dev, dtype=torch.float32) if need[0] else None
+        for h in range(H):
+            point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
+                               None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * N, stream_id,
+                               wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h])
+        if dx is not None:
+            dx = (dx.sum(0) if H > 1 else dx[0]).reshape(shape)
+        return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None)
 
 
 def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
@@ -380,9 +515,10 @@ def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
 def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
                      variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                      mean_bias: Tensor, stage_cache: Optional[dict] = None):
-    """-> (token, kl [], info [1], holder).  With `stage_cache` (a dict owned by the caller, one per GP) consecutive
+    """-> (token, kl, info, holder).  With `stage_cache` (a dict owned by the caller, one per GP layer) consecutive
     calls with unchanged parameter tensors (same `_version`) share one stage - and therefore one M x M backward -
-    until a backward pass has consumed it."""
+    until a backward pass has consumed it.  Parameters with a leading H (inducing points [H, M, D]) describe the H
+    independent GPs of a multi-output layer: kl is [H], token [H, G]."""
     params = (inducing_points, raw_lengthscale, raw_outputscale, variational_mean, variational_stddev, mean_weights,
               mean_bias)
     want_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in params)
@@ -406,14 +542,16 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
                  want_sample: bool = False, stage_cache: Optional[dict] = None):
-    """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]).
-    `stage_cache`: see svgp_param_stage."""
+    """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]); with inducing points [H, M, D]
+    (multi-output layer) the outputs are [..., H], kl [H], info [H], and GP h draws its sample with Philox counters
+    offset + h * N + n.  `stage_cache`: see svgp_param_stage."""
     token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
                                                variational_stddev, mean_weights, mean_bias, stage_cache)
     if x.numel() == 0:
-        e = x.new_empty(x.shape[:-1], dtype=torch.float32)
+        shp = tuple(x.shape[:-1]) + ((token.shape[0],) if token.dim() == 2 else ())
+        e = x.new_empty(shp, dtype=torch.float32)
         return e, e.clone(), (e.clone() if want_sample else None), kl, info
-    mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[0]), int(seed), int(offset),
+    mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
                                              int(stream_id), bool(want_sample))
     return mean, var, sample, kl, info
 
