@@ -49,7 +49,7 @@ struct WsLayout {
   int nvec;                 // number of per-CTA vector partials (persistent backward CTAs)
   int vec_len;              // floats per vector partial
   // byte offsets
-  size_t hyp, hyp64, stamps, inv_ell, ell, center, wl, Zt, ZtT, zn, mvec, cvec, svec, beta;
+  size_t hyp, hyp64, stamps, inv_ell, ell, center, wl, Zt, ZtT, zn, znc, mvec, cvec, svec, beta;
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
   size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
   size_t v64, t64;                 // fp64 scratch of the M x M backward (part of the parameter stage)
@@ -129,6 +129,7 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.Zt = take(MP * DP * 4);
   w.ZtT = take(DP * MP * 4);
   w.zn = take(MP * 4);
+  w.znc = take(MP * 4);   // -1/2 log2(e) |z~_j|^2 + log2(os)  (-1e30 on padded columns): exponent offset of the tc kernels
   w.mvec = take(MP * 4);
   w.cvec = take(MP * 4);
   w.svec = take(MP * 4);

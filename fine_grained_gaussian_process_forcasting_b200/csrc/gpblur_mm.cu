@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   }
   GPBLUR_STAMP();
   float* zn = ws_ptr<float>(a.ws, L.zn);
+  float* znc = ws_ptr<float>(a.ws, L.znc);
   // beta = Linv^T m : one CTA per 32-column chunk, lanes = columns (coalesced rows), the 8 warps split the rows
   {
     __shared__ double bred[8][32];
@@ -513,7 +514,11 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     float z2 = 0.f;
     for (int d = lane; d < DP; d += 32) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
     z2 = warp_sum(z2);
-    if (lane == 0) zn[j] = z2;
+    if (lane == 0) {
+      zn[j] = z2;
+      const float l2os = (float)(log(softplus64((double)a.p.raw_outputscale[0])) * 1.4426950408889634);
+      znc[j] = j < M ? fmaf(-0.72134752044448170f, z2, l2os) : -1e30f;
+    }
   }
   GPBLUR_STAMP();
 #undef GPBLUR_STAMP

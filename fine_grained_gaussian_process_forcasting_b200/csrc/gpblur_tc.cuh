@@ -47,6 +47,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// 1-D TMA bulk copy shared -> global (bulk async-group completion): the epilogues stage a row segment in shared
+// memory and let the TMA engine write it out as full lines instead of 32 scattered 16-byte stores per instruction
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every bulk store committed by this thread has finished READING its shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- fences ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -131,6 +142,13 @@ __device__ __forceinline__ float fast_exp(float x) {
   const float t2 = fmaf(x, 1.9259629911266175e-08f, r) + t;     // + x * (log2e - fl(log2e))
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t2));
+  return y;
+}
+
+// 2^x, one MUFU (relative error ~2^-22); the exponent arrives pre-scaled by log2(e)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 

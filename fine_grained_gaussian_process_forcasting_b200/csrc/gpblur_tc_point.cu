@@ -55,102 +55,129 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-// Two-stage operand ring shared by the producer warps (0..7) and the issuer warp (8).  Both roles run the SAME slab
-// schedule (same loops, same counters); producers never wait for the issuer except through the barriers below:
+// One pipeline slab = one K = 32 step of one GEMM of the tile: the producers write the A planes of ring stage
+// (slab & 1), the TMA engine brings the pre-split B image, the issuer thread fires 3 x 4 MMAs into TMEM.
+// The sequence of slabs is the same for every tile, so it is tabulated ONCE per CTA in shared memory and the issuer
+// (lane 0 of warp 8) runs a tight loop over the table: its per-slab critical path is only barrier waits, 12
+// tcgen05.mma with incrementally updated descriptors, one commit and the next TMA request.
+constexpr int kMaxFwdSlabs = 10 * (4 + 8);   // NP (NP + 1) / 2 block pairs x (d-slabs + 8 whitening slabs), M <= 1024
+constexpr int kMaxBwdSlabs = 4 * 4 + 32 + 24 + 16 + 8;   // sum over p of (d-slabs + NSL - p SPB)
+struct SlabDesc {
+  const float* img;    // B image in global memory (hi plane | lo plane), rows x 32 k each
+  int rows;            // B rows = MMA N (also sets the leading byte offset of the B descriptor)
+  uint32_t tmem_off;   // accumulator column offset inside the CTA's TMEM allocation
+  int first;           // 1: the first MMA overwrites the accumulator (no accumulate)
+};
+
+// Ring barriers:
 //   bars[0..1] mma_done : tcgen05.commit - the MMAs that read stage st have retired (stage reusable)
 //   bars[2..3] b_full   : the TMA bulk copy of stage st's B planes has landed (complete_tx)
 //   bars[4..5] a_ready  : all 256 producers have written (and proxy-fenced) stage st's A planes
+__device__ __forceinline__ void init_ring_barriers(uint64_t* br) {
+  tc::mbar_init(&br[0], 1); tc::mbar_init(&br[1], 1);
+  tc::mbar_init(&br[2], 1); tc::mbar_init(&br[3], 1);
+  tc::mbar_init(&br[4], kThreads); tc::mbar_init(&br[5], kThreads);
+  tc::fence_barrier_init();
+}
+
+template <int NB>
+__device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st, const float* image, int rows) {
+  float* b_hi = base + st * Stage<NB>::FLOATS + 2 * Stage<NB>::A_PLANE;
+  float* b_lo = b_hi + Stage<NB>::B_PLANE;
+  const uint32_t bytes = (uint32_t)rows * 128u;          // 8 k-chunks x rows x 16 B
+  tc::mbar_expect_tx(&bars[2 + st], 2 * bytes);
+  tc::bulk_g2s(b_hi, image, bytes, &bars[2 + st]);
+  tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
+}
+
+// The issuer: ONE thread.  `ntiles_mine` tiles, each `nslabs` table entries.
+template <int NB>
+__device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
+                                         int ntiles_mine) {
+  if (ntiles_mine <= 0 || nslabs <= 0) return;
+  constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
+  constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
+  uint64_t a_hi_desc[2], a_lo_desc[2], b_hi_base[2], b_lo_base[2];
+#pragma unroll
+  for (int st = 0; st < 2; ++st) {
+    const uint32_t a_hi = tc::smem_u32(base + st * Stage<NB>::FLOATS);
+    const uint32_t a_lo = a_hi + Stage<NB>::A_PLANE * 4;
+    const uint32_t b_hi = a_lo + Stage<NB>::A_PLANE * 4;
+    const uint32_t b_lo = b_hi + Stage<NB>::B_PLANE * 4;
+    a_hi_desc[st] = kDescHi | kALbo | (uint64_t)(a_hi >> 4);
+    a_lo_desc[st] = kDescHi | kALbo | (uint64_t)(a_lo >> 4);
+    b_hi_base[st] = kDescHi | (uint64_t)(b_hi >> 4);
+    b_lo_base[st] = kDescHi | (uint64_t)(b_lo >> 4);
+  }
+  uint32_t uses[2] = {0, 0};
+  issue_bulk_b<NB>(base, bars, 0, tab[0].img, tab[0].rows);
+  int slab = 0;
+  for (int t = 0; t < ntiles_mine; ++t) {
+    for (int i = 0; i < nslabs; ++i, ++slab) {
+      const int st = slab & 1;
+      const uint32_t phase = uses[st] & 1;
+      const SlabDesc d = tab[i];
+      const uint32_t idesc = tc::make_idesc_tf32(TNP, d.rows);
+      const uint64_t dbh0 = b_hi_base[st] | ((uint64_t)d.rows << 16);      // LBO = rows * 16 B
+      const uint64_t dbl0 = b_lo_base[st] | ((uint64_t)d.rows << 16);
+      const uint64_t dah0 = a_hi_desc[st], dal0 = a_lo_desc[st];
+      const uint32_t tmem_d = tmem_base + d.tmem_off;
+      const uint64_t bstep = (uint64_t)(2 * d.rows);                       // two k-chunks of rows * 16 B, >> 4
+      tc::mbar_wait(&bars[4 + st], phase);        // A planes written
+      tc::mbar_wait(&bars[2 + st], phase);        // B image landed
+      tc::tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < KT / 8; ++j) {
+        const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
+        const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
+        tc::umma_tf32(tmem_d, dal, dbh, idesc, (d.first && j == 0) ? 0u : 1u);   // small cross terms first
+        tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+      }
+      tc::umma_commit(&bars[st]);
+      uses[st] += 1;
+      // TMA request for the next slab's B image into the other stage, as soon as its last readers have retired
+      const bool more = (i + 1 < nslabs) || (t + 1 < ntiles_mine);
+      if (more) {
+        const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
+        const int nst = st ^ 1;
+        if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
+        issue_bulk_b<NB>(base, bars, nst, nx.img, nx.rows);
+      }
+    }
+  }
+}
+
+// Producer-side view of the ring (warps 0..7; every producer thread keeps the same counters).
 template <int NB>
 struct Pipe {
   float* base;
   uint64_t* bars;
   uint32_t uses[2];
   int slab;
-  bool prefetched;
-  bool issuer;     // role of the calling warp
-  bool elect;      // the one issuing thread (lane 0 of the issuer warp)
-  long long iseg[6];   // issuer cycle accounting (debug)
-  __device__ __forceinline__ void init(float* b, uint64_t* br) {
-    base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; prefetched = false;
-    issuer = (threadIdx.x >> 5) == kIssuerWarp;
-    elect = threadIdx.x == kThreads;
-    for (int i = 0; i < 6; ++i) iseg[i] = 0;
-  }
-  __device__ __forceinline__ void planes(int st, float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) const {
+  __device__ __forceinline__ void init(float* b, uint64_t* br) { base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; }
+  // wait until the MMAs that last read this stage have retired, return its A planes
+  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo) {
+    const int st = slab & 1;
+    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
     a_hi = base + st * Stage<NB>::FLOATS;
     a_lo = a_hi + Stage<NB>::A_PLANE;
-    b_hi = a_lo + Stage<NB>::A_PLANE;
-    b_lo = b_hi + Stage<NB>::B_PLANE;
   }
-  // producers: wait until the MMAs that last read this stage have retired, return its planes
-  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo, float*& b_hi, float*& b_lo) {
+  // publish this stage's A planes to the issuer (no CTA barrier)
+  __device__ __forceinline__ void commit() {
     const int st = slab & 1;
-    if (!issuer && uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
-    planes(st, a_hi, a_lo, b_hi, b_lo);
-  }
-  __device__ __forceinline__ void issue_bulk(int st, const float* image, int rows) {
-    float *a_hi, *a_lo, *b_hi, *b_lo;
-    planes(st, a_hi, a_lo, b_hi, b_lo);
-    const uint32_t bytes = (uint32_t)rows * 128u;          // 8 k-chunks x rows x 16 B
-    tc::mbar_expect_tx(&bars[2 + st], 2 * bytes);
-    tc::bulk_g2s(b_hi, image, bytes, &bars[2 + st]);
-    tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
-  }
-  // issuer: B operand of the CURRENT slab (a no-op when the previous commit() already prefetched it)
-  __device__ __forceinline__ void bulk_b(const float* image, int rows) {
-    if (elect && !prefetched) {
-      const int st = slab & 1;
-      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
-      issue_bulk(st, image, rows);
-    }
-  }
-  // producers: publish this stage's A planes (no CTA barrier).  issuer: wait for A and B, issue the N-column MMAs
-  // into tmem_d, commit, then start the TMA copy of the NEXT slab's B image into the other stage as soon as the
-  // MMAs that still read it have retired.
-  __device__ __forceinline__ void commit(uint32_t tmem_d, int ncols, bool first, int b_rows, const float* next_image,
-                                         int next_rows) {
-    const int st = slab & 1;
-    const uint32_t phase = uses[st] & 1;
-    if (!issuer) {
-      tc::tc_fence_before();
-      tc::fence_async_smem();
-      mbar_arrive(&bars[4 + st]);
-    } else if (elect) {
-      long long t0 = clock64(), t1;
-      tc::mbar_wait(&bars[4 + st], phase);
-      t1 = clock64(); iseg[0] += t1 - t0; t0 = t1;
-      tc::mbar_wait(&bars[2 + st], phase);
-      t1 = clock64(); iseg[1] += t1 - t0; t0 = t1;
-      tc::tc_fence_after();
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      planes(st, a_hi, a_lo, b_hi, b_lo);
-      tc::issue_slab_3xtf32<KT, NB>(tmem_d, a_hi, a_lo, b_hi, b_lo, tc::make_idesc_tf32(TNP, ncols), first, b_rows);
-      tc::umma_commit(&bars[st]);
-      t1 = clock64(); iseg[2] += t1 - t0; t0 = t1;
-      if (next_image) {
-        const int nst = st ^ 1;
-        if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
-        t1 = clock64(); iseg[3] += t1 - t0; t0 = t1;
-        issue_bulk(nst, next_image, next_rows);
-        t1 = clock64(); iseg[4] += t1 - t0; t0 = t1;
-      }
-    }
+    tc::tc_fence_before();
+    tc::fence_async_smem();
+    mbar_arrive(&bars[4 + st]);
     uses[st] += 1;
     slab += 1;
-    prefetched = next_image != nullptr;
   }
-  // producers: block until every MMA issued so far has completed
+  // block until every MMA of the slabs committed so far has completed
   __device__ __forceinline__ void drain() {
-    if (issuer || slab == 0) return;
+    if (slab == 0) return;
     const int st = (slab - 1) & 1;
     tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
     tc::tc_fence_after();
-  }
-  __device__ __forceinline__ static void init_barriers(uint64_t* br) {
-    tc::mbar_init(&br[0], 1); tc::mbar_init(&br[1], 1);
-    tc::mbar_init(&br[2], 1); tc::mbar_init(&br[3], 1);
-    tc::mbar_init(&br[4], kThreads); tc::mbar_init(&br[5], kThreads);
-    tc::fence_barrier_init();
   }
 };
 
@@ -229,28 +256,24 @@ __device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, 
   });
 }
 
-// S[128, BW] = X~ Z~[block q]^T into TMEM columns [0, BW).  xr0 / xr1: the first two d-slabs of this tile's x when
-// `preloaded` (loaded one tile ahead so that the HBM latency hides behind the previous tile's MMAs and epilogue).
-// With `stats`, per-row |x~|^2 and x~ . (ell w) are folded from per-slab partials in fixed order (deterministic).
+// Producer side of S[128, BW] = X~ Z~[block q]^T (TMEM columns [0, BW)): nds slabs of the x tile.  xr0 / xr1: the
+// first two d-slabs of this tile's x when `preloaded` (loaded one tile ahead so that the HBM latency hides behind the
+// previous tile's MMAs and epilogue).  With `stats`, per-row |x~|^2 and x~ . (ell w) are folded from per-slab
+// partials in fixed order (deterministic).
 template <int BW>
-__device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const TcPointArgs& a, const XLoader& xl, int q,
-                                        const float* after_image, int after_rows, bool stats, float* part_n,
-                                        float* part_w, float* xn_s, float* xw_s, bool preloaded,
+__device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, const XLoader& xl, bool stats,
+                                        float* part_n, float* part_w, float* xn_s, float* xw_s, bool preloaded,
                                         const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1) {
   const WsLayout& L = a.L;
-  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const int DP = L.DP, MP = L.MP;
+  const int DP = L.DP;
   const int nds = DP >= KT ? DP / KT : 1;
-  const bool prod = !pipe.issuer;
   for (int ds = 0; ds < nds; ++ds) {
     OpRegs<TNP> ra;
-    if (prod) {
-      if (preloaded && ds == 0) ra = xr0;
-      else if (preloaded && ds == 1) ra = xr1;
-      else load_x_slab(ra, xl, ds, DP);
-    }
-    if (prod && stats) {
+    if (preloaded && ds == 0) ra = xr0;
+    else if (preloaded && ds == 1) ra = xr1;
+    else load_x_slab(ra, xl, ds, DP);
+    if (stats) {
       // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
       const int rr = lane & 7, cq = lane >> 3;
@@ -265,14 +288,11 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const T
         part_w[c * TNP + row] = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
       }
     }
-    float *a_hi, *a_lo, *b_hi, *b_lo;
-    pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-    pipe.bulk_b(ZtU + tc_zt_image(MP, nds, q, ds), BW);   // Z~ image: TMA bulk copy of the pre-split block
-    if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-    const bool last = ds + 1 == nds;
-    pipe.commit(tmem_s, BW, ds == 0, BW, last ? after_image : ZtU + tc_zt_image(MP, nds, q, ds + 1),
-                last ? after_rows : BW);
-    if (prod && stats) {
+    float *a_hi, *a_lo;
+    pipe.acquire(a_hi, a_lo);
+    store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+    pipe.commit();
+    if (stats) {
       // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
       prod_sync();
       if (threadIdx.x < TNP) {
@@ -290,13 +310,93 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, uint32_t tmem_s, const T
   }
 }
 
-// cross-covariance values of one 32-column chunk from the S accumulators: k = os exp(-1/2 max(|x|^2 + |z|^2 - 2 s, 0))
-__device__ __forceinline__ void kernel_values(float (&v)[32], float xn, const float* zn_s, int col0, int M, float os) {
+// ---- slab tables (one entry per pipeline slab of a tile, in issue order) ----
+// forward: for p, for q <= p: nds slabs of S = X~ Z~[q]^T, then SPB whitening slabs of block q into output block p
+template <int BW>
+__device__ __forceinline__ int fwd_table(SlabDesc* tab, const TcPointArgs& a) {
+  const WsLayout& L = a.L;
+  const int MP = L.MP, NP = MP / BW, SPB = BW / KT;
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
+  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
+  const int per = nds + SPB, total = NP * (NP + 1) / 2 * per;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    const int pair = i / per, j = i - pair * per;
+    int p = 0;
+    while ((p + 1) * (p + 2) / 2 <= pair) ++p;
+    const int q = pair - p * (p + 1) / 2;
+    SlabDesc d;
+    if (j < nds) {
+      d.img = ZtU + tc_zt_image(MP, nds, q, j);
+      d.rows = BW; d.tmem_off = 0; d.first = j == 0;
+    } else {
+      const int sl = j - nds, sg = q * SPB + sl;
+      int rows;
+      d.img = LinvU + tc_linv_image(MP, p, sg, &rows);
+      d.rows = rows; d.tmem_off = (uint32_t)(BW + BW - rows); d.first = (q == 0 && sl == 0);
+    }
+    tab[i] = d;
+  }
+  return total;
+}
+// backward: for p: nds slabs of S (block p), then T[:, block p] slabs s = NSL - 1 ... p SPB (decreasing)
+template <int BW>
+__device__ __forceinline__ int bwd_table(SlabDesc* tab, const TcPointArgs& a) {
+  const WsLayout& L = a.L;
+  const int MP = L.MP, NP = MP / BW, SPB = BW / KT, NSL = MP / KT;
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
+  const float* LCTU = ws_cptr<float>(a.ws, L.LCTU);
+  int total = 0;
+  for (int p = 0; p < NP; ++p) total += nds + NSL - p * SPB;
+  for (int i = threadIdx.x; i < total; i += kThreads) {
+    int p = 0, base = 0;
+    while (i >= base + nds + NSL - p * SPB) { base += nds + NSL - p * SPB; ++p; }
+    const int j = i - base;
+    SlabDesc d;
+    if (j < nds) {
+      d.img = ZtU + tc_zt_image(MP, nds, p, j);
+      d.rows = BW; d.tmem_off = 0; d.first = j == 0;
+    } else {
+      const int sg = NSL - 1 - (j - nds);
+      int rows;
+      d.img = LCTU + tc_lct_image(MP, p, sg, &rows);
+      d.rows = rows; d.tmem_off = (uint32_t)BW; d.first = sg == NSL - 1;
+    }
+    tab[i] = d;
+  }
+  return total;
+}
+
+// cross-covariance values of one 32-column chunk from the S accumulators:
+//   k = os exp(-1/2 max(|x|^2 + |z|^2 - 2 s, 0)) = 2^min(s log2e + xnc + znc[m], log2 os)
+// with xnc = -1/2 log2e |x~|^2 and znc[m] = -1/2 log2e |z~_m|^2 + log2 os (-1e30 on padded columns => k = 0):
+// 4 FP32 instructions + one MUFU per element.
+__device__ __forceinline__ void kernel_values(float (&v)[32], float xnc, const float* znc_s, int col0, float l2os) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int m = col0 + i;
-    const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-    v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
+  for (int i = 0; i < 32; ++i)
+    v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + znc_s[col0 + i]), l2os));
+}
+
+// Epilogue store of a [32 rows x 32 columns] chunk owned by one warp (lane = row): every lane parks its 32 values in
+// its shared-memory staging row (pitch 36 floats: conflict-free 16-byte stores), then the warp writes the chunk out
+// transposed - 8 lanes cover one 128-byte row segment, 4 full lines per store instruction - instead of eight
+// 16-byte stores per lane that touch 32 different lines each.  `wstg` = staging of this warp (32 x 36 floats),
+// `dst` = global address of (row 0 of the warp, first column of the chunk), `ld` = row pitch, `nvalid` rows exist.
+constexpr int kStagePitch = 36;
+__device__ __forceinline__ void warp_store_chunk32(float* dst, size_t ld, float* wstg, const float (&v)[32], int lane,
+                                                   int nvalid) {
+  __syncwarp();                                  // the previous chunk has been read out of the staging rows
+  float* mine = wstg + lane * kStagePitch;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  __syncwarp();
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    const float4 t = *reinterpret_cast<const float4*>(wstg + r * kStagePitch + c4);
+    if (r < nvalid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c4) = t;
   }
 }
 
@@ -311,156 +411,145 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
+  __shared__ SlabDesc tab[kMaxFwdSlabs];
+  __shared__ int tab_n;
   __shared__ float zn_s[GPBLUR_MAX_M], m_s[GPBLUR_MAX_M], c_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
   __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];   // per-slab row-statistic partials
 
   const WsLayout& L = a.L;
-  const int M = L.M, MP = L.MP;
+  const int MP = L.MP;
   const int NP = MP / BW, SPB = BW / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
-  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   float* Ag = ws_ptr<float>(a.ws, L.A);
   const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
-  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float l2os = log2f(os);
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) Pipe<1>::init_barriers(bars);
-  if (tid < kThreads)
+  if (tid == 0) init_ring_barriers(bars);
+  if (tid < kThreads) {
     for (int i = tid; i < MP; i += kThreads) {
-      zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+      zn_s[i] = ws_cptr<float>(a.ws, L.znc)[i];     // exponent offsets, see kernel_values()
       m_s[i] = ws_cptr<float>(a.ws, L.mvec)[i];
       c_s[i] = ws_cptr<float>(a.ws, L.cvec)[i];
     }
+    const int n = fwd_table<BW>(tab, a);
+    if (tid == 0) tab_n = n;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
-  Pipe<BW> pipe;
-  pipe.init(stage_base, bars);
-  const bool prod = !pipe.issuer;                   // warps 0..7 produce operands and run the epilogues
+  const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
-  const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
-  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+  if (warp == kIssuerWarp) {
+    // ---------------- issuer warp: one thread drives the TMA requests and the tensor core ----------------
+    if (lane == 0) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
+  } else {
+    // ---------------- producer / epilogue warps ----------------
+    Pipe<BW> pipe;
+    pipe.init(stage_base, bars);
+    const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
+    const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-  long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = clock64();
+    long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
 #define SEG(i) do { if (a.dbg) { const long long tnow = clock64(); seg[i] += tnow - tlast; tlast = tnow; } } while (0)
-  OpRegs<TNP> xr0, xr1;
-  if (prod) {
-    const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
-    load_x_slab(xr0, xl0, 0, L.DP);
-    if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
-  }
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const long long n0 = (long long)tile * TNP;
-    const long long gn = n0 + row;
-    const XLoader xl = make_xloader(a, n0);
-    const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-    float mu = 0.f, vv = 0.f;
-    SEG(7);
-    for (int p = 0; p < NP; ++p) {
-      for (int q = 0; q <= p; ++q) {
-        int rows0;
-        const float* first_linv = LinvU + tc_linv_image(MP, p, q * SPB, &rows0);
-        const bool first_pass = p == 0 && q == 0;
-        phase_a<BW>(pipe, tmem_s, a, xl, q, first_linv, rows0, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0,
-                    xr1);
-        if (prod && first_pass && more_tiles) {     // next tile's x: in flight during the MMAs and epilogues
-          const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-          load_x_slab(xr0, xln, 0, L.DP);
-          if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
-        }
-        SEG(0);                                     // phase A (x split, Z~ bulk, S MMAs issued)
-        pipe.drain();                               // S of block q complete
-        SEG(1);
-        const float xn = prod ? xn_s[row] : 0.f;
-        // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
-        for (int sl = 0; sl < SPB; ++sl) {
-          const int s = q * SPB + sl;               // global k-slab
-          // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
-          float v[16];
-          const int col0 = sl * KT + half * 16;
-          if (prod) {
+    OpRegs<TNP> xr0, xr1;
+    {
+      const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
+      load_x_slab(xr0, xl0, 0, L.DP);
+      if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
+    }
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long long n0 = (long long)tile * TNP;
+      const long long gn = n0 + row;
+      const XLoader xl = make_xloader(a, n0);
+      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      float mu = 0.f, vv = 0.f;
+      SEG(7);
+      for (int p = 0; p < NP; ++p) {
+        for (int q = 0; q <= p; ++q) {
+          const bool first_pass = p == 0 && q == 0;
+          phase_a<BW>(pipe, a, xl, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0, xr1);
+          if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
+            const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+            load_x_slab(xr0, xln, 0, L.DP);
+            if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+          }
+          SEG(0);                                     // phase A (x split, A planes published)
+          pipe.drain();                               // S of block q complete
+          SEG(1);
+          const float xnc = -0.72134752044448170f * xn_s[row];
+          // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
+          for (int sl = 0; sl < SPB; ++sl) {
+            // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
+            float v[16];
+            const int col0 = sl * KT + half * 16;
             tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int m = q * BW + col0 + i;
-              const float d2 = fmaxf(xn + zn_s[m] - 2.0f * v[i], 0.f);
-              v[i] = (m < M) ? os * tc::fast_exp(-0.5f * d2) : 0.f;
-            }
-          }
-          SEG(2);                                   // TMEM load + exp
-          int rows;
-          const float* img = LinvU + tc_linv_image(MP, p, s, &rows);
-          float *a_hi, *a_lo, *b_hi, *b_lo;
-          pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-          SEG(3);                                   // stage acquire (MMA s-2 retired)
-          pipe.bulk_b(img, rows);
-          if (prod) {
+            for (int i = 0; i < 16; ++i)
+              v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + zn_s[q * BW + col0 + i]), l2os));
+            SEG(2);                                   // TMEM load + exp
+            float *a_hi, *a_lo;
+            pipe.acquire(a_hi, a_lo);
+            SEG(3);                                   // stage acquire (MMA s-2 retired)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)             // k-chunks half * 4 + c of the slab
+            for (int c = 0; c < 4; ++c)               // k-chunks half * 4 + c of the slab
               tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
                               make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+            SEG(4);                                   // split + store of the k slab
+            pipe.commit();
+            SEG(5);                                   // fences + arrive
           }
-          // what to prefetch next: the next Linv slab of this block, else the Z~ image of the next (p, q) / tile
-          const float* nxt = nullptr;
-          int nxt_rows = BW;
-          if (sl + 1 < SPB) nxt = LinvU + tc_linv_image(MP, p, s + 1, &nxt_rows);
-          else if (q < p) nxt = ZtU + tc_zt_image(MP, nds, q + 1, 0);
-          else if (p + 1 < NP || more_tiles) nxt = ZtU + tc_zt_image(MP, nds, 0, 0);
-          SEG(4);                                   // split + store of the k slab
-          pipe.commit(tmem_a + (uint32_t)(BW - rows), rows, q == 0 && sl == 0, rows, nxt, nxt_rows);
-          SEG(5);                                   // fence + barrier (+ thread 0: wait B, issue MMAs, prefetch)
         }
-      }
-      pipe.drain();
-      SEG(1);
-      // ---- epilogue of output block p: mean / variance partials of the own point; save A ----
-      if (prod) {
+        pipe.drain();
+        SEG(1);
+        // ---- epilogue of output block p: mean / variance partials of the own point; save A ----
 #pragma unroll 1
-      for (int ch = 0; ch < BW / 64; ++ch) {
-        const int col = half * (BW / 2) + ch * 32;
-        float v[32];
-        tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
-        const int gcol = p * BW + col;
+        for (int ch = 0; ch < BW / 64; ++ch) {
+          const int col = half * (BW / 2) + ch * 32;
+          float v[32];
+          tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
+          const int gcol = p * BW + col;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mu = fmaf(v[i], m_s[gcol + i], mu);
-          vv = fmaf(c_s[gcol + i] * v[i], v[i], vv);
+          for (int i = 0; i < 32; ++i) {
+            mu = fmaf(v[i], m_s[gcol + i], mu);
+            vv = fmaf(c_s[gcol + i] * v[i], v[i], vv);
+          }
+          // both stages' A planes are idle here (every MMA has retired, only B prefetches may be in flight):
+          // column half h stages its rows in stage h's A region
+          if (L.training) {
+            const long long w0 = n0 + quad * 32;      // first point of this warp
+            const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+            warp_store_chunk32(Ag + (size_t)w0 * MP + gcol, MP,
+                               stage_base + half * Stage<BW>::FLOATS + quad * 32 * kStagePitch, v, lane, nvalid);
+          }
         }
-        if (L.training && gn < N) {
-          float* dst = Ag + (size_t)gn * MP + gcol;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
+        // staging is drained (and the TMEM reads are done) before ANY producer publishes A planes of the next phase
+        tc::tc_fence_before();
+        prod_sync();
+        SEG(6);                                       // block epilogue
       }
-      }   // the next MMAs into these columns are issued only after every producer's next commit(), which fences
-      SEG(6);                                       // block epilogue
+      if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
+      prod_sync();
+      if (half == 0 && gn < N) {
+        const float mean = mu + mu_s[row] + xw_s[row] + cwb;
+        const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
+        a.mean[gn] = mean;
+        a.var[gn] = var;
+        if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
+      }
+      prod_sync();
     }
-    if (prod) {
-    if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
-    prod_sync();
-    if (half == 0 && gn < N) {
-      const float mean = mu + mu_s[row] + xw_s[row] + cwb;
-      const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
-      a.mean[gn] = mean;
-      a.var[gn] = var;
-      if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
-    }
-    prod_sync();
-    }
-  }
-  if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
-    for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
-  if (a.dbg && blockIdx.x == 0 && pipe.elect)
-    for (int i = 0; i < 6; ++i) a.dbg[16 + i] = pipe.iseg[i];
+    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
+      for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
 #undef SEG
+  }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
@@ -475,136 +564,128 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
+  __shared__ SlabDesc tab[kMaxBwdSlabs];
+  __shared__ int tab_n;
   __shared__ float zn_s[GPBLUR_MAX_M], beta_s[GPBLUR_MAX_M];
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
   __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];
 
   const WsLayout& L = a.L;
-  const int M = L.M, MP = L.MP;
+  const int MP = L.MP;
   const int NP = MP / BW, SPB = BW / KT, NSL = MP / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* LCTU = ws_cptr<float>(a.ws, L.LCTU);
-  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
   float* rrow = ws_ptr<float>(a.ws, L.rrow);
-  const float os = hyp[H_OS];
-  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float l2os = log2f(hyp[H_OS]);
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) Pipe<1>::init_barriers(bars);
-  if (tid < kThreads)
+  if (tid == 0) init_ring_barriers(bars);
+  if (tid < kThreads) {
     for (int i = tid; i < MP; i += kThreads) {
-      zn_s[i] = ws_cptr<float>(a.ws, L.zn)[i];
+      zn_s[i] = ws_cptr<float>(a.ws, L.znc)[i];     // exponent offsets, see kernel_values()
       beta_s[i] = ws_cptr<float>(a.ws, L.beta)[i];
     }
+    const int n = bwd_table<BW>(tab, a);
+    if (tid == 0) tab_n = n;
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + BW;
-  Pipe<BW> pipe;
-  pipe.init(stage_base, bars);
-  const bool prod = !pipe.issuer;
+  const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+  if (warp == kIssuerWarp) {
+    if (lane == 0) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
+  } else {
+    Pipe<BW> pipe;
+    pipe.init(stage_base, bars);
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-  OpRegs<TNP> xr0, xr1;
-  if (prod) {
-    const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
-    load_x_slab(xr0, xl0, 0, L.DP);
-    if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
-  }
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const long long n0 = (long long)tile * TNP;
-    const long long gn = n0 + row;
-    const XLoader xl = make_xloader(a, n0);
-    const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-    // ---- fold the upstream gradients of this thread's point ----
-    float gm = 0.f, gv = 0.f;
-    if (prod && gn < N) {
-      if (a.g_mean) gm = a.g_mean[gn];
-      if (a.g_var) gv = a.g_var[gn];
-      const float v = a.var_in[gn];
-      if (a.g_sample) {
-        const float gs = a.g_sample[gn];
-        const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
-        gm += gs;
-        gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
-      }
-      if (v <= kMinVariance) gv = 0.f;
-      if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
+    OpRegs<TNP> xr0, xr1;
+    {
+      const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
+      load_x_slab(xr0, xl0, 0, L.DP);
+      if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
     }
-    auto load_a = [&](OpRegs<TNP>& regs, int sl) {
-      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-        long long g2 = n0 + r;
-        if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
-        return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
-      });
-    };
-    float rsum = 0.f;
-    for (int p = 0; p < NP; ++p) {
-      int rows_top;
-      const float* top_img = LCTU + tc_lct_image(MP, p, NSL - 1, &rows_top);
-      phase_a<BW>(pipe, tmem_s, a, xl, p, top_img, rows_top, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
-      if (prod && p == 0 && more_tiles) {
-        const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-        load_x_slab(xr0, xln, 0, L.DP);
-        if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
-      }
-      // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
-      OpRegs<TNP> ra;
-      if (prod) load_a(ra, NSL - 1);
-      for (int s = NSL - 1; s >= p * SPB; --s) {
-        int rows;
-        const float* img = LCTU + tc_lct_image(MP, p, s, &rows);
-        float *a_hi, *a_lo, *b_hi, *b_lo;
-        pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-        pipe.bulk_b(img, rows);
-        if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-        const float* nxt = nullptr;
-        int nxt_rows = BW;
-        if (s > p * SPB) {
-          if (prod) load_a(ra, s - 1);                // next slab's saved-A tile flies during the MMAs
-          nxt = LCTU + tc_lct_image(MP, p, s - 1, &nxt_rows);
-        } else if (p + 1 < NP) {
-          nxt = ZtU + tc_zt_image(MP, nds, p + 1, 0);
-        } else if (more_tiles) {
-          nxt = ZtU + tc_zt_image(MP, nds, 0, 0);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long long n0 = (long long)tile * TNP;
+      const long long gn = n0 + row;
+      const XLoader xl = make_xloader(a, n0);
+      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      // ---- fold the upstream gradients of this thread's point ----
+      float gm = 0.f, gv = 0.f;
+      if (gn < N) {
+        if (a.g_mean) gm = a.g_mean[gn];
+        if (a.g_var) gv = a.g_var[gn];
+        const float v = a.var_in[gn];
+        if (a.g_sample) {
+          const float gs = a.g_sample[gn];
+          const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
+          gm += gs;
+          gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
         }
-        pipe.commit(tmem_t, rows, s == NSL - 1, rows, nxt, nxt_rows);
+        if (v <= kMinVariance) gv = 0.f;
+        if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
       }
-      pipe.drain();
-      if (prod) {
-      const float xn = xn_s[row];
+      auto load_a = [&](OpRegs<TNP>& regs, int sl) {
+        load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
+          long long g2 = n0 + r;
+          if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
+          return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
+        });
+      };
+      float rsum = 0.f;
+      for (int p = 0; p < NP; ++p) {
+        phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
+        if (p == 0 && more_tiles) {
+          const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
+          load_x_slab(xr0, xln, 0, L.DP);
+          if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+        }
+        // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
+        OpRegs<TNP> ra;
+        load_a(ra, NSL - 1);
+        for (int s = NSL - 1; s >= p * SPB; --s) {
+          float *a_hi, *a_lo;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+          if (s > p * SPB) load_a(ra, s - 1);           // next slab's saved-A tile flies during the MMAs
+          pipe.commit();
+        }
+        pipe.drain();
+        const float xnc = -0.72134752044448170f * xn_s[row];
 #pragma unroll 1
-      for (int ch = 0; ch < BW / 64; ++ch) {
-        const int col = half * (BW / 2) + ch * 32;
-        const int gcol = p * BW + col;
-        float k[32], t[32];
-        tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
-        tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
-        kernel_values(k, xn, zn_s, gcol, M, os);
+        for (int ch = 0; ch < BW / 64; ++ch) {
+          const int col = half * (BW / 2) + ch * 32;
+          const int gcol = p * BW + col;
+          float k[32], t[32];
+          tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
+          tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
+          kernel_values(k, xnc, zn_s, gcol, l2os);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[gcol + i]);
-          t[i] = kb * k[i];
-          rsum += t[i];
+          for (int i = 0; i < 32; ++i) {
+            const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[gcol + i]);
+            t[i] = kb * k[i];
+            rsum += t[i];
+          }
+          {
+            const long long w0 = n0 + quad * 32;
+            const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+            warp_store_chunk32(Wg + (size_t)w0 * MP + gcol, MP,
+                               stage_base + half * Stage<BW>::FLOATS + quad * 32 * kStagePitch, t, lane, nvalid);
+          }
         }
-        if (gn < N) {
-          float* dst = Wg + (size_t)gn * MP + gcol;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
-        }
+        // staging is drained (and the TMEM reads are done) before ANY producer publishes A planes of the next phase
+        tc::tc_fence_before();
+        prod_sync();
       }
-      }
-    }
-    if (prod) {
       if (half == 1) r_s[row] = rsum;
       prod_sync();
       if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
@@ -625,6 +706,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
+  __shared__ SlabDesc tab[GPBLUR_MAX_M / KT];
   __shared__ float red[8][32][33];
   __shared__ float part_q[8][32], part_t[8][32], part_sc[8][4];
   __shared__ float q_s[DPT], t1_s[DPT], sc_s[4];
@@ -645,17 +727,27 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
 
   constexpr uint32_t TMEM_COLS = DPT;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) Pipe<1>::init_barriers(bars);
-  if (tid < kThreads)
+  if (tid == 0) init_ring_barriers(bars);
+  if (tid < kThreads) {
     for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
+    for (int i = tid; i < MP / KT; i += kThreads) {
+      SlabDesc d;
+      d.img = ZtTU + tc_slab_ztt(DPT, i);
+      d.rows = DPT; d.tmem_off = 0; d.first = i == 0;
+      tab[i] = d;
+    }
+  }
   if (tid < 4) sc_s[tid] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (warp == kIssuerWarp) {
+    if (lane == 0) issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine);
+  } else {
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
-  const bool prod = !pipe.issuer;
 
   // epilogue mapping: the 8 warps cover 4 lane quadrants x 2 column halves of the [128, DPT] tile; with DPT = 32
   // only the first 4 warps have columns.
@@ -676,20 +768,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
       });
     };
     OpRegs<TNP> ra;
-    if (prod) load_w(ra, 0);
+    load_w(ra, 0);
     for (int s = 0; s < MP / KT; ++s) {
-      float *a_hi, *a_lo, *b_hi, *b_lo;
-      pipe.acquire(a_hi, a_lo, b_hi, b_lo);
-      pipe.bulk_b(ZtTU + tc_slab_ztt(DPT, s), DPT);
-      if (prod) store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      if (prod && s + 1 < MP / KT) load_w(ra, s + 1);
-      const bool last = s + 1 == MP / KT;
-      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      const float* nxt = last ? (more_tiles ? ZtTU : nullptr) : ZtTU + tc_slab_ztt(DPT, s + 1);
-      pipe.commit(tmem_d, DPT, s == 0, DPT, nxt, DPT);
+      float *a_hi, *a_lo;
+      pipe.acquire(a_hi, a_lo);
+      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+      if (s + 1 < MP / KT) load_w(ra, s + 1);
+      pipe.commit();
     }
     pipe.drain();
-    if (!prod) continue;                            // the issuer warp only runs the slab schedule
 
     const long long gn = n0 + row;
     const bool live = gn < N;
@@ -796,8 +883,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
       for (int w = 0; w < 4; ++w) s += part_sc[w][tid];
       sc_s[tid] += s;
     }
+    tc::tc_fence_before();   // the TMEM reads of this tile are done before the next tile's MMAs are released
     prod_sync();
   }
+  }   // producer warps
   __syncthreads();
   float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
   if (tid < kThreads) {

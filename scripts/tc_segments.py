@@ -23,8 +23,3 @@ for who, off in (("thread 0 (issuer)", 0), ("thread 32", 8)):
     for i, nm in enumerate(names):
         print(f"   {nm:22s} {t[off + i]:10d}  {100 * t[off + i] / max(tot, 1):5.1f}%  per tile {t[off + i] // per_cta}")
 
-inames = ["wait A ready", "wait B landed", "issue 12 MMAs + commit", "wait other stage retired", "issue TMA bulk"]
-tot = sum(t[16:21])
-print("issuer thread: total accounted", tot, "per tile", tot // per_cta)
-for i, nm in enumerate(inames):
-    print(f"   {nm:26s} {t[16 + i]:10d}  per tile {t[16 + i] // per_cta}")
