@@ -319,18 +319,16 @@ def run_ours(args, wl, name):
     elbo_h = torch.empty(1, B).pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES // 4, device=device)
     from fine_grained_gaussian_process_forcasting_b200.gpcompat import DeepGPLayer
+    from fine_grained_gaussian_process_forcasting_b200.graphs import GraphedStep
     layers = [m for m in model.modules() if isinstance(m, DeepGPLayer)]
 
-    def step(i, xin, yin):
+    def step_body(xin, yin):
+        """forward (mean, variance, fused sample, ELBO) + backward (dX, every GP parameter gradient)"""
         bucket.zero()
-        for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
-            ly.invalidate_param_stage()
         outs, grads = [], []
         elbo = None
         for c, L in enumerate(calls):
             x = xin[c].detach().requires_grad_(True)      # fresh leaf: dX flows back to the forecaster
-            for ly in layers:                                 # global window index -> Philox counter
-                ly._rng_offset = (i * world + rank) * B * L * max(1, ly.output_dims or 1)
             last = c == len(calls) - 1
             out = model.blur(x, yin if last else None, num_data=D)
             outs += [out.mean, out.sample]
@@ -340,6 +338,13 @@ def run_ours(args, wl, name):
                 outs.append(elbo)
                 grads.append(g_elbo)
         torch.autograd.backward(outs, grads)
+        return elbo
+
+    def eager_step(i, xin, yin):
+        for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
+            ly.invalidate_param_stage()
+            ly._rng_offset = (i * world + rank) * B * sum(calls) * max(1, ly.output_dims or 1)   # global window index
+        elbo = step_body(xin, yin)
         if world > 1:
             bucket.all_reduce(average=True)
         return elbo
@@ -350,27 +355,68 @@ def run_ours(args, wl, name):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up ----
-    for i in range(max(3, args.warmup)):
-        step(i, xs[i % nbuf], ys[i % nbuf])
+    # ---- warm-up (eager) ----
+    launches0 = _cabi.launch_count()
+    eager_step(0, xs[0], ys[0])
+    launches_per_step = _cabi.launch_count() - launches0
+    for i in range(1, max(3, args.warmup)):
+        eager_step(i, xs[i % nbuf], ys[i % nbuf])
+    sync_all()
+
+    # ---- the step as ONE CUDA graph (graphs.GraphedStep): static inputs, device-resident Philox offsets ----
+    graphed = None
+    graph_note = "eager launches (--eager)"
+    if not args.eager:
+        try:
+            graphed = GraphedStep(model, lambda *ins: (step_body(ins[:-1], ins[-1]),), list(xs[0]) + [ys[0]],
+                                  warmup=2, world=world, rank=rank)
+            graph_note = "whole step (fwd + bwd) replayed as one CUDA graph; NCCL all-reduce outside the graph"
+        except Exception as e:    # pragma: no cover - report and fall back to eager launches
+            graph_note = f"CUDA graph capture failed ({type(e).__name__}: {e}); eager launches"
+            graphed = None
+            for ly in layers:
+                ly.rng_offset_dev = None
+    sync_all()
+
+    def run_step(i, xin, yin):
+        """one step on inputs already in HBM; returns the per-window ELBO"""
+        if graphed is None:
+            return eager_step(i, xin, yin)
+        for dst, src in zip(graphed.inputs, list(xin) + [yin]):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        (elbo,) = graphed.replay()
+        if world > 1:
+            bucket.all_reduce(average=True)
+        return elbo
+
+    for i in range(3):
+        run_step(i, xs[i % nbuf], ys[i % nbuf])
     sync_all()
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _cabi.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
+        if graphed is not None:                         # stage this step's inputs in the graph's static buffers
+            for dst, src in zip(graphed.inputs, list(xs[i % nbuf]) + [ys[i % nbuf]]):
+                dst.copy_(src, non_blocking=True)
         flush.zero_()                                   # L2 flush between timed iterations (outside the events)
         evs[i][0].record()
-        step(i, xs[i % nbuf], ys[i % nbuf])
+        if graphed is not None:
+            graphed.replay()
+            if world > 1:
+                bucket.all_reduce(average=True)
+        else:
+            eager_step(i, xs[i % nbuf], ys[i % nbuf])
         evs[i][1].record()
     sync_all()
     t_wall = time.perf_counter() - t_wall0
-    launches = _cabi.launch_count() - launches0
+    launches = launches_per_step * args.steps
     ms_dev = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_dev], device=device, dtype=torch.float64)
@@ -381,11 +427,15 @@ def run_ours(args, wl, name):
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- timed region 2: end to end through the module API with host buffers ----
-    xdev = [torch.empty_like(x) for x in xs[0]]
-    ydev = torch.empty_like(ys[0])
+    if graphed is not None:
+        xdev, ydev = graphed.inputs[:-1], graphed.inputs[-1]
+    else:
+        xdev = [torch.empty_like(x) for x in xs[0]]
+        ydev = torch.empty_like(ys[0])
+    cur = torch.cuda.current_stream(device)
     for c in range(len(calls)):                          # untimed warm-up of the pinned-copy path
         xdev[c].copy_(xh[0][c], non_blocking=True)
-    step(0, xdev, ydev)
+    run_step(0, xdev, ydev)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -393,9 +443,9 @@ def run_ours(args, wl, name):
         for c in range(len(calls)):
             xdev[c].copy_(xh[0][c], non_blocking=True)
         ydev.copy_(yh, non_blocking=True)
-        elbo = step(i, xdev, ydev)
+        elbo = run_step(i, xdev, ydev)
         elbo_h.copy_(elbo.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller reads the step's result on the host
+        cur.synchronize()                               # the caller reads the step's result on the host
     e1.record()
     sync_all()
     t2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -405,6 +455,19 @@ def run_ours(args, wl, name):
     h2d = sum(x.numel() for x in xh[0]) * 4 + yh.numel() * 4
     d2h = elbo_h.numel() * 4
 
+    # ---- eager timing for comparison (host-issue bound on the small shapes) ----
+    ev_e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for ly in layers:
+        ly.rng_offset_dev = None
+    sync_all()
+    n_e = max(3, min(args.steps, 10))
+    ev_e[0].record()
+    for i in range(n_e):
+        eager_step(i, xs[i % nbuf], ys[i % nbuf])
+    ev_e[1].record()
+    sync_all()
+    eager_ms = ev_e[0].elapsed_time(ev_e[1]) / n_e
+
     # ---- per-stage device times (library profile hooks: CUDA events on the launching stream) ----
     stage_ms = {}
     if rank == 0 or True:
@@ -412,7 +475,7 @@ def run_ours(args, wl, name):
         nprof = max(3, min(args.steps, 10))
         for i in range(nprof):
             flush.zero_()
-            step(i, xs[i % nbuf], ys[i % nbuf])
+            eager_step(i, xs[i % nbuf], ys[i % nbuf])
         torch.cuda.synchronize()
         prof = _cabi.profile_collect()
         _cabi.profile_enable(False)
@@ -467,6 +530,7 @@ def run_ours(args, wl, name):
             "config": {"workload": name, "desc": wl["desc"], "B_per_gpu": B, "L": calls, "D": D, "M": M,
                        "parallelism": f"dp{world}", "l2": f"flush ({L2_FLUSH_BYTES >> 20} MiB write) between timed steps "
                        "+ 3 rotating input sets", "timing": "per-step CUDA events, max over ranks",
+                       "launch": graph_note,
                        "regime": "R-exercise (SURVEY 8d)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -475,6 +539,7 @@ def run_ours(args, wl, name):
             "cpu_baseline": cb,
             "stage_ms_per_step": {k: round(v[0], 5) for k, v in stage_ms.items()},
             "wall_ms_per_step": t_wall * 1e3 / args.steps,
+            "eager_ms_per_step": eager_ms,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -490,6 +555,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GPBLUR_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "
+                    "step as a CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

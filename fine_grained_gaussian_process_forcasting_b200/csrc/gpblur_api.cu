@@ -36,6 +36,13 @@ ProfScope::~ProfScope() {
   g_prof_recs.push_back(r);
 }
 
+static thread_local const unsigned long long* g_offset_dev = nullptr;
+const unsigned long long* current_offset_dev() { return g_offset_dev; }
+struct OffsetDevScope {
+  explicit OffsetDevScope(const unsigned long long* p) { g_offset_dev = p; }
+  ~OffsetDevScope() { g_offset_dev = nullptr; }
+};
+
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
@@ -283,7 +290,9 @@ int gpblur_svgp_param_stage(const gpblur_svgp_params* p, int D, int M, float* kl
 
 int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long N, int D, int M, float* mean,
                               float* var, float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
-                              int training, void* ws, size_t ws_bytes, void* stream) {
+                              const unsigned long long* offset_dev, int training, void* ws, size_t ws_bytes,
+                              void* stream) {
+  OffsetDevScope ods(offset_dev);
   if (!param_stage || N < 0 || D < 1 || M < 1) return GPBLUR_EINVAL;
   if (D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return GPBLUR_EUNSUPPORTED;
   if (N > 0 && (!x || !mean || !var)) return GPBLUR_EINVAL;
@@ -312,14 +321,15 @@ int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long
   const WsLayout L0 = make_layout(0, D, M, 0);
   if (kl) cudaMemcpyAsync(kl, ws_cptr<float>(param_stage, L0.hyp) + H_KL, sizeof(float), cudaMemcpyDeviceToDevice, st);
   if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
-  return gpblur_svgp_point_forward(param_stage, x, N, D, M, mean, var, sample, seed, offset, stream_id, training, ws,
-                                   ws_bytes, stream);
+  return gpblur_svgp_point_forward(param_stage, x, N, D, M, mean, var, sample, seed, offset, stream_id, nullptr,
+                                   training, ws, ws_bytes, stream);
 }
 
 int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const float* g_mean, const float* g_var,
                                const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
-                               uint32_t stream_id, float* dx, double* stage_grad, void* ws, size_t ws_bytes,
-                               void* stream) {
+                               uint32_t stream_id, const unsigned long long* offset_dev, float* dx,
+                               double* stage_grad, void* ws, size_t ws_bytes, void* stream) {
+  OffsetDevScope ods(offset_dev);
   if (N < 0 || D < 1 || M < 1) return GPBLUR_EINVAL;
   if (D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return GPBLUR_EUNSUPPORTED;
   if (!stage_grad || !ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
@@ -361,8 +371,8 @@ int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long 
   const WsLayout L = make_layout(N, D, M, 1);
   if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
   double* sgrad = ws_ptr<double>(ws, L.sgrad);
-  rc = gpblur_svgp_point_backward(x, N, D, M, g_mean, g_var, g_sample, var, seed, offset, stream_id, dx, sgrad, ws,
-                                  ws_bytes, stream);
+  rc = gpblur_svgp_point_backward(x, N, D, M, g_mean, g_var, g_sample, var, seed, offset, stream_id, nullptr, dx,
+                                  sgrad, ws, ws_bytes, stream);
   if (rc) return rc;
   return launch_mm_backward(*p, L, ws, sgrad, g_kl, grad_bucket, (cudaStream_t)stream);
 }

@@ -272,6 +272,12 @@ struct ProfScope {
   ~ProfScope();
 };
 void note_launch(int n = 1);
+// Device-resident Philox offset addend of the entry point running on this host thread (null = none).  Set by the
+// extern "C" layer around the launchers; read when the kernel arguments are filled.
+const unsigned long long* current_offset_dev();
+__device__ __forceinline__ uint64_t rng_offset(uint64_t offset, const unsigned long long* offset_dev) {
+  return offset + (offset_dev ? (uint64_t)*offset_dev : 0ull);
+}
 int check_launch(const char* what);
 int num_sms();
 int tile_override(const char* env);   // 0 = heuristic, else forced tile height (tuning knob)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, Cfg::TN <= 64 ? 2 : 1) point_bwd_ker
         const float v = a.var[gn];
         if (a.g_sample) {
           const float gs = a.g_sample[gn];
-          const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
+          const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
           gm += gs;
           gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
         }

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, Cfg::PT <= 4 ? 2 : 1) point_fwd_kern
         a.mean[gn] = mean;
         a.var[gn] = var;
         if (a.sample) {
-          const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
+          const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
           a.sample[gn] = fmaf(sqrtf(var), eps, mean);
         }
       }
@@ -211,7 +211,7 @@ int dispatch_fwd_tn(const PointFwdArgs& a, cudaStream_t st) {
 int launch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
                          uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
   if (L.N <= 0) return GPBLUR_OK;
-  PointFwdArgs a{L, ws, x, mean, var, sample, seed, offset, stream_id, 0};
+  PointFwdArgs a{L, ws, x, mean, var, sample, seed, offset, stream_id, 0, current_offset_dev()};
   if (L.MP == 32) return dispatch_fwd_tn<4, 32>(a, st);
   if (L.MP == 64) return dispatch_fwd_tn<4, 64>(a, st);
   return dispatch_fwd_tn<8, 128>(a, st);

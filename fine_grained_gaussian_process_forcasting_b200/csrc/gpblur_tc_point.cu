@@ -34,6 +34,7 @@ struct TcPointArgs {
   const float* var_in;
   float* dx;
   uint64_t seed, offset;
+  const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
   uint32_t stream_id;
   int ntiles;
   long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
         const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
         a.mean[gn] = mean;
         a.var[gn] = var;
-        if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id), mean);
+        if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id), mean);
       }
       prod_sync();
     }
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         const float v = a.var_in[gn];
         if (a.g_sample) {
           const float gs = a.g_sample[gn];
-          const float eps = philox_normal(a.seed, a.offset + (uint64_t)gn, a.stream_id);
+          const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
           gm += gs;
           gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
         }
@@ -929,7 +930,7 @@ int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* 
                             uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
   TcPointArgs a{};
   a.L = L; a.ws = ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
-  a.seed = seed; a.offset = offset; a.stream_id = stream_id;
+  a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
   const int grid = tc_grid(L);
@@ -952,7 +953,7 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
                              uint32_t stream_id, float* dx, cudaStream_t st) {
   TcPointArgs a{};
   a.L = L; a.ws = ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
-  a.seed = seed; a.offset = offset; a.stream_id = stream_id;
+  a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   const int grid = tc_grid(L);
   {

@@ -91,6 +91,7 @@ struct PointFwdArgs {
   uint64_t seed, offset;
   uint32_t stream_id;
   int ntiles;
+  const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
 };
 
 struct PointBwdArgs {
@@ -105,6 +106,7 @@ struct PointBwdArgs {
   uint32_t stream_id;
   float* dx;
   int ntiles;
+  const unsigned long long* offset_dev;
 };
 
 // Stage a [TN][DP] tile of X into shared memory, centred and scaled: Xs[n][d] = (x - c) / ell (0 beyond N, D).

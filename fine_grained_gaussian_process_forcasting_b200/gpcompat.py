@@ -462,6 +462,7 @@ class DeepGPLayer(ApproximateGP):
         self._rng_stream = 0
         self.fused_sample = True
         self.last_info = None
+        self.rng_offset_dev = None         # optional int64 device scalar added to the Philox offset (graphs.py)
         self.share_param_stage = True      # reuse Kzz / Cholesky / Linv between calls with unchanged parameters
         self._stage_caches = {}
 
@@ -473,6 +474,9 @@ class DeepGPLayer(ApproximateGP):
         """Drop the cached M x M stage (parameters are also tracked by tensor version, so an optimizer step
         invalidates it automatically; benchmarks that never step call this to stay honest)."""
         self._stage_caches = {}
+        vs = self.variational_strategy
+        vs._last_kl = None          # it references the autograd graph of the dropped stage
+        vs._last_kl_versions = None
 
     def _next_counters(self, n: int):
         seed, off, stream = self._rng_seed, self._rng_offset, self._rng_stream
@@ -525,7 +529,8 @@ class DeepGPLayer(ApproximateGP):
         seed, off, stream = self._next_counters(n_pts * (H or 1)) if self.fused_sample else (0, 0, 0)
         mean, var, sample, kl, info = ops.svgp_predict(inputs, *self._layer_params(), seed, off, stream,
                                                        want_sample=self.fused_sample,
-                                                       stage_cache=self._stage_cache())
+                                                       stage_cache=self._stage_cache(),
+                                                       offset_dev=self.rng_offset_dev)
         self.last_info = info
         if check_cholesky.value():
             k = int(info.max().item())

@@ -1,0 +1,75 @@
+"""CUDA-graph capture of a whole GP-blur training step (forward + hand-written backward).
+
+The small configurations of the path are launch-bound: one step of the reference's default shape is ~17 kernel
+launches of 10-200 us each, and the host (Python autograd + ctypes) needs ~0.8 ms to issue them.  ``GraphedStep``
+records the launches once and replays them with ONE ``cudaGraphLaunch`` per step:
+
+* inputs live in static device buffers (``copy_`` new data into ``.inputs`` before ``replay()``);
+* parameter gradients accumulate into the parameters' existing ``.grad`` tensors (use ``FlatGradBucket`` so that
+  they are one flat buffer), outputs are static tensors returned by ``replay()``;
+* the fused sampler stays fresh across replays: every GP layer gets a device-resident Philox offset word
+  (``rng_offset_dev``) that the captured kernels add to their counters, and the graph itself bumps that word at
+  the end of each replay by the number of counters the step consumed.
+
+Nothing here is specific to benchmarking: any callable built from this package's modules can be captured.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from .gpcompat import DeepGPLayer
+
+
+class GraphedStep:
+    def __init__(self, module: torch.nn.Module, step_fn: Callable[..., Sequence[torch.Tensor]],
+                 example_inputs: Sequence[torch.Tensor], warmup: int = 3, world: int = 1, rank: int = 0):
+        """``step_fn(*inputs)`` runs forward AND backward through ``module`` and returns the tensors the caller
+        wants to read (e.g. the per-window ELBO); ``example_inputs`` fix the shapes.  The function must not
+        synchronise with the host (no ``.item()``).  ``world`` / ``rank``: with batch-sharded data parallelism the
+        Philox offset word starts at rank * (counters per step) and advances by world * (counters per step), so
+        that the ranks draw disjoint counters."""
+        dev = example_inputs[0].device
+        self.module = module
+        self.layers = [m for m in module.modules() if isinstance(m, DeepGPLayer)]
+        self.inputs = [t.clone() for t in example_inputs]
+        for ly in self.layers:                       # device-resident Philox offsets (see module docstring)
+            ly.rng_offset_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+            ly._rng_offset = 0
+        self._consumed = {}
+        self._offsets = [ly.rng_offset_dev for ly in self.layers]   # the captured kernels read these words
+
+        def run():
+            for ly in self.layers:
+                ly.invalidate_param_stage()          # parameters change between replays: never reuse a stage
+                ly._rng_offset = 0
+            outs = step_fn(*self.inputs)
+            for ly in self.layers:                   # counters consumed by this step (host-side bookkeeping)
+                ly.rng_offset_dev.add_(world * ly._rng_offset)
+                self._consumed[id(ly)] = ly._rng_offset
+            return outs
+
+        for ly in self.layers:                       # drop autograd graphs of earlier eager steps: their AccumulateGrad
+            ly.invalidate_param_stage()              # nodes are bound to the eager stream and would break the capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = run()
+        for ly in self.layers:
+            ly.invalidate_param_stage()              # tensors of the capture pool must not leak into eager calls
+            ly.rng_offset_dev.fill_(rank * self._consumed.get(id(ly), 0))
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def set_rng_offset(self, value: int):
+        for ly in self.layers:
+            ly.rng_offset_dev.fill_(int(value))

@@ -246,7 +246,7 @@ def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None):
 
 
 def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, stream_id: int, want_sample: bool,
-                      training: bool, out: Optional[Tensor] = None):
+                      training: bool, out: Optional[Tensor] = None, offset_dev: Optional[Tensor] = None):
     """x [N, D] + parameter stage -> (mean [N], var [N], sample [N] | None, workspace uint8).
     `out`: preallocated float32 [(3 | 2) * N] receiving mean | var | sample."""
     _need_cuda(x, stage)
@@ -260,14 +260,15 @@ def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, 
     with torch.cuda.device(dev):
         rc = _cabi.lib().gpblur_svgp_point_forward(
             _ptr(stage), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
-            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, int(training),
-            _ptr(ws), ws.numel(), _stream())
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, _ptr(offset_dev),
+            int(training), _ptr(ws), ws.numel(), _stream())
     _cabi.check(rc, "gpblur_svgp_point_forward")
     return mean, var, sample, ws
 
 
 def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, offset, stream_id, ws,
-                       need_dx: bool = True, dx: Optional[Tensor] = None, sgrad: Optional[Tensor] = None):
+                       need_dx: bool = True, dx: Optional[Tensor] = None, sgrad: Optional[Tensor] = None,
+                       offset_dev: Optional[Tensor] = None):
     """-> (dx [N, D] | None, stage_grad float64 [stage_grad_doubles(D, M)])."""
     _need_cuda(x, ws, g_mean, g_var, g_sample, var)
     N, D = x.shape
@@ -279,7 +280,7 @@ def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, of
     with torch.cuda.device(dev):
         rc = _cabi.lib().gpblur_svgp_point_backward(
             _ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(var),
-            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, _ptr(offset_dev),
             _ptr(dx if need_dx else None), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
     _cabi.check(rc, "gpblur_svgp_point_backward")
     return (dx if need_dx else None), sgrad
@@ -450,7 +451,7 @@ class _PointFunction(torch.autograd.Function):
     With an [H, G] token (multi-output layer) every output gains a trailing H: mean [..., H]."""
 
     @staticmethod
-    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample):
+    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample, offset_dev):
         shape = x.shape
         D = shape[-1]
         x2 = _f32c(x).reshape(-1, D)
@@ -464,11 +465,12 @@ class _PointFunction(torch.autograd.Function):
         wss = []
         for h in range(H):
             _, _, _, ws = point_forward_raw(stage[h], x2, M, seed, offset + h * N, stream_id, want_sample, training,
-                                            out=out[h])
+                                            out=out[h], offset_dev=offset_dev)
             wss.append(ws)
         if training:
             ctx.save_for_backward(x2, out, *wss)
         ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout)
+        ctx.offset_dev = offset_dev
         ctx.set_materialize_grads(False)
         out_shape = tuple(shape[:-1]) + ((H,) if batched else ())
 
@@ -499,10 +501,11 @@ class _PointFunction(torch.autograd.Function):
         for h in range(H):
             point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
                                None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * N, stream_id,
-                               wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h])
+                               wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h],
+                               offset_dev=ctx.offset_dev)
         if dx is not None:
             dx = (dx.sum(0) if H > 1 else dx[0]).reshape(shape)
-        return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None)
+        return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None, None)
 
 
 def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
@@ -541,10 +544,12 @@ def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outpu
 def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
-                 want_sample: bool = False, stage_cache: Optional[dict] = None):
+                 want_sample: bool = False, stage_cache: Optional[dict] = None,
+                 offset_dev: Optional[Tensor] = None):
     """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]); with inducing points [H, M, D]
     (multi-output layer) the outputs are [..., H], kl [H], info [H], and GP h draws its sample with Philox counters
-    offset + h * N + n.  `stage_cache`: see svgp_param_stage."""
+    offset + h * N + n.  `stage_cache`: see svgp_param_stage.  `offset_dev`: optional int64 device scalar added to
+    `offset` when the kernels run (CUDA-graph replays draw fresh counters by bumping it between replays)."""
     token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
                                                variational_stddev, mean_weights, mean_bias, stage_cache)
     if x.numel() == 0:
@@ -552,7 +557,7 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
         e = x.new_empty(shp, dtype=torch.float32)
         return e, e.clone(), (e.clone() if want_sample else None), kl, info
     mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
-                                             int(stream_id), bool(want_sample))
+                                             int(stream_id), bool(want_sample), offset_dev)
     return mean, var, sample, kl, info
 
 

@@ -115,15 +115,18 @@ size_t gpblur_svgp_stage_grad_doubles(int D, int M);
 int gpblur_svgp_param_stage(const gpblur_svgp_params* p, int D, int M, float* kl, int* info,
                             void* stage, size_t stage_bytes, void* stream);
 /* `ws` (gpblur_svgp_workspace_bytes(N, D, M, training)) receives a copy of the stage and, when training, the
- * saved whitened cross-covariance; hand the same `ws` to gpblur_svgp_point_backward. */
+ * saved whitened cross-covariance; hand the same `ws` to gpblur_svgp_point_backward.
+ * `offset_dev` (nullable): device-resident uint64 added to `offset` when the kernel runs, so that a step captured in
+ * a CUDA graph draws fresh Philox counters on every replay (the host bumps the device word between replays). */
 int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long N, int D, int M,
                               float* mean, float* var, float* sample, uint64_t seed, uint64_t offset,
-                              uint32_t stream_id, int training, void* ws, size_t ws_bytes,
-                              void* stream);
+                              uint32_t stream_id, const unsigned long long* offset_dev, int training,
+                              void* ws, size_t ws_bytes, void* stream);
 int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const float* g_mean,
                                const float* g_var, const float* g_sample, const float* var,
-                               uint64_t seed, uint64_t offset, uint32_t stream_id, float* dx,
-                               double* stage_grad, void* ws, size_t ws_bytes, void* stream);
+                               uint64_t seed, uint64_t offset, uint32_t stream_id,
+                               const unsigned long long* offset_dev, float* dx, double* stage_grad,
+                               void* ws, size_t ws_bytes, void* stream);
 /* `stage` is the buffer filled by gpblur_svgp_param_stage; its fp64 scratch regions are overwritten. */
 int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M,
                                      const double* stage_grad, const float* g_kl,

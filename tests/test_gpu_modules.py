@@ -334,3 +334,54 @@ def test_two_calls_on_one_stage_match_the_oracle_gradients(cuda):
             assert rel(pd[k].grad.reshape(-1), p64[k].grad.reshape(-1)) < tol, (D, M, k)
         for xg, xr in zip(xs, xo):
             assert rel(xg.grad, xr.grad) < tol
+
+
+def test_graphed_step_matches_eager_and_draws_fresh_samples(cuda):
+    """CUDA-graph capture of forward + backward (graphs.GraphedStep): replays reproduce the eager step bit for bit
+    (same Philox counters), and consecutive replays draw different samples through the device-resident offset."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    from fine_grained_gaussian_process_forcasting_b200.graphs import GraphedStep
+    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
+    B, L, D, M = 8, 24, 32, 128
+    p = O.init_params_exercise(D, M, 21)
+    x, y, gm, _ = O.make_inputs(B, L, D, 22)
+    with gpcompat.num_likelihood_samples(1):
+        model = DeepGPp(D, 5, num_inducing=M).to(cuda)
+        load_params(model, p)
+        model.train()
+        hl = model.hidden_layer
+        hl.set_rng(99, 0, 0)
+        bucket = FlatGradBucket(gp_parameters(model))
+        gmd = gm.to(cuda).unsqueeze(0)
+        dx_static = torch.zeros(B, L, D, device=cuda)
+
+        def step(xin, yin):
+            bucket.zero()
+            xl = xin.detach().requires_grad_(True)
+            out = model.blur(xl, yin, num_data=D)
+            torch.autograd.backward([out.mean, out.sample, out.elbo],
+                                    [gmd, gmd, torch.full((1, B), -1.0 / B, device=cuda)])
+            dx_static.copy_(xl.grad)
+            return out.mean, out.sample, out.elbo
+
+        g = GraphedStep(model, step, [x.to(cuda), y.to(cuda).unsqueeze(0)])
+        mean1, sample1, elbo1 = [t.clone() for t in g.replay()]
+        grads1, dx1 = bucket.flat.clone(), dx_static.clone()
+        mean2, sample2, elbo2 = [t.clone() for t in g.replay()]
+        torch.cuda.synchronize()
+        assert torch.equal(mean1, mean2) and torch.equal(elbo1, elbo2)
+        assert not torch.equal(sample1, sample2)                      # fresh counters on every replay
+        # eager reference with the counters of replay 1 (offset 0) and replay 2 (offset N)
+        hl.rng_offset_dev = None
+        for k, (mean_g, sample_g) in enumerate(((mean1, sample1), (mean2, sample2))):
+            hl.invalidate_param_stage()
+            hl._rng_offset = k * B * L
+            m_e, s_e, e_e = step(x.to(cuda), y.to(cuda).unsqueeze(0))
+            assert torch.equal(m_e, mean_g) and torch.equal(s_e, sample_g)
+        # gradients of replay 1 against an eager step with offset 0
+        hl.invalidate_param_stage()
+        hl._rng_offset = 0
+        step(x.to(cuda), y.to(cuda).unsqueeze(0))
+        torch.cuda.synchronize()
+        assert torch.equal(bucket.flat, grads1) and torch.equal(dx_static, dx1)
