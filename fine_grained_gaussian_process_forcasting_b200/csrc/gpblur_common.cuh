@@ -160,7 +160,12 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     // (MP / 128) row tiles x splitsZ CTAs: about one wave of 148 SMs each, >= 128 rows per split
     const int qt = w.MP >= 256 ? w.MP / 256 : 1;
     const long long maxs = (N + 127) / 128;
-    long long sS = 148 / ((w.MP / 128) * qt), sZ = 148 / (w.MP / 128);
+    // the Gram kernel skips the [128 x 256] tiles strictly above the diagonal: only the rest needs SMs
+    int gram_tiles = 0;
+    for (int pt = 0; pt < w.MP / 128; ++pt)
+      for (int q = 0; q < qt; ++q)
+        if (q * 256 <= pt * 128 + 127) ++gram_tiles;
+    long long sS = 148 / gram_tiles, sZ = 148 / (w.MP / 128);
     if (sS > maxs) sS = maxs;
     if (sZ > maxs) sZ = maxs;
     w.splitsS = (int)(sS < 1 ? 1 : sS);

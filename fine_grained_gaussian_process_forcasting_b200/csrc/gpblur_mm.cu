@@ -44,15 +44,44 @@ __device__ __forceinline__ void load_tile(Tile& dst, const MatRef& m, int r0, in
   }
 }
 
+// register half of load_tile: fetch (global -> registers) now, park (registers -> shared) later
+__device__ __forceinline__ void fetch_tile(double (&v)[4], const MatRef& m, int r0, int c0) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i;
+    v[i] = m.trans ? m.p[(size_t)(c0 + r) * m.ld + r0 + tx] : m.p[(size_t)(r0 + r) * m.ld + c0 + tx];
+  }
+}
+__device__ __forceinline__ void park_tile(Tile& dst, const double (&v)[4], bool trans) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i;
+    if (!trans) dst[r][tx] = v[i];
+    else dst[tx][r] = v[i];
+  }
+}
+
 // acc[i] (+)= sum_{k in [k0, k1)} A(r0 + ty + 8 i, k) * B(k, c0 + tx);  k0, k1 multiples of 32.
+// Software-pipelined: the global (L2) loads of k-step kk + 1 are in flight while step kk is multiplied out of shared
+// memory - these small fp64 GEMMs are latency-bound, one exposed L2 round trip per k-step was most of their time.
 __device__ __forceinline__ void tile_gemm(double acc[4], const MatRef& A, int r0, const MatRef& B, int c0,
                                           int k0, int k1, Tile& As, Tile& Bs) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (k0 >= k1) return;
+  double ra[4], rb[4];
+  fetch_tile(ra, A, r0, k0);
+  fetch_tile(rb, B, k0, c0);
   for (int kk = k0; kk < k1; kk += TB) {
     __syncthreads();
-    load_tile(As, A, r0, kk);
-    load_tile(Bs, B, kk, c0);
+    park_tile(As, ra, A.trans);
+    park_tile(Bs, rb, B.trans);
     __syncthreads();
+    if (kk + TB < k1) {
+      fetch_tile(ra, A, r0, kk + TB);
+      fetch_tile(rb, B, kk + TB, c0);
+    }
 #pragma unroll 8
     for (int k = 0; k < TB; ++k) {
       const double b = Bs[k][tx];
@@ -71,42 +100,73 @@ __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
   j = t - ii * (ii + 1) / 2;
 }
 
-// Cholesky of a 32 x 32 block held one row per lane in registers (warp-shuffle pivot / column broadcasts).
-// On exit a[c] = L[lane][c] (0 above the diagonal), rinv = 1 / L[lane][lane]; returns the first bad pivot (1-based).
-__device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int lane) {
+// 1 / sqrt(d) in double from the fp32 MUFU seed and ONE third-order Newton step (error ~ (5/16) e^3, e ~ 2^-22):
+// 4 dependent FP64 operations instead of the library routine's special-case handling on the pivot critical path.
+// d is a Cholesky pivot of a jittered kernel matrix: 1e-4 <~ d <~ outputscale, far from fp32 under/overflow.
+__device__ __forceinline__ double fast_rsqrt64(double d) {
+  const double y = (double)rsqrtf((float)d);
+  const double e = fma(-d * y, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// Cholesky of a 32 x 32 block held one row per lane in registers.  Per column: pivot broadcast (shuffle), reciprocal
+// square root, then the scaled column goes through a double-buffered shared-memory vector so that the 31 - c
+// trailing updates of a lane read their multipliers with broadcast loads (one 16-byte load per two columns) instead
+// of two shuffles each.  On exit a[c] = L[lane][c] (0 above the diagonal), rinv = 1 / L[lane][lane]; returns the
+// first bad pivot (1-based).  `lcol`: 2 x 32 doubles of shared memory, 16-byte aligned.
+__device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int lane, double* lcol) {
   int bad = 0;
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
     const double d = __shfl_sync(0xffffffffu, a[c], c);
     if (!(d > 0.0) && bad == 0) bad = c + 1;
-    const double rs = rsqrt(d);
+    const double rs = fast_rsqrt64(d);
     const double l = a[c] * rs;
     rinv = (lane == c) ? rs : rinv;
     a[c] = (lane >= c) ? l : 0.0;
+    double* buf = lcol + (c & 1) * TB;
+    buf[lane] = l;
+    __syncwarp();
     // branch-free trailing update: lanes above the diagonal (lane < c2) update entries that are never read
     // (they are overwritten with 0 when their column is processed), so no predicate is needed
+    if ((c + 1) & 1) {
+      if (c + 1 < TB) a[c + 1] = fma(-l, buf[c + 1], a[c + 1]);
 #pragma unroll
-    for (int c2 = c + 1; c2 < TB; ++c2) {
-      const double lc2 = __shfl_sync(0xffffffffu, l, c2);
-      a[c2] = fma(-l, lc2, a[c2]);
+      for (int c2 = c + 2; c2 + 1 < TB; c2 += 2) {
+        const double2 m2 = *reinterpret_cast<const double2*>(buf + c2);
+        a[c2] = fma(-l, m2.x, a[c2]);
+        a[c2 + 1] = fma(-l, m2.y, a[c2 + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int c2 = c + 1; c2 + 1 < TB; c2 += 2) {
+        const double2 m2 = *reinterpret_cast<const double2*>(buf + c2);
+        a[c2] = fma(-l, m2.x, a[c2]);
+        a[c2 + 1] = fma(-l, m2.y, a[c2 + 1]);
+      }
     }
   }
   return bad;
 }
 
-// Inverse of the lower-triangular block Lb (shared memory, row-major) with reciprocal diagonal rd:
-// lane = column of the inverse, result X[r][lane] written to Xb.
+// Inverse of the lower-triangular block Lb (shared memory, row-major) with reciprocal diagonal rd: lane = column of
+// the inverse.  Column-oriented forward substitution: once x[k] is known, the 31 - k partial sums of the rows below
+// are updated independently (instruction-level parallelism), so the dependent chain is 2 operations per row instead
+// of a dot product of growing length.  Result X[r][lane] written to Xb.
 __device__ __forceinline__ void trinv32_warp(const Tile& Lb, const double* rd, Tile& Xb, int lane) {
-  double x[TB];
+  double sacc[TB];   // partial sums; slot k is overwritten with x[k] once row k is solved
 #pragma unroll
-  for (int r = 0; r < TB; ++r) {
-    double s = (r == lane) ? 1.0 : 0.0;
+  for (int r = 0; r < TB; ++r) sacc[r] = (r == lane) ? 1.0 : 0.0;
 #pragma unroll
-    for (int k = 0; k < r; ++k) s = fma(-Lb[r][k], x[k], s);
-    x[r] = (r >= lane) ? s * rd[r] : 0.0;
+  for (int k = 0; k < TB; ++k) {
+    const double xk = (k >= lane) ? sacc[k] * rd[k] : 0.0;
+    sacc[k] = xk;
+#pragma unroll
+    for (int r = k + 1; r < TB; ++r) sacc[r] = fma(-Lb[r][k], xk, sacc[r]);
   }
+  // stores only after every load of Lb (the compiler cannot prove that Xb and Lb do not alias)
 #pragma unroll
-  for (int r = 0; r < TB; ++r) Xb[r][lane] = x[r];
+  for (int r = 0; r < TB; ++r) Xb[r][lane] = sacc[r];
 }
 
 struct MmFwdArgs {
@@ -283,6 +343,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   // per block column kb: every participating CTA factorises the diagonal block in registers (one warp, shuffle
   // broadcasts) and inverts it, so the panel solve X L_kk^T = A_ik becomes the GEMM X = A_ik Dinv^T.
   __shared__ double rdiag[TB];
+  __shared__ __align__(16) double lcol[2 * TB];
   Tile& Di = Cs[0];   // inverse of the diagonal block
   for (int kb = 0; kb < nb; ++kb) {
     const int nrb = nb - kb - 1;
@@ -297,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         for (int c = 0; c < TB; ++c) arow[c] = src[c];
         if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[10] = global_ns() + (unsigned long long)(arow[0] == 12345.678);
         double rinv = 0.0;
-        const int bad = chol32_warp(arow, rinv, lane);
+        const int bad = chol32_warp(arow, rinv, lane, lcol);
         if (bad && blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + bad);
         if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(rinv == 12345.678);
 #pragma unroll
@@ -578,9 +639,9 @@ __global__ void __launch_bounds__(kThreads) stage_grad_reduce_kernel(SgReduceArg
       } else if (e < n_u + n_vec + n_S) {
         const size_t idx = e - n_u - n_vec;
         const int i = (int)(idx / MP), j = (int)(idx - (size_t)i * MP);
-        // the FFMA Gram holds only the lower tile triangle (tile size tp): mirror the rest; the tensor-core Gram
-        // (ncpart > 0) writes every tile
-        const bool lower = a.ncpart > 0 || (i / tp >= j / tp);
+        // the FFMA Gram holds only the lower tile triangle (tile size tp); the tensor-core Gram (ncpart > 0)
+        // computes the [128 x 256] tiles (i / 128, j / 256) that touch the lower triangle: mirror the rest
+        const bool lower = a.ncpart > 0 ? ((j / 256) * 256 <= (i / 128) * 128 + 127) : (i / tp >= j / tp);
         const int si = lower ? i : j, sj = lower ? j : i;
         for (int sp = g; sp < L.splitsS; sp += 8) s += (double)Spart[((size_t)sp * MP + si) * MP + sj];
       } else {
@@ -792,6 +853,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       const int npart = kThreads / DP;           // DP in {16, 32, 64, 128}
       const int d = tid % DP, part = tid / DP;
       double s = 0.0;
+#pragma unroll 8
       for (int i = part; i < M; i += npart) s += t64[(size_t)i * DP + d];
       colred[tid] = s;
       __syncthreads();

@@ -651,13 +651,28 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
         }
         // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
-        OpRegs<TNP> ra;
-        load_a(ra, NSL - 1);
-        for (int s = NSL - 1; s >= p * SPB; --s) {
+        // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
+        // flight cannot cover the HBM latency (Little's law), three can
+        OpRegs<TNP> r0, r1, r2;
+        const int s_lo = p * SPB;
+        load_a(r0, NSL - 1);
+        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
+        if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
+        for (int s = NSL - 1; s >= s_lo; s -= 3) {
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
-          store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-          if (s > p * SPB) load_a(ra, s - 1);           // next slab's saved-A tile flies during the MMAs
+          store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+          if (s - 3 >= s_lo) load_a(r0, s - 3);
+          pipe.commit();
+          if (s - 1 < s_lo) break;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+          if (s - 4 >= s_lo) load_a(r1, s - 4);
+          pipe.commit();
+          if (s - 2 < s_lo) break;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
+          if (s - 5 >= s_lo) load_a(r2, s - 5);
           pipe.commit();
         }
         pipe.drain();
@@ -768,13 +783,27 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
         return gn < N ? ldg4(Wg + (size_t)gn * MP + sl * KT + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
     };
-    OpRegs<TNP> ra;
-    load_w(ra, 0);
-    for (int s = 0; s < MP / KT; ++s) {
+    // W slabs are fetched three slabs ahead (rotating register sets) to keep enough bytes in flight per SM
+    OpRegs<TNP> r0, r1, r2;
+    const int nsl = MP / KT;
+    load_w(r0, 0);
+    if (1 < nsl) load_w(r1, 1);
+    if (2 < nsl) load_w(r2, 2);
+    for (int s = 0; s < nsl; s += 3) {
       float *a_hi, *a_lo;
       pipe.acquire(a_hi, a_lo);
-      store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-      if (s + 1 < MP / KT) load_w(ra, s + 1);
+      store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+      if (s + 3 < nsl) load_w(r0, s + 3);
+      pipe.commit();
+      if (s + 1 >= nsl) break;
+      pipe.acquire(a_hi, a_lo);
+      store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+      if (s + 4 < nsl) load_w(r1, s + 4);
+      pipe.commit();
+      if (s + 2 >= nsl) break;
+      pipe.acquire(a_hi, a_lo);
+      store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
+      if (s + 5 < nsl) load_w(r2, s + 5);
       pipe.commit();
     }
     pipe.drain();

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int p0 = blockIdx.x * 128;
   const int q0 = blockIdx.z * TQ;               // column tile (Gram with MP > 256)
+  // the Gram matrix is symmetric: tiles strictly above the diagonal are never read (stage_grad_reduce mirrors them)
+  if (GRAM && q0 > p0 + 127) return;
   const long long r0 = (long long)blockIdx.y * a.rows_per_split;
   long long r1 = r0 + a.rows_per_split;
   if (r1 > a.N) r1 = a.N;
