@@ -127,6 +127,17 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
       tc::mbar_wait(&bars[4 + st], phase);        // A planes written
       tc::mbar_wait(&bars[2 + st], phase);        // B image landed
       tc::tc_fence_after();
+      // TMA request for the next slab's B image into the other stage.  If that stage's last readers have already
+      // retired (the usual case: the producers are slower than the tensor core), the request goes out BEFORE this
+      // slab's MMAs are issued, so the L2 round trip overlaps the issue time instead of following it.
+      const bool more = (i + 1 < nslabs) || (t + 1 < ntiles_mine);
+      const int nst = st ^ 1;
+      bool requested = !more;
+      if (more && (uses[nst] == 0 || tc::mbar_test(&bars[nst], (uses[nst] - 1) & 1))) {
+        const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
+        issue_bulk_b<NB>(base, bars, nst, nx.img, nx.rows);
+        requested = true;
+      }
 #pragma unroll
       for (int j = 0; j < KT / 8; ++j) {
         const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
@@ -137,11 +148,8 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
       }
       tc::umma_commit(&bars[st]);
       uses[st] += 1;
-      // TMA request for the next slab's B image into the other stage, as soon as its last readers have retired
-      const bool more = (i + 1 < nslabs) || (t + 1 < ntiles_mine);
-      if (more) {
+      if (!requested) {                           // the other stage was still being read: wait, then request
         const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
-        const int nst = st ^ 1;
         if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
         issue_bulk_b<NB>(base, bars, nst, nx.img, nx.rows);
       }
@@ -723,8 +731,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[GPBLUR_MAX_M / KT];
-  __shared__ float red[8][32][33];
-  __shared__ float part_q[8][32], part_t[8][32], part_sc[8][4];
+  __shared__ __align__(16) float red[8][32][kStagePitch];   // per-warp staging tile (x~ in, dx out)
+  __shared__ float rg_s[8][2][32];                             // per-warp r[n], g_mu[n] of its 32 points
+  __shared__ float part_q[8][32], part_t[8][32], part_q2[8][32], part_t2[8][32], part_sc[8][4];
   __shared__ float q_s[DPT], t1_s[DPT], sc_s[4];
 
   const WsLayout& L = a.L;
@@ -764,6 +773,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   } else {
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
+  long long dseg[6] = {0, 0, 0, 0, 0, 0};
+  long long dlast = clock64();
+#define DSEG(i) do { if (a.dbg) { const long long tnow = clock64(); dseg[i] += tnow - dlast; dlast = tnow; } } while (0)
 
   // epilogue mapping: the 8 warps cover 4 lane quadrants x 2 column halves of the [128, DPT] tile; with DPT = 32
   // only the first 4 warps have columns.
@@ -783,107 +795,150 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
         return gn < N ? ldg4(Wg + (size_t)gn * MP + sl * KT + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
     };
+    // per-point scalars and the x rows of the first epilogue chunk: requested now, consumed after the GEMM
+    const long long gn = n0 + row;
+    const bool live = gn < N;
+    const float r = live ? rrow[gn] : 0.f;
+    const float gm = live ? gsc[gn] : 0.f;
+    const float gv = live ? gsc[N + gn] : 0.f;
+    const long long w0 = n0 + quad * 32;
+    const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    auto load_x_chunk = [&](float4 (&xq)[8], int col) {
+      const int d = col + c4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < nvalid && d < D) {
+          const float* xr = a.x + (size_t)(w0 + rr) * D + d;
+          if (vec) xv = ldg4(xr);
+          else {
+            xv.x = xr[0];
+            if (d + 1 < D) xv.y = xr[1];
+            if (d + 2 < D) xv.z = xr[2];
+            if (d + 3 < D) xv.w = xr[3];
+          }
+        }
+        xq[it] = xv;
+      }
+    };
+    float4 xq[8];
+    if (has_cols) load_x_chunk(xq, DPT >= 64 ? half * (DPT / 2) : 0);
     // W slabs are fetched three slabs ahead (rotating register sets) to keep enough bytes in flight per SM
     OpRegs<TNP> r0, r1, r2;
     const int nsl = MP / KT;
+    DSEG(0);
     load_w(r0, 0);
     if (1 < nsl) load_w(r1, 1);
     if (2 < nsl) load_w(r2, 2);
     for (int s = 0; s < nsl; s += 3) {
       float *a_hi, *a_lo;
       pipe.acquire(a_hi, a_lo);
+      DSEG(1);
       store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+      DSEG(2);
       if (s + 3 < nsl) load_w(r0, s + 3);
       pipe.commit();
+      DSEG(3);
       if (s + 1 >= nsl) break;
       pipe.acquire(a_hi, a_lo);
+      DSEG(1);
       store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+      DSEG(2);
       if (s + 4 < nsl) load_w(r1, s + 4);
       pipe.commit();
+      DSEG(3);
       if (s + 2 >= nsl) break;
       pipe.acquire(a_hi, a_lo);
+      DSEG(1);
       store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
+      DSEG(2);
       if (s + 5 < nsl) load_w(r2, s + 5);
       pipe.commit();
+      DSEG(3);
     }
     pipe.drain();
+    DSEG(4);
 
-    const long long gn = n0 + row;
-    const bool live = gn < N;
-    const float r = live ? rrow[gn] : 0.f;
-    const float gm = live ? gsc[gn] : 0.f;
-    const float gv = live ? gsc[N + gn] : 0.f;
     if (has_cols) {
+      // the warp owns the points n0 + quad * 32 + [0, 32) and 32 dimensions per chunk.  x comes in with coalesced
+      // 16-byte loads (8 lanes per row segment), is centred / scaled once and parked in the warp's staging tile
+      // red[warp][row][.] (pitch 36: conflict-free row AND column access); the per-dimension sums read it by column
+      // (lane = dimension), the dx rows are written back through the same tile, transposed and coalesced.
+      float (*stg)[kStagePitch] = red[warp];
+      rg_s[warp][0][lane] = live ? r : 0.f;
+      rg_s[warp][1][lane] = live ? gm : 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < CH_PER_HALF; ++ch) {
         const int col = (DPT >= 64 ? half * (DPT / 2) : 0) + ch * 32;
+        __syncwarp();
+        {
+          const int d = col + c4;
+          const float4 c4v = d < DP ? ldg4(center + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 iev = d < DP ? ldg4(inv_ell + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ch > 0) load_x_chunk(xq, col);           // DPT = 128 only; the first chunk was prefetched
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            float4 xv = xq[it];
+            if (rr < nvalid && d < D) {
+              xv.x = (xv.x - c4v.x) * iev.x; xv.y = (xv.y - c4v.y) * iev.y;
+              xv.z = (xv.z - c4v.z) * iev.z; xv.w = (xv.w - c4v.w) * iev.w;
+            }
+            *reinterpret_cast<float4*>(&stg[rr][c4]) = xv;
+          }
+        }
+        __syncwarp();
+        // per-dimension reductions over the 32 points of this warp (lane = dimension col + lane), fixed order:
+        // q_d = sum r x~^2, t1_d = sum g_mu x~
+        float sq = 0.f, st = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const float xv = stg[rr][lane];
+          sq = fmaf(rg_s[warp][0][rr] * xv, xv, sq);
+          st = fmaf(rg_s[warp][1][rr], xv, st);
+        }
+        // dx row of this lane's point: (W Z~ - r x~) / ell + g_mu w
         float v[32];
         tc::tmem_ld32(tmem_d + lane_base + (uint32_t)col, v);
-        float xs[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const int d = col + i;
-          float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && d < D) {
-            const float* xr = a.x + (size_t)gn * D;
-            if (vec) xv = ldg4(xr + d);
-            else {
-              xv.x = xr[d];
-              if (d + 1 < D) xv.y = xr[d + 1];
-              if (d + 2 < D) xv.z = xr[d + 2];
-              if (d + 3 < D) xv.w = xr[d + 3];
-            }
-          }
-          const float4 c4 = d < DP ? ldg4(center + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 xs4 = *reinterpret_cast<const float4*>(&stg[lane][i]);
           const float4 ie = d < DP ? ldg4(inv_ell + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          xs[i + 0] = (xv.x - c4.x) * ie.x; xs[i + 1] = (xv.y - c4.y) * ie.y;
-          xs[i + 2] = (xv.z - c4.z) * ie.z; xs[i + 3] = (xv.w - c4.w) * ie.w;
+          const float4 w4 = d < DP ? ldg4(wl + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[i + 0] = (v[i + 0] - r * xs4.x) * ie.x + gm * (w4.x * ie.x);
+          v[i + 1] = (v[i + 1] - r * xs4.y) * ie.y + gm * (w4.y * ie.y);
+          v[i + 2] = (v[i + 2] - r * xs4.z) * ie.z + gm * (w4.z * ie.z);
+          v[i + 3] = (v[i + 3] - r * xs4.w) * ie.w + gm * (w4.w * ie.w);
         }
-        // dx
-        if (a.dx && live) {
-          float* dst = a.dx + (size_t)gn * D + col;
+        __syncwarp();                                // every lane is done reading x~ by column
+        if (a.dx) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int d = col + i;
-            if (d < D) {
-              const float4 ie = ldg4(inv_ell + d), w4 = ldg4(wl + d);
-              float4 o;
-              o.x = (v[i + 0] - r * xs[i + 0]) * ie.x + gm * (w4.x * ie.x);
-              o.y = (v[i + 1] - r * xs[i + 1]) * ie.y + gm * (w4.y * ie.y);
-              o.z = (v[i + 2] - r * xs[i + 2]) * ie.z + gm * (w4.z * ie.z);
-              o.w = (v[i + 3] - r * xs[i + 3]) * ie.w + gm * (w4.w * ie.w);
-              if (vec) *reinterpret_cast<float4*>(dst + i) = o;
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(&stg[lane][i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          __syncwarp();
+          const int d = col + c4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            if (rr < nvalid && d < D) {
+              const float4 o = *reinterpret_cast<const float4*>(&stg[rr][c4]);
+              float* dst = a.dx + (size_t)(w0 + rr) * D + d;
+              if (vec) *reinterpret_cast<float4*>(dst) = o;
               else {
-                dst[i] = o.x;
-                if (d + 1 < D) dst[i + 1] = o.y;
-                if (d + 2 < D) dst[i + 2] = o.z;
-                if (d + 3 < D) dst[i + 3] = o.w;
+                dst[0] = o.x;
+                if (d + 1 < D) dst[1] = o.y;
+                if (d + 2 < D) dst[2] = o.z;
+                if (d + 3 < D) dst[3] = o.w;
               }
             }
           }
         }
-        // per-dimension reductions over the 32 points of this warp: q_d = sum r x~^2, t1_d = sum g_mu x~
-#pragma unroll
-        for (int i = 0; i < 32; ++i) red[warp][lane][i] = live ? r * xs[i] * xs[i] : 0.f;
-        __syncwarp();
-        float sq = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) sq += red[warp][rr][lane];
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) red[warp][lane][i] = live ? gm * xs[i] : 0.f;
-        __syncwarp();
-        float st = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) st += red[warp][rr][lane];
-        __syncwarp();
         // this warp's partial for dimension col + lane; (quad, half, ch) -> combined below in fixed order
-        if (CH_PER_HALF == 1) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
-        else {
-          // DPT = 128: two chunks per half; accumulate the second chunk into a second slot of the same warp
-          if (ch == 0) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
-          else { red[warp][0][lane] = sq; red[warp][1][lane] = st; }
-        }
+        if (ch == 0) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
+        else { part_q2[warp][lane] = sq; part_t2[warp][lane] = st; }   // DPT = 128: second chunk of the half
       }
     }
     {
@@ -903,7 +958,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
       for (int qd = 0; qd < 4; ++qd) {
         const int w = hf * 4 + qd;
         if (ch == 0) { sq += part_q[w][ln]; st += part_t[w][ln]; }
-        else { sq += red[w][0][ln]; st += red[w][1][ln]; }
+        else { sq += part_q2[w][ln]; st += part_t2[w][ln]; }
       }
       q_s[d] += sq;
       t1_s[d] += st;
@@ -915,7 +970,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
     }
     tc::tc_fence_before();   // the TMEM reads of this tile are done before the next tile's MMAs are released
     prod_sync();
+    DSEG(5);
   }
+  if (a.dbg && blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 6; ++i) a.dbg[24 + i] = dseg[i];
+#undef DSEG
   }   // producer warps
   __syncthreads();
   float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
@@ -984,6 +1043,7 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
   a.L = L; a.ws = ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
+  a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
   const int grid = tc_grid(L);
   {
     ProfScope ps(ST_POINT_BWD, st);
