@@ -485,43 +485,55 @@ def run_ours(args, wl, name):
     if rank == 0:
         peaks = load_peaks()
         N_total = B * sum(calls)
-        # dominant kernel and its roofline
+        # dominant kernel and its roofline; the once-per-update M x M kernels (mm_fwd / mm_bwd / sg_reduce) are
+        # latency-bound fp64 work with no per-window traffic, so the dominant PER-POINT kernel is reported too
         dom = max(stage_ms.items(), key=lambda kv: kv[1][0])[0] if stage_ms else None
-        roof = None
-        if dom is not None:
-            ms_dom, launches_dom = stage_ms[dom]
-            per_launch_s = ms_dom * 1e-3 / max(launches_dom, 1)
-            n_per_launch = N_total / max(launches_dom, 1)
-            if "H" in wl:                       # two-layer stack: H + 1 launches per stage, each over all N points
-                n_per_launch = N_total          # (work model uses the layer-1 dims D, M: H of the H + 1 launches)
-            by, fl = stage_work(dom, int(n_per_launch), D, M)
-            tf32_peak = peaks["bf16_tflops"] / 2.0
-            intensity = fl / max(by, 1)
-            if by > 0 and intensity < tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9):
-                roof = {"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-            else:
-                roof = {"bound": "tensor", "achieved": fl / per_launch_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "peak_note": "TF32 dense rate = 1/2 of the measured cuBLAS bf16 burst peak; 'achieved' counts "
-                                     "ALGORITHMIC flops (a 3xTF32 kernel issues 3 MMAs per product; M <= 64 and "
-                                     "M > 256 still run FP32 FFMA, peak ~74 TFLOP/s)"}
-            roof["frac"] = roof["achieved"] / roof["peak"]
-            # measured DRAM traffic of that kernel (ncu --set full capture of this same command, per launch)
-            roof["traffic"] = None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-                ent = tj.get(name, {}).get(dom)
-                if ent:
-                    roof["traffic"] = ent["bytes_per_launch"]
-                    roof["traffic_source"] = "profiles/ncu_traffic.json (dram__bytes_read+write per launch, ncu --set full)"
-            except Exception:
-                pass
-            roof["algorithmic_bytes_per_launch"] = by
-            roof["algorithmic_flops_per_launch"] = fl
-            roof["kernel"] = dom
-            roof["kernel_ms_per_launch"] = per_launch_s * 1e3
-            roof["peak_source"] = peaks["source"]
-            roof["hbm_frac_whole_step"] = (B * sum(bytes_per_window(L, D) for L in calls) / (ms_per_step * 1e-3) / 1e9
-                                           / peaks["hbm_gbs"])
+        point_stages = {k: v for k, v in stage_ms.items() if k in ("point_fwd", "point_bwd", "dx", "gram", "wx")}
+        dom_point = max(point_stages.items(), key=lambda kv: kv[1][0])[0] if point_stages else None
+        roofs = {}
+        for which, dom in (("roofline", dom), ("roofline_per_point_kernel", dom_point)):
+          roof = None
+          if dom is not None:
+              ms_dom, launches_dom = stage_ms[dom]
+              per_launch_s = ms_dom * 1e-3 / max(launches_dom, 1)
+              n_per_launch = N_total / max(launches_dom, 1)
+              if "H" in wl:                       # two-layer stack: H + 1 launches per stage, each over all N points
+                  n_per_launch = N_total          # (work model uses the layer-1 dims D, M: H of the H + 1 launches)
+              by, fl = stage_work(dom, int(n_per_launch), D, M)
+              tf32_peak = peaks["bf16_tflops"] / 2.0
+              intensity = fl / max(by, 1)
+              if by > 0 and intensity < tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9):
+                  roof = {"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+              else:
+                  roof = {"bound": "tensor", "achieved": fl / per_launch_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                          "peak_note": "TF32 dense rate = 1/2 of the measured cuBLAS bf16 burst peak; 'achieved' counts "
+                                       "ALGORITHMIC flops (a 3xTF32 kernel issues 3 MMAs per product, so its "
+                                       "ceiling is frac = 1/3; M <= 64 runs FP32 FFMA, peak ~74 TFLOP/s)"}
+              roof["frac"] = roof["achieved"] / roof["peak"]
+              if roof["bound"] == "tensor" and M > 64 and dom in point_stages:
+                  roof["frac_of_3xtf32_ceiling"] = 3.0 * roof["frac"]
+              if dom in ("mm_fwd", "mm_bwd", "sg_reduce"):
+                  roof["note"] = ("once-per-parameter-update M x M stage (fp64 Cholesky / inverse / Cholesky backward on "
+                                  "CUDA cores): serial panel factorisations + grid barriers, latency-bound; no "
+                                  "per-window traffic - see roofline_per_point_kernel for the throughput kernels")
+              # measured DRAM traffic of that kernel (ncu --set full capture of this same command, per launch)
+              roof["traffic"] = None
+              try:
+                  tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                  ent = tj.get(name, {}).get(dom)
+                  if ent:
+                      roof["traffic"] = ent["bytes_per_launch"]
+                      roof["traffic_source"] = "profiles/ncu_traffic.json (dram__bytes_read+write per launch, ncu --set full)"
+              except Exception:
+                  pass
+              roof["algorithmic_bytes_per_launch"] = by
+              roof["algorithmic_flops_per_launch"] = fl
+              roof["kernel"] = dom
+              roof["kernel_ms_per_launch"] = per_launch_s * 1e3
+              roof["peak_source"] = peaks["source"]
+              roof["hbm_frac_whole_step"] = (B * sum(bytes_per_window(L, D) for L in calls) / (ms_per_step * 1e-3) / 1e9
+                                             / peaks["hbm_gbs"])
+          roofs[which] = roof
         cb = None if args.no_cpu_baseline else time_cpu_reference(wl, 3, 1)[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -535,7 +547,8 @@ def run_ours(args, wl, name):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof,
+            "roofline": roofs.get("roofline"),
+            "roofline_per_point_kernel": roofs.get("roofline_per_point_kernel"),
             "cpu_baseline": cb,
             "stage_ms_per_step": {k: round(v[0], 5) for k, v in stage_ms.items()},
             "wall_ms_per_step": t_wall * 1e3 / args.steps,
