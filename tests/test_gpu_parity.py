@@ -52,6 +52,9 @@ SHAPES = [
     (5, 13, 48, 100),      # D padded 48 -> 64, M padded 100 -> 128
     (3, 24, 32, 300),      # M padded 300 -> 512 (two 256-column blocks on the tensor-core path)
     (700, 24, 64, 64),     # enough points for the 128-point tiles, M = 64 path
+    (8, 24, 10, 256),      # C4 second layer: input width H = 10 (D % 4 != 0) on the tensor-core path
+    (40, 24, 20, 128),     # D = 20 -> padded 32, tensor-core path, several 128-point tiles with a ragged tail
+    (1100, 1, 128, 256),   # D = 128 (widest supported), L = 1
 ]
 
 
