@@ -643,7 +643,16 @@ __global__ void __launch_bounds__(kThreads) stage_grad_reduce_kernel(SgReduceArg
         // computes the [128 x 256] tiles (i / 128, j / 256) that touch the lower triangle: mirror the rest
         const bool lower = a.ncpart > 0 ? ((j / 256) * 256 <= (i / 128) * 128 + 127) : (i / tp >= j / tp);
         const int si = lower ? i : j, sj = lower ? j : i;
-        for (int sp = g; sp < L.splitsS; sp += 8) s += (double)Spart[((size_t)sp * MP + si) * MP + sj];
+        // loads batched 4 deep before the (ordered) adds: independent requests in flight
+        const float* src = Spart + (size_t)si * MP + sj;
+        const size_t pstride = (size_t)MP * MP;
+        int sp = g;
+        for (; sp + 24 < L.splitsS; sp += 32) {
+          const float v0 = src[(size_t)sp * pstride], v1 = src[(size_t)(sp + 8) * pstride];
+          const float v2 = src[(size_t)(sp + 16) * pstride], v3 = src[(size_t)(sp + 24) * pstride];
+          s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+        }
+        for (; sp < L.splitsS; sp += 8) s += (double)src[(size_t)sp * pstride];
       } else {
         const size_t idx = e - n_u - n_vec - n_S;
         for (int sp = g; sp < L.splitsZ; sp += 8) s += (double)WXpart[(size_t)sp * MP * DP + idx];
