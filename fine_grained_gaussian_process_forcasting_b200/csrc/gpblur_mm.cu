@@ -345,10 +345,13 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   __shared__ double rdiag[TB];
   __shared__ __align__(16) double lcol[2 * TB];
   Tile& Di = Cs[0];   // inverse of the diagonal block
+  // The triangular inverse X = L^-1 is built INSIDE the factorisation loop (no separate phase, no extra grid
+  // barriers): block row kb of X is X[kb][j] = -Dinv_kb * Y[kb][j] (j < kb) with Y[kb][j] = sum_{k=j}^{kb-1} L[kb][k] X[k][j]
+  // accumulated into T64 by rank-32 updates during the trailing phases of steps j .. kb - 1.
   for (int kb = 0; kb < nb; ++kb) {
     const int nrb = nb - kb - 1;
-    const bool has_rows = (int)blockIdx.x < nrb;
-    if (has_rows || blockIdx.x == 0) {
+    const int n_items = nrb + kb;               // panel row blocks + inverse tiles of block row kb
+    if ((int)blockIdx.x < n_items || blockIdx.x == 0) {
       __syncthreads();
       if (kb == 0 && blockIdx.x == 0 && tid == 0) stamps[9] = global_ns();
       if (warp == 0) {
@@ -369,89 +372,92 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(Di[31][0] == 12345.678);
       }
       __syncthreads();
-      // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
-      for (int rb = blockIdx.x; rb < nrb; rb += G) {
-        const int row0 = (kb + 1 + rb) * TB;
-        __syncthreads();
-        load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
-        __syncthreads();
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int k = 0; k < TB; ++k) {
-          const double b = Di[lane][k];
+      // the diagonal block of the inverse is not read by anybody during this phase: publish it right away (the
+      // trailing phase below needs it)
+      if (blockIdx.x == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = fma(As[warp + 8 * i][k], b, acc[i]);
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * i;
+          Li64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Di[r][lane];
         }
+      }
+      for (int it = blockIdx.x; it < n_items; it += G) {
+        __syncthreads();
+        if (it < nrb) {
+          // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
+          const int row0 = (kb + 1 + it) * TB;
+          load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
+          __syncthreads();
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+          for (int k = 0; k < TB; ++k) {
+            const double bv = Di[lane][k];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) L64[(size_t)(row0 + warp + 8 * i) * MP + kb * TB + lane] = acc[i];
+            for (int i = 0; i < 4; ++i) acc[i] = fma(As[warp + 8 * i][k], bv, acc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) L64[(size_t)(row0 + warp + 8 * i) * MP + kb * TB + lane] = acc[i];
+        } else {
+          // inverse tile X[kb][j] = -Dinv_kb * Y[kb][j]
+          const int j = it - nrb;
+          load_tile(As, MatRef{T64, MP, false}, kb * TB, j * TB);
+          __syncthreads();
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+          for (int k = 0; k < TB; ++k) {
+            const double yv = As[k][lane];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fma(Di[warp + 8 * i][k], yv, acc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) Li64[(size_t)(kb * TB + warp + 8 * i) * MP + j * TB + lane] = -acc[i];
+        }
       }
     }
     grid.sync();
-    // the factorised diagonal block (and its inverse, which seeds phase 3) are published only now: other
-    // CTAs read the unfactorised block above
+    // the factorised diagonal block is published only now: other CTAs read the unfactorised block above
     if (blockIdx.x == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = warp + 8 * i;
         L64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Dg[r][lane];
-        Li64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Di[r][lane];
       }
     }
-    // trailing update: C_ij -= L_ik L_jk^T for kb < j <= i
+    // trailing update: C_ij -= L_ik L_jk^T for kb < j <= i;  plus the rank-32 update of the inverse's partial sums
+    // Y[i][j] (+)= L[i][kb] X[kb][j] for every later block row i > kb and j <= kb (one k-step per tile, all
+    // independent: the late steps of the factorisation leave most CTAs idle anyway)
     const int ntr = nrb * (nrb + 1) / 2;
-    for (int t = blockIdx.x; t < ntr; t += G) {
-      int ti, tj;
-      tri_decode(t, ti, tj);
-      const int bi = kb + 1 + ti, bj = kb + 1 + tj;
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
-                kb * TB + TB, As, Bs);
+    const int ny = nrb * (kb + 1);
+    for (int t = blockIdx.x; t < ntr + ny; t += G) {
+      if (t < ntr) {
+        int ti, tj;
+        tri_decode(t, ti, tj);
+        const int bi = kb + 1 + ti, bj = kb + 1 + tj;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
+                  kb * TB + TB, As, Bs);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp + 8 * i;
-        if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] -= acc[i];
-      }
-    }
-    grid.sync();   // also publishes the last diagonal block before phase 3
-  }
-
-  GPBLUR_STAMP();
-  // ---------------- phase 3b: recursive doubling  inv([[A,0],[C,B]]) = [[Ai,0],[-Bi C Ai, Bi]] ----
-  for (int s = TB; s < MP; s *= 2) {
-    const int sb = s / TB;                    // blocks per half
-    const int npairs = (MP + 2 * s - 1) / (2 * s);
-    // phase a: T = C * Ainv
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int pr = 0; pr < npairs; ++pr) {
-        const int start = pr * 2 * s, mid = start + s;
-        if (mid >= MP) continue;
-        const int end = (start + 2 * s < MP) ? start + 2 * s : MP;
-        const int rbk = (end - mid) / TB;
-        const int nt = rbk * sb;
-        for (int t = blockIdx.x; t < nt; t += G) {
-          const int tr = t / sb, tc = t - tr * sb;
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          if (pass == 0) {
-            // T[mid + r][start + c] = sum_{k >= c-tile} L[mid + r][start + k] Ainv[start + k][start + c]
-            tile_gemm(acc, MatRef{L64, MP, false}, mid + tr * TB, MatRef{Li64, MP, false},
-                      start + tc * TB, start + tc * TB, mid, As, Bs);
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * i;
+          if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] -= acc[i];
+        }
+      } else {
+        const int yi = (t - ntr) / (kb + 1), j = (t - ntr) - yi * (kb + 1);
+        const int bi = kb + 1 + yi;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{Li64, MP, false}, j * TB, kb * TB, kb * TB + TB, As, Bs);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              T64[(size_t)(mid + tr * TB + warp + 8 * i) * MP + start + tc * TB + lane] = acc[i];
-          } else {
-            // X[mid + r][start + c] = - sum_{k <= r-tile} Binv[mid + r][mid + k] T[mid + k][start + c]
-            tile_gemm(acc, MatRef{Li64, MP, false}, mid + tr * TB, MatRef{T64, MP, false},
-                      start + tc * TB, mid, mid + (tr + 1) * TB, As, Bs);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              Li64[(size_t)(mid + tr * TB + warp + 8 * i) * MP + start + tc * TB + lane] = -acc[i];
-          }
+        for (int i = 0; i < 4; ++i) {
+          double* y = T64 + (size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane;
+          *y = (j == kb) ? acc[i] : *y + acc[i];       // the first contribution to Y[i][kb] comes from this step
         }
       }
-      grid.sync();
     }
+    grid.sync();   // also publishes the last diagonal block before phase 4
   }
 
+  GPBLUR_STAMP();   // (the slot of the former recursive-doubling inverse phase: now ~0)
+  GPBLUR_STAMP();
   GPBLUR_STAMP();
   // ---------------- phase 4: fp32 operands ----------------
   for (int t = blockIdx.x; t < nb * nb; t += G) {
