@@ -227,10 +227,11 @@ __device__ __forceinline__ void store_kmajor(float* hi, float* lo, const OpRegs<
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// x tile row (point) -> centred / scaled float4 of k-chunk `dchunk`
+// x tile row (point), k-chunk `dchunk`: raw() only issues the global load (so that a prefetch one tile ahead does
+// not stall on its own data), transform() centres / scales it when the value is consumed.
 struct XLoader {
   const float* x; long long n0, N; int D; const float* center; const float* inv_ell; bool vec;
-  __device__ __forceinline__ float4 operator()(int row, int dchunk) const {
+  __device__ __forceinline__ float4 raw(int row, int dchunk) const {
     const long long gn = n0 + row;
     const int d = dchunk * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -243,7 +244,14 @@ struct XLoader {
         if (d + 2 < D) v.z = r[d + 2];
         if (d + 3 < D) v.w = r[d + 3];
       }
-      const float4 c = ldg4(center + d), ie = ldg4(inv_ell + d);
+    }
+    return v;
+  }
+  __device__ __forceinline__ float4 transform(float4 v, int row, int dchunk) const {
+    const long long gn = n0 + row;
+    const int d = dchunk * 4;
+    if (gn < N && d < D) {
+      const float4 c = ldg4(center + d), ie = ldg4(inv_ell + d);   // padded entries: centre 0, 1 / ell 0
       v.x = (v.x - c.x) * ie.x; v.y = (v.y - c.y) * ie.y; v.z = (v.z - c.z) * ie.z; v.w = (v.w - c.w) * ie.w;
     }
     return v;
@@ -256,13 +264,24 @@ __device__ __forceinline__ XLoader make_xloader(const TcPointArgs& a, long long 
                  (L.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0)};
 }
 
-// phase A of both kernels: S[128, MP] = X~ Z~^T into TMEM columns [0, MP)
-// registers of one 32-wide d-slab of the x tile (centred / scaled)
+// RAW registers of one 32-wide d-slab of the x tile (loads only)
 __device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
   load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
     const int dchunk = ds * (KT / 4) + c;
-    return dchunk * 4 < DP ? xl(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return dchunk * 4 < DP ? xl.raw(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
   });
+}
+// centre / scale the registers of load_x_slab in place (same (row, chunk) mapping as load_kmajor)
+__device__ __forceinline__ void transform_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rr = lane & 7, cq = lane >> 3;
+#pragma unroll
+  for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
+    const int wt = warp + 8 * p;
+    const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
+    const int dchunk = ds * (KT / 4) + c;
+    if (dchunk * 4 < DP) ra.v[p] = xl.transform(ra.v[p], row, dchunk);
+  }
 }
 
 // Producer side of S[128, BW] = X~ Z~[block q]^T (TMEM columns [0, BW)): nds slabs of the x tile.  xr0 / xr1: the
@@ -282,6 +301,7 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     if (preloaded && ds == 0) ra = xr0;
     else if (preloaded && ds == 1) ra = xr1;
     else load_x_slab(ra, xl, ds, DP);
+    transform_x_slab(ra, xl, ds, DP);
     if (stats) {
       // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
