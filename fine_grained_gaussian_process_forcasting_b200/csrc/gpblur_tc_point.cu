@@ -429,6 +429,26 @@ __device__ __forceinline__ void warp_store_chunk32(float* dst, size_t ld, float*
   }
 }
 
+// Same for a [32 rows x 16 columns] half chunk (staging pitch 20 floats): 4 lanes cover one 64-byte row segment,
+// 8 rows per store instruction.  Used by the epilogue pieces that are interleaved with the MMA slabs, where the
+// operand ring is busy and the staging lives in its own 2.5 KB per warp.
+constexpr int kStagePitch16 = 20;
+__device__ __forceinline__ void warp_store_chunk16(float* dst, size_t ld, float* wstg, const float (&v)[16], int lane,
+                                                   int nvalid) {
+  __syncwarp();
+  float* mine = wstg + lane * kStagePitch16;
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  __syncwarp();
+  const int rsub = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + rsub;
+    const float4 t = *reinterpret_cast<const float4*>(wstg + r * kStagePitch16 + c4);
+    if (r < nvalid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c4) = t;
+  }
+}
+
 // =================================================================================================
 // forward.  The inducing dimension is processed in column blocks of width BW (= min(MP, 256), the TMEM budget:
 // S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
@@ -442,9 +462,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxFwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[GPBLUR_MAX_M], m_s[GPBLUR_MAX_M], c_s[GPBLUR_MAX_M];
+  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q; m, c = s^2 - 1 of block p
   __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
-  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];   // per-slab row-statistic partials
+  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the interleaved epilogue
+  // per-slab row-statistic partials of phase A live in the same memory: every use of one is separated from every use
+  // of the other by a producer barrier (phase A ends with one, a tile ends with two)
+  float* part_n = &estg[0][0];
+  float* part_w = part_n + (KT / 4) * TNP;
+  static_assert(2 * (KT / 4) * TNP <= 8 * 32 * kStagePitch16, "row-statistic partials must fit in the staging tiles");
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -453,6 +478,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
   float* Ag = ws_ptr<float>(a.ws, L.A);
+  const float* znc_g = ws_cptr<float>(a.ws, L.znc);
+  const float* mvec_g = ws_cptr<float>(a.ws, L.mvec);
+  const float* cvec_g = ws_cptr<float>(a.ws, L.cvec);
   const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
   const float l2os = log2f(os);
 
@@ -460,10 +488,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) init_ring_barriers(bars);
   if (tid < kThreads) {
-    for (int i = tid; i < MP; i += kThreads) {
-      zn_s[i] = ws_cptr<float>(a.ws, L.znc)[i];     // exponent offsets, see kernel_values()
-      m_s[i] = ws_cptr<float>(a.ws, L.mvec)[i];
-      c_s[i] = ws_cptr<float>(a.ws, L.cvec)[i];
+    for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per (p, q) when MP > BW
+      zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
+      m_s[i] = mvec_g[i];
+      c_s[i] = cvec_g[i];
     }
     const int n = fwd_table<BW>(tab, a);
     if (tid == 0) tab_n = n;
@@ -501,9 +529,35 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
       float mu = 0.f, vv = 0.f;
       SEG(7);
+      const long long w0 = n0 + quad * 32;        // first point of this warp
+      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+      // epilogue of one 32-column chunk c of output block p (16 columns per column half): mean / variance partials
+      // of the own point, A saved for the backward.  The chunk is final as soon as whitening slab c of the pass
+      // q == p has retired, so most chunks are handled INSIDE the slab loop, while the tensor core works on the
+      // later slabs; the staging tile is private to the warp (the operand ring is busy).
+      auto epi_chunk = [&](int p, int c) {
+        const int col = c * 32 + half * 16;
+        float v[16];
+        tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          mu = fmaf(v[i], m_s[col + i], mu);
+          vv = fmaf(c_s[col + i] * v[i], v[i], vv);
+        }
+        if (L.training)
+          warp_store_chunk16(Ag + (size_t)w0 * MP + p * BW + col, MP, estg[warp], v, lane, nvalid);
+      };
       for (int p = 0; p < NP; ++p) {
         for (int q = 0; q <= p; ++q) {
           const bool first_pass = p == 0 && q == 0;
+          if (NP > 1) {                               // per-block constants (single block: loaded once at kernel start)
+            prod_sync();
+            if (tid < BW) {
+              zn_s[tid] = znc_g[q * BW + tid];
+              if (q == 0) { m_s[tid] = mvec_g[p * BW + tid]; c_s[tid] = cvec_g[p * BW + tid]; }
+            }
+            prod_sync();
+          }
           phase_a<BW>(pipe, a, xl, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0, xr1);
           if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
             const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
@@ -522,7 +576,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
             tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + zn_s[q * BW + col0 + i]), l2os));
+              v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + zn_s[col0 + i]), l2os));
             SEG(2);                                   // TMEM load + exp
             float *a_hi, *a_lo;
             pipe.acquire(a_hi, a_lo);
@@ -534,32 +588,18 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
             SEG(4);                                   // split + store of the k slab
             pipe.commit();
             SEG(5);                                   // fences + arrive
+            if (q == p && sl >= 2) {                  // slab sl - 2 has retired (acquire above): its chunk is final
+              tc::tc_fence_after();
+              epi_chunk(p, sl - 2);
+              SEG(6);
+            }
           }
         }
         pipe.drain();
         SEG(1);
-        // ---- epilogue of output block p: mean / variance partials of the own point; save A ----
-#pragma unroll 1
-        for (int ch = 0; ch < BW / 64; ++ch) {
-          const int col = half * (BW / 2) + ch * 32;
-          float v[32];
-          tc::tmem_ld32(tmem_a + lane_base + (uint32_t)col, v);
-          const int gcol = p * BW + col;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mu = fmaf(v[i], m_s[gcol + i], mu);
-            vv = fmaf(c_s[gcol + i] * v[i], v[i], vv);
-          }
-          // both stages' A planes are idle here (every MMA has retired, only B prefetches may be in flight):
-          // column half h stages its rows in stage h's A region
-          if (L.training) {
-            const long long w0 = n0 + quad * 32;      // first point of this warp
-            const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-            warp_store_chunk32(Ag + (size_t)w0 * MP + gcol, MP,
-                               stage_base + half * Stage<BW>::FLOATS + quad * 32 * kStagePitch, v, lane, nvalid);
-          }
-        }
-        // staging is drained (and the TMEM reads are done) before ANY producer publishes A planes of the next phase
+        epi_chunk(p, SPB - 2);
+        epi_chunk(p, SPB - 1);
+        // the TMEM reads are done before ANY producer publishes A planes of the next phase (its MMAs overwrite them)
         tc::tc_fence_before();
         prod_sync();
         SEG(6);                                       // block epilogue
