@@ -569,14 +569,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
           SEG(1);
           const float xnc = -0.72134752044448170f * xn_s[row];
           // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
+          // the S columns of slab sl + 1 are requested from TMEM before slab sl is exponentiated (two register sets)
+          uint32_t sreg[2][16];
+          tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(half * 16), sreg[0]);
+#pragma unroll
           for (int sl = 0; sl < SPB; ++sl) {
             // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
             float v[16];
             const int col0 = sl * KT + half * 16;
-            tc::tmem_ld16(tmem_s + lane_base + (uint32_t)col0, v);
+            tc::tmem_ld16_wait(sreg[sl & 1]);
+            if (sl + 1 < SPB) tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(col0 + KT), sreg[(sl + 1) & 1]);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + zn_s[col0 + i]), l2os));
+              v[i] = tc::ex2_approx(fminf(fmaf(__uint_as_float(sreg[sl & 1][i]), 1.4426950408889634f,
+                                               xnc + zn_s[col0 + i]), l2os));
             SEG(2);                                   // TMEM load + exp
             float *a_hi, *a_lo;
             pipe.acquire(a_hi, a_lo);
