@@ -641,9 +641,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxBwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[GPBLUR_MAX_M], beta_s[GPBLUR_MAX_M];
+  __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
-  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];
+  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the interleaved epilogue
+  // per-slab row-statistic partials of phase A live in the same memory (separated from every staging use by the
+  // producer barriers at the end of phase A and at the end of a tile)
+  float* part_n = &estg[0][0];
+  float* part_w = part_n + (KT / 4) * TNP;
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -655,15 +659,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
   float* rrow = ws_ptr<float>(a.ws, L.rrow);
+  const float* znc_g = ws_cptr<float>(a.ws, L.znc);
+  const float* beta_g = ws_cptr<float>(a.ws, L.beta);
   const float l2os = log2f(hyp[H_OS]);
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid == 0) init_ring_barriers(bars);
   if (tid < kThreads) {
-    for (int i = tid; i < MP; i += kThreads) {
-      zn_s[i] = ws_cptr<float>(a.ws, L.znc)[i];     // exponent offsets, see kernel_values()
-      beta_s[i] = ws_cptr<float>(a.ws, L.beta)[i];
+    for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per p when MP > BW
+      zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
+      beta_s[i] = beta_g[i];
     }
     const int n = bwd_table<BW>(tab, a);
     if (tid == 0) tab_n = n;
@@ -694,6 +700,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
       const long long gn = n0 + row;
       const XLoader xl = make_xloader(a, n0);
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      const long long w0 = n0 + quad * 32;        // first point of this warp
+      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
       // ---- fold the upstream gradients of this thread's point ----
       float gm = 0.f, gv = 0.f;
       if (gn < N) {
@@ -716,19 +724,52 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
         });
       };
-      float rsum = 0.f;
+      float rsum = 0.f, xnc = 0.f;
+      // epilogue of one 32-column chunk c of column block p (16 columns per column half): W = kbar o k, its row sum,
+      // W saved for the dx / W^T X kernels.  T[:, chunk c] is last touched by slab p SPB + c, and the slabs run in
+      // DEcreasing order, so chunk c is final once that slab has retired: most chunks are handled inside the slab
+      // loop while the tensor core works on the remaining slabs.
+      auto epi_chunk = [&](int p, int c) {
+        const int col = c * 32 + half * 16;
+        uint32_t kr[16], tr[16];
+        tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)col, kr);
+        tc::tmem_ld16_issue(tmem_t + lane_base + (uint32_t)col, tr);
+        tc::tmem_ld16_wait(kr);
+        tc::tmem_ld16_wait(tr);
+        float t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float k = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i]), 1.4426950408889634f, xnc + zn_s[col + i]), l2os));
+          const float kb = fmaf(2.0f * gv, __uint_as_float(tr[i]), gm * beta_s[col + i]);
+          t[i] = kb * k;
+          rsum += t[i];
+        }
+        warp_store_chunk16(Wg + (size_t)w0 * MP + p * BW + col, MP, estg[warp], t, lane, nvalid);
+      };
       for (int p = 0; p < NP; ++p) {
+        if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
+          prod_sync();
+          if (tid < BW) { zn_s[tid] = znc_g[p * BW + tid]; beta_s[tid] = beta_g[p * BW + tid]; }
+          prod_sync();
+        }
         phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
         if (p == 0 && more_tiles) {
           const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
           load_x_slab(xr0, xln, 0, L.DP);
           if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
         }
+        xnc = -0.72134752044448170f * xn_s[row];
         // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
         // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
         // flight cannot cover the HBM latency (Little's law), three can
         OpRegs<TNP> r0, r1, r2;
         const int s_lo = p * SPB;
+        // after the acquire of slab s, slab s + 2 has retired: if it lies in block p, its chunk (and S, complete
+        // since the first T slab was issued behind it) is final
+        auto interleaved = [&](int s) {
+          const int c = s + 2 - s_lo;
+          if (s + 2 <= NSL - 1 && c < SPB) { tc::tc_fence_after(); epi_chunk(p, c); }
+        };
         load_a(r0, NSL - 1);
         if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
         if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
@@ -738,41 +779,24 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
           if (s - 3 >= s_lo) load_a(r0, s - 3);
           pipe.commit();
+          interleaved(s);
           if (s - 1 < s_lo) break;
           pipe.acquire(a_hi, a_lo);
           store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
           if (s - 4 >= s_lo) load_a(r1, s - 4);
           pipe.commit();
+          interleaved(s - 1);
           if (s - 2 < s_lo) break;
           pipe.acquire(a_hi, a_lo);
           store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
           if (s - 5 >= s_lo) load_a(r2, s - 5);
           pipe.commit();
+          interleaved(s - 2);
         }
         pipe.drain();
-        const float xnc = -0.72134752044448170f * xn_s[row];
-#pragma unroll 1
-        for (int ch = 0; ch < BW / 64; ++ch) {
-          const int col = half * (BW / 2) + ch * 32;
-          const int gcol = p * BW + col;
-          float k[32], t[32];
-          tc::tmem_ld32(tmem_s + lane_base + (uint32_t)col, k);
-          tc::tmem_ld32(tmem_t + lane_base + (uint32_t)col, t);
-          kernel_values(k, xnc, zn_s, gcol, l2os);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float kb = fmaf(2.0f * gv, t[i], gm * beta_s[gcol + i]);
-            t[i] = kb * k[i];
-            rsum += t[i];
-          }
-          {
-            const long long w0 = n0 + quad * 32;
-            const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-            warp_store_chunk32(Wg + (size_t)w0 * MP + gcol, MP,
-                               stage_base + half * Stage<BW>::FLOATS + quad * 32 * kStagePitch, t, lane, nvalid);
-          }
-        }
-        // staging is drained (and the TMEM reads are done) before ANY producer publishes A planes of the next phase
+        epi_chunk(p, 1);
+        epi_chunk(p, 0);
+        // the TMEM reads are done before ANY producer publishes A planes of the next phase (its MMAs overwrite them)
         tc::tc_fence_before();
         prod_sync();
       }
