@@ -689,6 +689,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
+    long long bseg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long blast = clock64();
+#define BSEG(i) do { if (a.dbg) { const long long tnow = clock64(); bseg[i] += tnow - blast; blast = tnow; } } while (0)
     OpRegs<TNP> xr0, xr1;
     {
       const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
@@ -725,6 +728,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         });
       };
       float rsum = 0.f, xnc = 0.f;
+      BSEG(0);                                        // tile head (upstream gradients)
       // epilogue of one 32-column chunk c of column block p (16 columns per column half): W = kbar o k, its row sum,
       // W saved for the dx / W^T X kernels.  T[:, chunk c] is last touched by slab p SPB + c, and the slabs run in
       // DEcreasing order, so chunk c is final once that slab has retired: most chunks are handled inside the slab
@@ -759,6 +763,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
         }
         xnc = -0.72134752044448170f * xn_s[row];
+        BSEG(1);                                      // phase A
         // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
         // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
         // flight cannot cover the HBM latency (Little's law), three can
@@ -768,7 +773,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         // since the first T slab was issued behind it) is final
         auto interleaved = [&](int s) {
           const int c = s + 2 - s_lo;
+          BSEG(4);                                    // next loads + commit
           if (s + 2 <= NSL - 1 && c < SPB) { tc::tc_fence_after(); epi_chunk(p, c); }
+          BSEG(5);                                    // interleaved epilogue chunk
         };
         load_a(r0, NSL - 1);
         if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
@@ -776,24 +783,31 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         for (int s = NSL - 1; s >= s_lo; s -= 3) {
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
+          BSEG(2);                                    // acquire (MMA s + 2 retired)
           store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+          BSEG(3);                                    // split + store (waits for the global loads of the slab)
           if (s - 3 >= s_lo) load_a(r0, s - 3);
           pipe.commit();
           interleaved(s);
           if (s - 1 < s_lo) break;
           pipe.acquire(a_hi, a_lo);
+          BSEG(2);
           store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+          BSEG(3);
           if (s - 4 >= s_lo) load_a(r1, s - 4);
           pipe.commit();
           interleaved(s - 1);
           if (s - 2 < s_lo) break;
           pipe.acquire(a_hi, a_lo);
+          BSEG(2);
           store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
+          BSEG(3);
           if (s - 5 >= s_lo) load_a(r2, s - 5);
           pipe.commit();
           interleaved(s - 2);
         }
         pipe.drain();
+        BSEG(6);                                      // drain
         epi_chunk(p, 1);
         epi_chunk(p, 0);
         // the TMEM reads are done before ANY producer publishes A planes of the next phase (its MMAs overwrite them)
@@ -804,7 +818,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
       prod_sync();
       if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
       prod_sync();
+      BSEG(7);                                        // final chunks + row sums
     }
+    if (a.dbg && blockIdx.x == 0 && tid == 0)
+      for (int i = 0; i < 8; ++i) a.dbg[16 + i] = bseg[i];
+#undef BSEG
   }
   tc::tc_fence_before();
   __syncthreads();

@@ -14,7 +14,7 @@ x = torch.randn(N, D, device=dev)
 g = torch.randn(N, device=dev)
 for it in range(3):
     mean, var, sample, kl, info, ws = ops.svgp_forward_raw(x, *args, 0, 0, 0, True, True)
-    dx, bucket = ops.svgp_backward_raw(x, *args, g, g, None, None, var, 0, 0, 0, ws)
+    dx, sgrad = ops.point_backward_raw(x, M, g, g, None, var, 0, 0, 0, ws)   # no M x M backward: it reuses the stamp slots
 torch.cuda.synchronize()
 t = ops.debug_fetch(4, N, D, M, ws).cpu().tolist()
 names = ["tile head + first loads", "acquire (MMA s-2 retired)", "split + store", "next loads + commit", "drain", "epilogue"]
@@ -24,3 +24,9 @@ tot = sum(t[24:30])
 print("dx kernel, thread 0: total cycles", tot, "per tile", tot // per_cta)
 for i, nm in enumerate(names):
     print(f"   {nm:28s} {t[24 + i]:10d}  {100 * t[24 + i] / max(tot, 1):5.1f}%  per tile {t[24 + i] // per_cta}")
+
+bn = ["tile head", "phase A", "acquire (MMA s+2 retired)", "split + store (global A loads)", "next loads + commit", "interleaved epilogue", "drain", "final chunks + row sums"]
+tot = sum(t[16:24])
+print("bwd kernel, thread 0: total cycles", tot, "per tile", tot // per_cta)
+for i, nm in enumerate(bn):
+    print(f"   {nm:32s} {t[16 + i]:10d}  {100 * t[16 + i] / max(tot, 1):5.1f}%  per tile {t[16 + i] // per_cta}")
