@@ -488,6 +488,9 @@ def run_ours(args, wl, name):
         ly.rng_offset_dev = None
     sync_all()
     n_e = max(3, min(args.steps, 10))
+    for i in range(3):                                   # the caching allocator re-grows outside the graph pool
+        eager_step(i, xs[i % nbuf], ys[i % nbuf])
+    sync_all()
     ev_e[0].record()
     for i in range(n_e):
         eager_step(i, xs[i % nbuf], ys[i % nbuf])
@@ -539,6 +542,9 @@ def run_ours(args, wl, name):
               roof["frac"] = roof["achieved"] / roof["peak"]
               if roof["bound"] == "tensor" and M > 64 and dom in point_stages:
                   roof["frac_of_3xtf32_ceiling"] = 3.0 * roof["frac"]
+              if M <= 64 and dom in point_stages:     # FP32-FFMA path: CUDA-core bound long before HBM
+                  roof["ffma_tflops_achieved"] = fl / per_launch_s / 1e12
+                  roof["ffma_frac_of_74_tflops"] = roof["ffma_tflops_achieved"] / 74.0
               if dom in ("mm_fwd", "mm_bwd", "sg_reduce"):
                   roof["note"] = ("once-per-parameter-update M x M stage (fp64 Cholesky / inverse / Cholesky backward on "
                                   "CUDA cores): serial panel factorisations + grid barriers, latency-bound; no "
