@@ -37,6 +37,7 @@ struct TcPointArgs {
   const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
   uint32_t stream_id;
   int ntiles;
+  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP): 4 = skip the W / A chunk stores, 5 = skip chunk math
   long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
 };
 
@@ -748,7 +749,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           t[i] = kb * k;
           rsum += t[i];
         }
-        warp_store_chunk16(Wg + (size_t)w0 * MP + p * BW + col, MP, estg[warp], t, lane, nvalid);
+        if (a.exp_mode != 4)
+          warp_store_chunk16(Wg + (size_t)w0 * MP + p * BW + col, MP, estg[warp], t, lane, nvalid);
       };
       for (int p = 0; p < NP; ++p) {
         if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
@@ -767,7 +769,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
         // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
         // flight cannot cover the HBM latency (Little's law), three can
-        OpRegs<TNP> r0, r1, r2;
+        OpRegs<TNP> r0, r1;
         const int s_lo = p * SPB;
         // after the acquire of slab s, slab s + 2 has retired: if it lies in block p, its chunk (and S, complete
         // since the first T slab was issued behind it) is final
@@ -779,14 +781,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         };
         load_a(r0, NSL - 1);
         if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
-        if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
-        for (int s = NSL - 1; s >= s_lo; s -= 3) {
+        for (int s = NSL - 1; s >= s_lo; s -= 2) {
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
           BSEG(2);                                    // acquire (MMA s + 2 retired)
           store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
           BSEG(3);                                    // split + store (waits for the global loads of the slab)
-          if (s - 3 >= s_lo) load_a(r0, s - 3);
+          if (s - 2 >= s_lo) load_a(r0, s - 2);
           pipe.commit();
           interleaved(s);
           if (s - 1 < s_lo) break;
@@ -794,17 +795,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           BSEG(2);
           store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
           BSEG(3);
-          if (s - 4 >= s_lo) load_a(r1, s - 4);
+          if (s - 3 >= s_lo) load_a(r1, s - 3);
           pipe.commit();
           interleaved(s - 1);
-          if (s - 2 < s_lo) break;
-          pipe.acquire(a_hi, a_lo);
-          BSEG(2);
-          store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
-          BSEG(3);
-          if (s - 5 >= s_lo) load_a(r2, s - 5);
-          pipe.commit();
-          interleaved(s - 2);
         }
         pipe.drain();
         BSEG(6);                                      // drain
@@ -1152,6 +1145,7 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
+  a.exp_mode = tile_override("GPBLUR_TC_EXP");
   const int grid = tc_grid(L);
   {
     ProfScope ps(ST_POINT_BWD, st);
