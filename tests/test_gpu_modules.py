@@ -385,3 +385,46 @@ def test_graphed_step_matches_eager_and_draws_fresh_samples(cuda):
         step(x.to(cuda), y.to(cuda).unsqueeze(0))
         torch.cuda.synchronize()
         assert torch.equal(bucket.flat, grads1) and torch.equal(dx_static, dx1)
+
+
+def test_anomaly_mode_and_concurrent_threads(cuda):
+    """The reference enables torch.autograd.set_detect_anomaly(True) at import (forecast_denoising.py:11) and runs
+    optuna with n_jobs=4 threads, each with its own model on the same device (train.py:86): the ops must produce no
+    NaN / Inf in backward and be re-entrant."""
+    import threading
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    B, L, D, M = 8, 24, 32, 128
+    p = O.init_params_exercise(D, M, 31)
+    x, y, _, _ = O.make_inputs(B, L, D, 32)
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            with gpcompat.num_likelihood_samples(1), torch.autograd.detect_anomaly(check_nan=True):
+                model = DeepGPp(D, 100 + k, num_inducing=M).to(cuda)
+                load_params(model, p)
+                for _ in range(3):
+                    xd = x.to(cuda).requires_grad_(True)
+                    m_enc, _ = model.predict(xd)                 # two calls on one stage, like the reference
+                    _, dist = model.predict(xd)
+                    mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
+                    loss = -mll(dist, y.to(cuda).unsqueeze(0)).mean() + m_enc.mean()
+                    model.zero_grad()
+                    loss.backward()
+                torch.cuda.synchronize()
+                g = model.hidden_layer.variational_strategy.inducing_points.grad
+                assert torch.isfinite(g).all() and torch.isfinite(xd.grad).all()
+                results[k] = (loss.item(), g.double().cpu())
+        except Exception as e:    # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    # identical parameters and inputs in every thread -> identical results (deterministic kernels)
+    for k in range(1, 4):
+        assert results[k][0] == results[0][0] and torch.equal(results[k][1], results[0][1])
