@@ -322,22 +322,36 @@ def run_ours(args, wl, name):
     from fine_grained_gaussian_process_forcasting_b200.graphs import GraphedStep
     layers = [m for m in model.modules() if isinstance(m, DeepGPLayer)]
 
+    # The GP calls of one step are independent given the shared parameter stage; the small decoder-side call only
+    # fills a third of the SMs, so it is issued on a second stream and runs in the tail of the encoder-side kernels
+    # (autograd replays each call's backward on the stream of its forward).
+    from fine_grained_gaussian_process_forcasting_b200.graphs import CallStreams
+    call_streams = CallStreams(device, len(calls)) if (args.call_streams and len(calls) > 1) else None
+
     def step_body(xin, yin):
         """forward (mean, variance, fused sample, ELBO) + backward (dX, every GP parameter gradient)"""
         bucket.zero()
         outs, grads = [], []
         elbo = None
+        if call_streams is not None:
+            for ly in layers:                             # the shared stage is built once, on the main stream
+                ly._kl_only()
         for c, L in enumerate(calls):
             x = xin[c].detach().requires_grad_(True)      # fresh leaf: dX flows back to the forecaster
             last = c == len(calls) - 1
-            out = model.blur(x, yin if last else None, num_data=D)
+            fn = (lambda x=x, last=last: model.blur(x, yin if last else None, num_data=D))
+            out = call_streams.run(c, fn) if call_streams is not None else fn()
             outs += [out.mean, out.sample]
             grads += [gms[c], gss[c]]
             if last:
                 elbo = out.elbo
                 outs.append(elbo)
                 grads.append(g_elbo)
+        if call_streams is not None:
+            call_streams.join()
         torch.autograd.backward(outs, grads)
+        if call_streams is not None:
+            call_streams.join()
         return elbo
 
     def eager_step(i, xin, yin):
@@ -576,6 +590,7 @@ def run_ours(args, wl, name):
                        "parallelism": f"dp{world}", "l2": f"flush ({L2_FLUSH_BYTES >> 20} MiB write) between timed steps "
                        "+ 3 rotating input sets", "timing": "per-step CUDA events, max over ranks",
                        "launch": graph_note,
+                       "call_streams": call_streams is not None,
                        "regime": "R-exercise (SURVEY 8d)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pipeline": "pinned host inputs -> copy stream (step i + 1 in flight during step i) -> device "
@@ -603,6 +618,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GPBLUR_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    ap.add_argument("--no-call-streams", dest="call_streams", action="store_false",
+                    help="issue the GP calls of a step on one stream (default: one extra stream per additional call)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "
                     "step as a CUDA graph")
     args = ap.parse_args()

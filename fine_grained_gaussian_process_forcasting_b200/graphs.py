@@ -73,3 +73,39 @@ class GraphedStep:
     def set_rng_offset(self, value: int):
         for ly in self.layers:
             ly.rng_offset_dev.fill_(int(value))
+
+
+class CallStreams:
+    """Issue the independent GP calls of one step (the reference makes two: encoder- and decoder-side,
+    denoise_model_2.py:50-51) on separate CUDA streams, so that a call that cannot fill the GPU runs in the tail
+    of the other one's persistent kernels.  Call 0 stays on the current stream; autograd replays every call's
+    backward on the stream of its forward.  Works eagerly and inside a ``GraphedStep`` capture (fork / join events
+    become graph dependencies).
+
+        cs = CallStreams(device, 2)
+        enc_out = cs.run(0, lambda: model.blur(x_enc))
+        dec_out = cs.run(1, lambda: model.blur(x_dec, y))
+        cs.join()                      # before the outputs are consumed on the current stream
+        torch.autograd.backward(...); cs.join()
+    """
+
+    def __init__(self, device, n_calls: int):
+        self.device = torch.device(device)
+        self.side = [None] + [torch.cuda.Stream(device=self.device) for _ in range(max(0, n_calls - 1))]
+
+    def run(self, i: int, fn):
+        side = self.side[i]
+        if side is None:
+            return fn()
+        main = torch.cuda.current_stream(self.device)
+        side.wait_stream(main)
+        torch.cuda.set_stream(side)
+        try:
+            return fn()
+        finally:
+            torch.cuda.set_stream(main)
+
+    def join(self):
+        main = torch.cuda.current_stream(self.device)
+        for side in self.side[1:]:
+            main.wait_stream(side)

@@ -428,3 +428,59 @@ def test_anomaly_mode_and_concurrent_threads(cuda):
     # identical parameters and inputs in every thread -> identical results (deterministic kernels)
     for k in range(1, 4):
         assert results[k][0] == results[0][0] and torch.equal(results[k][1], results[0][1])
+
+
+def test_call_streams_match_single_stream(cuda):
+    """graphs.CallStreams: the encoder- and decoder-side call of one step on two streams (eagerly and inside a
+    CUDA-graph capture) give bit-identical outputs and gradients to the single-stream step."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    from fine_grained_gaussian_process_forcasting_b200.graphs import GraphedStep, CallStreams
+    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
+    D, M = 32, 256
+    p = O.init_params_exercise(D, M, 41)
+    x_enc, _, g_enc, _ = O.make_inputs(16, 96, D, 42)
+    x_dec, y, g_dec, _ = O.make_inputs(16, 24, D, 43)
+    with gpcompat.num_likelihood_samples(1):
+        model = DeepGPp(D, 7, num_inducing=M).to(cuda)
+        load_params(model, p)
+        model.train()
+        hl = model.hidden_layer
+        hl.set_rng(5, 0, 0)
+        bucket = FlatGradBucket(gp_parameters(model))
+        ge, gd = g_enc.to(cuda).unsqueeze(0), g_dec.to(cuda).unsqueeze(0)
+        cs = CallStreams(cuda, 2)
+        dxs = [torch.zeros(16, 96, D, device=cuda), torch.zeros(16, 24, D, device=cuda)]
+
+        def step(xe, xd, yy, streams):
+            bucket.zero()
+            hl.invalidate_param_stage()
+            hl._rng_offset = 0
+            hl._kl_only()
+            xe = xe.detach().requires_grad_(True)
+            xd = xd.detach().requires_grad_(True)
+            o1 = streams.run(0, lambda: model.blur(xe)) if streams else model.blur(xe)
+            o2 = streams.run(1, lambda: model.blur(xd, yy, num_data=D)) if streams else model.blur(xd, yy, num_data=D)
+            if streams:
+                streams.join()
+            torch.autograd.backward([o1.mean, o1.sample, o2.mean, o2.elbo],
+                                    [ge, ge, gd, torch.full((1, 16), -1.0 / 16, device=cuda)])
+            if streams:
+                streams.join()
+            dxs[0].copy_(xe.grad)
+            dxs[1].copy_(xd.grad)
+            return o1.mean, o1.sample, o2.mean, o2.elbo
+
+        ins = [x_enc.to(cuda), x_dec.to(cuda), y.to(cuda).unsqueeze(0)]
+        ref = [t.detach().clone() for t in step(*ins, None)]      # detached: keep no autograd graph alive
+        torch.cuda.synchronize()
+        ref_b, ref_dx = bucket.flat.clone(), [d.clone() for d in dxs]
+        got = [t.detach().clone() for t in step(*ins, cs)]
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(ref, got))
+        assert torch.equal(bucket.flat, ref_b) and all(torch.equal(a, b) for a, b in zip(dxs, ref_dx))
+        g = GraphedStep(model, lambda a, b, c: step(a, b, c, cs), ins)
+        got = [t.clone() for t in g.replay()]
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(ref, got))
+        assert torch.equal(bucket.flat, ref_b) and all(torch.equal(a, b) for a, b in zip(dxs, ref_dx))
