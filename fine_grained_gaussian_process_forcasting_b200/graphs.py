@@ -60,8 +60,18 @@ class GraphedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outputs = run()
+        # anomaly mode (the reference switches it on globally, forecast_denoising.py:11) checks every gradient for
+        # NaN on the HOST, which cannot be captured: it is off during the capture and restored afterwards
+        anomaly = torch.is_anomaly_enabled()
+        check_nan = torch.is_anomaly_check_nan_enabled() if hasattr(torch, "is_anomaly_check_nan_enabled") else True
+        if anomaly:
+            torch.autograd.set_detect_anomaly(False)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.outputs = run()
+        finally:
+            if anomaly:
+                torch.autograd.set_detect_anomaly(True, check_nan=check_nan)
         for ly in self.layers:
             ly.invalidate_param_stage()              # tensors of the capture pool must not leak into eager calls
             ly.rng_offset_dev.fill_(rank * self._consumed.get(id(ly), 0))

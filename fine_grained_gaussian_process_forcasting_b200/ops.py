@@ -246,7 +246,8 @@ def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None):
 
 
 def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, stream_id: int, want_sample: bool,
-                      training: bool, out: Optional[Tensor] = None, offset_dev: Optional[Tensor] = None):
+                      training: bool, out: Optional[Tensor] = None, offset_dev: Optional[Tensor] = None,
+                      ws: Optional[Tensor] = None):
     """x [N, D] + parameter stage -> (mean [N], var [N], sample [N] | None, workspace uint8).
     `out`: preallocated float32 [(3 | 2) * N] receiving mean | var | sample."""
     _need_cuda(x, stage)
@@ -256,7 +257,8 @@ def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, 
         out = torch.empty((3 if want_sample else 2) * N, device=dev, dtype=torch.float32)   # one allocation
     mean, var = out[:N], out[N:2 * N]
     sample = out[2 * N:3 * N] if want_sample else None
-    ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
+    if ws is None:
+        ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
         rc = _cabi.lib().gpblur_svgp_point_forward(
             _ptr(stage), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
@@ -462,11 +464,17 @@ class _PointFunction(torch.autograd.Function):
         nout = 3 if want_sample else 2
         out = torch.empty(H, nout * N, device=x2.device, dtype=torch.float32)
         stage = holder["stage"]
-        wss = []
-        for h in range(H):
-            _, _, _, ws = point_forward_raw(stage[h], x2, M, seed, offset + h * N, stream_id, want_sample, training,
-                                            out=out[h], offset_dev=offset_dev)
-            wss.append(ws)
+        # the H GPs of a multi-output layer are independent: their (persistent, one CTA per SM) kernels alternate
+        # between side streams so that each one starts in the tail of the previous one
+        wss = [torch.empty(workspace_bytes(N, D, M, training), device=x2.device, dtype=torch.uint8) for _ in range(H)]
+        fork = _Fork(x2.device, H)
+        try:
+            for h in range(H):
+                fork.enter(h)
+                point_forward_raw(stage[h], x2, M, seed, offset + h * N, stream_id, want_sample, training,
+                                  out=out[h], offset_dev=offset_dev, ws=wss[h])
+        finally:
+            fork.join()
         if training:
             ctx.save_for_backward(x2, out, *wss)
         ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout)
@@ -498,11 +506,16 @@ class _PointFunction(torch.autograd.Function):
         G = stage_grad_doubles(D, M)
         sgrad = torch.empty(H, G, device=dev, dtype=torch.float64)
         dx = torch.empty(H, N, D, device=dev, dtype=torch.float32) if need[0] else None
-        for h in range(H):
-            point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
-                               None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * N, stream_id,
-                               wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h],
-                               offset_dev=ctx.offset_dev)
+        fork = _Fork(dev, H)
+        try:
+            for h in range(H):
+                fork.enter(h)
+                point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
+                                   None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * N, stream_id,
+                                   wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h],
+                                   offset_dev=ctx.offset_dev)
+        finally:
+            fork.join()
         if dx is not None:
             dx = (dx.sum(0) if H > 1 else dx[0]).reshape(shape)
         return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None, None)

@@ -401,7 +401,7 @@ def test_anomaly_mode_and_concurrent_threads(cuda):
 
     def worker(k):
         try:
-            with gpcompat.num_likelihood_samples(1), torch.autograd.detect_anomaly(check_nan=True):
+            with gpcompat.num_likelihood_samples(1):
                 model = DeepGPp(D, 100 + k, num_inducing=M).to(cuda)
                 load_params(model, p)
                 for _ in range(3):
@@ -419,11 +419,17 @@ def test_anomaly_mode_and_concurrent_threads(cuda):
         except Exception as e:    # pragma: no cover
             errors.append(repr(e))
 
-    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    # anomaly mode is a process-global switch (the reference flips it at import): set it around the threads, not
+    # inside them, and restore it - a leaked anomaly mode would break CUDA-graph capture in later tests
+    torch.autograd.set_detect_anomaly(True, check_nan=True)
+    try:
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        torch.autograd.set_detect_anomaly(False)
     assert not errors, errors
     # identical parameters and inputs in every thread -> identical results (deterministic kernels)
     for k in range(1, 4):
