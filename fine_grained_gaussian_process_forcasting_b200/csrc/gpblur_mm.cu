@@ -610,7 +610,7 @@ struct SgReduceArgs {
   int ncpart;   // > 0: column sums of W come as [ncpart][MP] partials from the tensor-core W^T X kernel
 };
 
-__global__ void __launch_bounds__(kThreads) stage_grad_reduce_kernel(SgReduceArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) stage_grad_reduce_kernel(SgReduceArgs a) {   // latency-bound: occupancy matters
   const WsLayout& L = a.L;
   const int MP = L.MP, DP = L.DP;
   const float* Spart = ws_cptr<float>(a.ws, L.Spart);
