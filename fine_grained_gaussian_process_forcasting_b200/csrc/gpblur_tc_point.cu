@@ -12,6 +12,8 @@
 //   dx       : dx = (W Z~ - r x~) / ell + g_mu w as a third small GEMM (N = Dp) + the per-dimension reductions.
 // Operand tiles are produced by all 256 threads (coalesced 16-byte loads, TF32 hi/lo split, canonical K-major
 // no-swizzle UMMA layout), one elected thread issues the MMAs, tcgen05.commit -> mbarrier tracks completion.
+#include <cstdlib>
+
 #include "gpblur_tc.cuh"
 
 namespace gpblur {
@@ -38,6 +40,7 @@ struct TcPointArgs {
   uint32_t stream_id;
   int ntiles;
   int exp_mode;     // timing experiments only (GPBLUR_TC_EXP): 4 = skip the W / A chunk stores, 5 = skip chunk math
+  long long* trace; // optional event trace buffer (GPBLUR_TRACE_PTR = device address, debugging only)
   long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
 };
 
@@ -95,7 +98,7 @@ __device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st
 // The issuer: ONE thread.  `ntiles_mine` tiles, each `nslabs` table entries.
 template <int NB>
 __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
-                                         int ntiles_mine) {
+                                         int ntiles_mine, long long* trace = nullptr) {
   if (ntiles_mine <= 0 || nslabs <= 0) return;
   constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
   constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
@@ -125,8 +128,12 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
       const uint64_t dah0 = a_hi_desc[st], dal0 = a_lo_desc[st];
       const uint32_t tmem_d = tmem_base + d.tmem_off;
       const uint64_t bstep = (uint64_t)(2 * d.rows);                       // two k-chunks of rows * 16 B, >> 4
+      long long* tr = (trace && slab < 48) ? trace + slab * 6 : nullptr;
+      if (tr) tr[0] = clock64();
       tc::mbar_wait(&bars[4 + st], phase);        // A planes written
+      if (tr) tr[1] = clock64();
       tc::mbar_wait(&bars[2 + st], phase);        // B image landed
+      if (tr) tr[2] = clock64();
       tc::tc_fence_after();
       // TMA request for the next slab's B image into the other stage.  If that stage's last readers have already
       // retired (the usual case: the producers are slower than the tensor core), the request goes out BEFORE this
@@ -147,7 +154,9 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
         tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
         tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
       }
+      if (tr) tr[3] = clock64();
       tc::umma_commit(&bars[st]);
+      if (tr) tr[4] = clock64();
       uses[st] += 1;
       if (!requested) {                           // the other stage was still being read: wait, then request
         const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   const uint32_t tmem_d = tmem_slot;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (warp == kIssuerWarp) {
-    if (lane == 0) issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine);
+    if (lane == 0) issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
   } else {
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
@@ -888,14 +897,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(a.dx) & 15) == 0);
 
+  OpRegs<TNP> r0, r1, r2;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const long long n0 = (long long)tile * TNP;
-    auto load_w = [&](OpRegs<TNP>& regs, int sl) {
+    auto load_w_at = [&](OpRegs<TNP>& regs, long long nbase, int sl) {
       load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-        const long long gn = n0 + r;
+        const long long gn = nbase + r;
         return gn < N ? ldg4(Wg + (size_t)gn * MP + sl * KT + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       });
     };
+    auto load_w = [&](OpRegs<TNP>& regs, int sl) { load_w_at(regs, n0, sl); };
     // per-point scalars and the x rows of the first epilogue chunk: requested now, consumed after the GEMM
     const long long gn = n0 + row;
     const bool live = gn < N;
@@ -926,21 +937,29 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
     };
     float4 xq[8];
     if (has_cols) load_x_chunk(xq, DPT >= 64 ? half * (DPT / 2) : 0);
-    // W slabs are fetched three slabs ahead (rotating register sets) to keep enough bytes in flight per SM
-    OpRegs<TNP> r0, r1, r2;
+    // W slabs are fetched three slabs ahead (rotating register sets) to keep enough bytes in flight per SM; the
+    // first three of a tile are requested before the PREVIOUS tile's epilogue (see below)
     const int nsl = MP / KT;
     DSEG(0);
-    load_w(r0, 0);
-    if (1 < nsl) load_w(r1, 1);
-    if (2 < nsl) load_w(r2, 2);
+    if (tile == (int)blockIdx.x) {
+      load_w(r0, 0);
+      if (1 < nsl) load_w(r1, 1);
+      if (2 < nsl) load_w(r2, 2);
+    }
     for (int s = 0; s < nsl; s += 3) {
       float *a_hi, *a_lo;
+      long long* ptr = (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 255) && pipe.slab < 48)
+                           ? a.trace + 512 + (tid == 0 ? 0 : 256) + pipe.slab * 4 : nullptr;
+      if (ptr) ptr[0] = clock64();
       pipe.acquire(a_hi, a_lo);
+      if (ptr) ptr[1] = clock64();
       DSEG(1);
       store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+      if (ptr) ptr[2] = clock64();
       DSEG(2);
       if (s + 3 < nsl) load_w(r0, s + 3);
       pipe.commit();
+      if (ptr) ptr[3] = clock64();
       DSEG(3);
       if (s + 1 >= nsl) break;
       pipe.acquire(a_hi, a_lo);
@@ -958,6 +977,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
       if (s + 5 < nsl) load_w(r2, s + 5);
       pipe.commit();
       DSEG(3);
+    }
+    if (tile + (int)gridDim.x < a.ntiles) {         // next tile's first W slabs fly during this tile's epilogue
+      const long long n1 = n0 + (long long)gridDim.x * TNP;
+      load_w_at(r0, n1, 0);
+      if (1 < nsl) load_w_at(r1, n1, 1);
+      if (2 < nsl) load_w_at(r2, n1, 2);
     }
     pipe.drain();
     DSEG(4);
@@ -1146,6 +1171,10 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
   a.exp_mode = tile_override("GPBLUR_TC_EXP");
+  {
+    const char* tp = getenv("GPBLUR_TRACE_PTR");
+    a.trace = tp ? reinterpret_cast<long long*>(strtoull(tp, nullptr, 0)) : nullptr;
+  }
   const int grid = tc_grid(L);
   {
     ProfScope ps(ST_POINT_BWD, st);
