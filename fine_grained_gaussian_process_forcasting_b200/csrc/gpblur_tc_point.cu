@@ -767,6 +767,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           if (tid < BW) { zn_s[tid] = znc_g[p * BW + tid]; beta_s[tid] = beta_g[p * BW + tid]; }
           prod_sync();
         }
+        // the first two saved-A slabs of this block are requested BEFORE phase A: their HBM latency hides behind it
+        OpRegs<TNP> r0, r1;
+        const int s_lo = p * SPB;
+        load_a(r0, NSL - 1);
+        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
         phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
         if (p == 0 && more_tiles) {
           const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
@@ -778,8 +783,6 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
         // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
         // flight cannot cover the HBM latency (Little's law), three can
-        OpRegs<TNP> r0, r1;
-        const int s_lo = p * SPB;
         // after the acquire of slab s, slab s + 2 has retired: if it lies in block p, its chunk (and S, complete
         // since the first T slab was issued behind it) is final
         auto interleaved = [&](int s) {
@@ -788,8 +791,6 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           if (s + 2 <= NSL - 1 && c < SPB) { tc::tc_fence_after(); epi_chunk(p, c); }
           BSEG(5);                                    // interleaved epilogue chunk
         };
-        load_a(r0, NSL - 1);
-        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
         for (int s = NSL - 1; s >= s_lo; s -= 2) {
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
