@@ -71,6 +71,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // every bulk store committed by this thread has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, which also tells the compiler that the result is warp-uniform (uniform registers, no
+// per-thread -> uniform conversion loops around the tcgen05 instructions)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uniform_u64(uint64_t v) {
+  return ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)v, 0);
+}
+
 // ---- fences ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -95,17 +95,25 @@ __device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st
   tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
 }
 
-// The issuer: ONE thread.  `ntiles_mine` tiles, each `nslabs` table entries.
+// The issuer: the whole warp 8 walks the table with WARP-UNIFORM values (lane-0 broadcasts of the table entries), one
+// elected lane executes the tcgen05 / TMA / commit instructions.  Uniform operands live in uniform registers: a
+// single thread with per-thread registers costs ~100 cycles per MMA in register -> uniform-register conversion loops
+// (measured with scripts/dx_trace.py), more than the execution time of an N <= 128 MMA.
+// `ntiles_mine` tiles, each `nslabs` table entries.
 template <int NB>
 __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
                                          int ntiles_mine, long long* trace = nullptr) {
   if (ntiles_mine <= 0 || nslabs <= 0) return;
   constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
   constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
+  const uint32_t base_addr = tc::uniform_u32(tc::smem_u32(base));
+  tmem_base = tc::uniform_u32(tmem_base);
+  nslabs = (int)tc::uniform_u32((uint32_t)nslabs);
+  ntiles_mine = (int)tc::uniform_u32((uint32_t)ntiles_mine);
   uint64_t a_hi_desc[2], a_lo_desc[2], b_hi_base[2], b_lo_base[2];
 #pragma unroll
   for (int st = 0; st < 2; ++st) {
-    const uint32_t a_hi = tc::smem_u32(base + st * Stage<NB>::FLOATS);
+    const uint32_t a_hi = base_addr + st * Stage<NB>::FLOATS * 4;
     const uint32_t a_lo = a_hi + Stage<NB>::A_PLANE * 4;
     const uint32_t b_hi = a_lo + Stage<NB>::A_PLANE * 4;
     const uint32_t b_lo = b_hi + Stage<NB>::B_PLANE * 4;
@@ -114,21 +122,28 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
     b_hi_base[st] = kDescHi | (uint64_t)(b_hi >> 4);
     b_lo_base[st] = kDescHi | (uint64_t)(b_lo >> 4);
   }
+  auto request_b = [&](int st, int entry) {
+    const float* img = reinterpret_cast<const float*>(tc::uniform_u64(reinterpret_cast<uint64_t>(tab[entry].img)));
+    const int rows = (int)tc::uniform_u32((uint32_t)tab[entry].rows);
+    if (tc::elect_one()) issue_bulk_b<NB>(base, bars, st, img, rows);
+    __syncwarp();
+  };
   uint32_t uses[2] = {0, 0};
-  issue_bulk_b<NB>(base, bars, 0, tab[0].img, tab[0].rows);
+  request_b(0, 0);
   int slab = 0;
   for (int t = 0; t < ntiles_mine; ++t) {
     for (int i = 0; i < nslabs; ++i, ++slab) {
       const int st = slab & 1;
       const uint32_t phase = uses[st] & 1;
-      const SlabDesc d = tab[i];
-      const uint32_t idesc = tc::make_idesc_tf32(TNP, d.rows);
-      const uint64_t dbh0 = b_hi_base[st] | ((uint64_t)d.rows << 16);      // LBO = rows * 16 B
-      const uint64_t dbl0 = b_lo_base[st] | ((uint64_t)d.rows << 16);
+      const uint32_t rows = tc::uniform_u32((uint32_t)tab[i].rows);
+      const uint32_t tmem_d = tmem_base + tc::uniform_u32(tab[i].tmem_off);
+      const uint32_t first = tc::uniform_u32((uint32_t)tab[i].first);
+      const uint32_t idesc = tc::make_idesc_tf32(TNP, (int)rows);
+      const uint64_t dbh0 = b_hi_base[st] | ((uint64_t)rows << 16);        // LBO = rows * 16 B
+      const uint64_t dbl0 = b_lo_base[st] | ((uint64_t)rows << 16);
       const uint64_t dah0 = a_hi_desc[st], dal0 = a_lo_desc[st];
-      const uint32_t tmem_d = tmem_base + d.tmem_off;
-      const uint64_t bstep = (uint64_t)(2 * d.rows);                       // two k-chunks of rows * 16 B, >> 4
-      long long* tr = (trace && slab < 48) ? trace + slab * 6 : nullptr;
+      const uint64_t bstep = (uint64_t)(2 * rows);                         // two k-chunks of rows * 16 B, >> 4
+      long long* tr = (trace && slab < 48 && (threadIdx.x & 31) == 0) ? trace + slab * 6 : nullptr;
       if (tr) tr[0] = clock64();
       tc::mbar_wait(&bars[4 + st], phase);        // A planes written
       if (tr) tr[1] = clock64();
@@ -140,28 +155,33 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
       // slab's MMAs are issued, so the L2 round trip overlaps the issue time instead of following it.
       const bool more = (i + 1 < nslabs) || (t + 1 < ntiles_mine);
       const int nst = st ^ 1;
+      const int nxt = (i + 1 < nslabs) ? i + 1 : 0;
       bool requested = !more;
-      if (more && (uses[nst] == 0 || tc::mbar_test(&bars[nst], (uses[nst] - 1) & 1))) {
-        const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
-        issue_bulk_b<NB>(base, bars, nst, nx.img, nx.rows);
-        requested = true;
+      if (more) {
+        const uint32_t freed = uses[nst] == 0 ? 1u : tc::uniform_u32(tc::mbar_test(&bars[nst], (uses[nst] - 1) & 1) ? 1u : 0u);
+        if (freed) {
+          request_b(nst, nxt);
+          requested = true;
+        }
       }
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int j = 0; j < KT / 8; ++j) {
-        const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
-        const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
-        tc::umma_tf32(tmem_d, dal, dbh, idesc, (d.first && j == 0) ? 0u : 1u);   // small cross terms first
-        tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-        tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        for (int j = 0; j < KT / 8; ++j) {
+          const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
+          const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
+          tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
+          tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+          tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        }
+        tc::umma_commit(&bars[st]);
       }
+      __syncwarp();
       if (tr) tr[3] = clock64();
-      tc::umma_commit(&bars[st]);
       if (tr) tr[4] = clock64();
       uses[st] += 1;
       if (!requested) {                           // the other stage was still being read: wait, then request
-        const SlabDesc& nx = tab[(i + 1 < nslabs) ? i + 1 : 0];
         if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
-        issue_bulk_b<NB>(base, bars, nst, nx.img, nx.rows);
+        request_b(nst, nxt);
       }
     }
   }
@@ -514,7 +534,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
 
   if (warp == kIssuerWarp) {
     // ---------------- issuer warp: one thread drives the TMA requests and the tensor core ----------------
-    if (lane == 0) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
+    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
   } else {
     // ---------------- producer / epilogue warps ----------------
     Pipe<BW> pipe;
@@ -691,7 +711,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == kIssuerWarp) {
-    if (lane == 0) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
+    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
   } else {
     Pipe<BW> pipe;
     pipe.init(stage_base, bars);
@@ -880,7 +900,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   const uint32_t tmem_d = tmem_slot;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (warp == kIssuerWarp) {
-    if (lane == 0) issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
+    issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
   } else {
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
