@@ -13,6 +13,12 @@ namespace gpblur {
 namespace {
 
 constexpr int KT = 32;   // reduction rows per pipeline slab (4 UMMA k-steps)
+constexpr int kIssuerWarp = kThreads / 32;        // warp 8: dedicated MMA issuer
+constexpr int kBlockThreads = kThreads + 32;
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
 
 struct TcReduceArgs {
   const float* U;   // [N][ldu]   A-operand source (rows of the output = columns p of U)
@@ -34,7 +40,7 @@ struct TcSmem {
 };
 
 template <int TQ, bool GRAM>
-__global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArgs a) {
   using S = TcSmem<TQ>;
   constexpr int BG0 = kThreads / TQ > 0 ? kThreads / TQ : 1;
   constexpr int BG = BG0 > KT / 4 ? KT / 4 : BG0;             // thread groups along the B chunks (1, 2, 4, 8)
@@ -42,7 +48,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
   constexpr uint32_t TMEM_COLS = TQ < 32 ? 32 : TQ;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];      // [0..1] mma_done (tcgen05.commit), [2..3] a_ready (256 producers)
   __shared__ uint32_t tmem_slot;
   __shared__ float scs[2][KT], gms[2][KT];
   __shared__ float ured[2][128];
@@ -61,6 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], kThreads);
+    tc::mbar_init(&bars[3], kThreads);
     tc::fence_barrier_init();
   }
   tc::tc_fence_before();
@@ -69,127 +77,143 @@ __global__ void __launch_bounds__(kThreads, 1) tc_reduce_kernel(TcReduceArgs a) 
   const uint32_t tmem_d = tmem_slot;
   constexpr uint32_t idesc = tc::make_idesc_tf32(128, TQ);
 
-  // ---- loader thread mapping ----
-  const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk parity (chunks acg, acg+2, acg+4, acg+6)
-  const int bq = tid % TQ, bcg = (tid / TQ) % BG;      // B: row, chunk group
-  float4 areg[4], breg[BCH];
-  float usum = 0.f;
-
-  auto prefetch = [&](int s) {
-    const long long n0 = r0 + (long long)s * KT;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = acg + 2 * i;
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long long n = n0 + 4 * c + e;
-        v[e] = (n < r1) ? a.U[(size_t)n * a.ldu + p0 + ar] : 0.f;
+  if (warp == kIssuerWarp) {
+    // ---------------- issuer warp: one thread fires the MMAs as soon as a slab's operands are published ----------------
+    if (lane == 0) {
+      uint32_t iuses[2] = {0, 0};
+      for (int s = 0; s < nsl; ++s) {
+        const int st = s & 1;
+        float* a_hi = stage_base + st * S::STAGE;
+        float* a_lo = a_hi + S::A_PLANE;
+        float* b_hi = a_lo + S::A_PLANE;
+        float* b_lo = b_hi + S::B_PLANE;
+        tc::mbar_wait(&bars[2 + st], iuses[st] & 1);
+        tc::tc_fence_after();
+        tc::issue_slab_3xtf32<KT, TQ>(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, s == 0);
+        tc::umma_commit(&bars[st]);
+        iuses[st] += 1;
       }
-      areg[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    if (TQ >= kThreads || tid < TQ * BG) {
-#pragma unroll
-      for (int i = 0; i < BCH; ++i) {
-        const int c = bcg + BG * i;
+  } else {
+    // ---- loader thread mapping ----
+    const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk parity (chunks acg, acg+2, acg+4, acg+6)
+    const int bq = tid % TQ, bcg = (tid / TQ) % BG;      // B: row, chunk group
+    float4 areg[4], breg[BCH];
+    float usum = 0.f;
+
+    auto prefetch = [&](int s) {
+      const long long n0 = r0 + (long long)s * KT;
+  #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = acg + 2 * i;
         float v[4];
-#pragma unroll
+  #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const long long n = n0 + 4 * c + e;
-          v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
+          v[e] = (n < r1) ? a.U[(size_t)n * a.ldu + p0 + ar] : 0.f;
         }
-        breg[i] = make_float4(v[0], v[1], v[2], v[3]);
+        areg[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
-    }
-  };
-  // per-row scales of slab s go through shared memory; they are staged one iteration ahead, BEFORE that
-  // iteration's __syncthreads, so the barrier orders the write against the reads of the next iteration
-  auto stage_scales = [&](int s) {
-    if (tid < KT) {
-      const long long n = r0 + (long long)s * KT + tid;
-      scs[s & 1][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
-      gms[s & 1][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
-    }
-  };
+      if (TQ >= kThreads || tid < TQ * BG) {
+  #pragma unroll
+        for (int i = 0; i < BCH; ++i) {
+          const int c = bcg + BG * i;
+          float v[4];
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const long long n = n0 + 4 * c + e;
+            v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
+          }
+          breg[i] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    };
+    // per-row scales of slab s go through shared memory; they are staged one iteration ahead, BEFORE that
+    // iteration's __syncthreads, so the barrier orders the write against the reads of the next iteration
+    auto stage_scales = [&](int s) {
+      if (tid < KT) {
+        const long long n = r0 + (long long)s * KT + tid;
+        scs[s & 1][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
+        gms[s & 1][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
+      }
+    };
 
-  uint32_t uses[2] = {0, 0};
-  if (nsl > 0) { prefetch(0); stage_scales(0); }
-  __syncthreads();
-  for (int s = 0; s < nsl; ++s) {
-    const int st = s & 1;
-    if (s + 1 < nsl) stage_scales(s + 1);
-    float* a_hi = stage_base + st * S::STAGE;
-    float* a_lo = a_hi + S::A_PLANE;
-    float* b_hi = a_lo + S::A_PLANE;
-    float* b_lo = b_hi + S::B_PLANE;
-    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);   // MMAs of slab s-2 are done with this stage
-    // ---- transform: split into TF32 hi / lo planes in the UMMA layout ----
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = acg + 2 * i;
-      tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), areg[i]);
-      {
-        usum = fmaf(gms[st][4 * c + 0], areg[i].x, usum);
-        usum = fmaf(gms[st][4 * c + 1], areg[i].y, usum);
-        usum = fmaf(gms[st][4 * c + 2], areg[i].z, usum);
-        usum = fmaf(gms[st][4 * c + 3], areg[i].w, usum);
+    uint32_t uses[2] = {0, 0};
+    if (nsl > 0) { prefetch(0); stage_scales(0); }
+    prod_sync();
+    for (int s = 0; s < nsl; ++s) {
+      const int st = s & 1;
+      if (s + 1 < nsl) stage_scales(s + 1);
+      float* a_hi = stage_base + st * S::STAGE;
+      float* a_lo = a_hi + S::A_PLANE;
+      float* b_hi = a_lo + S::A_PLANE;
+      float* b_lo = b_hi + S::B_PLANE;
+      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);   // MMAs of slab s-2 are done with this stage
+      // ---- transform: split into TF32 hi / lo planes in the UMMA layout ----
+  #pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = acg + 2 * i;
+        tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), areg[i]);
+        {
+          usum = fmaf(gms[st][4 * c + 0], areg[i].x, usum);
+          usum = fmaf(gms[st][4 * c + 1], areg[i].y, usum);
+          usum = fmaf(gms[st][4 * c + 2], areg[i].z, usum);
+          usum = fmaf(gms[st][4 * c + 3], areg[i].w, usum);
+        }
       }
-    }
-    if (TQ >= kThreads || tid < TQ * BG) {
-#pragma unroll
-      for (int i = 0; i < BCH; ++i) {
-        const int c = bcg + BG * i;
-        float4 v = breg[i];
-        v.x *= scs[st][4 * c + 0]; v.y *= scs[st][4 * c + 1];
-        v.z *= scs[st][4 * c + 2]; v.w *= scs[st][4 * c + 3];
-        tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
+      if (TQ >= kThreads || tid < TQ * BG) {
+  #pragma unroll
+        for (int i = 0; i < BCH; ++i) {
+          const int c = bcg + BG * i;
+          float4 v = breg[i];
+          v.x *= scs[st][4 * c + 0]; v.y *= scs[st][4 * c + 1];
+          v.z *= scs[st][4 * c + 2]; v.w *= scs[st][4 * c + 3];
+          tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
+        }
       }
+      tc::tc_fence_before();
+      tc::fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&bars[2 + st]);  // the issuer warp fires the MMAs once all 256 producers have arrived
+      uses[st] += 1;
+      if (s + 1 < nsl) prefetch(s + 1);   // global loads of the next slab fly while the tensor core works
+      prod_sync();                 // orders the staged scales of slab s + 1 (and the reuse of this slab's) among producers
     }
-    tc::fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
+
+    // ---- epilogue ----
+    float* Cs = a.C + (size_t)blockIdx.y * a.P * a.ldc;
+    const int row = (warp & 3) * 32 + lane;
+    constexpr int CHUNKS = TQ / 32;                 // 32-column chunks of the tile
+    constexpr int CPW = CHUNKS >= 2 ? CHUNKS / 2 : 1;   // chunks per warp (two column halves when possible)
+    const int c_begin = CHUNKS >= 2 ? (warp >> 2) * CPW : 0;
+    const bool active = CHUNKS >= 2 || warp < 4;
+    if (nsl > 0) {
+      const int last = (nsl - 1) & 1;
+      tc::mbar_wait(&bars[last], (uses[last] - 1) & 1);
       tc::tc_fence_after();
-      tc::issue_slab_3xtf32<KT, TQ>(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, s == 0);
-      tc::umma_commit(&bars[st]);
     }
-    uses[st] += 1;
-    if (s + 1 < nsl) prefetch(s + 1);   // global loads of the next slab fly while the tensor core works
-  }
-
-  // ---- epilogue ----
-  float* Cs = a.C + (size_t)blockIdx.y * a.P * a.ldc;
-  const int row = (warp & 3) * 32 + lane;
-  constexpr int CHUNKS = TQ / 32;                 // 32-column chunks of the tile
-  constexpr int CPW = CHUNKS >= 2 ? CHUNKS / 2 : 1;   // chunks per warp (two column halves when possible)
-  const int c_begin = CHUNKS >= 2 ? (warp >> 2) * CPW : 0;
-  const bool active = CHUNKS >= 2 || warp < 4;
-  if (nsl > 0) {
-    const int last = (nsl - 1) & 1;
-    tc::mbar_wait(&bars[last], (uses[last] - 1) & 1);
-    tc::tc_fence_after();
-  }
-  if (active) {
-#pragma unroll
-    for (int cc = 0; cc < CPW; ++cc) {
-      const int col = (c_begin + cc) * 32;
-      float v[32];
-      if (nsl > 0) {
-        tc::tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    if (active) {
+  #pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int col = (c_begin + cc) * 32;
+        float v[32];
+        if (nsl > 0) {
+          tc::tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, v);
+        } else {
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        float* dst = Cs + (size_t)(p0 + row) * a.ldc + q0 + col;
+  #pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (q0 + col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-      float* dst = Cs + (size_t)(p0 + row) * a.ldc + q0 + col;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (q0 + col + i < a.ldc) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
-  }
-  if (a.uvec && blockIdx.z == 0) {
-    ured[acg][ar] = usum;
-    __syncthreads();
-    if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
-  }
+    if (a.uvec && blockIdx.z == 0) {
+      ured[acg][ar] = usum;
+      prod_sync();
+      if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
+    }
+  }   // producer warps
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_d, TMEM_COLS);
@@ -204,7 +228,7 @@ int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t
     configured = true;
   }
   ProfScope ps(GRAM ? ST_GRAM : ST_WX, st);
-  tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits, qtiles), kThreads, smem, st>>>(a);
+  tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits, qtiles), kBlockThreads, smem, st>>>(a);
   note_launch();
   return check_launch("tc_reduce");
 }
