@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[4];      // [0..1] mma_done (tcgen05.commit), [2..3] a_ready (256 producers)
   __shared__ uint32_t tmem_slot;
-  __shared__ float scs[2][KT], gms[2][KT];
+  __shared__ float scs[4][KT], gms[4][KT];
   __shared__ float ured[2][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,10 +98,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     // ---- loader thread mapping ----
     const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk parity (chunks acg, acg+2, acg+4, acg+6)
     const int bq = tid % TQ, bcg = (tid / TQ) % BG;      // B: row, chunk group
-    float4 areg[4], breg[BCH];
+    struct Regs { float4 a[4]; float4 b[BCH]; };
     float usum = 0.f;
 
-    auto prefetch = [&](int s) {
+    // the gathered operands of TWO slabs are in flight per thread (two register sets): with one, the global-load
+    // latency of slab s + 1 was exposed between the split / store of consecutive slabs
+    auto prefetch = [&](Regs& rg, int s) {
       const long long n0 = r0 + (long long)s * KT;
   #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
           const long long n = n0 + 4 * c + e;
           v[e] = (n < r1) ? a.U[(size_t)n * a.ldu + p0 + ar] : 0.f;
         }
-        areg[i] = make_float4(v[0], v[1], v[2], v[3]);
+        rg.a[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
       if (TQ >= kThreads || tid < TQ * BG) {
   #pragma unroll
@@ -124,26 +126,23 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
             const long long n = n0 + 4 * c + e;
             v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
           }
-          breg[i] = make_float4(v[0], v[1], v[2], v[3]);
+          rg.b[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     };
-    // per-row scales of slab s go through shared memory; they are staged one iteration ahead, BEFORE that
-    // iteration's __syncthreads, so the barrier orders the write against the reads of the next iteration
+    // per-row scales of slab s go through shared memory (4 buffers: staged two slabs ahead, before the producer
+    // barrier of the iteration, which orders the write against the reads two iterations later)
     auto stage_scales = [&](int s) {
       if (tid < KT) {
         const long long n = r0 + (long long)s * KT + tid;
-        scs[s & 1][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
-        gms[s & 1][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
+        scs[s & 3][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
+        gms[s & 3][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
       }
     };
 
     uint32_t uses[2] = {0, 0};
-    if (nsl > 0) { prefetch(0); stage_scales(0); }
-    prod_sync();
-    for (int s = 0; s < nsl; ++s) {
-      const int st = s & 1;
-      if (s + 1 < nsl) stage_scales(s + 1);
+    auto produce = [&](const Regs& rg, int s) {
+      const int st = s & 1, sb = s & 3;
       float* a_hi = stage_base + st * S::STAGE;
       float* a_lo = a_hi + S::A_PLANE;
       float* b_hi = a_lo + S::A_PLANE;
@@ -153,21 +152,21 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = acg + 2 * i;
-        tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), areg[i]);
+        tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), rg.a[i]);
         {
-          usum = fmaf(gms[st][4 * c + 0], areg[i].x, usum);
-          usum = fmaf(gms[st][4 * c + 1], areg[i].y, usum);
-          usum = fmaf(gms[st][4 * c + 2], areg[i].z, usum);
-          usum = fmaf(gms[st][4 * c + 3], areg[i].w, usum);
+          usum = fmaf(gms[sb][4 * c + 0], rg.a[i].x, usum);
+          usum = fmaf(gms[sb][4 * c + 1], rg.a[i].y, usum);
+          usum = fmaf(gms[sb][4 * c + 2], rg.a[i].z, usum);
+          usum = fmaf(gms[sb][4 * c + 3], rg.a[i].w, usum);
         }
       }
       if (TQ >= kThreads || tid < TQ * BG) {
   #pragma unroll
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
-          float4 v = breg[i];
-          v.x *= scs[st][4 * c + 0]; v.y *= scs[st][4 * c + 1];
-          v.z *= scs[st][4 * c + 2]; v.w *= scs[st][4 * c + 3];
+          float4 v = rg.b[i];
+          v.x *= scs[sb][4 * c + 0]; v.y *= scs[sb][4 * c + 1];
+          v.z *= scs[sb][4 * c + 2]; v.w *= scs[sb][4 * c + 3];
           tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
         }
       }
@@ -175,8 +174,22 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
       tc::fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&bars[2 + st]);  // the issuer warp fires the MMAs once all 256 producers have arrived
       uses[st] += 1;
-      if (s + 1 < nsl) prefetch(s + 1);   // global loads of the next slab fly while the tensor core works
-      prod_sync();                 // orders the staged scales of slab s + 1 (and the reuse of this slab's) among producers
+    };
+
+    Regs rg0, rg1;
+    if (0 < nsl) { prefetch(rg0, 0); stage_scales(0); }
+    if (1 < nsl) { prefetch(rg1, 1); stage_scales(1); }
+    prod_sync();
+    for (int s = 0; s < nsl; s += 2) {
+      if (s + 2 < nsl) stage_scales(s + 2);
+      produce(rg0, s);
+      if (s + 2 < nsl) prefetch(rg0, s + 2);
+      prod_sync();                 // orders the staged scales (and the reuse of their buffers) among producers
+      if (s + 1 >= nsl) break;
+      if (s + 3 < nsl) stage_scales(s + 3);
+      produce(rg1, s + 1);
+      if (s + 3 < nsl) prefetch(rg1, s + 3);
+      prod_sync();
     }
 
     // ---- epilogue ----
