@@ -146,6 +146,27 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                : "memory");
 }
 
+// ---- A operand in tensor memory (TS form) ---------------------------------------------------------------
+// For kind::tf32 with M = 128 the A tile lives at TMEM lane = row, column = base + k (one fp32 cell per element;
+// verified by scripts/micro/umma_ts.cu).  A thread that owns row `lane` of its warp's lane quadrant writes 4
+// consecutive k-values with one tcgen05.st; the MMA then reads A from TMEM and only B from shared memory.
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+               "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------------
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |

@@ -33,9 +33,8 @@ struct TcReduceArgs {
 
 template <int TQ>
 struct TcSmem {
-  static constexpr int A_PLANE = (KT / 4) * 128 * 4;   // floats
-  static constexpr int B_PLANE = (KT / 4) * TQ * 4;
-  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int B_PLANE = (KT / 4) * TQ * 4;    // floats; the A operand lives in tensor memory
+  static constexpr int STAGE = 2 * B_PLANE;
   static constexpr size_t bytes = (size_t)2 * STAGE * 4 + 1024;
 };
 
@@ -45,7 +44,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   constexpr int BG0 = kThreads / TQ > 0 ? kThreads / TQ : 1;
   constexpr int BG = BG0 > KT / 4 ? KT / 4 : BG0;             // thread groups along the B chunks (1, 2, 4, 8)
   constexpr int BCH = (KT / 4) / BG;                          // B chunks per thread
-  constexpr uint32_t TMEM_COLS = TQ < 32 ? 32 : TQ;
+  constexpr uint32_t D_COLS = TQ < 32 ? 32 : TQ;
+  constexpr uint32_t TMEM_COLS = D_COLS + 128 <= 256 ? 256 : 512;   // + two A stages of 64 columns (hi 32 | lo 32)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[4];      // [0..1] mma_done (tcgen05.commit), [2..3] a_ready (256 producers)
@@ -83,13 +83,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
       uint32_t iuses[2] = {0, 0};
       for (int s = 0; s < nsl; ++s) {
         const int st = s & 1;
-        float* a_hi = stage_base + st * S::STAGE;
-        float* a_lo = a_hi + S::A_PLANE;
-        float* b_hi = a_lo + S::A_PLANE;
+        float* b_hi = stage_base + st * S::STAGE;
         float* b_lo = b_hi + S::B_PLANE;
+        const uint32_t a_hi_t = tmem_d + D_COLS + st * 64, a_lo_t = a_hi_t + 32;
         tc::mbar_wait(&bars[2 + st], iuses[st] & 1);
         tc::tc_fence_after();
-        tc::issue_slab_3xtf32<KT, TQ>(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, s == 0);
+        const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+#pragma unroll
+        for (int j = 0; j < KT / 8; ++j) {
+          const uint64_t dbh = tc::make_smem_desc(bh + 2 * j * TQ * 16, TQ * 16, 128);
+          const uint64_t dbl = tc::make_smem_desc(bl + 2 * j * TQ * 16, TQ * 16, 128);
+          tc::umma_tf32_ts(tmem_d, a_lo_t + 8 * j, dbh, idesc, (s == 0 && j == 0) ? 0u : 1u);   // small cross terms first
+          tc::umma_tf32_ts(tmem_d, a_hi_t + 8 * j, dbl, idesc, 1u);
+          tc::umma_tf32_ts(tmem_d, a_hi_t + 8 * j, dbh, idesc, 1u);
+        }
         tc::umma_commit(&bars[st]);
         iuses[st] += 1;
       }
@@ -143,16 +150,22 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     uint32_t uses[2] = {0, 0};
     auto produce = [&](const Regs& rg, int s) {
       const int st = s & 1, sb = s & 3;
-      float* a_hi = stage_base + st * S::STAGE;
-      float* a_lo = a_hi + S::A_PLANE;
-      float* b_hi = a_lo + S::A_PLANE;
+      float* b_hi = stage_base + st * S::STAGE;
       float* b_lo = b_hi + S::B_PLANE;
-      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);   // MMAs of slab s-2 are done with this stage
-      // ---- transform: split into TF32 hi / lo planes in the UMMA layout ----
+      if (uses[st] > 0) {                                               // MMAs of slab s-2 are done with this stage
+        tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+        tc::tc_fence_after();
+      }
+      // ---- A operand: this thread owns output row `ar` = TMEM lane; its k-chunks go straight to tensor memory ----
+      const uint32_t a_hi_t = tmem_d + D_COLS + st * 64 + ((uint32_t)((warp & 3) * 32) << 16), a_lo_t = a_hi_t + 32;
   #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = acg + 2 * i;
-        tc::store_split(a_hi, a_lo, tc::op_off<128>(ar, c), rg.a[i]);
+        float4 h, l;
+        tc::split_tf32(rg.a[i].x, h.x, l.x); tc::split_tf32(rg.a[i].y, h.y, l.y);
+        tc::split_tf32(rg.a[i].z, h.z, l.z); tc::split_tf32(rg.a[i].w, h.w, l.w);
+        tc::tmem_st4(a_hi_t + 4 * c, h);
+        tc::tmem_st4(a_lo_t + 4 * c, l);
         {
           usum = fmaf(gms[sb][4 * c + 0], rg.a[i].x, usum);
           usum = fmaf(gms[sb][4 * c + 1], rg.a[i].y, usum);
@@ -170,8 +183,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
           tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
         }
       }
+      tc::tmem_st_wait();          // the tensor-memory stores of this thread have landed
       tc::tc_fence_before();
-      tc::fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+      tc::fence_async_smem();      // generic-proxy writes of B -> visible to the tensor core (async proxy)
       mbar_arrive(&bars[2 + st]);  // the issuer warp fires the MMAs once all 256 producers have arrived
       uses[st] += 1;
     };
