@@ -13,9 +13,12 @@ namespace gpblur {
 namespace {
 
 constexpr int KT = 32;   // reduction rows per pipeline slab (4 UMMA k-steps)
-constexpr int kIssuerWarp = kThreads / 32;        // warp 8: dedicated MMA issuer
-constexpr int kBlockThreads = kThreads + 32;
-__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 16 producer warps: the producers are bound by instruction latency (gather, TF32 split, stores), not by bandwidth,
+// and with the A operand in tensor memory a thread needs few enough registers for 4 warps per scheduler
+constexpr int kProd = 512;
+constexpr int kIssuerWarp = kProd / 32;           // warp 16: dedicated MMA issuer
+constexpr int kBlockThreads = kProd + 32;
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
@@ -41,7 +44,7 @@ struct TcSmem {
 template <int TQ, bool GRAM>
 __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArgs a) {
   using S = TcSmem<TQ>;
-  constexpr int BG0 = kThreads / TQ > 0 ? kThreads / TQ : 1;
+  constexpr int BG0 = kProd / TQ > 0 ? kProd / TQ : 1;
   constexpr int BG = BG0 > KT / 4 ? KT / 4 : BG0;             // thread groups along the B chunks (1, 2, 4, 8)
   constexpr int BCH = (KT / 4) / BG;                          // B chunks per thread
   constexpr uint32_t D_COLS = TQ < 32 ? 32 : TQ;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   __shared__ __align__(8) uint64_t bars[4];      // [0..1] mma_done (tcgen05.commit), [2..3] a_ready (256 producers)
   __shared__ uint32_t tmem_slot;
   __shared__ float scs[4][KT], gms[4][KT];
-  __shared__ float ured[2][128];
+  __shared__ float ured[4][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int p0 = blockIdx.x * 128;
@@ -67,8 +70,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], kThreads);
-    tc::mbar_init(&bars[3], kThreads);
+    tc::mbar_init(&bars[2], kProd);
+    tc::mbar_init(&bars[3], kProd);
     tc::fence_barrier_init();
   }
   tc::tc_fence_before();
@@ -103,9 +106,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     }
   } else {
     // ---- loader thread mapping ----
-    const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk parity (chunks acg, acg+2, acg+4, acg+6)
+    const int ar = tid & 127, acg = tid >> 7;            // A: row, chunk group (chunks acg, acg + 4)
     const int bq = tid % TQ, bcg = (tid / TQ) % BG;      // B: row, chunk group
-    struct Regs { float4 a[4]; float4 b[BCH]; };
+    struct Regs { float4 a[2]; float4 b[BCH]; };
     float usum = 0.f;
 
     // the gathered operands of TWO slabs are in flight per thread (two register sets): with one, the global-load
@@ -113,8 +116,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     auto prefetch = [&](Regs& rg, int s) {
       const long long n0 = r0 + (long long)s * KT;
   #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = acg + 2 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int c = acg + 4 * i;
         float v[4];
   #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
         }
         rg.a[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
-      if (TQ >= kThreads || tid < TQ * BG) {
+      if (TQ >= kProd || tid < TQ * BG) {
   #pragma unroll
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
       // ---- A operand: this thread owns output row `ar` = TMEM lane; its k-chunks go straight to tensor memory ----
       const uint32_t a_hi_t = tmem_d + D_COLS + st * 64 + ((uint32_t)((warp & 3) * 32) << 16), a_lo_t = a_hi_t + 32;
   #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = acg + 2 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int c = acg + 4 * i;
         float4 h, l;
         tc::split_tf32(rg.a[i].x, h.x, l.x); tc::split_tf32(rg.a[i].y, h.y, l.y);
         tc::split_tf32(rg.a[i].z, h.z, l.z); tc::split_tf32(rg.a[i].w, h.w, l.w);
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
           usum = fmaf(gms[sb][4 * c + 3], rg.a[i].w, usum);
         }
       }
-      if (TQ >= kThreads || tid < TQ * BG) {
+      if (TQ >= kProd || tid < TQ * BG) {
   #pragma unroll
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     constexpr int CHUNKS = TQ / 32;                 // 32-column chunks of the tile
     constexpr int CPW = CHUNKS >= 2 ? CHUNKS / 2 : 1;   // chunks per warp (two column halves when possible)
     const int c_begin = CHUNKS >= 2 ? (warp >> 2) * CPW : 0;
-    const bool active = CHUNKS >= 2 || warp < 4;
+    const bool active = warp < 8 && (CHUNKS >= 2 || warp < 4);
     if (nsl > 0) {
       const int last = (nsl - 1) & 1;
       tc::mbar_wait(&bars[last], (uses[last] - 1) & 1);
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     if (a.uvec && blockIdx.z == 0) {
       ured[acg][ar] = usum;
       prod_sync();
-      if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = ured[0][tid] + ured[1][tid];
+      if (tid < 128) a.uvec[(size_t)blockIdx.y * a.P + p0 + tid] = (ured[0][tid] + ured[1][tid]) + (ured[2][tid] + ured[3][tid]);
     }
   }   // producer warps
   tc::tc_fence_before();
