@@ -10,8 +10,10 @@
 //   backward : S again, T = a (diag(c) Linv) (slabs in decreasing order so the first MMA initialises every column)
 //              -> kbar = g_mu beta + 2 g_var T, W = kbar o k, r = rowsum(W); W and r go to HBM once.
 //   dx       : dx = (W Z~ - r x~) / ell + g_mu w as a third small GEMM (N = Dp) + the per-dimension reductions.
-// Operand tiles are produced by all 256 threads (coalesced 16-byte loads, TF32 hi/lo split, canonical K-major
-// no-swizzle UMMA layout), one elected thread issues the MMAs, tcgen05.commit -> mbarrier tracks completion.
+// Operand tiles are produced by the 8 producer warps (coalesced 16-byte loads, TF32 hi/lo split, canonical K-major
+// no-swizzle UMMA layout); a 9th warp walks a per-CTA slab table with warp-uniform values and one elected lane issues
+// the TMA requests and the MMAs; tcgen05.commit -> mbarrier tracks completion; epilogue chunks are interleaved with
+// the slabs (an accumulator chunk is final as soon as the last slab that touches it has retired).
 #include <cstdlib>
 
 #include "gpblur_tc.cuh"
