@@ -41,7 +41,8 @@ struct TcPointArgs {
   const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
   uint32_t stream_id;
   int ntiles;
-  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP): 4 = skip the W / A chunk stores, 5 = skip chunk math
+  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP; results are WRONG): 4 = skip the W chunk stores,
+                    // 6 = skip the saved-A slab loads / stores of the backward (upper bound of a loader warp group)
   long long* trace; // optional event trace buffer (GPBLUR_TRACE_PTR = device address, debugging only)
   long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
 };
@@ -817,17 +818,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
           BSEG(2);                                    // acquire (MMA s + 2 retired)
-          store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+          if (a.exp_mode != 6) store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
           BSEG(3);                                    // split + store (waits for the global loads of the slab)
-          if (s - 2 >= s_lo) load_a(r0, s - 2);
+          if (s - 2 >= s_lo && a.exp_mode != 6) load_a(r0, s - 2);
           pipe.commit();
           interleaved(s);
           if (s - 1 < s_lo) break;
           pipe.acquire(a_hi, a_lo);
           BSEG(2);
-          store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+          if (a.exp_mode != 6) store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
           BSEG(3);
-          if (s - 3 >= s_lo) load_a(r1, s - 3);
+          if (s - 3 >= s_lo && a.exp_mode != 6) load_a(r1, s - 3);
           pipe.commit();
           interleaved(s - 1);
         }
