@@ -74,7 +74,8 @@ struct SlabDesc {
   const float* img;    // B image in global memory (hi plane | lo plane), rows x 32 k each
   int rows;            // B rows = MMA N (also sets the leading byte offset of the B descriptor)
   uint32_t tmem_off;   // accumulator column offset inside the CTA's TMEM allocation
-  int first;           // 1: the first MMA overwrites the accumulator (no accumulate)
+  int first;           // bit 0: the first MMA overwrites the accumulator (no accumulate);
+                       // bits 8..: 1 + index of the chunk barrier to signal when this slab's MMAs retire (0 = none)
 };
 
 // Ring barriers:
@@ -105,7 +106,7 @@ __device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st
 // `ntiles_mine` tiles, each `nslabs` table entries.
 template <int NB>
 __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
-                                         int ntiles_mine, long long* trace = nullptr) {
+                                         int ntiles_mine, long long* trace = nullptr, uint64_t* chunk_bars = nullptr) {
   if (ntiles_mine <= 0 || nslabs <= 0) return;
   constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
   constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
@@ -140,7 +141,8 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
       const uint32_t phase = uses[st] & 1;
       const uint32_t rows = tc::uniform_u32((uint32_t)tab[i].rows);
       const uint32_t tmem_d = tmem_base + tc::uniform_u32(tab[i].tmem_off);
-      const uint32_t first = tc::uniform_u32((uint32_t)tab[i].first);
+      const uint32_t first_sig = tc::uniform_u32((uint32_t)tab[i].first);
+      const uint32_t first = first_sig & 1u, sig = first_sig >> 8;
       const uint32_t idesc = tc::make_idesc_tf32(TNP, (int)rows);
       const uint64_t dbh0 = b_hi_base[st] | ((uint64_t)rows << 16);        // LBO = rows * 16 B
       const uint64_t dbl0 = b_lo_base[st] | ((uint64_t)rows << 16);
@@ -177,6 +179,7 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
           tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
         }
         tc::umma_commit(&bars[st]);
+        if (sig) tc::umma_commit(&chunk_bars[sig - 1]);   // an accumulator chunk is final: tell the row-owner warps
       }
       __syncwarp();
       if (tr) tr[3] = clock64();
@@ -204,6 +207,23 @@ struct Pipe {
     if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
     a_hi = base + st * Stage<NB>::FLOATS;
     a_lo = a_hi + Stage<NB>::A_PLANE;
+  }
+  // advance over slabs produced by ANOTHER warp group (both groups count every slab of the shared ring)
+  // (the caller must be synchronised with the retirement of the skipped slabs some other way - the row owners wait on
+  // the chunk barriers - or the parity waits of acquire() alias)
+  __device__ __forceinline__ void skip(int n) {
+    for (int i = 0; i < n; ++i) { uses[slab & 1] += 1; slab += 1; }
+  }
+  // same, but staying within two slabs of the retired MMAs like a producing group does: the parity of a ring barrier
+  // is only meaningful one phase ahead, and the slab that follows the skipped ones must not be published before the
+  // other group has published (and the tensor core retired) the skipped ones
+  __device__ __forceinline__ void skip_wait(int n) {
+    for (int i = 0; i < n; ++i) {
+      const int st = slab & 1;
+      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
+      uses[st] += 1;
+      slab += 1;
+    }
   }
   // publish this stage's A planes to the issuer (no CTA barrier)
   __device__ __forceinline__ void commit() {
@@ -236,7 +256,7 @@ struct OpRegs {
 
 template <int PLANE_ROWS, class F>
 __device__ __forceinline__ void load_kmajor(OpRegs<PLANE_ROWS>& regs, int nrows, F&& load4) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
   const int rr = lane & 7, cq = lane >> 3;
   const int ntiles = (nrows >> 3) * 2;   // warp tiles: (8-row block, 4-chunk group)
 #pragma unroll
@@ -248,7 +268,7 @@ __device__ __forceinline__ void load_kmajor(OpRegs<PLANE_ROWS>& regs, int nrows,
 
 template <int PLANE_ROWS>
 __device__ __forceinline__ void store_kmajor(float* hi, float* lo, const OpRegs<PLANE_ROWS>& regs, int nrows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
   const int rr = lane & 7, cq = lane >> 3;
   const int ntiles = (nrows >> 3) * 2;
 #pragma unroll
@@ -306,7 +326,7 @@ __device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, 
 }
 // centre / scale the registers of load_x_slab in place (same (row, chunk) mapping as load_kmajor)
 __device__ __forceinline__ void transform_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
   const int rr = lane & 7, cq = lane >> 3;
 #pragma unroll
   for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
@@ -337,7 +357,7 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     transform_x_slab(ra, xl, ds, DP);
     if (stats) {
       // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
-      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
       const int rr = lane & 7, cq = lane >> 3;
 #pragma unroll
       for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
@@ -423,7 +443,8 @@ __device__ __forceinline__ int bwd_table(SlabDesc* tab, const TcPointArgs& a) {
       const int sg = NSL - 1 - (j - nds);
       int rows;
       d.img = LCTU + tc_lct_image(MP, p, sg, &rows);
-      d.rows = rows; d.tmem_off = (uint32_t)BW; d.first = sg == NSL - 1;
+      const int c = sg - p * SPB;                   // chunk finalised by this slab (slabs run in decreasing order)
+      d.rows = rows; d.tmem_off = (uint32_t)BW; d.first = (sg == NSL - 1 ? 1 : 0) | (c < SPB ? ((c + 1) << 8) : 0);
     }
     tab[i] = d;
   }
@@ -666,19 +687,29 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
 // =================================================================================================
 // backward: W = kbar o k and its row sums, one column block p of width BW at a time
 // =================================================================================================
+// Warp roles of the backward kernel (640 threads; 96 registers per thread suffice once the loader work is split off):
+//   warps 0..7   ROW OWNERS : phase A (x~ planes, row statistics), epilogue chunks (thread = point), W stores
+//   warps 8..15  LOADERS    : the saved-A slabs of the T GEMM: global loads -> TF32 split -> A planes -> arrive
+//   warp 16      ISSUER     : TMA requests + MMAs (+ per-chunk commits), warps 17..19 idle
+// The two producer groups share one operand ring; both count every slab, each arrives (256 threads) only on its own.
+constexpr int kBwdThreads = 640;
+constexpr int kBwdIssuerWarp = 16;
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
 template <int BW>
-__global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
+  __shared__ __align__(8) uint64_t chunk_bars[8];                    // accumulator chunk c of the current block is final
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxBwdSlabs];
   __shared__ int tab_n;
   __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
-  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the interleaved epilogue
-  // per-slab row-statistic partials of phase A live in the same memory (separated from every staging use by the
-  // producer barriers at the end of phase A and at the end of a tile)
+  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
+  // per-slab row-statistic partials of phase A live in the same memory (row-owner warps only; separated from every
+  // staging use by the group barriers at the end of phase A and at the end of a tile)
   float* part_n = &estg[0][0];
   float* part_w = part_n + (KT / 4) * TNP;
 
@@ -695,10 +726,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   const float* znc_g = ws_cptr<float>(a.ws, L.znc);
   const float* beta_g = ws_cptr<float>(a.ws, L.beta);
   const float l2os = log2f(hyp[H_OS]);
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) init_ring_barriers(bars);
+  if (tid == 0) {
+    init_ring_barriers(bars);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&chunk_bars[i], 1);
+    tc::fence_barrier_init();
+  }
   if (tid < kThreads) {
     for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per p when MP > BW
       zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
@@ -713,14 +749,58 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
   const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + BW;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == kIssuerWarp) {
-    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
+  if (warp >= kBwdIssuerWarp) {
+    // ---------------- issuer warpgroup ----------------
+    if (warp == kBwdIssuerWarp) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, nullptr, chunk_bars);
+  } else if (warp >= 8) {
+    // ---------------- loader warps: saved-A slabs -> A planes ----------------
+    Pipe<BW> pipe;
+    pipe.init(stage_base, bars);
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long long n0 = (long long)tile * TNP;
+      auto load_a = [&](OpRegs<TNP>& regs, int sl) {
+        load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
+          long long g2 = n0 + r;
+          if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
+          return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
+        });
+      };
+      for (int p = 0; p < NP; ++p) {
+        const int s_lo = p * SPB;
+        // three slabs in flight (rotating register sets); the first ones are requested while the row owners are
+        // still in phase A
+        OpRegs<TNP> r0, r1, r2;
+        load_a(r0, NSL - 1);
+        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
+        if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
+        pipe.skip_wait(nds);                          // the phase-A slabs of this block belong to the row owners
+        for (int s = NSL - 1; s >= s_lo; s -= 3) {
+          float *a_hi, *a_lo;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
+          if (s - 3 >= s_lo) load_a(r0, s - 3);
+          pipe.commit();
+          if (s - 1 < s_lo) break;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
+          if (s - 4 >= s_lo) load_a(r1, s - 4);
+          pipe.commit();
+          if (s - 2 < s_lo) break;
+          pipe.acquire(a_hi, a_lo);
+          store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
+          if (s - 5 >= s_lo) load_a(r2, s - 5);
+          pipe.commit();
+        }
+      }
+    }
   } else {
+    // ---------------- row-owner warps ----------------
     Pipe<BW> pipe;
     pipe.init(stage_base, bars);
     const int quad = warp & 3, half = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t blk = 0;                                 // blocks processed so far: phase of the chunk barriers
 
     long long bseg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long blast = clock64();
@@ -753,19 +833,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         if (v <= kMinVariance) gv = 0.f;
         if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
       }
-      auto load_a = [&](OpRegs<TNP>& regs, int sl) {
-        load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-          long long g2 = n0 + r;
-          if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
-          return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
-        });
-      };
       float rsum = 0.f, xnc = 0.f;
       BSEG(0);                                        // tile head (upstream gradients)
       // epilogue of one 32-column chunk c of column block p (16 columns per column half): W = kbar o k, its row sum,
-      // W saved for the dx / W^T X kernels.  T[:, chunk c] is last touched by slab p SPB + c, and the slabs run in
-      // DEcreasing order, so chunk c is final once that slab has retired: most chunks are handled inside the slab
-      // loop while the tensor core works on the remaining slabs.
+      // W saved for the dx / W^T X kernels.  T[:, chunk c] is last touched by slab p SPB + c, the slabs run in
+      // DEcreasing order, and the issuer commits that slab onto chunk_bars[c]: the chunks are handled while the
+      // tensor core (and the loader warps) work on the remaining slabs.
       auto epi_chunk = [&](int p, int c) {
         const int col = c * 32 + half * 16;
         uint32_t kr[16], tr[16];
@@ -784,17 +857,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         if (a.exp_mode != 4)
           warp_store_chunk16(Wg + (size_t)w0 * MP + p * BW + col, MP, estg[warp], t, lane, nvalid);
       };
-      for (int p = 0; p < NP; ++p) {
+      for (int p = 0; p < NP; ++p, ++blk) {
         if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
-          prod_sync();
+          group_sync(1);
           if (tid < BW) { zn_s[tid] = znc_g[p * BW + tid]; beta_s[tid] = beta_g[p * BW + tid]; }
-          prod_sync();
+          group_sync(1);
         }
-        // the first two saved-A slabs of this block are requested BEFORE phase A: their HBM latency hides behind it
-        OpRegs<TNP> r0, r1;
-        const int s_lo = p * SPB;
-        load_a(r0, NSL - 1);
-        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
         phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
         if (p == 0 && more_tiles) {
           const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
@@ -803,48 +871,23 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_bwd_kernel(TcPointA
         }
         xnc = -0.72134752044448170f * xn_s[row];
         BSEG(1);                                      // phase A
-        // ---- T[:, block p] += a[:, slab s] (diag(c) Linv)[slab s, block p], slabs in DEcreasing order ----
-        // the saved-A slabs are fetched THREE slabs ahead (rotating register sets): one slab of 16 KB per SM in
-        // flight cannot cover the HBM latency (Little's law), three can
-        // after the acquire of slab s, slab s + 2 has retired: if it lies in block p, its chunk (and S, complete
-        // since the first T slab was issued behind it) is final
-        auto interleaved = [&](int s) {
-          const int c = s + 2 - s_lo;
-          BSEG(4);                                    // next loads + commit
-          if (s + 2 <= NSL - 1 && c < SPB) { tc::tc_fence_after(); epi_chunk(p, c); }
-          BSEG(5);                                    // interleaved epilogue chunk
-        };
-        for (int s = NSL - 1; s >= s_lo; s -= 2) {
-          float *a_hi, *a_lo;
-          pipe.acquire(a_hi, a_lo);
-          BSEG(2);                                    // acquire (MMA s + 2 retired)
-          if (a.exp_mode != 6) store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
-          BSEG(3);                                    // split + store (waits for the global loads of the slab)
-          if (s - 2 >= s_lo && a.exp_mode != 6) load_a(r0, s - 2);
-          pipe.commit();
-          interleaved(s);
-          if (s - 1 < s_lo) break;
-          pipe.acquire(a_hi, a_lo);
-          BSEG(2);
-          if (a.exp_mode != 6) store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
-          BSEG(3);
-          if (s - 3 >= s_lo && a.exp_mode != 6) load_a(r1, s - 3);
-          pipe.commit();
-          interleaved(s - 1);
+        pipe.skip(NSL - p * SPB);                     // the T slabs of this block belong to the loader warps
+        for (int c = SPB - 1; c >= 0; --c) {
+          tc::mbar_wait(&chunk_bars[c], blk & 1);
+          tc::tc_fence_after();
+          BSEG(2);                                    // wait for the chunk's last slab
+          epi_chunk(p, c);
+          BSEG(5);                                    // epilogue chunk
         }
-        pipe.drain();
-        BSEG(6);                                      // drain
-        epi_chunk(p, 1);
-        epi_chunk(p, 0);
-        // the TMEM reads are done before ANY producer publishes A planes of the next phase (its MMAs overwrite them)
+        // the TMEM reads are done before ANY row owner publishes A planes of the next phase (its MMAs overwrite S)
         tc::tc_fence_before();
-        prod_sync();
+        group_sync(1);
       }
       if (half == 1) r_s[row] = rsum;
-      prod_sync();
+      group_sync(1);
       if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
-      prod_sync();
-      BSEG(7);                                        // final chunks + row sums
+      group_sync(1);
+      BSEG(7);                                        // row sums
     }
     if (a.dbg && blockIdx.x == 0 && tid == 0)
       for (int i = 0; i < 8; ++i) a.dbg[16 + i] = bseg[i];
@@ -1205,11 +1248,11 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
     if (L.MP == 128) {
       static bool cfg = false;
       if (!cfg) { set_smem(tc_point_bwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-      tc_point_bwd_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
+      tc_point_bwd_kernel<128><<<grid, kBwdThreads, tc_smem_bytes<128>(), st>>>(a);
     } else {
       static bool cfg = false;
       if (!cfg) { set_smem(tc_point_bwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-      tc_point_bwd_kernel<256><<<grid, kBlockThreads, tc_smem_bytes<256>(), st>>>(a);
+      tc_point_bwd_kernel<256><<<grid, kBwdThreads, tc_smem_bytes<256>(), st>>>(a);
     }
     note_launch();
     int rc = check_launch("tc_point_bwd");
