@@ -109,33 +109,57 @@ __device__ __forceinline__ double fast_rsqrt64(double d) {
   return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
-// Cholesky of a 32 x 32 block held one row per lane in registers.  Per column: pivot broadcast (shuffle), reciprocal
-// square root, then the scaled column goes through a double-buffered shared-memory vector so that the 31 - c
-// trailing updates of a lane read their multipliers with broadcast loads (one 16-byte load per two columns) instead
-// of two shuffles each.  On exit a[c] = L[lane][c] (0 above the diagonal), rinv = 1 / L[lane][lane]; returns the
-// first bad pivot (1-based).  `lcol`: 2 x 32 doubles of shared memory, 16-byte aligned.
-__device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int lane, double* lcol) {
+// Cholesky of a 32 x 32 block held one row per lane in registers, FUSED with the inverse of the factor.
+// Per column c: pivot broadcast (shuffle), reciprocal square root, then the scaled column goes through a
+// double-buffered shared-memory vector so that the trailing updates of a lane read their multipliers with broadcast
+// loads (one 16-byte load per two columns) instead of two shuffles each.
+//  * The NEXT pivot never waits for that shared-memory round trip: in lane c + 1 the multiplier of column c + 1 is the
+//    lane's own l, so `piv = a[c + 1] - l * l` is formed locally and shuffled at the top of the next iteration (the
+//    dependent chain per column is shuffle -> rsqrt -> 2 FP64 operations).
+//  * The same column broadcast drives one step of the column-oriented forward substitution X = L^-1 (lane = column
+//    of X): x[c] = s[c] / L[c][c], then s[r] -= L[r][c] x[c] for r > c - independent FMAs that fill the latency of
+//    the pivot chain, so the block inverse costs no extra time (it used to be a second 32-step loop).
+// On exit a[c] = L[lane][c] (0 above the diagonal), x[r] = (L^-1)[r][lane]; returns the first bad pivot (1-based).
+// `lcol`: 2 x 32 doubles of shared memory, 16-byte aligned.
+__device__ __forceinline__ int chol32_inv_warp(double (&a)[TB], double (&x)[TB], int lane, double* lcol) {
   int bad = 0;
 #pragma unroll
+  for (int r = 0; r < TB; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  if (!(d > 0.0)) bad = 1;
+  double rs = fast_rsqrt64(d);
+#pragma unroll
   for (int c = 0; c < TB; ++c) {
-    const double d = __shfl_sync(0xffffffffu, a[c], c);
-    if (!(d > 0.0) && bad == 0) bad = c + 1;
-    const double rs = fast_rsqrt64(d);
     const double l = a[c] * rs;
-    rinv = (lane == c) ? rs : rinv;
+    const double xc = (c >= lane) ? x[c] * rs : 0.0;
+    // software pipelining by hand: the pivot of column c + 1 (meaningful in lane c + 1: a[c + 1] - l^2) is shuffled
+    // and its reciprocal square root started BEFORE the trailing update of column c is issued
+    if (c + 1 < TB) {
+      const double piv = fma(-l, l, a[c + 1]);
+      d = __shfl_sync(0xffffffffu, piv, c + 1);
+      if (!(d > 0.0) && bad == 0) bad = c + 2;
+      rs = fast_rsqrt64(d);
+    }
     a[c] = (lane >= c) ? l : 0.0;
+    x[c] = xc;
     double* buf = lcol + (c & 1) * TB;
     buf[lane] = l;
     __syncwarp();
     // branch-free trailing update: lanes above the diagonal (lane < c2) update entries that are never read
     // (they are overwritten with 0 when their column is processed), so no predicate is needed
     if ((c + 1) & 1) {
-      if (c + 1 < TB) a[c + 1] = fma(-l, buf[c + 1], a[c + 1]);
+      if (c + 1 < TB) {
+        const double m = buf[c + 1];
+        a[c + 1] = fma(-l, m, a[c + 1]);
+        x[c + 1] = fma(-m, xc, x[c + 1]);
+      }
 #pragma unroll
       for (int c2 = c + 2; c2 + 1 < TB; c2 += 2) {
         const double2 m2 = *reinterpret_cast<const double2*>(buf + c2);
         a[c2] = fma(-l, m2.x, a[c2]);
         a[c2 + 1] = fma(-l, m2.y, a[c2 + 1]);
+        x[c2] = fma(-m2.x, xc, x[c2]);
+        x[c2 + 1] = fma(-m2.y, xc, x[c2 + 1]);
       }
     } else {
 #pragma unroll
@@ -143,30 +167,12 @@ __device__ __forceinline__ int chol32_warp(double (&a)[TB], double& rinv, int la
         const double2 m2 = *reinterpret_cast<const double2*>(buf + c2);
         a[c2] = fma(-l, m2.x, a[c2]);
         a[c2 + 1] = fma(-l, m2.y, a[c2 + 1]);
+        x[c2] = fma(-m2.x, xc, x[c2]);
+        x[c2 + 1] = fma(-m2.y, xc, x[c2 + 1]);
       }
     }
   }
   return bad;
-}
-
-// Inverse of the lower-triangular block Lb (shared memory, row-major) with reciprocal diagonal rd: lane = column of
-// the inverse.  Column-oriented forward substitution: once x[k] is known, the 31 - k partial sums of the rows below
-// are updated independently (instruction-level parallelism), so the dependent chain is 2 operations per row instead
-// of a dot product of growing length.  Result X[r][lane] written to Xb.
-__device__ __forceinline__ void trinv32_warp(const Tile& Lb, const double* rd, Tile& Xb, int lane) {
-  double sacc[TB];   // partial sums; slot k is overwritten with x[k] once row k is solved
-#pragma unroll
-  for (int r = 0; r < TB; ++r) sacc[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-  for (int k = 0; k < TB; ++k) {
-    const double xk = (k >= lane) ? sacc[k] * rd[k] : 0.0;
-    sacc[k] = xk;
-#pragma unroll
-    for (int r = k + 1; r < TB; ++r) sacc[r] = fma(-Lb[r][k], xk, sacc[r]);
-  }
-  // stores only after every load of Lb (the compiler cannot prove that Xb and Lb do not alias)
-#pragma unroll
-  for (int r = 0; r < TB; ++r) Xb[r][lane] = sacc[r];
 }
 
 struct MmFwdArgs {
@@ -342,7 +348,6 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   // ---------------- phase 2: blocked Cholesky (right-looking) ----------------
   // per block column kb: every participating CTA factorises the diagonal block in registers (one warp, shuffle
   // broadcasts) and inverts it, so the panel solve X L_kk^T = A_ik becomes the GEMM X = A_ik Dinv^T.
-  __shared__ double rdiag[TB];
   __shared__ __align__(16) double lcol[2 * TB];
   Tile& Di = Cs[0];   // inverse of the diagonal block
   // The triangular inverse X = L^-1 is built INSIDE the factorisation loop (no separate phase, no extra grid
@@ -354,21 +359,24 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     if ((int)blockIdx.x < n_items || blockIdx.x == 0) {
       __syncthreads();
       if (kb == 0 && blockIdx.x == 0 && tid == 0) stamps[9] = global_ns();
+      // the operand tile of this CTA's first item is requested NOW: its L2 round trip hides behind the factorisation
+      double pre[4] = {0.0, 0.0, 0.0, 0.0};
+      if ((int)blockIdx.x < n_items) {
+        if ((int)blockIdx.x < nrb) fetch_tile(pre, MatRef{L64, MP, false}, (kb + 1 + blockIdx.x) * TB, kb * TB);
+        else fetch_tile(pre, MatRef{T64, MP, false}, kb * TB, ((int)blockIdx.x - nrb) * TB);
+      }
       if (warp == 0) {
         double arow[TB];
         const double* src = L64 + (size_t)(kb * TB + lane) * MP + kb * TB;
 #pragma unroll
         for (int c = 0; c < TB; ++c) arow[c] = src[c];
         if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[10] = global_ns() + (unsigned long long)(arow[0] == 12345.678);
-        double rinv = 0.0;
-        const int bad = chol32_warp(arow, rinv, lane, lcol);
+        double xcol[TB];
+        const int bad = chol32_inv_warp(arow, xcol, lane, lcol);
         if (bad && blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + bad);
-        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(rinv == 12345.678);
+        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(xcol[31] == 12345.678);
 #pragma unroll
-        for (int c = 0; c < TB; ++c) Dg[lane][c] = arow[c];
-        rdiag[lane] = rinv;
-        __syncwarp();
-        trinv32_warp(Dg, rdiag, Di, lane);
+        for (int c = 0; c < TB; ++c) { Dg[lane][c] = arow[c]; Di[c][lane] = xcol[c]; }
         if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(Di[31][0] == 12345.678);
       }
       __syncthreads();
@@ -386,7 +394,8 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         if (it < nrb) {
           // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
           const int row0 = (kb + 1 + it) * TB;
-          load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
+          if (it == (int)blockIdx.x) park_tile(As, pre, false);
+          else load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
           __syncthreads();
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
@@ -400,7 +409,8 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         } else {
           // inverse tile X[kb][j] = -Dinv_kb * Y[kb][j]
           const int j = it - nrb;
-          load_tile(As, MatRef{T64, MP, false}, kb * TB, j * TB);
+          if (it == (int)blockIdx.x) park_tile(As, pre, false);
+          else load_tile(As, MatRef{T64, MP, false}, kb * TB, j * TB);
           __syncthreads();
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
@@ -433,24 +443,28 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         int ti, tj;
         tri_decode(t, ti, tj);
         const int bi = kb + 1 + ti, bj = kb + 1 + tj;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, cv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                      // C tile requested together with the operands
+          cv[i] = L64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane];
         tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
                   kb * TB + TB, As, Bs);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = warp + 8 * i;
-          if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] -= acc[i];
+          if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] = cv[i] - acc[i];
         }
       } else {
         const int yi = (t - ntr) / (kb + 1), j = (t - ntr) - yi * (kb + 1);
         const int bi = kb + 1 + yi;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, yv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (j != kb) {                                   // the first contribution to Y[i][kb] comes from this step
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yv[i] = T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane];
+        }
         tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{Li64, MP, false}, j * TB, kb * TB, kb * TB + TB, As, Bs);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double* y = T64 + (size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane;
-          *y = (j == kb) ? acc[i] : *y + acc[i];       // the first contribution to Y[i][kb] comes from this step
-        }
+        for (int i = 0; i < 4; ++i) T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane] = yv[i] + acc[i];
       }
     }
     grid.sync();   // also publishes the last diagonal block before phase 4
