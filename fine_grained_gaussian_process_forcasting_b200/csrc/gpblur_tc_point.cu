@@ -356,7 +356,9 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     else load_x_slab(ra, xl, ds, DP);
     transform_x_slab(ra, xl, ds, DP);
     if (stats) {
-      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
+      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor): the
+      // four chunk groups of a row sit in lanes rr, rr + 8, rr + 16, rr + 24 (fixed shuffle tree), the two chunk halves
+      // in neighbouring warps (two shared-memory partials per row)
       const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
       const int rr = lane & 7, cq = lane >> 3;
 #pragma unroll
@@ -366,8 +368,13 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
         const int dchunk = ds * (KT / 4) + c;
         const float4 v = ra.v[p];
         const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        part_n[c * TNP + row] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        part_w[c * TNP + row] = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+        float pn = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        float pw = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+        pn += __shfl_xor_sync(0xffffffffu, pn, 8);
+        pw += __shfl_xor_sync(0xffffffffu, pw, 8);
+        pn += __shfl_xor_sync(0xffffffffu, pn, 16);
+        pw += __shfl_xor_sync(0xffffffffu, pw, 16);
+        if (cq == 0) { part_n[(wt & 1) * TNP + row] = pn; part_w[(wt & 1) * TNP + row] = pw; }
       }
     }
     float *a_hi, *a_lo;
@@ -375,15 +382,12 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
     pipe.commit();
     if (stats) {
-      // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
+      // fold this slab's partials in fixed order (bit-deterministic)
       prod_sync();
       if (threadIdx.x < TNP) {
         float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
-#pragma unroll
-        for (int c = 0; c < KT / 4; ++c) {
-          n2 += part_n[c * TNP + threadIdx.x];
-          xw += part_w[c * TNP + threadIdx.x];
-        }
+        n2 += part_n[threadIdx.x] + part_n[TNP + threadIdx.x];
+        xw += part_w[threadIdx.x] + part_w[TNP + threadIdx.x];
         xn_s[threadIdx.x] = n2;
         xw_s[threadIdx.x] = xw;
       }
@@ -415,7 +419,8 @@ __device__ __forceinline__ int fwd_table(SlabDesc* tab, const TcPointArgs& a) {
       const int sl = j - nds, sg = q * SPB + sl;
       int rows;
       d.img = LinvU + tc_linv_image(MP, p, sg, &rows);
-      d.rows = rows; d.tmem_off = (uint32_t)(BW + BW - rows); d.first = (q == 0 && sl == 0);
+      d.rows = rows; d.tmem_off = (uint32_t)(BW + BW - rows);
+      d.first = ((q == 0 && sl == 0) ? 1 : 0) | (q == p ? ((sl + 1) << 8) : 0);   // chunk sl of block p final
     }
     tab[i] = d;
   }
@@ -508,22 +513,34 @@ __device__ __forceinline__ void warp_store_chunk16(float* dst, size_t ld, float*
 // S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
 // cross-covariance blocks q <= p (Linv is lower triangular); for MP > 256 block q is recomputed for every p >= q.
 // =================================================================================================
+// Warp roles (544 threads):
+//   warps 0..7   K PRODUCERS : phase A (x~ planes, row statistics), then per whitening slab: S chunk from TMEM ->
+//                              k = 2^(...) -> TF32 split -> A planes -> arrive.  They never touch the A accumulators.
+//   warps 8..15  EPILOGUE    : thread = point; chunk c of output block p is read from TMEM as soon as the issuer's
+//                              commit of whitening slab c (pass q == p) lands on chunk_bars[c]: mean / variance
+//                              partials, A saved for the backward; final mean / variance / sample of the tile
+//   warp 16      ISSUER      : TMA requests + MMAs (+ per-chunk commits)
+// The K producers run ahead into the next block / tile (its phase A and the first k slab) while the epilogue warps
+// finish; they wait on `epi_done` only before publishing the slab whose MMAs overwrite the A accumulators.
+constexpr int kTwoGroupThreads = 2 * kThreads + 32;
+constexpr int kTwoGroupIssuerWarp = 2 * kThreads / 32;
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
 template <int BW>
-__global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
+  __shared__ __align__(8) uint64_t chunk_bars[8];   // chunk c of the current output block is final (tcgen05.commit)
+  __shared__ __align__(8) uint64_t epi_done;        // the epilogue warps have read every chunk of the current block
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxFwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q; m, c = s^2 - 1 of block p
-  __shared__ float xn_s[TNP], xw_s[TNP], mu_s[TNP], vv_s[TNP];
-  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the interleaved epilogue
-  // per-slab row-statistic partials of phase A live in the same memory: every use of one is separated from every use
-  // of the other by a producer barrier (phase A ends with one, a tile ends with two)
-  float* part_n = &estg[0][0];
-  float* part_w = part_n + (KT / 4) * TNP;
-  static_assert(2 * (KT / 4) * TNP <= 8 * 32 * kStagePitch16, "row-statistic partials must fit in the staging tiles");
+  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q (K warps); m, c = s^2 - 1 of block p
+  __shared__ float xn_s[TNP], xw_s[2][TNP];         // row statistics (xw: per tile parity, read by the epilogue warps)
+  __shared__ float mu_s[TNP], vv_s[TNP];
+  __shared__ float part_n[2 * TNP], part_w[2 * TNP];
+  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -540,7 +557,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) init_ring_barriers(bars);
+  if (tid == 0) {
+    init_ring_barriers(bars);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&chunk_bars[i], 1);
+    tc::mbar_init(&epi_done, kThreads);
+    tc::fence_barrier_init();
+  }
   if (tid < kThreads) {
     for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per (p, q) when MP > BW
       zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
@@ -555,18 +577,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int quad = warp & 3, half = (warp >> 2) & 1;  // TMEM lane quadrant / column half of this warp
+  const int row = quad * 32 + lane;                   // the point this thread owns
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-  if (warp == kIssuerWarp) {
-    // ---------------- issuer warp: one thread drives the TMA requests and the tensor core ----------------
-    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine);
-  } else {
-    // ---------------- producer / epilogue warps ----------------
+  if (warp == kTwoGroupIssuerWarp) {
+    // ---------------- issuer warp: one elected thread drives the TMA requests and the tensor core ----------------
+    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, nullptr, chunk_bars);
+  } else if (warp < 8) {
+    // ---------------- K producers ----------------
     Pipe<BW> pipe;
     pipe.init(stage_base, bars);
-    const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant / column half of this warp
-    const int row = quad * 32 + lane;                 // the point this thread owns in the epilogues
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-
     long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #define SEG(i) do { if (a.dbg) { const long long tnow = clock64(); seg[i] += tnow - tlast; tlast = tnow; } } while (0)
@@ -576,43 +597,21 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
       load_x_slab(xr0, xl0, 0, L.DP);
       if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
     }
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    uint32_t blk = 0, tpar = 0;                       // output blocks started so far; tile parity
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1) {
       const long long n0 = (long long)tile * TNP;
-      const long long gn = n0 + row;
       const XLoader xl = make_xloader(a, n0);
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      float mu = 0.f, vv = 0.f;
       SEG(7);
-      const long long w0 = n0 + quad * 32;        // first point of this warp
-      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-      // epilogue of one 32-column chunk c of output block p (16 columns per column half): mean / variance partials
-      // of the own point, A saved for the backward.  The chunk is final as soon as whitening slab c of the pass
-      // q == p has retired, so most chunks are handled INSIDE the slab loop, while the tensor core works on the
-      // later slabs; the staging tile is private to the warp (the operand ring is busy).
-      auto epi_chunk = [&](int p, int c) {
-        const int col = c * 32 + half * 16;
-        float v[16];
-        tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          mu = fmaf(v[i], m_s[col + i], mu);
-          vv = fmaf(c_s[col + i] * v[i], v[i], vv);
-        }
-        if (L.training)
-          warp_store_chunk16(Ag + (size_t)w0 * MP + p * BW + col, MP, estg[warp], v, lane, nvalid);
-      };
-      for (int p = 0; p < NP; ++p) {
+      for (int p = 0; p < NP; ++p, ++blk) {
         for (int q = 0; q <= p; ++q) {
           const bool first_pass = p == 0 && q == 0;
           if (NP > 1) {                               // per-block constants (single block: loaded once at kernel start)
             prod_sync();
-            if (tid < BW) {
-              zn_s[tid] = znc_g[q * BW + tid];
-              if (q == 0) { m_s[tid] = mvec_g[p * BW + tid]; c_s[tid] = cvec_g[p * BW + tid]; }
-            }
+            zn_s[tid] = znc_g[q * BW + tid];          // BW == kThreads whenever NP > 1
             prod_sync();
           }
-          phase_a<BW>(pipe, a, xl, first_pass, part_n, part_w, xn_s, xw_s, first_pass, xr0, xr1);
+          phase_a<BW>(pipe, a, xl, first_pass, part_n, part_w, xn_s, xw_s[tpar], first_pass, xr0, xr1);
           if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
             const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
             load_x_slab(xr0, xln, 0, L.DP);
@@ -646,38 +645,65 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
               tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
                               make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
             SEG(4);                                   // split + store of the k slab
+            // the MMAs of the first slab of an output block OVERWRITE the A accumulators: the epilogue warps must
+            // have read the previous block out of them
+            if (q == 0 && sl == 0 && blk > 0) tc::mbar_wait(&epi_done, (blk - 1) & 1);
             pipe.commit();
-            SEG(5);                                   // fences + arrive
-            if (q == p && sl >= 2) {                  // slab sl - 2 has retired (acquire above): its chunk is final
-              tc::tc_fence_after();
-              epi_chunk(p, sl - 2);
-              SEG(6);
-            }
+            SEG(5);                                   // (epilogue wait) + fences + arrive
           }
         }
-        pipe.drain();
-        SEG(1);
-        epi_chunk(p, SPB - 2);
-        epi_chunk(p, SPB - 1);
-        // the TMEM reads are done before ANY producer publishes A planes of the next phase (its MMAs overwrite them)
+      }
+    }
+    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
+      for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
+#undef SEG
+  } else {
+    // ---------------- epilogue warps ----------------
+    const int ew = warp - 8, etid = tid - kThreads;
+    uint32_t blk = 0, tpar = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1) {
+      const long long n0 = (long long)tile * TNP;
+      const long long gn = n0 + row;
+      const long long w0 = n0 + quad * 32;        // first point of this warp
+      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+      float mu = 0.f, vv = 0.f;
+      for (int p = 0; p < NP; ++p, ++blk) {
+        if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
+          group_sync(2);
+          m_s[etid] = mvec_g[p * BW + etid];          // BW == kThreads whenever NP > 1
+          c_s[etid] = cvec_g[p * BW + etid];
+          group_sync(2);
+        }
+        // chunk c (16 columns per column half) is final once whitening slab c of the pass q == p has retired (Linv is
+        // lower triangular): mean / variance partials of the own point, A saved for the backward
+        for (int c = 0; c < SPB; ++c) {
+          tc::mbar_wait(&chunk_bars[c], blk & 1);
+          tc::tc_fence_after();
+          const int col = c * 32 + half * 16;
+          float v[16];
+          tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            mu = fmaf(v[i], m_s[col + i], mu);
+            vv = fmaf(c_s[col + i] * v[i], v[i], vv);
+          }
+          if (L.training)
+            warp_store_chunk16(Ag + (size_t)w0 * MP + p * BW + col, MP, estg[ew], v, lane, nvalid);
+        }
         tc::tc_fence_before();
-        prod_sync();
-        SEG(6);                                       // block epilogue
+        mbar_arrive(&epi_done);                       // the K producers may let the next block overwrite A
       }
       if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
-      prod_sync();
+      group_sync(2);
       if (half == 0 && gn < N) {
-        const float mean = mu + mu_s[row] + xw_s[row] + cwb;
+        const float mean = mu + mu_s[row] + xw_s[tpar][row] + cwb;
         const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
         a.mean[gn] = mean;
         a.var[gn] = var;
         if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id), mean);
       }
-      prod_sync();
+      group_sync(2);
     }
-    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
-      for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
-#undef SEG
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -687,18 +713,17 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_point_fwd_kernel(TcPointA
 // =================================================================================================
 // backward: W = kbar o k and its row sums, one column block p of width BW at a time
 // =================================================================================================
-// Warp roles of the backward kernel (640 threads; 96 registers per thread suffice once the loader work is split off):
+// Warp roles of the backward kernel (544 threads, 120 registers each):
 //   warps 0..7   ROW OWNERS : phase A (x~ planes, row statistics), epilogue chunks (thread = point), W stores
 //   warps 8..15  LOADERS    : the saved-A slabs of the T GEMM: global loads -> TF32 split -> A planes -> arrive
-//   warp 16      ISSUER     : TMA requests + MMAs (+ per-chunk commits), warps 17..19 idle
+//   warp 16      ISSUER     : TMA requests + MMAs (+ per-chunk commits)
 // The two producer groups share one operand ring; both count every slab, each arrives (256 threads) only on its own.
-constexpr int kBwdThreads = 640;
-constexpr int kBwdIssuerWarp = 16;
-__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+constexpr int kBwdThreads = kTwoGroupThreads;
+constexpr int kBwdIssuerWarp = kTwoGroupIssuerWarp;
 
 template <int BW>
 __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ __align__(8) uint64_t chunk_bars[8];                    // accumulator chunk c of the current block is final
@@ -708,10 +733,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
   __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
-  // per-slab row-statistic partials of phase A live in the same memory (row-owner warps only; separated from every
-  // staging use by the group barriers at the end of phase A and at the end of a tile)
-  float* part_n = &estg[0][0];
-  float* part_w = part_n + (KT / 4) * TNP;
+  __shared__ float part_n[2 * TNP], part_w[2 * TNP];
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -903,7 +925,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
 // =================================================================================================
 template <int DPT>   // DPT = MMA N = padded input dim (32, 64 or 128)
 __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
@@ -1185,7 +1207,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
 }
 
 template <int NB>
-constexpr size_t tc_smem_bytes() { return (size_t)2 * Stage<NB>::FLOATS * 4 + 1024; }
+constexpr size_t tc_smem_bytes() { return (size_t)2 * Stage<NB>::FLOATS * 4; }
 
 int tc_grid(const WsLayout& L) {
   const long long nt = (L.N + TNP - 1) / TNP;
@@ -1219,11 +1241,11 @@ int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* 
   if (L.MP == 128) {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_point_fwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-    tc_point_fwd_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
+    tc_point_fwd_kernel<128><<<grid, kTwoGroupThreads, tc_smem_bytes<128>(), st>>>(a);
   } else {
     static bool cfg = false;
     if (!cfg) { set_smem(tc_point_fwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-    tc_point_fwd_kernel<256><<<grid, kBlockThreads, tc_smem_bytes<256>(), st>>>(a);
+    tc_point_fwd_kernel<256><<<grid, kTwoGroupThreads, tc_smem_bytes<256>(), st>>>(a);
   }
   note_launch();
   return check_launch("tc_point_fwd");
