@@ -104,9 +104,13 @@ __device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st
 // single thread with per-thread registers costs ~100 cycles per MMA in register -> uniform-register conversion loops
 // (measured with scripts/dx_trace.py), more than the execution time of an N <= 128 MMA.
 // `ntiles_mine` tiles, each `nslabs` table entries.
-template <int NB>
+// POLL: see the comment at the MMA loop.  Measured on c5 M=256 (same box A/B): dx kernel 0.183 -> 0.171 ms, backward
+// kernel 0.272 -> 0.296 ms, forward neutral - so only the dx kernel polls.  The test is additionally predicated on the
+// run-time flag `poll_rt` (GPBLUR_TC_EXP bit 3 clears it): with a compile-time-only condition ptxas lays the poll out
+// differently and the dx kernel is SLOWER than without polling (0.186 ms).
+template <int NB, bool POLL = false>
 __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
-                                         int ntiles_mine, long long* trace = nullptr, uint64_t* chunk_bars = nullptr) {
+                                         int ntiles_mine, long long* trace = nullptr, uint64_t* chunk_bars = nullptr, bool poll_rt = true) {
   if (ntiles_mine <= 0 || nslabs <= 0) return;
   constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
   constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
@@ -169,26 +173,56 @@ __device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t t
           requested = true;
         }
       }
-      if (tc::elect_one()) {
+      // The MMA issue BLOCKS once the tensor-core queue is full (12 MMAs take 1400 - 2000 cycles to issue), and the
+      // other stage is released by the previous slab's MMAs somewhere in the middle of that.  With POLL the elected
+      // thread tests that barrier between k-steps and sends the next slab's TMA request from there instead of after
+      // the last MMA (scripts/fwd_trace.py shows the request path).
+      if constexpr (POLL) {
+        uint32_t req_flag = requested ? 1u : 0u;
+        if (tc::elect_one()) {
+          const float* nimg = tab[nxt].img;
+          const int nrows = tab[nxt].rows;
+          const uint32_t nparity = (uses[nst] - 1) & 1;
 #pragma unroll
-        for (int j = 0; j < KT / 8; ++j) {
-          const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
-          const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
-          tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
-          tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-          tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          for (int j = 0; j < KT / 8; ++j) {
+            const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
+            const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
+            tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
+            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            if (poll_rt && !req_flag && tc::mbar_test(&bars[nst], nparity)) {
+              issue_bulk_b<NB>(base, bars, nst, nimg, nrows);
+              req_flag = 1u;
+            }
+          }
+          tc::umma_commit(&bars[st]);
+          if (sig) tc::umma_commit(&chunk_bars[sig - 1]);
         }
-        tc::umma_commit(&bars[st]);
-        if (sig) tc::umma_commit(&chunk_bars[sig - 1]);   // an accumulator chunk is final: tell the row-owner warps
+        __syncwarp();
+        requested = __any_sync(0xffffffffu, req_flag != 0);
+      } else {
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KT / 8; ++j) {
+            const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
+            const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
+            tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
+            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          tc::umma_commit(&bars[st]);
+          if (sig) tc::umma_commit(&chunk_bars[sig - 1]);   // an accumulator chunk is final: tell the row-owner warps
+        }
+        __syncwarp();
       }
-      __syncwarp();
       if (tr) tr[3] = clock64();
-      if (tr) tr[4] = clock64();
       uses[st] += 1;
+      if (tr) tr[5] = requested ? 0 : 1;          // 1: the request had to wait for the previous slab's MMAs
       if (!requested) {                           // the other stage was still being read: wait, then request
         if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
         request_b(nst, nxt);
       }
+      if (tr) tr[4] = clock64();
     }
   }
 }
@@ -356,9 +390,7 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     else load_x_slab(ra, xl, ds, DP);
     transform_x_slab(ra, xl, ds, DP);
     if (stats) {
-      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor): the
-      // four chunk groups of a row sit in lanes rr, rr + 8, rr + 16, rr + 24 (fixed shuffle tree), the two chunk halves
-      // in neighbouring warps (two shared-memory partials per row)
+      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
       const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
       const int rr = lane & 7, cq = lane >> 3;
 #pragma unroll
@@ -368,13 +400,8 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
         const int dchunk = ds * (KT / 4) + c;
         const float4 v = ra.v[p];
         const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float pn = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        float pw = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
-        pn += __shfl_xor_sync(0xffffffffu, pn, 8);
-        pw += __shfl_xor_sync(0xffffffffu, pw, 8);
-        pn += __shfl_xor_sync(0xffffffffu, pn, 16);
-        pw += __shfl_xor_sync(0xffffffffu, pw, 16);
-        if (cq == 0) { part_n[(wt & 1) * TNP + row] = pn; part_w[(wt & 1) * TNP + row] = pw; }
+        part_n[c * TNP + row] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        part_w[c * TNP + row] = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
       }
     }
     float *a_hi, *a_lo;
@@ -382,12 +409,15 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
     pipe.commit();
     if (stats) {
-      // fold this slab's partials in fixed order (bit-deterministic)
+      // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
       prod_sync();
       if (threadIdx.x < TNP) {
         float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
-        n2 += part_n[threadIdx.x] + part_n[TNP + threadIdx.x];
-        xw += part_w[threadIdx.x] + part_w[TNP + threadIdx.x];
+#pragma unroll
+        for (int c = 0; c < KT / 4; ++c) {
+          n2 += part_n[c * TNP + threadIdx.x];
+          xw += part_w[c * TNP + threadIdx.x];
+        }
         xn_s[threadIdx.x] = n2;
         xw_s[threadIdx.x] = xw;
       }
@@ -420,7 +450,7 @@ __device__ __forceinline__ int fwd_table(SlabDesc* tab, const TcPointArgs& a) {
       int rows;
       d.img = LinvU + tc_linv_image(MP, p, sg, &rows);
       d.rows = rows; d.tmem_off = (uint32_t)(BW + BW - rows);
-      d.first = ((q == 0 && sl == 0) ? 1 : 0) | (q == p ? ((sl + 1) << 8) : 0);   // chunk sl of block p final
+      d.first = (q == 0 && sl == 0) ? 1 : 0;
     }
     tab[i] = d;
   }
@@ -513,38 +543,69 @@ __device__ __forceinline__ void warp_store_chunk16(float* dst, size_t ld, float*
 // S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
 // cross-covariance blocks q <= p (Linv is lower triangular); for MP > 256 block q is recomputed for every p >= q.
 // =================================================================================================
-// Warp roles (544 threads):
-//   warps 0..7   K PRODUCERS : phase A (x~ planes, row statistics), then per whitening slab: S chunk from TMEM ->
-//                              k = 2^(...) -> TF32 split -> A planes -> arrive.  They never touch the A accumulators.
-//   warps 8..15  EPILOGUE    : thread = point; chunk c of output block p is read from TMEM as soon as the issuer's
-//                              commit of whitening slab c (pass q == p) lands on chunk_bars[c]: mean / variance
-//                              partials, A saved for the backward; final mean / variance / sample of the tile
-//   warp 16      ISSUER      : TMA requests + MMAs (+ per-chunk commits)
-// The K producers run ahead into the next block / tile (its phase A and the first k slab) while the epilogue warps
-// finish; they wait on `epi_done` only before publishing the slab whose MMAs overwrite the A accumulators.
+// Warp roles (544 threads): TWO producer groups (warps 0..7 and 8..15) that own ALTERNATE pipeline slabs - group g
+// always writes ring stage g - and the issuer warp 16.  The per-slab work of a producer is a chain of latencies
+// (TMEM load -> exp -> stage acquire -> shared-memory stores under UMMA operand traffic -> proxy fence -> arrive) that
+// eight warps cannot hide: 2000 cycles per slab against 1536 cycles of MMAs (N = 256).  With two groups each chain
+// has two slab times, and the chunk epilogues (chunk c is final once whitening slab c of the pass q == p has retired,
+// which the owner of slab c + 2 learns from its stage acquire) are spread over both groups as well.
+// Both groups count every slab, but a group only ever waits on the barriers of its OWN stage (its phase can only move
+// when the group itself commits) - with one exception, the wait for S after phase A, whose last slab may belong to
+// the other group: the 512-thread barrier in front of it guarantees that the owner has seen the stage's previous use
+// retire, and the stage cannot advance another phase before this group publishes the slab in between.  (Waiting on
+// the other group's stage anywhere else can observe the barrier TWO phases later and alias.)
 constexpr int kTwoGroupThreads = 2 * kThreads + 32;
 constexpr int kTwoGroupIssuerWarp = 2 * kThreads / 32;
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+// all 512 producer threads (the issuer warp never joins)
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
+
+// Store of a [32 rows x 16 columns] half chunk held one row per lane (16 consecutive floats), without staging:
+// neighbouring lanes exchange two 16-byte pieces, so that every store instruction writes 32 contiguous bytes per lane
+// pair - complete sectors - instead of half sectors of 32 different rows.  `dst` = global address of (row 0 of the
+// warp, first column), `ld` = row pitch in floats, `nvalid` rows exist.
+__device__ __forceinline__ void warp_store_rows16(float* dst, size_t ld, const float (&v)[16], int lane, int nvalid) {
+  const bool odd = lane & 1;
+  float sx[8], rx[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {          // even lanes send pieces 1 and 3, odd lanes pieces 0 and 2
+    sx[i] = odd ? v[i] : v[4 + i];
+    sx[4 + i] = odd ? v[8 + i] : v[12 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rx[i] = __shfl_xor_sync(0xffffffffu, sx[i], 1);
+  const int row_a = lane & ~1, row_b = row_a + 1;
+  float* pa = dst + (size_t)row_a * ld + (odd ? 4 : 0);
+  float* pb = dst + (size_t)row_b * ld + (odd ? 4 : 0);
+  if (row_a < nvalid) {
+    *reinterpret_cast<float4*>(pa) = odd ? make_float4(rx[0], rx[1], rx[2], rx[3]) : make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(pa + 8) =
+        odd ? make_float4(rx[4], rx[5], rx[6], rx[7]) : make_float4(v[8], v[9], v[10], v[11]);
+  }
+  if (row_b < nvalid) {
+    *reinterpret_cast<float4*>(pb) = odd ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(rx[0], rx[1], rx[2], rx[3]);
+    *reinterpret_cast<float4*>(pb + 8) =
+        odd ? make_float4(v[12], v[13], v[14], v[15]) : make_float4(rx[4], rx[5], rx[6], rx[7]);
+  }
+}
 
 template <int BW>
 __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
-  __shared__ __align__(8) uint64_t chunk_bars[8];   // chunk c of the current output block is final (tcgen05.commit)
-  __shared__ __align__(8) uint64_t epi_done;        // the epilogue warps have read every chunk of the current block
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxFwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q (K warps); m, c = s^2 - 1 of block p
-  __shared__ float xn_s[TNP], xw_s[2][TNP];         // row statistics (xw: per tile parity, read by the epilogue warps)
-  __shared__ float mu_s[TNP], vv_s[TNP];
-  __shared__ float part_n[2 * TNP], part_w[2 * TNP];
-  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
+  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q; m, c = s^2 - 1 of block p
+  constexpr int kMaxDs = 4;                         // d-slabs of the x tile (D <= 128)
+  __shared__ float part_n[kMaxDs][2][TNP], part_w[kMaxDs][2][TNP];   // row-statistic partials per d-slab / chunk half
+  __shared__ float mu_s[4][TNP], vv_s[4][TNP];      // mean / variance partials per (group, column half)
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
-  const int NP = MP / BW, SPB = BW / KT;
+  const int NP = MP / BW;
+  constexpr int SPB = BW / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
@@ -552,17 +613,15 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
   const float* znc_g = ws_cptr<float>(a.ws, L.znc);
   const float* mvec_g = ws_cptr<float>(a.ws, L.mvec);
   const float* cvec_g = ws_cptr<float>(a.ws, L.cvec);
+  const float* wl = ws_cptr<float>(a.ws, L.wl);
   const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
   const float l2os = log2f(os);
+  const int DP = L.DP;
+  const int nds = DP >= KT ? DP / KT : 1;
 
   constexpr uint32_t TMEM_COLS = 2 * BW;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) {
-    init_ring_barriers(bars);
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&chunk_bars[i], 1);
-    tc::mbar_init(&epi_done, kThreads);
-    tc::fence_barrier_init();
-  }
+  if (tid == 0) init_ring_barriers(bars);
   if (tid < kThreads) {
     for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per (p, q) when MP > BW
       zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
@@ -577,133 +636,200 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
   tc::tc_fence_after();
   const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int quad = warp & 3, half = (warp >> 2) & 1;  // TMEM lane quadrant / column half of this warp
-  const int row = quad * 32 + lane;                   // the point this thread owns
-  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
   if (warp == kTwoGroupIssuerWarp) {
     // ---------------- issuer warp: one elected thread drives the TMA requests and the tensor core ----------------
-    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, nullptr, chunk_bars);
-  } else if (warp < 8) {
-    // ---------------- K producers ----------------
+    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
+  } else {
+    // ---------------- producer groups ----------------
+    const int g = warp >> 3;                          // group = ring stage this thread writes
+    const int quad = warp & 3, half = (warp >> 2) & 1;   // TMEM lane quadrant / column half of this warp
+    const int row = quad * 32 + lane;                 // the point this thread owns
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int slabs_per_tile = tab_n;
     Pipe<BW> pipe;
     pipe.init(stage_base, bars);
     long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #define SEG(i) do { if (a.dbg) { const long long tnow = clock64(); seg[i] += tnow - tlast; tlast = tnow; } } while (0)
-    OpRegs<TNP> xr0, xr1;
-    {
-      const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
-      load_x_slab(xr0, xl0, 0, L.DP);
-      if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
-    }
-    uint32_t blk = 0, tpar = 0;                       // output blocks started so far; tile parity
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1) {
+    // the first d-slab of a tile that this group owns (slab parity) is loaded one tile ahead
+    OpRegs<TNP> xr;
+    int ds_pre = g;                                   // tile 0 starts at slab 0: group g owns d-slab g
+    if (ds_pre < nds) load_x_slab(xr, make_xloader(a, (long long)blockIdx.x * TNP), ds_pre, DP);
+    // ---- phase A of one pass: S[128, BW] = X~ Z~[block q]^T, the d-slabs alternate between the groups.  (Issuing it
+    // one pass ahead, before the tail epilogue of the previous block, was measured: no gain - the tensor pipe, not
+    // the producers, paces these kernels.) ----
+    auto phase_a_slabs = [&](const XLoader& xl, bool first_pass) {
+      for (int ds = 0; ds < nds; ++ds) {
+        if ((pipe.slab & 1) != g) { pipe.skip(1); continue; }
+        OpRegs<TNP> ra;
+        if (first_pass && ds == ds_pre) ra = xr;
+        else load_x_slab(ra, xl, ds, DP);
+        transform_x_slab(ra, xl, ds, DP);
+        if (first_pass) {
+          // row-statistic partials (same (row, chunk) mapping as load_kmajor): the four chunk groups of a row sit
+          // in lanes rr, rr + 8, rr + 16, rr + 24 (fixed shuffle tree), the two chunk halves in neighbouring warps
+          const int gw = warp & 7, rr = lane & 7, cq = lane >> 3;
+#pragma unroll
+          for (int ps = 0; ps < OpRegs<TNP>::PASSES; ++ps) {
+            const int wt = gw + 8 * ps;
+            const int prow = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
+            const int dchunk = ds * (KT / 4) + c;
+            const float4 v = ra.v[ps];
+            const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // explicit FMA chains: the lambda is inlined at two call sites, and the outputs must not depend on how
+            // the compiler contracts each copy (shard invariance is tested bit-exactly)
+            float pn = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x)));
+            float pw = fmaf(v.w, w4.w, fmaf(v.z, w4.z, fmaf(v.y, w4.y, v.x * w4.x)));
+            pn += __shfl_xor_sync(0xffffffffu, pn, 8);
+            pw += __shfl_xor_sync(0xffffffffu, pw, 8);
+            pn += __shfl_xor_sync(0xffffffffu, pn, 16);
+            pw += __shfl_xor_sync(0xffffffffu, pw, 16);
+            if (cq == 0) { part_n[ds][wt & 1][prow] = pn; part_w[ds][wt & 1][prow] = pw; }
+          }
+        }
+        float *a_hi, *a_lo;
+        pipe.acquire(a_hi, a_lo);
+        store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+        pipe.commit();
+      }
+    };
+    bool have_prev = false;                           // deferred mean / variance / sample of the previous tile
+    long long prev_gn = 0;
+    float xw_prev = 0.f;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const long long n0 = (long long)tile * TNP;
       const XLoader xl = make_xloader(a, n0);
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
+      const long long w0 = n0 + quad * 32;        // first point of this warp
+      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
+      float mu = 0.f, vv = 0.f, xnc = 0.f;
       SEG(7);
-      for (int p = 0; p < NP; ++p, ++blk) {
+      // epilogue of one 32-column chunk c of output block p (16 columns per column half): mean / variance partials
+      // of the own point, A saved for the backward
+      auto epi_chunk = [&](int p, int c) {
+        const int col = c * 32 + half * 16;
+        float v[16];
+        tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          mu = fmaf(v[i], m_s[col + i], mu);
+          vv = fmaf(c_s[col + i] * v[i], v[i], vv);
+        }
+        if (L.training) warp_store_rows16(Ag + (size_t)w0 * MP + p * BW + col, MP, v, lane, nvalid);
+      };
+      for (int p = 0; p < NP; ++p) {
         for (int q = 0; q <= p; ++q) {
           const bool first_pass = p == 0 && q == 0;
           if (NP > 1) {                               // per-block constants (single block: loaded once at kernel start)
-            prod_sync();
-            zn_s[tid] = znc_g[q * BW + tid];          // BW == kThreads whenever NP > 1
-            prod_sync();
+            tc::tc_fence_before();
+            producers_sync();
+            if (tid < BW) {
+              zn_s[tid] = znc_g[q * BW + tid];
+              if (q == 0) { m_s[tid] = mvec_g[p * BW + tid]; c_s[tid] = cvec_g[p * BW + tid]; }
+            }
           }
-          phase_a<BW>(pipe, a, xl, first_pass, part_n, part_w, xn_s, xw_s[tpar], first_pass, xr0, xr1);
-          if (first_pass && more_tiles) {             // next tile's x: in flight during the MMAs and epilogues
-            const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-            load_x_slab(xr0, xln, 0, L.DP);
-            if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
+          phase_a_slabs(xl, first_pass);
+          // every producer has (a) read the previous output block out of the A accumulators - the first whitening
+          // slab below overwrites them -, (b) published its row-statistic partials / the block constants
+          tc::tc_fence_before();
+          producers_sync();
+          tc::tc_fence_after();
+          if (first_pass) {
+            float n2 = 0.f, xw = 0.f;
+            for (int ds = 0; ds < nds; ++ds) {        // fixed order (bit-deterministic)
+              n2 += part_n[ds][0][row] + part_n[ds][1][row];
+              xw += part_w[ds][0][row] + part_w[ds][1][row];
+            }
+            xnc = -0.72134752044448170f * n2;
+            if (g == 0 && half == 0) {
+              if (have_prev && prev_gn < N) {         // the previous tile's partials are complete (barrier above)
+                const float mean = mu_s[0][row] + mu_s[1][row] + mu_s[2][row] + mu_s[3][row] + xw_prev + cwb;
+                const float var = fmaxf(os + jit + vv_s[0][row] + vv_s[1][row] + vv_s[2][row] + vv_s[3][row], kMinVariance);
+                a.mean[prev_gn] = mean;
+                a.var[prev_gn] = var;
+                if (a.sample)
+                  a.sample[prev_gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)prev_gn, a.stream_id), mean);
+              }
+              xw_prev = xw;
+            }
+            if (more_tiles) {                         // next tile's first own d-slab: in flight during this tile
+              ds_pre = (((pipe.slab - nds + slabs_per_tile) & 1) == g) ? 0 : 1;
+              if (ds_pre < nds) load_x_slab(xr, make_xloader(a, n0 + (long long)gridDim.x * TNP), ds_pre, DP);
+            }
           }
-          SEG(0);                                     // phase A (x split, A planes published)
+          SEG(0);                                     // phase A (x split, A planes published, barrier)
           pipe.drain();                               // S of block q complete
           SEG(1);
-          const float xnc = -0.72134752044448170f * xn_s[row];
           // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
-          // the S columns of slab sl + 1 are requested from TMEM before slab sl is exponentiated (two register sets)
+          // this group owns the slabs sl = f, f + 2, ...; the S columns of its next slab are requested from TMEM
+          // before the current one is exponentiated (two register sets)
+          const int f = ((pipe.slab & 1) == g) ? 0 : 1;
           uint32_t sreg[2][16];
-          tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(half * 16), sreg[0]);
+          tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(f * KT + half * 16), sreg[0]);
 #pragma unroll
-          for (int sl = 0; sl < SPB; ++sl) {
+          for (int i = 0; i < SPB / 2; ++i) {
+            if (f == 1) pipe.skip(1);
+            const int sl = 2 * i + f;
             // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
             float v[16];
             const int col0 = sl * KT + half * 16;
-            tc::tmem_ld16_wait(sreg[sl & 1]);
-            if (sl + 1 < SPB) tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(col0 + KT), sreg[(sl + 1) & 1]);
+            tc::tmem_ld16_wait(sreg[i & 1]);
+            if (i + 1 < SPB / 2) tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(col0 + 2 * KT), sreg[(i + 1) & 1]);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i] = tc::ex2_approx(fminf(fmaf(__uint_as_float(sreg[sl & 1][i]), 1.4426950408889634f,
-                                               xnc + zn_s[col0 + i]), l2os));
+            for (int j = 0; j < 16; ++j)
+              v[j] = tc::ex2_approx(fminf(fmaf(__uint_as_float(sreg[i & 1][j]), 1.4426950408889634f,
+                                               xnc + zn_s[col0 + j]), l2os));
             SEG(2);                                   // TMEM load + exp
+            long long* ptr = (a.trace && blockIdx.x == 0 && (tid & 255) == 0 && pipe.slab < 48) ? a.trace + 512 + pipe.slab * 4 : nullptr;
+            if (ptr) ptr[0] = clock64();
             float *a_hi, *a_lo;
-            pipe.acquire(a_hi, a_lo);
-            SEG(3);                                   // stage acquire (MMA s-2 retired)
+            pipe.acquire(a_hi, a_lo);                 // slab sl - 2 (this group's previous one) has retired
+            if (ptr) ptr[1] = clock64();
+            SEG(3);
 #pragma unroll
             for (int c = 0; c < 4; ++c)               // k-chunks half * 4 + c of the slab
               tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
                               make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
             SEG(4);                                   // split + store of the k slab
-            // the MMAs of the first slab of an output block OVERWRITE the A accumulators: the epilogue warps must
-            // have read the previous block out of them
-            if (q == 0 && sl == 0 && blk > 0) tc::mbar_wait(&epi_done, (blk - 1) & 1);
+            if (ptr) ptr[2] = clock64();
             pipe.commit();
-            SEG(5);                                   // (epilogue wait) + fences + arrive
+            if (ptr) ptr[3] = clock64();
+            SEG(5);                                   // fences + arrive
+            if (q == p && sl >= 2) {                  // chunk sl - 2 is final: handled while the tensor core works on
+              tc::tc_fence_after();
+              epi_chunk(p, sl - 2);
+              SEG(6);
+            }
+            if (f == 0) pipe.skip(1);
+          }
+          if (q == p) {
+            // this group's last slab of the block: its chunk is final once it has retired
+            tc::mbar_wait(&bars[g], (pipe.uses[g] - 1) & 1);
+            tc::tc_fence_after();
+            epi_chunk(p, SPB - 2 + f);
+            SEG(6);
           }
         }
       }
+      mu_s[g * 2 + half][row] = mu;
+      vv_s[g * 2 + half][row] = vv;
+      have_prev = true;
+      prev_gn = n0 + row;
+    }
+    tc::tc_fence_before();
+    producers_sync();
+    if (g == 0 && half == 0 && have_prev && prev_gn < N) {
+      const float mean = mu_s[0][row] + mu_s[1][row] + mu_s[2][row] + mu_s[3][row] + xw_prev + cwb;
+      const float var = fmaxf(os + jit + vv_s[0][row] + vv_s[1][row] + vv_s[2][row] + vv_s[3][row], kMinVariance);
+      a.mean[prev_gn] = mean;
+      a.var[prev_gn] = var;
+      if (a.sample)
+        a.sample[prev_gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)prev_gn, a.stream_id), mean);
     }
     if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
       for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
 #undef SEG
-  } else {
-    // ---------------- epilogue warps ----------------
-    const int ew = warp - 8, etid = tid - kThreads;
-    uint32_t blk = 0, tpar = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1) {
-      const long long n0 = (long long)tile * TNP;
-      const long long gn = n0 + row;
-      const long long w0 = n0 + quad * 32;        // first point of this warp
-      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-      float mu = 0.f, vv = 0.f;
-      for (int p = 0; p < NP; ++p, ++blk) {
-        if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
-          group_sync(2);
-          m_s[etid] = mvec_g[p * BW + etid];          // BW == kThreads whenever NP > 1
-          c_s[etid] = cvec_g[p * BW + etid];
-          group_sync(2);
-        }
-        // chunk c (16 columns per column half) is final once whitening slab c of the pass q == p has retired (Linv is
-        // lower triangular): mean / variance partials of the own point, A saved for the backward
-        for (int c = 0; c < SPB; ++c) {
-          tc::mbar_wait(&chunk_bars[c], blk & 1);
-          tc::tc_fence_after();
-          const int col = c * 32 + half * 16;
-          float v[16];
-          tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            mu = fmaf(v[i], m_s[col + i], mu);
-            vv = fmaf(c_s[col + i] * v[i], v[i], vv);
-          }
-          if (L.training)
-            warp_store_chunk16(Ag + (size_t)w0 * MP + p * BW + col, MP, estg[ew], v, lane, nvalid);
-        }
-        tc::tc_fence_before();
-        mbar_arrive(&epi_done);                       // the K producers may let the next block overwrite A
-      }
-      if (half == 1) { mu_s[row] = mu; vv_s[row] = vv; }
-      group_sync(2);
-      if (half == 0 && gn < N) {
-        const float mean = mu + mu_s[row] + xw_s[tpar][row] + cwb;
-        const float var = fmaxf(os + jit + vv + vv_s[row], kMinVariance);
-        a.mean[gn] = mean;
-        a.var[gn] = var;
-        if (a.sample) a.sample[gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id), mean);
-      }
-      group_sync(2);
-    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -713,12 +839,12 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
 // =================================================================================================
 // backward: W = kbar o k and its row sums, one column block p of width BW at a time
 // =================================================================================================
-// Warp roles of the backward kernel (544 threads, 120 registers each):
+// Warp roles of the backward kernel (640 threads, 96 registers each; warps 17..19 idle):
 //   warps 0..7   ROW OWNERS : phase A (x~ planes, row statistics), epilogue chunks (thread = point), W stores
 //   warps 8..15  LOADERS    : the saved-A slabs of the T GEMM: global loads -> TF32 split -> A planes -> arrive
 //   warp 16      ISSUER     : TMA requests + MMAs (+ per-chunk commits)
 // The two producer groups share one operand ring; both count every slab, each arrives (256 threads) only on its own.
-constexpr int kBwdThreads = kTwoGroupThreads;
+constexpr int kBwdThreads = 640;   // (measured: 0.30 ms at 640 threads against 0.33 ms at 544, c5 M=256)
 constexpr int kBwdIssuerWarp = kTwoGroupIssuerWarp;
 
 template <int BW>
@@ -733,7 +859,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
   __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
-  __shared__ float part_n[2 * TNP], part_w[2 * TNP];
+  // per-slab row-statistic partials of phase A live in the same memory (row-owner warps only; separated from every
+  // staging use by the group barriers at the end of phase A and at the end of a tile)
+  float* part_n = &estg[0][0];
+  float* part_w = part_n + (KT / 4) * TNP;
+  static_assert(2 * (KT / 4) * TNP <= 8 * 32 * kStagePitch16, "row-statistic partials must fit in the staging tiles");
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -877,7 +1007,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
           rsum += t[i];
         }
         if (a.exp_mode != 4)
-          warp_store_chunk16(Wg + (size_t)w0 * MP + p * BW + col, MP, estg[warp], t, lane, nvalid);
+          warp_store_rows16(Wg + (size_t)w0 * MP + p * BW + col, MP, t, lane, nvalid);   // (no staging: lane-pair exchange)
       };
       for (int p = 0; p < NP; ++p, ++blk) {
         if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
@@ -968,7 +1098,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) 
   const uint32_t tmem_d = tmem_slot;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (warp == kIssuerWarp) {
-    issuer_loop<DPT>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
+    issuer_loop<DPT, true>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr, nullptr,
+                           !(a.exp_mode & 8));
   } else {
   Pipe<DPT> pipe;
   pipe.init(stage_base, bars);
@@ -1236,6 +1367,11 @@ int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* 
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
+  a.exp_mode = tile_override("GPBLUR_TC_EXP");
+  {
+    const char* tp = getenv("GPBLUR_FWD_TRACE_PTR");
+    a.trace = tp ? reinterpret_cast<long long*>(strtoull(tp, nullptr, 0)) : nullptr;
+  }
   const int grid = tc_grid(L);
   ProfScope ps(ST_POINT_FWD, st);
   if (L.MP == 128) {
