@@ -378,7 +378,7 @@ __device__ __forceinline__ void transform_x_slab(OpRegs<TNP>& ra, const XLoader&
 template <int BW>
 __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, const XLoader& xl, bool stats,
                                         float* part_n, float* part_w, float* xn_s, float* xw_s, bool preloaded,
-                                        const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1) {
+                                        const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1, uint64_t* gate, uint32_t blk) {
   const WsLayout& L = a.L;
   const float* wl = ws_cptr<float>(a.ws, L.wl);
   const int DP = L.DP;
@@ -407,6 +407,10 @@ __device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, co
     float *a_hi, *a_lo;
     pipe.acquire(a_hi, a_lo);
     store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
+    // `gate[ds / 2]` (one phase per block): the other producer group has passed this pair of slabs in its own slab
+    // count (see the loader warps of the backward kernel).  It gets there long before; the wait only rules out
+    // parity aliasing on the ring barriers.
+    if ((ds & 1) == 0) tc::mbar_wait(&gate[ds >> 1], blk & 1);
     pipe.commit();
     if (stats) {
       // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
@@ -853,6 +857,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[6];
   __shared__ __align__(8) uint64_t chunk_bars[8];                    // accumulator chunk c of the current block is final
+  __shared__ __align__(8) uint64_t ld_ready[2];                      // the loader warps have passed phase-A slabs 0-1 / 2-3 of the block
   __shared__ uint32_t tmem_slot;
   __shared__ SlabDesc tab[kMaxBwdSlabs];
   __shared__ int tab_n;
@@ -885,6 +890,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   if (tid == 0) {
     init_ring_barriers(bars);
     for (int i = 0; i < 8; ++i) tc::mbar_init(&chunk_bars[i], 1);
+    tc::mbar_init(&ld_ready[0], kThreads);
+    tc::mbar_init(&ld_ready[1], kThreads);
     tc::fence_barrier_init();
   }
   if (tid < kThreads) {
@@ -925,7 +932,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
         load_a(r0, NSL - 1);
         if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
         if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
-        pipe.skip_wait(nds);                          // the phase-A slabs of this block belong to the row owners
+        // the phase-A slabs of this block belong to the row owners.  skip_wait() tests the PREVIOUS use of the slab's
+        // stage; the row owners publish a pair of slabs only after the arrival for it, so no loader can find a ring barrier two
+        // phases further than it expects (parity aliasing)
+        for (int ds = 0; ds < nds; ds += 2) {
+          pipe.skip_wait(nds - ds < 2 ? nds - ds : 2);
+          mbar_arrive(&ld_ready[ds >> 1]);
+        }
         for (int s = NSL - 1; s >= s_lo; s -= 3) {
           float *a_hi, *a_lo;
           pipe.acquire(a_hi, a_lo);
@@ -1015,7 +1028,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
           if (tid < BW) { zn_s[tid] = znc_g[p * BW + tid]; beta_s[tid] = beta_g[p * BW + tid]; }
           group_sync(1);
         }
-        phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1);
+        phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1, ld_ready, blk);
         if (p == 0 && more_tiles) {
           const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
           load_x_slab(xr0, xln, 0, L.DP);
