@@ -6,7 +6,9 @@ import csv, json, re, subprocess, sys
 STAGE = [("mm_forward", "mm_fwd"), ("mm_backward", "mm_bwd"), ("tc_point_fwd", "point_fwd"), ("point_fwd", "point_fwd"),
          ("tc_point_bwd", "point_bwd"), ("point_bwd", "point_bwd"), ("tc_dx", "dx")]
 def stage_of(name):
-    if "reduce" in name:
+    if "stage_grad" in name:
+        return "sg_reduce"
+    if "tc_reduce" in name or "reduce_kernel<" in name:
         return "gram" if re.search(r"(1|true)>", name) else "wx"
     for k, v in STAGE:
         if k in name:

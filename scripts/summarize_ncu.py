@@ -48,13 +48,13 @@ try:
                          text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     h, units = r[0], r[1]
-    out.write("\n# ncu --set full, top kernels (one launch each)\n")
-    seen = set()
+    out.write("\n# ncu --set full, top kernels (the longest captured launch of each)\n")
+    ik, it = h.index("Kernel Name"), h.index("gpu__time_duration.sum")
+    best = {}
     for row in r[2:]:
-        name = row[h.index("Kernel Name")]
-        if name in seen:
-            continue
-        seen.add(name)
+        if row[ik] not in best or float(row[it]) > float(best[row[ik]][it]):
+            best[row[ik]] = row
+    for name, row in best.items():
         out.write(f"\n## `{name[:120]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
         for w in want:
             if w in h:
