@@ -63,32 +63,69 @@ __device__ __forceinline__ void park_tile(Tile& dst, const double (&v)[4], bool 
   }
 }
 
+// fp64 tensor-core step D(8x8) += A(8x4) B(4x8): lane = 4 g + t holds A[g][t], B[t][g], C[g][2t], C[g][2t + 1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Shared-memory scratch of tile_gemm: A as At[row][k] and B TRANSPOSED as Bt[col][k], pitch 34 doubles: the fragment
+// loads of dmma884 (address 34 g + t + const) then hit every 8-byte bank exactly twice (the minimum for 256 bytes).
+constexpr int GLD = TB + 2;
+constexpr int kGemmScratchDoubles = 2 * TB * GLD;
+
 // acc[i] (+)= sum_{k in [k0, k1)} A(r0 + ty + 8 i, k) * B(k, c0 + tx);  k0, k1 multiples of 32.
-// Software-pipelined: the global (L2) loads of k-step kk + 1 are in flight while step kk is multiplied out of shared
-// memory - these small fp64 GEMMs are latency-bound, one exposed L2 round trip per k-step was most of their time.
+// The 32 x 32 x 32 products run on the FP64 tensor path (mma.sync m8n8k4): warp w owns rows 8 (w & 3) .. + 8 and
+// columns 16 (w >> 2) .. + 16, i.e. two 8 x 8 accumulators sharing one A fragment - 3 shared-memory loads per 16
+// FMAs per lane, where the FFMA-style loop needed 5 loads per 4 and was bound by them (phases of the backward M x M
+// kernel: ~10 -> ~6 us at M = 256).  Software-pipelined: the global (L2) loads of k-step kk + 1 are in flight while
+// step kk is multiplied.  The accumulators go back to the callers' (row ty + 8 i, column tx) mapping through `scratch`.
 __device__ __forceinline__ void tile_gemm(double acc[4], const MatRef& A, int r0, const MatRef& B, int c0,
-                                          int k0, int k1, Tile& As, Tile& Bs) {
+                                          int k0, int k1, double* scratch) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (k0 >= k1) return;
+  double* At = scratch;
+  double* Bt = scratch + TB * GLD;
+  const int g = tx >> 2, t = tx & 3;
+  const int rw = 8 * (ty & 3), cw = 16 * (ty >> 2);
+  double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
   double ra[4], rb[4];
   fetch_tile(ra, A, r0, k0);
   fetch_tile(rb, B, k0, c0);
   for (int kk = k0; kk < k1; kk += TB) {
     __syncthreads();
-    park_tile(As, ra, A.trans);
-    park_tile(Bs, rb, B.trans);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      // fetch_tile(): non-transposed -> element (row r, column tx), transposed -> element (row tx, column r)
+      if (!A.trans) At[r * GLD + tx] = ra[i]; else At[tx * GLD + r] = ra[i];      // At[row = tile row][col = k]
+      if (!B.trans) Bt[tx * GLD + r] = rb[i]; else Bt[r * GLD + tx] = rb[i];      // Bt[col = tile column][row = k]
+    }
     __syncthreads();
     if (kk + TB < k1) {
       fetch_tile(ra, A, r0, kk + TB);
       fetch_tile(rb, B, kk + TB, c0);
     }
-#pragma unroll 8
-    for (int k = 0; k < TB; ++k) {
-      const double b = Bs[k][tx];
+    const double* ap = At + (rw + g) * GLD + t;
+    const double* bp0 = Bt + (cw + g) * GLD + t;
+    const double* bp1 = bp0 + 8 * GLD;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fma(As[ty + 8 * i][k], b, acc[i]);
+    for (int k4 = 0; k4 < TB; k4 += 4) {
+      const double a = ap[k4];
+      dmma884(c[0][0], c[0][1], a, bp0[k4]);
+      dmma884(c[1][0], c[1][1], a, bp1[k4]);
     }
   }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    At[(rw + g) * GLD + cw + 8 * j + 2 * t] = c[j][0];
+    At[(rw + g) * GLD + cw + 8 * j + 2 * t + 1] = c[j][1];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] += At[(ty + 8 * i) * GLD + tx];
 }
 
 // decode t -> (i, j) with j <= i, t = i (i + 1) / 2 + j
@@ -189,6 +226,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
   Tile& As = tiles[0];
   Tile& Bs = tiles[1];
+  double* gsm = reinterpret_cast<double*>(tiles + 11);   // tile_gemm scratch
   Tile* Cs = tiles + 2;   // 8 per-warp tiles
   Tile& Dg = tiles[10];   // factorised diagonal block of the current panel
 
@@ -448,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         for (int i = 0; i < 4; ++i)                      // C tile requested together with the operands
           cv[i] = L64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane];
         tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
-                  kb * TB + TB, As, Bs);
+                  kb * TB + TB, gsm);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = warp + 8 * i;
@@ -462,7 +500,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) yv[i] = T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane];
         }
-        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{Li64, MP, false}, j * TB, kb * TB, kb * TB + TB, As, Bs);
+        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{Li64, MP, false}, j * TB, kb * TB, kb * TB + TB, gsm);
 #pragma unroll
         for (int i = 0; i < 4; ++i) T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane] = yv[i] + acc[i];
       }
@@ -694,9 +732,7 @@ __global__ void __launch_bounds__(kThreads, 6) stage_grad_reduce_kernel(SgReduce
 __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
-  Tile& As = tiles[0];
-  Tile& Bs = tiles[1];
+  double* gsm = reinterpret_cast<double*>(smem_raw);      // tile_gemm scratch
 
   const WsLayout& L = a.L;
   const int D = L.D, DP = L.DP, M = L.M, MP = L.MP;
@@ -756,7 +792,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
         continue;
       }
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{T64, MP, false}, bj * TB, bi * TB, MP, As, Bs);
+      tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{T64, MP, false}, bj * TB, bi * TB, MP, gsm);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
@@ -778,7 +814,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       continue;
     }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_gemm(acc, MatRef{L64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, bi * TB, MP, As, Bs);
+    tile_gemm(acc, MatRef{L64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, bi * TB, MP, gsm);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
@@ -802,7 +838,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     // sum over k in [bj-tile, bi-tile]; operand zeros handle the ragged edges inside the diagonal tiles
     tile_gemm(acc, MatRef{T64, MP, false}, bi * TB, MatRef{Li64, MP, false}, bj * TB, bj * TB,
-              (bi + 1) * TB, As, Bs);
+              (bi + 1) * TB, gsm);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
@@ -815,7 +851,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     const int bi = t / nb, bj = t - bi * nb;
     const int kb0 = bi > bj ? bi : bj;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, kb0 * TB, MP, As, Bs);
+    tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, kb0 * TB, MP, gsm);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
@@ -929,7 +965,7 @@ int coop_grid(const void* func, int want, size_t smem) {
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
                       cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = sizeof(Tile) * 11;
+  const size_t smem = sizeof(Tile) * 11 + kGemmScratchDoubles * sizeof(double);
   if (!attr_set) {
     cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
@@ -953,7 +989,7 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = sizeof(Tile) * 2;
+  const size_t smem = kGemmScratchDoubles * sizeof(double);
   if (!attr_set) {
     cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;

@@ -490,58 +490,13 @@ __device__ __forceinline__ int bwd_table(SlabDesc* tab, const TcPointArgs& a) {
   return total;
 }
 
-// cross-covariance values of one 32-column chunk from the S accumulators:
+// Cross-covariance values from the S accumulators (inlined where used):
 //   k = os exp(-1/2 max(|x|^2 + |z|^2 - 2 s, 0)) = 2^min(s log2e + xnc + znc[m], log2 os)
 // with xnc = -1/2 log2e |x~|^2 and znc[m] = -1/2 log2e |z~_m|^2 + log2 os (-1e30 on padded columns => k = 0):
 // 4 FP32 instructions + one MUFU per element.
-__device__ __forceinline__ void kernel_values(float (&v)[32], float xnc, const float* znc_s, int col0, float l2os) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    v[i] = tc::ex2_approx(fminf(fmaf(v[i], 1.4426950408889634f, xnc + znc_s[col0 + i]), l2os));
-}
 
-// Epilogue store of a [32 rows x 32 columns] chunk owned by one warp (lane = row): every lane parks its 32 values in
-// its shared-memory staging row (pitch 36 floats: conflict-free 16-byte stores), then the warp writes the chunk out
-// transposed - 8 lanes cover one 128-byte row segment, 4 full lines per store instruction - instead of eight
-// 16-byte stores per lane that touch 32 different lines each.  `wstg` = staging of this warp (32 x 36 floats),
-// `dst` = global address of (row 0 of the warp, first column of the chunk), `ld` = row pitch, `nvalid` rows exist.
+// Pitch (floats) of a per-warp [32 rows x 32 columns] shared-memory staging tile: conflict-free 16-byte accesses.
 constexpr int kStagePitch = 36;
-__device__ __forceinline__ void warp_store_chunk32(float* dst, size_t ld, float* wstg, const float (&v)[32], int lane,
-                                                   int nvalid) {
-  __syncwarp();                                  // the previous chunk has been read out of the staging rows
-  float* mine = wstg + lane * kStagePitch;
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-  __syncwarp();
-  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + rsub;
-    const float4 t = *reinterpret_cast<const float4*>(wstg + r * kStagePitch + c4);
-    if (r < nvalid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c4) = t;
-  }
-}
-
-// Same for a [32 rows x 16 columns] half chunk (staging pitch 20 floats): 4 lanes cover one 64-byte row segment,
-// 8 rows per store instruction.  Used by the epilogue pieces that are interleaved with the MMA slabs, where the
-// operand ring is busy and the staging lives in its own 2.5 KB per warp.
-constexpr int kStagePitch16 = 20;
-__device__ __forceinline__ void warp_store_chunk16(float* dst, size_t ld, float* wstg, const float (&v)[16], int lane,
-                                                   int nvalid) {
-  __syncwarp();
-  float* mine = wstg + lane * kStagePitch16;
-#pragma unroll
-  for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-  __syncwarp();
-  const int rsub = lane >> 2, c4 = (lane & 3) * 4;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int r = it * 8 + rsub;
-    const float4 t = *reinterpret_cast<const float4*>(wstg + r * kStagePitch16 + c4);
-    if (r < nvalid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c4) = t;
-  }
-}
-
 // =================================================================================================
 // forward.  The inducing dimension is processed in column blocks of width BW (= min(MP, 256), the TMEM budget:
 // S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
@@ -628,7 +583,7 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
   if (tid == 0) init_ring_barriers(bars);
   if (tid < kThreads) {
     for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per (p, q) when MP > BW
-      zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
+      zn_s[i] = znc_g[i];                            // exponent offsets (formula above)
       m_s[i] = mvec_g[i];
       c_s[i] = cvec_g[i];
     }
@@ -863,12 +818,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   __shared__ int tab_n;
   __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
   __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
-  __shared__ __align__(16) float estg[8][32 * kStagePitch16];        // per-warp staging of the epilogue chunks
-  // per-slab row-statistic partials of phase A live in the same memory (row-owner warps only; separated from every
-  // staging use by the group barriers at the end of phase A and at the end of a tile)
-  float* part_n = &estg[0][0];
-  float* part_w = part_n + (KT / 4) * TNP;
-  static_assert(2 * (KT / 4) * TNP <= 8 * 32 * kStagePitch16, "row-statistic partials must fit in the staging tiles");
+  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];  // per-slab row-statistic partials of phase A
 
   const WsLayout& L = a.L;
   const int MP = L.MP;
@@ -896,7 +846,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArg
   }
   if (tid < kThreads) {
     for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per p when MP > BW
-      zn_s[i] = znc_g[i];                            // exponent offsets, see kernel_values()
+      zn_s[i] = znc_g[i];                            // exponent offsets (formula above)
       beta_s[i] = beta_g[i];
     }
     const int n = bwd_table<BW>(tab, a);
