@@ -31,6 +31,7 @@ struct MatRef {
   const double* p;
   int ld;
   bool trans;   // element(i, j) = trans ? p[j * ld + i] : p[i * ld + j]
+  const float* pf = nullptr;   // fp32 source instead of p (widened on load; fetch_tile() only)
 };
 
 // dst[r][c] = M(r0 + r, c0 + c), coalesced for both orientations.  256 threads.
@@ -50,7 +51,8 @@ __device__ __forceinline__ void fetch_tile(double (&v)[4], const MatRef& m, int 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = ty + 8 * i;
-    v[i] = m.trans ? m.p[(size_t)(c0 + r) * m.ld + r0 + tx] : m.p[(size_t)(r0 + r) * m.ld + c0 + tx];
+    const size_t off = m.trans ? (size_t)(c0 + r) * m.ld + r0 + tx : (size_t)(r0 + r) * m.ld + c0 + tx;
+    v[i] = m.pf ? (double)m.pf[off] : m.p[off];
   }
 }
 __device__ __forceinline__ void park_tile(Tile& dst, const double (&v)[4], bool trans) {
@@ -79,7 +81,7 @@ constexpr int kGemmScratchDoubles = 2 * TB * GLD;
 // The 32 x 32 x 32 products run on the FP64 tensor path (mma.sync m8n8k4): warp w owns rows 8 (w & 3) .. + 8 and
 // columns 16 (w >> 2) .. + 16, i.e. two 8 x 8 accumulators sharing one A fragment - 3 shared-memory loads per 16
 // FMAs per lane, where the FFMA-style loop needed 5 loads per 4 and was bound by them (phases of the backward M x M
-// kernel: ~10 -> ~6 us at M = 256).  Software-pipelined: the global (L2) loads of k-step kk + 1 are in flight while
+// kernel: ~10 -> ~7.5 us at M = 256; neither a two-deep operand prefetch nor four accumulator chains changed that).  Software-pipelined: the global (L2) loads of k-step kk + 1 are in flight while
 // step kk is multiplied.  The accumulators go back to the callers' (row ty + 8 i, column tx) mapping through `scratch`.
 __device__ __forceinline__ void tile_gemm(double acc[4], const MatRef& A, int r0, const MatRef& B, int c0,
                                           int k0, int k1, double* scratch) {
@@ -874,27 +876,65 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
 
   GPBLUR_STAMP();
   // ---------------- phase 6: Kzz-path + a-space gradients of Z; per-(i, d) terms of d ell -------
-  for (int idx = gtid; idx < MP * DP; idx += gsize) {
-    const int i = idx / DP, d = idx - i * DP;
-    double tval = 0.0;
-    if (i < M && d < D) {
-      double V = 0.0, rz = 0.0;
-      for (int j = 0; j < M; ++j) {
-        const double w = U64[(size_t)i * MP + j];
-        V = fma(w, (double)Zt[(size_t)j * DP + d], V);
-        rz += w;
+  // V = Wzz Z~ is an [MP, MP] x [MP, DP] product: 32 x 32 tiles on the FP64 tensor path (a thread-per-(i, d) loop over
+  // j exposed one L2 round trip per few terms: 16 us at M = 256, 166 us at M = 1024); the row sums of Wzz come from a
+  // lane-strided pass with a fixed shuffle tree.
+  auto zgrad_terms = [&](int i, int d, double V, double rz) {
+    const double wx = WX64[(size_t)i * DP + d];
+    const double ie = (double)inv_ell[d];
+    const double csum = vec64[i];
+    const double z = (double)Zt[(size_t)i * DP + d];
+    const double wxt = (wx - csum * (double)center[d]) * ie;          // (W^T Xtilde)_id
+    const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
+    a.bucket[(size_t)i * D + d] = (float)dz;
+    return -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
+  };
+  if (DP >= TB) {
+    __shared__ double rz_s[TB];
+    const int ndt = DP / TB;
+    for (int t = blockIdx.x; t < nb * ndt; t += G) {
+      const int bi = t / ndt, bd = t - bi * ndt;
+      __syncthreads();
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int r = warp + 8 * r4;
+        const double* urow = U64 + (size_t)(bi * TB + r) * MP;
+        double sacc = 0.0;
+        for (int j = lane; j < MP; j += 32) sacc += urow[j];
+        sacc = warp_sum(sacc);
+        if (lane == 0) rz_s[r] = sacc;
       }
-      if (d == 0) rz64[i] = rz;
-      const double wx = WX64[(size_t)i * DP + d];
-      const double ie = (double)inv_ell[d];
-      const double csum = vec64[i];
-      const double z = (double)Zt[(size_t)i * DP + d];
-      const double wxt = (wx - csum * (double)center[d]) * ie;          // (W^T Xtilde)_id
-      const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
-      a.bucket[(size_t)i * D + d] = (float)dz;
-      tval = -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      tile_gemm(acc, MatRef{U64, MP, false}, bi * TB, MatRef{nullptr, DP, false, Zt}, bd * TB, 0, MP, gsm);
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int i = bi * TB + warp + 8 * r4, d = bd * TB + lane;
+        double tval = 0.0;
+        if (i < M && d < D) {
+          const double rz = rz_s[warp + 8 * r4];
+          if (d == 0) rz64[i] = rz;
+          tval = zgrad_terms(i, d, acc[r4], rz);
+        }
+        t64[(size_t)i * DP + d] = tval;
+      }
     }
-    t64[idx] = tval;
+  } else {
+    // DP = 16: thread per (i, d)
+    for (int idx = gtid; idx < MP * DP; idx += gsize) {
+      const int i = idx / DP, d = idx - i * DP;
+      double tval = 0.0;
+      if (i < M && d < D) {
+        double V = 0.0, rz = 0.0;
+        for (int j = 0; j < M; ++j) {
+          const double w = U64[(size_t)i * MP + j];
+          V = fma(w, (double)Zt[(size_t)j * DP + d], V);
+          rz += w;
+        }
+        if (d == 0) rz64[i] = rz;
+        tval = zgrad_terms(i, d, V, rz);
+      }
+      t64[idx] = tval;
+    }
   }
   grid.sync();
 
