@@ -241,6 +241,37 @@ def test_backward_linearity_at_full_size(cuda):
         assert rel(a + 2 * b, c) < 2e-4
 
 
+@pytest.mark.parametrize("D,M", [(64, 256), (128, 256), (64, 512)])
+def test_tile_position_invariance_of_the_tensor_core_kernels(cuda, D, M):
+    """The tensor-core point kernels are persistent: a CTA that owns several 128-point tiles lets its producer groups
+    run ahead of each other across slab / tile boundaries (two producer groups in the forward; row owners, loaders and
+    per-chunk barriers in the backward; two gates when D = 128; two column blocks when M = 512).  One shot over 282
+    tiles (two tiles on most CTAs) must reproduce three shards of 94 tiles (one tile per CTA): outputs bit-exactly,
+    dx to rounding, parameter gradients up to the order of the fp32 / fp64 partial sums."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    B, L = 1500, 24
+    gen = torch.Generator(device=cuda).manual_seed(11)
+    names = ["inducing_points", "raw_lengthscale", "raw_outputscale", "variational_mean", "variational_stddev",
+             "weights", "bias"]
+    p = {k: v.to(cuda).requires_grad_(True) for k, v in O.init_params_exercise(D, M, 5).items()}
+    x = torch.randn(B, L, D, device=cuda, generator=gen).requires_grad_(True)
+    gm = torch.randn(B, L, device=cuda, generator=gen)
+    gv = torch.randn(B, L, device=cuda, generator=gen)
+
+    def run(lo, hi):
+        xs = x[lo:hi].detach().requires_grad_(True)
+        mean, var, _, _, _ = ops.svgp_predict(xs, *(p[k] for k in names))
+        g = torch.autograd.grad([mean, var], [xs] + [p[k] for k in names], [gm[lo:hi], gv[lo:hi]])
+        return mean.detach(), var.detach(), g
+    m_all, v_all, g_all = run(0, B)
+    parts = [run(lo, lo + 500) for lo in (0, 500, 1000)]
+    assert torch.equal(torch.cat([q[0] for q in parts]), m_all)
+    assert torch.equal(torch.cat([q[1] for q in parts]), v_all)
+    assert rel(torch.cat([q[2][0] for q in parts]), g_all[0]) < 1e-6                     # dx: per-point work only
+    for i in range(1, len(g_all)):
+        assert rel(sum(q[2][i] for q in parts), g_all[i]) < 2e-4, names[i - 1]
+
+
 def test_sharded_wrapper_single_process(cuda):
     from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
     from fine_grained_gaussian_process_forcasting_b200.distributed import ShardedGPBlur
