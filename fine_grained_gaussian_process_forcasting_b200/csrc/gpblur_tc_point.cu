@@ -41,9 +41,9 @@ struct TcPointArgs {
   const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
   uint32_t stream_id;
   int ntiles;
-  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP; results are WRONG): 4 = skip the W chunk stores,
-                    // 6 = skip the saved-A slab loads / stores of the backward (upper bound of a loader warp group)
-  long long* trace; // optional event trace buffer (GPBLUR_TRACE_PTR = device address, debugging only)
+  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP): 4 = skip the W chunk stores of the backward (results
+                    // are WRONG), bit 3 (8) = no TMA-request polling in the dx issuer (results unchanged)
+  long long* trace; // optional event trace buffer (GPBLUR_TRACE_PTR / GPBLUR_FWD_TRACE_PTR = device address)
   long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
 };
 
