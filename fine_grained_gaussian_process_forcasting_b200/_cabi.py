@@ -86,6 +86,7 @@ SIGNATURES = {
         C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
         C.POINTER(C.c_int), C.c_void_p]),
     "gpblur_profile_enable": (C.c_int, [C.c_int]),
+    "gpblur_debug_set_trace": (C.c_int, [C.c_void_p]),
     "gpblur_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.c_int]),
     "gpblur_launch_count": (C.c_ulonglong, []),
     "gpblur_last_cuda_error": (C.c_char_p, []),

@@ -34,12 +34,17 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def _flags():
+    """GPBLUR_TRACE=1 compiles the clock64 event trace of the tensor-core point kernels in (scripts/tc2_trace.py)."""
+    return NVCC_FLAGS + (["-DGPBLUR_TRACE=1"] if os.environ.get("GPBLUR_TRACE") == "1" else [])
+
+
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -63,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path):
         obj = OBJ / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *_flags(), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ / (src.stem + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:

@@ -43,6 +43,9 @@ struct OffsetDevScope {
   ~OffsetDevScope() { g_offset_dev = nullptr; }
 };
 
+static std::atomic<long long*> g_trace{nullptr};
+long long* debug_trace_buffer() { return g_trace.load(std::memory_order_relaxed); }
+
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
@@ -224,6 +227,16 @@ inline int ew_grid(long long n, int block) { return (int)((n + block - 1) / bloc
 
 }  // namespace
 
+int dispatch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
+                           uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
+  if (tc_point_supported(L)) {
+    if (tc2_point_supported(L) && tile_override("GPBLUR_TC_V") != 1)
+      return launch_tc2_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+    return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  }
+  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+}
+
 int launch_stage_grad_reduce(const WsLayout& L, const void* ws, double* sgrad, cudaStream_t st) {
   if (tc_point_supported(L)) return stage_grad_reduce_impl(L, ws, sgrad, tc_vector_partials(L), L.splitsZ, st);
   return stage_grad_reduce_impl(L, ws, sgrad, bwd_vector_partials(L), 0, st);
@@ -232,6 +245,11 @@ int launch_stage_grad_reduce(const WsLayout& L, const void* ws, double* sgrad, c
 }  // namespace gpblur
 
 using namespace gpblur;
+
+namespace gpblur {
+int dispatch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
+                           uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st);
+}
 
 extern "C" {
 
@@ -264,8 +282,7 @@ int gpblur_svgp_forward(const gpblur_svgp_params* p, const float* x, long long N
   rc = launch_mm_forward(*p, L, ws, kl, info, st);
   if (rc) return rc;
   if (N == 0) return GPBLUR_OK;
-  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
-  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  return dispatch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
 size_t gpblur_svgp_param_stage_bytes(int D, int M) {
@@ -304,8 +321,7 @@ int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long
   if (param_stage != ws) cudaMemcpyAsync(ws, param_stage, pbytes, cudaMemcpyDeviceToDevice, st);
   int rc = check_launch("param_stage_copy");
   if (rc || N == 0) return rc;
-  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
-  return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
+  return dispatch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
 int gpblur_svgp_forward_cached(const gpblur_svgp_params* p, const float* x, long long N, int D, int M, float* mean,
@@ -468,13 +484,18 @@ int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, voi
     case 0: off = L.L64; bytes = mm8; break;
     case 1: off = L.Linv64; bytes = mm8; break;
     case 2: off = L.K64; bytes = mm8; break;
-    case 3: off = L.A; bytes = (size_t)N * L.MP * 4; break;
+    case 3: off = L.A; bytes = (size_t)(L.MP >= 128 ? round_up_ll(N, 128) : N) * L.MP * 4; break;   // tile-major if MP >= 128
     case 4: off = L.stamps; bytes = kStampSlots * 8; break;
     default: return GPBLUR_EINVAL;
   }
   if (out_bytes < bytes) return GPBLUR_EWORKSPACE;
   cudaMemcpyAsync(out, ws_cptr<char>(ws, off), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return check_launch("debug_fetch");
+}
+
+int gpblur_debug_set_trace(void* device_buffer) {
+  g_trace.store(static_cast<long long*>(device_buffer));
+  return GPBLUR_OK;
 }
 
 int gpblur_profile_enable(int on) {

@@ -52,6 +52,7 @@ struct WsLayout {
   size_t hyp, hyp64, stamps, inv_ell, ell, center, wl, Zt, ZtT, zn, znc, mvec, cvec, svec, beta;
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
   size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
+  size_t ZtQ;                      // Z~ images in row blocks of tc_bq(MP) (TS-form point kernels)
   size_t v64, t64;                 // fp64 scratch of the M x M backward (part of the parameter stage)
   size_t A, W, Spart, upart, WXpart, vecpart, gsc, rrow, cpart, sgrad;
   size_t total;
@@ -61,6 +62,11 @@ struct WsLayout {
 // Every image is [hi plane | lo plane], a plane is [8 k-chunks][rows][4 floats] (64 * rows floats per image).
 // The inducing dimension is processed in column blocks of width BW = min(MP, 256).
 __host__ __device__ inline int tc_bw(int MP) { return MP >= 256 ? 256 : MP; }
+// TS-form point kernels: the cross-covariance logits S are formed in column blocks of BQ = min(MP, 128) inducing points
+__host__ __device__ inline int tc_bq(int MP) { return MP >= 128 ? 128 : MP; }
+__host__ __device__ inline size_t tc_zq_image(int MP, int nds, int q, int ds) {
+  return (size_t)(q * nds + ds) * 64 * tc_bq(MP);
+}
 // Z~ images: block q (rows m = q BW + r, r < BW), d-slab ds (k = d)
 __host__ __device__ inline size_t tc_zt_image(int MP, int nds, int q, int ds) {
   return (size_t)(q * nds + ds) * 64 * tc_bw(MP);
@@ -99,6 +105,14 @@ __host__ __device__ inline size_t tc_lct_image(int MP, int p, int s, int* rows) 
 }
 __host__ __device__ inline size_t tc_lct_total(int MP) { return tc_lct_image(MP, MP / tc_bw(MP), MP / 32, nullptr); }
 __host__ __device__ inline size_t tc_slab_ztt(int dpt, int s) { return (size_t)s * 64 * dpt; }
+
+// Tile-major layout of the saved [N, MP] matrices A and W of the tensor-core path: per 128-point tile
+// [MP / 4 column pieces][128 rows][4 floats].  A thread that owns one point (row) and 16 consecutive columns writes /
+// reads 4 float4, and the 32 lanes of a warp (32 consecutive rows) touch 512 contiguous bytes per instruction instead
+// of 32 different lines.  Returns the FLOAT index of element (n, m).
+__host__ __device__ inline size_t tc_tiled_index(long long n, int m, int MP) {
+  return ((((size_t)(n >> 7) * (size_t)(MP >> 2) + (size_t)(m >> 2)) << 7) + (size_t)(n & 127)) * 4 + (size_t)(m & 3);
+}
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -150,6 +164,7 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     w.LinvU = take(tc_linv_total(w.MP) * 4);
     w.LCTU = take(tc_lct_total(w.MP) * 4);
     w.ZtTU = take(nsl * 64 * dpt * 4);
+    w.ZtQ = take(nds * 64 * MP * 4);
   }
   const int tp = w.MP < 128 ? w.MP : 128;
   const int nt = w.MP / tp;
@@ -176,8 +191,10 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
   w.v64 = take((size_t)(3 * MP + w.vec_len) * 8);
   w.t64 = take((size_t)MP * DP * 8);
   if (training) {
-    w.A = take((size_t)N * MP * 4);
-    w.W = take((size_t)N * MP * 4);
+    // the tensor-core kernels keep A and W TILE-major (see tc_tiled_index): whole 128-point tiles
+    const size_t Nt = w.MP >= 128 ? (size_t)round_up_ll(N, 128) : (size_t)N;
+    w.A = take(Nt * MP * 4);
+    w.W = take(Nt * MP * 4);
     w.Spart = take((size_t)w.splitsS * MP * MP * 4);
     w.upart = take((size_t)w.splitsS * MP * 4);
     w.WXpart = take((size_t)w.splitsZ * MP * DP * 4);
@@ -284,6 +301,7 @@ __device__ __forceinline__ uint64_t rng_offset(uint64_t offset, const unsigned l
   return offset + (offset_dev ? (uint64_t)*offset_dev : 0ull);
 }
 int check_launch(const char* what);
+long long* debug_trace_buffer();      // device buffer registered with gpblur_debug_set_trace (null: tracing off)
 int num_sms();
 int tile_override(const char* env);   // 0 = heuristic, else forced tile height (tuning knob)
 
@@ -310,5 +328,9 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
                              const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
                              uint32_t stream_id, float* dx, cudaStream_t st);
 int tc_vector_partials(const WsLayout& L);
+// TS-form (A operand in tensor memory) point kernels
+bool tc2_point_supported(const WsLayout& L);
+int launch_tc2_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
+                             uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st);
 
 }  // namespace gpblur

@@ -563,6 +563,22 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       base[(c * BW + r) * 4 + e] = hi;
       base[32 * BW + (c * BW + r) * 4 + e] = lo;
     }
+    // the same values in row blocks of BQ = tc_bq(MP) (TS-form point kernels)
+    {
+      float* ZtQ = ws_ptr<float>(a.ws, L.ZtQ);
+      const int BQ = tc_bq(MP), NQ = MP / BQ;
+      for (int idx = gtid; idx < NQ * nds * 8 * BQ * 4; idx += gsize) {
+        const int e = idx & 3, r = (idx >> 2) % BQ, c = ((idx >> 2) / BQ) & 7, img = (idx >> 2) / (BQ * 8);
+        const int q = img / nds, ds = img - q * nds;
+        const int d = ds * 32 + c * 4 + e;
+        const float v = (d < DP) ? Zt[(size_t)(q * BQ + r) * DP + d] : 0.f;
+        float hi, lo;
+        split(v, hi, lo);
+        float* base = ZtQ + tc_zq_image(MP, nds, q, ds);
+        base[(c * BQ + r) * 4 + e] = hi;
+        base[32 * BQ + (c * BQ + r) * 4 + e] = lo;
+      }
+    }
     // Z~^T slabs (rows d, k = m): element (c, r, e) of slab s = Zt[32 s + 4 c + e][r]
     for (int idx = gtid; idx < nsl * 8 * dpt * 4; idx += gsize) {
       const int e = idx & 3, r = (idx >> 2) % dpt, c = ((idx >> 2) / dpt) & 7, sl = (idx >> 2) / (dpt * 8);

@@ -55,8 +55,11 @@ class FlatGradBucket:
         """Sum (or mean) the bucket across ranks.  No-op when torch.distributed is not initialised."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-        if average:
+        # NCCL averages inside the collective (no separate div_ kernel; capturable in a CUDA graph); gloo has no AVG
+        use_avg = average and self.flat.is_cuda and dist.get_backend(group) == "nccl"
+        op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
+        if average and not use_avg:
             if async_op:
                 work.wait()
                 work = None
@@ -64,14 +67,31 @@ class FlatGradBucket:
         return work
 
 
+def _gp_layers(module: nn.Module):
+    from .gpcompat import DeepGPLayer
+    return [m for m in module.modules() if isinstance(m, DeepGPLayer)]
+
+
 def broadcast_parameters(module: nn.Module, src: int = 0, group=None) -> None:
+    """Make every rank hold rank `src`'s parameters and buffers.
+
+    The first-call variational initialisation (gpytorch: variational_mean <- 1e-3 randn from the rank's own RNG)
+    is run BEFORE the broadcast, so that it cannot overwrite the broadcast values on the first forward and leave the
+    replicas different for good.  The broadcast writes through ``p.detach()`` (shares the version counter, unlike
+    ``p.data``), so parameter stages / KL values cached on the tensor versions are invalidated; they are also
+    dropped explicitly."""
+    layers = _gp_layers(module)
+    for layer in layers:
+        layer.variational_strategy._ensure_initialized()
     if not (dist.is_available() and dist.is_initialized()):
         return
     with torch.no_grad():
         for _, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
-            dist.broadcast(p.data, src=src, group=group)
+            dist.broadcast(p.detach(), src=src, group=group)
         for _, b in sorted(module.named_buffers(), key=lambda kv: kv[0]):
-            dist.broadcast(b.data, src=src, group=group)
+            dist.broadcast(b.detach(), src=src, group=group)
+    for layer in layers:
+        layer.invalidate_param_stage()
 
 
 class ShardedGPBlur(nn.Module):
@@ -92,15 +112,16 @@ class ShardedGPBlur(nn.Module):
         self.step_index = 0
 
     def _layers(self):
-        from .gpcompat import DeepGPLayer
-        return [m for m in self.model.modules() if isinstance(m, DeepGPLayer)]
+        return _gp_layers(self.model)
 
     def forward(self, x_local, y_local=None, first_global_window: int = 0, global_windows: Optional[int] = None,
                 num_data=None):
         L = x_local.shape[-2]
         total = (global_windows if global_windows is not None else x_local.shape[0]) * L
         for layer in self._layers():
+            # counters of GP h, point n: step * total * H + h * total + (global n): identical for any rank count
             layer._rng_offset = self.step_index * total * max(1, layer.output_dims or 1) + first_global_window * L
+            layer._rng_h_stride = total
         self.step_index += 1
         return self.model.blur(x_local, y_local, num_data=num_data)
 

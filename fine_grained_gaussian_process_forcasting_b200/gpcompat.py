@@ -305,10 +305,20 @@ class MultivariateNormal:
         return self.mean - std2, self.mean + std2
 
     def expand(self, *shape):
-        def ex(t):
-            return None if t is None else t.expand(*shape)
-        return self.__class__(ex(self._mean), None, variance=ex(self._variance), sample=ex(self._sample),
-                              kl=self.kl, layer=self._layer)
+        """Leading sample dimension S of DeepGP outputs.  S == 1 (the reference, train.py:20) is a pure view
+        (``unsqueeze``: no reduction kernel in its backward); for S > 1 the single fused sample is dropped, so that
+        ``rsample()`` draws S * n independent Philox counters like gpytorch's Normal(...).rsample() on the expanded
+        distribution."""
+        if len(shape) == self._mean.dim() + 1 and shape[0] == 1:
+            def ex(t):
+                return None if t is None else t.unsqueeze(0)
+            keep_sample = True
+        else:
+            def ex(t):
+                return None if t is None else t.expand(*shape)
+            keep_sample = False
+        return self.__class__(ex(self._mean), None, variance=ex(self._variance),
+                              sample=ex(self._sample) if keep_sample else None, kl=self.kl, layer=self._layer)
 
     def __add__(self, other):
         return MultivariateNormal(self._mean + other, self._covar, variance=self._variance, sample=self._sample,
@@ -460,6 +470,7 @@ class DeepGPLayer(ApproximateGP):
         self._rng_seed = 0
         self._rng_offset = 0
         self._rng_stream = 0
+        self._rng_h_stride = None          # Philox counter stride between the H GPs (None: the points of the call)
         self.fused_sample = True
         self.last_info = None
         self.rng_offset_dev = None         # optional int64 device scalar added to the Philox offset (graphs.py)
@@ -530,7 +541,7 @@ class DeepGPLayer(ApproximateGP):
         mean, var, sample, kl, info = ops.svgp_predict(inputs, *self._layer_params(), seed, off, stream,
                                                        want_sample=self.fused_sample,
                                                        stage_cache=self._stage_cache(),
-                                                       offset_dev=self.rng_offset_dev)
+                                                       offset_dev=self.rng_offset_dev, h_stride=self._rng_h_stride)
         self.last_info = info
         if check_cholesky.value():
             k = int(info.max().item())

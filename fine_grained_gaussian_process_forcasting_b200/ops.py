@@ -203,7 +203,8 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
     if which == 4:
         out = torch.empty(32, device=ws.device, dtype=torch.int64)
     elif which == 3:
-        out = torch.empty(N, Mp, device=ws.device, dtype=torch.float32)
+        Nt = (N + 127) // 128 * 128 if Mp >= 128 else N     # tensor-core path: whole 128-point tiles, tile-major
+        out = torch.empty(Nt, Mp, device=ws.device, dtype=torch.float32)
     else:
         out = torch.empty(Mp, Mp, device=ws.device, dtype=torch.float64)
     with torch.cuda.device(ws.device):
@@ -211,6 +212,9 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
                                             C.byref(mp), _stream())
     _cabi.check(rc, "gpblur_debug_fetch")
     assert mp.value == Mp
+    if which == 3 and Mp >= 128:
+        # [tile][Mp / 4 pieces][128 rows][4] -> [N, Mp]   (csrc/gpblur_common.cuh: tc_tiled_index)
+        out = out.reshape(-1, Mp // 4, 128, 4).permute(0, 2, 1, 3).reshape(-1, Mp)[:N].contiguous()
     return out
 
 
@@ -453,7 +457,7 @@ class _PointFunction(torch.autograd.Function):
     With an [H, G] token (multi-output layer) every output gains a trailing H: mean [..., H]."""
 
     @staticmethod
-    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample, offset_dev):
+    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample, offset_dev, h_stride=None):
         shape = x.shape
         D = shape[-1]
         x2 = _f32c(x).reshape(-1, D)
@@ -461,6 +465,7 @@ class _PointFunction(torch.autograd.Function):
         batched = token.dim() == 2
         H = token.shape[0] if batched else 1
         training = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        hs = N if h_stride is None else int(h_stride)       # Philox counter stride between the H GPs of a layer
         nout = 3 if want_sample else 2
         out = torch.empty(H, nout * N, device=x2.device, dtype=torch.float32)
         stage = holder["stage"]
@@ -471,13 +476,13 @@ class _PointFunction(torch.autograd.Function):
         try:
             for h in range(H):
                 fork.enter(h)
-                point_forward_raw(stage[h], x2, M, seed, offset + h * N, stream_id, want_sample, training,
+                point_forward_raw(stage[h], x2, M, seed, offset + h * hs, stream_id, want_sample, training,
                                   out=out[h], offset_dev=offset_dev, ws=wss[h])
         finally:
             fork.join()
         if training:
             ctx.save_for_backward(x2, out, *wss)
-        ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout)
+        ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout, hs)
         ctx.offset_dev = offset_dev
         ctx.set_materialize_grads(False)
         out_shape = tuple(shape[:-1]) + ((H,) if batched else ())
@@ -491,7 +496,7 @@ class _PointFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mean, g_var, g_sample):
         x2, out, *wss = ctx.saved_tensors
-        seed, offset, stream_id, M, shape, H, batched, nout = ctx.meta
+        seed, offset, stream_id, M, shape, H, batched, nout, hs = ctx.meta
         N, D = x2.shape
         dev = x2.device
 
@@ -511,14 +516,15 @@ class _PointFunction(torch.autograd.Function):
             for h in range(H):
                 fork.enter(h)
                 point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
-                                   None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * N, stream_id,
+                                   None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * hs, stream_id,
                                    wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h],
                                    offset_dev=ctx.offset_dev)
         finally:
             fork.join()
         if dx is not None:
             dx = (dx.sum(0) if H > 1 else dx[0]).reshape(shape)
-        return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None, None)
+        return (dx, (sgrad if batched else sgrad[0]) if need[1] else None, None, None, None, None, None, None, None,
+                None)
 
 
 def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
@@ -558,10 +564,11 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
                  want_sample: bool = False, stage_cache: Optional[dict] = None,
-                 offset_dev: Optional[Tensor] = None):
+                 offset_dev: Optional[Tensor] = None, h_stride: Optional[int] = None):
     """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]); with inducing points [H, M, D]
     (multi-output layer) the outputs are [..., H], kl [H], info [H], and GP h draws its sample with Philox counters
-    offset + h * N + n.  `stage_cache`: see svgp_param_stage.  `offset_dev`: optional int64 device scalar added to
+    offset + h * h_stride + n (h_stride defaults to the N points of this call; batch-sharded callers pass the GLOBAL
+    point count so that the counters do not depend on the number of ranks).  `stage_cache`: see svgp_param_stage.  `offset_dev`: optional int64 device scalar added to
     `offset` when the kernels run (CUDA-graph replays draw fresh counters by bumping it between replays)."""
     token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
                                                variational_stddev, mean_weights, mean_bias, stage_cache)
@@ -570,7 +577,7 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
         e = x.new_empty(shp, dtype=torch.float32)
         return e, e.clone(), (e.clone() if want_sample else None), kl, info
     mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
-                                             int(stream_id), bool(want_sample), offset_dev)
+                                             int(stream_id), bool(want_sample), offset_dev, h_stride)
     return mean, var, sample, kl, info
 
 

@@ -179,6 +179,10 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
 int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
                        size_t out_bytes, int* mp, void* stream);
 
+/* Developer probe: register a device buffer (>= 32 KB, zero-filled by the caller) that CTA 0 of the tensor-core
+ * point kernels fills with clock64 event stamps (scripts/tc2_trace.py); NULL switches tracing off (default). */
+int gpblur_debug_set_trace(void* device_buffer);
+
 /* Optional per-stage timing for bench.py's roofline: while enabled, every launch is bracketed with CUDA
  * events on its own stream.  gpblur_profile_collect synchronises on the recorded events, writes the
  * accumulated milliseconds / launch counts per stage (order: mm_fwd, point_fwd, point_bwd, gram, wx,

@@ -223,6 +223,16 @@ def _gloo_worker(rank, world, port, out):
     gathered = [torch.zeros_like(z0) for _ in range(world)]
     dist.all_gather(gathered, z0)
     same = all(torch.equal(gathered[0], g) for g in gathered)
+    # the first-call variational init (1e-3 randn from each rank's own RNG) ran BEFORE the broadcast and cannot run
+    # again on the first forward: the replicas hold rank 0's variational mean and keep it
+    vs = model.hidden_layer.variational_strategy
+    torch.manual_seed(1000 + rank)
+    vs._ensure_initialized()                                  # what the first forward does: must be a no-op now
+    vm = vs._variational_distribution.variational_mean.detach().clone()
+    gvm = [torch.zeros_like(vm) for _ in range(world)]
+    dist.all_gather(gvm, vm)
+    same = same and all(torch.equal(gvm[0], g) for g in gvm) and bool(vm.abs().max() > 0) \
+        and int(vs.variational_params_initialized) == 1
     bucket.zero()
     zeroed = all(float(p.grad.abs().max()) == 0.0 for p in params)
     if rank == 0:
