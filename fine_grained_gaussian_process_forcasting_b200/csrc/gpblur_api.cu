@@ -229,11 +229,7 @@ inline int ew_grid(long long n, int block) { return (int)((n + block - 1) / bloc
 
 int dispatch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
                            uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
-  if (tc_point_supported(L)) {
-    if (tc2_point_supported(L) && tile_override("GPBLUR_TC_V") != 1)
-      return launch_tc2_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
-    return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
-  }
+  if (tc_point_supported(L)) return launch_tc_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
   return launch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, st);
 }
 
@@ -486,6 +482,7 @@ int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, voi
     case 2: off = L.K64; bytes = mm8; break;
     case 3: off = L.A; bytes = (size_t)(L.MP >= 128 ? round_up_ll(N, 128) : N) * L.MP * 4; break;   // tile-major if MP >= 128
     case 4: off = L.stamps; bytes = kStampSlots * 8; break;
+    case 5: off = L.W; bytes = (size_t)(L.MP >= 128 ? round_up_ll(N, 128) : N) * L.MP * 4; break;   // W = kbar o k (after a backward)
     default: return GPBLUR_EINVAL;
   }
   if (out_bytes < bytes) return GPBLUR_EWORKSPACE;

@@ -53,6 +53,7 @@ struct WsLayout {
   size_t K64, L64, Linv64, T64, U64, LinvT32, LC32, Linv32, LCT32;
   size_t ZtU, LinvU, LCTU, ZtTU;   // constant operands pre-split (TF32 hi | lo) in UMMA slab layout (tensor-core path)
   size_t ZtQ;                      // Z~ images in row blocks of tc_bq(MP) (TS-form point kernels)
+  size_t LCTQ;                     // (diag(c) Linv)^T images in row blocks of tc_bq(MP) (TS-form backward)
   size_t v64, t64;                 // fp64 scratch of the M x M backward (part of the parameter stage)
   size_t A, W, Spart, upart, WXpart, vecpart, gsc, rrow, cpart, sgrad;
   size_t total;
@@ -105,6 +106,23 @@ __host__ __device__ inline size_t tc_lct_image(int MP, int p, int s, int* rows) 
 }
 __host__ __device__ inline size_t tc_lct_total(int MP) { return tc_lct_image(MP, MP / tc_bw(MP), MP / 32, nullptr); }
 __host__ __device__ inline size_t tc_slab_ztt(int dpt, int s) { return (size_t)s * 64 * dpt; }
+// TS-form backward: (diag(c) Linv)^T images in column blocks of BT = tc_bq(MP): image (p, s), k-slab s >= p BT / 32,
+// holds rows j = p BT + r, r < min(BT, 32 (s + 1) - p BT), k = i = 32 s + 4 c + e: value c_i Linv[i][j] (0 for j > i).
+// Returns the float offset, *rows the row count.
+__host__ __device__ inline size_t tc_lctq_image(int MP, int p, int s, int* rows) {
+  const int BT = tc_bq(MP), spb = BT / 32, nsl = MP / 32;
+  size_t off = 0;
+  for (int pp = 0; pp < p; ++pp)      // slabs of block pp itself: rows 32, 64, ..., BT; slabs above it: BT rows each
+    off += (size_t)64 * ((size_t)16 * spb * (spb + 1) + (size_t)(nsl - (pp + 1) * spb) * BT);
+  for (int ss = p * spb; ss < s; ++ss) {
+    const int r = 32 * (ss + 1) - p * BT;
+    off += (size_t)64 * (r < BT ? r : BT);
+  }
+  const int r = 32 * (s + 1) - p * BT;
+  if (rows) *rows = r < BT ? r : BT;
+  return off;
+}
+__host__ __device__ inline size_t tc_lctq_total(int MP) { return tc_lctq_image(MP, MP / tc_bq(MP), MP / 32, nullptr); }
 
 // Tile-major layout of the saved [N, MP] matrices A and W of the tensor-core path: per 128-point tile
 // [MP / 4 column pieces][128 rows][4 floats].  A thread that owns one point (row) and 16 consecutive columns writes /
@@ -165,6 +183,7 @@ inline WsLayout make_layout(long long N, int D, int M, int training) {
     w.LCTU = take(tc_lct_total(w.MP) * 4);
     w.ZtTU = take(nsl * 64 * dpt * 4);
     w.ZtQ = take(nds * 64 * MP * 4);
+    w.LCTQ = take(tc_lctq_total(w.MP) * 4);
   }
   const int tp = w.MP < 128 ? w.MP : 128;
   const int nt = w.MP / tp;
@@ -328,9 +347,5 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
                              const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
                              uint32_t stream_id, float* dx, cudaStream_t st);
 int tc_vector_partials(const WsLayout& L);
-// TS-form (A operand in tensor memory) point kernels
-bool tc2_point_supported(const WsLayout& L);
-int launch_tc2_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
-                             uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st);
 
 }  // namespace gpblur

@@ -595,23 +595,26 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     // One image per CTA at a time, the threads stride over its elements with independent loads in flight (a grid-wide
     // strided loop PER IMAGE cost one exposed L2 round trip per image: 8 us at M = 256, 88 us at M = 1024).
     {
+      // forward images (output blocks of BW = tc_bw(MP)) and backward images (column blocks of BT = tc_bq(MP))
+      float* LCTQ = ws_ptr<float>(a.ws, L.LCTQ);
+      const int BT = tc_bq(MP), NPT = MP / BT, spt = BT / 32;
       const int n_fwd = spb * NP * (NP + 1) / 2;
-      const int n_bwd = NP * nsl - spb * NP * (NP - 1) / 2;
-      int parts = G / (n_fwd + n_bwd);              // few images (M = 256: 16): several CTAs share one image
+      const int n_bwd = NPT * nsl - spt * NPT * (NPT - 1) / 2;
+      int parts = G / (n_fwd + n_bwd);              // few images (M = 256: 20): several CTAs share one image
       parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
       for (int unit = blockIdx.x; unit < (n_fwd + n_bwd) * parts; unit += G) {
         const int img = unit / parts, part = unit - img * parts;
         const bool fwd_img = img < n_fwd;
         int rem = fwd_img ? img : img - n_fwd, pp = 0;
         while (true) {
-          const int cnt = fwd_img ? (pp + 1) * spb : nsl - pp * spb;
+          const int cnt = fwd_img ? (pp + 1) * spb : nsl - pp * spt;
           if (rem < cnt) break;
           rem -= cnt;
           ++pp;
         }
-        const int sl = fwd_img ? rem : pp * spb + rem;
+        const int sl = fwd_img ? rem : pp * spt + rem;
         int nr;
-        float* base = fwd_img ? LinvU + tc_linv_image(MP, pp, sl, &nr) : LCTU + tc_lct_image(MP, pp, sl, &nr);
+        float* base = fwd_img ? LinvU + tc_linv_image(MP, pp, sl, &nr) : LCTQ + tc_lctq_image(MP, pp, sl, &nr);
         const int ilo = (pp + 1) * BW - nr;
 #pragma unroll 4
         for (int idx = part * kThreads + tid; idx < 8 * nr * 4; idx += parts * kThreads) {
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
             const int i = ilo + r, j = 32 * sl + 4 * c + e;
             v = (j <= i) ? (float)Li64[(size_t)i * MP + j] : 0.f;
           } else {
-            const int i = 32 * sl + 4 * c + e, j = pp * BW + r;
+            const int i = 32 * sl + 4 * c + e, j = pp * BT + r;
             v = (j <= i) ? (float)Li64[(size_t)i * MP + j] * cvec[i] : 0.f;
           }
           float hi, lo;

@@ -1,31 +1,49 @@
-// Per-point forward / backward of the whitened SVGP on the 5th-gen tensor cores (tcgen05, 3xTF32) for
-// padded inducing counts MP in {128, 256}.  One CTA owns a tile of 128 points = the M dimension of the MMA; the
-// accumulators live in TMEM (S = x~ z~^T in columns [0, MP), the whitened / back-substituted product in columns
-// [MP, 2 MP)); in every epilogue a thread owns ONE point (TMEM lane), so mean / variance / row sums need no
-// cross-thread reduction, and the exp()'d cross-covariance goes straight from TMEM registers into the next MMA's
-// shared-memory operand planes: it never touches HBM.
+// Per-point forward / backward of the whitened SVGP on the 5th-gen tensor cores, TS form (tcgen05.mma with the A
+// operand in TENSOR MEMORY): replaces, per DeepGPp.predict call, gpytorch's batched kernel build + fp64
+// trsm_batched + predictive mean / variance kernels (/root/reference/denoising_model/DeepGP.py:56-73, 94-99) and
+// their autograd backward.
 //
-//   forward  : S = X~ Z~^T -> k = os exp(-1/2 d^2) -> A = k Linv^T (block-triangular: slab s only feeds columns
-//              >= 32 s) -> mean, var, sample; A saved for the backward.
-//   backward : S again, T = a (diag(c) Linv) (slabs in decreasing order so the first MMA initialises every column)
-//              -> kbar = g_mu beta + 2 g_var T, W = kbar o k, r = rowsum(W); W and r go to HBM once.
-//   dx       : dx = (W Z~ - r x~) / ell + g_mu w as a third small GEMM (N = Dp) + the per-dimension reductions.
-// Operand tiles are produced by the 8 producer warps (coalesced 16-byte loads, TF32 hi/lo split, canonical K-major
-// no-swizzle UMMA layout); a 9th warp walks a per-CTA slab table with warp-uniform values and one elected lane issues
-// the TMA requests and the MMAs; tcgen05.commit -> mbarrier tracks completion; epilogue chunks are interleaved with
-// the slabs (an accumulator chunk is final as soon as the last slab that touches it has retired).
-#include <cstdlib>
-
+// One CTA owns a tile of 128 points = the M dimension of the MMA and the 128 TMEM lanes.  A producer thread owns
+// ONE point (lane) and 16 of the 32 k-values of a pipeline slab, so every A operand - the scaled inputs x~, the
+// exp()'d cross-covariance k, the saved whitened a, W = kbar o k - goes from registers straight into tensor memory
+// with tcgen05.st (hi plane | lo plane of the 3xTF32 split): no shared-memory stores, no proxy fences, and the
+// tensor core reads only the constant B operand (pre-split slab images pulled by cp.async.bulk) from shared memory.
+// The round-1 SS-form kernels spent 80 KB of shared-memory traffic per slab on the A planes and were bound by it
+// (DESIGN.md section 5).
+//
+// TMEM columns (fp32):  [ S : BQ | ACC : BWO | A operand ring : 64 per stage (hi 32 | lo 32) ]
+//   forward : S = X~ Z~[q]^T for a block of BQ = min(MP, 128) inducing points; ACC = whitened product for an
+//             output block of BWO = min(MP, 256) columns: every whitening MMA of the blocks below the diagonal
+//             has N = BWO, the cross-covariance of a block is exponentiated exactly once per output block.
+// Pipeline: slab g uses A stage g & 1 and B stage g % NSTB; every wait is on a barrier whose NEXT phase cannot
+// complete without the waiter's own arrival (or is signalled once per block for exactly one waiting group), so a
+// parity can never be observed two phases late.
 #include "gpblur_tc.cuh"
+
+// clock64 event trace of CTA 0 (scripts/tc2_trace.py): compiled out of release builds (GPBLUR_TRACE=1 python -m ...build)
+#ifndef GPBLUR_TRACE
+#define GPBLUR_TRACE 0
+#endif
+#if GPBLUR_TRACE
+#define TRACE_PTR(cond, expr) ((cond) ? (expr) : nullptr)
+#else
+#define TRACE_PTR(cond, expr) (static_cast<long long*>(nullptr))
+#endif
 
 namespace gpblur {
 
 namespace {
 
-constexpr int KT = 32;
-constexpr int TNP = 128;   // points per tile (MMA M)
+constexpr int KT = 32;          // k-values per pipeline slab (4 UMMA k-steps)
+constexpr int TNP = 128;        // points per tile (MMA M)
+constexpr int kGroup = 256;     // threads per producer group (8 warps: 4 lane quadrants x 2 k-halves)
+constexpr int kProducers = 2 * kGroup;
+constexpr int kIssuerWarp = kProducers / 32;
+constexpr int kCtaThreads = kProducers + 128;   // + the issuer warpgroup: warp 16 issues, warps 17..19 only donate registers
+constexpr int kRegsIssuer = 32, kRegsProducer = 112;   // setmaxnreg: 512 x 112 + 128 x 32 = 61440 = 640 x 96 (the launch allocation)
+constexpr int kMaxDs = 4;       // d-slabs of the x tile (D <= 128)
 
-struct TcPointArgs {
+struct Tc2Args {
   WsLayout L;
   void* ws;
   const float* x;
@@ -41,483 +59,240 @@ struct TcPointArgs {
   const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
   uint32_t stream_id;
   int ntiles;
-  int exp_mode;     // timing experiments only (GPBLUR_TC_EXP): 4 = skip the W chunk stores of the backward (results
-                    // are WRONG), bit 3 (8) = no TMA-request polling in the dx issuer (results unchanged)
-  long long* trace; // optional event trace buffer (GPBLUR_TRACE_PTR / GPBLUR_FWD_TRACE_PTR = device address)
-  long long* dbg;   // optional cycle accounting (GPBLUR_TC_DEBUG=1): [thread 0 | thread 32][16 segments]
+  long long* trace;   // optional clock64 event trace of CTA 0 (gpblur_debug_set_trace; null in production)
 };
 
-template <int NB>   // NB = row capacity of the B operand planes
-struct Stage {
-  static constexpr int A_PLANE = (KT / 4) * TNP * 4;   // floats
-  static constexpr int B_PLANE = (KT / 4) * NB * 4;
-  static constexpr int FLOATS = 2 * A_PLANE + 2 * B_PLANE;
+// One pipeline slab = one K = 32 step of one GEMM of the tile.  The sequence is the same for every tile: tabulated
+// once per CTA in shared memory, walked by the issuer warp.
+struct Slab {
+  const float* img;    // B image in global memory: [hi plane | lo plane], a plane is [8 k-chunks][rows][4 floats]
+  int rows;            // B rows = MMA N
+  uint32_t tmem_off;   // accumulator column offset inside the CTA's TMEM allocation
+  uint32_t flags;      // SF_* | (1 + chunk barrier index) << 8
+};
+constexpr uint32_t SF_FIRST = 1u;    // the first MMA overwrites the accumulator
+constexpr uint32_t SF_SIG_S = 2u;    // commit onto s_full: S of this pass is complete once the slab retires
+constexpr uint32_t SF_SIG_DX = 4u;   // commit onto dx_full (backward): the dx accumulator of the tile is complete
+constexpr uint32_t SF_GRP_E = 8u;    // (backward) the A operand comes from the row-owner group's private stage
+
+struct Bars {
+  uint64_t a_ready[3];   // producers -> issuer: the A operand of the slab in this stage is in tensor memory
+  uint64_t mma_done[3];  // tcgen05.commit: the MMAs that read this A stage have retired
+  uint64_t b_full[6];    // cp.async.bulk complete_tx: the B image of this stage has landed
+  uint64_t b_empty[6];   // tcgen05.commit: the MMAs that read this B stage have retired
+  uint64_t s_full;       // the S block of the current pass is complete
+  uint64_t chunk[8];     // accumulator chunk c of the current output block is final
 };
 
-constexpr int kIssuerWarp = kThreads / 32;         // warp 8: the dedicated TMA / MMA issuer
-constexpr int kBlockThreads = kThreads + 32;       // 8 producer / epilogue warps + the issuer warp
-
-// named barrier among the 256 producer threads only (the issuer warp never joins it)
-__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-
-// One pipeline slab = one K = 32 step of one GEMM of the tile: the producers write the A planes of ring stage
-// (slab & 1), the TMA engine brings the pre-split B image, the issuer thread fires 3 x 4 MMAs into TMEM.
-// The sequence of slabs is the same for every tile, so it is tabulated ONCE per CTA in shared memory and the issuer
-// (lane 0 of warp 8) runs a tight loop over the table: its per-slab critical path is only barrier waits, 12
-// tcgen05.mma with incrementally updated descriptors, one commit and the next TMA request.
-constexpr int kMaxFwdSlabs = 10 * (4 + 8);   // NP (NP + 1) / 2 block pairs x (d-slabs + 8 whitening slabs), M <= 1024
-constexpr int kMaxBwdSlabs = 4 * 4 + 32 + 24 + 16 + 8;   // sum over p of (d-slabs + NSL - p SPB)
-struct SlabDesc {
-  const float* img;    // B image in global memory (hi plane | lo plane), rows x 32 k each
-  int rows;            // B rows = MMA N (also sets the leading byte offset of the B descriptor)
-  uint32_t tmem_off;   // accumulator column offset inside the CTA's TMEM allocation
-  int first;           // bit 0: the first MMA overwrites the accumulator (no accumulate);
-                       // bits 8..: 1 + index of the chunk barrier to signal when this slab's MMAs retire (0 = none)
-};
-
-// Ring barriers:
-//   bars[0..1] mma_done : tcgen05.commit - the MMAs that read stage st have retired (stage reusable)
-//   bars[2..3] b_full   : the TMA bulk copy of stage st's B planes has landed (complete_tx)
-//   bars[4..5] a_ready  : all 256 producers have written (and proxy-fenced) stage st's A planes
-__device__ __forceinline__ void init_ring_barriers(uint64_t* br) {
-  tc::mbar_init(&br[0], 1); tc::mbar_init(&br[1], 1);
-  tc::mbar_init(&br[2], 1); tc::mbar_init(&br[3], 1);
-  tc::mbar_init(&br[4], kThreads); tc::mbar_init(&br[5], kThreads);
-  tc::fence_barrier_init();
-}
-
-template <int NB>
-__device__ __forceinline__ void issue_bulk_b(float* base, uint64_t* bars, int st, const float* image, int rows) {
-  float* b_hi = base + st * Stage<NB>::FLOATS + 2 * Stage<NB>::A_PLANE;
-  float* b_lo = b_hi + Stage<NB>::B_PLANE;
-  const uint32_t bytes = (uint32_t)rows * 128u;          // 8 k-chunks x rows x 16 B
-  tc::mbar_expect_tx(&bars[2 + st], 2 * bytes);
-  tc::bulk_g2s(b_hi, image, bytes, &bars[2 + st]);
-  tc::bulk_g2s(b_lo, image + (size_t)rows * 32, bytes, &bars[2 + st]);
-}
-
-// The issuer: the whole warp 8 walks the table with WARP-UNIFORM values (lane-0 broadcasts of the table entries), one
-// elected lane executes the tcgen05 / TMA / commit instructions.  Uniform operands live in uniform registers: a
-// single thread with per-thread registers costs ~100 cycles per MMA in register -> uniform-register conversion loops
-// (measured with scripts/dx_trace.py), more than the execution time of an N <= 128 MMA.
-// `ntiles_mine` tiles, each `nslabs` table entries.
-// POLL: see the comment at the MMA loop.  Measured on c5 M=256 (same box A/B): dx kernel 0.183 -> 0.171 ms, backward
-// kernel 0.272 -> 0.296 ms, forward neutral - so only the dx kernel polls.  The test is additionally predicated on the
-// run-time flag `poll_rt` (GPBLUR_TC_EXP bit 3 clears it): with a compile-time-only condition ptxas lays the poll out
-// differently and the dx kernel is SLOWER than without polling (0.186 ms).
-template <int NB, bool POLL = false>
-__device__ __noinline__ void issuer_loop(float* base, uint64_t* bars, uint32_t tmem_base, const SlabDesc* tab, int nslabs,
-                                         int ntiles_mine, long long* trace = nullptr, uint64_t* chunk_bars = nullptr, bool poll_rt = true) {
-  if (ntiles_mine <= 0 || nslabs <= 0) return;
-  constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);      // SBO = 128 B, version 1
-  constexpr uint64_t kALbo = (uint64_t)((TNP * 16) >> 4) << 16;                         // A planes: 128 rows
-  const uint32_t base_addr = tc::uniform_u32(tc::smem_u32(base));
-  tmem_base = tc::uniform_u32(tmem_base);
-  nslabs = (int)tc::uniform_u32((uint32_t)nslabs);
-  ntiles_mine = (int)tc::uniform_u32((uint32_t)ntiles_mine);
-  uint64_t a_hi_desc[2], a_lo_desc[2], b_hi_base[2], b_lo_base[2];
-#pragma unroll
-  for (int st = 0; st < 2; ++st) {
-    const uint32_t a_hi = base_addr + st * Stage<NB>::FLOATS * 4;
-    const uint32_t a_lo = a_hi + Stage<NB>::A_PLANE * 4;
-    const uint32_t b_hi = a_lo + Stage<NB>::A_PLANE * 4;
-    const uint32_t b_lo = b_hi + Stage<NB>::B_PLANE * 4;
-    a_hi_desc[st] = kDescHi | kALbo | (uint64_t)(a_hi >> 4);
-    a_lo_desc[st] = kDescHi | kALbo | (uint64_t)(a_lo >> 4);
-    b_hi_base[st] = kDescHi | (uint64_t)(b_hi >> 4);
-    b_lo_base[st] = kDescHi | (uint64_t)(b_lo >> 4);
-  }
-  auto request_b = [&](int st, int entry) {
-    const float* img = reinterpret_cast<const float*>(tc::uniform_u64(reinterpret_cast<uint64_t>(tab[entry].img)));
-    const int rows = (int)tc::uniform_u32((uint32_t)tab[entry].rows);
-    if (tc::elect_one()) issue_bulk_b<NB>(base, bars, st, img, rows);
-    __syncwarp();
-  };
-  uint32_t uses[2] = {0, 0};
-  request_b(0, 0);
-  int slab = 0;
-  for (int t = 0; t < ntiles_mine; ++t) {
-    for (int i = 0; i < nslabs; ++i, ++slab) {
-      const int st = slab & 1;
-      const uint32_t phase = uses[st] & 1;
-      const uint32_t rows = tc::uniform_u32((uint32_t)tab[i].rows);
-      const uint32_t tmem_d = tmem_base + tc::uniform_u32(tab[i].tmem_off);
-      const uint32_t first_sig = tc::uniform_u32((uint32_t)tab[i].first);
-      const uint32_t first = first_sig & 1u, sig = first_sig >> 8;
-      const uint32_t idesc = tc::make_idesc_tf32(TNP, (int)rows);
-      const uint64_t dbh0 = b_hi_base[st] | ((uint64_t)rows << 16);        // LBO = rows * 16 B
-      const uint64_t dbl0 = b_lo_base[st] | ((uint64_t)rows << 16);
-      const uint64_t dah0 = a_hi_desc[st], dal0 = a_lo_desc[st];
-      const uint64_t bstep = (uint64_t)(2 * rows);                         // two k-chunks of rows * 16 B, >> 4
-      long long* tr = (trace && slab < 48 && (threadIdx.x & 31) == 0) ? trace + slab * 6 : nullptr;
-      if (tr) tr[0] = clock64();
-      tc::mbar_wait(&bars[4 + st], phase);        // A planes written
-      if (tr) tr[1] = clock64();
-      tc::mbar_wait(&bars[2 + st], phase);        // B image landed
-      if (tr) tr[2] = clock64();
-      tc::tc_fence_after();
-      // TMA request for the next slab's B image into the other stage.  If that stage's last readers have already
-      // retired (the usual case: the producers are slower than the tensor core), the request goes out BEFORE this
-      // slab's MMAs are issued, so the L2 round trip overlaps the issue time instead of following it.
-      const bool more = (i + 1 < nslabs) || (t + 1 < ntiles_mine);
-      const int nst = st ^ 1;
-      const int nxt = (i + 1 < nslabs) ? i + 1 : 0;
-      bool requested = !more;
-      if (more) {
-        const uint32_t freed = uses[nst] == 0 ? 1u : tc::uniform_u32(tc::mbar_test(&bars[nst], (uses[nst] - 1) & 1) ? 1u : 0u);
-        if (freed) {
-          request_b(nst, nxt);
-          requested = true;
-        }
-      }
-      // The MMA issue BLOCKS once the tensor-core queue is full (12 MMAs take 1400 - 2000 cycles to issue), and the
-      // other stage is released by the previous slab's MMAs somewhere in the middle of that.  With POLL the elected
-      // thread tests that barrier between k-steps and sends the next slab's TMA request from there instead of after
-      // the last MMA (scripts/fwd_trace.py shows the request path).
-      if constexpr (POLL) {
-        uint32_t req_flag = requested ? 1u : 0u;
-        if (tc::elect_one()) {
-          const float* nimg = tab[nxt].img;
-          const int nrows = tab[nxt].rows;
-          const uint32_t nparity = (uses[nst] - 1) & 1;
-#pragma unroll
-          for (int j = 0; j < KT / 8; ++j) {
-            const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
-            const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
-            tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
-            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-            if (poll_rt && !req_flag && tc::mbar_test(&bars[nst], nparity)) {
-              issue_bulk_b<NB>(base, bars, nst, nimg, nrows);
-              req_flag = 1u;
-            }
-          }
-          tc::umma_commit(&bars[st]);
-          if (sig) tc::umma_commit(&chunk_bars[sig - 1]);
-        }
-        __syncwarp();
-        requested = __any_sync(0xffffffffu, req_flag != 0);
-      } else {
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int j = 0; j < KT / 8; ++j) {
-            const uint64_t dah = dah0 + (uint64_t)(j * 2 * TNP), dal = dal0 + (uint64_t)(j * 2 * TNP);
-            const uint64_t dbh = dbh0 + (uint64_t)j * bstep, dbl = dbl0 + (uint64_t)j * bstep;
-            tc::umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);   // small cross terms first
-            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-          }
-          tc::umma_commit(&bars[st]);
-          if (sig) tc::umma_commit(&chunk_bars[sig - 1]);   // an accumulator chunk is final: tell the row-owner warps
-        }
-        __syncwarp();
-      }
-      if (tr) tr[3] = clock64();
-      uses[st] += 1;
-      if (tr) tr[5] = requested ? 0 : 1;          // 1: the request had to wait for the previous slab's MMAs
-      if (!requested) {                           // the other stage was still being read: wait, then request
-        if (uses[nst] > 0) tc::mbar_wait(&bars[nst], (uses[nst] - 1) & 1);
-        request_b(nst, nxt);
-      }
-      if (tr) tr[4] = clock64();
-    }
-  }
-}
-
-// Producer-side view of the ring (warps 0..7; every producer thread keeps the same counters).
-template <int NB>
-struct Pipe {
-  float* base;
-  uint64_t* bars;
-  uint32_t uses[2];
-  int slab;
-  __device__ __forceinline__ void init(float* b, uint64_t* br) { base = b; bars = br; uses[0] = uses[1] = 0; slab = 0; }
-  // wait until the MMAs that last read this stage have retired, return its A planes
-  __device__ __forceinline__ void acquire(float*& a_hi, float*& a_lo) {
-    const int st = slab & 1;
-    if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
-    a_hi = base + st * Stage<NB>::FLOATS;
-    a_lo = a_hi + Stage<NB>::A_PLANE;
-  }
-  // advance over slabs produced by ANOTHER warp group (both groups count every slab of the shared ring)
-  // (the caller must be synchronised with the retirement of the skipped slabs some other way - the row owners wait on
-  // the chunk barriers - or the parity waits of acquire() alias)
-  __device__ __forceinline__ void skip(int n) {
-    for (int i = 0; i < n; ++i) { uses[slab & 1] += 1; slab += 1; }
-  }
-  // same, but staying within two slabs of the retired MMAs like a producing group does: the parity of a ring barrier
-  // is only meaningful one phase ahead, and the slab that follows the skipped ones must not be published before the
-  // other group has published (and the tensor core retired) the skipped ones
-  __device__ __forceinline__ void skip_wait(int n) {
-    for (int i = 0; i < n; ++i) {
-      const int st = slab & 1;
-      if (uses[st] > 0) tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
-      uses[st] += 1;
-      slab += 1;
-    }
-  }
-  // publish this stage's A planes to the issuer (no CTA barrier)
-  __device__ __forceinline__ void commit() {
-    const int st = slab & 1;
-    tc::tc_fence_before();
-    tc::fence_async_smem();
-    mbar_arrive(&bars[4 + st]);
-    uses[st] += 1;
-    slab += 1;
-  }
-  // block until every MMA of the slabs committed so far has completed
-  __device__ __forceinline__ void drain() {
-    if (slab == 0) return;
-    const int st = (slab - 1) & 1;
-    tc::mbar_wait(&bars[st], (uses[st] - 1) & 1);
-    tc::tc_fence_after();
-  }
-};
-
-// A [rows x 32 k] K-major operand slab is produced in two steps so that every global load of a slab is in flight
-// before the first one is consumed: load_kmajor() fills registers (load4(row, chunk) returns the 4 values
-// k = 4 chunk .. 4 chunk + 3 of `row`), store_kmajor() splits them into the TF32 hi / lo planes.  A warp covers
-// 8 rows x 4 chunks per pass (64 contiguous bytes per row); stores are conflict-free (8 consecutive rows per
-// quarter warp).  `nrows` is a runtime multiple of 8, PLANE_ROWS the plane capacity.
-template <int PLANE_ROWS>
-struct OpRegs {
-  static constexpr int PASSES = (PLANE_ROWS / 8 * 2 + 7) / 8;
-  float4 v[PASSES];
-};
-
-template <int PLANE_ROWS, class F>
-__device__ __forceinline__ void load_kmajor(OpRegs<PLANE_ROWS>& regs, int nrows, F&& load4) {
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
-  const int rr = lane & 7, cq = lane >> 3;
-  const int ntiles = (nrows >> 3) * 2;   // warp tiles: (8-row block, 4-chunk group)
-#pragma unroll
-  for (int p = 0; p < OpRegs<PLANE_ROWS>::PASSES; ++p) {
-    const int wt = warp + 8 * p;
-    if (wt < ntiles) regs.v[p] = load4((wt >> 1) * 8 + rr, (wt & 1) * 4 + cq);
-  }
-}
-
-template <int PLANE_ROWS>
-__device__ __forceinline__ void store_kmajor(float* hi, float* lo, const OpRegs<PLANE_ROWS>& regs, int nrows) {
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
-  const int rr = lane & 7, cq = lane >> 3;
-  const int ntiles = (nrows >> 3) * 2;
-#pragma unroll
-  for (int p = 0; p < OpRegs<PLANE_ROWS>::PASSES; ++p) {
-    const int wt = warp + 8 * p;
-    if (wt < ntiles) tc::store_split(hi, lo, tc::op_off<PLANE_ROWS>((wt >> 1) * 8 + rr, (wt & 1) * 4 + cq), regs.v[p]);
-  }
-}
+// all 512 producer threads (the issuer warp never joins)
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// global load that stays where it is written: the compiler treats plain loads through the (read-only) kernel
+// arguments as invariant and sinks a prefetch down to its first use, which puts the L2 / HBM latency back on the
+// critical path (trace: 1.2k cycles per first-pass x~ slab)
+__device__ __forceinline__ float4 ldg4_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ldg1_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// x tile row (point), k-chunk `dchunk`: raw() only issues the global load (so that a prefetch one tile ahead does
-// not stall on its own data), transform() centres / scales it when the value is consumed.
-struct XLoader {
-  const float* x; long long n0, N; int D; const float* center; const float* inv_ell; bool vec;
-  __device__ __forceinline__ float4 raw(int row, int dchunk) const {
-    const long long gn = n0 + row;
-    const int d = dchunk * 4;
+// wait for two barriers with one shared-memory round trip per poll: even lanes poll (barA, parA), odd lanes (barB, parB)
+__device__ __forceinline__ void mbar_wait2(uint64_t* barA, uint32_t parA, uint64_t* barB, uint32_t parB) {
+  const bool odd = threadIdx.x & 1;
+  const uint32_t addr = tc::smem_u32(odd ? barB : barA), parity = odd ? parB : parA;
+  for (uint32_t tries = 0;; ++tries) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) break;
+    if (tries > (1u << 24)) asm volatile("trap;");
+  }
+}
+
+// ---- B loader (warp 17): streams the pre-split slab images into the B ring with cp.async.bulk; a stage is refilled
+// as soon as the issuer's commit on b_empty says that the MMAs which read it have retired ----
+template <int NSTB>
+__device__ __noinline__ void tc2_loader(unsigned char* bbase, uint32_t stage_bytes, Bars* bars, const Slab* tab,
+                                        int nslabs, int ntiles_mine) {
+  if (ntiles_mine <= 0 || nslabs <= 0) return;
+  const int total = nslabs * ntiles_mine;
+  int i = 0, stB = 0;
+  uint32_t ephase = 1;                                      // parity of the PREVIOUS use of the stage (first round: none)
+  for (int g = 0; g < total; ++g) {
+    const float* img = reinterpret_cast<const float*>(tc::uniform_u64(reinterpret_cast<uint64_t>(tab[i].img)));
+    const uint32_t rows = tc::uniform_u32((uint32_t)tab[i].rows);
+    if (g >= NSTB) tc::mbar_wait(&bars->b_empty[stB], ephase);
+    if (tc::elect_one()) {
+      const uint32_t bytes = rows * 256u;                   // hi + lo planes: 2 x 8 k-chunks x rows x 16 B, contiguous
+      tc::mbar_expect_tx(&bars->b_full[stB], bytes);
+      tc::bulk_g2s(bbase + (size_t)stB * stage_bytes, img, bytes, &bars->b_full[stB]);
+    }
+    __syncwarp();
+    if (++i == nslabs) i = 0;
+    if (++stB == NSTB) { stB = 0; ephase ^= 1u; }
+  }
+}
+
+// ---- MMA issuer (warp 16): the whole warp walks the slab table with warp-uniform values, one elected lane executes
+// the tcgen05.mma / commit instructions.  The next slab's table entry is fetched while this slab's operands are
+// awaited, both operand barriers are polled in the same shared-memory round trip ----
+// SPLIT (backward): the two producer groups do not alternate, so they own SEPARATE A stages - the loaders the ring
+// [0, NSTA - 1), the row owners stage NSTA - 1 - and every stage barrier is only ever awaited by the group whose own
+// arrival gates its next phase.  (On a shared ring a group that skips the other group's slabs can poll a barrier two
+// phases early, where the parity test aliases: it then overwrites an operand that is still being read.)
+template <int NSTA, int NSTB, bool SPLIT = false>
+__device__ __noinline__ void tc2_issuer(unsigned char* bbase, uint32_t stage_bytes, Bars* bars, uint32_t tmem_base,
+                                        uint32_t aop_col, const Slab* tab, int nslabs, int ntiles_mine,
+                                        long long* trace, uint64_t* dx_full = nullptr) {
+  if (ntiles_mine <= 0 || nslabs <= 0) return;
+  nslabs = (int)tc::uniform_u32((uint32_t)nslabs);
+  const int total = (int)tc::uniform_u32((uint32_t)(nslabs * ntiles_mine));
+  tmem_base = tc::uniform_u32(tmem_base);
+  const uint32_t b0 = tc::uniform_u32(tc::smem_u32(bbase));
+  constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);   // SBO = 128 B, version 1
+  int i = 0, stB = 0, stA = 0;
+  uint32_t bphase = 0, aphase = 0;
+  uint32_t cnt_l = 0, cnt_e = 0;                            // (SPLIT) slabs issued so far per producer group
+  uint32_t n_rows = (uint32_t)tab[0].rows, n_off = tab[0].tmem_off, n_flags = tab[0].flags;
+  for (int g = 0; g < total; ++g) {
+    const uint32_t rows = tc::uniform_u32(n_rows);
+    const uint32_t tmem_d = tmem_base + tc::uniform_u32(n_off);
+    const uint32_t flags = tc::uniform_u32(n_flags);
+    {
+      const int in = (i + 1 == nslabs) ? 0 : i + 1;         // table entry of the next slab: in flight during the waits
+      n_rows = (uint32_t)tab[in].rows; n_off = tab[in].tmem_off; n_flags = tab[in].flags;
+    }
+    const uint32_t idesc = tc::make_idesc_tf32(TNP, (int)rows);
+    if (SPLIT) {
+      if (flags & SF_GRP_E) { stA = NSTA - 1; aphase = cnt_e & 1u; ++cnt_e; }
+      else { stA = (int)(cnt_l % (uint32_t)(NSTA - 1)); aphase = (cnt_l / (uint32_t)(NSTA - 1)) & 1u; ++cnt_l; }
+    }
+    const uint32_t a_hi_t = tmem_base + aop_col + (uint32_t)stA * 64u, a_lo_t = a_hi_t + 32u;
+    const uint32_t bh = b0 + (uint32_t)stB * stage_bytes, bl = bh + rows * 128u;
+    const uint64_t dbh0 = kDescHi | ((uint64_t)rows << 16) | (uint64_t)(bh >> 4);   // LBO = rows * 16 B
+    const uint64_t dbl0 = kDescHi | ((uint64_t)rows << 16) | (uint64_t)(bl >> 4);
+    long long* tr = TRACE_PTR(trace && g < 96 && (threadIdx.x & 31) == 0, trace + g * 8);
+    if (tr) tr[0] = clock64();
+    mbar_wait2(&bars->a_ready[stA], aphase, &bars->b_full[stB], bphase);
+    if (tr) tr[2] = clock64();
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+#pragma unroll
+      for (int j = 0; j < KT / 8; ++j) {
+        const uint64_t dbh = dbh0 + (uint64_t)(2 * j) * rows, dbl = dbl0 + (uint64_t)(2 * j) * rows;
+        tc::umma_tf32_ts(tmem_d, a_lo_t + 8 * j, dbh, idesc, ((flags & SF_FIRST) && j == 0) ? 0u : 1u);   // small terms first
+        tc::umma_tf32_ts(tmem_d, a_hi_t + 8 * j, dbl, idesc, 1u);
+        tc::umma_tf32_ts(tmem_d, a_hi_t + 8 * j, dbh, idesc, 1u);
+      }
+      tc::umma_commit(&bars->mma_done[stA]);
+      tc::umma_commit(&bars->b_empty[stB]);
+      if (flags & SF_SIG_S) tc::umma_commit(&bars->s_full);
+      if (flags & SF_SIG_DX) tc::umma_commit(dx_full);
+      if (flags >> 8) tc::umma_commit(&bars->chunk[(flags >> 8) - 1]);
+    }
+    __syncwarp();
+    if (tr) { tr[3] = clock64(); tr[5] = rows; }
+    if (++i == nslabs) i = 0;
+    if (++stB == NSTB) { stB = 0; bphase ^= 1u; }
+    if (!SPLIT) { if (++stA == NSTA) { stA = 0; aphase ^= 1u; } }
+  }
+}
+
+// producer side of one slab: wait until the MMAs that last read A stage (g % NSTA) have retired, then the caller
+// stores its operand columns and publishes
+template <int NSTA>
+__device__ __forceinline__ void stage_acquire(Bars* bars, int g, bool known_free = false) {
+  if (g >= NSTA && !known_free) {
+    tc::mbar_wait(&bars->mma_done[g % NSTA], (uint32_t)(g / NSTA - 1) & 1u);
+    tc::tc_fence_after();
+  }
+}
+template <int NSTA>
+__device__ __forceinline__ void stage_publish(Bars* bars, int g) {
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  mbar_arrive(&bars->a_ready[g % NSTA]);
+}
+
+// producer side of a PRIVATE ring of `nst` stages starting at stage `st0` (backward): `cnt` = slabs this group has
+// produced so far
+__device__ __forceinline__ int ring_acquire(Bars* bars, uint32_t cnt, int st0, int nst) {
+  const int st = st0 + (int)(cnt % (uint32_t)nst);
+  if (cnt >= (uint32_t)nst) {
+    tc::mbar_wait(&bars->mma_done[st], (cnt / (uint32_t)nst - 1u) & 1u);
+    tc::tc_fence_after();
+  }
+  return st;
+}
+__device__ __forceinline__ void ring_publish(Bars* bars, int st) {
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  mbar_arrive(&bars->a_ready[st]);
+}
+
+// split 16 values into the TF32 hi / lo planes of A stage `st`: columns [kofs, kofs + 16) of the slab
+__device__ __forceinline__ void store_operand16(uint32_t aop_lane_base, int st, int kofs, const float (&v)[16]) {
+  float h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tc::split_tf32(v[i], h[i], l[i]);
+  tc::tmem_st16(aop_lane_base + (uint32_t)(st * 64 + kofs), h);
+  tc::tmem_st16(aop_lane_base + (uint32_t)(st * 64 + 32 + kofs), l);
+}
+
+// 16 input dimensions [d0, d0 + 16) of point gn: raw loads only (a prefetch does not stall on its own data)
+struct XRow16 { float4 v[4]; };
+__device__ __forceinline__ void load_x16(XRow16& r, const float* x, long long gn, long long N, int D, int d0, bool vec) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = d0 + 4 * i;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gn < N && d < D) {
-      const float* r = x + (size_t)gn * D;
-      if (vec) v = ldg4(r + d);
+      const float* p = x + (size_t)gn * D + d;
+      if (vec) v = ldg4_pinned(p);
       else {
-        v.x = r[d];
-        if (d + 1 < D) v.y = r[d + 1];
-        if (d + 2 < D) v.z = r[d + 2];
-        if (d + 3 < D) v.w = r[d + 3];
+        v.x = ldg1_pinned(p);
+        if (d + 1 < D) v.y = ldg1_pinned(p + 1);
+        if (d + 2 < D) v.z = ldg1_pinned(p + 2);
+        if (d + 3 < D) v.w = ldg1_pinned(p + 3);
       }
     }
-    return v;
+    r.v[i] = v;
   }
-  __device__ __forceinline__ float4 transform(float4 v, int row, int dchunk) const {
-    const long long gn = n0 + row;
-    const int d = dchunk * 4;
-    if (gn < N && d < D) {
-      const float4 c = ldg4(center + d), ie = ldg4(inv_ell + d);   // padded entries: centre 0, 1 / ell 0
-      v.x = (v.x - c.x) * ie.x; v.y = (v.y - c.y) * ie.y; v.z = (v.z - c.z) * ie.z; v.w = (v.w - c.w) * ie.w;
-    }
-    return v;
-  }
-};
-
-__device__ __forceinline__ XLoader make_xloader(const TcPointArgs& a, long long n0) {
-  const WsLayout& L = a.L;
-  return XLoader{a.x, n0, L.N, L.D, ws_cptr<float>(a.ws, L.center), ws_cptr<float>(a.ws, L.inv_ell),
-                 (L.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0)};
 }
-
-// RAW registers of one 32-wide d-slab of the x tile (loads only)
-__device__ __forceinline__ void load_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
-  load_kmajor<TNP>(ra, TNP, [&](int row, int c) {
-    const int dchunk = ds * (KT / 4) + c;
-    return dchunk * 4 < DP ? xl.raw(row, dchunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-  });
-}
-// centre / scale the registers of load_x_slab in place (same (row, chunk) mapping as load_kmajor)
-__device__ __forceinline__ void transform_x_slab(OpRegs<TNP>& ra, const XLoader& xl, int ds, int DP) {
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
-  const int rr = lane & 7, cq = lane >> 3;
+// centre / scale (padded dimensions: centre 0, 1 / ell 0 => 0) + the row-statistic partials of these 16 dimensions
+__device__ __forceinline__ void transform_x16(const XRow16& r, float (&o)[16], int d0, int DP, const float* center,
+                                              const float* inv_ell, const float* wl, float& pn, float& pw) {
+  pn = 0.f; pw = 0.f;
 #pragma unroll
-  for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
-    const int wt = warp + 8 * p;
-    const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
-    const int dchunk = ds * (KT / 4) + c;
-    if (dchunk * 4 < DP) ra.v[p] = xl.transform(ra.v[p], row, dchunk);
+  for (int i = 0; i < 4; ++i) {
+    const int d = d0 + 4 * i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < DP) {
+      const float4 c = ldg4(center + d), ie = ldg4(inv_ell + d), w4 = ldg4(wl + d);
+      v.x = (r.v[i].x - c.x) * ie.x; v.y = (r.v[i].y - c.y) * ie.y;
+      v.z = (r.v[i].z - c.z) * ie.z; v.w = (r.v[i].w - c.w) * ie.w;
+      // explicit FMA chains: the outputs must not depend on how the compiler contracts (shard invariance is tested
+      // bit-exactly)
+      pn = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, fmaf(v.x, v.x, pn))));
+      pw = fmaf(v.w, w4.w, fmaf(v.z, w4.z, fmaf(v.y, w4.y, fmaf(v.x, w4.x, pw))));
+    }
+    o[4 * i + 0] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
   }
 }
-
-// Producer side of S[128, BW] = X~ Z~[block q]^T (TMEM columns [0, BW)): nds slabs of the x tile.  xr0 / xr1: the
-// first two d-slabs of this tile's x when `preloaded` (loaded one tile ahead so that the HBM latency hides behind the
-// previous tile's MMAs and epilogue).  With `stats`, per-row |x~|^2 and x~ . (ell w) are folded from per-slab
-// partials in fixed order (deterministic).
-template <int BW>
-__device__ __forceinline__ void phase_a(Pipe<BW>& pipe, const TcPointArgs& a, const XLoader& xl, bool stats,
-                                        float* part_n, float* part_w, float* xn_s, float* xw_s, bool preloaded,
-                                        const OpRegs<TNP>& xr0, const OpRegs<TNP>& xr1, uint64_t* gate, uint32_t blk) {
-  const WsLayout& L = a.L;
-  const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const int DP = L.DP;
-  const int nds = DP >= KT ? DP / KT : 1;
-  for (int ds = 0; ds < nds; ++ds) {
-    OpRegs<TNP> ra;
-    if (preloaded && ds == 0) ra = xr0;
-    else if (preloaded && ds == 1) ra = xr1;
-    else load_x_slab(ra, xl, ds, DP);
-    transform_x_slab(ra, xl, ds, DP);
-    if (stats) {
-      // row-statistic partials of the chunks this thread just loaded (same (row, chunk) mapping as load_kmajor)
-      const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;   // warp within its 8-warp producer group
-      const int rr = lane & 7, cq = lane >> 3;
-#pragma unroll
-      for (int p = 0; p < OpRegs<TNP>::PASSES; ++p) {
-        const int wt = warp + 8 * p;
-        const int row = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
-        const int dchunk = ds * (KT / 4) + c;
-        const float4 v = ra.v[p];
-        const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        part_n[c * TNP + row] = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        part_w[c * TNP + row] = v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
-      }
-    }
-    float *a_hi, *a_lo;
-    pipe.acquire(a_hi, a_lo);
-    store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-    // `gate[ds / 2]` (one phase per block): the other producer group has passed this pair of slabs in its own slab
-    // count (see the loader warps of the backward kernel).  It gets there long before; the wait only rules out
-    // parity aliasing on the ring barriers.
-    if ((ds & 1) == 0) tc::mbar_wait(&gate[ds >> 1], blk & 1);
-    pipe.commit();
-    if (stats) {
-      // fold this slab's 8 chunk partials in fixed order (bit-deterministic)
-      prod_sync();
-      if (threadIdx.x < TNP) {
-        float n2 = ds == 0 ? 0.f : xn_s[threadIdx.x], xw = ds == 0 ? 0.f : xw_s[threadIdx.x];
-#pragma unroll
-        for (int c = 0; c < KT / 4; ++c) {
-          n2 += part_n[c * TNP + threadIdx.x];
-          xw += part_w[c * TNP + threadIdx.x];
-        }
-        xn_s[threadIdx.x] = n2;
-        xw_s[threadIdx.x] = xw;
-      }
-      prod_sync();
-    }
-  }
-}
-
-// ---- slab tables (one entry per pipeline slab of a tile, in issue order) ----
-// forward: for p, for q <= p: nds slabs of S = X~ Z~[q]^T, then SPB whitening slabs of block q into output block p
-template <int BW>
-__device__ __forceinline__ int fwd_table(SlabDesc* tab, const TcPointArgs& a) {
-  const WsLayout& L = a.L;
-  const int MP = L.MP, NP = MP / BW, SPB = BW / KT;
-  const int nds = L.DP >= KT ? L.DP / KT : 1;
-  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
-  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
-  const int per = nds + SPB, total = NP * (NP + 1) / 2 * per;
-  for (int i = threadIdx.x; i < total; i += kThreads) {
-    const int pair = i / per, j = i - pair * per;
-    int p = 0;
-    while ((p + 1) * (p + 2) / 2 <= pair) ++p;
-    const int q = pair - p * (p + 1) / 2;
-    SlabDesc d;
-    if (j < nds) {
-      d.img = ZtU + tc_zt_image(MP, nds, q, j);
-      d.rows = BW; d.tmem_off = 0; d.first = j == 0;
-    } else {
-      const int sl = j - nds, sg = q * SPB + sl;
-      int rows;
-      d.img = LinvU + tc_linv_image(MP, p, sg, &rows);
-      d.rows = rows; d.tmem_off = (uint32_t)(BW + BW - rows);
-      d.first = (q == 0 && sl == 0) ? 1 : 0;
-    }
-    tab[i] = d;
-  }
-  return total;
-}
-// backward: for p: nds slabs of S (block p), then T[:, block p] slabs s = NSL - 1 ... p SPB (decreasing)
-template <int BW>
-__device__ __forceinline__ int bwd_table(SlabDesc* tab, const TcPointArgs& a) {
-  const WsLayout& L = a.L;
-  const int MP = L.MP, NP = MP / BW, SPB = BW / KT, NSL = MP / KT;
-  const int nds = L.DP >= KT ? L.DP / KT : 1;
-  const float* ZtU = ws_cptr<float>(a.ws, L.ZtU);
-  const float* LCTU = ws_cptr<float>(a.ws, L.LCTU);
-  int total = 0;
-  for (int p = 0; p < NP; ++p) total += nds + NSL - p * SPB;
-  for (int i = threadIdx.x; i < total; i += kThreads) {
-    int p = 0, base = 0;
-    while (i >= base + nds + NSL - p * SPB) { base += nds + NSL - p * SPB; ++p; }
-    const int j = i - base;
-    SlabDesc d;
-    if (j < nds) {
-      d.img = ZtU + tc_zt_image(MP, nds, p, j);
-      d.rows = BW; d.tmem_off = 0; d.first = j == 0;
-    } else {
-      const int sg = NSL - 1 - (j - nds);
-      int rows;
-      d.img = LCTU + tc_lct_image(MP, p, sg, &rows);
-      const int c = sg - p * SPB;                   // chunk finalised by this slab (slabs run in decreasing order)
-      d.rows = rows; d.tmem_off = (uint32_t)BW; d.first = (sg == NSL - 1 ? 1 : 0) | (c < SPB ? ((c + 1) << 8) : 0);
-    }
-    tab[i] = d;
-  }
-  return total;
-}
-
-// Cross-covariance values from the S accumulators (inlined where used):
-//   k = os exp(-1/2 max(|x|^2 + |z|^2 - 2 s, 0)) = 2^min(s log2e + xnc + znc[m], log2 os)
-// with xnc = -1/2 log2e |x~|^2 and znc[m] = -1/2 log2e |z~_m|^2 + log2 os (-1e30 on padded columns => k = 0):
-// 4 FP32 instructions + one MUFU per element.
-
-// Pitch (floats) of a per-warp [32 rows x 32 columns] shared-memory staging tile: conflict-free 16-byte accesses.
-constexpr int kStagePitch = 36;
-// =================================================================================================
-// forward.  The inducing dimension is processed in column blocks of width BW (= min(MP, 256), the TMEM budget:
-// S in columns [0, BW), the whitened product of the current output block in [BW, 2 BW)).  Output block p needs the
-// cross-covariance blocks q <= p (Linv is lower triangular); for MP > 256 block q is recomputed for every p >= q.
-// =================================================================================================
-// Warp roles (544 threads): TWO producer groups (warps 0..7 and 8..15) that own ALTERNATE pipeline slabs - group g
-// always writes ring stage g - and the issuer warp 16.  The per-slab work of a producer is a chain of latencies
-// (TMEM load -> exp -> stage acquire -> shared-memory stores under UMMA operand traffic -> proxy fence -> arrive) that
-// eight warps cannot hide: 2000 cycles per slab against 1536 cycles of MMAs (N = 256).  With two groups each chain
-// has two slab times, and the chunk epilogues (chunk c is final once whitening slab c of the pass q == p has retired,
-// which the owner of slab c + 2 learns from its stage acquire) are spread over both groups as well.
-// Both groups count every slab, but a group only ever waits on the barriers of its OWN stage (its phase can only move
-// when the group itself commits) - with one exception, the wait for S after phase A, whose last slab may belong to
-// the other group: the 512-thread barrier in front of it guarantees that the owner has seen the stage's previous use
-// retire, and the stage cannot advance another phase before this group publishes the slab in between.  (Waiting on
-// the other group's stage anywhere else can observe the barrier TWO phases later and alias.)
-constexpr int kTwoGroupThreads = 2 * kThreads + 32;
-constexpr int kTwoGroupIssuerWarp = 2 * kThreads / 32;
-__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-// all 512 producer threads (the issuer warp never joins)
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
 
 // Store of a [32 rows x 16 columns] half chunk held one row per lane (16 consecutive floats), without staging:
 // neighbouring lanes exchange two 16-byte pieces, so that every store instruction writes 32 contiguous bytes per lane
@@ -548,23 +323,69 @@ __device__ __forceinline__ void warp_store_rows16(float* dst, size_t ld, const f
   }
 }
 
-template <int BW>
-__global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPointArgs a) {
+// ---- forward slab table: for every output block P, for every S block q below or on it: nds phase-A slabs, then the
+// BQ / 32 whitening slabs of block q ----
+template <int BQ, int BWO>
+__device__ __forceinline__ int fwd_table(Slab* tab, const Tc2Args& a, int nthreads) {
+  const WsLayout& L = a.L;
+  const int MP = L.MP, NPO = MP / BWO, SPQ = BQ / KT, QPB = BWO / BQ;
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float* ZtQ = ws_cptr<float>(a.ws, L.ZtQ);
+  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
+  const int per = nds + SPQ;
+  const int total = QPB * NPO * (NPO + 1) / 2 * per;
+  for (int i = threadIdx.x; i < total; i += nthreads) {
+    const int pass = i / per, j = i - pass * per;
+    int P = 0;
+    while (QPB * (P + 1) * (P + 2) / 2 <= pass) ++P;      // passes before block P: QPB * P (P + 1) / 2
+    const int q = pass - QPB * P * (P + 1) / 2;
+    Slab d;
+    if (j < nds) {
+      d.img = ZtQ + tc_zq_image(MP, nds, q, j);
+      d.rows = BQ; d.tmem_off = 0;
+      d.flags = (j == 0 ? SF_FIRST : 0u) | (j == nds - 1 ? SF_SIG_S : 0u);
+    } else {
+      const int sl = j - nds, sg = q * SPQ + sl;
+      int rows;
+      d.img = LinvU + tc_linv_image(MP, P, sg, &rows);
+      d.rows = rows; d.tmem_off = (uint32_t)(BQ + BWO - rows);
+      d.flags = (q == 0 && sl == 0) ? SF_FIRST : 0u;
+      const int c = sg - P * (BWO / KT);                    // this slab is the last one that touches chunk c of block P
+      if (c >= 0) d.flags |= (uint32_t)(c + 1) << 8;
+    }
+    tab[i] = d;
+  }
+  return total;
+}
+
+constexpr int kMaxFwdSlabs = 20 * 8;   // MP = 1024: 20 passes x (4 d-slabs + 4 whitening slabs)
+
+// =================================================================================================
+// forward
+// =================================================================================================
+// Warp roles (544 threads): two producer groups (warps 0..7, 8..15) own ALTERNATE pipeline slabs (group = slab
+// parity = A stage), so the latency chain of a slab (TMEM load -> exp -> stage acquire -> tcgen05.st -> arrive) has
+// two slab times; warp 16 issues.  Accumulator chunk c is read out (mean / variance partials, A saved for the
+// backward) by group c & 1 as soon as the issuer's commit on chunk[c] says that its last slab has retired.
+template <int BQ, int BWO, int NSTB>
+__global__ void __launch_bounds__(kCtaThreads, 1) tc2_fwd_kernel(Tc2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[6];
+  __shared__ __align__(8) Bars bars;
   __shared__ uint32_t tmem_slot;
-  __shared__ SlabDesc tab[kMaxFwdSlabs];
+  __shared__ Slab tab[kMaxFwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[BW], m_s[BW], c_s[BW];      // exponent offsets of block q; m, c = s^2 - 1 of block p
-  constexpr int kMaxDs = 4;                         // d-slabs of the x tile (D <= 128)
-  __shared__ float part_n[kMaxDs][2][TNP], part_w[kMaxDs][2][TNP];   // row-statistic partials per d-slab / chunk half
-  __shared__ float mu_s[4][TNP], vv_s[4][TNP];      // mean / variance partials per (group, column half)
+  __shared__ float part_n[kMaxDs][2][TNP], part_w[kMaxDs][2][TNP];   // row-statistic partials per d-slab / k-half
+  __shared__ float mu_s[4][TNP], vv_s[4][TNP];                      // mean / variance partials per (group, k-half)
+  constexpr int NSTA = 2;
+  constexpr uint32_t S_COL = 0, ACC_COL = BQ, AOP_COL = BQ + BWO;
+  constexpr uint32_t USED_COLS = BQ + BWO + NSTA * 64;
+  constexpr uint32_t TMEM_COLS = USED_COLS <= 256 ? 256 : 512;
+  static_assert(USED_COLS <= 512, "tensor memory budget");
+  constexpr uint32_t STAGE_BYTES = BWO * 256;
+  constexpr int SPQ = BQ / KT, QPB = BWO / BQ, CPB = BWO / KT;
 
   const WsLayout& L = a.L;
-  const int MP = L.MP;
-  const int NP = MP / BW;
-  constexpr int SPB = BW / KT;
+  const int MP = L.MP, NPO = MP / BWO;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
@@ -572,223 +393,268 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
   const float* znc_g = ws_cptr<float>(a.ws, L.znc);
   const float* mvec_g = ws_cptr<float>(a.ws, L.mvec);
   const float* cvec_g = ws_cptr<float>(a.ws, L.cvec);
+  const float* center = ws_cptr<float>(a.ws, L.center);
+  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
   const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
-  const float l2os = log2f(os);
-  const int DP = L.DP;
+  const int DP = L.DP, D = L.D;
   const int nds = DP >= KT ? DP / KT : 1;
 
-  constexpr uint32_t TMEM_COLS = 2 * BW;
+  // the small constant vectors live in shared memory behind the B ring: with ~200 KB of shared memory carved out
+  // the L1 keeps nothing, and every one of these (warp-uniform) reads was an L2 round trip on the producers' critical
+  // path (trace: 700 - 2700 cycles per epilogue chunk)
+  float* cst = reinterpret_cast<float*>(smem_raw + (size_t)NSTB * STAGE_BYTES);
+  float* znc_s = cst;                // [MP] exponent offsets
+  float* mvec_s = znc_s + MP;        // [MP] variational mean
+  float* cvec_s = mvec_s + MP;       // [MP] s^2 - 1
+  float* cen_s = cvec_s + MP;        // [DP] centre
+  float* iel_s = cen_s + DP;         // [DP] 1 / ell
+  float* wl_s = iel_s + DP;          // [DP] ell * w
+  for (int i = tid; i < MP; i += kCtaThreads) { znc_s[i] = znc_g[i]; mvec_s[i] = mvec_g[i]; cvec_s[i] = cvec_g[i]; }
+  for (int i = tid; i < DP; i += kCtaThreads) { cen_s[i] = center[i]; iel_s[i] = inv_ell[i]; wl_s[i] = wl[i]; }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) init_ring_barriers(bars);
-  if (tid < kThreads) {
-    for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per (p, q) when MP > BW
-      zn_s[i] = znc_g[i];                            // exponent offsets (formula above)
-      m_s[i] = mvec_g[i];
-      c_s[i] = cvec_g[i];
-    }
-    const int n = fwd_table<BW>(tab, a);
+  if (tid == 32) {
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars.a_ready[i], kGroup); tc::mbar_init(&bars.mma_done[i], 1); }
+    for (int i = 0; i < 6; ++i) { tc::mbar_init(&bars.b_full[i], 1); tc::mbar_init(&bars.b_empty[i], 1); }
+    tc::mbar_init(&bars.s_full, 1);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&bars.chunk[i], 1);
+    tc::fence_barrier_init();
+  }
+  {
+    const int n = fwd_table<BQ, BWO>(tab, a, kCtaThreads);
     if (tid == 0) tab_n = n;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_a = tmem_slot + BW;
+  const uint32_t tmem_base = tmem_slot;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp == kTwoGroupIssuerWarp) {
-    // ---------------- issuer warp: one elected thread drives the TMA requests and the tensor core ----------------
-    issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr);
+  if (warp >= kIssuerWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
+    if (warp == kIssuerWarp)
+      tc2_issuer<NSTA, NSTB>(smem_raw, STAGE_BYTES, &bars, tmem_base, AOP_COL, tab, tab_n, tiles_mine,
+                             blockIdx.x == 0 ? a.trace : nullptr);
+    else if (warp == kIssuerWarp + 1)
+      tc2_loader<NSTB>(smem_raw, STAGE_BYTES, &bars, tab, tab_n, tiles_mine);
   } else {
-    // ---------------- producer groups ----------------
-    const int g = warp >> 3;                          // group = ring stage this thread writes
-    const int quad = warp & 3, half = (warp >> 2) & 1;   // TMEM lane quadrant / column half of this warp
-    const int row = quad * 32 + lane;                 // the point this thread owns
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    const int g = warp >> 3;                              // producer group = parity of the slabs it produces
+    const int quad = warp & 3, half = (warp >> 2) & 1;   // TMEM lane quadrant / k-half of this warp
+    const int row = quad * 32 + lane;                     // the point this thread owns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + S_COL, tmem_acc = tmem_base + lane_base + ACC_COL;
+    const uint32_t aop_base = tmem_base + lane_base + AOP_COL;
+    const float os = hyp[H_OS], jit = hyp[H_JIT], cwb = hyp[H_CWB];
+    const float l2os = log2f(os);
+    const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
     const int slabs_per_tile = tab_n;
-    Pipe<BW> pipe;
-    pipe.init(stage_base, bars);
-    long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tlast = clock64();
-#define SEG(i) do { if (a.dbg) { const long long tnow = clock64(); seg[i] += tnow - tlast; tlast = tnow; } } while (0)
-    // the first d-slab of a tile that this group owns (slab parity) is loaded one tile ahead
-    OpRegs<TNP> xr;
-    int ds_pre = g;                                   // tile 0 starts at slab 0: group g owns d-slab g
-    if (ds_pre < nds) load_x_slab(xr, make_xloader(a, (long long)blockIdx.x * TNP), ds_pre, DP);
-    // ---- phase A of one pass: S[128, BW] = X~ Z~[block q]^T, the d-slabs alternate between the groups.  (Issuing it
-    // one pass ahead, before the tail epilogue of the previous block, was measured: no gain - the tensor pipe, not
-    // the producers, paces these kernels.) ----
-    auto phase_a_slabs = [&](const XLoader& xl, bool first_pass) {
-      for (int ds = 0; ds < nds; ++ds) {
-        if ((pipe.slab & 1) != g) { pipe.skip(1); continue; }
-        OpRegs<TNP> ra;
-        if (first_pass && ds == ds_pre) ra = xr;
-        else load_x_slab(ra, xl, ds, DP);
-        transform_x_slab(ra, xl, ds, DP);
-        if (first_pass) {
-          // row-statistic partials (same (row, chunk) mapping as load_kmajor): the four chunk groups of a row sit
-          // in lanes rr, rr + 8, rr + 16, rr + 24 (fixed shuffle tree), the two chunk halves in neighbouring warps
-          const int gw = warp & 7, rr = lane & 7, cq = lane >> 3;
-#pragma unroll
-          for (int ps = 0; ps < OpRegs<TNP>::PASSES; ++ps) {
-            const int wt = gw + 8 * ps;
-            const int prow = (wt >> 1) * 8 + rr, c = (wt & 1) * 4 + cq;
-            const int dchunk = ds * (KT / 4) + c;
-            const float4 v = ra.v[ps];
-            const float4 w4 = dchunk * 4 < DP ? ldg4(wl + dchunk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            // explicit FMA chains: the lambda is inlined at two call sites, and the outputs must not depend on how
-            // the compiler contracts each copy (shard invariance is tested bit-exactly)
-            float pn = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x)));
-            float pw = fmaf(v.w, w4.w, fmaf(v.z, w4.z, fmaf(v.y, w4.y, v.x * w4.x)));
-            pn += __shfl_xor_sync(0xffffffffu, pn, 8);
-            pw += __shfl_xor_sync(0xffffffffu, pw, 8);
-            pn += __shfl_xor_sync(0xffffffffu, pn, 16);
-            pw += __shfl_xor_sync(0xffffffffu, pw, 16);
-            if (cq == 0) { part_n[ds][wt & 1][prow] = pn; part_w[ds][wt & 1][prow] = pw; }
-          }
-        }
-        float *a_hi, *a_lo;
-        pipe.acquire(a_hi, a_lo);
-        store_kmajor<TNP>(a_hi, a_lo, ra, TNP);
-        pipe.commit();
-      }
-    };
-    bool have_prev = false;                           // deferred mean / variance / sample of the previous tile
+    int gs = 0;                                           // global slab counter (identical in every producer thread)
+    uint32_t pass_ctr = 0, blk_ctr = 0;                   // phases of s_full / chunk[]
+
+    // Slab ownership is fixed: group g produces the d-slabs ds with (ds & 1) == g and the whitening slabs sl with
+    // (sl & 1) == g, whatever A stage (gs % NSTA) they fall on - the stage barriers are functions of gs alone.
+    // x of the group's first own d-slab of a TILE is requested one tile ahead (the L1 left beside 200 KB of shared
+    // memory keeps nothing: every reload is an L2 / HBM round trip); the scaled values xt[] stay in registers for
+    // the later passes of the tile (up to two d-slabs, D <= 64; a third / fourth d-slab is reloaded).
+    XRow16 xr;
+    const bool own_x = g < nds;
+    if (own_x) load_x16(xr, a.x, (long long)blockIdx.x * TNP + row, N, D, g * KT + half * 16, vec);
+    float xt[16];
+
+    bool have_prev = false;                               // deferred mean / variance / sample of the previous tile
     long long prev_gn = 0;
     float xw_prev = 0.f;
+    float mu = 0.f, vv = 0.f;                             // partials of the tile whose chunks are being read out
+    auto finalize_prev = [&]() {
+      if (g == 0 && half == 0 && have_prev && prev_gn < N) {
+        const float mean = mu_s[0][row] + mu_s[1][row] + mu_s[2][row] + mu_s[3][row] + xw_prev + cwb;
+        const float var = fmaxf(os + jit + vv_s[0][row] + vv_s[1][row] + vv_s[2][row] + vv_s[3][row], kMinVariance);
+        a.mean[prev_gn] = mean;
+        a.var[prev_gn] = var;
+        if (a.sample)
+          a.sample[prev_gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)prev_gn, a.stream_id), mean);
+      }
+    };
+    // read-out of chunk c (32 columns; 16 per k-half) of output block P of tile `etile`: mean / variance partials, A
+    // saved for the backward in the tile-major layout (tc_tiled_index): 512 contiguous bytes per warp and instruction
+    int epi_ctr = 0;
+    auto epi_chunk = [&](int P, int c, uint32_t par, int etile) {
+      long long* et = TRACE_PTR(a.trace && blockIdx.x == 0 && (tid & 255) == 0 && epi_ctr < 24, a.trace + 3072 + (g * 24 + epi_ctr) * 8);
+      ++epi_ctr;
+      if (et) { et[0] = clock64(); et[6] = c; }
+      tc::mbar_wait(&bars.chunk[c], par);
+      tc::tc_fence_after();
+      if (et) et[1] = clock64();
+      const int col = c * KT + half * 16;
+      float v[16];
+      tc::tmem_ld16(tmem_acc + (uint32_t)col, v);
+      if (et) et[2] = clock64();
+      const float* mp = mvec_s + P * BWO + col;
+      const float* cp = cvec_s + P * BWO + col;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 m4 = ldg4(mp + i), c4 = ldg4(cp + i);
+        mu = fmaf(v[i + 0], m4.x, mu); vv = fmaf(c4.x * v[i + 0], v[i + 0], vv);
+        mu = fmaf(v[i + 1], m4.y, mu); vv = fmaf(c4.y * v[i + 1], v[i + 1], vv);
+        mu = fmaf(v[i + 2], m4.z, mu); vv = fmaf(c4.z * v[i + 2], v[i + 2], vv);
+        mu = fmaf(v[i + 3], m4.w, mu); vv = fmaf(c4.w * v[i + 3], v[i + 3], vv);
+      }
+      if (et) et[3] = clock64() + (long long)(mu == 12345.f);
+      if (L.training) {
+        float4* At = reinterpret_cast<float4*>(Ag) + ((size_t)etile * (size_t)(MP >> 2) + (size_t)((P * BWO + col) >> 2)) * TNP + row;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) At[(size_t)i * TNP] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      if (et) et[4] = clock64();
+    };
+    // The last two chunks a pass finalises are read out later: after the next pass's x~ operands have been published
+    // and - unless that pass starts a new output block, whose first whitening slab overwrites ACC - after this
+    // group's first whitening slab of that pass, so that the tensor core always has queued work meanwhile
+    int pend_n = 0, pend_ca = 0, pend_P = 0, pend_tile = 0;
+    uint32_t pend_par = 0;
+    auto run_pending = [&]() {
+      if (pend_n) {
+        epi_chunk(pend_P, ((pend_ca & 1) == g) ? pend_ca : pend_ca + 1, pend_par, pend_tile);
+        pend_n = 0;
+      }
+    };
+
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const long long n0 = (long long)tile * TNP;
-      const XLoader xl = make_xloader(a, n0);
+      const long long gn = n0 + row;
       const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      const long long w0 = n0 + quad * 32;        // first point of this warp
-      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-      float mu = 0.f, vv = 0.f, xnc = 0.f;
-      SEG(7);
-      // epilogue of one 32-column chunk c of output block p (16 columns per column half): mean / variance partials
-      // of the own point, A saved for the backward
-      auto epi_chunk = [&](int p, int c) {
-        const int col = c * 32 + half * 16;
-        float v[16];
-        tc::tmem_ld16(tmem_a + lane_base + (uint32_t)col, v);
+      float xnc = 0.f;
+      bool first_pass = true;
+      for (int P = 0; P < NPO; ++P, ++blk_ctr) {
+        const int nq = (P + 1) * QPB;
+        for (int q = 0; q < nq; ++q, ++pass_ctr) {
+          const bool last_pass = (P == NPO - 1) && (q == nq - 1);
+          // ---- phase A: S[128, BQ] = X~ Z~[block q]^T, the d-slabs alternate between the groups ----
+          for (int ds = 0; ds < nds; ++ds, ++gs) {
+            if ((ds & 1) != g) continue;
+            long long* ptr = TRACE_PTR(a.trace && blockIdx.x == 0 && (tid & 255) == 0 && gs < 96, a.trace + 1024 + gs * 8);
+            if (ptr) { ptr[0] = clock64(); ptr[1] = ptr[0]; }
+            float v[16];
+            if (ds == g && !first_pass) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          mu = fmaf(v[i], m_s[col + i], mu);
-          vv = fmaf(c_s[col + i] * v[i], v[i], vv);
-        }
-        if (L.training) warp_store_rows16(Ag + (size_t)w0 * MP + p * BW + col, MP, v, lane, nvalid);
-      };
-      for (int p = 0; p < NP; ++p) {
-        for (int q = 0; q <= p; ++q) {
-          const bool first_pass = p == 0 && q == 0;
-          if (NP > 1) {                               // per-block constants (single block: loaded once at kernel start)
-            tc::tc_fence_before();
-            producers_sync();
-            if (tid < BW) {
-              zn_s[tid] = znc_g[q * BW + tid];
-              if (q == 0) { m_s[tid] = mvec_g[p * BW + tid]; c_s[tid] = cvec_g[p * BW + tid]; }
+              for (int i = 0; i < 16; ++i) v[i] = xt[i];
+            } else {
+              XRow16 xs;
+              if (ds == g) xs = xr;
+              else load_x16(xs, a.x, gn, N, D, ds * KT + half * 16, vec);
+              float pn, pw;
+              transform_x16(xs, v, ds * KT + half * 16, DP, cen_s, iel_s, wl_s, pn, pw);
+              if (first_pass) { part_n[ds][half][row] = pn; part_w[ds][half][row] = pw; }
+              if (ds == g) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xt[i] = v[i];
+              }
             }
+            if (ptr) ptr[2] = clock64() + (long long)(v[0] == 12345.f);
+            stage_acquire<NSTA>(&bars, gs);
+            if (ptr) ptr[3] = clock64();
+            store_operand16(aop_base, gs % NSTA, half * 16, v);
+            stage_publish<NSTA>(&bars, gs);
+            if (ptr) ptr[4] = clock64();
           }
-          phase_a_slabs(xl, first_pass);
-          // every producer has (a) read the previous output block out of the A accumulators - the first whitening
-          // slab below overwrites them -, (b) published its row-statistic partials / the block constants
+          if (last_pass && more_tiles && own_x)           // next tile's x: in flight during this pass
+            load_x16(xr, a.x, gn + (long long)gridDim.x * TNP, N, D, g * KT + half * 16, vec);
+          const bool defer_more = q > 0;                   // ACC is not overwritten by this pass: read-out can wait
+          if (!defer_more) run_pending();                 // last chunks of the previous pass
+          bool do_finalize = false;
+          if (first_pass) {
+            if (have_prev) { mu_s[g * 2 + half][row] = mu; vv_s[g * 2 + half][row] = vv; }   // previous tile complete
+            mu = 0.f; vv = 0.f;
+          }
+          // every producer has (a) read the previous output block out of ACC - the first whitening slab of a block
+          // overwrites it -, (b) published its row-statistic partials and the partials of the previous tile
           tc::tc_fence_before();
           producers_sync();
           tc::tc_fence_after();
+          float xw_new = 0.f;
           if (first_pass) {
             float n2 = 0.f, xw = 0.f;
-            for (int ds = 0; ds < nds; ++ds) {        // fixed order (bit-deterministic)
+            for (int ds = 0; ds < nds; ++ds) {            // fixed order (bit-deterministic)
               n2 += part_n[ds][0][row] + part_n[ds][1][row];
               xw += part_w[ds][0][row] + part_w[ds][1][row];
             }
             xnc = -0.72134752044448170f * n2;
-            if (g == 0 && half == 0) {
-              if (have_prev && prev_gn < N) {         // the previous tile's partials are complete (barrier above)
-                const float mean = mu_s[0][row] + mu_s[1][row] + mu_s[2][row] + mu_s[3][row] + xw_prev + cwb;
-                const float var = fmaxf(os + jit + vv_s[0][row] + vv_s[1][row] + vv_s[2][row] + vv_s[3][row], kMinVariance);
-                a.mean[prev_gn] = mean;
-                a.var[prev_gn] = var;
-                if (a.sample)
-                  a.sample[prev_gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)prev_gn, a.stream_id), mean);
+            xw_new = xw;
+            do_finalize = true;                           // (after this group's first slab: off the S -> k chain)
+            first_pass = false;
+          }
+          // ---- S of block q complete ----
+          long long* st = TRACE_PTR(a.trace && blockIdx.x == 0 && (tid & 255) == 0 && pass_ctr < 32, a.trace + 2048 + pass_ctr * 4 + g * 2);
+          if (st) st[0] = clock64();
+          tc::mbar_wait(&bars.s_full, pass_ctr & 1u);
+          tc::tc_fence_after();
+          if (st) st[1] = clock64();
+          // ---- whitening: ACC[:, j >= 32 sg] += k[:, slab sg] Linv[j, slab sg]^T ----
+          const float* znq = znc_s + q * BQ;
+          const int c0 = q * SPQ - P * CPB;               // chunk finalised by slab sl of this pass: c0 + sl (if >= 0)
+#pragma unroll 1
+          for (int sl = 0; sl < SPQ; ++sl, ++gs) {
+            // ONE read-out site per iteration: the deferred chunk of the previous pass (group 1, whose first slab is
+            // needed one slab time later, BEFORE its first slab - which also leaves the special-function unit to
+            // group 0 for the slab the tensor core is waiting for -, group 0 after its first slab), or the chunk that
+            // became final two slabs ago (group c & 1)
+            {
+              int rc = -1, rP = P, rt = tile;
+              uint32_t rpar = blk_ctr & 1u;
+              const int c = c0 + sl - 2;
+              if (sl >= 2 && c >= 0 && (c & 1) == g) rc = c;
+              else if (defer_more && pend_n && sl == 1 - g) {
+                rc = ((pend_ca & 1) == g) ? pend_ca : pend_ca + 1; rP = pend_P; rt = pend_tile; rpar = pend_par;
+                pend_n = 0;
               }
-              xw_prev = xw;
+              if (rc >= 0) epi_chunk(rP, rc, rpar, rt);
+              if (do_finalize && sl == 1) {
+                finalize_prev();
+                if (g == 0 && half == 0) xw_prev = xw_new;
+                do_finalize = false;
+              }
             }
-            if (more_tiles) {                         // next tile's first own d-slab: in flight during this tile
-              ds_pre = (((pipe.slab - nds + slabs_per_tile) & 1) == g) ? 0 : 1;
-              if (ds_pre < nds) load_x_slab(xr, make_xloader(a, n0 + (long long)gridDim.x * TNP), ds_pre, DP);
+            if ((sl & 1) == g) {
+              const int col0 = sl * KT + half * 16;
+              long long* ptr = TRACE_PTR(a.trace && blockIdx.x == 0 && (tid & 255) == 0 && gs < 96, a.trace + 1024 + gs * 8);
+              if (ptr) ptr[0] = clock64();
+              float v[16];
+              tc::tmem_ld16(tmem_s + (uint32_t)col0, v);
+              if (ptr) ptr[1] = clock64();
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 z4 = ldg4(znq + col0 + j);
+                v[j + 0] = tc::ex2_approx(fminf(fmaf(v[j + 0], 1.4426950408889634f, xnc + z4.x), l2os));
+                v[j + 1] = tc::ex2_approx(fminf(fmaf(v[j + 1], 1.4426950408889634f, xnc + z4.y), l2os));
+                v[j + 2] = tc::ex2_approx(fminf(fmaf(v[j + 2], 1.4426950408889634f, xnc + z4.z), l2os));
+                v[j + 3] = tc::ex2_approx(fminf(fmaf(v[j + 3], 1.4426950408889634f, xnc + z4.w), l2os));
+              }
+              if (ptr) ptr[2] = clock64() + (long long)(v[0] == 12345.f);
+              // s_full (a commit: every earlier MMA has retired) already covers the stages of the first two slabs
+              stage_acquire<NSTA>(&bars, gs, sl < NSTA);
+              if (ptr) ptr[3] = clock64();
+              store_operand16(aop_base, gs % NSTA, half * 16, v);
+              stage_publish<NSTA>(&bars, gs);
+              if (ptr) ptr[4] = clock64();
             }
           }
-          SEG(0);                                     // phase A (x split, A planes published, barrier)
-          pipe.drain();                               // S of block q complete
-          SEG(1);
-          // ---- whitening: A[:, block p] += k[:, slab s] Linv[block p rows >= 32 s, slab s]^T ----
-          // this group owns the slabs sl = f, f + 2, ...; the S columns of its next slab are requested from TMEM
-          // before the current one is exponentiated (two register sets)
-          const int f = ((pipe.slab & 1) == g) ? 0 : 1;
-          uint32_t sreg[2][16];
-          tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(f * KT + half * 16), sreg[0]);
-#pragma unroll
-          for (int i = 0; i < SPB / 2; ++i) {
-            if (f == 1) pipe.skip(1);
-            const int sl = 2 * i + f;
-            // fused epilogue of S: the two column halves of a lane quadrant take 16 columns each
-            float v[16];
-            const int col0 = sl * KT + half * 16;
-            tc::tmem_ld16_wait(sreg[i & 1]);
-            if (i + 1 < SPB / 2) tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)(col0 + 2 * KT), sreg[(i + 1) & 1]);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              v[j] = tc::ex2_approx(fminf(fmaf(__uint_as_float(sreg[i & 1][j]), 1.4426950408889634f,
-                                               xnc + zn_s[col0 + j]), l2os));
-            SEG(2);                                   // TMEM load + exp
-            long long* ptr = (a.trace && blockIdx.x == 0 && (tid & 255) == 0 && pipe.slab < 48) ? a.trace + 512 + pipe.slab * 4 : nullptr;
-            if (ptr) ptr[0] = clock64();
-            float *a_hi, *a_lo;
-            pipe.acquire(a_hi, a_lo);                 // slab sl - 2 (this group's previous one) has retired
-            if (ptr) ptr[1] = clock64();
-            SEG(3);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)               // k-chunks half * 4 + c of the slab
-              tc::store_split(a_hi, a_lo, tc::op_off<TNP>(row, half * 4 + c),
-                              make_float4(v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
-            SEG(4);                                   // split + store of the k slab
-            if (ptr) ptr[2] = clock64();
-            pipe.commit();
-            if (ptr) ptr[3] = clock64();
-            SEG(5);                                   // fences + arrive
-            if (q == p && sl >= 2) {                  // chunk sl - 2 is final: handled while the tensor core works on
-              tc::tc_fence_after();
-              epi_chunk(p, sl - 2);
-              SEG(6);
-            }
-            if (f == 0) pipe.skip(1);
+          if (do_finalize) {                              // (SPQ < 2 never happens: BQ >= 64)
+            finalize_prev();
+            if (g == 0 && half == 0) xw_prev = xw_new;
           }
-          if (q == p) {
-            // this group's last slab of the block: its chunk is final once it has retired
-            tc::mbar_wait(&bars[g], (pipe.uses[g] - 1) & 1);
-            tc::tc_fence_after();
-            epi_chunk(p, SPB - 2 + f);
-            SEG(6);
+          if (c0 + SPQ - 2 >= 0) {                        // the last two chunks finalised by this pass: deferred
+            pend_n = 2; pend_ca = c0 + SPQ - 2; pend_P = P; pend_par = blk_ctr & 1u; pend_tile = tile;
           }
         }
       }
-      mu_s[g * 2 + half][row] = mu;
-      vv_s[g * 2 + half][row] = vv;
       have_prev = true;
-      prev_gn = n0 + row;
+      prev_gn = gn;
     }
+    run_pending();
+    if (have_prev) { mu_s[g * 2 + half][row] = mu; vv_s[g * 2 + half][row] = vv; }
     tc::tc_fence_before();
     producers_sync();
-    if (g == 0 && half == 0 && have_prev && prev_gn < N) {
-      const float mean = mu_s[0][row] + mu_s[1][row] + mu_s[2][row] + mu_s[3][row] + xw_prev + cwb;
-      const float var = fmaxf(os + jit + vv_s[0][row] + vv_s[1][row] + vv_s[2][row] + vv_s[3][row], kMinVariance);
-      a.mean[prev_gn] = mean;
-      a.var[prev_gn] = var;
-      if (a.sample)
-        a.sample[prev_gn] = fmaf(sqrtf(var), philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)prev_gn, a.stream_id), mean);
-    }
-    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32))
-      for (int i = 0; i < 8; ++i) a.dbg[(tid == 0 ? 0 : 8) + i] = seg[i];
-#undef SEG
+    finalize_prev();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -796,556 +662,553 @@ __global__ void __launch_bounds__(kTwoGroupThreads, 1) tc_point_fwd_kernel(TcPoi
 }
 
 // =================================================================================================
-// backward: W = kbar o k and its row sums, one column block p of width BW at a time
+// backward: W = kbar o k, its row sums, dx and the per-dimension reductions in ONE kernel (W never leaves the chip on
+// its way into the dx GEMM)
 // =================================================================================================
-// Warp roles of the backward kernel (640 threads, 96 registers each; warps 17..19 idle):
-//   warps 0..7   ROW OWNERS : phase A (x~ planes, row statistics), epilogue chunks (thread = point), W stores
-//   warps 8..15  LOADERS    : the saved-A slabs of the T GEMM: global loads -> TF32 split -> A planes -> arrive
-//   warp 16      ISSUER     : TMA requests + MMAs (+ per-chunk commits)
-// The two producer groups share one operand ring; both count every slab, each arrives (256 threads) only on its own.
-constexpr int kBwdThreads = 640;   // (measured: 0.30 ms at 640 threads against 0.33 ms at 544, c5 M=256)
-constexpr int kBwdIssuerWarp = kTwoGroupIssuerWarp;
+//   S  = X~ Z~[p]^T                                   (column block p of BT = min(MP, 128) inducing points)
+//   T  = a (diag(c) Linv)[:, block p]                 (slabs of the saved a in DEcreasing order: the first MMA
+//                                                      initialises every column, chunk c is final after slab p SPB + c)
+//   W  = (g_mu beta + 2 g_var T) o k,  r = rowsum(W)  (thread = point; W is saved tile-major for the W^T X reduction)
+//   DX += W[:, chunk] Z~[chunk]                        (A operand = W straight from the epilogue registers)
+//   dx = (DX - r x~) / ell + g_mu w                   (staged through shared memory: coalesced row-major stores)
+// TMEM columns: [ S : BT | T : BT | DX : DXW | A operand ring : 64 per stage ].
+// Warp roles (640 threads): warps 0..7 LOADERS (saved-a slabs: tile-major loads three slabs ahead -> tcgen05.st; x~ slabs
+// from the shared x~ tile), warps 8..15 ROW OWNERS (x tile -> shared memory, chunk epilogues, W operand of the dx GEMM,
+// dx epilogue), warp 16 MMA issuer, warp 17 B loader.  Slab g uses A stage g % NSTA whoever produces it.
+struct BwdBars {
+  Bars b;
+  uint64_t dx_full;      // the DX accumulator of the tile is complete
+  uint64_t x_ready;      // the row owners have put the x~ tile of the current tile into shared memory
+};
 
-template <int BW>
-__global__ void __launch_bounds__(kBwdThreads, 1) tc_point_bwd_kernel(TcPointArgs a) {
+// slab order of one tile (see the kernel header); returns the slab count.  `kind`: 0 = saved-a slab, 1 = x~ slab,
+// 2 = W slab (the producers walk the same order)
+template <int BT, int DXW>
+__device__ __forceinline__ int bwd_table(Slab* tab, const Tc2Args& a, int nthreads) {
+  const WsLayout& L = a.L;
+  const int MP = L.MP, NP = MP / BT, SPB = BT / KT, NSL = MP / KT;
+  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  const float* ZtQ = ws_cptr<float>(a.ws, L.ZtQ);
+  const float* LCTQ = ws_cptr<float>(a.ws, L.LCTQ);
+  const float* ZtTU = ws_cptr<float>(a.ws, L.ZtTU);
+  int total = 0;
+  for (int p = 0; p < NP; ++p) total += (NSL - p * SPB) + nds + SPB;
+  for (int i = threadIdx.x; i < total; i += nthreads) {
+    int p = 0, base = 0;
+    while (true) {
+      const int cnt = (NSL - p * SPB) + nds + SPB;
+      if (i < base + cnt) break;
+      base += cnt;
+      ++p;
+    }
+    const int j = i - base;
+    const int ndense = NSL - (p + 1) * SPB;               // slabs above block p: BT rows each
+    Slab d;
+    if (j < ndense || (j >= ndense + nds && j < ndense + nds + SPB)) {
+      const int t = j < ndense ? j : j - nds;             // index among the T slabs of the block (decreasing s)
+      const int sg = NSL - 1 - t;
+      int rows;
+      d.img = LCTQ + tc_lctq_image(MP, p, sg, &rows);
+      d.rows = rows; d.tmem_off = (uint32_t)BT;
+      d.flags = (t == 0 ? SF_FIRST : 0u);
+      const int c = sg - p * SPB;
+      if (c < SPB) d.flags |= (uint32_t)(c + 1) << 8;
+    } else if (j < ndense + nds) {
+      const int ds = j - ndense;
+      d.img = ZtQ + tc_zq_image(MP, nds, p, ds);
+      d.rows = BT; d.tmem_off = 0;
+      d.flags = (ds == 0 ? SF_FIRST : 0u) | (ds == nds - 1 ? SF_SIG_S : 0u);
+    } else {
+      const int c = SPB - 1 - (j - ndense - nds - SPB);   // W chunks in the order they become final
+      d.img = ZtTU + tc_slab_ztt(DXW, p * SPB + c);
+      d.rows = DXW; d.tmem_off = (uint32_t)(2 * BT);
+      d.flags = SF_GRP_E | ((p == 0 && c == SPB - 1) ? SF_FIRST : 0u) | ((p == NP - 1 && c == 0) ? SF_SIG_DX : 0u);
+    }
+    tab[i] = d;
+  }
+  return total;
+}
+constexpr int kMaxBwdSlabs = (32 + 28 + 24 + 20 + 16 + 12 + 8 + 4) + 8 * (4 + 4);   // MP = 1024, BT = 128, D = 128
+
+// sum over the 32 lanes of v[i] for 16 values at once ("transpose-reduce": 16 shuffles instead of 80); afterwards lane l
+// holds the total of value index ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int warp_reduce16_index(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+template <int BT, int DXW, int NSTA, int NSTB>
+__global__ void __launch_bounds__(kCtaThreads, 1) tc2_bwd_kernel(Tc2Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[6];
-  __shared__ __align__(8) uint64_t chunk_bars[8];                    // accumulator chunk c of the current block is final
-  __shared__ __align__(8) uint64_t ld_ready[2];                      // the loader warps have passed phase-A slabs 0-1 / 2-3 of the block
+  __shared__ __align__(8) BwdBars bb;
   __shared__ uint32_t tmem_slot;
-  __shared__ SlabDesc tab[kMaxBwdSlabs];
+  __shared__ Slab tab[kMaxBwdSlabs];
   __shared__ int tab_n;
-  __shared__ float zn_s[BW], beta_s[BW];                              // exponent offsets / beta of column block p
-  __shared__ float xn_s[TNP], xw_s[TNP], r_s[TNP];
-  __shared__ float part_n[(KT / 4) * TNP], part_w[(KT / 4) * TNP];  // per-slab row-statistic partials of phase A
+  __shared__ float r_s[2][TNP];                   // row sums of W per k-half
+  __shared__ float vec_s[2][4][2 * 128];          // [k-half][quadrant][q (DXW / 2) | t1 (DXW / 2)] per-warp partials
+  __shared__ float sc_s[8][4];                    // per-warp scalar sums
+  constexpr uint32_t S_COL = 0, T_COL = BT, DX_COL = 2 * BT, AOP_COL = 2 * BT + DXW;
+  constexpr uint32_t USED_COLS = 2 * BT + DXW + NSTA * 64;
+  constexpr uint32_t TMEM_COLS = USED_COLS <= 256 ? 256 : 512;
+  static_assert(USED_COLS <= 512, "tensor memory budget");
+  constexpr uint32_t BROWS = BT > DXW ? BT : DXW;
+  constexpr uint32_t STAGE_BYTES = BROWS * 256;
+  constexpr int SPB = BT / KT;
+  constexpr int HW = DXW / 2;                     // dx columns per k-half
+  constexpr int NPIECE = HW / 16;                 // 16-column pieces per row owner
+  constexpr int XP = DXW + 4;                     // pitch (floats) of the x~ tile: conflict-free 16-byte row reads
+  constexpr int SP = 20;                          // pitch of a [32 rows x 16 columns] dx staging tile
 
   const WsLayout& L = a.L;
-  const int MP = L.MP;
-  const int NP = MP / BW, SPB = BW / KT, NSL = MP / KT;
+  const int MP = L.MP, NP = MP / BT, NSL = MP / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* hyp = ws_cptr<float>(a.ws, L.hyp);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
-  float* rrow = ws_ptr<float>(a.ws, L.rrow);
-  const float* znc_g = ws_cptr<float>(a.ws, L.znc);
-  const float* beta_g = ws_cptr<float>(a.ws, L.beta);
-  const float l2os = log2f(hyp[H_OS]);
-  const int nds = L.DP >= KT ? L.DP / KT : 1;
+  float* vecpart = ws_ptr<float>(a.ws, L.vecpart);
+  const int DP = L.DP, D = L.D;
+  const int nds = DP >= KT ? DP / KT : 1;
 
-  constexpr uint32_t TMEM_COLS = 2 * BW;
+  // shared memory behind the B ring: constants, the x~ tile, the dx staging tiles of the 8 row-owner warps
+  float* cst = reinterpret_cast<float*>(smem_raw + (size_t)NSTB * STAGE_BYTES);
+  float* znc_s = cst;                // [MP] exponent offsets
+  float* beta_s = znc_s + MP;        // [MP] Linv^T m
+  float* cen_s = beta_s + MP;        // [DXW] centre
+  float* iel_s = cen_s + DXW;        // [DXW] 1 / ell
+  float* wl_s = iel_s + DXW;         // [DXW] ell * w
+  float* xt_s = wl_s + DXW;          // [128][XP] scaled inputs of the tile
+  float* stg_s = xt_s + TNP * XP;    // [8][32][SP]
+  {
+    const float* znc_g = ws_cptr<float>(a.ws, L.znc);
+    const float* beta_g = ws_cptr<float>(a.ws, L.beta);
+    const float* center = ws_cptr<float>(a.ws, L.center);
+    const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
+    const float* wl = ws_cptr<float>(a.ws, L.wl);
+    for (int i = tid; i < MP; i += kCtaThreads) { znc_s[i] = znc_g[i]; beta_s[i] = beta_g[i]; }
+    for (int i = tid; i < DXW; i += kCtaThreads) {
+      const bool ok = i < DP;
+      cen_s[i] = ok ? center[i] : 0.f; iel_s[i] = ok ? inv_ell[i] : 0.f; wl_s[i] = ok ? wl[i] : 0.f;
+    }
+  }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) {
-    init_ring_barriers(bars);
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&chunk_bars[i], 1);
-    tc::mbar_init(&ld_ready[0], kThreads);
-    tc::mbar_init(&ld_ready[1], kThreads);
+  if (tid == 32) {
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(&bb.b.a_ready[i], kGroup); tc::mbar_init(&bb.b.mma_done[i], 1); }
+    for (int i = 0; i < 6; ++i) { tc::mbar_init(&bb.b.b_full[i], 1); tc::mbar_init(&bb.b.b_empty[i], 1); }
+    tc::mbar_init(&bb.b.s_full, 1);
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&bb.b.chunk[i], 1);
+    tc::mbar_init(&bb.dx_full, 1);
+    tc::mbar_init(&bb.x_ready, kGroup);
     tc::fence_barrier_init();
   }
-  if (tid < kThreads) {
-    for (int i = tid; i < BW; i += kThreads) {      // block 0; reloaded per p when MP > BW
-      zn_s[i] = znc_g[i];                            // exponent offsets (formula above)
-      beta_s[i] = beta_g[i];
-    }
-    const int n = bwd_table<BW>(tab, a);
+  {
+    const int n = bwd_table<BT, DXW>(tab, a, kCtaThreads);
     if (tid == 0) tab_n = n;
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_s = tmem_slot, tmem_t = tmem_slot + BW;
+  const uint32_t tmem_base = tmem_slot;
   const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  Bars* bars = &bb.b;
 
-  if (warp >= kBwdIssuerWarp) {
-    // ---------------- issuer warpgroup ----------------
-    if (warp == kBwdIssuerWarp) issuer_loop<BW>(stage_base, bars, tmem_slot, tab, tab_n, tiles_mine, nullptr, chunk_bars);
-  } else if (warp >= 8) {
-    // ---------------- loader warps: saved-A slabs -> A planes ----------------
-    Pipe<BW> pipe;
-    pipe.init(stage_base, bars);
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const long long n0 = (long long)tile * TNP;
-      auto load_a = [&](OpRegs<TNP>& regs, int sl) {
-        load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-          long long g2 = n0 + r;
-          if (g2 >= N) g2 = N - 1;                       // clamped rows carry g = 0
-          return ldg4(Ag + (size_t)g2 * MP + sl * KT + c * 4);
-        });
-      };
-      for (int p = 0; p < NP; ++p) {
-        const int s_lo = p * SPB;
-        // three slabs in flight (rotating register sets); the first ones are requested while the row owners are
-        // still in phase A
-        OpRegs<TNP> r0, r1, r2;
-        load_a(r0, NSL - 1);
-        if (NSL - 2 >= s_lo) load_a(r1, NSL - 2);
-        if (NSL - 3 >= s_lo) load_a(r2, NSL - 3);
-        // the phase-A slabs of this block belong to the row owners.  skip_wait() tests the PREVIOUS use of the slab's
-        // stage; the row owners publish a pair of slabs only after the arrival for it, so no loader can find a ring barrier two
-        // phases further than it expects (parity aliasing)
-        for (int ds = 0; ds < nds; ds += 2) {
-          pipe.skip_wait(nds - ds < 2 ? nds - ds : 2);
-          mbar_arrive(&ld_ready[ds >> 1]);
-        }
-        for (int s = NSL - 1; s >= s_lo; s -= 3) {
-          float *a_hi, *a_lo;
-          pipe.acquire(a_hi, a_lo);
-          store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
-          if (s - 3 >= s_lo) load_a(r0, s - 3);
-          pipe.commit();
-          if (s - 1 < s_lo) break;
-          pipe.acquire(a_hi, a_lo);
-          store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
-          if (s - 4 >= s_lo) load_a(r1, s - 4);
-          pipe.commit();
-          if (s - 2 < s_lo) break;
-          pipe.acquire(a_hi, a_lo);
-          store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
-          if (s - 5 >= s_lo) load_a(r2, s - 5);
-          pipe.commit();
-        }
-      }
+  if (warp >= kIssuerWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsIssuer));
+    if (warp == kIssuerWarp) {
+      // the issuer's extra commit: SF_SIG_DX rides on the s_full slot of the generic issuer via a wrapper table flag
+      tc2_issuer<NSTA, NSTB, true>(smem_raw, STAGE_BYTES, bars, tmem_base, AOP_COL, tab, tab_n, tiles_mine,
+                                   blockIdx.x == 0 ? a.trace : nullptr, &bb.dx_full);
+    } else if (warp == kIssuerWarp + 1) {
+      tc2_loader<NSTB>(smem_raw, STAGE_BYTES, bars, tab, tab_n, tiles_mine);
     }
   } else {
-    // ---------------- row-owner warps ----------------
-    Pipe<BW> pipe;
-    pipe.init(stage_base, bars);
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    const int grp = warp >> 3;                            // 0 = loaders, 1 = row owners
+    const int quad = warp & 3, half = (warp >> 2) & 1;   // TMEM lane quadrant / k-half of this warp
+    const int row = quad * 32 + lane;                     // the point this thread owns
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint32_t blk = 0;                                 // blocks processed so far: phase of the chunk barriers
+    const uint32_t aop_base = tmem_base + lane_base + AOP_COL;
+    uint32_t tile_ctr = 0;
 
-    long long bseg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long blast = clock64();
-#define BSEG(i) do { if (a.dbg) { const long long tnow = clock64(); bseg[i] += tnow - blast; blast = tnow; } } while (0)
-    OpRegs<TNP> xr0, xr1;
-    {
-      const XLoader xl0 = make_xloader(a, (long long)blockIdx.x * TNP);
-      load_x_slab(xr0, xl0, 0, L.DP);
-      if (L.DP > KT) load_x_slab(xr1, xl0, 1, L.DP);
-    }
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const long long n0 = (long long)tile * TNP;
-      const long long gn = n0 + row;
-      const XLoader xl = make_xloader(a, n0);
-      const bool more_tiles = tile + (int)gridDim.x < a.ntiles;
-      const long long w0 = n0 + quad * 32;        // first point of this warp
-      const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-      // ---- fold the upstream gradients of this thread's point ----
-      float gm = 0.f, gv = 0.f;
-      if (gn < N) {
-        if (a.g_mean) gm = a.g_mean[gn];
-        if (a.g_var) gv = a.g_var[gn];
-        const float v = a.var_in[gn];
-        if (a.g_sample) {
-          const float gs = a.g_sample[gn];
-          const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
-          gm += gs;
-          gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);
-        }
-        if (v <= kMinVariance) gv = 0.f;
-        if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
-      }
-      float rsum = 0.f, xnc = 0.f;
-      BSEG(0);                                        // tile head (upstream gradients)
-      // epilogue of one 32-column chunk c of column block p (16 columns per column half): W = kbar o k, its row sum,
-      // W saved for the dx / W^T X kernels.  T[:, chunk c] is last touched by slab p SPB + c, the slabs run in
-      // DEcreasing order, and the issuer commits that slab onto chunk_bars[c]: the chunks are handled while the
-      // tensor core (and the loader warps) work on the remaining slabs.
-      auto epi_chunk = [&](int p, int c) {
-        const int col = c * 32 + half * 16;
-        uint32_t kr[16], tr[16];
-        tc::tmem_ld16_issue(tmem_s + lane_base + (uint32_t)col, kr);
-        tc::tmem_ld16_issue(tmem_t + lane_base + (uint32_t)col, tr);
-        tc::tmem_ld16_wait(kr);
-        tc::tmem_ld16_wait(tr);
-        float t[16];
+    if (grp == 0) {
+      // =================== loaders ===================
+      uint32_t cnt = 0;                                   // slabs produced by this group (private ring [0, NSTA - 1))
+      // three saved-a slabs in flight (rotating register sets), requested in the order of the table
+      float4 ra[3][4];
+      auto load_a = [&](float4 (&r)[4], int tile, int sg) {
+        const float4* At = reinterpret_cast<const float4*>(Ag) +
+                           ((size_t)tile * (size_t)(MP >> 2) + (size_t)((sg * KT + half * 16) >> 2)) * TNP + row;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float k = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i]), 1.4426950408889634f, xnc + zn_s[col + i]), l2os));
-          const float kb = fmaf(2.0f * gv, __uint_as_float(tr[i]), gm * beta_s[col + i]);
-          t[i] = kb * k;
-          rsum += t[i];
-        }
-        if (a.exp_mode != 4)
-          warp_store_rows16(Wg + (size_t)w0 * MP + p * BW + col, MP, t, lane, nvalid);   // (no staging: lane-pair exchange)
+        for (int i = 0; i < 4; ++i) r[i] = ldg4_pinned(reinterpret_cast<const float*>(At + (size_t)i * TNP));
       };
-      for (int p = 0; p < NP; ++p, ++blk) {
-        if (NP > 1) {                                 // per-block constants (single block: loaded once at kernel start)
-          group_sync(1);
-          if (tid < BW) { zn_s[tid] = znc_g[p * BW + tid]; beta_s[tid] = beta_g[p * BW + tid]; }
-          group_sync(1);
-        }
-        phase_a<BW>(pipe, a, xl, p == 0, part_n, part_w, xn_s, xw_s, p == 0, xr0, xr1, ld_ready, blk);
-        if (p == 0 && more_tiles) {
-          const XLoader xln = make_xloader(a, n0 + (long long)gridDim.x * TNP);
-          load_x_slab(xr0, xln, 0, L.DP);
-          if (L.DP > KT) load_x_slab(xr1, xln, 1, L.DP);
-        }
-        xnc = -0.72134752044448170f * xn_s[row];
-        BSEG(1);                                      // phase A
-        pipe.skip(NSL - p * SPB);                     // the T slabs of this block belong to the loader warps
-        for (int c = SPB - 1; c >= 0; --c) {
-          tc::mbar_wait(&chunk_bars[c], blk & 1);
-          tc::tc_fence_after();
-          BSEG(2);                                    // wait for the chunk's last slab
-          epi_chunk(p, c);
-          BSEG(5);                                    // epilogue chunk
-        }
-        // the TMEM reads are done before ANY row owner publishes A planes of the next phase (its MMAs overwrite S)
-        tc::tc_fence_before();
-        group_sync(1);
+      // the sequence of saved-a slabs of this CTA: (tile, p, t) -> slab sg = NSL - 1 - t, t < NSL - p SPB
+      int pf_tile = blockIdx.x, pf_p = 0, pf_t = 0;       // next slab to request
+      auto pf_advance = [&]() {
+        if (++pf_t == NSL - pf_p * SPB) { pf_t = 0; if (++pf_p == NP) { pf_p = 0; pf_tile += gridDim.x; } }
+      };
+      int slot_w = 0, slot_r = 0;
+      for (int i = 0; i < 3; ++i) {
+        if (pf_tile < a.ntiles) { load_a(ra[slot_w], pf_tile, NSL - 1 - pf_t); pf_advance(); }
+        slot_w = slot_w == 2 ? 0 : slot_w + 1;
       }
-      if (half == 1) r_s[row] = rsum;
-      group_sync(1);
-      if (half == 0 && gn < N) rrow[gn] = rsum + r_s[row];
-      group_sync(1);
-      BSEG(7);                                        // row sums
-    }
-    if (a.dbg && blockIdx.x == 0 && tid == 0)
-      for (int i = 0; i < 8; ++i) a.dbg[16 + i] = bseg[i];
-#undef BSEG
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
-}
-
-// =================================================================================================
-// dx = (W Z~ - r x~) / ell + g_mu w  and the per-dimension reductions q, wbar + scalar sums
-// =================================================================================================
-template <int DPT>   // DPT = MMA N = padded input dim (32, 64 or 128)
-__global__ void __launch_bounds__(kBlockThreads, 1) tc_dx_kernel(TcPointArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(8) uint64_t bars[6];
-  __shared__ uint32_t tmem_slot;
-  __shared__ SlabDesc tab[GPBLUR_MAX_M / KT];
-  __shared__ __align__(16) float red[8][32][kStagePitch];   // per-warp staging tile (x~ in, dx out)
-  __shared__ float rg_s[8][2][32];                             // per-warp r[n], g_mu[n] of its 32 points
-  __shared__ float part_q[8][32], part_t[8][32], part_q2[8][32], part_t2[8][32], part_sc[8][4];
-  __shared__ float q_s[DPT], t1_s[DPT], sc_s[4];
-
-  const WsLayout& L = a.L;
-  const int D = L.D, DP = L.DP, MP = L.MP;
-  const long long N = L.N;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
-  const float* ellv = ws_cptr<float>(a.ws, L.ell);
-  const float* center = ws_cptr<float>(a.ws, L.center);
-  const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const float* ZtTU = ws_cptr<float>(a.ws, L.ZtTU);
-  const float* Wg = ws_cptr<float>(a.ws, L.W);
-  const float* gsc = ws_cptr<float>(a.ws, L.gsc);
-  const float* rrow = ws_cptr<float>(a.ws, L.rrow);
-  float* vecpart = ws_ptr<float>(a.ws, L.vecpart);
-
-  constexpr uint32_t TMEM_COLS = DPT;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
-  if (tid == 0) init_ring_barriers(bars);
-  if (tid < kThreads) {
-    for (int i = tid; i < DPT; i += kThreads) { q_s[i] = 0.f; t1_s[i] = 0.f; }
-    for (int i = tid; i < MP / KT; i += kThreads) {
-      SlabDesc d;
-      d.img = ZtTU + tc_slab_ztt(DPT, i);
-      d.rows = DPT; d.tmem_off = 0; d.first = i == 0;
-      tab[i] = d;
-    }
-  }
-  if (tid < 4) sc_s[tid] = 0.f;
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
-  const int tiles_mine = a.ntiles > (int)blockIdx.x ? (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (warp == kIssuerWarp) {
-    issuer_loop<DPT, true>(stage_base, bars, tmem_slot, tab, MP / KT, tiles_mine, blockIdx.x == 0 ? a.trace : nullptr, nullptr,
-                           !(a.exp_mode & 8));
-  } else {
-  Pipe<DPT> pipe;
-  pipe.init(stage_base, bars);
-  long long dseg[6] = {0, 0, 0, 0, 0, 0};
-  long long dlast = clock64();
-#define DSEG(i) do { if (a.dbg) { const long long tnow = clock64(); dseg[i] += tnow - dlast; dlast = tnow; } } while (0)
-
-  // epilogue mapping: the 8 warps cover 4 lane quadrants x 2 column halves of the [128, DPT] tile; with DPT = 32
-  // only the first 4 warps have columns.
-  const int quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-  constexpr int CH_PER_HALF = DPT >= 64 ? DPT / 64 : 1;
-  const bool has_cols = DPT >= 64 || half == 0;
-  const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(a.dx) & 15) == 0);
-
-  OpRegs<TNP> r0, r1, r2;
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const long long n0 = (long long)tile * TNP;
-    auto load_w_at = [&](OpRegs<TNP>& regs, long long nbase, int sl) {
-      load_kmajor<TNP>(regs, TNP, [&](int r, int c) {
-        const long long gn = nbase + r;
-        return gn < N ? ldg4(Wg + (size_t)gn * MP + sl * KT + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      });
-    };
-    auto load_w = [&](OpRegs<TNP>& regs, int sl) { load_w_at(regs, n0, sl); };
-    // per-point scalars and the x rows of the first epilogue chunk: requested now, consumed after the GEMM
-    const long long gn = n0 + row;
-    const bool live = gn < N;
-    const float r = live ? rrow[gn] : 0.f;
-    const float gm = live ? gsc[gn] : 0.f;
-    const float gv = live ? gsc[N + gn] : 0.f;
-    const long long w0 = n0 + quad * 32;
-    const int nvalid = N - w0 >= 32 ? 32 : (N > w0 ? (int)(N - w0) : 0);
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-    auto load_x_chunk = [&](float4 (&xq)[8], int col) {
-      const int d = col + c4;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tile_ctr) {
+        for (int p = 0; p < NP; ++p) {
+          const int ndense = NSL - (p + 1) * SPB;
+          const int nt = NSL - p * SPB;
+          for (int t = 0; t < nt; ++t) {
+            if (t == ndense) {
+              // ---- x~ slabs of S block p (from the shared x~ tile the row owners publish once per tile) ----
+              if (p == 0) tc::mbar_wait(&bb.x_ready, tile_ctr & 1u);
+              for (int ds = 0; ds < nds; ++ds, ++cnt) {
+                float v[16];
+                const float* xr = xt_s + row * XP + ds * KT + half * 16;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rsub;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < nvalid && d < D) {
-          const float* xr = a.x + (size_t)(w0 + rr) * D + d;
-          if (vec) xv = ldg4(xr);
-          else {
-            xv.x = xr[0];
-            if (d + 1 < D) xv.y = xr[1];
-            if (d + 2 < D) xv.z = xr[2];
-            if (d + 3 < D) xv.w = xr[3];
-          }
-        }
-        xq[it] = xv;
-      }
-    };
-    float4 xq[8];
-    if (has_cols) load_x_chunk(xq, DPT >= 64 ? half * (DPT / 2) : 0);
-    // W slabs are fetched three slabs ahead (rotating register sets) to keep enough bytes in flight per SM; the
-    // first three of a tile are requested before the PREVIOUS tile's epilogue (see below)
-    const int nsl = MP / KT;
-    DSEG(0);
-    if (tile == (int)blockIdx.x) {
-      load_w(r0, 0);
-      if (1 < nsl) load_w(r1, 1);
-      if (2 < nsl) load_w(r2, 2);
-    }
-    for (int s = 0; s < nsl; s += 3) {
-      float *a_hi, *a_lo;
-      long long* ptr = (a.trace && blockIdx.x == 0 && (tid == 0 || tid == 255) && pipe.slab < 48)
-                           ? a.trace + 512 + (tid == 0 ? 0 : 256) + pipe.slab * 4 : nullptr;
-      if (ptr) ptr[0] = clock64();
-      pipe.acquire(a_hi, a_lo);
-      if (ptr) ptr[1] = clock64();
-      DSEG(1);
-      store_kmajor<TNP>(a_hi, a_lo, r0, TNP);
-      if (ptr) ptr[2] = clock64();
-      DSEG(2);
-      if (s + 3 < nsl) load_w(r0, s + 3);
-      pipe.commit();
-      if (ptr) ptr[3] = clock64();
-      DSEG(3);
-      if (s + 1 >= nsl) break;
-      pipe.acquire(a_hi, a_lo);
-      DSEG(1);
-      store_kmajor<TNP>(a_hi, a_lo, r1, TNP);
-      DSEG(2);
-      if (s + 4 < nsl) load_w(r1, s + 4);
-      pipe.commit();
-      DSEG(3);
-      if (s + 2 >= nsl) break;
-      pipe.acquire(a_hi, a_lo);
-      DSEG(1);
-      store_kmajor<TNP>(a_hi, a_lo, r2, TNP);
-      DSEG(2);
-      if (s + 5 < nsl) load_w(r2, s + 5);
-      pipe.commit();
-      DSEG(3);
-    }
-    if (tile + (int)gridDim.x < a.ntiles) {         // next tile's first W slabs fly during this tile's epilogue
-      const long long n1 = n0 + (long long)gridDim.x * TNP;
-      load_w_at(r0, n1, 0);
-      if (1 < nsl) load_w_at(r1, n1, 1);
-      if (2 < nsl) load_w_at(r2, n1, 2);
-    }
-    pipe.drain();
-    DSEG(4);
-
-    if (has_cols) {
-      // the warp owns the points n0 + quad * 32 + [0, 32) and 32 dimensions per chunk.  x comes in with coalesced
-      // 16-byte loads (8 lanes per row segment), is centred / scaled once and parked in the warp's staging tile
-      // red[warp][row][.] (pitch 36: conflict-free row AND column access); the per-dimension sums read it by column
-      // (lane = dimension), the dx rows are written back through the same tile, transposed and coalesced.
-      float (*stg)[kStagePitch] = red[warp];
-      rg_s[warp][0][lane] = live ? r : 0.f;
-      rg_s[warp][1][lane] = live ? gm : 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < CH_PER_HALF; ++ch) {
-        const int col = (DPT >= 64 ? half * (DPT / 2) : 0) + ch * 32;
-        __syncwarp();
-        {
-          const int d = col + c4;
-          const float4 c4v = d < DP ? ldg4(center + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 iev = d < DP ? ldg4(inv_ell + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ch > 0) load_x_chunk(xq, col);           // DPT = 128 only; the first chunk was prefetched
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            float4 xv = xq[it];
-            if (rr < nvalid && d < D) {
-              xv.x = (xv.x - c4v.x) * iev.x; xv.y = (xv.y - c4v.y) * iev.y;
-              xv.z = (xv.z - c4v.z) * iev.z; xv.w = (xv.w - c4v.w) * iev.w;
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 x4 = *reinterpret_cast<const float4*>(xr + i);
+                  v[i] = x4.x; v[i + 1] = x4.y; v[i + 2] = x4.z; v[i + 3] = x4.w;
+                }
+                const int st = ring_acquire(bars, cnt, 0, NSTA - 1);
+                store_operand16(aop_base, st, half * 16, v);
+                ring_publish(bars, st);
+              }
             }
-            *reinterpret_cast<float4*>(&stg[rr][c4]) = xv;
+            // ---- saved-a slab sg = NSL - 1 - t ----
+            {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 x4 = slot_r == 0 ? ra[0][i] : (slot_r == 1 ? ra[1][i] : ra[2][i]);
+                v[4 * i] = x4.x; v[4 * i + 1] = x4.y; v[4 * i + 2] = x4.z; v[4 * i + 3] = x4.w;
+              }
+              const int st = ring_acquire(bars, cnt, 0, NSTA - 1);
+              store_operand16(aop_base, st, half * 16, v);
+              ring_publish(bars, st);
+              ++cnt;
+              // refill the slot with the slab three ahead
+              if (pf_tile < a.ntiles) {
+                if (slot_r == 0) load_a(ra[0], pf_tile, NSL - 1 - pf_t);
+                else if (slot_r == 1) load_a(ra[1], pf_tile, NSL - 1 - pf_t);
+                else load_a(ra[2], pf_tile, NSL - 1 - pf_t);
+                pf_advance();
+              }
+              slot_r = slot_r == 2 ? 0 : slot_r + 1;
+            }
           }
         }
-        __syncwarp();
-        // per-dimension reductions over the 32 points of this warp (lane = dimension col + lane), fixed order:
-        // q_d = sum r x~^2, t1_d = sum g_mu x~
-        float sq = 0.f, st = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          const float xv = stg[rr][lane];
-          sq = fmaf(rg_s[warp][0][rr] * xv, xv, sq);
-          st = fmaf(rg_s[warp][1][rr], xv, st);
+      }
+    } else {
+      // =================== row owners ===================
+      const float l2os = log2f(hyp[H_OS]);
+      const uint32_t tmem_s = tmem_base + lane_base + S_COL, tmem_t = tmem_base + lane_base + T_COL;
+      const uint32_t tmem_dx = tmem_base + lane_base + DX_COL;
+      const int et = tid - kGroup;                        // thread index within the group
+      const int ew = warp - 8;                            // warp index within the group
+      float* stg = stg_s + ew * 32 * SP;
+      const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+      const bool vec_dx = a.dx && (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.dx) & 15) == 0);
+      uint32_t pass_ctr = 0;
+      float qacc[NPIECE], tacc[NPIECE];                   // per-dimension reductions of this warp (lane-distributed)
+#pragma unroll
+      for (int i = 0; i < NPIECE; ++i) { qacc[i] = 0.f; tacc[i] = 0.f; }
+      float s_gm = 0.f, s_r = 0.f, s_gv = 0.f;           // scalar sums (k-half 0 threads)
+      uint32_t cnt = 0;                                   // W slabs produced so far (private stage NSTA - 1)
+      // x rows of a tile go global -> shared memory with cp.async (coalesced: 16 bytes per thread and request, no
+      // registers), one tile ahead: issued after the previous tile's dx epilogue, awaited at the tile head
+      constexpr int XREQ = TNP * (DXW / 4) / kGroup;      // requests per thread
+      auto request_x_tile = [&](long long n0) {
+        if (!vec) return;                                 // (unaligned / D % 4 != 0: loaded synchronously below)
+#pragma unroll 4
+        for (int i = 0; i < XREQ; ++i) {
+          const int idx = et + i * kGroup;
+          const int r = idx / (DXW / 4), c4 = (idx % (DXW / 4)) * 4;
+          if (n0 + r < N && c4 < D) cp_async16(xt_s + r * XP + c4, a.x + (size_t)(n0 + r) * D + c4);
         }
-        // dx row of this lane's point: (W Z~ - r x~) / ell + g_mu w
-        float v[32];
-        tc::tmem_ld32(tmem_d + lane_base + (uint32_t)col, v);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int d = col + i;
-          const float4 xs4 = *reinterpret_cast<const float4*>(&stg[lane][i]);
-          const float4 ie = d < DP ? ldg4(inv_ell + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 w4 = d < DP ? ldg4(wl + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[i + 0] = (v[i + 0] - r * xs4.x) * ie.x + gm * (w4.x * ie.x);
-          v[i + 1] = (v[i + 1] - r * xs4.y) * ie.y + gm * (w4.y * ie.y);
-          v[i + 2] = (v[i + 2] - r * xs4.z) * ie.z + gm * (w4.z * ie.z);
-          v[i + 3] = (v[i + 3] - r * xs4.w) * ie.w + gm * (w4.w * ie.w);
+        cp_async_commit();
+      };
+      request_x_tile((long long)blockIdx.x * TNP);
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tile_ctr) {
+        const long long n0 = (long long)tile * TNP;
+        const long long gn = n0 + row;
+        const bool live = gn < N;
+        // ---- upstream gradients of this thread's point (requested early) ----
+        float gm = 0.f, gv = 0.f;
+        if (live) {
+          if (a.g_mean) gm = a.g_mean[gn];
+          if (a.g_var) gv = a.g_var[gn];
+          const float vr = a.var_in[gn];
+          if (a.g_sample) {
+            const float gsv = a.g_sample[gn];
+            const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
+            gm += gsv;
+            gv = fmaf(gsv * eps, 0.5f * rsqrtf(vr), gv);
+          }
+          if (vr <= kMinVariance) gv = 0.f;
+          if (half == 0) { gsc[gn] = gm; gsc[N + gn] = gv; }
         }
-        __syncwarp();                                // every lane is done reading x~ by column
-        if (a.dx) {
+        // ---- x~ tile: centre / scale in place (every thread transforms the pieces it requested itself) ----
+        if (vec) cp_async_wait<0>();
+#pragma unroll 4
+        for (int i = 0; i < XREQ; ++i) {
+          const int idx = et + i * kGroup;
+          const int r = idx / (DXW / 4), c4 = (idx % (DXW / 4)) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n0 + r < N && c4 < D) {
+            if (vec) v = *reinterpret_cast<const float4*>(xt_s + r * XP + c4);
+            else {
+              const float* p = a.x + (size_t)(n0 + r) * D + c4;
+              v.x = p[0];
+              if (c4 + 1 < D) v.y = p[1];
+              if (c4 + 2 < D) v.z = p[2];
+              if (c4 + 3 < D) v.w = p[3];
+            }
+            const float4 c = *reinterpret_cast<const float4*>(cen_s + c4), ie = *reinterpret_cast<const float4*>(iel_s + c4);
+            v.x = (v.x - c.x) * ie.x; v.y = (v.y - c.y) * ie.y; v.z = (v.z - c.z) * ie.z; v.w = (v.w - c.w) * ie.w;
+          }
+          *reinterpret_cast<float4*>(xt_s + r * XP + c4) = v;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        mbar_arrive(&bb.x_ready);
+        float xnc;
+        {
+          float n2 = 0.f;
+          const float* xr = xt_s + row * XP;
+#pragma unroll 4
+          for (int i = 0; i < DXW; i += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + i);
+            n2 = fmaf(x4.w, x4.w, fmaf(x4.z, x4.z, fmaf(x4.y, x4.y, fmaf(x4.x, x4.x, n2))));
+          }
+          xnc = -0.72134752044448170f * n2;
+        }
+        float rsum = 0.f;
+        for (int p = 0; p < NP; ++p, ++pass_ctr) {
+          tc::mbar_wait(&bars->s_full, pass_ctr & 1u);    // S block p complete
+          tc::tc_fence_after();
+#pragma unroll 1
+          for (int c = SPB - 1; c >= 0; --c, ++cnt) {
+            // chunk c of T is final once slab p SPB + c has retired (the slabs run in decreasing order)
+            tc::mbar_wait(&bars->chunk[c], pass_ctr & 1u);
+            tc::tc_fence_after();
+            const int col = c * KT + half * 16;
+            uint32_t kr[16], tr[16];
+            tc::tmem_ld16_issue(tmem_s + (uint32_t)col, kr);
+            tc::tmem_ld16_issue(tmem_t + (uint32_t)col, tr);
+            tc::tmem_ld16_wait(kr);
+            tc::tmem_ld16_wait(tr);
+            float w[16];
+            const float* zp = znc_s + p * BT + col;
+            const float* bp = beta_s + p * BT + col;
+            const float gv2 = 2.0f * gv;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(&stg[lane][i]) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          __syncwarp();
-          const int d = col + c4;
+            for (int i = 0; i < 16; i += 4) {
+              const float4 z4 = *reinterpret_cast<const float4*>(zp + i), b4 = *reinterpret_cast<const float4*>(bp + i);
+              const float k0 = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i + 0]), 1.4426950408889634f, xnc + z4.x), l2os));
+              const float k1 = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i + 1]), 1.4426950408889634f, xnc + z4.y), l2os));
+              const float k2 = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i + 2]), 1.4426950408889634f, xnc + z4.z), l2os));
+              const float k3 = tc::ex2_approx(fminf(fmaf(__uint_as_float(kr[i + 3]), 1.4426950408889634f, xnc + z4.w), l2os));
+              w[i + 0] = fmaf(gv2, __uint_as_float(tr[i + 0]), gm * b4.x) * k0;
+              w[i + 1] = fmaf(gv2, __uint_as_float(tr[i + 1]), gm * b4.y) * k1;
+              w[i + 2] = fmaf(gv2, __uint_as_float(tr[i + 2]), gm * b4.z) * k2;
+              w[i + 3] = fmaf(gv2, __uint_as_float(tr[i + 3]), gm * b4.w) * k3;
+            }
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            if (rr < nvalid && d < D) {
-              const float4 o = *reinterpret_cast<const float4*>(&stg[rr][c4]);
-              float* dst = a.dx + (size_t)(w0 + rr) * D + d;
-              if (vec) *reinterpret_cast<float4*>(dst) = o;
-              else {
-                dst[0] = o.x;
-                if (d + 1 < D) dst[1] = o.y;
-                if (d + 2 < D) dst[2] = o.z;
-                if (d + 3 < D) dst[3] = o.w;
+            for (int i = 0; i < 16; ++i) rsum += w[i];
+            // the W operand of the dx GEMM first (the tensor core is waiting for it), then the tile-major copy for W^T X
+            {
+              const int st = ring_acquire(bars, cnt, NSTA - 1, 1);
+              store_operand16(aop_base, st, half * 16, w);
+              ring_publish(bars, st);
+            }
+            {
+              float4* Wt = reinterpret_cast<float4*>(Wg) + ((size_t)tile * (size_t)(MP >> 2) + (size_t)((p * BT + col) >> 2)) * TNP + row;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) Wt[(size_t)i * TNP] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            }
+          }
+        }
+        // ---- row sums: the two k-halves of a point ----
+        r_s[half][row] = rsum;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float rtot = r_s[0][row] + r_s[1][row];
+        if (half == 0 && live) { s_gm += gm; s_r += rtot; s_gv += gv; }
+        // ---- dx epilogue ----
+        tc::mbar_wait(&bb.dx_full, tile_ctr & 1u);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int pc = 0; pc < NPIECE; ++pc) {
+          const int col = half * HW + pc * 16;
+          float v[16], qv[16], tv[16];
+          tc::tmem_ld16(tmem_dx + (uint32_t)col, v);
+          const float* xr = xt_s + row * XP + col;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + i);
+            const float4 ie = *reinterpret_cast<const float4*>(iel_s + col + i), w4 = *reinterpret_cast<const float4*>(wl_s + col + i);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ies[4] = {ie.x, ie.y, ie.z, ie.w}, ws4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[i + e] = (v[i + e] - rtot * xs[e]) * ies[e] + gm * (ws4[e] * ies[e]);
+              qv[i + e] = rtot * xs[e] * xs[e];
+              tv[i + e] = gm * xs[e];
+            }
+          }
+          // per-dimension sums over the 32 points of the warp (fixed shuffle tree: deterministic)
+          qacc[pc] += warp_reduce16(qv, lane);
+          tacc[pc] += warp_reduce16(tv, lane);
+          if (a.dx) {
+            // [32 rows x 16 columns] through the warp's staging tile: 8 rows x 64 contiguous bytes per store instruction
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(stg + lane * SP + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            __syncwarp();
+            const int c4 = (lane & 3) * 4, rsub = lane >> 2;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + rsub;
+              const long long gr = n0 + quad * 32 + rr;
+              const int d = col + c4;
+              if (gr < N && d < D) {
+                const float4 o = *reinterpret_cast<const float4*>(stg + rr * SP + c4);
+                float* dst = a.dx + (size_t)gr * D + d;
+                if (vec_dx) *reinterpret_cast<float4*>(dst) = o;
+                else {
+                  dst[0] = o.x;
+                  if (d + 1 < D) dst[1] = o.y;
+                  if (d + 2 < D) dst[2] = o.z;
+                  if (d + 3 < D) dst[3] = o.w;
+                }
               }
             }
           }
         }
-        // this warp's partial for dimension col + lane; (quad, half, ch) -> combined below in fixed order
-        if (ch == 0) { part_q[warp][lane] = sq; part_t[warp][lane] = st; }
-        else { part_q2[warp][lane] = sq; part_t2[warp][lane] = st; }   // DPT = 128: second chunk of the half
+        // the DX reads of this tile are done before this group publishes the next tile's first W slab; the x~ tile may be
+        // overwritten (every slab of this tile has retired: dx_full)
+        tc::tc_fence_before();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (tile + (int)gridDim.x < a.ntiles) request_x_tile(n0 + (long long)gridDim.x * TNP);
+      }
+      // ---- per-CTA vector partial: [colsum MP (from the W^T X kernel) | q DP | wbar DP | scalars] ----
+      if ((lane & 1) == 0) {
+        const int idx = warp_reduce16_index(lane);
+#pragma unroll
+        for (int pc = 0; pc < NPIECE; ++pc) {
+          vec_s[half][quad][pc * 16 + idx] = qacc[pc];
+          vec_s[half][quad][HW + pc * 16 + idx] = tacc[pc];
+        }
+      }
+      {
+        const float sg = warp_sum(s_gm), sr = warp_sum(s_r), sv = warp_sum(s_gv);
+        if (lane == 0) { sc_s[ew][VS_GMU] = sg; sc_s[ew][VS_RSUM] = sr; sc_s[ew][VS_GVAR] = sv; sc_s[ew][3] = 0.f; }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
+      const float* ellv = ws_cptr<float>(a.ws, L.ell);
+      float sgm = 0.f;
+      for (int w = 0; w < 4; ++w) sgm += sc_s[w][VS_GMU];                 // k-half 0 warps, fixed order
+      for (int i = et; i < MP; i += kGroup) vp[i] = 0.f;
+      for (int d = et; d < DP; d += kGroup) {
+        float q = 0.f, t1 = 0.f;
+        if (d < DXW) {
+          const int hf = d / HW, within = d % HW;
+          for (int qd = 0; qd < 4; ++qd) { q += vec_s[hf][qd][within]; t1 += vec_s[hf][qd][HW + within]; }
+        }
+        vp[MP + d] = q;
+        vp[MP + DP + d] = d < D ? ellv[d] * t1 + cen_s[d < DXW ? d : 0] * sgm : 0.f;
+      }
+      if (et < VS_COUNT) {
+        float sum = 0.f;
+        if (et < 3) for (int w = 0; w < 4; ++w) sum += sc_s[w][et];
+        vp[MP + 2 * DP + et] = sum;
       }
     }
-    {
-      const float sg = warp_sum(live && half == 0 ? gm : 0.f);
-      const float sr = warp_sum(live && half == 0 ? r : 0.f);
-      const float sv = warp_sum(live && half == 0 ? gv : 0.f);
-      if (lane == 0) { part_sc[warp][VS_GMU] = sg; part_sc[warp][VS_RSUM] = sr; part_sc[warp][VS_GVAR] = sv; }
-    }
-    prod_sync();
-    // combine the 4 lane quadrants in fixed order: dimension d = half * (DPT / 2) + ch * 32 + lane
-    if (tid < DPT) {
-      const int d = tid;
-      const int hf = DPT >= 64 ? d / (DPT / 2) : 0;
-      const int within = DPT >= 64 ? d % (DPT / 2) : d;
-      const int ch = within / 32, ln = within % 32;
-      float sq = 0.f, st = 0.f;
-      for (int qd = 0; qd < 4; ++qd) {
-        const int w = hf * 4 + qd;
-        if (ch == 0) { sq += part_q[w][ln]; st += part_t[w][ln]; }
-        else { sq += part_q2[w][ln]; st += part_t2[w][ln]; }
-      }
-      q_s[d] += sq;
-      t1_s[d] += st;
-    }
-    if (tid < 3) {
-      float s = 0.f;
-      for (int w = 0; w < 4; ++w) s += part_sc[w][tid];
-      sc_s[tid] += s;
-    }
-    tc::tc_fence_before();   // the TMEM reads of this tile are done before the next tile's MMAs are released
-    prod_sync();
-    DSEG(5);
-  }
-  if (a.dbg && blockIdx.x == 0 && tid == 0)
-    for (int i = 0; i < 6; ++i) a.dbg[24 + i] = dseg[i];
-#undef DSEG
-  }   // producer warps
-  __syncthreads();
-  float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
-  if (tid < kThreads) {
-    for (int i = tid; i < MP; i += kThreads) vp[i] = 0.f;        // column sums come from the W^T X kernel
-    for (int d = tid; d < DP; d += kThreads) {
-      vp[MP + d] = d < DPT ? q_s[d] : 0.f;
-      vp[MP + DP + d] = (d < D && d < DPT) ? ellv[d] * t1_s[d] + center[d] * sc_s[VS_GMU] : 0.f;
-    }
-    if (tid < VS_COUNT) vp[MP + 2 * DP + tid] = tid < 3 ? sc_s[tid] : 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_slot, TMEM_COLS);
 }
 
-template <int NB>
-constexpr size_t tc_smem_bytes() { return (size_t)2 * Stage<NB>::FLOATS * 4; }
-
-int tc_grid(const WsLayout& L) {
+int tc2_grid(const WsLayout& L) {
   const long long nt = (L.N + TNP - 1) / TNP;
   const int sms = num_sms();
   return (int)(nt < sms ? (nt < 1 ? 1 : nt) : sms);
 }
 
+// cudaFuncSetAttribute is per device: set it on every launch (cheap) rather than caching per process
 template <class K>
 void set_smem(K kernel, size_t bytes) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+template <int BQ, int BWO, int NSTB>
+int launch_fwd(const Tc2Args& a, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)NSTB * BWO * 256 + (size_t)(3 * a.L.MP + 3 * a.L.DP) * sizeof(float);
+  set_smem(tc2_fwd_kernel<BQ, BWO, NSTB>, smem);
+  tc2_fwd_kernel<BQ, BWO, NSTB><<<grid, kCtaThreads, smem, st>>>(a);
+  return 0;
+}
+
+template <int BT, int DXW, int NSTA, int NSTB>
+int launch_bwd(const Tc2Args& a, int grid, cudaStream_t st) {
+  constexpr size_t brows = BT > DXW ? BT : DXW;
+  const size_t smem = (size_t)NSTB * brows * 256 +
+                      (size_t)(2 * a.L.MP + 3 * DXW + TNP * (DXW + 4) + 8 * 32 * 20) * sizeof(float);
+  set_smem(tc2_bwd_kernel<BT, DXW, NSTA, NSTB>, smem);
+  tc2_bwd_kernel<BT, DXW, NSTA, NSTB><<<grid, kCtaThreads, smem, st>>>(a);
+  return 0;
+}
+
 }  // namespace
 
 bool tc_point_supported(const WsLayout& L) {
-  if (tile_override("GPBLUR_TC") < 0) return false;       // GPBLUR_TC=-1 forces the FP32 FFMA kernels
+  if (tile_override("GPBLUR_TC") < 0) return false;       // GPBLUR_TC=-1 forces the FP32 FFMA kernels (tests)
   return (L.MP == 128 || (L.MP >= 256 && L.MP % 256 == 0)) && L.N >= 1;
 }
 
-int tc_vector_partials(const WsLayout& L) { return tc_grid(L); }
+int tc_vector_partials(const WsLayout& L) { return tc2_grid(L); }
 
 int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
                             uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
-  TcPointArgs a{};
+  Tc2Args a{};
   a.L = L; a.ws = ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
-  a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
-  a.exp_mode = tile_override("GPBLUR_TC_EXP");
-  {
-    const char* tp = getenv("GPBLUR_FWD_TRACE_PTR");
-    a.trace = tp ? reinterpret_cast<long long*>(strtoull(tp, nullptr, 0)) : nullptr;
-  }
-  const int grid = tc_grid(L);
+  a.trace = debug_trace_buffer();
+  const int grid = tc2_grid(L);
   ProfScope ps(ST_POINT_FWD, st);
-  if (L.MP == 128) {
-    static bool cfg = false;
-    if (!cfg) { set_smem(tc_point_fwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-    tc_point_fwd_kernel<128><<<grid, kTwoGroupThreads, tc_smem_bytes<128>(), st>>>(a);
-  } else {
-    static bool cfg = false;
-    if (!cfg) { set_smem(tc_point_fwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-    tc_point_fwd_kernel<256><<<grid, kTwoGroupThreads, tc_smem_bytes<256>(), st>>>(a);
-  }
+  if (L.MP == 128) launch_fwd<128, 128, 4>(a, grid, st);
+  else launch_fwd<128, 256, 3>(a, grid, st);
   note_launch();
   return check_launch("tc_point_fwd");
 }
@@ -1353,48 +1216,18 @@ int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* 
 int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const float* g_mean, const float* g_var,
                              const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
                              uint32_t stream_id, float* dx, cudaStream_t st) {
-  TcPointArgs a{};
+  Tc2Args a{};
   a.L = L; a.ws = ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
-  a.dbg = tile_override("GPBLUR_TC_DEBUG") > 0 ? ws_ptr<long long>(ws, L.stamps) : nullptr;
-  a.exp_mode = tile_override("GPBLUR_TC_EXP");
-  {
-    const char* tp = getenv("GPBLUR_TRACE_PTR");
-    a.trace = tp ? reinterpret_cast<long long*>(strtoull(tp, nullptr, 0)) : nullptr;
-  }
-  const int grid = tc_grid(L);
-  {
-    ProfScope ps(ST_POINT_BWD, st);
-    if (L.MP == 128) {
-      static bool cfg = false;
-      if (!cfg) { set_smem(tc_point_bwd_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-      tc_point_bwd_kernel<128><<<grid, kBwdThreads, tc_smem_bytes<128>(), st>>>(a);
-    } else {
-      static bool cfg = false;
-      if (!cfg) { set_smem(tc_point_bwd_kernel<256>, tc_smem_bytes<256>()); cfg = true; }
-      tc_point_bwd_kernel<256><<<grid, kBwdThreads, tc_smem_bytes<256>(), st>>>(a);
-    }
-    note_launch();
-    int rc = check_launch("tc_point_bwd");
-    if (rc) return rc;
-  }
-  ProfScope ps(ST_OTHER, st);
-  if (L.DP <= 32) {
-    static bool cfg = false;
-    if (!cfg) { set_smem(tc_dx_kernel<32>, tc_smem_bytes<32>()); cfg = true; }
-    tc_dx_kernel<32><<<grid, kBlockThreads, tc_smem_bytes<32>(), st>>>(a);
-  } else if (L.DP == 64) {
-    static bool cfg = false;
-    if (!cfg) { set_smem(tc_dx_kernel<64>, tc_smem_bytes<64>()); cfg = true; }
-    tc_dx_kernel<64><<<grid, kBlockThreads, tc_smem_bytes<64>(), st>>>(a);
-  } else {
-    static bool cfg = false;
-    if (!cfg) { set_smem(tc_dx_kernel<128>, tc_smem_bytes<128>()); cfg = true; }
-    tc_dx_kernel<128><<<grid, kBlockThreads, tc_smem_bytes<128>(), st>>>(a);
-  }
+  a.trace = debug_trace_buffer();
+  const int grid = tc2_grid(L);
+  ProfScope ps(ST_POINT_BWD, st);
+  if (L.DP <= 32) launch_bwd<128, 32, 3, 4>(a, grid, st);
+  else if (L.DP == 64) launch_bwd<128, 64, 3, 4>(a, grid, st);
+  else launch_bwd<128, 128, 2, 3>(a, grid, st);
   note_launch();
-  return check_launch("tc_dx");
+  return check_launch("tc_point_bwd");
 }
 
 }  // namespace gpblur

@@ -3,7 +3,9 @@
 //   W^T X : WX[m][d] = sum_n W[n][m] * X[n][d]
 // Both operands are "MN-major" in memory (the reduction index n is the slow one), so the producer threads gather
 // 4 consecutive n per 16-byte k-chunk, split every value into TF32 hi/lo planes and write the canonical K-major
-// no-swizzle UMMA tiles; one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = TQ, K = 8) into a TMEM
+// no-swizzle UMMA tiles.  A and W arrive TILE-major from the point kernels (tc_tiled_index: per 128-point tile
+// [MP / 4 column pieces][128 rows][4 floats]): the 4 lanes that own the 4 columns of a piece load the float4 of 4
+// consecutive rows (64 contiguous bytes) and transpose 4 x 4 among themselves with 4 shuffles; one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = TQ, K = 8) into a TMEM
 // accumulator, completion is tracked with tcgen05.commit -> mbarrier, and the epilogue reads TMEM with tcgen05.ld.
 // Split over N across CTAs (grid.y); partials are reduced in fixed order by the M x M backward stage.
 #include "gpblur_tc.cuh"
@@ -24,15 +26,34 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 struct TcReduceArgs {
-  const float* U;   // [N][ldu]   A-operand source (rows of the output = columns p of U)
-  const float* V;   // [N][ldv]   B-operand source (columns q)
+  const float* U;   // tile-major [N, MP]   A-operand source (rows of the output = columns p of U)
+  const float* V;   // B-operand source (columns q): tile-major [N, MP] (Gram) or row-major [N][ldv] (W^T X: V = x)
   const float* sc;  // [N] scale applied to V rows, or null
   const float* gm;  // [N] weights of the fused column sum u (Gram only), or null
   float* C;         // [splits][P][ldc]
   float* uvec;      // [splits][P]
   long long N;
   int ldu, ldv, vcols, P, ldc, rows_per_split;
+  int MP;           // padded inducing count (tile-major indexing)
 };
+
+// in-register 4 x 4 transpose among the 4 lanes l = 4 j + e of a quad: lane e holds row e = (m0, m1, m2, m3) and ends
+// up with column e = (row 0, row 1, row 2, row 3)[e]
+__device__ __forceinline__ float4 quad_transpose(float4 v, int lane) {
+  {
+    const bool odd = lane & 1;
+    const float s0 = odd ? v.x : v.y, s1 = odd ? v.z : v.w;
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (odd) { v.x = r0; v.z = r1; } else { v.y = r0; v.w = r1; }
+  }
+  {
+    const bool up = lane & 2;
+    const float s0 = up ? v.x : v.z, s1 = up ? v.y : v.w;
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (up) { v.x = r0; v.y = r1; } else { v.z = r0; v.w = r1; }
+  }
+  return v;
+}
 
 template <int TQ>
 struct TcSmem {
@@ -117,26 +138,31 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
       const long long n0 = r0 + (long long)s * KT;
   #pragma unroll
       for (int i = 0; i < 2; ++i) {
+        // rows n0 + 4 c .. + 3, column p0 + ar: this lane fetches row n0 + 4 c + (lane & 3) of its column piece
         const int c = acg + 4 * i;
-        float v[4];
-  #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const long long n = n0 + 4 * c + e;
-          v[e] = (n < r1) ? a.U[(size_t)n * a.ldu + p0 + ar] : 0.f;
-        }
-        rg.a[i] = make_float4(v[0], v[1], v[2], v[3]);
+        const long long n = n0 + 4 * c + (lane & 3);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < r1) v = *reinterpret_cast<const float4*>(a.U + tc_tiled_index(n, (p0 + ar) & ~3, a.MP));
+        rg.a[i] = quad_transpose(v, lane);
       }
       if (TQ >= kProd || tid < TQ * BG) {
   #pragma unroll
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
-          float v[4];
+          if (GRAM) {
+            const long long n = n0 + 4 * c + (lane & 3);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < r1 && q0 + bq < a.vcols) v = *reinterpret_cast<const float4*>(a.V + tc_tiled_index(n, (q0 + bq) & ~3, a.MP));
+            rg.b[i] = quad_transpose(v, lane);
+          } else {
+            float v[4];
   #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const long long n = n0 + 4 * c + e;
-            v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              const long long n = n0 + 4 * c + e;
+              v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
+            }
+            rg.b[i] = make_float4(v[0], v[1], v[2], v[3]);
           }
-          rg.b[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
       }
     };
@@ -277,7 +303,7 @@ int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream
   TcReduceArgs g{};
   g.U = ws_cptr<float>(ws, L.A); g.V = g.U; g.sc = gsc + L.N; g.gm = gsc;
   g.C = ws_ptr<float>(ws, L.Spart); g.uvec = ws_ptr<float>(ws, L.upart);
-  g.N = L.N; g.ldu = MP; g.ldv = MP; g.vcols = MP; g.P = MP; g.ldc = MP;
+  g.N = L.N; g.ldu = MP; g.ldv = MP; g.vcols = MP; g.P = MP; g.ldc = MP; g.MP = MP;
   g.rows_per_split = rows(L.splitsS);
   int rc = (MP == 128) ? launch_tc_reduce<128, true>(g, 1, L.splitsS, st)
                        : launch_tc_reduce<256, true>(g, MP / 128, L.splitsS, st, MP / 256);
@@ -285,7 +311,7 @@ int launch_tc_reductions(const WsLayout& L, void* ws, const float* x, cudaStream
   TcReduceArgs w{};
   w.U = ws_cptr<float>(ws, L.W); w.V = x; w.sc = nullptr; w.gm = nullptr;
   w.C = ws_ptr<float>(ws, L.WXpart); w.uvec = ws_ptr<float>(ws, L.cpart);   // + column sums of W
-  w.N = L.N; w.ldu = MP; w.ldv = L.D; w.vcols = L.D; w.P = MP; w.ldc = L.DP;
+  w.N = L.N; w.ldu = MP; w.ldv = L.D; w.vcols = L.D; w.P = MP; w.ldc = L.DP; w.MP = MP;
   w.rows_per_split = rows(L.splitsZ);
   const int pt = MP / 128;
   switch (L.DP) {

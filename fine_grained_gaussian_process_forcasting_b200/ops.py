@@ -202,7 +202,7 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
     Mp = 32 if M <= 32 else 64 if M <= 64 else 128 if M <= 128 else (M + 255) // 256 * 256
     if which == 4:
         out = torch.empty(32, device=ws.device, dtype=torch.int64)
-    elif which == 3:
+    elif which in (3, 5):
         Nt = (N + 127) // 128 * 128 if Mp >= 128 else N     # tensor-core path: whole 128-point tiles, tile-major
         out = torch.empty(Nt, Mp, device=ws.device, dtype=torch.float32)
     else:
@@ -212,7 +212,7 @@ def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
                                             C.byref(mp), _stream())
     _cabi.check(rc, "gpblur_debug_fetch")
     assert mp.value == Mp
-    if which == 3 and Mp >= 128:
+    if which in (3, 5) and Mp >= 128:
         # [tile][Mp / 4 pieces][128 rows][4] -> [N, Mp]   (csrc/gpblur_common.cuh: tc_tiled_index)
         out = out.reshape(-1, Mp // 4, 128, 4).permute(0, 2, 1, 3).reshape(-1, Mp)[:N].contiguous()
     return out

@@ -42,7 +42,6 @@ def check_fwd(B, L, D, M):
     A_o = torch.linalg.solve_triangular(torch.linalg.cholesky(Kzz), Kzx, upper=False).t()
     stage, kl, info = stage_of(pd, D)
     xd = x32.to(dev).reshape(-1, D)
-    os.environ["GPBLUR_TC_V"] = "2"
     mean, var, sample, ws = ops.point_forward_raw(stage, xd, M, 1234, 5, 0, True, True)
     torch.cuda.synchronize()
     A = ops.debug_fetch(3, B * L, D, M, ws)[:, :M]
@@ -58,8 +57,7 @@ def time_fwd(B, L, D, M, iters=20):
     ws = torch.empty(ops.workspace_bytes(N, D, M, True), device=dev, dtype=torch.uint8)
     outb = torch.empty(3 * N, device=dev)
     res = {}
-    for v in ("2", "1"):
-        os.environ["GPBLUR_TC_V"] = v
+    for v in ("2",):
         for _ in range(3):
             ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True, out=outb, ws=ws)
         torch.cuda.synchronize()
@@ -71,7 +69,58 @@ def time_fwd(B, L, D, M, iters=20):
         torch.cuda.synchronize()
         res[v] = e0.elapsed_time(e1) / iters
     # includes the per-call D2D copy of the parameter stage
-    print(f"time fwd B={B} L={L} D={D} M={M}: new {res['2']*1e3:.1f} us  old {res['1']*1e3:.1f} us", flush=True)
+    print(f"time fwd B={B} L={L} D={D} M={M}: {res['2']*1e3:.1f} us", flush=True)
+
+
+def check_bwd(B, L, D, M):
+    p32 = O.init_params_exercise(D, M, seed=21)
+    x32, y32, gm32, gv32 = O.make_inputs(B, L, D, seed=22)
+    gs32 = torch.randn(B, L, generator=torch.Generator().manual_seed(23))
+    gkl = 0.37
+    seed, offset, stream = 99, 1000, 2
+    p64 = O.clone_params(p32, torch.float64, requires_grad=True)
+    x64 = x32.double().requires_grad_(True)
+    mo, vo = O.svgp_predict_closed_form(p64, x64)
+    eps = torch.from_numpy(O.philox_normal(seed, offset, B * L, stream)).double().reshape(B, L)
+    so = O.rsample(mo, vo, eps)
+    loss = (gm32.double() * mo).sum() + (gv32.double() * vo).sum() + (gs32.double() * so).sum() + gkl * O.kl_meanfield(p64)
+    loss.backward()
+    pd = {k: v.to(dev).requires_grad_(True) for k, v in p32.items()}
+    xd = x32.to(dev).requires_grad_(True)
+    mean, var, sample, kl, info = ops.svgp_predict(xd, pd["inducing_points"], pd["raw_lengthscale"], pd["raw_outputscale"],
+                                                   pd["variational_mean"], pd["variational_stddev"], pd["weights"], pd["bias"],
+                                                   seed=seed, offset=offset, stream_id=stream, want_sample=True)
+    lc = (gm32.to(dev) * mean).sum() + (gv32.to(dev) * var).sum() + (gs32.to(dev) * sample).sum() + gkl * kl
+    lc.backward()
+    torch.cuda.synchronize()
+    errs = {"dx": rel(xd.grad, x64.grad)}
+    for k in ["inducing_points", "raw_lengthscale", "raw_outputscale", "variational_mean", "variational_stddev", "weights", "bias"]:
+        errs[k[:8]] = rel(pd[k].grad, p64[k].grad)
+    print(f"bwd B={B} L={L} D={D} M={M}: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()), flush=True)
+
+
+def time_bwd(B, L, D, M, iters=10):
+    from fine_grained_gaussian_process_forcasting_b200 import _cabi
+    p32, pd = params(D, M)
+    pdg = {k: v.clone().requires_grad_(True) for k, v in pd.items()}
+    x = torch.randn(B, L, D, device=dev, requires_grad=True)
+    gm = torch.randn(B, L, device=dev)
+
+    def step():
+        mean, var, sample, kl, info = ops.svgp_predict(x, pdg["inducing_points"], pdg["raw_lengthscale"], pdg["raw_outputscale"],
+                                                       pdg["variational_mean"], pdg["variational_stddev"], pdg["weights"],
+                                                       pdg["bias"], seed=1, offset=0, stream_id=0, want_sample=True)
+        torch.autograd.backward([mean, sample], [gm, gm])
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    _cabi.profile_enable(True)
+    for _ in range(iters):
+        step()
+    torch.cuda.synchronize()
+    prof = _cabi.profile_collect()
+    _cabi.profile_enable(False)
+    print(f"stages B={B} L={L} D={D} M={M}: " + " ".join(f"{k}={ms / max(cnt, 1) * 1e3:.1f}us" for k, (ms, cnt) in prof.items() if cnt), flush=True)
 
 
 if __name__ == "__main__":
@@ -82,3 +131,46 @@ if __name__ == "__main__":
             check_fwd(*shp)
         for shp in [(8192, 24, 64, 256), (256, 192, 64, 256), (8192, 24, 64, 128), (8192, 24, 64, 512), (8192, 24, 64, 1024)]:
             time_fwd(*shp)
+    if what == "wdbg":
+        B, L, D, M = (int(v) for v in sys.argv[2:6])
+        p32 = O.init_params_exercise(D, M, seed=21)
+        x32, y32, gm32, gv32 = O.make_inputs(B, L, D, seed=22)
+        pd = {k: v.to(dev) for k, v in p32.items()}
+        N = B * L
+        xd = x32.to(dev).reshape(N, D)
+        args = (pd["inducing_points"], pd["raw_lengthscale"].reshape(-1), pd["raw_outputscale"].reshape(1),
+                pd["variational_mean"], pd["variational_stddev"], pd["weights"].reshape(-1), pd["bias"])
+        mean, var, sample, kl, info, ws = ops.svgp_forward_raw(xd, *args, 1, 0, 0, True, True)
+        gm = gm32.to(dev).reshape(N).contiguous(); gv = gv32.to(dev).reshape(N).contiguous()
+        gkl = torch.zeros(1, device=dev)
+        dx, bucket = ops.svgp_backward_raw(xd, *args, gm, gv, None, gkl, var, 1, 0, 0, ws)
+        torch.cuda.synchronize()
+        W = ops.debug_fetch(5, N, D, M, ws)[:, :M].double().cpu()
+        p64 = O.clone_params(p32, torch.float64)
+        ell = O.softplus(p64["raw_lengthscale"]).reshape(D); os_ = O.softplus(p64["raw_outputscale"])
+        Z = p64["inducing_points"]
+        Kzz = O.rbf_scale_direct(Z, Z, ell, os_) + O.JITTER * torch.eye(M, dtype=torch.float64)
+        K = O.rbf_scale_direct(x32.double().reshape(N, D), Z, ell, os_)          # [N, M]
+        Lc = torch.linalg.cholesky(Kzz)
+        Linv = torch.linalg.solve_triangular(Lc, torch.eye(M, dtype=torch.float64), upper=False)
+        Aa = K @ Linv.t()
+        cvec = p64["variational_stddev"] ** 2 - 1
+        beta = Linv.t() @ p64["variational_mean"]
+        vo = O.svgp_predict_closed_form(p64, x32.double())[1].reshape(N)
+        gvv = gv32.double().reshape(N).clone(); gvv[vo <= 1e-6] = 0
+        kbar = gm32.double().reshape(N, 1) * beta.reshape(1, M) + 2 * gvv.reshape(N, 1) * ((Aa * cvec) @ Linv)
+        Wo = kbar * K
+        err = (W - Wo).abs()
+        print("W rel err", (err.max() / Wo.abs().max()).item())
+        for c in range(M // 32):
+            blk = err[:, c * 32:(c + 1) * 32]
+            print(f"  chunk {c}: max err {blk.max().item():.3e} (ref max {Wo[:, c*32:(c+1)*32].abs().max().item():.3e})  "
+                  f"rows with err>1e-4: {(blk.max(dim=1).values > 1e-4).sum().item()} / {N}")
+        sys.exit(0)
+    if what in ("bwd", "all"):
+        for shp in [(16, 24, 64, 128), (16, 24, 32, 128), (8, 24, 64, 256), (8, 192, 32, 256), (8, 24, 16, 256), (4, 24, 64, 512),
+                    (2, 24, 64, 1024), (5, 13, 48, 100), (3, 24, 32, 300), (8, 24, 10, 256), (40, 24, 20, 128), (1100, 1, 128, 256),
+                    (700, 24, 64, 256)]:
+            check_bwd(*shp)
+        for shp in [(8192, 24, 64, 256), (256, 192, 64, 256), (8192, 24, 64, 128), (8192, 24, 64, 1024)]:
+            time_bwd(*shp)
