@@ -18,16 +18,29 @@ for _ in range(2):
     ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True)
 torch.cuda.synchronize()
 buf = torch.zeros(4096, dtype=torch.int64, device=dev)
-_cabi.lib().gpblur_debug_set_trace(C.c_void_p(buf.data_ptr()))
-ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True)
-torch.cuda.synchronize()
-_cabi.lib().gpblur_debug_set_trace(None)
+MODE = sys.argv[3] if len(sys.argv) > 3 else "fwd"
+if MODE == "fwd":
+    _cabi.lib().gpblur_debug_set_trace(C.c_void_p(buf.data_ptr()))
+    ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True)
+    torch.cuda.synchronize()
+    _cabi.lib().gpblur_debug_set_trace(None)
+else:
+    N = B * L
+    mean, var, sample, ws = ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True)
+    gm = torch.randn(N, device=dev); gv = torch.randn(N, device=dev)
+    for _ in range(2):
+        ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws)
+    torch.cuda.synchronize()
+    _cabi.lib().gpblur_debug_set_trace(C.c_void_p(buf.data_ptr()))
+    ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws)
+    torch.cuda.synchronize()
+    _cabi.lib().gpblur_debug_set_trace(None)
 t = buf.cpu()
 iss = t[:768].reshape(96, 8)
 prod = t[1024:1024 + 768].reshape(96, 8)
 t0 = int(iss[0, 0])
 print("issuer: slab rows | wait_a_start a_ready b_full issued requested | d(issue) d(total)  [cycles rel. to slab 0 start]")
-for g in range(40):
+for g in range(64):
     r = iss[g]
     if r[0] == 0: break
     print(f"  {g:3d} N={int(r[5]):3d} | start {int(r[0])-t0:7d} ready {int(r[2])-t0:7d} issued {int(r[3])-t0:7d} | "
