@@ -48,6 +48,8 @@ WORKLOADS = {
 for _m in (64, 128, 256, 512, 1024):
     WORKLOADS[f"c5_m{_m}"] = dict(B=8192, calls=[24], D=64, M=_m,
                                   desc=f"configs[4]: inducing sweep point B=8192 L=24 D=64 M={_m}")
+WORKLOADS["c3"]["strong"] = True     # configs[2]: B = 1024 GLOBAL, batch-sharded (128 windows per GPU on 8)
+EXTRA_WORKLOADS = ["c1", "c3", "c5_m256", "c5_m1024"]
 WORKLOADS["c4"] = dict(B=2048, calls=[24], D=64, M=256, H=10,
                        desc="configs[3]: two-layer DeepGP blur B=2048 L=24 D=64 M=256, hidden width H=10 "
                             "(H independent GPs D->H, reparameterised sample, one GP H->1)")
@@ -202,44 +204,92 @@ def cpu_reference_step_fn_two_layer(wl, B_cpu, seed=1234):
     return step
 
 
-def time_cpu_reference(wl, steps, warmup, budget_s=25.0):
+def gpytorch_step_fn(wl, B_cpu, seed=1234):
+    """The reference's OWN classes on real gpytorch - only when gpytorch can be imported (it is
+    not in this image's wheelhouse) and the reference tree is reachable (baseline/_ref or /root/reference)."""
+    for extra in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(extra) and extra not in sys.path:
+            sys.path.append(extra)
+    import gpytorch                                    # noqa: F401  (ImportError -> caller falls back to the port)
+    from denoising_model.DeepGP import DeepGPp         # the reference's unmodified module
+    if "H" in wl:
+        raise ImportError("the reference defines no two-layer model")
+    D, M = wl["D"], wl["M"]
+    from oracle import gp_oracle as O
+    model = DeepGPp(D, seed)
+    if M != 256:
+        from denoising_model.DeepGP import ToyDeepGPHiddenLayer
+        model.hidden_layer = ToyDeepGPHiddenLayer(input_dims=D, output_dims=None, seed=seed, num_inducing=M,
+                                                  mean_type="linear")
+    calls = [O.make_inputs(B_cpu, L, D, seed + 1 + i) for i, L in enumerate(wl["calls"])]
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = 0.0
+        with gpytorch.settings.num_likelihood_samples(1):
+            for i, (x, y, gm, gv) in enumerate(calls):
+                x = x.detach().requires_grad_(True)
+                mean, dist = model.predict(x)
+                loss = loss + (gm * mean[0]).sum()
+                if i == len(calls) - 1:
+                    mll = gpytorch.mlls.DeepApproximateMLL(gpytorch.mlls.VariationalELBO(model.likelihood, model, D))
+                    loss = loss - mll(dist, y.unsqueeze(0)).mean()
+        loss.backward()
+        return float(loss.detach())
+    return step, f"gpytorch {gpytorch.__version__}"
+
+
+def time_cpu_reference(wl, steps, warmup, budget_s=100.0):
+    """Times the reference's CPU implementation of the path on all host cores: `warmup` + `steps` steps on a bounded
+    sample B_cpu <= B of the workload, sized from one calibration step so that the whole run fits `budget_s`."""
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    # bounded sample: pick B_cpu so that one step costs a few seconds at most
-    N_per_window = sum(wl["calls"])
-    M = wl["M"]
-    cost = N_per_window * (M + max(wl["calls"])) ** 2 / 1e9 + M ** 3 / 1e9 * 4   # rough Gflop-ish per window
-    cost *= wl.get("H", 0) + 1
-    B_cpu = int(max(2, min(wl["B"], 6.0 / max(cost, 1e-3))))
-    B_cpu = int(os.environ.get("GPBLUR_CPU_SAMPLE_B", B_cpu))
-    step = cpu_reference_step_fn(wl, B_cpu)
-    for _ in range(max(1, warmup)):
+    kind, impl = "port", (f"oracle reference-order restatement of the gpytorch path (fp32 kernels, fp64 batched "
+                          f"Cholesky/solve, autograd backward), torch {torch.__version__} CPU")
+    make = cpu_reference_step_fn
+    try:
+        gpytorch_step_fn(wl, 2)
+        make = lambda w, b: gpytorch_step_fn(w, b)[0]      # noqa: E731
+        kind, impl = "reference", gpytorch_step_fn(wl, 2)[1] + " (the reference's own DeepGPp) on CPU"
+    except Exception as e:                                  # gpytorch / linear_operator are not installable here
+        impl += f"; gpytorch unavailable ({type(e).__name__})"
+    B = wl["B"]
+    B_cpu = os.environ.get("GPBLUR_CPU_SAMPLE_B")
+    if B_cpu is None:
+        # calibration: one step on a small sample, then the largest B_cpu <= B whose (warmup + steps) steps fit
+        b0 = max(2, min(B, 4))
+        cal = make(wl, b0)
+        cal()
+        t0 = time.perf_counter()
+        cal()
+        per_window = (time.perf_counter() - t0) / b0
+        B_cpu = int(max(2, min(B, budget_s / max(per_window * (steps + warmup), 1e-9))))
+    B_cpu = int(B_cpu)
+    step = make(wl, B_cpu)
+    for _ in range(max(0, warmup)):
         step()
     t0 = time.perf_counter()
-    done = 0
     for _ in range(steps):
         step()
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = (time.perf_counter() - t0) / done
-    return dict(value=B_cpu / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{done} steps of B={B_cpu} windows (of the workload's B={wl['B']}), calls L={wl['calls']}, "
-                       f"oracle reference-order restatement of the gpytorch path (fp32 kernels, fp64 batched "
-                       f"Cholesky/solve, autograd backward), torch {torch.__version__} CPU"), dt
+    dt = (time.perf_counter() - t0) / steps
+    full = B_cpu == B
+    return dict(value=B_cpu / dt, unit=UNIT, cores=cores, kind=kind, nproc=os.cpu_count(),
+                sample=f"{steps} steps (+{warmup} warm-up) of B={B_cpu} windows "
+                       f"({'the full workload' if full else 'a bounded sample of the workload, B=' + str(B)}), "
+                       f"calls L={wl['calls']}, {impl}"), dt, B_cpu
 
 
 def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    cb, dt = time_cpu_reference(wl, steps, min(args.warmup, 1))
+    cb, dt, B_cpu = time_cpu_reference(wl, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "desc": wl["desc"], "B": wl["B"], "L": wl["calls"], "D": wl["D"], "M": wl["M"]},
+        "config": {"workload": name, "desc": wl["desc"], "B_per_gpu": wl["B"], "B_cpu_sample": B_cpu, "L": wl["calls"],
+                   "D": wl["D"], "M": wl["M"], "regime": "R-exercise (SURVEY 8d)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -286,9 +336,9 @@ def make_model(wl, device, seed=1234):
 
 
 def run_ours(args, wl, name):
+    """The driver's line: the default workload in full, plus (unless --single) a `workloads` dict with the other
+    BASELINE.json configurations measured the same way in the same process (c3 strong-scaled: B = 1024 global)."""
     from fine_grained_gaussian_process_forcasting_b200 import _cabi
-    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,6 +352,32 @@ def run_ours(args, wl, name):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     _cabi.lib()
+    ctx = dict(world=world, rank=rank, local_rank=local_rank, device=device, dist=dist)
+    line = measure(args, wl, name, ctx, primary=True)
+    if not args.single:
+        extra = {}
+        for other in EXTRA_WORKLOADS:
+            if other == name:
+                continue
+            wlo = dict(WORKLOADS[other])
+            if wlo.get("strong"):                         # fixed GLOBAL batch: B / world windows per GPU
+                wlo["B"] = max(1, wlo["B"] // world)
+            sub = measure(args, wlo, other, ctx, primary=False)
+            if rank == 0:
+                extra[other] = sub
+        if rank == 0:
+            line["workloads"] = extra
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure(args, wl, name, ctx, primary=True):
+    from fine_grained_gaussian_process_forcasting_b200 import _cabi
+    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
+    world, rank, local_rank, device, dist = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["device"], ctx["dist"]
 
     B, D, M, calls = wl["B"], wl["D"], wl["M"], wl["calls"]
     model = make_model(wl, device)
@@ -352,16 +428,17 @@ def run_ours(args, wl, name):
         torch.autograd.backward(outs, grads)
         if call_streams is not None:
             call_streams.join()
+        if world > 1 and allreduce_in_step[0]:
+            bucket.all_reduce(average=True)               # NCCL AVG on the flat bucket: part of the captured step
         return elbo
+
+    allreduce_in_step = [True]
 
     def eager_step(i, xin, yin):
         for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
             ly.invalidate_param_stage()
             ly._rng_offset = (i * world + rank) * B * sum(calls) * max(1, ly.output_dims or 1)   # global window index
-        elbo = step_body(xin, yin)
-        if world > 1:
-            bucket.all_reduce(average=True)
-        return elbo
+        return step_body(xin, yin)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -381,15 +458,23 @@ def run_ours(args, wl, name):
     graphed = None
     graph_note = "eager launches (--eager)"
     if not args.eager:
-        try:
-            graphed = GraphedStep(model, lambda *ins: (step_body(ins[:-1], ins[-1]),), list(xs[0]) + [ys[0]],
-                                  warmup=2, world=world, rank=rank)
-            graph_note = "whole step (fwd + bwd) replayed as one CUDA graph; NCCL all-reduce outside the graph"
-        except Exception as e:    # pragma: no cover - report and fall back to eager launches
-            graph_note = f"CUDA graph capture failed ({type(e).__name__}: {e}); eager launches"
-            graphed = None
-            for ly in layers:
-                ly.rng_offset_dev = None
+        for attempt in (0, 1):
+            try:
+                graphed = GraphedStep(model, lambda *ins: (step_body(ins[:-1], ins[-1]),), list(xs[0]) + [ys[0]],
+                                      warmup=2, world=world, rank=rank)
+                graph_note = "whole step (fwd + bwd" + (" + NCCL all-reduce of the gradient bucket" if world > 1 and
+                             allreduce_in_step[0] else "") + ") replayed as one CUDA graph" + \
+                             ("; NCCL all-reduce issued after the replay" if world > 1 and not allreduce_in_step[0] else "")
+                break
+            except Exception as e:    # pragma: no cover - report and fall back
+                graphed = None
+                for ly in layers:
+                    ly.rng_offset_dev = None
+                if world > 1 and allreduce_in_step[0] and attempt == 0:
+                    allreduce_in_step[0] = False         # retry with the collective outside the graph
+                    continue
+                graph_note = f"CUDA graph capture failed ({type(e).__name__}: {e}); eager launches"
+                break
     sync_all()
 
     def run_step(i, xin, yin):
@@ -400,7 +485,7 @@ def run_ours(args, wl, name):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         (elbo,) = graphed.replay()
-        if world > 1:
+        if world > 1 and not allreduce_in_step[0]:
             bucket.all_reduce(average=True)
         return elbo
 
@@ -423,7 +508,7 @@ def run_ours(args, wl, name):
         evs[i][0].record()
         if graphed is not None:
             graphed.replay()
-            if world > 1:
+            if world > 1 and not allreduce_in_step[0]:
                 bucket.all_reduce(average=True)
         else:
             eager_step(i, xs[i % nbuf], ys[i % nbuf])
@@ -526,6 +611,55 @@ def run_ours(args, wl, name):
         stage_ms = {k: (ms / nprof, cnt / nprof) for k, (ms, cnt) in prof.items() if cnt}
     sync_all()
 
+    # ---- --check (N > 1): the all-reduced gradient bucket against ONE rank's run on the concatenated batch ----
+    allreduce_check = None
+    if args.check and world > 1:
+        zs = [torch.zeros_like(g_) for g_ in gss]          # no sample gradient: the counters of a window depend on its rank
+        saved = list(gss)
+        gss[:] = zs
+        eager_step(0, xs[0], ys[0])                         # sharded: bucket = mean over ranks (all-reduce in the step)
+        if not allreduce_in_step[0]:
+            bucket.all_reduce(average=True)
+        sharded = bucket.flat.clone()
+        gx = [[torch.empty_like(x) for _ in range(world)] for x in xs[0]]
+        for c in range(len(calls)):
+            dist.all_gather(gx[c], xs[0][c])
+        gy = [torch.empty_like(ys[0]) for _ in range(world)]
+        dist.all_gather(gy, ys[0])
+        ggm = [[torch.empty_like(g_) for _ in range(world)] for g_ in gms]
+        for c in range(len(calls)):
+            dist.all_gather(ggm[c], gms[c])
+        if rank == 0:
+            keep = (list(gms), g_elbo)
+            xin = [torch.cat(gx[c], 0) for c in range(len(calls))]
+            yin = torch.cat(gy, 1)
+            gms[:] = [torch.cat(ggm[c], 1) / world for c in range(len(calls))]
+            gss[:] = [torch.zeros_like(g_) for g_ in gms]
+            g_elbo_full = torch.full((1, B * world), -1.0 / (B * world), device=device)
+            was = allreduce_in_step[0]
+            allreduce_in_step[0] = False
+            for ly in layers:
+                ly.invalidate_param_stage()
+            bucket.zero()
+            outs, grads = [], []
+            for c, L_ in enumerate(calls):
+                x = xin[c].detach().requires_grad_(True)
+                last = c == len(calls) - 1
+                out = model.blur(x, yin if last else None, num_data=D)
+                outs += [out.mean, out.sample]
+                grads += [gms[c], gss[c]]
+                if last:
+                    outs.append(out.elbo)
+                    grads.append(g_elbo_full)
+            bucket.zero()
+            torch.autograd.backward(outs, grads)
+            full = bucket.flat.clone()
+            allreduce_in_step[0] = was
+            gms[:] = keep[0]
+            allreduce_check = float(((sharded - full).abs().max() / full.abs().max().clamp_min(1e-30)).item())
+        gss[:] = saved
+        sync_all()
+
     if rank == 0:
         peaks = load_peaks()
         N_total = B * sum(calls)
@@ -581,12 +715,13 @@ def run_ours(args, wl, name):
               roof["hbm_frac_whole_step"] = (B * sum(bytes_per_window(L, D) for L in calls) / (ms_per_step * 1e-3) / 1e9
                                              / peaks["hbm_gbs"])
           roofs[which] = roof
-        cb = None if args.no_cpu_baseline else time_cpu_reference(wl, 3, 1)[0]
+        cb = None if (args.no_cpu_baseline or not primary) else time_cpu_reference(wl, 3, 1, budget_s=20.0)[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if wl.get("strong") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "desc": wl["desc"], "B_per_gpu": B, "L": calls, "D": D, "M": M,
+            "config": {"workload": name, "desc": wl["desc"], "B_per_gpu": B, "B_global": B * world, "L": calls, "D": D, "M": M,
                        "parallelism": f"dp{world}", "l2": f"flush ({L2_FLUSH_BYTES >> 20} MiB write) between timed steps "
                        "+ 3 rotating input sets", "timing": "per-step CUDA events, max over ranks",
                        "launch": graph_note,
@@ -604,10 +739,13 @@ def run_ours(args, wl, name):
             "wall_ms_per_step": t_wall * 1e3 / args.steps,
             "eager_ms_per_step": eager_ms,
         }
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        if allreduce_check is not None:
+            line["allreduce_check"] = allreduce_check
+            line["allreduce_check_note"] = ("max |mean over ranks of the per-rank gradient buckets - bucket of ONE rank on "
+                                            "the concatenated batch| / max |.| (sample gradients off: the Philox "
+                                            "counters of a window depend on its rank's offset)")
+        return line
+    return None
 
 
 def main():
@@ -622,6 +760,9 @@ def main():
                     help="issue the GP calls of a step on one stream (default: one extra stream per additional call)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "
                     "step as a CUDA graph")
+    ap.add_argument("--single", action="store_true", help="measure only --workload (no `workloads` dict)")
+    ap.add_argument("--check", action="store_true", help="N > 1: verify the all-reduced gradient bucket against a "
+                    "single-rank run on the concatenated batch (adds `allreduce_check` to the line)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

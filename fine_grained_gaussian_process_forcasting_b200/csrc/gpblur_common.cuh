@@ -326,7 +326,7 @@ int tile_override(const char* env);   // 0 = heuristic, else forced tile height 
 
 // launchers implemented in the other translation units
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
-                      cudaStream_t st);
+                      cudaStream_t st, double extra_jitter = 0.0);
 // stage: the parameter stage of the forward (its fp64 scratch regions are overwritten); sgrad: summed stage gradient
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st);

@@ -220,6 +220,7 @@ struct MmFwdArgs {
   void* ws;
   float* kl;
   int* info;
+  double extra_jitter;   // added to the diagonal of Kzz on top of the variational jitter (psd_safe_cholesky retries)
 };
 
 __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       const double os = softplus64((double)a.p.raw_outputscale[0]);
       hyp[H_OS] = (float)os;
       hyp[H_JIT] = kJitter;
+      hyp64[H_JIT] = (double)kJitter + a.extra_jitter;      // diagonal actually added to Kzz (the backward removes it)
       hyp[H_KL] = (float)(0.5 * t);
       hyp64[H_OS] = os;
       hyp64[H_KL] = 0.5 * t;
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       for (int i = 0; i < 4; ++i) {
         const int gi = bi * TB + ty + 8 * i, gj = bj * TB + tx;
         double kv;
-        if (gi < M && gj < M) kv = os * exp(-0.5 * acc[i]) + (gi == gj ? (double)kJitter : 0.0);
+        if (gi < M && gj < M) kv = os * exp(-0.5 * acc[i]) + (gi == gj ? (double)kJitter + a.extra_jitter : 0.0);
         else kv = (gi == gj) ? 1.0 : 0.0;
         K64[(size_t)gi * MP + gj] = kv;
         K64[(size_t)gj * MP + gi] = kv;
@@ -890,12 +892,13 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
 
   GPBLUR_STAMP();
   // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
+  const double zz_jitter = ws_cptr<double>(a.ws, L.hyp64)[H_JIT];
   for (int idx = gtid; idx < MP * MP; idx += gsize) {
     const int i = idx / MP, j = idx - i * MP;
     double v = 0.0;
     if (i < M && j < M) {
       const double kb = 0.5 * (T64[idx] + T64[(size_t)j * MP + i]);
-      const double kz = K64[idx] - (i == j ? (double)kJitter : 0.0);
+      const double kz = K64[idx] - (i == j ? zz_jitter : 0.0);
       v = kb * kz;
     }
     U64[idx] = v;
@@ -1031,20 +1034,17 @@ int coop_grid(const void* func, int want, size_t smem) {
 }  // namespace
 
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
-                      cudaStream_t st) {
-  static bool attr_set = false;
+                      cudaStream_t st, double extra_jitter) {
   const size_t smem = sizeof(Tile) * 11 + kGemmScratchDoubles * sizeof(double);
-  if (!attr_set) {
-    cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  // per-DEVICE attribute: set on every launch (cheap) instead of a process-wide flag
+  cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nb = L.MP / TB;
   int want = nb * nb;
   const int dwant = (L.MP * L.DP + kThreads * 4 - 1) / (kThreads * 4);
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
-  MmFwdArgs args{p, L, ws, kl, info};
+  MmFwdArgs args{p, L, ws, kl, info, extra_jitter};
   void* kargs[] = {&args};
   ProfScope ps(ST_MM_FWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_forward_kernel, dim3(grid), dim3(kThreads),
@@ -1056,12 +1056,8 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st) {
-  static bool attr_set = false;
   const size_t smem = kGemmScratchDoubles * sizeof(double);
-  if (!attr_set) {
-    cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   const int nb = L.MP / TB;
   int want = nb * nb;
   const int dwant = (L.MP * L.DP + kThreads - 1) / kThreads;

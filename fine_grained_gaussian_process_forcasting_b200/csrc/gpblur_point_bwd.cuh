@@ -366,11 +366,7 @@ template <class Cfg, int DP>
 int launch_bwd_cfg(const PointBwdArgs& a0, cudaStream_t st) {
   PointBwdArgs a = a0;
   const size_t smem = sizeof(float) * BwdSmem<Cfg, DP>::floats(a.L.MP);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(point_bwd_kernel<Cfg, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  cudaFuncSetAttribute(point_bwd_kernel<Cfg, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   a.ntiles = (int)((a.L.N + Cfg::TN - 1) / Cfg::TN);
   const int grid = bwd_persistent_grid(a.L, Cfg::TN);
   ProfScope ps(ST_POINT_BWD, st);

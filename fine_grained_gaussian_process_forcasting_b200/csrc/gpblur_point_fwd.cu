@@ -165,11 +165,7 @@ template <class Cfg>
 int launch_fwd_cfg(const PointFwdArgs& a0, cudaStream_t st) {
   PointFwdArgs a = a0;
   const size_t smem = fwd_smem_bytes<Cfg>(a.L);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(point_fwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  cudaFuncSetAttribute(point_fwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   a.ntiles = (int)((a.L.N + Cfg::TN - 1) / Cfg::TN);
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, point_fwd_kernel<Cfg>, kThreads, smem);

@@ -277,12 +277,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
 
 template <int TQ, bool GRAM>
 int launch_tc_reduce(const TcReduceArgs& a, int ptiles, int splits, cudaStream_t st, int qtiles = 1) {
-  static bool configured = false;
   const size_t smem = TcSmem<TQ>::bytes;
-  if (!configured) {
-    cudaFuncSetAttribute(tc_reduce_kernel<TQ, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  // the attribute is per DEVICE: set on every launch (cheap) instead of a process-wide flag
+  cudaFuncSetAttribute(tc_reduce_kernel<TQ, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfScope ps(GRAM ? ST_GRAM : ST_WX, st);
   tc_reduce_kernel<TQ, GRAM><<<dim3(ptiles, splits, qtiles), kBlockThreads, smem, st>>>(a);
   note_launch();

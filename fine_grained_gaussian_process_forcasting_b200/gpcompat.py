@@ -65,10 +65,11 @@ class num_likelihood_samples(_ValueContext):
 
 
 class check_cholesky(_ValueContext):
-    """If True, every forward synchronises on the Cholesky ``info`` flag and raises NotPSDError when Kzz
-    is not positive definite (gpytorch's psd_safe_cholesky also syncs on ``info``).  If False the flag is
-    only kept on the layer (``last_info``) and NaNs propagate."""
-    _global_value = False
+    """If True (default, gpytorch's behaviour), building the M x M stage synchronises on the Cholesky ``info`` flag
+    and follows psd_safe_cholesky: retry with 1e-6, 1e-5, 1e-4 extra diagonal jitter (NumericalWarning), then raise
+    NotPSDError.  If False - and always while a CUDA graph is being captured - the flag is only kept on the layer
+    (``last_info``; ``graphs.GraphedStep.check_info()`` reads it after a replay) and NaNs would propagate."""
+    _global_value = True
 
 
 class variational_cholesky_jitter:
@@ -83,12 +84,8 @@ class min_variance:
         return 1e-6
 
 
-class NotPSDError(RuntimeError):
-    pass
-
-
-class NumericalWarning(RuntimeWarning):
-    pass
+NotPSDError = ops.NotPSDError
+NumericalWarning = ops.NumericalWarning
 
 
 # ------------------------------------------------------------------------------------------------
@@ -517,7 +514,8 @@ class DeepGPLayer(ApproximateGP):
         return self._stage_caches.setdefault(None, {}) if self.share_param_stage else None
 
     def _kl_only(self):
-        _, kl, _, _ = ops.svgp_param_stage(*self._layer_params(), stage_cache=self._stage_cache())
+        _, kl, _, _ = ops.svgp_param_stage(*self._layer_params(), stage_cache=self._stage_cache(),
+                                           check=bool(check_cholesky.value()))
         return kl.sum() if kl.dim() else kl
 
     def __call__(self, inputs, are_samples=False, **kwargs):
@@ -541,13 +539,9 @@ class DeepGPLayer(ApproximateGP):
         mean, var, sample, kl, info = ops.svgp_predict(inputs, *self._layer_params(), seed, off, stream,
                                                        want_sample=self.fused_sample,
                                                        stage_cache=self._stage_cache(),
-                                                       offset_dev=self.rng_offset_dev, h_stride=self._rng_h_stride)
+                                                       offset_dev=self.rng_offset_dev, h_stride=self._rng_h_stride,
+                                                       check=bool(check_cholesky.value()))
         self.last_info = info
-        if check_cholesky.value():
-            k = int(info.max().item())
-            if k != 0:
-                raise NotPSDError(f"Kzz + jitter is not positive definite (pivot {k}); gpytorch would retry "
-                                  f"with more jitter")
         if H is None:
             cls = MultivariateNormal
         else:

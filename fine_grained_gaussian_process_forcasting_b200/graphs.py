@@ -80,6 +80,15 @@ class GraphedStep:
         self.graph.replay()
         return self.outputs
 
+    def check_info(self):
+        """Cholesky status of the last replay (the capture cannot synchronise on it): raises NotPSDError if any layer's
+        Kzz + jitter was not positive definite.  Synchronises with the device."""
+        from .ops import NotPSDError
+        for ly in self.layers:
+            if ly.last_info is not None and int(ly.last_info.max().item()) != 0:
+                raise NotPSDError(f"Kzz + jitter is not positive definite (pivot {int(ly.last_info.max().item())}) in a "
+                                  f"graph replay; re-run the step eagerly to get the jitter retries")
+
     def set_rng_offset(self, value: int):
         for ly in self.layers:
             ly.rng_offset_dev.fill_(int(value))

@@ -15,6 +15,14 @@ from . import _cabi
 
 Tensor = torch.Tensor
 
+# NVTX ranges around every op (forward ranges here, backward ranges inside the autograd Functions): visible in
+# nsys / ncu --nvtx timelines; GPBLUR_NVTX=0 switches them off
+import contextlib
+import os
+
+_NVTX = os.environ.get("GPBLUR_NVTX", "1") != "0"
+_null_ctx = contextlib.nullcontext
+
 
 def _ptr(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
@@ -225,9 +233,10 @@ def stage_grad_doubles(D: int, M: int) -> int:
     return int(_cabi.lib().gpblur_svgp_stage_grad_doubles(D, M))
 
 
-def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None):
+def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None, extra_jitter: float = 0.0):
     """Once-per-parameter-update M x M stage: -> (stage uint8 [param_stage_bytes], kl [1], info [1] int32).
-    `out` = preallocated (stage, kl, info) (the call then only launches on the current stream)."""
+    `out` = preallocated (stage, kl, info) (the call then only launches on the current stream).
+    `extra_jitter` is added to the diagonal of Kzz on top of the variational jitter (psd_safe_cholesky retries)."""
     _need_cuda(Z, raw_ell, raw_os, m, s, w, b)
     M, D = Z.shape
     dev = Z.device
@@ -243,8 +252,12 @@ def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None):
         stage, kl, info = out
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().gpblur_svgp_param_stage(C.byref(p), D, M, _ptr(kl), _ptr(info), _ptr(stage), stage.numel(),
-                                                 _stream())
+        if extra_jitter:
+            rc = _cabi.lib().gpblur_svgp_param_stage_jitter(C.byref(p), D, M, float(extra_jitter), _ptr(kl), _ptr(info),
+                                                            _ptr(stage), stage.numel(), _stream())
+        else:
+            rc = _cabi.lib().gpblur_svgp_param_stage(C.byref(p), D, M, _ptr(kl), _ptr(info), _ptr(stage), stage.numel(),
+                                                     _stream())
     _cabi.check(rc, "gpblur_svgp_param_stage")
     return stage, kl, info
 
@@ -387,7 +400,8 @@ class _ParamStageFunction(torch.autograd.Function):
             for h in range(H):
                 fork.enter(h)
                 param_stage_raw(Zc[h], ellc[h], osc[h], mc[h], sc[h], None if wc is None else wc[h % wc.shape[0]],
-                                bc[h % bc.shape[0]], out=(stage[h], kl[h:h + 1], info[h:h + 1]))
+                                bc[h % bc.shape[0]], out=(stage[h], kl[h:h + 1], info[h:h + 1]),
+                                extra_jitter=float(holder.get("extra_jitter", 0.0)))
         finally:
             fork.join()
         holder["stage"] = stage
@@ -404,6 +418,11 @@ class _ParamStageFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_token, g_kl, _g_info):
+        with torch.cuda.nvtx.range("gpblur.param_stage_backward") if _NVTX else _null_ctx():
+            return _ParamStageFunction._backward(ctx, g_token, g_kl, _g_info)
+
+    @staticmethod
+    def _backward(ctx, g_token, g_kl, _g_info):
         Zc, ellc, osc, mc, sc, wc, bc = ctx.saved_tensors
         holder = ctx.holder
         H, M, D = Zc.shape
@@ -495,6 +514,11 @@ class _PointFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_mean, g_var, g_sample):
+        with torch.cuda.nvtx.range("gpblur.point_backward") if _NVTX else _null_ctx():
+            return _PointFunction._backward(ctx, g_mean, g_var, g_sample)
+
+    @staticmethod
+    def _backward(ctx, g_mean, g_var, g_sample):
         x2, out, *wss = ctx.saved_tensors
         seed, offset, stream_id, M, shape, H, batched, nout, hs = ctx.meta
         N, D = x2.shape
@@ -534,9 +558,21 @@ def _stage_key(Z, raw_ell, raw_os, m, s, w, b):
     return key + (tuple(Z.shape),)
 
 
+class NotPSDError(RuntimeError):
+    """Kzz + jitter is not positive definite even after the jitter retries (gpytorch.utils.errors.NotPSDError)."""
+
+
+class NumericalWarning(RuntimeWarning):
+    pass
+
+
+# psd_safe_cholesky (gpytorch, fp32): on failure add 1e-6, 1e-5, 1e-4 to the diagonal, then give up
+JITTER_RETRIES = (1e-6, 1e-5, 1e-4)
+
+
 def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
                      variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
-                     mean_bias: Tensor, stage_cache: Optional[dict] = None):
+                     mean_bias: Tensor, stage_cache: Optional[dict] = None, check: bool = False):
     """-> (token, kl, info, holder).  With `stage_cache` (a dict owned by the caller, one per GP layer) consecutive
     calls with unchanged parameter tensors (same `_version`) share one stage - and therefore one M x M backward -
     until a backward pass has consumed it.  Parameters with a leading H (inducing points [H, M, D]) describe the H
@@ -552,7 +588,24 @@ def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outpu
                 and ent[0].requires_grad == want_grad:
             return ent
     holder = {}
-    token, kl, info = _ParamStageFunction.apply(*params, holder)
+    with torch.cuda.nvtx.range("gpblur.param_stage") if _NVTX else _null_ctx():
+        token, kl, info = _ParamStageFunction.apply(*params, holder)
+    # Cholesky status (LAPACK-style info, 0 = ok).  Reading it synchronises with the device, as gpytorch's
+    # psd_safe_cholesky does; it is skipped while a CUDA graph is being captured (check GraphedStep.check_info()).
+    if check and not torch._C._cuda_isCurrentStreamCapturing():
+        k = int(info.max().item())
+        if k != 0:
+            import warnings
+            for jit in JITTER_RETRIES:
+                holder = {"extra_jitter": jit}
+                token, kl, info = _ParamStageFunction.apply(*params, holder)
+                if int(info.max().item()) == 0:
+                    warnings.warn(f"Kzz + 1e-4 I is not positive definite (pivot {k}): added jitter of {jit:.1e} to the "
+                                  f"diagonal", NumericalWarning)
+                    break
+            else:
+                raise NotPSDError(f"Kzz is not positive definite after adding jitter up to {JITTER_RETRIES[-1]:.1e} "
+                                  f"(first failing pivot {k})")
     ent = (token, kl, info, holder)
     if stage_cache is not None:
         stage_cache["key"] = key
@@ -564,20 +617,21 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
                  want_sample: bool = False, stage_cache: Optional[dict] = None,
-                 offset_dev: Optional[Tensor] = None, h_stride: Optional[int] = None):
+                 offset_dev: Optional[Tensor] = None, h_stride: Optional[int] = None, check: bool = False):
     """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]); with inducing points [H, M, D]
     (multi-output layer) the outputs are [..., H], kl [H], info [H], and GP h draws its sample with Philox counters
     offset + h * h_stride + n (h_stride defaults to the N points of this call; batch-sharded callers pass the GLOBAL
     point count so that the counters do not depend on the number of ranks).  `stage_cache`: see svgp_param_stage.  `offset_dev`: optional int64 device scalar added to
     `offset` when the kernels run (CUDA-graph replays draw fresh counters by bumping it between replays)."""
     token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
-                                               variational_stddev, mean_weights, mean_bias, stage_cache)
+                                               variational_stddev, mean_weights, mean_bias, stage_cache, check=check)
     if x.numel() == 0:
         shp = tuple(x.shape[:-1]) + ((token.shape[0],) if token.dim() == 2 else ())
         e = x.new_empty(shp, dtype=torch.float32)
         return e, e.clone(), (e.clone() if want_sample else None), kl, info
-    mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
-                                             int(stream_id), bool(want_sample), offset_dev, h_stride)
+    with torch.cuda.nvtx.range("gpblur.point_forward") if _NVTX else _null_ctx():
+        mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
+                                                 int(stream_id), bool(want_sample), offset_dev, h_stride)
     return mean, var, sample, kl, info
 
 

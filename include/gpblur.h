@@ -127,6 +127,13 @@ int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const 
                                uint64_t seed, uint64_t offset, uint32_t stream_id,
                                const unsigned long long* offset_dev, float* dx, double* stage_grad,
                                void* ws, size_t ws_bytes, void* stream);
+/* Same as gpblur_svgp_param_stage with `extra_jitter` >= 0 added to the diagonal of Kzz on top of the variational
+ * jitter 1e-4.  Replaces the retry loop of gpytorch's psd_safe_cholesky (called from VariationalStrategy.forward,
+ * /root/reference/denoising_model/DeepGP.py:33-38): when `info` reports a non-positive pivot the host retries with
+ * 1e-6, 1e-5, 1e-4 and raises NotPSDError after that.  The jitter of the data-side diagonal diag(Kxx) stays 1e-4. */
+int gpblur_svgp_param_stage_jitter(const gpblur_svgp_params* p, int D, int M, double extra_jitter, float* kl,
+                                   int* info, void* stage, size_t stage_bytes, void* stream);
+
 /* `stage` is the buffer filled by gpblur_svgp_param_stage; its fp64 scratch regions are overwritten. */
 int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M,
                                      const double* stage_grad, const float* g_kl,

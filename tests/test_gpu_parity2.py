@@ -163,3 +163,20 @@ def test_sharded_multi_output_counters_match_single_rank(cuda):
         s_a = layer1_sample(x[:B // 2], 0)
         s_b = layer1_sample(x[B // 2:], B // 2)
         assert torch.equal(torch.cat([s_a, s_b], dim=1), s_full)
+
+
+def test_not_psd_raises_after_jitter_retries(cuda):
+    """gpytorch's psd_safe_cholesky convention: retry with extra jitter, then NotPSDError (default check is ON)."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    with gpcompat.num_likelihood_samples(1):
+        m = DeepGPp(16, 1, num_inducing=32).to(cuda)
+        x = torch.randn(4, 8, 16, device=cuda)
+        m.predict(x)                                              # healthy parameters: fine
+        with torch.no_grad():
+            m.hidden_layer.variational_strategy.inducing_points[3, 0] = float("nan")
+        with pytest.raises(gpcompat.NotPSDError):
+            m.predict(x)
+        with gpcompat.check_cholesky(False):                      # opt-out: flag only
+            m.predict(x)
+            assert int(m.hidden_layer.last_info.max().item()) != 0
