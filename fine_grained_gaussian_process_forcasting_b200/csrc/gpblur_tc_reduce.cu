@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
         const long long n = n0 + 4 * c + (lane & 3);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n < r1) v = *reinterpret_cast<const float4*>(a.U + tc_tiled_index(n, (p0 + ar) & ~3, a.MP));
-        rg.a[i] = quad_transpose(v, lane);
+        rg.a[i] = v;       // raw: the 4 x 4 transpose happens in produce(), two slabs later (a dependent shuffle here
+                           // would stall the prefetch on its own HBM round trip)
       }
       if (TQ >= kProd || tid < TQ * BG) {
   #pragma unroll
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
             const long long n = n0 + 4 * c + (lane & 3);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (n < r1 && q0 + bq < a.vcols) v = *reinterpret_cast<const float4*>(a.V + tc_tiled_index(n, (q0 + bq) & ~3, a.MP));
-            rg.b[i] = quad_transpose(v, lane);
+            rg.b[i] = v;   // raw (see above)
           } else {
             float v[4];
   #pragma unroll
@@ -190,23 +191,24 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = acg + 4 * i;
+        const float4 av = quad_transpose(rg.a[i], lane);
         float4 h, l;
-        tc::split_tf32(rg.a[i].x, h.x, l.x); tc::split_tf32(rg.a[i].y, h.y, l.y);
-        tc::split_tf32(rg.a[i].z, h.z, l.z); tc::split_tf32(rg.a[i].w, h.w, l.w);
+        tc::split_tf32(av.x, h.x, l.x); tc::split_tf32(av.y, h.y, l.y);
+        tc::split_tf32(av.z, h.z, l.z); tc::split_tf32(av.w, h.w, l.w);
         tc::tmem_st4(a_hi_t + 4 * c, h);
         tc::tmem_st4(a_lo_t + 4 * c, l);
         {
-          usum = fmaf(gms[sb][4 * c + 0], rg.a[i].x, usum);
-          usum = fmaf(gms[sb][4 * c + 1], rg.a[i].y, usum);
-          usum = fmaf(gms[sb][4 * c + 2], rg.a[i].z, usum);
-          usum = fmaf(gms[sb][4 * c + 3], rg.a[i].w, usum);
+          usum = fmaf(gms[sb][4 * c + 0], av.x, usum);
+          usum = fmaf(gms[sb][4 * c + 1], av.y, usum);
+          usum = fmaf(gms[sb][4 * c + 2], av.z, usum);
+          usum = fmaf(gms[sb][4 * c + 3], av.w, usum);
         }
       }
       if (TQ >= kProd || tid < TQ * BG) {
   #pragma unroll
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
-          float4 v = rg.b[i];
+          float4 v = GRAM ? quad_transpose(rg.b[i], lane) : rg.b[i];
           v.x *= scs[sb][4 * c + 0]; v.y *= scs[sb][4 * c + 1];
           v.z *= scs[sb][4 * c + 2]; v.w *= scs[sb][4 * c + 3];
           tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
