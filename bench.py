@@ -382,7 +382,7 @@ def measure(args, wl, name, ctx, primary=True):
     B, D, M, calls = wl["B"], wl["D"], wl["M"], wl["calls"]
     model = make_model(wl, device)
     model.train()
-    bucket = FlatGradBucket(gp_parameters(model))
+    bucket = FlatGradBucket(gp_parameters(model), module=model)
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     nbuf = 3   # rotate inputs; an L2 flush is also issued between timed steps
     xs = [[torch.randn(B, L, D, device=device, generator=g) for L in calls] for _ in range(nbuf)]

@@ -69,6 +69,9 @@ SIGNATURES = {
     "gpblur_svgp_param_stage_backward": (C.c_int, [
         C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
         C.c_void_p]),
+    "gpblur_svgp_param_stage_backward_acc": (C.c_int, [
+        C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+        C.c_void_p]),
     "gpblur_elbo_forward": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
         C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),

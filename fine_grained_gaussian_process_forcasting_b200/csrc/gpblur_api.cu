@@ -383,6 +383,17 @@ int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M, 
   return launch_mm_backward(*p, L, stage, stage_grad, g_kl, grad_bucket, (cudaStream_t)stream);
 }
 
+int gpblur_svgp_param_stage_backward_acc(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,
+                                         const float* g_kl, float* grad_bucket, int accumulate, void* stage,
+                                         size_t stage_bytes, void* stream) {
+  int rc = validate(p, 0, D, M);
+  if (rc) return rc;
+  if (!stage_grad || !grad_bucket || !stage || (reinterpret_cast<uintptr_t>(stage) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(0, D, M, 0);
+  if (stage_bytes < L.total) return GPBLUR_EWORKSPACE;
+  return launch_mm_backward(*p, L, stage, stage_grad, g_kl, grad_bucket, (cudaStream_t)stream, accumulate ? 1 : 0);
+}
+
 int gpblur_svgp_backward(const gpblur_svgp_params* p, const float* x, long long N, int D, int M,
                          const float* g_mean, const float* g_var, const float* g_sample, const float* g_kl,
                          const float* var, uint64_t seed, uint64_t offset, uint32_t stream_id, float* dx,

@@ -683,7 +683,9 @@ struct MmBwdArgs {
   const double* sgrad;    // summed stage gradient [u | vec | S | W^T X], see stage_grad_doubles()
   const float* g_kl;
   float* bucket;
+  int accumulate;         // != 0: add into `bucket` (it is the caller's live gradient buffer) instead of overwriting it
 };
+#define GPBLUR_PUT(ptr, val) do { float* p_ = (ptr); const float v_ = (val); *p_ = a.accumulate ? *p_ + v_ : v_; } while (0)
 
 // Per-call reduction of the split partials into the stage gradient (fixed order => bit-deterministic).
 struct SgReduceArgs {
@@ -917,7 +919,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     const double z = (double)Zt[(size_t)i * DP + d];
     const double wxt = (wx - csum * (double)center[d]) * ie;          // (W^T Xtilde)_id
     const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
-    a.bucket[(size_t)i * D + d] = (float)dz;
+    GPBLUR_PUT(&a.bucket[(size_t)i * D + d], (float)dz);
     return -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
   };
   if (DP >= TB) {
@@ -997,14 +999,14 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
         double tot = q[d];
         for (int p2 = 0; p2 < npart; ++p2) tot += colred[p2 * DP + d];
         const double dell = tot * (double)inv_ell[d];
-        b_ell[d] = (float)(dell * sigmoid64((double)a.p.raw_lengthscale[d]));
-        b_w[d] = a.p.mean_weights ? (float)wbar[d] : 0.f;
+        GPBLUR_PUT(&b_ell[d], (float)(dell * sigmoid64((double)a.p.raw_lengthscale[d])));
+        GPBLUR_PUT(&b_w[d], a.p.mean_weights ? (float)wbar[d] : 0.f);
       }
     }
     for (int m = tid; m < M; m += kThreads) {
       const double mm = (double)mvec[m], ss = (double)svec[m];
-      b_m[m] = (float)(u64[m] + gkl * mm);
-      b_s[m] = (float)(2.0 * ss * sdiag[m] + gkl * (ss - 1.0 / ss));
+      GPBLUR_PUT(&b_m[m], (float)(u64[m] + gkl * mm));
+      GPBLUR_PUT(&b_s[m], (float)(2.0 * ss * sdiag[m] + gkl * (ss - 1.0 / ss)));
     }
     if (warp == 0) {
       double s = 0.0;
@@ -1012,8 +1014,8 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       s = warp_sum(s);
       if (lane == 0) {
         const double dos = (s + sc[VS_RSUM]) / os + sc[VS_GVAR];
-        b_os[0] = (float)(dos * sigmoid64((double)a.p.raw_outputscale[0]));
-        b_b[0] = (float)sc[VS_GMU];
+        GPBLUR_PUT(&b_os[0], (float)(dos * sigmoid64((double)a.p.raw_outputscale[0])));
+        GPBLUR_PUT(&b_b[0], (float)sc[VS_GMU]);
       }
     }
   }
@@ -1055,7 +1057,7 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 }
 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
-                       const float* g_kl, float* grad_bucket, cudaStream_t st) {
+                       const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate) {
   const size_t smem = kGemmScratchDoubles * sizeof(double);
   cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   const int nb = L.MP / TB;
@@ -1064,7 +1066,7 @@ int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* sta
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
-  MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket};
+  MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate};
   void* kargs[] = {&args};
   ProfScope ps(ST_MM_BWD, st);
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),

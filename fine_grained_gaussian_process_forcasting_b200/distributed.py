@@ -34,19 +34,44 @@ class FlatGradBucket:
     """One contiguous fp32 gradient buffer; every parameter's ``.grad`` is a view into it, so autograd
     accumulates straight into the bucket and the all-reduce needs no packing copy."""
 
-    def __init__(self, params: Iterable[nn.Parameter]):
+    def __init__(self, params: Iterable[nn.Parameter], module: Optional[nn.Module] = None):
+        """`module`: if given, every single-output GP layer with a linear mean whose seven parameters are all in
+        `params` gets them laid out contiguously in the C-ABI bucket order (include/gpblur.h: Z, raw_lengthscale,
+        raw_outputscale, variational_mean, variational_stddev, weights, bias) and becomes a GRADIENT SINK: its M x M
+        backward kernel accumulates straight into this buffer (``layer._grad_sink``) and autograd launches no
+        per-parameter accumulation kernels for it."""
         self.params = list(params)
         if not self.params:
             raise ValueError("no parameters")
         dev = self.params[0].device
+        if any(p.dtype != torch.float32 or p.device != dev for p in self.params):
+            raise ValueError("FlatGradBucket needs fp32 parameters on one device")
+        sinks = []
+        if module is not None:
+            from .gpcompat import LinearMean
+            have = {id(p) for p in self.params}
+            taken = set()
+            for layer in _gp_layers(module):
+                mm = getattr(layer, "mean_module", None)
+                if layer.output_dims is not None or not isinstance(mm, LinearMean) or mm.bias is None:
+                    continue
+                seven = list(layer._layer_params())
+                if all(id(p) in have and id(p) not in taken for p in seven):
+                    sinks.append((layer, seven))
+                    taken.update(id(p) for p in seven)
+            ordered = [p for _, seven in sinks for p in seven] + [p for p in self.params if id(p) not in taken]
+            self.params = ordered
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         o = 0
+        starts = {}
         for p in self.params:
-            if p.dtype != torch.float32 or p.device != dev:
-                raise ValueError("FlatGradBucket needs fp32 parameters on one device")
+            starts[id(p)] = o
             p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
+        for layer, seven in sinks:
+            a = starts[id(seven[0])]
+            layer._grad_sink = self.flat[a:a + sum(p.numel() for p in seven)]
 
     def zero(self):
         self.flat.zero_()
@@ -108,7 +133,7 @@ class ShardedGPBlur(nn.Module):
         self.group = group
         if broadcast:
             broadcast_parameters(model, 0, group)
-        self.bucket = FlatGradBucket(gp_parameters(model))
+        self.bucket = FlatGradBucket(gp_parameters(model), module=model)
         self.step_index = 0
 
     def _layers(self):

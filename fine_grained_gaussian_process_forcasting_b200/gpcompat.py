@@ -468,6 +468,7 @@ class DeepGPLayer(ApproximateGP):
         self._rng_offset = 0
         self._rng_stream = 0
         self._rng_h_stride = None          # Philox counter stride between the H GPs (None: the points of the call)
+        self._grad_sink = None             # flat fp32 view the M x M backward accumulates into (FlatGradBucket)
         self.fused_sample = True
         self.last_info = None
         self.rng_offset_dev = None         # optional int64 device scalar added to the Philox offset (graphs.py)
@@ -515,7 +516,7 @@ class DeepGPLayer(ApproximateGP):
 
     def _kl_only(self):
         _, kl, _, _ = ops.svgp_param_stage(*self._layer_params(), stage_cache=self._stage_cache(),
-                                           check=bool(check_cholesky.value()))
+                                           check=bool(check_cholesky.value()), grad_sink=self._grad_sink)
         return kl.sum() if kl.dim() else kl
 
     def __call__(self, inputs, are_samples=False, **kwargs):
@@ -540,7 +541,8 @@ class DeepGPLayer(ApproximateGP):
                                                        want_sample=self.fused_sample,
                                                        stage_cache=self._stage_cache(),
                                                        offset_dev=self.rng_offset_dev, h_stride=self._rng_h_stride,
-                                                       check=bool(check_cholesky.value()))
+                                                       check=bool(check_cholesky.value()),
+                                                       grad_sink=self._grad_sink)
         self.last_info = info
         if H is None:
             cls = MultivariateNormal

@@ -306,16 +306,17 @@ def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, of
 
 
 def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor,
-                             bucket: Optional[Tensor] = None):
-    """Summed stage gradient (+ g_kl) -> flat parameter-gradient bucket [M*D + 2M + 2D + 2]."""
+                             bucket: Optional[Tensor] = None, accumulate: bool = False):
+    """Summed stage gradient (+ g_kl) -> flat parameter-gradient bucket [M*D + 2M + 2D + 2] (`accumulate`: added to
+    `bucket` instead of overwriting it)."""
     _need_cuda(Z, sgrad, stage, g_kl)
     M, D = Z.shape
     if bucket is None:
         bucket = torch.empty(grad_bucket_floats(D, M), device=Z.device, dtype=torch.float32)
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(Z.device):
-        rc = _cabi.lib().gpblur_svgp_param_stage_backward(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
-                                                          _ptr(stage), stage.numel(), _stream())
+        rc = _cabi.lib().gpblur_svgp_param_stage_backward_acc(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
+                                                              int(accumulate), _ptr(stage), stage.numel(), _stream())
     _cabi.check(rc, "gpblur_svgp_param_stage_backward")
     return bucket
 
@@ -434,8 +435,16 @@ class _ParamStageFunction(torch.autograd.Function):
             sgrad = g_token.to(torch.float64).reshape(H, G).contiguous()
         gk = None if g_kl is None else _f32c(g_kl).reshape(-1).expand(H).contiguous()
         nb = grad_bucket_floats(D, M)
-        bucket = torch.empty(H, nb, device=dev, dtype=torch.float32)
         stage = holder["stage"]
+        sink = holder.get("grad_sink")
+        if sink is not None and H == 1 and wc is not None:
+            # the caller's flat gradient buffer holds this layer's parameters contiguously in bucket order
+            # (distributed.FlatGradBucket): the kernel accumulates straight into it, autograd gets no gradient to add
+            param_stage_backward_raw(Zc[0], ellc[0], osc[0], mc[0], sc[0], wc[0], bc[0], sgrad[0],
+                                     None if gk is None else gk[0:1], stage[0], bucket=sink, accumulate=True)
+            holder["consumed"] = True
+            return (None,) * 8
+        bucket = torch.empty(H, nb, device=dev, dtype=torch.float32)
         fork = _Fork(dev, H)
         try:
             for h in range(H):
@@ -572,7 +581,8 @@ JITTER_RETRIES = (1e-6, 1e-5, 1e-4)
 
 def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor,
                      variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
-                     mean_bias: Tensor, stage_cache: Optional[dict] = None, check: bool = False):
+                     mean_bias: Tensor, stage_cache: Optional[dict] = None, check: bool = False,
+                     grad_sink: Optional[Tensor] = None):
     """-> (token, kl, info, holder).  With `stage_cache` (a dict owned by the caller, one per GP layer) consecutive
     calls with unchanged parameter tensors (same `_version`) share one stage - and therefore one M x M backward -
     until a backward pass has consumed it.  Parameters with a leading H (inducing points [H, M, D]) describe the H
@@ -587,7 +597,7 @@ def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outpu
         if ent is not None and stage_cache.get("key") == key and not ent[3]["consumed"] \
                 and ent[0].requires_grad == want_grad:
             return ent
-    holder = {}
+    holder = {} if grad_sink is None else {"grad_sink": grad_sink}
     with torch.cuda.nvtx.range("gpblur.param_stage") if _NVTX else _null_ctx():
         token, kl, info = _ParamStageFunction.apply(*params, holder)
     # Cholesky status (LAPACK-style info, 0 = ok).  Reading it synchronises with the device, as gpytorch's
@@ -598,6 +608,8 @@ def svgp_param_stage(inducing_points: Tensor, raw_lengthscale: Tensor, raw_outpu
             import warnings
             for jit in JITTER_RETRIES:
                 holder = {"extra_jitter": jit}
+                if grad_sink is not None:
+                    holder["grad_sink"] = grad_sink
                 token, kl, info = _ParamStageFunction.apply(*params, holder)
                 if int(info.max().item()) == 0:
                     warnings.warn(f"Kzz + 1e-4 I is not positive definite (pivot {k}): added jitter of {jit:.1e} to the "
@@ -617,14 +629,16 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
                  variational_mean: Tensor, variational_stddev: Tensor, mean_weights: Optional[Tensor],
                  mean_bias: Tensor, seed: int = 0, offset: int = 0, stream_id: int = 0,
                  want_sample: bool = False, stage_cache: Optional[dict] = None,
-                 offset_dev: Optional[Tensor] = None, h_stride: Optional[int] = None, check: bool = False):
+                 offset_dev: Optional[Tensor] = None, h_stride: Optional[int] = None, check: bool = False,
+                 grad_sink: Optional[Tensor] = None):
     """x [..., D] -> (mean [...], var [...], sample [...] | None, kl [], info [1]); with inducing points [H, M, D]
     (multi-output layer) the outputs are [..., H], kl [H], info [H], and GP h draws its sample with Philox counters
     offset + h * h_stride + n (h_stride defaults to the N points of this call; batch-sharded callers pass the GLOBAL
     point count so that the counters do not depend on the number of ranks).  `stage_cache`: see svgp_param_stage.  `offset_dev`: optional int64 device scalar added to
     `offset` when the kernels run (CUDA-graph replays draw fresh counters by bumping it between replays)."""
     token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
-                                               variational_stddev, mean_weights, mean_bias, stage_cache, check=check)
+                                               variational_stddev, mean_weights, mean_bias, stage_cache, check=check,
+                                               grad_sink=grad_sink)
     if x.numel() == 0:
         shp = tuple(x.shape[:-1]) + ((token.shape[0],) if token.dim() == 2 else ())
         e = x.new_empty(shp, dtype=torch.float32)

@@ -127,6 +127,13 @@ int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const 
                                uint64_t seed, uint64_t offset, uint32_t stream_id,
                                const unsigned long long* offset_dev, float* dx, double* stage_grad,
                                void* ws, size_t ws_bytes, void* stream);
+/* gpblur_svgp_param_stage_backward with `accumulate` != 0: the gradients are ADDED to `grad_bucket`, which then is
+ * the caller's live flat gradient buffer (what the data-parallel all-reduce operates on) - no intermediate bucket
+ * and no per-parameter accumulation kernels on the framework side. */
+int gpblur_svgp_param_stage_backward_acc(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,
+                                         const float* g_kl, float* grad_bucket, int accumulate, void* stage,
+                                         size_t stage_bytes, void* stream);
+
 /* Same as gpblur_svgp_param_stage with `extra_jitter` >= 0 added to the diagonal of Kzz on top of the variational
  * jitter 1e-4.  Replaces the retry loop of gpytorch's psd_safe_cholesky (called from VariationalStrategy.forward,
  * /root/reference/denoising_model/DeepGP.py:33-38): when `info` reports a non-positive pivot the host retries with

@@ -180,3 +180,32 @@ def test_not_psd_raises_after_jitter_retries(cuda):
         with gpcompat.check_cholesky(False):                      # opt-out: flag only
             m.predict(x)
             assert int(m.hidden_layer.last_info.max().item()) != 0
+
+
+def test_grad_sink_matches_autograd_accumulation(cuda):
+    """FlatGradBucket(module=...) lets the M x M backward kernel accumulate into the flat buffer: same gradients as the
+    ordinary autograd accumulation, also over two backward passes (accumulate semantics of .grad)."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200.distributed import FlatGradBucket, gp_parameters
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    B, L, D, M = 6, 24, 32, 128
+    p = O.init_params_exercise(D, M, 41)
+    x, y, _, _ = O.make_inputs(B, L, D, 42)
+
+    def run(use_sink, passes):
+        with gpcompat.num_likelihood_samples(1):
+            m = DeepGPp(D, 1, num_inducing=M).to(cuda)
+            _load_layer(m.hidden_layer, p)
+            bucket = FlatGradBucket(gp_parameters(m), module=m) if use_sink else None
+            assert (m.hidden_layer._grad_sink is not None) == use_sink
+            for _ in range(passes):
+                out = m.blur(x.to(cuda).requires_grad_(True), y.to(cuda))
+                (out.mean.sum() + out.sample.sum() - out.elbo.mean()).backward()
+                m.hidden_layer._rng_offset = 0
+            torch.cuda.synchronize()
+            return {n: q.grad.detach().clone().reshape(-1) for n, q in m.named_parameters()}
+
+    for passes in (1, 2):
+        ga, gb = run(False, passes), run(True, passes)
+        for n in ga:
+            assert rel(gb[n], ga[n]) < 1e-6, (n, passes, rel(gb[n], ga[n]))
