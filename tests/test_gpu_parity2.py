@@ -209,3 +209,67 @@ def test_grad_sink_matches_autograd_accumulation(cuda):
         ga, gb = run(False, passes), run(True, passes)
         for n in ga:
             assert rel(gb[n], ga[n]) < 1e-6, (n, passes, rel(gb[n], ga[n]))
+
+
+def test_gpytorch_shim_path_runs_forward_and_backward_on_gpu(cuda):
+    """The `import gpytorch` shim on a GPU: a user-side deep GP layer written ONLY against the
+    gpytorch names the reference imports (DeepGP.py:6-11), evaluated with the reference's call protocol (predict ->
+    likelihood(dist).mean, DeepApproximateMLL(VariationalELBO(...))(dist, y), forecast_denoising.py:87-89), checked
+    against the oracle.  (The reference's own DeepGP.py cannot travel to the GPU box; tests/test_host.py builds it on
+    the shim in the CPU container.)"""
+    import fine_grained_gaussian_process_forcasting_b200 as pkg
+    pkg.install_gpytorch_shim()
+    import gpytorch
+    from gpytorch.means import LinearMean
+    from gpytorch.kernels import RBFKernel, ScaleKernel
+    from gpytorch.variational import VariationalStrategy, MeanFieldVariationalDistribution
+    from gpytorch.distributions import MultivariateNormal
+    from gpytorch.models.deep_gps import DeepGPLayer, DeepGP
+    from gpytorch.likelihoods import GaussianLikelihood
+    from gpytorch.mlls import DeepApproximateMLL, VariationalELBO
+
+    B, L, D, M = 5, 24, 32, 128
+
+    class Layer(DeepGPLayer):
+        def __init__(self):
+            z = torch.randn(M, D)
+            q = MeanFieldVariationalDistribution(num_inducing_points=M, batch_shape=torch.Size([]))
+            super().__init__(VariationalStrategy(self, z, q, learn_inducing_locations=True), D, None)
+            self.mean_module = LinearMean(D)
+            self.covar_module = ScaleKernel(RBFKernel(batch_shape=torch.Size([]), ard_num_dims=D), batch_shape=torch.Size([]),
+                                            ard_num_dims=None)
+
+        def forward(self, x):
+            return MultivariateNormal(self.mean_module(x), self.covar_module(x))
+
+    class Net(DeepGP):
+        def __init__(self):
+            super().__init__()
+            self.hidden_layer = Layer()
+            self.likelihood = GaussianLikelihood()
+
+        def forward(self, x):
+            return self.hidden_layer(x)
+
+    p = O.init_params_exercise(D, M, 51)
+    x, y, _, _ = O.make_inputs(B, L, D, 52)
+    with gpytorch.settings.num_likelihood_samples(1):
+        net = Net().to(cuda)
+        _load_layer(net.hidden_layer, p)
+        xd = x.to(cuda).requires_grad_(True)
+        dist = net(xd)
+        mean = net.likelihood(dist).mean
+        mll = DeepApproximateMLL(VariationalELBO(net.likelihood, net, D))
+        loss = -mll(dist, y.to(cuda).unsqueeze(0)).mean()
+        loss.backward()
+    p64 = O.clone_params(p, torch.float64, requires_grad=True)
+    p64["raw_noise"] = torch.zeros(1, dtype=torch.float64)
+    x64 = x.double().requires_grad_(True)
+    lo = O.mll_error(p64, x64, y.double(), float(D), reference_order=False)
+    lo.backward()
+    mo, vo = O.svgp_predict_closed_form(p64, x64)
+    assert tuple(mean.shape) == (1, B, L)
+    assert rel(mean[0], mo) < 1e-4 and rel(dist.variance[0], vo) < 1e-4
+    assert abs(loss.item() - lo.item()) < 1e-4 * abs(lo.item())
+    assert rel(xd.grad, x64.grad) < 2e-4
+    assert rel(net.hidden_layer.variational_strategy.inducing_points.grad, p64["inducing_points"].grad) < 2e-4
