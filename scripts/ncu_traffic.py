@@ -3,8 +3,8 @@
 --set full reports under gpurun_out/ into profiles/ncu_traffic.json: {workload: {stage: {bytes, kernel, ms}}}.
 bench.py reads that file to fill roofline.traffic."""
 import csv, json, re, subprocess, sys
-STAGE = [("mm_forward", "mm_fwd"), ("mm_backward", "mm_bwd"), ("tc_point_fwd", "point_fwd"), ("point_fwd", "point_fwd"),
-         ("tc_point_bwd", "point_bwd"), ("point_bwd", "point_bwd"), ("tc_dx", "dx")]
+STAGE = [("mm_forward", "mm_fwd"), ("mm_backward", "mm_bwd"), ("tc2_fwd", "point_fwd"), ("point_fwd", "point_fwd"),
+         ("tc2_bwd", "point_bwd"), ("point_bwd", "point_bwd")]
 def stage_of(name):
     if "stage_grad" in name:
         return "sg_reduce"
