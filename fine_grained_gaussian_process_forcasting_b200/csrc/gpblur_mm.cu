@@ -15,6 +15,8 @@
 // All matrices are [MP, MP] row-major doubles with MP a multiple of 32 (identity padding).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "gpblur_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -24,6 +26,8 @@ namespace gpblur {
 namespace {
 
 constexpr int TB = 32;          // block size of the blocked algorithms
+// "not yet written" marker of the diagonal blocks of L^-1 (a NaN payload no arithmetic produces)
+constexpr long long kDinvSentinel = (long long)0xFFF7A5A5DEADBEEFull;
 constexpr int TLD = TB + 1;     // padded leading dimension of a shared tile
 typedef double Tile[TB][TLD];
 
@@ -139,33 +143,53 @@ __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
   j = t - ii * (ii + 1) / 2;
 }
 
-// 1 / sqrt(d) in double from the fp32 MUFU seed and ONE third-order Newton step (error ~ (5/16) e^3, e ~ 2^-22):
+// Grid-wide barrier on a monotonically increasing counter (zeroed by the host before the launch): the cooperative-launch
+// API costs 10 - 25 us of launch overhead per M x M kernel on this driver, a plain launch of <= 1 CTA per SM does not.
+// All CTAs are co-resident (grid <= SM count x occupancy, checked by the launcher); a CTA that cannot be scheduled yet
+// because an independent kernel holds its SM only delays the barrier.
+__device__ __forceinline__ void counter_grid_sync(unsigned* cnt, unsigned& target, int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += (unsigned)G;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// 1 / sqrt(d) in double from the FP64 MUFU seed (MUFU.RSQ64H works on the high word: ~20 good bits, no conversions to
+// and from fp32 on the pivot chain) and ONE third-order Newton step (error ~ (5/16) e^3, e ~ 2^-20 -> below 2^-60):
 // 4 dependent FP64 operations instead of the library routine's special-case handling on the pivot critical path.
-// d is a Cholesky pivot of a jittered kernel matrix: 1e-4 <~ d <~ outputscale, far from fp32 under/overflow.
+// d is a Cholesky pivot of a jittered kernel matrix: 1e-4 <~ d <~ outputscale, far from under/overflow.
 __device__ __forceinline__ double fast_rsqrt64(double d) {
-  const double y = (double)rsqrtf((float)d);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   const double e = fma(-d * y, y, 1.0);
   return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
-// Cholesky of a 32 x 32 block held one row per lane in registers, FUSED with the inverse of the factor.
+// Cholesky of a 32 x 32 block held one row per lane in registers, FUSED with the inverse of the factor (one warp).
 // Per column c: pivot broadcast (shuffle), reciprocal square root, then the scaled column goes through a
 // double-buffered shared-memory vector so that the trailing updates of a lane read their multipliers with broadcast
 // loads (one 16-byte load per two columns) instead of two shuffles each.
 //  * The NEXT pivot never waits for that shared-memory round trip: in lane c + 1 the multiplier of column c + 1 is the
 //    lane's own l, so `piv = a[c + 1] - l * l` is formed locally and shuffled at the top of the next iteration (the
-//    dependent chain per column is shuffle -> rsqrt -> 2 FP64 operations).
+//    dependent chain per column is shuffle -> rsqrt -> 2 FP64 operations: 126 cycles measured).
 //  * The same column broadcast drives one step of the column-oriented forward substitution X = L^-1 (lane = column
-//    of X): x[c] = s[c] / L[c][c], then s[r] -= L[r][c] x[c] for r > c - independent FMAs that fill the latency of
-//    the pivot chain, so the block inverse costs no extra time (it used to be a second 32-step loop).
-// On exit a[c] = L[lane][c] (0 above the diagonal), x[r] = (L^-1)[r][lane]; returns the first bad pivot (1-based).
-// `lcol`: 2 x 32 doubles of shared memory, 16-byte aligned.
-__device__ __forceinline__ int chol32_inv_warp(double (&a)[TB], double (&x)[TB], int lane, double* lcol) {
-  int bad = 0;
+//    of X): x[c] = s[c] / L[c][c], then s[r] -= L[r][c] x[c] for r > c.
+//  * No pivot test inside the loop (it cost 1000 of 6900 cycles): a non-positive pivot turns its reciprocal square
+//    root, and with it the rest of the factor, into NaN / Inf; the caller finds the first bad diagonal entry afterwards.
+// Measured alone (scripts/micro/chol32_bench.cu, B200): chain only 4000 cycles, + trailing update 5100, + inverse
+// 5900 (3.0 us).  Two warps (factor | inverse, handshake through a shared-memory flag) were SLOWER: 7100 cycles with a
+// polling consumer, 10000 with a fence per column.
+// On exit a[c] = L[lane][c] (0 above the diagonal), x[r] = (L^-1)[r][lane].  `lcol`: 2 x 32 doubles, 16-byte aligned.
+__device__ __forceinline__ void chol32_inv_warp(double (&a)[TB], double (&x)[TB], int lane, double* lcol) {
 #pragma unroll
   for (int r = 0; r < TB; ++r) x[r] = (r == lane) ? 1.0 : 0.0;
   double d = __shfl_sync(0xffffffffu, a[0], 0);
-  if (!(d > 0.0)) bad = 1;
   double rs = fast_rsqrt64(d);
 #pragma unroll
   for (int c = 0; c < TB; ++c) {
@@ -176,7 +200,6 @@ __device__ __forceinline__ int chol32_inv_warp(double (&a)[TB], double (&x)[TB],
     if (c + 1 < TB) {
       const double piv = fma(-l, l, a[c + 1]);
       d = __shfl_sync(0xffffffffu, piv, c + 1);
-      if (!(d > 0.0) && bad == 0) bad = c + 2;
       rs = fast_rsqrt64(d);
     }
     a[c] = (lane >= c) ? l : 0.0;
@@ -211,7 +234,78 @@ __device__ __forceinline__ int chol32_inv_warp(double (&a)[TB], double (&x)[TB],
       }
     }
   }
-  return bad;
+}
+
+// ---- 32 x 32 x 32 products with BOTH operands already in shared memory (FP64 tensor path), accumulators kept in the
+// mma fragment layout: warp w owns rows 8 (w & 3) .. + 8 and columns 16 (w >> 2) .. + 16; lane = 4 g + t holds
+// C[rw + g][cw + 8 j + 2 t], C[rw + g][cw + 8 j + 2 t + 1] for j = 0, 1.  Operand buffers: A as At[row][k], B TRANSPOSED
+// as Bt[col][k], pitch GLD doubles.
+struct Frag {
+  double c[2][2];
+};
+__device__ __forceinline__ void frag_coords(int& row, int& col0) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  row = 8 * (w & 3) + (lane >> 2);
+  col0 = 16 * (w >> 2) + 2 * (lane & 3);
+}
+__device__ __forceinline__ void smem_gemm32(Frag& f, const double* At, const double* Bt) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* ap = At + (8 * (w & 3) + g) * GLD + t;
+  const double* bp0 = Bt + (16 * (w >> 2) + g) * GLD + t;
+  const double* bp1 = bp0 + 8 * GLD;
+#pragma unroll
+  for (int k4 = 0; k4 < TB; k4 += 4) {
+    const double av = ap[k4];
+    dmma884(f.c[0][0], f.c[0][1], av, bp0[k4]);
+    dmma884(f.c[1][0], f.c[1][1], av, bp1[k4]);
+  }
+}
+// dst[row][col] = sign * f (row-major, pitch GLD): the layout of an A operand, and of a B operand read as B^T
+__device__ __forceinline__ void frag_park(double* dst, const Frag& f, double sign) {
+  int row, col0;
+  frag_coords(row, col0);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    *reinterpret_cast<double2*>(dst + row * GLD + col0 + 8 * j) = make_double2(sign * f.c[j][0], sign * f.c[j][1]);
+}
+// dst[col][row] = sign * f: the layout of a B operand read as B
+__device__ __forceinline__ void frag_park_t(double* dst, const Frag& f, double sign) {
+  int row, col0;
+  frag_coords(row, col0);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    dst[(col0 + 8 * j) * GLD + row] = sign * f.c[j][0];
+    dst[(col0 + 8 * j + 1) * GLD + row] = sign * f.c[j][1];
+  }
+}
+__device__ __forceinline__ void frag_load(Frag& f, const double* src, int ld, int r0, int c0) {
+  int row, col0;
+  frag_coords(row, col0);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double2 v = *reinterpret_cast<const double2*>(src + (size_t)(r0 + row) * ld + c0 + col0 + 8 * j);
+    f.c[j][0] = v.x;
+    f.c[j][1] = v.y;
+  }
+}
+__device__ __forceinline__ void frag_store(double* dst, int ld, int r0, int c0, const Frag& f, double sign) {
+  int row, col0;
+  frag_coords(row, col0);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    *reinterpret_cast<double2*>(dst + (size_t)(r0 + row) * ld + c0 + col0 + 8 * j) =
+        make_double2(sign * f.c[j][0], sign * f.c[j][1]);
+}
+// registers of fetch_tile() -> operand buffer (pitch GLD); trans: dst[col][row]
+__device__ __forceinline__ void park_operand(double* dst, const double (&v)[4], bool trans) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 8 * i;
+    if (!trans) dst[r * GLD + tx] = v[i];
+    else dst[tx * GLD + r] = v[i];
+  }
 }
 
 struct MmFwdArgs {
@@ -221,10 +315,15 @@ struct MmFwdArgs {
   float* kl;
   int* info;
   double extra_jitter;   // added to the diagonal of Kzz on top of the variational jitter (psd_safe_cholesky retries)
+  unsigned* bar;         // != nullptr: plain launch, counter_grid_sync() on this zeroed word; nullptr: cooperative launch
+  int debug_stop;        // >= 0: every CTA returns after that phase (timing experiments; results are incomplete)
+  unsigned* flags;       // two zeroed words: diagonal blocks published, worker arrivals (phase 2)
 };
 
 __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   cg::grid_group grid = cg::this_grid();
+  unsigned bar_target = 0;
+#define GPBLUR_GRID_SYNC() do { if (a.bar) counter_grid_sync(a.bar, bar_target, (int)gridDim.x); else grid.sync(); } while (0)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
   Tile& As = tiles[0];
@@ -256,6 +355,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   double* L64 = ws_ptr<double>(a.ws, L.L64);
   double* Li64 = ws_ptr<double>(a.ws, L.Linv64);
   double* T64 = ws_ptr<double>(a.ws, L.T64);
+  double* W64 = ws_ptr<double>(a.ws, L.U64);   // forward only: trailing matrix of the Cholesky (the backward reuses it)
   float* LinvT32 = ws_ptr<float>(a.ws, L.LinvT32);
   float* LC32 = ws_ptr<float>(a.ws, L.LC32);
   float* Linv32 = ws_ptr<float>(a.ws, L.Linv32);
@@ -265,6 +365,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   int stamp_i = 0;
 #define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
   GPBLUR_STAMP();
+  if (a.debug_stop == 0) return;
 
   // ---------------- phase 0: per-dimension hyper-parameters, centre, KL ----------------
   for (int d = blockIdx.x * 8 + warp; d < DP; d += G * 8) {
@@ -311,8 +412,9 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       if (a.info) a.info[0] = 0;
     }
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
   GPBLUR_STAMP();
+  if (a.debug_stop == 1) return;
 
   // ---------------- phase 1: Zt, vectors, Kzz ----------------
   for (int idx = gtid; idx < MP * DP; idx += gsize) {
@@ -379,140 +481,267 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         else kv = (gi == gj) ? 1.0 : 0.0;
         K64[(size_t)gi * MP + gj] = kv;
         K64[(size_t)gj * MP + gi] = kv;
-        L64[(size_t)gi * MP + gj] = (gj <= gi) ? kv : 0.0;
-        if (bi != bj) L64[(size_t)gj * MP + gi] = 0.0;
+        W64[(size_t)gi * MP + gj] = kv;                       // working copy (lower block triangle) of the factorisation
+        if (bi == bj) Li64[(size_t)gi * MP + gj] = __longlong_as_double(kDinvSentinel);   // armed: see phase 2
+        if (bi != bj) L64[(size_t)gj * MP + gi] = 0.0;        // L is written once per block; the upper block triangle is 0
       }
     }
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
   GPBLUR_STAMP();
+  if (a.debug_stop == 2) return;
 
-  // ---------------- phase 2: blocked Cholesky (right-looking) ----------------
-  // per block column kb: every participating CTA factorises the diagonal block in registers (one warp, shuffle
-  // broadcasts) and inverts it, so the panel solve X L_kk^T = A_ik becomes the GEMM X = A_ik Dinv^T.
+  // ---------------- phase 2: blocked Cholesky (right-looking, look-ahead) + triangular inverse ----------------
+  // CTA 0 owns the critical path: factorise the diagonal block (one warp, registers, 3 us) and invert it, publish
+  // L_kk / Dinv, then update the NEXT diagonal block itself (2 small products) and go on factorising.  Every other CTA
+  // is a worker one step behind: it waits for Dinv_kb, then does the trailing tiles and the triangular-inverse sums of
+  // step kb.  With Dinv the panel solve is the product P_i = A_ik Dinv^T - cheap enough (32^3) to be REPEATED by every
+  // CTA that needs it instead of being published through memory behind another barrier:
+  //   trailing tile (i, j), kb < j <= i :  C_ij -= P_i P_j^T                       (3 small products, 2 CTA barriers)
+  //   inverse sums  (i, j), i > kb >= j :  Y_ij += P_i X_kj,  X_kj = -Dinv Y_kj (j < kb) or Dinv (j = kb)
+  // where Y_ij = sum_k L_ik X_kj accumulates in T64 and block row kb of X = L^-1 is X_kj above (the triangular inverse
+  // costs no extra phase).  Synchronisation: Dinv_kb is its own flag (its block of Li64 is armed with a sentinel in phase
+  // 1 and polled by the workers), and `wcnt` counts worker arrivals (a worker arrives once per step in which it had
+  // tiles); nobody waits at a grid-wide barrier inside the loop.  The working matrix (W64) is only read in block column kb and only written in tiles (i, j > kb) owned by
+  // one CTA per step; the factor L (L64: P_i, written by the owner of tile (i, kb + 1)) and the inverse (Li64: X_kj,
+  // written by the owner of (kb + 1, j)) are write-once outputs.
+  // Measured at M = 256 (us): round-1 scheme (redundant factorisation, 2 grid barriers per step) 82; one barrier per
+  // step 61; look-ahead: see DESIGN.md.
   __shared__ __align__(16) double lcol[2 * TB];
-  Tile& Di = Cs[0];   // inverse of the diagonal block
-  // The triangular inverse X = L^-1 is built INSIDE the factorisation loop (no separate phase, no extra grid
-  // barriers): block row kb of X is X[kb][j] = -Dinv_kb * Y[kb][j] (j < kb) with Y[kb][j] = sum_{k=j}^{kb-1} L[kb][k] X[k][j]
-  // accumulated into T64 by rank-32 updates during the trailing phases of steps j .. kb - 1.
+  double* opbuf = reinterpret_cast<double*>(smem_raw);   // 7 operand buffers of 32 x GLD doubles (the Tile slots of other phases)
+  double* sD = opbuf + 0 * TB * GLD;     // Dinv           [row][k]   (A operand of X_kj; B operand (as B^T) of P_i)
+  double* sDT = opbuf + 1 * TB * GLD;    // Dinv^T         [col][row] (B operand when X_kj = Dinv)
+  double* sA = opbuf + 2 * TB * GLD;     // A_ik           [row][k]
+  double* sB = opbuf + 3 * TB * GLD;     // A_jk [row][k]  or Y_kj^T [col][k]
+  double* sP = opbuf + 4 * TB * GLD;     // P_i            [row][k]
+  double* sQ = opbuf + 5 * TB * GLD;     // P_j [row][k] (= B^T layout of P_j^T)  or X_kj^T [col][k]
+  double* sL = opbuf + 6 * TB * GLD;     // diagonal block: A_kk before, L_kk after the factorisation, row-major
+  static_assert(sizeof(Tile) * 11 >= sizeof(double) * 7 * TB * GLD, "operand buffers live in the Tile slots");
+  unsigned* wcnt = a.flags;
+  const int NW = G - 1;                                  // workers (nb > 1 implies G >= 4, see launch_mm_forward)
+  unsigned w_arrived_prev = 0;                           // worker arrivals expected through step kb - 1
+  auto wait_counter = [&](const unsigned* ctr, unsigned target) {
+    if (tid == 0) {
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      } while (v < target);
+    }
+    __syncthreads();
+  };
+  auto signal_counter = [&](unsigned* ctr) {             // after the CTA's global writes
+    __syncthreads();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  };
+  double* sL1 = opbuf + 7 * TB * GLD;    // second diagonal-block buffer (CTA 0 alternates: the next block is built while
+                                         // the factor of the current one is still being written out)
+  double* sC = sB;                       // CTA 0: the next diagonal block before its update
+  if (blockIdx.x == 0) {                                  // first diagonal block: one coalesced round trip
+    double dg4[4];
+    fetch_tile(dg4, MatRef{W64, MP, false}, 0, 0);
+    park_operand(sL, dg4, false);
+  }
   for (int kb = 0; kb < nb; ++kb) {
     const int nrb = nb - kb - 1;
-    const int n_items = nrb + kb;               // panel row blocks + inverse tiles of block row kb
-    if ((int)blockIdx.x < n_items || blockIdx.x == 0) {
-      __syncthreads();
-      if (kb == 0 && blockIdx.x == 0 && tid == 0) stamps[9] = global_ns();
-      // the operand tile of this CTA's first item is requested NOW: its L2 round trip hides behind the factorisation
-      double pre[4] = {0.0, 0.0, 0.0, 0.0};
-      if ((int)blockIdx.x < n_items) {
-        if ((int)blockIdx.x < nrb) fetch_tile(pre, MatRef{L64, MP, false}, (kb + 1 + blockIdx.x) * TB, kb * TB);
-        else fetch_tile(pre, MatRef{T64, MP, false}, kb * TB, ((int)blockIdx.x - nrb) * TB);
-      }
+    const int ntr = nrb * (nrb + 1) / 2;                 // trailing tiles (tile 0 = the next diagonal block: CTA 0's)
+    const int ny = nrb * (kb + 1);                       // inverse partial-sum tiles
+    const int n_items = nrb > 0 ? ntr - 1 + ny : kb;     // worker tiles; last block column: only X[kb][j], j < kb
+    if (blockIdx.x == 0) {
+      // Critical path of the whole phase: factorisation -> 2 small products -> factorisation ...  Everything else CTA 0
+      // does is moved off it: warps 1-7 fetch the operands of the look-ahead products WHILE warp 0 factorises, the
+      // outputs of a step are plain stores, and the release that publishes them (a memory barrier: ~0.5 us) is issued
+      // by a thread of warp 1 at the start of the NEXT step, under the next factorisation.
+      double* cur = (kb & 1) ? sL1 : sL;
+      double* nxt = (kb & 1) ? sL : sL1;
+      __syncthreads();                                    // `cur` holds A_kk; the stores of step kb - 1 are issued
+      if (kb == 0 && tid == 0) stamps[9] = global_ns();
+      if (a.debug_stop == 9 && tid == 0 && kb < 8) stamps[16 + 2 * kb] = global_ns();   // per-step probe
+      if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[16] = global_ns();
+      if (a.debug_stop == 8 && tid == 0 && kb == 3) stamps[21] = global_ns();
       if (warp == 0) {
         double arow[TB];
-        const double* src = L64 + (size_t)(kb * TB + lane) * MP + kb * TB;
 #pragma unroll
-        for (int c = 0; c < TB; ++c) arow[c] = src[c];
-        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[10] = global_ns() + (unsigned long long)(arow[0] == 12345.678);
+        for (int c = 0; c < TB; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(cur + lane * GLD + c);
+          arow[c] = v.x;
+          arow[c + 1] = v.y;
+        }
+        if (kb == 0 && lane == 0) stamps[10] = global_ns() + (unsigned long long)(arow[0] == 12345.678);
         double xcol[TB];
-        const int bad = chol32_inv_warp(arow, xcol, lane, lcol);
-        if (bad && blockIdx.x == 0 && lane == 0 && a.info) atomicCAS(a.info, 0, kb * TB + bad);
-        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(xcol[31] == 12345.678);
+        chol32_inv_warp(arow, xcol, lane, lcol);
+        if (kb == 0 && lane == 0) stamps[11] = global_ns() + (unsigned long long)(xcol[31] == 12345.678);
 #pragma unroll
-        for (int c = 0; c < TB; ++c) { Dg[lane][c] = arow[c]; Di[c][lane] = xcol[c]; }
-        if (kb == 0 && blockIdx.x == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(Di[31][0] == 12345.678);
-      }
-      __syncthreads();
-      // the diagonal block of the inverse is not read by anybody during this phase: publish it right away (the
-      // trailing phase below needs it)
-      if (blockIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = warp + 8 * i;
-          Li64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Di[r][lane];
+        for (int c = 0; c < TB; ++c) {
+          cur[lane * GLD + c] = arow[c];
+          sD[c * GLD + lane] = xcol[c];        // xcol[r] = Dinv[r][lane]
         }
-      }
-      for (int it = blockIdx.x; it < n_items; it += G) {
-        __syncthreads();
-        if (it < nrb) {
-          // panel rows owned by this CTA: X = A_ik * Dinv^T  (all 256 threads on one 32 x 32 block)
-          const int row0 = (kb + 1 + it) * TB;
-          if (it == (int)blockIdx.x) park_tile(As, pre, false);
-          else load_tile(As, MatRef{L64, MP, false}, row0, kb * TB);
-          __syncthreads();
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-          for (int k = 0; k < TB; ++k) {
-            const double bv = Di[lane][k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fma(As[warp + 8 * i][k], bv, acc[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) L64[(size_t)(row0 + warp + 8 * i) * MP + kb * TB + lane] = acc[i];
-        } else {
-          // inverse tile X[kb][j] = -Dinv_kb * Y[kb][j]
-          const int j = it - nrb;
-          if (it == (int)blockIdx.x) park_tile(As, pre, false);
-          else load_tile(As, MatRef{T64, MP, false}, kb * TB, j * TB);
-          __syncthreads();
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-          for (int k = 0; k < TB; ++k) {
-            const double yv = As[k][lane];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fma(Di[warp + 8 * i][k], yv, acc[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) Li64[(size_t)(kb * TB + warp + 8 * i) * MP + j * TB + lane] = -acc[i];
+        if (a.info) {
+          // first non-positive pivot: its column (and everything after it) is NaN / Inf or non-positive on the diagonal
+          const double dg = cur[lane * GLD + lane];   // own row: written by this lane
+          const unsigned badmask = __ballot_sync(0xffffffffu, !(dg > 0.0) || !(dg < 1e300));
+          if (badmask && lane == 0) atomicCAS(a.info, 0, kb * TB + __ffs(badmask));
         }
-      }
-    }
-    grid.sync();
-    // the factorised diagonal block is published only now: other CTAs read the unfactorised block above
-    if (blockIdx.x == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp + 8 * i;
-        L64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = Dg[r][lane];
-      }
-    }
-    // trailing update: C_ij -= L_ik L_jk^T for kb < j <= i;  plus the rank-32 update of the inverse's partial sums
-    // Y[i][j] (+)= L[i][kb] X[kb][j] for every later block row i > kb and j <= kb (one k-step per tile, all
-    // independent: the late steps of the factorisation leave most CTAs idle anyway)
-    const int ntr = nrb * (nrb + 1) / 2;
-    const int ny = nrb * (kb + 1);
-    for (int t = blockIdx.x; t < ntr + ny; t += G) {
-      if (t < ntr) {
-        int ti, tj;
-        tri_decode(t, ti, tj);
-        const int bi = kb + 1 + ti, bj = kb + 1 + tj;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0}, cv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)                      // C tile requested together with the operands
-          cv[i] = L64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane];
-        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{L64, MP, true}, bj * TB, kb * TB,
-                  kb * TB + TB, gsm);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = warp + 8 * i;
-          if (bi != bj || lane <= r) L64[(size_t)(bi * TB + r) * MP + bj * TB + lane] = cv[i] - acc[i];
-        }
+        if (kb == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(sD[0] == 12345.678);
       } else {
-        const int yi = (t - ntr) / (kb + 1), j = (t - ntr) - yi * (kb + 1);
-        const int bi = kb + 1 + yi;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0}, yv[4] = {0.0, 0.0, 0.0, 0.0};
-        if (j != kb) {                                   // the first contribution to Y[i][kb] comes from this step
-#pragma unroll
-          for (int i = 0; i < 4; ++i) yv[i] = T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane];
+        if (nrb > 0) {
+          // both tiles were last updated by workers in step kb - 1
+          if (kb > 0 && tid == 32) {
+            unsigned v;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(wcnt) : "memory");
+            } while (v < w_arrived_prev);
+          }
+          asm volatile("bar.sync 1, 224;" ::: "memory");
+          const double* srcA = W64 + (size_t)(kb + 1) * TB * MP + kb * TB;
+          const double* srcC = W64 + (size_t)(kb + 1) * TB * MP + (kb + 1) * TB;
+          for (int e = tid - 32; e < TB * TB; e += 224) {
+            const int r = e >> 5, c = e & 31;
+            sA[r * GLD + c] = srcA[(size_t)r * MP + c];
+            sC[r * GLD + c] = srcC[(size_t)r * MP + c];
+          }
         }
-        tile_gemm(acc, MatRef{L64, MP, false}, bi * TB, MatRef{Li64, MP, false}, j * TB, kb * TB, kb * TB + TB, gsm);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) T64[(size_t)(bi * TB + warp + 8 * i) * MP + j * TB + lane] = yv[i] + acc[i];
       }
+      __syncthreads();                                    // L_kk, Dinv, and the look-ahead operands are in shared memory
+      if (a.debug_stop == 9 && tid == 0 && kb < 8) stamps[17 + 2 * kb] = global_ns();
+      if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[17] = global_ns();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                       // write-once outputs: diagonal blocks of L and of L^-1
+        const int r = warp + 8 * i;
+        L64[(size_t)(kb * TB + r) * MP + kb * TB + lane] = cur[r * GLD + lane];
+        // Dinv is its own flag: the workers poll this block until the sentinel is gone (8-byte stores are atomic), so
+        // no release (a ~0.5 us memory barrier) sits between the factorisation and the look-ahead products
+        *reinterpret_cast<volatile double*>(Li64 + (size_t)(kb * TB + r) * MP + kb * TB + lane) = sD[r * GLD + lane];
+      }
+      if (nrb > 0) {
+        // look-ahead: the next diagonal block, C = A_(kb+1)(kb+1) - P P^T with P = A_(kb+1)(kb) Dinv^T = L_(kb+1)(kb)
+        if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[18] = global_ns();
+        Frag pfr = {};
+        smem_gemm32(pfr, sA, sD);
+        frag_park(sP, pfr, 1.0);
+        frag_store(L64, MP, (kb + 1) * TB, kb * TB, pfr, 1.0);
+        __syncthreads();
+        if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[19] = global_ns();
+        Frag u = {};
+        smem_gemm32(u, sP, sP);
+        int row, col0;
+        frag_coords(row, col0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double2 cv = *reinterpret_cast<const double2*>(sC + row * GLD + col0 + 8 * j);
+          *reinterpret_cast<double2*>(nxt + row * GLD + col0 + 8 * j) = make_double2(cv.x - u.c[j][0], cv.y - u.c[j][1]);
+        }
+        if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[20] = global_ns() + (unsigned long long)(u.c[0][0] == 12345.678);
+      }
+    } else if ((int)blockIdx.x - 1 < n_items) {
+      const int w = (int)blockIdx.x - 1;
+      auto item_decode = [&](int it, int& bi, int& bj, bool& trailing) {
+        if (nrb == 0) { bi = kb; bj = it; trailing = false; return; }
+        const int t = it + 1;                             // trailing tile 0 is CTA 0's
+        if (t < ntr) {
+          int ti, tj;
+          tri_decode(t, ti, tj);
+          bi = kb + 1 + ti; bj = kb + 1 + tj; trailing = true;
+        } else {
+          const int yi = (t - ntr) / (kb + 1);
+          bi = kb + 1 + yi; bj = (t - ntr) - yi * (kb + 1); trailing = false;
+        }
+      };
+      double preA[4] = {0.0, 0.0, 0.0, 0.0}, preB[4] = {0.0, 0.0, 0.0, 0.0};
+      auto item_fetch = [&](int it) {
+        int bi, bj; bool trailing;
+        item_decode(it, bi, bj, trailing);
+        if (nrb > 0) fetch_tile(preA, MatRef{W64, MP, false}, bi * TB, kb * TB);
+        if (trailing) { if (bj != bi) fetch_tile(preB, MatRef{W64, MP, false}, bj * TB, kb * TB); }
+        else if (bj != kb) fetch_tile(preB, MatRef{T64, MP, false}, kb * TB, bj * TB);
+      };
+      if (kb > 0) wait_counter(wcnt, w_arrived_prev);    // every tile of step kb - 1 is visible
+      else __syncthreads();
+      item_fetch(w);                                      // in flight while CTA 0 still factorises
+      {
+        // Dinv_kb: poll the block itself (volatile loads bypass L1) until CTA 0 has overwritten the sentinel
+        double dv[4];
+        const int tx = lane, ty = warp;
+        const volatile long long* src =
+            reinterpret_cast<const volatile long long*>(Li64 + (size_t)(kb * TB + ty) * MP + kb * TB + tx);
+        long long b0, b1, b2, b3;
+        do {                                      // the four loads of a thread travel together (one L2 round trip)
+          b0 = src[0];
+          b1 = src[(size_t)8 * MP];
+          b2 = src[(size_t)16 * MP];
+          b3 = src[(size_t)24 * MP];
+        } while (b0 == kDinvSentinel || b1 == kDinvSentinel || b2 == kDinvSentinel || b3 == kDinvSentinel);
+        dv[0] = __longlong_as_double(b0);
+        dv[1] = __longlong_as_double(b1);
+        dv[2] = __longlong_as_double(b2);
+        dv[3] = __longlong_as_double(b3);
+        park_operand(sD, dv, false);
+        park_operand(sDT, dv, true);
+      }
+      for (int it = w; it < n_items; it += NW) {
+        int bi, bj; bool trailing;
+        item_decode(it, bi, bj, trailing);
+        if (it != w) {
+          __syncthreads();                      // the previous item's products are done with the operand buffers
+          item_fetch(it);
+        }
+        if (nrb == 0) {
+          // X[kb][bj] = -Dinv Y[kb][bj]
+          park_operand(sB, preB, true);
+          __syncthreads();
+          Frag x = {};
+          smem_gemm32(x, sD, sB);
+          frag_store(Li64, MP, kb * TB, bj * TB, x, -1.0);
+          continue;
+        }
+        park_operand(sA, preA, false);
+        if (trailing) { if (bj != bi) park_operand(sB, preB, false); }
+        else if (bj != kb) park_operand(sB, preB, true);
+        Frag cfr = {};                          // C_ij or Y_ij, requested before the products
+        if (trailing) frag_load(cfr, W64, MP, bi * TB, bj * TB);
+        else if (bj != kb) frag_load(cfr, T64, MP, bi * TB, bj * TB);
+        __syncthreads();
+        Frag p = {};
+        smem_gemm32(p, sA, sD);                 // P_i = A_ik Dinv^T  (B^T layout of Dinv^T is Dinv row-major)
+        frag_park(sP, p, 1.0);
+        const double* second = sQ;
+        if (trailing) {
+          if (bj != bi) {
+            Frag q = {};
+            smem_gemm32(q, sB, sD);
+            frag_park(sQ, q, 1.0);
+          } else {
+            second = sP;
+          }
+          if (bj == kb + 1) frag_store(L64, MP, bi * TB, kb * TB, p, 1.0);      // L[bi][kb], write-once
+        } else if (bj != kb) {
+          Frag x = {};
+          smem_gemm32(x, sD, sB);               // Dinv Y_kj
+          frag_park_t(sQ, x, -1.0);             // X_kj = -(...) as a B operand: [col][k]
+          if (bi == kb + 1) frag_store(Li64, MP, kb * TB, bj * TB, x, -1.0);    // X[kb][bj], write-once
+        } else {
+          second = sDT;
+        }
+        __syncthreads();
+        Frag u = {};
+        smem_gemm32(u, sP, second);
+        if (trailing) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { cfr.c[j][0] -= u.c[j][0]; cfr.c[j][1] -= u.c[j][1]; }
+          frag_store(W64, MP, bi * TB, bj * TB, cfr, 1.0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { cfr.c[j][0] += u.c[j][0]; cfr.c[j][1] += u.c[j][1]; }
+          frag_store(T64, MP, bi * TB, bj * TB, cfr, 1.0);
+        }
+      }
+      signal_counter(wcnt);
     }
-    grid.sync();   // also publishes the last diagonal block before phase 4
+    w_arrived_prev += (unsigned)(n_items < NW ? n_items : NW);
   }
+  GPBLUR_GRID_SYNC();   // L, L^-1 complete and visible
 
   GPBLUR_STAMP();   // (the slot of the former recursive-doubling inverse phase: now ~0)
+  if (a.debug_stop == 3) return;
   GPBLUR_STAMP();
   GPBLUR_STAMP();
   // ---------------- phase 4: fp32 operands ----------------
@@ -684,6 +913,7 @@ struct MmBwdArgs {
   const float* g_kl;
   float* bucket;
   int accumulate;         // != 0: add into `bucket` (it is the caller's live gradient buffer) instead of overwriting it
+  unsigned* bar;          // see MmFwdArgs
 };
 #define GPBLUR_PUT(ptr, val) do { float* p_ = (ptr); const float v_ = (val); *p_ = a.accumulate ? *p_ + v_ : v_; } while (0)
 
@@ -765,6 +995,7 @@ __global__ void __launch_bounds__(kThreads, 6) stage_grad_reduce_kernel(SgReduce
 
 __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   cg::grid_group grid = cg::this_grid();
+  unsigned bar_target = 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* gsm = reinterpret_cast<double*>(smem_raw);      // tile_gemm scratch
 
@@ -812,7 +1043,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     if (i == j) sdiag[i] = s;
     T64[idx] = (double)cvec[i] * s;
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 1: Lbar = -tril( beta u^T + 2 Linv^T cS ) -> U64 ----------------
@@ -836,7 +1067,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     }
     (void)ntl;
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 2: Phi( L^T Lbar ) -> T64 (lower) ----------------
@@ -858,7 +1089,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       T64[(size_t)gi * MP + gj] = v;
     }
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 3: Tm = Phi Linv -> U64 (lower) ----------------
@@ -877,7 +1108,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     for (int i = 0; i < 4; ++i)
       U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 4: Kb = Linv^T Tm -> T64 (full) ----------------
@@ -890,7 +1121,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     for (int i = 0; i < 4; ++i)
       T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
@@ -905,7 +1136,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     }
     U64[idx] = v;
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 6: Kzz-path + a-space gradients of Z; per-(i, d) terms of d ell -------
@@ -969,7 +1200,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       t64[idx] = tval;
     }
   }
-  grid.sync();
+  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 7: final bucket (block 0) ----------------
@@ -1024,6 +1255,12 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   (void)hyp;
 }
 
+// GPBLUR_MM_COOP=1: cooperative launches + cg grid.sync() (the round-1 path) instead of plain launches + counter barrier
+bool mm_cooperative() {
+  static const int v = [] { const char* e = getenv("GPBLUR_MM_COOP"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
+
 int coop_grid(const void* func, int want, size_t smem) {
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, kThreads, smem);
@@ -1046,9 +1283,18 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
-  MmFwdArgs args{p, L, ws, kl, info, extra_jitter};
-  void* kargs[] = {&args};
+  static const int dbg_stop = [] { const char* e = getenv("GPBLUR_MM_STOP"); return e ? atoi(e) : -1; }();
+  unsigned* sync_words = reinterpret_cast<unsigned*>(ws_ptr<unsigned long long>(ws, L.stamps) + 14);   // 4 words
+  MmFwdArgs args{p, L, ws, kl, info, extra_jitter, nullptr, dbg_stop, sync_words + 1};
   ProfScope ps(ST_MM_FWD, st);
+  cudaMemsetAsync(sync_words, 0, 4 * sizeof(unsigned), st);
+  if (!mm_cooperative()) {
+    args.bar = sync_words;
+    mm_forward_kernel<<<grid, kThreads, smem, st>>>(args);
+    note_launch();
+    return check_launch("mm_forward");
+  }
+  void* kargs[] = {&args};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_forward_kernel, dim3(grid), dim3(kThreads),
                                               kargs, smem, st);
   note_launch();
@@ -1066,9 +1312,16 @@ int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* sta
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
-  MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate};
-  void* kargs[] = {&args};
+  MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate, nullptr};
   ProfScope ps(ST_MM_BWD, st);
+  if (!mm_cooperative()) {
+    args.bar = reinterpret_cast<unsigned*>(ws_ptr<unsigned long long>(stage, L.stamps) + 31);
+    cudaMemsetAsync(args.bar, 0, sizeof(unsigned), st);
+    mm_backward_kernel<<<grid, kThreads, smem, st>>>(args);
+    note_launch();
+    return check_launch("mm_backward");
+  }
+  void* kargs[] = {&args};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),
                                               kargs, smem, st);
   note_launch();

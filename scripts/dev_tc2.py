@@ -131,6 +131,10 @@ if __name__ == "__main__":
             check_fwd(*shp)
         for shp in [(8192, 24, 64, 256), (256, 192, 64, 256), (8192, 24, 64, 128), (8192, 24, 64, 512), (8192, 24, 64, 1024)]:
             time_fwd(*shp)
+    if what == "stages":                       # python scripts/dev_tc2.py stages B L D M [iters]
+        shp = tuple(int(v) for v in sys.argv[2:6])
+        time_bwd(*shp, iters=int(sys.argv[6]) if len(sys.argv) > 6 else 200)
+        sys.exit(0)
     if what == "wdbg":
         B, L, D, M = (int(v) for v in sys.argv[2:6])
         p32 = O.init_params_exercise(D, M, seed=21)

@@ -9,7 +9,7 @@ for M in (32, 128, 256, 1024):
     D, B, L = 64, 64, 24
     p = {k: v.to(dev).requires_grad_(True) for k, v in O.init_params_exercise(D, M, 1).items()}
     x = torch.randn(B * L, D, device=dev)
-    for it in range(3):
+    for it in range(int(os.environ.get("ITERS", "300"))):
         mean, var, sample, kl, info, ws = ops.svgp_forward_raw(x, p["inducing_points"].detach(), p["raw_lengthscale"].detach().reshape(-1),
             p["raw_outputscale"].detach().reshape(1), p["variational_mean"].detach(), p["variational_stddev"].detach(),
             p["weights"].detach().reshape(-1), p["bias"].detach(), 0, 0, 0, False, True)
