@@ -134,6 +134,133 @@ __device__ __forceinline__ void tile_gemm(double acc[4], const MatRef& A, int r0
   for (int i = 0; i < 4; ++i) acc[i] += At[(ty + 8 * i) * GLD + tx];
 }
 
+// ---- products of the backward M x M phases: 16 x 32 output tiles, the WHOLE k-range staged at once ----
+// FP64 runs at 64 FMA / clk / SM on B200 whether issued as DFMA or as mma.m8n8k4 (measured: one mma per 4 cycles per
+// SM, 26 cycles dependent): a 32 x 32 tile with K = 256 is 2.1 us of pure pipe time on the one SM that owns it, and
+// the phases of the backward are chains of such products separated by grid barriers.  So (1) tiles are 16 x 32: at
+// M = 256 a phase has up to 128 of them, one per SM; (2) every operand element of up to KW = 256 k-values is requested
+// up front with 8-byte cp.async copies straight into shared memory (no registers: ~100 KB in flight per CTA), in commit
+// groups of 64 k so that the mma loop starts when the first group has landed (tile_gemm() above pays one L2 round
+// trip and two CTA barriers per 32 k).
+constexpr int KW = 256;
+constexpr int PW = KW + 2;                               // pitch (doubles): fragment loads hit every bank pair twice
+template <int RT>
+constexpr size_t wide_bytes() { return (size_t)(RT + TB) * PW * sizeof(double) + KW * sizeof(double); }
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// acc[i] += sum_{k in [k0, k1)} A(r0 + ty + 8 i, k) * B(k, c0 + tx), i < RT / 8;  k0, k1 multiples of 32.
+// RT = 16 or 32 rows per tile (16: up to 128 tiles per phase at M = 256, one per SM; 32: half the operand traffic
+// per flop, for the sizes where every SM has several tiles anyway).
+//  * B may be an fp32 matrix (B.pf): staged as floats, widened when the fragment is read;
+//  * kscale != nullptr: A(r, k) is multiplied by kscale[k] (fp32, global) when the fragment is read;
+//  * rowsum != nullptr (RT doubles of shared memory): receives the row sums of the A block, fixed order.
+// `wide`: wide_bytes<RT>() of shared memory.
+template <int RT>
+__device__ __forceinline__ void wide_gemm(double (&acc)[RT / 8], const MatRef& A, int r0, const MatRef& B, int c0, int k0,
+                                          int k1, double* wide, const float* kscale = nullptr, double* rowsum = nullptr) {
+  if (k0 >= k1) return;
+  constexpr int NCB = RT / 16;                           // 8-column blocks per warp
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  double* Aw = wide;                                     // [RT rows][k]
+  double* Bw = wide + RT * PW;                           // [32 cols][k]
+  double* sc = Bw + TB * PW;                             // [k] scale of the chunk
+  float* Bf = reinterpret_cast<float*>(Bw);              // fp32 B: [col][k], pitch 2 PW floats
+  const int g = tx >> 2, t = tx & 3;
+  const int rw = RT == 16 ? 8 * (ty & 1) : 8 * (ty & 3);
+  const int cw = RT == 16 ? 8 * (ty >> 1) : 16 * (ty >> 2);
+  double c[2][NCB][2] = {};                              // [even / odd k-step][column block][element]: two mma chains
+  for (int kc = k0; kc < k1; kc += KW) {
+    const int klen = (k1 - kc) < KW ? (k1 - kc) : KW;   // multiple of 32
+    const int ngroups = (klen + 63) / 64;
+    __syncthreads();                                     // previous chunk / previous user of `wide` is done
+    if (kscale)
+      for (int k = tid; k < klen; k += kThreads) sc[k] = (double)kscale[kc + k];
+    for (int gq = 0; gq < 4; ++gq) {
+      if (gq < ngroups) {
+        const int kg0 = gq * 64, kgl = (klen - kg0) < 64 ? (klen - kg0) : 64;   // 64 or 32
+        const int sh = kgl == 64 ? 6 : 5;
+        for (int e = tid; e < RT * kgl; e += kThreads) {
+          int row, k;
+          if (!A.trans) { row = e >> sh; k = kg0 + (e & (kgl - 1)); }
+          else { k = kg0 + e / RT; row = e % RT; }
+          const size_t off = A.trans ? (size_t)(kc + k) * A.ld + r0 + row : (size_t)(r0 + row) * A.ld + kc + k;
+          cp_async8(Aw + row * PW + k, A.p + off);
+        }
+        for (int e = tid; e < TB * kgl; e += kThreads) {
+          int col, k;
+          if (B.trans) { col = e >> sh; k = kg0 + (e & (kgl - 1)); }
+          else { k = kg0 + (e >> 5); col = e & 31; }
+          const size_t off = B.trans ? (size_t)(c0 + col) * B.ld + kc + k : (size_t)(kc + k) * B.ld + c0 + col;
+          if (B.pf) cp_async4(Bf + col * (2 * PW) + k, B.pf + off);
+          else cp_async8(Bw + col * PW + k, B.p + off);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // (empty groups keep the wait counts static)
+    }
+    for (int gq = 0; gq < ngroups; ++gq) {
+      if (gq == 0) cp_async_wait<3>();
+      else if (gq == 1) cp_async_wait<2>();
+      else if (gq == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncthreads();
+      const int kg0 = gq * 64, kgl = (klen - kg0) < 64 ? (klen - kg0) : 64;
+      if (rowsum) {
+        // row sums of this k-group (rows ty, ty + 8, ...), fixed order: groups in sequence, shuffle tree inside
+#pragma unroll
+        for (int rr = 0; rr < RT / 8; ++rr) {
+          const int row = ty + 8 * rr;
+          double sacc = Aw[row * PW + kg0 + tx];
+          if (kgl == 64) sacc += Aw[row * PW + kg0 + 32 + tx];
+          sacc = warp_sum(sacc);
+          if (tx == 0) rowsum[row] = ((kc == k0 && gq == 0) ? 0.0 : rowsum[row]) + sacc;
+        }
+      }
+      const double* ap = Aw + (rw + g) * PW + t + kg0;
+      const double* sp = sc + t + kg0;
+#pragma unroll 4
+      for (int k4 = 0; k4 < kgl; k4 += 8) {
+        double a0 = ap[k4], a1 = ap[k4 + 4];
+        if (kscale) { a0 *= sp[k4]; a1 *= sp[k4 + 4]; }
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) {
+          double b0, b1;
+          if (!B.pf) {
+            const double* bp = Bw + (cw + 8 * cb + g) * PW + t + kg0;
+            b0 = bp[k4]; b1 = bp[k4 + 4];
+          } else {
+            const float* bp = Bf + (cw + 8 * cb + g) * (2 * PW) + t + kg0;
+            b0 = (double)bp[k4]; b1 = (double)bp[k4 + 4];
+          }
+          dmma884(c[0][cb][0], c[0][cb][1], a0, b0);
+          dmma884(c[1][cb][0], c[1][cb][1], a1, b1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // fragments -> the callers' (row ty + 8 i, column tx) mapping through the (now free) A buffer
+#pragma unroll
+  for (int cb = 0; cb < NCB; ++cb) {
+    Aw[(rw + g) * PW + cw + 8 * cb + 2 * t] = c[0][cb][0] + c[1][cb][0];
+    Aw[(rw + g) * PW + cw + 8 * cb + 2 * t + 1] = c[0][cb][1] + c[1][cb][1];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RT / 8; ++i) acc[i] += Aw[(ty + 8 * i) * PW + tx];
+}
+
 // decode t -> (i, j) with j <= i, t = i (i + 1) / 2 + j
 __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
   int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -993,7 +1120,10 @@ __global__ void __launch_bounds__(kThreads, 6) stage_grad_reduce_kernel(SgReduce
   (void)g_u; (void)g_vec; (void)g_S; (void)g_WX;
 }
 
+template <int RT>
 __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
+  constexpr int NH = TB / RT;   // row parts of a 32 x 32 tile
+  constexpr int NR = RT / 8;    // rows per thread
   cg::grid_group grid = cg::this_grid();
   unsigned bar_target = 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1027,8 +1157,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   const double* WX64 = S64 + (size_t)MP * MP;
   // fp64 vector scratch: [unused MP | unused vec_len | diag(S) MP | rz MP]
   double* v64 = ws_ptr<double>(a.ws, L.v64);
-  double* sdiag = v64 + MP + L.vec_len;
-  double* rz64 = sdiag + MP;
+  double* rz64 = v64 + 2 * MP + L.vec_len;
   double* t64 = ws_ptr<double>(a.ws, L.t64);   // [MP, DP] per-(i, d) terms of d lengthscale
 
   unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps) + 16;
@@ -1036,53 +1165,42 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
 #define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
   GPBLUR_STAMP();
 
-  // ---------------- phase 0: cS = diag(c) S, diag(S) ----------------
-  for (int idx = gtid; idx < MP * MP; idx += gsize) {
-    const int i = idx / MP, j = idx - i * MP;
-    const double s = S64[idx];
-    if (i == j) sdiag[i] = s;
-    T64[idx] = (double)cvec[i] * s;
-  }
-  GPBLUR_GRID_SYNC();
-
-  GPBLUR_STAMP();
-  // ---------------- phase 1: Lbar = -tril( beta u^T + 2 Linv^T cS ) -> U64 ----------------
-  {
-    const int ntl = nb * (nb + 1) / 2;
-    for (int t = blockIdx.x; t < nb * nb; t += G) {
-      const int bi = t / nb, bj = t - bi * nb;
-      if (bi < bj) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
-        continue;
-      }
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{T64, MP, false}, bj * TB, bi * TB, MP, gsm);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
-        const double g = (double)beta[gi] * u64[gj] + 2.0 * acc[i];
-        U64[(size_t)gi * MP + gj] = (gj <= gi) ? -g : 0.0;
-      }
-    }
-    (void)ntl;
-  }
-  GPBLUR_GRID_SYNC();
-
-  GPBLUR_STAMP();
-  // ---------------- phase 2: Phi( L^T Lbar ) -> T64 (lower) ----------------
-  for (int t = blockIdx.x; t < nb * nb; t += G) {
-    const int bi = t / nb, bj = t - bi * nb;
+  // Work items of the product phases: item t -> tile t / NH = (bi, bj), rows bi * 32 + RT (t % NH) .. + RT.
+  // ---------------- phase 1: Lbar = -tril( beta u^T + 2 Linv^T diag(c) S ) -> U64 ----------------
+  // (diag(c) is applied to the k index of the A operand on the fly: the former elementwise phase 0 and its barrier are gone)
+  for (int t = blockIdx.x; t < NH * nb * nb; t += G) {
+    const int tile = t / NH, bi = tile / nb, bj = tile - bi * nb, r0 = bi * TB + RT * (t % NH);
     if (bi < bj) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+      for (int i = 0; i < NR; ++i) U64[(size_t)(r0 + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
       continue;
     }
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_gemm(acc, MatRef{L64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, bi * TB, MP, gsm);
+    double acc[NR] = {};
+    wide_gemm<RT>(acc, MatRef{Li64, MP, true}, r0, MatRef{S64, MP, false}, bj * TB, bi * TB, MP, gsm, cvec);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gi = bi * TB + warp + 8 * i, gj = bj * TB + lane;
+    for (int i = 0; i < NR; ++i) {
+      const int gi = r0 + warp + 8 * i, gj = bj * TB + lane;
+      const double g = (double)beta[gi] * u64[gj] + 2.0 * acc[i];
+      U64[(size_t)gi * MP + gj] = (gj <= gi) ? -g : 0.0;
+    }
+  }
+  GPBLUR_GRID_SYNC();
+
+  GPBLUR_STAMP();
+  GPBLUR_STAMP();
+  // ---------------- phase 2: Phi( L^T Lbar ) -> T64 (lower) ----------------
+  for (int t = blockIdx.x; t < NH * nb * nb; t += G) {
+    const int tile = t / NH, bi = tile / nb, bj = tile - bi * nb, r0 = bi * TB + RT * (t % NH);
+    if (bi < bj) {
+#pragma unroll
+      for (int i = 0; i < NR; ++i) T64[(size_t)(r0 + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+      continue;
+    }
+    double acc[NR] = {};
+    wide_gemm<RT>(acc, MatRef{L64, MP, true}, r0, MatRef{U64, MP, false}, bj * TB, bi * TB, MP, gsm);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int gi = r0 + warp + 8 * i, gj = bj * TB + lane;
       double v = acc[i];
       if (gj > gi) v = 0.0;
       else if (gj == gi) v *= 0.5;
@@ -1093,93 +1211,99 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
 
   GPBLUR_STAMP();
   // ---------------- phase 3: Tm = Phi Linv -> U64 (lower) ----------------
-  for (int t = blockIdx.x; t < nb * nb; t += G) {
-    const int bi = t / nb, bj = t - bi * nb;
+  for (int t = blockIdx.x; t < NH * nb * nb; t += G) {
+    const int tile = t / NH, bi = tile / nb, bj = tile - bi * nb, r0 = bi * TB + RT * (t % NH);
     if (bi < bj) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
+      for (int i = 0; i < NR; ++i) U64[(size_t)(r0 + warp + 8 * i) * MP + bj * TB + lane] = 0.0;
       continue;
     }
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[NR] = {};
     // sum over k in [bj-tile, bi-tile]; operand zeros handle the ragged edges inside the diagonal tiles
-    tile_gemm(acc, MatRef{T64, MP, false}, bi * TB, MatRef{Li64, MP, false}, bj * TB, bj * TB,
-              (bi + 1) * TB, gsm);
+    wide_gemm<RT>(acc, MatRef{T64, MP, false}, r0, MatRef{Li64, MP, false}, bj * TB, bj * TB, (bi + 1) * TB, gsm);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      U64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
+    for (int i = 0; i < NR; ++i) U64[(size_t)(r0 + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
   }
   GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 4: Kb = Linv^T Tm -> T64 (full) ----------------
-  for (int t = blockIdx.x; t < nb * nb; t += G) {
-    const int bi = t / nb, bj = t - bi * nb;
+  for (int t = blockIdx.x; t < NH * nb * nb; t += G) {
+    const int tile = t / NH, bi = tile / nb, bj = tile - bi * nb, r0 = bi * TB + RT * (t % NH);
     const int kb0 = bi > bj ? bi : bj;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_gemm(acc, MatRef{Li64, MP, true}, bi * TB, MatRef{U64, MP, false}, bj * TB, kb0 * TB, MP, gsm);
+    double acc[NR] = {};
+    wide_gemm<RT>(acc, MatRef{Li64, MP, true}, r0, MatRef{U64, MP, false}, bj * TB, kb0 * TB, MP, gsm);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      T64[(size_t)(bi * TB + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
+    for (int i = 0; i < NR; ++i) T64[(size_t)(r0 + warp + 8 * i) * MP + bj * TB + lane] = acc[i];
   }
   GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
-  // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
   const double zz_jitter = ws_cptr<double>(a.ws, L.hyp64)[H_JIT];
-  for (int idx = gtid; idx < MP * MP; idx += gsize) {
-    const int i = idx / MP, j = idx - i * MP;
-    double v = 0.0;
-    if (i < M && j < M) {
-      const double kb = 0.5 * (T64[idx] + T64[(size_t)j * MP + i]);
-      const double kz = K64[idx] - (i == j ? zz_jitter : 0.0);
-      v = kb * kz;
+  // ---------------- phase 5: Wzz = sym(Kb) o (Kzz - jitter I) -> U64 ----------------
+  // (building Wzz on the fly while phase 6 stages its A operand was tried: the transposed read made it 2x slower)
+  {
+    for (int idx = gtid; idx < MP * MP; idx += gsize) {
+      const int i = idx / MP, j = idx - i * MP;
+      double v = 0.0;
+      if (i < M && j < M) {
+        const double kb = 0.5 * (T64[idx] + T64[(size_t)j * MP + i]);
+        const double kz = K64[idx] - (i == j ? zz_jitter : 0.0);
+        v = kb * kz;
+      }
+      U64[idx] = v;
     }
-    U64[idx] = v;
+    GPBLUR_GRID_SYNC();
   }
-  GPBLUR_GRID_SYNC();
 
   GPBLUR_STAMP();
   // ---------------- phase 6: Kzz-path + a-space gradients of Z; per-(i, d) terms of d ell -------
-  // V = Wzz Z~ is an [MP, MP] x [MP, DP] product: 32 x 32 tiles on the FP64 tensor path (a thread-per-(i, d) loop over
-  // j exposed one L2 round trip per few terms: 16 us at M = 256, 166 us at M = 1024); the row sums of Wzz come from a
-  // lane-strided pass with a fixed shuffle tree.
-  auto zgrad_terms = [&](int i, int d, double V, double rz) {
-    const double wx = WX64[(size_t)i * DP + d];
+  // V = Wzz Z~ is an [MP, MP] x [MP, DP] product: 16 x 32 tiles on the FP64 tensor path (a thread-per-(i, d) loop over
+  // j exposed one L2 round trip per few terms: 16 us at M = 256, 166 us at M = 1024); the row sums of Wzz come from
+  // the staged operand with a fixed shuffle tree.
+  auto zgrad_terms = [&](int i, int d, double V, double rz, double wx, double z, double csum) {
     const double ie = (double)inv_ell[d];
-    const double csum = vec64[i];
-    const double z = (double)Zt[(size_t)i * DP + d];
     const double wxt = (wx - csum * (double)center[d]) * ie;          // (W^T Xtilde)_id
     const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
     GPBLUR_PUT(&a.bucket[(size_t)i * D + d], (float)dz);
     return -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
   };
   if (DP >= TB) {
-    __shared__ double rz_s[TB];
+    __shared__ double rz_s[RT];
+    __shared__ double tred[8][32];
     const int ndt = DP / TB;
-    for (int t = blockIdx.x; t < nb * ndt; t += G) {
-      const int bi = t / ndt, bd = t - bi * ndt;
-      __syncthreads();
+    for (int t = blockIdx.x; t < NH * nb * ndt; t += G) {
+      const int tile = t / NH, bi = tile / ndt, bd = tile - bi * ndt, r0 = bi * TB + RT * (t % NH);
+      // operands of the epilogue, requested before the product
+      double e_wx[NR], e_z[NR], e_cs[NR];
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        const int r = warp + 8 * r4;
-        const double* urow = U64 + (size_t)(bi * TB + r) * MP;
-        double sacc = 0.0;
-        for (int j = lane; j < MP; j += 32) sacc += urow[j];
-        sacc = warp_sum(sacc);
-        if (lane == 0) rz_s[r] = sacc;
+      for (int r2 = 0; r2 < NR; ++r2) {
+        const int i = r0 + warp + 8 * r2, d = bd * TB + lane;
+        e_wx[r2] = WX64[(size_t)i * DP + d];
+        e_z[r2] = (double)Zt[(size_t)i * DP + d];
+        e_cs[r2] = vec64[i];
       }
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      tile_gemm(acc, MatRef{U64, MP, false}, bi * TB, MatRef{nullptr, DP, false, Zt}, bd * TB, 0, MP, gsm);
+      double acc[NR] = {};
+      wide_gemm<RT>(acc, MatRef{U64, MP, false}, r0, MatRef{nullptr, DP, false, Zt}, bd * TB, 0, MP, gsm, nullptr, rz_s);
+      double tsum = 0.0;
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        const int i = bi * TB + warp + 8 * r4, d = bd * TB + lane;
-        double tval = 0.0;
+      for (int r2 = 0; r2 < NR; ++r2) {
+        const int i = r0 + warp + 8 * r2, d = bd * TB + lane;
         if (i < M && d < D) {
-          const double rz = rz_s[warp + 8 * r4];
+          const double rz = rz_s[warp + 8 * r2];
           if (d == 0) rz64[i] = rz;
-          tval = zgrad_terms(i, d, acc[r4], rz);
+          tsum += zgrad_terms(i, d, acc[r2], rz, e_wx[r2], e_z[r2], e_cs[r2]);
         }
-        t64[(size_t)i * DP + d] = tval;
+      }
+      // column sums over the RT rows of the item (fixed order) -> t64[item row block][d]; phase 7 adds the NH nb blocks
+      __syncthreads();
+      tred[warp][lane] = tsum;
+      __syncthreads();
+      if (warp == 0) {
+        double tt = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tt += tred[w8][lane];
+        t64[(size_t)(NH * bi + (t % NH)) * DP + bd * TB + lane] = tt;
       }
     }
   } else {
@@ -1195,7 +1319,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
           rz += w;
         }
         if (d == 0) rz64[i] = rz;
-        tval = zgrad_terms(i, d, V, rz);
+        tval = zgrad_terms(i, d, V, rz, WX64[(size_t)i * DP + d], (double)Zt[(size_t)i * DP + d], vec64[i]);
       }
       t64[idx] = tval;
     }
@@ -1223,7 +1347,8 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
       const int d = tid % DP, part = tid / DP;
       double s = 0.0;
 #pragma unroll 8
-      for (int i = part; i < M; i += npart) s += t64[(size_t)i * DP + d];
+      const int trows = DP >= TB ? NH * nb : M;   // phase 6 leaves per-item column sums (DP >= 32) or the full terms
+      for (int i = part; i < trows; i += npart) s += t64[(size_t)i * DP + d];
       colred[tid] = s;
       __syncthreads();
       if (part == 0 && d < D) {
@@ -1237,7 +1362,7 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
     for (int m = tid; m < M; m += kThreads) {
       const double mm = (double)mvec[m], ss = (double)svec[m];
       GPBLUR_PUT(&b_m[m], (float)(u64[m] + gkl * mm));
-      GPBLUR_PUT(&b_s[m], (float)(2.0 * ss * sdiag[m] + gkl * (ss - 1.0 / ss)));
+      GPBLUR_PUT(&b_s[m], (float)(2.0 * ss * S64[(size_t)m * MP + m] + gkl * (ss - 1.0 / ss)));
     }
     if (warp == 0) {
       double s = 0.0;
@@ -1304,26 +1429,28 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate) {
-  const size_t smem = kGemmScratchDoubles * sizeof(double);
-  cudaFuncSetAttribute(mm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
   const int nb = L.MP / TB;
-  int want = nb * nb;
+  const bool half = 2 * nb * nb <= 2 * 148;       // 16-row tiles while that still gives every SM at most two of them
+  const size_t smem = half ? wide_bytes<16>() : wide_bytes<32>();
+  const void* func = half ? (const void*)mm_backward_kernel<16> : (const void*)mm_backward_kernel<32>;
+  cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
+  int want = (half ? 2 : 1) * nb * nb;
   const int dwant = (L.MP * L.DP + kThreads - 1) / kThreads;
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
-  const int grid = coop_grid((const void*)mm_backward_kernel, want, smem);
+  const int grid = coop_grid(func, want, smem);
   MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate, nullptr};
   ProfScope ps(ST_MM_BWD, st);
+  void* kargs[] = {&args};
   if (!mm_cooperative()) {
     args.bar = reinterpret_cast<unsigned*>(ws_ptr<unsigned long long>(stage, L.stamps) + 31);
     cudaMemsetAsync(args.bar, 0, sizeof(unsigned), st);
-    mm_backward_kernel<<<grid, kThreads, smem, st>>>(args);
+    cudaError_t e = cudaLaunchKernel(func, dim3(grid), dim3(kThreads), kargs, smem, st);
     note_launch();
+    if (e != cudaSuccess) return check_launch("mm_backward");
     return check_launch("mm_backward");
   }
-  void* kargs[] = {&args};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)mm_backward_kernel, dim3(grid), dim3(kThreads),
-                                              kargs, smem, st);
+  cudaError_t e = cudaLaunchCooperativeKernel(func, dim3(grid), dim3(kThreads), kargs, smem, st);
   note_launch();
   if (e != cudaSuccess) return check_launch("mm_backward");
   return GPBLUR_OK;
