@@ -38,6 +38,12 @@ ProfScope::~ProfScope() {
 
 static thread_local const unsigned long long* g_offset_dev = nullptr;
 const unsigned long long* current_offset_dev() { return g_offset_dev; }
+static thread_local const void* g_param_stage = nullptr;
+const void* current_param_stage() { return g_param_stage; }
+struct ParamStageScope {
+  explicit ParamStageScope(const void* p) { g_param_stage = p; }
+  ~ParamStageScope() { g_param_stage = nullptr; }
+};
 struct OffsetDevScope {
   explicit OffsetDevScope(const unsigned long long* p) { g_offset_dev = p; }
   ~OffsetDevScope() { g_offset_dev = nullptr; }
@@ -370,6 +376,33 @@ int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const 
     if (rc) return rc;
   }
   return launch_stage_grad_reduce(L, ws, stage_grad, st);
+}
+
+int gpblur_svgp_point_forward_shared(const void* param_stage, const float* x, long long N, int D, int M, float* mean,
+                                     float* var, float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                                     const unsigned long long* offset_dev, int training, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  OffsetDevScope ods(offset_dev);
+  if (!param_stage || (reinterpret_cast<uintptr_t>(param_stage) & 255) || N < 0 || D < 1 || M < 1) return GPBLUR_EINVAL;
+  if (D > GPBLUR_MAX_D || M > GPBLUR_MAX_M) return GPBLUR_EUNSUPPORTED;
+  if (N > 0 && (!x || !mean || !var)) return GPBLUR_EINVAL;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(N, D, M, training ? 1 : 0);
+  if (ws_bytes < L.total) return GPBLUR_EWORKSPACE;
+  if (N == 0) return GPBLUR_OK;
+  ParamStageScope pss(param_stage);
+  return dispatch_point_forward(L, ws, x, mean, var, sample, seed, offset, stream_id, (cudaStream_t)stream);
+}
+
+int gpblur_svgp_point_backward_shared(const void* param_stage, const float* x, long long N, int D, int M,
+                                      const float* g_mean, const float* g_var, const float* g_sample, const float* var,
+                                      uint64_t seed, uint64_t offset, uint32_t stream_id,
+                                      const unsigned long long* offset_dev, float* dx, double* stage_grad, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  if (!param_stage || (reinterpret_cast<uintptr_t>(param_stage) & 255)) return GPBLUR_EINVAL;
+  ParamStageScope pss(param_stage);
+  return gpblur_svgp_point_backward(x, N, D, M, g_mean, g_var, g_sample, var, seed, offset, stream_id, offset_dev, dx,
+                                    stage_grad, ws, ws_bytes, stream);
 }
 
 int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,

@@ -316,6 +316,9 @@ void note_launch(int n = 1);
 // Device-resident Philox offset addend of the entry point running on this host thread (null = none).  Set by the
 // extern "C" layer around the launchers; read when the kernel arguments are filled.
 const unsigned long long* current_offset_dev();
+// Parameter stage the point kernels of the current API call read their constant operands from (thread-local, set by
+// the gpblur_svgp_point_*_shared entry points); nullptr: the stage lives in the call's own workspace.
+const void* current_param_stage();
 __device__ __forceinline__ uint64_t rng_offset(uint64_t offset, const unsigned long long* offset_dev) {
   return offset + (offset_dev ? (uint64_t)*offset_dev : 0ull);
 }

@@ -270,12 +270,13 @@ __device__ __forceinline__ void tri_decode(int t, int& i, int& j) {
   j = t - ii * (ii + 1) / 2;
 }
 
-// Grid-wide barrier on a monotonically increasing counter (zeroed by the host before the launch): the cooperative-launch
-// API costs 10 - 25 us of launch overhead per M x M kernel on this driver, a plain launch of <= 1 CTA per SM does not.
+// Grid-wide barrier on a monotonically increasing counter (zeroed by the host before the launch), for plain launches
+// (GPBLUR_MM_COOP=0).  Measured: no faster and no slower than cooperative launches + grid.sync().
 // All CTAs are co-resident (grid <= SM count x occupancy, checked by the launcher); a CTA that cannot be scheduled yet
 // because an independent kernel holds its SM only delays the barrier.
 __device__ __forceinline__ void counter_grid_sync(unsigned* cnt, unsigned& target, int G) {
   __syncthreads();
+  if (G == 1) return;                         // a single CTA: its own global writes are visible after the CTA barrier
   if (threadIdx.x == 0) {
     target += (unsigned)G;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
@@ -493,110 +494,61 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
 #define GPBLUR_STAMP() do { if (blockIdx.x == 0 && tid == 0) stamps[stamp_i] = global_ns(); ++stamp_i; } while (0)
   GPBLUR_STAMP();
   if (a.debug_stop == 0) return;
+  if (blockIdx.x == 0 && tid == 0) *a.flags = 0u;   // worker-arrival counter of phase 2 (ordered by the phase-1 barrier)
 
-  // ---------------- phase 0: per-dimension hyper-parameters, centre, KL ----------------
-  for (int d = blockIdx.x * 8 + warp; d < DP; d += G * 8) {
-    if (d < D) {
-      const double ell = softplus64((double)a.p.raw_lengthscale[d]);
-      double s = 0.0;
-      for (int m = lane; m < M; m += 32) s += (double)Z[(size_t)m * D + d];
-      s = warp_sum(s);
-      if (lane == 0) {
-        const float c = (float)(s / (double)M);
-        center[d] = c;
-        ellv[d] = (float)ell;
-        inv_ell[d] = (float)(1.0 / ell);
-        T64[d] = 1.0 / ell;                 // fp64 copy for the Kzz build (T64 is free until phase 3b)
-        wl[d] = a.p.mean_weights ? (float)(ell * (double)a.p.mean_weights[d]) : 0.0f;
-      }
-    } else if (lane == 0) {
-      center[d] = 0.f; ellv[d] = 1.f; inv_ell[d] = 0.f; wl[d] = 0.f;
-    }
-  }
-  if (blockIdx.x == 0) {
-    // KL( N(m, diag s^2) || N(0, I) ) = 1/2 [ sum s^2 + sum m^2 - M - sum log s^2 ]
-    double part = 0.0;
-    for (int m = tid; m < M; m += kThreads) {
-      const double mm = (double)a.p.variational_mean[m];
-      const double ss = (double)a.p.variational_stddev[m];
-      part += ss * ss + mm * mm - 1.0 - log(ss * ss);
-    }
-    part = warp_sum(part);
-    __shared__ double red[8];
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int i = 0; i < 8; ++i) t += red[i];
-      const double os = softplus64((double)a.p.raw_outputscale[0]);
-      hyp[H_OS] = (float)os;
-      hyp[H_JIT] = kJitter;
-      hyp64[H_JIT] = (double)kJitter + a.extra_jitter;      // diagonal actually added to Kzz (the backward removes it)
-      hyp[H_KL] = (float)(0.5 * t);
-      hyp64[H_OS] = os;
-      hyp64[H_KL] = 0.5 * t;
-      if (a.kl) a.kl[0] = (float)(0.5 * t);
-      if (a.info) a.info[0] = 0;
-    }
-  }
-  GPBLUR_GRID_SYNC();
-  GPBLUR_STAMP();
-  if (a.debug_stop == 1) return;
-
-  // ---------------- phase 1: Zt, vectors, Kzz ----------------
-  for (int idx = gtid; idx < MP * DP; idx += gsize) {
-    const int m = idx / DP, d = idx - m * DP;
-    float v = 0.f;
-    if (m < M && d < D) v = (Z[(size_t)m * D + d] - center[d]) * inv_ell[d];
-    Zt[idx] = v;
-    ZtT[(size_t)d * MP + m] = v;
-  }
-  for (int m = gtid; m < MP; m += gsize) {
-    const float mm = m < M ? a.p.variational_mean[m] : 0.f;
-    const float ss = m < M ? a.p.variational_stddev[m] : 1.f;
-    mvec[m] = mm;
-    svec[m] = ss;
-    cvec[m] = m < M ? ss * ss - 1.0f : 0.f;
-  }
-  if (blockIdx.x == 0 && warp == 0) {
-    double s = 0.0;
-    if (a.p.mean_weights)
-      for (int d = lane; d < D; d += 32) s += (double)center[d] * (double)a.p.mean_weights[d];
-    s = warp_sum(s);
-    if (lane == 0) hyp[H_CWB] = (float)(s + (double)a.p.mean_bias[0]);
-  }
+  // ---------------- phase 1: Kzz (fp64, direct differences) | per-dimension hyper-parameters, centre, KL ----------------
+  // CTA 0 takes no part when there are other CTAs: it spends the phase warming the instruction cache for the
+  // factorisation (see phase 2)
+  const int p1_id = G > 1 ? (int)blockIdx.x - 1 : 0, p1_n = G > 1 ? G - 1 : 1;
+  // One barrier: the Kzz tiles take their 1 / lengthscale straight from the raw parameter (a softplus per thread), so
+  // nothing here waits for the hyper-parameter block; everything derived from it (Z~, vectors, Z~ operand images) is
+  // built by the worker CTAs of phase 2 while CTA 0 factorises the first diagonal block.
   {
     const double os = softplus64((double)a.p.raw_outputscale[0]);
     const int ntiles = nb * (nb + 1) / 2;
     const int tx = lane, ty = warp;
-    for (int t = blockIdx.x; t < ntiles; t += G) {
+    for (int t = p1_id; t >= 0 && t < ntiles; t += p1_n) {
       int bi, bj;
       tri_decode(t, bi, bj);
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int d0 = 0; d0 < D; d0 += TB) {
-        __syncthreads();
+      // all the rows of both blocks are requested at once (D <= 128: 4 k-steps x 4 rows x 2 blocks per thread), and
+      // the softplus of the lengthscales (a few hundred instructions) is evaluated while they are in flight
+      constexpr int kMaxSteps = GPBLUR_MAX_D / TB;
+      float za[kMaxSteps][4], zb[kMaxSteps][4];
+      double ie[kMaxSteps];
+#pragma unroll
+      for (int st = 0; st < kMaxSteps; ++st) {
+        const int d = st * TB + tx;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = ty + 8 * i;
-          const int d = d0 + tx;
-          double va = 0.0, vb = 0.0;
-          if (d < D) {
-            const double ie = T64[d];
-            const int ra = bi * TB + r, rb = bj * TB + r;
-            if (ra < M) va = (double)Z[(size_t)ra * D + d] * ie;
-            if (rb < M) vb = (double)Z[(size_t)rb * D + d] * ie;
-          }
-          As[r][tx] = va;
-          Bs[r][tx] = vb;
+          const int ra = bi * TB + ty + 8 * i, rb = bj * TB + ty + 8 * i;
+          za[st][i] = (d < D && ra < M) ? Z[(size_t)ra * D + d] : 0.f;
+          zb[st][i] = (d < D && rb < M) ? Z[(size_t)rb * D + d] : 0.f;
         }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < TB; ++k) {
-          const double b = Bs[tx][k];
+      }
+#pragma unroll
+      for (int st = 0; st < kMaxSteps; ++st) {
+        const int d = st * TB + tx;
+        ie[st] = d < D ? 1.0 / softplus64((double)a.p.raw_lengthscale[d]) : 0.0;
+      }
+#pragma unroll
+      for (int st = 0; st < kMaxSteps; ++st) {
+        if (st * TB < D) {
+          __syncthreads();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const double df = As[ty + 8 * i][k] - b;
-            acc[i] = fma(df, df, acc[i]);
+            As[ty + 8 * i][tx] = (double)za[st][i] * ie[st];
+            Bs[ty + 8 * i][tx] = (double)zb[st][i] * ie[st];
+          }
+          __syncthreads();
+#pragma unroll 8
+          for (int k = 0; k < TB; ++k) {
+            const double b = Bs[tx][k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double df = As[ty + 8 * i][k] - b;
+              acc[i] = fma(df, df, acc[i]);
+            }
           }
         }
       }
@@ -614,9 +566,131 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       }
     }
   }
-  GPBLUR_GRID_SYNC();
-  GPBLUR_STAMP();
-  if (a.debug_stop == 2) return;
+  // per-dimension hyper-parameters and the input centre: CTAs from the END of the grid first (the Kzz tiles start at 0)
+  for (int d = p1_id >= 0 ? (p1_n - 1 - p1_id) * 8 + warp : DP; d < DP; d += p1_n * 8) {
+    if (d < D) {
+      const double ell = softplus64((double)a.p.raw_lengthscale[d]);
+      double s = 0.0;
+      for (int m = lane; m < M; m += 32) s += (double)Z[(size_t)m * D + d];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float c = (float)(s / (double)M);
+        center[d] = c;
+        ellv[d] = (float)ell;
+        inv_ell[d] = (float)(1.0 / ell);
+        wl[d] = a.p.mean_weights ? (float)(ell * (double)a.p.mean_weights[d]) : 0.0f;
+      }
+    } else if (lane == 0) {
+      center[d] = 0.f; ellv[d] = 1.f; inv_ell[d] = 0.f; wl[d] = 0.f;
+    }
+  }
+  if (p1_id == p1_n - 1) {
+    // KL( N(m, diag s^2) || N(0, I) ) = 1/2 [ sum s^2 + sum m^2 - M - sum log s^2 ]
+    double part = 0.0;
+    for (int m = tid; m < M; m += kThreads) {
+      const double mm = (double)a.p.variational_mean[m];
+      const double ss = (double)a.p.variational_stddev[m];
+      part += ss * ss + mm * mm - 1.0 - log(ss * ss);
+    }
+    part = warp_sum(part);
+    __shared__ double red[8];
+    __syncthreads();
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      const double os = softplus64((double)a.p.raw_outputscale[0]);
+      hyp[H_OS] = (float)os;
+      hyp[H_JIT] = kJitter;
+      hyp64[H_JIT] = (double)kJitter + a.extra_jitter;      // diagonal actually added to Kzz (the backward removes it)
+      hyp[H_KL] = (float)(0.5 * t);
+      hyp64[H_OS] = os;
+      hyp64[H_KL] = 0.5 * t;
+      if (a.kl) a.kl[0] = (float)(0.5 * t);
+      if (a.info) a.info[0] = 0;
+    }
+  }
+  // (the barrier that ends phase 1 sits at the top of iteration kb = 0 of the phase-2 loop)
+
+  // Everything that depends only on the hyper-parameter block: Z~, Z~^T, the variational vectors, the Z~ operand images
+  // of the tensor-core kernels and the exponent offsets.  `part` of `nparts` CTAs.
+  float* zn = ws_ptr<float>(a.ws, L.zn);
+  float* znc = ws_ptr<float>(a.ws, L.znc);
+  auto split_tf32 = [](float v, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    lo = v - hi;
+  };
+  auto aux_operands = [&](int part, int nparts) {
+    const int ptid = part * kThreads + tid, psize = nparts * kThreads;
+    auto zt_of = [&](int m, int d) -> float {       // straight from the parameters: no dependence on the Zt array
+      return (m < M && d < D) ? (Z[(size_t)m * D + d] - center[d]) * inv_ell[d] : 0.f;
+    };
+    for (int idx = ptid; idx < MP * DP; idx += psize) {
+      const int m = idx / DP, d = idx - m * DP;
+      const float v = zt_of(m, d);
+      Zt[idx] = v;
+      ZtT[(size_t)d * MP + m] = v;
+    }
+    for (int m = ptid; m < MP; m += psize) {
+      const float mm = m < M ? a.p.variational_mean[m] : 0.f;
+      const float ss = m < M ? a.p.variational_stddev[m] : 1.f;
+      mvec[m] = mm;
+      svec[m] = ss;
+      cvec[m] = m < M ? ss * ss - 1.0f : 0.f;
+    }
+    if (part == 0 && warp == 0) {
+      double sdot = 0.0;
+      if (a.p.mean_weights)
+        for (int d = lane; d < D; d += 32) sdot += (double)center[d] * (double)a.p.mean_weights[d];
+      sdot = warp_sum(sdot);
+      if (lane == 0) hyp[H_CWB] = (float)(sdot + (double)a.p.mean_bias[0]);
+    }
+    // |z~_j|^2 and the exponent offsets: one warp per inducing point
+    {
+      const float l2os = (float)(log(softplus64((double)a.p.raw_outputscale[0])) * 1.4426950408889634);
+      for (int j = part * 8 + warp; j < MP; j += nparts * 8) {
+        float z2 = 0.f;
+        for (int d = lane; d < DP; d += 32) { const float v = zt_of(j, d); z2 = fmaf(v, v, z2); }
+        z2 = warp_sum(z2);
+        if (lane == 0) {
+          zn[j] = z2;
+          znc[j] = j < M ? fmaf(-0.72134752044448170f, z2, l2os) : -1e30f;
+        }
+      }
+    }
+    if (MP >= 128) {
+      const int nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
+      float* ZtQ = ws_ptr<float>(a.ws, L.ZtQ);
+      float* ZtTU = ws_ptr<float>(a.ws, L.ZtTU);
+      // Z~ images (rows m of block q of BQ rows, k = d): element (c, r, e) of image (q, ds) = Zt[q BQ + r][32 ds + 4 c + e]
+      const int BQ = tc_bq(MP), NQ = MP / BQ;
+      for (int idx = ptid; idx < NQ * nds * 8 * BQ * 4; idx += psize) {
+        const int e = idx & 3, r = (idx >> 2) % BQ, c = ((idx >> 2) / BQ) & 7, img = (idx >> 2) / (BQ * 8);
+        const int q = img / nds, ds = img - q * nds;
+        const int d = ds * 32 + c * 4 + e;
+        const float v = (d < DP) ? zt_of(q * BQ + r, d) : 0.f;
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        float* base = ZtQ + tc_zq_image(MP, nds, q, ds);
+        base[(c * BQ + r) * 4 + e] = hi;
+        base[32 * BQ + (c * BQ + r) * 4 + e] = lo;
+      }
+      // Z~^T slabs (rows d, k = m): element (c, r, e) of slab s = Zt[32 s + 4 c + e][r]
+      for (int idx = ptid; idx < nsl * 8 * dpt * 4; idx += psize) {
+        const int e = idx & 3, r = (idx >> 2) % dpt, c = ((idx >> 2) / dpt) & 7, sl = (idx >> 2) / (dpt * 8);
+        const int m = sl * 32 + c * 4 + e;
+        const float v = (r < DP) ? zt_of(m, r) : 0.f;
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        float* base = ZtTU + tc_slab_ztt(dpt, sl);
+        base[(c * dpt + r) * 4 + e] = hi;
+        base[32 * dpt + (c * dpt + r) * 4 + e] = lo;
+      }
+    }
+  };
 
   // ---------------- phase 2: blocked Cholesky (right-looking, look-ahead) + triangular inverse ----------------
   // CTA 0 owns the critical path: factorise the diagonal block (one warp, registers, 3 us) and invert it, publish
@@ -663,12 +737,27 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
   double* sL1 = opbuf + 7 * TB * GLD;    // second diagonal-block buffer (CTA 0 alternates: the next block is built while
                                          // the factor of the current one is still being written out)
   double* sC = sB;                       // CTA 0: the next diagonal block before its update
-  if (blockIdx.x == 0) {                                  // first diagonal block: one coalesced round trip
-    double dg4[4];
-    fetch_tile(dg4, MatRef{W64, MP, false}, 0, 0);
-    park_operand(sL, dg4, false);
-  }
-  for (int kb = 0; kb < nb; ++kb) {
+  // Iteration kb = -1 (CTA 0 only, DURING phase 1): the factorisation of an identity block, results discarded.  Its
+  // 33 KB of straight-line code are then in the instruction cache when the first real block arrives: the first
+  // factorisation took 6.4 us cold against 3.6 us warm.
+  for (int kb = G > 1 ? -1 : 0; kb < nb; ++kb) {
+    if (kb == 0) {
+      GPBLUR_GRID_SYNC();                                 // end of phase 1
+      GPBLUR_STAMP();
+      GPBLUR_STAMP();
+      if (a.debug_stop == 2) return;
+      if (blockIdx.x == 0) {                              // first diagonal block: one coalesced round trip
+        double dg4[4];
+        fetch_tile(dg4, MatRef{W64, MP, false}, 0, 0);
+        park_operand(sL, dg4, false);
+      } else {
+        aux_operands((int)blockIdx.x - 1, NW);            // hidden behind CTA 0's first factorisation
+      }
+    }
+    if (kb < 0) {
+      if (blockIdx.x != 0) continue;
+      for (int e = tid; e < TB * GLD; e += kThreads) sL1[e] = (e / GLD == e % GLD) ? 1.0 : 0.0;
+    }
     const int nrb = nb - kb - 1;
     const int ntr = nrb * (nrb + 1) / 2;                 // trailing tiles (tile 0 = the next diagonal block: CTA 0's)
     const int ny = nrb * (kb + 1);                       // inverse partial-sum tiles
@@ -682,7 +771,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
       double* nxt = (kb & 1) ? sL : sL1;
       __syncthreads();                                    // `cur` holds A_kk; the stores of step kb - 1 are issued
       if (kb == 0 && tid == 0) stamps[9] = global_ns();
-      if (a.debug_stop == 9 && tid == 0 && kb < 8) stamps[16 + 2 * kb] = global_ns();   // per-step probe
+      if (a.debug_stop == 9 && tid == 0 && kb >= 0 && kb < 8) stamps[16 + 2 * kb] = global_ns();   // per-step probe
       if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[16] = global_ns();
       if (a.debug_stop == 8 && tid == 0 && kb == 3) stamps[21] = global_ns();
       if (warp == 0) {
@@ -702,7 +791,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
           cur[lane * GLD + c] = arow[c];
           sD[c * GLD + lane] = xcol[c];        // xcol[r] = Dinv[r][lane]
         }
-        if (a.info) {
+        if (a.info && kb >= 0) {
           // first non-positive pivot: its column (and everything after it) is NaN / Inf or non-positive on the diagonal
           const double dg = cur[lane * GLD + lane];   // own row: written by this lane
           const unsigned badmask = __ballot_sync(0xffffffffu, !(dg > 0.0) || !(dg < 1e300));
@@ -710,7 +799,7 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         }
         if (kb == 0 && lane == 0) stamps[12] = global_ns() + (unsigned long long)(sD[0] == 12345.678);
       } else {
-        if (nrb > 0) {
+        if (nrb > 0 && kb >= 0) {
           // both tiles were last updated by workers in step kb - 1
           if (kb > 0 && tid == 32) {
             unsigned v;
@@ -729,8 +818,9 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
         }
       }
       __syncthreads();                                    // L_kk, Dinv, and the look-ahead operands are in shared memory
-      if (a.debug_stop == 9 && tid == 0 && kb < 8) stamps[17 + 2 * kb] = global_ns();
+      if (a.debug_stop == 9 && tid == 0 && kb >= 0 && kb < 8) stamps[17 + 2 * kb] = global_ns();
       if (a.debug_stop == 8 && tid == 0 && kb == 2) stamps[17] = global_ns();
+      if (kb < 0) continue;                               // warm-up iteration: nothing is published
 #pragma unroll
       for (int i = 0; i < 4; ++i) {                       // write-once outputs: diagonal blocks of L and of L^-1
         const int r = warp + 8 * i;
@@ -865,103 +955,57 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
     }
     w_arrived_prev += (unsigned)(n_items < NW ? n_items : NW);
   }
-  GPBLUR_GRID_SYNC();   // L, L^-1 complete and visible
+  if (NW == 0) aux_operands(0, 1);
+  GPBLUR_GRID_SYNC();   // L, L^-1 and the auxiliary operands complete and visible
 
   GPBLUR_STAMP();   // (the slot of the former recursive-doubling inverse phase: now ~0)
   if (a.debug_stop == 3) return;
   GPBLUR_STAMP();
   GPBLUR_STAMP();
-  // ---------------- phase 4: fp32 operands ----------------
-  for (int t = blockIdx.x; t < nb * nb; t += G) {
-    const int bi = t / nb, bj = t - bi * nb;
-    __syncthreads();
-    if (bi >= bj) load_tile(As, MatRef{Li64, MP, false}, bi * TB, bj * TB);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = warp + 8 * i;
-      // LC32 tile (bi, bj): element (r, lane)
-      const int gi = bi * TB + r, gj = bj * TB + lane;
-      float v = 0.f;
-      if (bi >= bj && gj <= gi) v = (float)As[r][lane];
-      LC32[(size_t)gi * MP + gj] = v * cvec[gi];
-      Linv32[(size_t)gi * MP + gj] = v;
-      // LinvT32 tile (bj, bi): element (r, lane) = Linv[bi*TB + lane][bj*TB + r]
-      const int ti = bi * TB + lane, tj = bj * TB + r;
-      float vt = 0.f;
-      if (bi >= bj && tj <= ti) vt = (float)As[lane][r];
-      LinvT32[(size_t)tj * MP + ti] = vt;
-      LCT32[(size_t)tj * MP + ti] = vt * cvec[ti];
-    }
-  }
-  GPBLUR_STAMP();
-  // ---- constant operands of the tensor-core kernels, pre-split into TF32 hi / lo UMMA slab images ----
-  if (MP >= 128) {
-    auto split = [](float v, float& hi, float& lo) {
-      uint32_t h;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-      hi = __uint_as_float(h);
-      lo = v - hi;
-    };
-    const int nsl = MP / 32, nds = DP >= 32 ? DP / 32 : 1, dpt = DP < 32 ? 32 : DP;
+  // ---------------- phase 4: fp32 operands, TF32 operand images of Linv, beta - ONE pass over disjoint CTA groups -------
+  // units: [nb^2 fp32 tiles | (n_fwd + n_bwd) * parts image parts | MP / 32 beta chunks]; a CTA takes units
+  // blockIdx.x, + G, ...: with G >= the unit count (launch_mm_forward) every CTA has one, and the three kinds of work -
+  // one L2 round trip each - overlap instead of queueing behind each other (they took 1.1 + 4.6 + 2.6 us in sequence).
+  {
+    const int nsl = MP / 32;
     const int BW = tc_bw(MP), NP = MP / BW, spb = BW / 32;
-    float* ZtU = ws_ptr<float>(a.ws, L.ZtU);
+    const int BT = tc_bq(MP), NPT = MP / BT, spt = BT / 32;
+    const int n_fwd = MP >= 128 ? spb * NP * (NP + 1) / 2 : 0;
+    const int n_bwd = MP >= 128 ? NPT * nsl - spt * NPT * (NPT - 1) / 2 : 0;
+    const int n_tiles = nb * nb, n_beta = MP / 32;
+    int parts = n_fwd + n_bwd > 0 ? (G - n_tiles - n_beta) / (n_fwd + n_bwd) : 1;
+    parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+    const int n_img = (n_fwd + n_bwd) * parts;
     float* LinvU = ws_ptr<float>(a.ws, L.LinvU);
-    float* LCTU = ws_ptr<float>(a.ws, L.LCTU);
-    float* ZtTU = ws_ptr<float>(a.ws, L.ZtTU);
-    // Z~ images (rows m of block q, k = d):   element (c, r, e) of image (q, ds) = Zt[q BW + r][32 ds + 4 c + e]
-    for (int idx = gtid; idx < NP * nds * 8 * BW * 4; idx += gsize) {
-      const int e = idx & 3, r = (idx >> 2) % BW, c = ((idx >> 2) / BW) & 7, img = (idx >> 2) / (BW * 8);
-      const int q = img / nds, ds = img - q * nds;
-      const int d = ds * 32 + c * 4 + e;
-      const float v = (d < DP) ? Zt[(size_t)(q * BW + r) * DP + d] : 0.f;
-      float hi, lo;
-      split(v, hi, lo);
-      float* base = ZtU + tc_zt_image(MP, nds, q, ds);
-      base[(c * BW + r) * 4 + e] = hi;
-      base[32 * BW + (c * BW + r) * 4 + e] = lo;
-    }
-    // the same values in row blocks of BQ = tc_bq(MP) (TS-form point kernels)
-    {
-      float* ZtQ = ws_ptr<float>(a.ws, L.ZtQ);
-      const int BQ = tc_bq(MP), NQ = MP / BQ;
-      for (int idx = gtid; idx < NQ * nds * 8 * BQ * 4; idx += gsize) {
-        const int e = idx & 3, r = (idx >> 2) % BQ, c = ((idx >> 2) / BQ) & 7, img = (idx >> 2) / (BQ * 8);
-        const int q = img / nds, ds = img - q * nds;
-        const int d = ds * 32 + c * 4 + e;
-        const float v = (d < DP) ? Zt[(size_t)(q * BQ + r) * DP + d] : 0.f;
-        float hi, lo;
-        split(v, hi, lo);
-        float* base = ZtQ + tc_zq_image(MP, nds, q, ds);
-        base[(c * BQ + r) * 4 + e] = hi;
-        base[32 * BQ + (c * BQ + r) * 4 + e] = lo;
-      }
-    }
-    // Z~^T slabs (rows d, k = m): element (c, r, e) of slab s = Zt[32 s + 4 c + e][r]
-    for (int idx = gtid; idx < nsl * 8 * dpt * 4; idx += gsize) {
-      const int e = idx & 3, r = (idx >> 2) % dpt, c = ((idx >> 2) / dpt) & 7, sl = (idx >> 2) / (dpt * 8);
-      const int m = sl * 32 + c * 4 + e;
-      const float v = (r < DP) ? Zt[(size_t)m * DP + r] : 0.f;
-      float hi, lo;
-      split(v, hi, lo);
-      float* base = ZtTU + tc_slab_ztt(dpt, sl);
-      base[(c * dpt + r) * 4 + e] = hi;
-      base[32 * dpt + (c * dpt + r) * 4 + e] = lo;
-    }
-    // Linv images (forward): image (p, s) holds rows i = ilo + r, ilo = max(p BW, 32 s), k = j = 32 s + 4 c + e
-    // (diag(c) Linv)^T images (backward): image (p, s) holds rows j = p BW + r, k = i = 32 s + 4 c + e
-    // One image per CTA at a time, the threads stride over its elements with independent loads in flight (a grid-wide
-    // strided loop PER IMAGE cost one exposed L2 round trip per image: 8 us at M = 256, 88 us at M = 1024).
-    {
-      // forward images (output blocks of BW = tc_bw(MP)) and backward images (column blocks of BT = tc_bq(MP))
-      float* LCTQ = ws_ptr<float>(a.ws, L.LCTQ);
-      const int BT = tc_bq(MP), NPT = MP / BT, spt = BT / 32;
-      const int n_fwd = spb * NP * (NP + 1) / 2;
-      const int n_bwd = NPT * nsl - spt * NPT * (NPT - 1) / 2;
-      int parts = G / (n_fwd + n_bwd);              // few images (M = 256: 20): several CTAs share one image
-      parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
-      for (int unit = blockIdx.x; unit < (n_fwd + n_bwd) * parts; unit += G) {
-        const int img = unit / parts, part = unit - img * parts;
+    float* LCTQ = ws_ptr<float>(a.ws, L.LCTQ);
+    __shared__ double bred[8][32];
+    for (int unit = blockIdx.x; unit < n_tiles + n_img + n_beta; unit += G) {
+      if (unit < n_tiles) {
+        const int bi = unit / nb, bj = unit - bi * nb;
+        __syncthreads();
+        if (bi >= bj) load_tile(As, MatRef{Li64, MP, false}, bi * TB, bj * TB);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * i;
+          // LC32 tile (bi, bj): element (r, lane)
+          const int gi = bi * TB + r, gj = bj * TB + lane;
+          float v = 0.f;
+          if (bi >= bj && gj <= gi) v = (float)As[r][lane];
+          LC32[(size_t)gi * MP + gj] = v * cvec[gi];
+          Linv32[(size_t)gi * MP + gj] = v;
+          // LinvT32 tile (bj, bi): element (r, lane) = Linv[bi*TB + lane][bj*TB + r]
+          const int ti = bi * TB + lane, tj = bj * TB + r;
+          float vt = 0.f;
+          if (bi >= bj && tj <= ti) vt = (float)As[lane][r];
+          LinvT32[(size_t)tj * MP + ti] = vt;
+          LCT32[(size_t)tj * MP + ti] = vt * cvec[ti];
+        }
+      } else if (unit < n_tiles + n_img) {
+        // Linv images (forward): image (p, s) holds rows i = ilo + r, ilo = max(p BW, 32 s), k = j = 32 s + 4 c + e
+        // (diag(c) Linv)^T images (backward): image (p, s) holds rows j = p BT + r, k = i = 32 s + 4 c + e
+        const int iu = unit - n_tiles;
+        const int img = iu / parts, part = iu - img * parts;
         const bool fwd_img = img < n_fwd;
         int rem = fwd_img ? img : img - n_fwd, pp = 0;
         while (true) {
@@ -986,47 +1030,33 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
             v = (j <= i) ? (float)Li64[(size_t)i * MP + j] * cvec[i] : 0.f;
           }
           float hi, lo;
-          split(v, hi, lo);
+          split_tf32(v, hi, lo);
           base[(c * nr + r) * 4 + e] = hi;
           base[32 * nr + (c * nr + r) * 4 + e] = lo;
+        }
+      } else {
+        // beta = Linv^T m : one unit per 32-column chunk, lanes = columns (coalesced rows), the 8 warps split the rows
+        const int cj = unit - n_tiles - n_img;
+        const int j = cj * 32 + lane;
+        double sacc = 0.0;
+#pragma unroll 4
+        for (int i = cj * 32 + warp; i < M; i += 8)
+          if (i >= j) sacc = fma(Li64[(size_t)i * MP + j], (double)mvec[i], sacc);
+        __syncthreads();
+        bred[warp][lane] = sacc;
+        __syncthreads();
+        if (warp == 0) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) t += bred[w][lane];
+          beta[j] = (float)t;
         }
       }
     }
   }
   GPBLUR_STAMP();
-  float* zn = ws_ptr<float>(a.ws, L.zn);
-  float* znc = ws_ptr<float>(a.ws, L.znc);
-  // beta = Linv^T m : one CTA per 32-column chunk, lanes = columns (coalesced rows), the 8 warps split the rows
-  {
-    __shared__ double bred[8][32];
-    for (int cj = blockIdx.x; cj < MP / 32; cj += G) {
-      const int j = cj * 32 + lane;
-      double sacc = 0.0;
-      for (int i = cj * 32 + warp; i < M; i += 8)
-        if (i >= j) sacc = fma(Li64[(size_t)i * MP + j], (double)mvec[i], sacc);
-      __syncthreads();
-      bred[warp][lane] = sacc;
-      __syncthreads();
-      if (warp == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += bred[w][lane];
-        beta[j] = (float)t;
-      }
-    }
-  }
+  GPBLUR_STAMP();
   if (blockIdx.x == 0 && tid == 0) stamps[13] = global_ns();
-  // |z~_j|^2 : one warp per inducing point
-  for (int j = blockIdx.x * 8 + warp; j < MP; j += G * 8) {
-    float z2 = 0.f;
-    for (int d = lane; d < DP; d += 32) { const float v = Zt[(size_t)j * DP + d]; z2 = fmaf(v, v, z2); }
-    z2 = warp_sum(z2);
-    if (lane == 0) {
-      zn[j] = z2;
-      const float l2os = (float)(log(softplus64((double)a.p.raw_outputscale[0])) * 1.4426950408889634);
-      znc[j] = j < M ? fmaf(-0.72134752044448170f, z2, l2os) : -1e30f;
-    }
-  }
   GPBLUR_STAMP();
 #undef GPBLUR_STAMP
 }
@@ -1380,9 +1410,11 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   (void)hyp;
 }
 
-// GPBLUR_MM_COOP=1: cooperative launches + cg grid.sync() (the round-1 path) instead of plain launches + counter barrier
+// Cooperative launches + cg grid.sync() by default.  GPBLUR_MM_COOP=0: plain launches + a counter barrier on a word
+// that a memset node zeroes before every launch - the kernels run equally fast, but each memset is one more graph node
+// (~3.5 us) on the critical path of a step.
 bool mm_cooperative() {
-  static const int v = [] { const char* e = getenv("GPBLUR_MM_COOP"); return e ? atoi(e) : 0; }();
+  static const int v = [] { const char* e = getenv("GPBLUR_MM_COOP"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
 
@@ -1403,18 +1435,24 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   // per-DEVICE attribute: set on every launch (cheap) instead of a process-wide flag
   cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nb = L.MP / TB;
-  int want = nb * nb;
-  const int dwant = (L.MP * L.DP + kThreads * 4 - 1) / (kThreads * 4);
-  if (want < dwant) want = dwant;
+  // CTA 0 (the factorisation chain) + workers, and enough CTAs that the final pass (fp32 tiles | operand images | beta
+  // chunks) gives each of them one unit
+  int n_img = 0;
+  if (L.MP >= 128) {
+    const int nsl = L.MP / 32, BW = tc_bw(L.MP), NP = L.MP / BW, spb = BW / 32, BT = tc_bq(L.MP), NPT = L.MP / BT, spt = BT / 32;
+    n_img = spb * NP * (NP + 1) / 2 + NPT * nsl - spt * NPT * (NPT - 1) / 2;
+  }
+  int want = nb * nb + nb + 3 * n_img;
+  if (want < 8) want = 8;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
   static const int dbg_stop = [] { const char* e = getenv("GPBLUR_MM_STOP"); return e ? atoi(e) : -1; }();
   unsigned* sync_words = reinterpret_cast<unsigned*>(ws_ptr<unsigned long long>(ws, L.stamps) + 14);   // 4 words
   MmFwdArgs args{p, L, ws, kl, info, extra_jitter, nullptr, dbg_stop, sync_words + 1};
   ProfScope ps(ST_MM_FWD, st);
-  cudaMemsetAsync(sync_words, 0, 4 * sizeof(unsigned), st);
   if (!mm_cooperative()) {
     args.bar = sync_words;
+    cudaMemsetAsync(sync_words, 0, sizeof(unsigned), st);
     mm_forward_kernel<<<grid, kThreads, smem, st>>>(args);
     note_launch();
     return check_launch("mm_forward");
@@ -1430,7 +1468,9 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate) {
   const int nb = L.MP / TB;
-  const bool half = 2 * nb * nb <= 2 * 148;       // 16-row tiles while that still gives every SM at most two of them
+  // 16-row tiles while that still gives every SM at most two of them; a single 32 x 32 block runs on ONE CTA (32-row
+  // tile), where the seven grid barriers are CTA barriers
+  const bool half = nb > 1 && 2 * nb * nb <= 2 * 148;
   const size_t smem = half ? wide_bytes<16>() : wide_bytes<32>();
   const void* func = half ? (const void*)mm_backward_kernel<16> : (const void*)mm_backward_kernel<32>;
   cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device
@@ -1438,6 +1478,7 @@ int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* sta
   const int dwant = (L.MP * L.DP + kThreads - 1) / kThreads;
   if (want < dwant) want = dwant;
   if (want > 148) want = 148;
+  if (nb == 1) want = 1;
   const int grid = coop_grid(func, want, smem);
   MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate, nullptr};
   ProfScope ps(ST_MM_BWD, st);

@@ -56,16 +56,16 @@ __global__ void __launch_bounds__(kThreads, Cfg::TN <= 64 ? 2 : 1) point_bwd_ker
   float* dpart = dred + DP;                       // [NPART][DP] = 256 floats
   float* sc_s = dpart + 256;                   // [16] scalar accumulators
 
-  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
-  const float* ellv = ws_cptr<float>(a.ws, L.ell);
-  const float* center = ws_cptr<float>(a.ws, L.center);
-  const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const float* Zt = ws_cptr<float>(a.ws, L.Zt);
-  const float* ZtT = ws_cptr<float>(a.ws, L.ZtT);
-  const float* zn = ws_cptr<float>(a.ws, L.zn);
-  const float* beta = ws_cptr<float>(a.ws, L.beta);
-  const float* LC = ws_cptr<float>(a.ws, L.LC32);
+  const float* hyp = ws_cptr<float>(a.stage, L.hyp);
+  const float* inv_ell = ws_cptr<float>(a.stage, L.inv_ell);
+  const float* ellv = ws_cptr<float>(a.stage, L.ell);
+  const float* center = ws_cptr<float>(a.stage, L.center);
+  const float* wl = ws_cptr<float>(a.stage, L.wl);
+  const float* Zt = ws_cptr<float>(a.stage, L.Zt);
+  const float* ZtT = ws_cptr<float>(a.stage, L.ZtT);
+  const float* zn = ws_cptr<float>(a.stage, L.zn);
+  const float* beta = ws_cptr<float>(a.stage, L.beta);
+  const float* LC = ws_cptr<float>(a.stage, L.LC32);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* vecpart = ws_ptr<float>(a.ws, L.vecpart);

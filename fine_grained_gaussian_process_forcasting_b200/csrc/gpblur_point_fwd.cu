@@ -29,15 +29,15 @@ __global__ void __launch_bounds__(kThreads, Cfg::PT <= 4 ? 2 : 1) point_fwd_kern
   float* mu_s = xw_s + TN;                // [TN]
   float* vv_s = mu_s + TN;                // [TN]
 
-  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
-  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
-  const float* center = ws_cptr<float>(a.ws, L.center);
-  const float* wl = ws_cptr<float>(a.ws, L.wl);
-  const float* ZtT = ws_cptr<float>(a.ws, L.ZtT);
-  const float* zn = ws_cptr<float>(a.ws, L.zn);
-  const float* mvec = ws_cptr<float>(a.ws, L.mvec);
-  const float* cvec = ws_cptr<float>(a.ws, L.cvec);
-  const float* LinvT = ws_cptr<float>(a.ws, L.LinvT32);
+  const float* hyp = ws_cptr<float>(a.stage, L.hyp);
+  const float* inv_ell = ws_cptr<float>(a.stage, L.inv_ell);
+  const float* center = ws_cptr<float>(a.stage, L.center);
+  const float* wl = ws_cptr<float>(a.stage, L.wl);
+  const float* ZtT = ws_cptr<float>(a.stage, L.ZtT);
+  const float* zn = ws_cptr<float>(a.stage, L.zn);
+  const float* mvec = ws_cptr<float>(a.stage, L.mvec);
+  const float* cvec = ws_cptr<float>(a.stage, L.cvec);
+  const float* LinvT = ws_cptr<float>(a.stage, L.LinvT32);
   float* Ag = ws_ptr<float>(a.ws, L.A);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -207,7 +207,7 @@ int dispatch_fwd_tn(const PointFwdArgs& a, cudaStream_t st) {
 int launch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
                          uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
   if (L.N <= 0) return GPBLUR_OK;
-  PointFwdArgs a{L, ws, x, mean, var, sample, seed, offset, stream_id, 0, current_offset_dev()};
+  PointFwdArgs a{L, ws, current_param_stage() ? current_param_stage() : ws, x, mean, var, sample, seed, offset, stream_id, 0, current_offset_dev()};
   if (L.MP == 32) return dispatch_fwd_tn<4, 32>(a, st);
   if (L.MP == 64) return dispatch_fwd_tn<4, 64>(a, st);
   return dispatch_fwd_tn<8, 128>(a, st);

@@ -46,6 +46,7 @@ constexpr int kMaxDs = 4;       // d-slabs of the x tile (D <= 128)
 struct Tc2Args {
   WsLayout L;
   void* ws;
+  const void* stage;   // parameter stage (== ws when the stage was built in / copied into the workspace)
   const float* x;
   float* mean;
   float* var;
@@ -330,8 +331,8 @@ __device__ __forceinline__ int fwd_table(Slab* tab, const Tc2Args& a, int nthrea
   const WsLayout& L = a.L;
   const int MP = L.MP, NPO = MP / BWO, SPQ = BQ / KT, QPB = BWO / BQ;
   const int nds = L.DP >= KT ? L.DP / KT : 1;
-  const float* ZtQ = ws_cptr<float>(a.ws, L.ZtQ);
-  const float* LinvU = ws_cptr<float>(a.ws, L.LinvU);
+  const float* ZtQ = ws_cptr<float>(a.stage, L.ZtQ);
+  const float* LinvU = ws_cptr<float>(a.stage, L.LinvU);
   const int per = nds + SPQ;
   const int total = QPB * NPO * (NPO + 1) / 2 * per;
   for (int i = threadIdx.x; i < total; i += nthreads) {
@@ -388,14 +389,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc2_fwd_kernel(Tc2Args a) {
   const int MP = L.MP, NPO = MP / BWO;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
+  const float* hyp = ws_cptr<float>(a.stage, L.hyp);
   float* Ag = ws_ptr<float>(a.ws, L.A);
-  const float* znc_g = ws_cptr<float>(a.ws, L.znc);
-  const float* mvec_g = ws_cptr<float>(a.ws, L.mvec);
-  const float* cvec_g = ws_cptr<float>(a.ws, L.cvec);
-  const float* center = ws_cptr<float>(a.ws, L.center);
-  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
-  const float* wl = ws_cptr<float>(a.ws, L.wl);
+  const float* znc_g = ws_cptr<float>(a.stage, L.znc);
+  const float* mvec_g = ws_cptr<float>(a.stage, L.mvec);
+  const float* cvec_g = ws_cptr<float>(a.stage, L.cvec);
+  const float* center = ws_cptr<float>(a.stage, L.center);
+  const float* inv_ell = ws_cptr<float>(a.stage, L.inv_ell);
+  const float* wl = ws_cptr<float>(a.stage, L.wl);
   const int DP = L.DP, D = L.D;
   const int nds = DP >= KT ? DP / KT : 1;
 
@@ -688,9 +689,9 @@ __device__ __forceinline__ int bwd_table(Slab* tab, const Tc2Args& a, int nthrea
   const WsLayout& L = a.L;
   const int MP = L.MP, NP = MP / BT, SPB = BT / KT, NSL = MP / KT;
   const int nds = L.DP >= KT ? L.DP / KT : 1;
-  const float* ZtQ = ws_cptr<float>(a.ws, L.ZtQ);
-  const float* LCTQ = ws_cptr<float>(a.ws, L.LCTQ);
-  const float* ZtTU = ws_cptr<float>(a.ws, L.ZtTU);
+  const float* ZtQ = ws_cptr<float>(a.stage, L.ZtQ);
+  const float* LCTQ = ws_cptr<float>(a.stage, L.LCTQ);
+  const float* ZtTU = ws_cptr<float>(a.stage, L.ZtTU);
   int total = 0;
   for (int p = 0; p < NP; ++p) total += (NSL - p * SPB) + nds + SPB;
   for (int i = threadIdx.x; i < total; i += nthreads) {
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc2_bwd_kernel(Tc2Args a) {
   const int MP = L.MP, NP = MP / BT, NSL = MP / KT;
   const long long N = L.N;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* hyp = ws_cptr<float>(a.ws, L.hyp);
+  const float* hyp = ws_cptr<float>(a.stage, L.hyp);
   const float* Ag = ws_cptr<float>(a.ws, L.A);
   float* Wg = ws_ptr<float>(a.ws, L.W);
   float* gsc = ws_ptr<float>(a.ws, L.gsc);
@@ -812,11 +813,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc2_bwd_kernel(Tc2Args a) {
   float* xt_s = wl_s + DXW;          // [128][XP] scaled inputs of the tile
   float* stg_s = xt_s + TNP * XP;    // [8][32][SP]
   {
-    const float* znc_g = ws_cptr<float>(a.ws, L.znc);
-    const float* beta_g = ws_cptr<float>(a.ws, L.beta);
-    const float* center = ws_cptr<float>(a.ws, L.center);
-    const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
-    const float* wl = ws_cptr<float>(a.ws, L.wl);
+    const float* znc_g = ws_cptr<float>(a.stage, L.znc);
+    const float* beta_g = ws_cptr<float>(a.stage, L.beta);
+    const float* center = ws_cptr<float>(a.stage, L.center);
+    const float* inv_ell = ws_cptr<float>(a.stage, L.inv_ell);
+    const float* wl = ws_cptr<float>(a.stage, L.wl);
     for (int i = tid; i < MP; i += kCtaThreads) { znc_s[i] = znc_g[i]; beta_s[i] = beta_g[i]; }
     for (int i = tid; i < DXW; i += kCtaThreads) {
       const bool ok = i < DP;
@@ -1134,7 +1135,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc2_bwd_kernel(Tc2Args a) {
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
       float* vp = vecpart + (size_t)blockIdx.x * L.vec_len;
-      const float* ellv = ws_cptr<float>(a.ws, L.ell);
+      const float* ellv = ws_cptr<float>(a.stage, L.ell);
       float sgm = 0.f;
       for (int w = 0; w < 4; ++w) sgm += sc_s[w][VS_GMU];                 // k-half 0 warps, fixed order
       for (int i = et; i < MP; i += kGroup) vp[i] = 0.f;
@@ -1201,7 +1202,7 @@ int tc_vector_partials(const WsLayout& L) { return tc2_grid(L); }
 int launch_tc_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var, float* sample,
                             uint64_t seed, uint64_t offset, uint32_t stream_id, cudaStream_t st) {
   Tc2Args a{};
-  a.L = L; a.ws = ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
+  a.L = L; a.ws = ws; a.stage = current_param_stage() ? current_param_stage() : ws; a.x = x; a.mean = mean; a.var = var; a.sample = sample;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.trace = debug_trace_buffer();
@@ -1217,7 +1218,7 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
                              const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
                              uint32_t stream_id, float* dx, cudaStream_t st) {
   Tc2Args a{};
-  a.L = L; a.ws = ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
+  a.L = L; a.ws = ws; a.stage = current_param_stage() ? current_param_stage() : ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.trace = debug_trace_buffer();

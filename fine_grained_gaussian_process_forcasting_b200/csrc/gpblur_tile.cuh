@@ -84,6 +84,7 @@ __device__ __forceinline__ void stage_points(float* dst, const float* __restrict
 struct PointFwdArgs {
   WsLayout L;
   void* ws;
+  const void* stage;   // parameter stage (== ws when the stage was built in / copied into the workspace)
   const float* x;
   float* mean;
   float* var;
@@ -97,6 +98,7 @@ struct PointFwdArgs {
 struct PointBwdArgs {
   WsLayout L;
   void* ws;
+  const void* stage;   // parameter stage (== ws when the stage was built in / copied into the workspace)
   const float* x;
   const float* g_mean;
   const float* g_var;

@@ -277,18 +277,21 @@ def point_forward_raw(stage: Tensor, x: Tensor, M: int, seed: int, offset: int, 
     if ws is None:
         ws = torch.empty(workspace_bytes(N, D, M, training), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().gpblur_svgp_point_forward(
+        # "_shared": the kernels read the stage in place (no device-to-device copy of it into `ws`)
+        rc = _cabi.lib().gpblur_svgp_point_forward_shared(
             _ptr(stage), _ptr(x), N, D, M, _ptr(mean), _ptr(var), _ptr(sample),
             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, _ptr(offset_dev),
             int(training), _ptr(ws), ws.numel(), _stream())
-    _cabi.check(rc, "gpblur_svgp_point_forward")
+    _cabi.check(rc, "gpblur_svgp_point_forward_shared")
     return mean, var, sample, ws
 
 
 def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, offset, stream_id, ws,
                        need_dx: bool = True, dx: Optional[Tensor] = None, sgrad: Optional[Tensor] = None,
-                       offset_dev: Optional[Tensor] = None):
-    """-> (dx [N, D] | None, stage_grad float64 [stage_grad_doubles(D, M)])."""
+                       offset_dev: Optional[Tensor] = None, stage: Optional[Tensor] = None):
+    """-> (dx [N, D] | None, stage_grad float64 [stage_grad_doubles(D, M)]).
+    `stage`: the parameter stage the matching point_forward_raw call read (None: the stage was built in `ws` itself by
+    svgp_forward_raw)."""
     _need_cuda(x, ws, g_mean, g_var, g_sample, var)
     N, D = x.shape
     dev = x.device
@@ -297,10 +300,13 @@ def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, of
     if sgrad is None:
         sgrad = torch.empty(stage_grad_doubles(D, M), device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().gpblur_svgp_point_backward(
-            _ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(var),
-            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, _ptr(offset_dev),
-            _ptr(dx if need_dx else None), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
+        args = (_ptr(x), N, D, M, _ptr(g_mean), _ptr(g_var), _ptr(g_sample), _ptr(var),
+                seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF, _ptr(offset_dev),
+                _ptr(dx if need_dx else None), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
+        if stage is not None:
+            rc = _cabi.lib().gpblur_svgp_point_backward_shared(_ptr(stage), *args)
+        else:
+            rc = _cabi.lib().gpblur_svgp_point_backward(*args)
     _cabi.check(rc, "gpblur_svgp_point_backward")
     return (dx if need_dx else None), sgrad
 
@@ -510,6 +516,7 @@ class _PointFunction(torch.autograd.Function):
             fork.join()
         if training:
             ctx.save_for_backward(x2, out, *wss)
+            ctx.stage = stage                                  # read in place by the backward kernels
         ctx.meta = (seed, offset, stream_id, M, shape, H, batched, nout, hs)
         ctx.offset_dev = offset_dev
         ctx.set_materialize_grads(False)
@@ -551,7 +558,7 @@ class _PointFunction(torch.autograd.Function):
                 point_backward_raw(x2, M, None if gm is None else gm[h], None if gv is None else gv[h],
                                    None if gs is None else gs[h], out[h, N:2 * N], seed, offset + h * hs, stream_id,
                                    wss[h], need_dx=need[0], dx=None if dx is None else dx[h], sgrad=sgrad[h],
-                                   offset_dev=ctx.offset_dev)
+                                   offset_dev=ctx.offset_dev, stage=ctx.stage[h])
         finally:
             fork.join()
         if dx is not None:

@@ -127,6 +127,19 @@ int gpblur_svgp_point_backward(const float* x, long long N, int D, int M, const 
                                uint64_t seed, uint64_t offset, uint32_t stream_id,
                                const unsigned long long* offset_dev, float* dx, double* stage_grad,
                                void* ws, size_t ws_bytes, void* stream);
+/* The same pair WITHOUT the copy of the stage into `ws`: the kernels read their constant operands (Z~ / Linv operand
+ * images, vectors, hyper-parameters) straight from `param_stage`, which must stay valid and unchanged until the
+ * matching backward call has run; `ws` only holds the per-call buffers (its stage prefix is left untouched).  One
+ * device-to-device copy of the whole stage (4.7 MB at M = 256: ~10 us) less per call. */
+int gpblur_svgp_point_forward_shared(const void* param_stage, const float* x, long long N, int D, int M,
+                                     float* mean, float* var, float* sample, uint64_t seed, uint64_t offset,
+                                     uint32_t stream_id, const unsigned long long* offset_dev, int training,
+                                     void* ws, size_t ws_bytes, void* stream);
+int gpblur_svgp_point_backward_shared(const void* param_stage, const float* x, long long N, int D, int M,
+                                      const float* g_mean, const float* g_var, const float* g_sample,
+                                      const float* var, uint64_t seed, uint64_t offset, uint32_t stream_id,
+                                      const unsigned long long* offset_dev, float* dx, double* stage_grad,
+                                      void* ws, size_t ws_bytes, void* stream);
 /* gpblur_svgp_param_stage_backward with `accumulate` != 0: the gradients are ADDED to `grad_bucket`, which then is
  * the caller's live flat gradient buffer (what the data-parallel all-reduce operates on) - no intermediate bucket
  * and no per-parameter accumulation kernels on the framework side. */

@@ -29,10 +29,10 @@ else:
     mean, var, sample, ws = ops.point_forward_raw(stage, x, M, 1, 0, 0, True, True)
     gm = torch.randn(N, device=dev); gv = torch.randn(N, device=dev)
     for _ in range(2):
-        ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws)
+        ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws, stage=stage)
     torch.cuda.synchronize()
     _cabi.lib().gpblur_debug_set_trace(C.c_void_p(buf.data_ptr()))
-    ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws)
+    ops.point_backward_raw(x, M, gm, gv, None, var, 1, 0, 0, ws, stage=stage)
     torch.cuda.synchronize()
     _cabi.lib().gpblur_debug_set_trace(None)
 t = buf.cpu()
