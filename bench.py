@@ -75,8 +75,8 @@ def stage_work(stage: str, N: int, D: int, M: int):
     """(algorithmic bytes, algorithmic flops) of one launch of `stage` over N points."""
     if stage == "point_fwd":
         return N * (4 * D + 12), N * (2 * M * D + M * M)
-    if stage == "point_bwd":
-        return N * (4 * D + 16), N * (2 * M * D + M * M)
+    if stage == "point_bwd":          # dX is fused into the backward kernel: x and upstream grads in, dx out
+        return N * (8 * D + 16), N * (4 * M * D + M * M)
     if stage == "dx":
         return N * 8 * D, 2 * N * M * D
     if stage == "gram":
@@ -385,7 +385,17 @@ def measure(args, wl, name, ctx, primary=True):
     bucket = FlatGradBucket(gp_parameters(model), module=model)
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     nbuf = 3   # rotate inputs; an L2 flush is also issued between timed steps
-    xs = [[torch.randn(B, L, D, device=device, generator=g) for L in calls] for _ in range(nbuf)]
+    # the activations of a step sit back to back in one buffer (what a caller that wants ONE fused GP evaluation per
+    # step provides, see DeepGPp.blur_segments); xs[k][c] are the per-call [B, L, D] views
+    def seg_views(flat):
+        out, o = [], 0
+        for L in calls:
+            out.append(flat[o:o + B * L].view(B, L, D))
+            o += B * L
+        return out
+    xflat = [torch.randn(B * sum(calls), D, device=device, generator=g) for _ in range(nbuf)]
+    xs = [seg_views(f) for f in xflat]
+    fused = bool(args.fuse_calls and len(calls) > 1 and hasattr(model, "blur_segments"))
     ys = [torch.randn(1, B, calls[-1], device=device, generator=g) for _ in range(nbuf)]
     gms = [torch.randn(1, B, L, device=device, generator=g) for L in calls]
     gss = [torch.randn(1, B, L, device=device, generator=g) for L in calls]
@@ -402,13 +412,28 @@ def measure(args, wl, name, ctx, primary=True):
     # fills a third of the SMs, so it is issued on a second stream and runs in the tail of the encoder-side kernels
     # (autograd replays each call's backward on the stream of its forward).
     from fine_grained_gaussian_process_forcasting_b200.graphs import CallStreams
-    call_streams = CallStreams(device, len(calls)) if (args.call_streams and len(calls) > 1) else None
+    call_streams = CallStreams(device, len(calls)) if (args.call_streams and len(calls) > 1 and not fused) else None
 
     def step_body(xin, yin):
         """forward (mean, variance, fused sample, ELBO) + backward (dX, every GP parameter gradient)"""
         bucket.zero()
         outs, grads = [], []
         elbo = None
+        if fused:
+            # ONE fused evaluation for all the activations of the step (one launch per kernel, one leaf for dX)
+            from fine_grained_gaussian_process_forcasting_b200 import ops as _ops
+            xf = _ops.as_one_buffer(list(xin)).detach().requires_grad_(True)
+            segs = model.blur_segments(xf, [(B, L) for L in calls], yin, num_data=D)
+            for c, o in enumerate(segs):
+                outs += [o.mean, o.sample]
+                grads += [gms[c], gss[c]]
+            elbo = segs[-1].elbo
+            outs.append(elbo)
+            grads.append(g_elbo)
+            torch.autograd.backward(outs, grads)
+            if world > 1 and allreduce_in_step[0]:
+                bucket.all_reduce(average=True)
+            return elbo
         if call_streams is not None:
             for ly in layers:                             # the shared stage is built once, on the main stream
                 ly._kl_only()
@@ -460,8 +485,12 @@ def measure(args, wl, name, ctx, primary=True):
     if not args.eager:
         for attempt in (0, 1):
             try:
-                graphed = GraphedStep(model, lambda *ins: (step_body(ins[:-1], ins[-1]),), list(xs[0]) + [ys[0]],
-                                      warmup=2, world=world, rank=rank)
+                if fused:     # static inputs: the flat activation buffer + targets
+                    graphed = GraphedStep(model, lambda xf, y: (step_body(seg_views(xf), y),), [xflat[0], ys[0]],
+                                          warmup=2, world=world, rank=rank)
+                else:
+                    graphed = GraphedStep(model, lambda *ins: (step_body(ins[:-1], ins[-1]),), list(xs[0]) + [ys[0]],
+                                          warmup=2, world=world, rank=rank)
                 graph_note = "whole step (fwd + bwd" + (" + NCCL all-reduce of the gradient bucket" if world > 1 and
                              allreduce_in_step[0] else "") + ") replayed as one CUDA graph" + \
                              ("; NCCL all-reduce issued after the replay" if world > 1 and not allreduce_in_step[0] else "")
@@ -476,12 +505,15 @@ def measure(args, wl, name, ctx, primary=True):
                 graph_note = f"CUDA graph capture failed ({type(e).__name__}: {e}); eager launches"
                 break
     sync_all()
+    g_inputs = None
+    if graphed is not None:       # the graph's static inputs as [x per call ..., y]
+        g_inputs = (seg_views(graphed.inputs[0]) + [graphed.inputs[1]]) if fused else list(graphed.inputs)
 
     def run_step(i, xin, yin):
         """one step on inputs already in HBM; returns the per-window ELBO"""
         if graphed is None:
             return eager_step(i, xin, yin)
-        for dst, src in zip(graphed.inputs, list(xin) + [yin]):
+        for dst, src in zip(g_inputs, list(xin) + [yin]):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         (elbo,) = graphed.replay()
@@ -502,7 +534,7 @@ def measure(args, wl, name, ctx, primary=True):
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         if graphed is not None:                         # stage this step's inputs in the graph's static buffers
-            for dst, src in zip(graphed.inputs, list(xs[i % nbuf]) + [ys[i % nbuf]]):
+            for dst, src in zip(g_inputs, list(xs[i % nbuf]) + [ys[i % nbuf]]):
                 dst.copy_(src, non_blocking=True)
         flush.zero_()                                   # L2 flush between timed iterations (outside the events)
         evs[i][0].record()
@@ -527,9 +559,9 @@ def measure(args, wl, name, ctx, primary=True):
 
     # ---- timed region 2: end to end through the module API with host buffers ----
     if graphed is not None:
-        xdev, ydev = graphed.inputs[:-1], graphed.inputs[-1]
+        xdev, ydev = g_inputs[:-1], g_inputs[-1]
     else:
-        xdev = [torch.empty_like(x) for x in xs[0]]
+        xdev = seg_views(torch.empty_like(xflat[0]))
         ydev = torch.empty_like(ys[0])
     # Every step's inputs start in PINNED HOST memory and its result is read on the host; all copies are inside the
     # timed region.  Like any training input pipeline, the host->device copy of step i + 1 is issued on a copy stream
@@ -726,6 +758,7 @@ def measure(args, wl, name, ctx, primary=True):
                        "+ 3 rotating input sets", "timing": "per-step CUDA events, max over ranks",
                        "launch": graph_note,
                        "call_streams": call_streams is not None,
+                       "calls_fused": fused,
                        "regime": "R-exercise (SURVEY 8d)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pipeline": "pinned host inputs -> copy stream (step i + 1 in flight during step i) -> device "
@@ -758,6 +791,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
     ap.add_argument("--no-call-streams", dest="call_streams", action="store_false",
                     help="issue the GP calls of a step on one stream (default: one extra stream per additional call)")
+    ap.add_argument("--no-fuse-calls", dest="fuse_calls", action="store_false",
+                    help="evaluate the GP once per activation (blur) instead of once per step (blur_segments)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "
                     "step as a CUDA graph")
     ap.add_argument("--single", action="store_true", help="measure only --workload (no `workloads` dict)")

@@ -90,6 +90,25 @@ class DeepGPp(gp.DeepGP):
         ``num_data`` defaulting to the input width (forecast_denoising.py:88 passes d_model)."""
         return _blur(self, x, y, num_data)
 
+    def blur_segments(self, x_flat, seg_shapes, y_last=None, num_data=None):
+        """The blur of SEVERAL activations of one step in one fused evaluation: ``x_flat [N, D]`` holds their points
+        back to back (e.g. the encoder-side [B, 192, D] then the decoder-side [B, 24, D] activations of
+        denoise_model_2.py:50-51), ``seg_shapes`` their output shapes ((B, 192), (B, 24)).  Returns one ``BlurOutput``
+        per segment - the same values as separate ``blur`` calls (same Philox counters) from one launch per kernel
+        instead of one per activation; ``y_last`` gives the ELBO of the last segment."""
+        dists = self.hidden_layer.call_segments(x_flat, seg_shapes)
+        outs = []
+        for i, dist in enumerate(dists):
+            elbo = None
+            if y_last is not None and i == len(dists) - 1:
+                nd = float(num_data if num_data is not None else x_flat.shape[-1])
+                tgt = y_last if y_last.dim() == dist.mean.dim() else y_last.unsqueeze(0)
+                kl = self.variational_strategy.kl_divergence()
+                elbo = ops.variational_elbo(dist.mean, dist.variance, tgt.expand(dist.mean.shape),
+                                            self.likelihood.raw_noise, kl, nd)
+            outs.append(BlurOutput(dist.mean, dist.variance, dist.sample_value, elbo, dist.kl, dist))
+        return outs
+
 
 def _blur(model, x, y=None, num_data=None) -> BlurOutput:
     dist = model(x)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "gpblur_common.cuh"
+#include "gpblur_tile.cuh"
 
 namespace gpblur {
 
@@ -40,6 +41,12 @@ static thread_local const unsigned long long* g_offset_dev = nullptr;
 const unsigned long long* current_offset_dev() { return g_offset_dev; }
 static thread_local const void* g_param_stage = nullptr;
 const void* current_param_stage() { return g_param_stage; }
+static thread_local SegGrads g_seg_grads = {};
+SegGrads current_seg_grads() { return g_seg_grads; }
+struct SegGradsScope {
+  explicit SegGradsScope(const SegGrads& s) { g_seg_grads = s; }
+  ~SegGradsScope() { g_seg_grads = SegGrads{}; }
+};
 struct ParamStageScope {
   explicit ParamStageScope(const void* p) { g_param_stage = p; }
   ~ParamStageScope() { g_param_stage = nullptr; }
@@ -402,6 +409,32 @@ int gpblur_svgp_point_backward_shared(const void* param_stage, const float* x, l
   if (!param_stage || (reinterpret_cast<uintptr_t>(param_stage) & 255)) return GPBLUR_EINVAL;
   ParamStageScope pss(param_stage);
   return gpblur_svgp_point_backward(x, N, D, M, g_mean, g_var, g_sample, var, seed, offset, stream_id, offset_dev, dx,
+                                    stage_grad, ws, ws_bytes, stream);
+}
+
+int gpblur_svgp_point_backward_segments(const void* param_stage, const float* x, long long N, int D, int M, int nseg,
+                                        const long long* seg_start, const float* const* g_mean,
+                                        const float* const* g_var, const float* const* g_sample, const float* var,
+                                        uint64_t seed, uint64_t offset, uint32_t stream_id,
+                                        const unsigned long long* offset_dev, float* dx, double* stage_grad, void* ws,
+                                        size_t ws_bytes, void* stream) {
+  if (nseg < 1 || nseg > kMaxSegments || !seg_start || seg_start[0] != 0) return GPBLUR_EINVAL;
+  SegGrads sg{};
+  sg.nseg = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    if (seg_start[i] < 0 || seg_start[i] > N || (i > 0 && seg_start[i] < seg_start[i - 1])) return GPBLUR_EINVAL;
+    sg.start[i] = seg_start[i];
+    sg.gm[i] = g_mean ? g_mean[i] : nullptr;
+    sg.gv[i] = g_var ? g_var[i] : nullptr;
+    sg.gs[i] = g_sample ? g_sample[i] : nullptr;
+  }
+  SegGradsScope sgs(sg);
+  // (the kernels look at the flat pointers only to decide whether a kind of gradient exists at all)
+  if (param_stage) {
+    return gpblur_svgp_point_backward_shared(param_stage, x, N, D, M, nullptr, nullptr, nullptr, var, seed, offset,
+                                             stream_id, offset_dev, dx, stage_grad, ws, ws_bytes, stream);
+  }
+  return gpblur_svgp_point_backward(x, N, D, M, nullptr, nullptr, nullptr, var, seed, offset, stream_id, offset_dev, dx,
                                     stage_grad, ws, ws_bytes, stream);
 }
 

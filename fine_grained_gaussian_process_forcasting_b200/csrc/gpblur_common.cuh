@@ -319,6 +319,8 @@ const unsigned long long* current_offset_dev();
 // Parameter stage the point kernels of the current API call read their constant operands from (thread-local, set by
 // the gpblur_svgp_point_*_shared entry points); nullptr: the stage lives in the call's own workspace.
 const void* current_param_stage();
+struct SegGrads;
+SegGrads current_seg_grads();   // per-segment upstream gradients of the current backward call (nseg == 0: none)
 __device__ __forceinline__ uint64_t rng_offset(uint64_t offset, const unsigned long long* offset_dev) {
   return offset + (offset_dev ? (uint64_t)*offset_dev : 0ull);
 }

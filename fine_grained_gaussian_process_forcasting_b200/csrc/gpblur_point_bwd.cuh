@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(kThreads, Cfg::TN <= 64 ? 2 : 1) point_bwd_ker
       const long long gn = n0 + t;
       float gm = 0.f, gv = 0.f;
       if (gn < N) {
-        if (a.g_mean) gm = a.g_mean[gn];
-        if (a.g_var) gv = a.g_var[gn];
+        float gs;
+        bool has_gs;
+        upstream_grads(a.seg, a.g_mean, a.g_var, a.g_sample, gn, gm, gv, gs, has_gs);
         const float v = a.var[gn];
-        if (a.g_sample) {
-          const float gs = a.g_sample[gn];
+        if (has_gs) {
           const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
           gm += gs;
           gv = fmaf(gs * eps, 0.5f * rsqrtf(v), gv);

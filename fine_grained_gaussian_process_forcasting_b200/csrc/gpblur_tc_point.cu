@@ -19,6 +19,7 @@
 // complete without the waiter's own arrival (or is signalled once per block for exactly one waiting group), so a
 // parity can never be observed two phases late.
 #include "gpblur_tc.cuh"
+#include "gpblur_tile.cuh"
 
 // clock64 event trace of CTA 0 (scripts/tc2_trace.py): compiled out of release builds (GPBLUR_TRACE=1 python -m ...build)
 #ifndef GPBLUR_TRACE
@@ -54,6 +55,7 @@ struct Tc2Args {
   const float* g_mean;
   const float* g_var;
   const float* g_sample;
+  SegGrads seg;          // per-segment upstream gradients (nseg == 0: g_mean / g_var / g_sample above)
   const float* var_in;
   float* dx;
   uint64_t seed, offset;
@@ -966,11 +968,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) tc2_bwd_kernel(Tc2Args a) {
         // ---- upstream gradients of this thread's point (requested early) ----
         float gm = 0.f, gv = 0.f;
         if (live) {
-          if (a.g_mean) gm = a.g_mean[gn];
-          if (a.g_var) gv = a.g_var[gn];
+          float gsv;
+          bool has_gs;
+          upstream_grads(a.seg, a.g_mean, a.g_var, a.g_sample, gn, gm, gv, gsv, has_gs);
           const float vr = a.var_in[gn];
-          if (a.g_sample) {
-            const float gsv = a.g_sample[gn];
+          if (has_gs) {
             const float eps = philox_normal(a.seed, rng_offset(a.offset, a.offset_dev) + (uint64_t)gn, a.stream_id);
             gm += gsv;
             gv = fmaf(gsv * eps, 0.5f * rsqrtf(vr), gv);
@@ -1218,7 +1220,7 @@ int launch_tc_point_backward(const WsLayout& L, void* ws, const float* x, const 
                              const float* g_sample, const float* var, uint64_t seed, uint64_t offset,
                              uint32_t stream_id, float* dx, cudaStream_t st) {
   Tc2Args a{};
-  a.L = L; a.ws = ws; a.stage = current_param_stage() ? current_param_stage() : ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.var_in = var; a.dx = dx;
+  a.L = L; a.ws = ws; a.stage = current_param_stage() ? current_param_stage() : ws; a.x = x; a.g_mean = g_mean; a.g_var = g_var; a.g_sample = g_sample; a.seg = current_seg_grads(); a.var_in = var; a.dx = dx;
   a.seed = seed; a.offset = offset; a.offset_dev = current_offset_dev(); a.stream_id = stream_id;
   a.ntiles = (int)((L.N + TNP - 1) / TNP);
   a.trace = debug_trace_buffer();

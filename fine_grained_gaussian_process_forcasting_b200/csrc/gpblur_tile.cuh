@@ -95,6 +95,36 @@ struct PointFwdArgs {
   const unsigned long long* offset_dev;   // optional device-resident addend of `offset` (CUDA-graph replays)
 };
 
+// Upstream gradients given per SEGMENT of the point range (several activations of one training step evaluated in one
+// call: gpblur_svgp_point_backward_segments): segment s covers points [start[s], start[s + 1]) and brings its own
+// (nullable) g_mean / g_var / g_sample arrays, indexed from the start of the segment.  nseg == 0: not used.
+constexpr int kMaxSegments = 4;
+struct SegGrads {
+  int nseg;
+  long long start[kMaxSegments];
+  const float* gm[kMaxSegments];
+  const float* gv[kMaxSegments];
+  const float* gs[kMaxSegments];
+};
+__device__ __forceinline__ void upstream_grads(const SegGrads& sg, const float* g_mean, const float* g_var,
+                                               const float* g_sample, long long gn, float& gm, float& gv, float& gsv,
+                                               bool& has_gs) {
+  const float *pm = g_mean, *pv = g_var, *ps = g_sample;
+  long long ln = gn;
+  if (sg.nseg > 0) {
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxSegments; ++i)
+      if (i < sg.nseg && gn >= sg.start[i]) s = i;
+    pm = sg.gm[s]; pv = sg.gv[s]; ps = sg.gs[s];
+    ln = gn - sg.start[s];
+  }
+  gm = pm ? pm[ln] : 0.f;
+  gv = pv ? pv[ln] : 0.f;
+  has_gs = ps != nullptr;
+  gsv = ps ? ps[ln] : 0.f;
+}
+
 struct PointBwdArgs {
   WsLayout L;
   void* ws;
@@ -109,6 +139,7 @@ struct PointBwdArgs {
   float* dx;
   int ntiles;
   const unsigned long long* offset_dev;
+  SegGrads seg;
 };
 
 // Stage a [TN][DP] tile of X into shared memory, centred and scaled: Xs[n][d] = (x - c) / ell (0 beyond N, D).

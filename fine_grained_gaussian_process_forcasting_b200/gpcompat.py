@@ -430,7 +430,13 @@ class _DeepGPVariationalStrategy:
         return [m.variational_strategy for m in self.model.modules() if isinstance(m, ApproximateGP)]
 
     def kl_divergence(self):
-        return sum(s.kl_divergence().sum() for s in self.sub_variational_strategies)
+        terms = [s.kl_divergence() for s in self.sub_variational_strategies]
+        if len(terms) == 1 and terms[0].numel() == 1:
+            return terms[0].reshape(())              # one GP: a view, no reduction / accumulation kernels
+        total = terms[0].sum()
+        for t in terms[1:]:
+            total = total + t.sum()
+        return total
 
 
 # ------------------------------------------------------------------------------------------------
@@ -555,6 +561,30 @@ class DeepGPLayer(ApproximateGP):
             S = num_likelihood_samples.value()
             dist = dist.expand(S, *mean.shape)
         return dist
+
+
+    def call_segments(self, x_flat, seg_shapes):
+        """ONE fused evaluation on x_flat [N, D] = the concatenated points of several activations (the reference
+        blurs the encoder and the decoder activations of a step with the same GP, denoise_model_2.py:50-51).
+        ``seg_shapes``: output shape of every segment, e.g. [(B, 192), (B, 24)].  Returns one distribution per
+        segment, exactly what separate calls return (same Philox counters: segment s starts where s - 1 ended)."""
+        vs = self.variational_strategy
+        vs._ensure_initialized()
+        if self.output_dims is not None:
+            raise NotImplementedError("call_segments: single-output layers only")
+        if x_flat.dim() != 2 or x_flat.shape[-1] != self.input_dims:
+            raise RuntimeError(f"call_segments expects [N, {self.input_dims}] points, got {tuple(x_flat.shape)}")
+        n_pts = x_flat.shape[0]
+        seed, off, stream = self._next_counters(n_pts) if self.fused_sample else (0, 0, 0)
+        segs, kl, info = ops.svgp_predict_segments(x_flat, seg_shapes, *self._layer_params(), seed, off, stream,
+                                                   want_sample=self.fused_sample, stage_cache=self._stage_cache(),
+                                                   offset_dev=self.rng_offset_dev,
+                                                   check=bool(check_cholesky.value()), grad_sink=self._grad_sink)
+        self.last_info = info
+        vs._cache_kl(kl)
+        S = num_likelihood_samples.value()
+        return [MultivariateNormal(m, None, variance=v, sample=sm, kl=kl, layer=self).expand(S, *m.shape)
+                for (m, v, sm) in segs]
 
 
 class DeepGP(GP):

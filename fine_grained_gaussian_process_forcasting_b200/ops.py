@@ -6,6 +6,8 @@ missing (``_cabi.lib``).
 """
 from __future__ import annotations
 
+import math
+
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -309,6 +311,37 @@ def point_backward_raw(x: Tensor, M: int, g_mean, g_var, g_sample, var, seed, of
             rc = _cabi.lib().gpblur_svgp_point_backward(*args)
     _cabi.check(rc, "gpblur_svgp_point_backward")
     return (dx if need_dx else None), sgrad
+
+
+def point_backward_segments_raw(x: Tensor, M: int, seg_sizes, g_means, g_vars, g_samples, var, seed, offset, stream_id,
+                                ws, need_dx: bool = True, offset_dev: Optional[Tensor] = None,
+                                stage: Optional[Tensor] = None):
+    """point_backward_raw with the upstream gradients given per segment of the point range (lists of tensors or None,
+    one entry per segment, indexed from the start of the segment) -> (dx [N, D] | None, stage_grad)."""
+    _need_cuda(x, ws, var)
+    N, D = x.shape
+    dev = x.device
+    nseg = len(seg_sizes)
+    starts, o = [], 0
+    for n in seg_sizes:
+        starts.append(o)
+        o += int(n)
+    assert o == N and 1 <= nseg <= 4
+
+    def ptr_array(ts):
+        return (C.c_void_p * nseg)(*[(_ptr(t) if t is not None else None) for t in ts])
+
+    keep = [None if t is None else _f32c(t) for t in list(g_means) + list(g_vars) + list(g_samples)]   # alive until launch
+    gm, gv, gs = keep[:nseg], keep[nseg:2 * nseg], keep[2 * nseg:]
+    dx = torch.empty(N, D, device=dev, dtype=torch.float32) if need_dx else None
+    sgrad = torch.empty(stage_grad_doubles(D, M), device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        rc = _cabi.lib().gpblur_svgp_point_backward_segments(
+            _ptr(stage), _ptr(x), N, D, M, nseg, (C.c_longlong * nseg)(*starts), ptr_array(gm), ptr_array(gv),
+            ptr_array(gs), _ptr(var), seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFF,
+            _ptr(offset_dev), _ptr(dx), _ptr(sgrad), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "gpblur_svgp_point_backward_segments")
+    return dx, sgrad
 
 
 def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor,
@@ -654,6 +687,90 @@ def svgp_predict(x: Tensor, inducing_points: Tensor, raw_lengthscale: Tensor, ra
         mean, var, sample = _PointFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
                                                  int(stream_id), bool(want_sample), offset_dev, h_stride)
     return mean, var, sample, kl, info
+
+
+def as_one_buffer(xs) -> Tensor:
+    """[..., D] activations -> their points back to back as ONE [N, D] tensor: a view when the tensors already sit
+    back to back in one allocation (e.g. slices of a staging buffer), otherwise a concatenation (one copy kernel)."""
+    D = xs[0].shape[-1]
+    ok = all(t.is_contiguous() and t.dtype == torch.float32 and t.shape[-1] == D for t in xs)
+    if ok:
+        base = xs[0].untyped_storage().data_ptr()
+        p = xs[0].data_ptr()
+        for t in xs:
+            ok = ok and t.untyped_storage().data_ptr() == base and t.data_ptr() == p
+            p += t.numel() * 4
+    if ok:
+        n = sum(t.numel() for t in xs) // D
+        return torch.as_strided(xs[0], (n, D), (D, 1))
+    return torch.cat([_f32c(t).reshape(-1, D) for t in xs], dim=0)
+
+
+class _PointSegFunction(torch.autograd.Function):
+    """_PointFunction (single-output GP) on the CONCATENATED points of several activations: one launch per kernel for
+    the whole step instead of one per activation.  Outputs come back per segment (views of one buffer) and the
+    backward reads each segment's upstream gradients where autograd left them (no concatenation kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, token, holder, M, seed, offset, stream_id, want_sample, offset_dev, seg_shapes):
+        D = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, D)
+        N = x2.shape[0]
+        sizes = [int(math.prod(shp)) for shp in seg_shapes]
+        if sum(sizes) != N:
+            raise ValueError(f"segment shapes {seg_shapes} do not cover the {N} points of x")
+        training = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        nout = 3 if want_sample else 2
+        out = torch.empty(nout * N, device=x2.device, dtype=torch.float32)
+        stage = holder["stage"]
+        ws = torch.empty(workspace_bytes(N, D, M, training), device=x2.device, dtype=torch.uint8)
+        point_forward_raw(stage[0], x2, M, seed, offset, stream_id, want_sample, training, out=out,
+                          offset_dev=offset_dev, ws=ws)
+        if training:
+            ctx.save_for_backward(x2, out, ws)
+            ctx.stage = stage
+        ctx.meta = (seed, offset, stream_id, M, tuple(x.shape), sizes, nout)
+        ctx.offset_dev = offset_dev
+        ctx.set_materialize_grads(False)
+        res, o = [], 0
+        for shp, n in zip(seg_shapes, sizes):
+            for k in range(3):
+                res.append(out[k * N + o:k * N + o + n].view(tuple(shp)) if k < nout else None)
+            o += n
+        return tuple(res)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x2, out, ws = ctx.saved_tensors
+        seed, offset, stream_id, M, xshape, sizes, nout = ctx.meta
+        N, D = x2.shape
+        need = ctx.needs_input_grad
+        gms, gvs, gss = list(grads[0::3]), list(grads[1::3]), list(grads[2::3])
+        with torch.cuda.nvtx.range("gpblur.point_backward") if _NVTX else _null_ctx():
+            dx, sgrad = point_backward_segments_raw(x2, M, sizes, gms, gvs, gss, out[N:2 * N], seed, offset, stream_id, ws,
+                                                    need_dx=need[0], offset_dev=ctx.offset_dev, stage=ctx.stage[0])
+        return (dx.reshape(xshape) if dx is not None else None, sgrad if need[1] else None) + (None,) * 8
+
+
+def svgp_predict_segments(x: Tensor, seg_shapes, inducing_points: Tensor, raw_lengthscale: Tensor,
+                          raw_outputscale: Tensor, variational_mean: Tensor, variational_stddev: Tensor,
+                          mean_weights: Optional[Tensor], mean_bias: Tensor, seed: int = 0, offset: int = 0,
+                          stream_id: int = 0, want_sample: bool = False, stage_cache: Optional[dict] = None,
+                          offset_dev: Optional[Tensor] = None, check: bool = False,
+                          grad_sink: Optional[Tensor] = None):
+    """svgp_predict for a single-output GP on x [N, D] = the concatenated points of several activations;
+    ``seg_shapes`` (e.g. [(B, 192), (B, 24)]) are the output shapes of the segments, in order.
+    -> ([(mean, var, sample | None) per segment], kl, info)."""
+    if inducing_points.dim() != 2:
+        raise ValueError("svgp_predict_segments: single-output layers only")
+    token, kl, info, holder = svgp_param_stage(inducing_points, raw_lengthscale, raw_outputscale, variational_mean,
+                                               variational_stddev, mean_weights, mean_bias, stage_cache, check=check,
+                                               grad_sink=grad_sink)
+    with torch.cuda.nvtx.range("gpblur.point_forward") if _NVTX else _null_ctx():
+        flat = _PointSegFunction.apply(x, token, holder, int(inducing_points.shape[-2]), int(seed), int(offset),
+                                       int(stream_id), bool(want_sample), offset_dev,
+                                       tuple(tuple(int(v) for v in shp) for shp in seg_shapes))
+    return [tuple(flat[3 * i:3 * i + 3]) for i in range(len(seg_shapes))], kl, info
 
 
 class _ElboFunction(torch.autograd.Function):

@@ -140,6 +140,18 @@ int gpblur_svgp_point_backward_shared(const void* param_stage, const float* x, l
                                       const float* var, uint64_t seed, uint64_t offset, uint32_t stream_id,
                                       const unsigned long long* offset_dev, float* dx, double* stage_grad,
                                       void* ws, size_t ws_bytes, void* stream);
+/* Several activations of one step in ONE call (the reference blurs the encoder and the decoder activations with the
+ * same GP, /root/reference/denoising_model/denoise_model_2.py:50-51): run the forward on the concatenated points
+ * `x` [N, D]; in the backward the upstream gradients stay where autograd produced them - segment s covers points
+ * [seg_start[s], seg_start[s + 1]) (seg_start[0] = 0, nseg <= 4) and g_mean[s] / g_var[s] / g_sample[s] (host arrays
+ * of nullable device pointers, or null arrays) are indexed from the start of the segment.  `param_stage` may be null
+ * when the stage lives in `ws`. */
+int gpblur_svgp_point_backward_segments(const void* param_stage, const float* x, long long N, int D, int M, int nseg,
+                                        const long long* seg_start, const float* const* g_mean,
+                                        const float* const* g_var, const float* const* g_sample, const float* var,
+                                        uint64_t seed, uint64_t offset, uint32_t stream_id,
+                                        const unsigned long long* offset_dev, float* dx, double* stage_grad,
+                                        void* ws, size_t ws_bytes, void* stream);
 /* gpblur_svgp_param_stage_backward with `accumulate` != 0: the gradients are ADDED to `grad_bucket`, which then is
  * the caller's live flat gradient buffer (what the data-parallel all-reduce operates on) - no intermediate bucket
  * and no per-parameter accumulation kernels on the framework side. */

@@ -273,3 +273,60 @@ def test_gpytorch_shim_path_runs_forward_and_backward_on_gpu(cuda):
     assert abs(loss.item() - lo.item()) < 1e-4 * abs(lo.item())
     assert rel(xd.grad, x64.grad) < 2e-4
     assert rel(net.hidden_layer.variational_strategy.inducing_points.grad, p64["inducing_points"].grad) < 2e-4
+
+
+@pytest.mark.parametrize("D,M,Ls", [(64, 256, (48, 24)), (32, 32, (24, 7, 13)), (64, 128, (40, 24))])
+def test_blur_segments_equals_separate_calls(cuda, D, M, Ls):
+    """DeepGPp.blur_segments (ONE fused evaluation over the concatenated activations of a step, per-segment upstream
+    gradients read in place by the backward kernels) == one blur call per activation: outputs bit-identical (same
+    kernels, same Philox counters), gradients to fp32 accumulation order."""
+    from fine_grained_gaussian_process_forcasting_b200.DeepGP import DeepGPp
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat, ops
+    B = 16
+    p = O.init_params_exercise(D, M, 51)
+    g = torch.Generator().manual_seed(52)
+    xs = [torch.randn(B, L, D, generator=g) for L in Ls]
+    y = torch.randn(B, Ls[-1], generator=g)
+    gms = [torch.randn(1, B, L, generator=g).to(cuda) for L in Ls]
+    gss = [torch.randn(1, B, L, generator=g).to(cuda) for L in Ls]
+    gss[0] = None                                     # a segment without a gradient on its sample
+
+    def run(fused):
+        with gpcompat.num_likelihood_samples(1):
+            m = DeepGPp(D, 3, num_inducing=M).to(cuda)
+            _load_layer(m.hidden_layer, p)
+            m.hidden_layer._rng_offset = 0
+            if fused:
+                flat = torch.cat([x.reshape(-1, D) for x in xs]).to(cuda)
+                views, o = [], 0
+                for x in xs:
+                    views.append(flat[o:o + x.shape[0] * x.shape[1]].view(x.shape))
+                    o += x.shape[0] * x.shape[1]
+                xf = ops.as_one_buffer(views)
+                assert xf.data_ptr() == flat.data_ptr() and xf.shape == flat.shape      # a view, no copy
+                xf = xf.detach().requires_grad_(True)
+                outs = m.blur_segments(xf, [(B, L) for L in Ls], y.to(cuda))
+                leaves = [xf]
+            else:
+                leaves = [x.to(cuda).requires_grad_(True) for x in xs]
+                outs = [m.blur(lv, y.to(cuda) if i == len(xs) - 1 else None) for i, lv in enumerate(leaves)]
+            heads, grads = [], []
+            for o_, gm_, gs_ in zip(outs, gms, gss):
+                heads.append(o_.mean); grads.append(gm_)
+                if gs_ is not None:
+                    heads.append(o_.sample); grads.append(gs_)
+            heads.append(outs[-1].elbo); grads.append(torch.full_like(outs[-1].elbo, -1.0 / B))
+            torch.autograd.backward(heads, grads)
+            torch.cuda.synchronize()
+            dx = torch.cat([lv.grad.reshape(-1, D) for lv in leaves])
+            pg = {n: q.grad.detach().clone().reshape(-1) for n, q in m.named_parameters()}
+            return outs, dx, pg
+
+    oa, dxa, ga = run(False)
+    ob, dxb, gb = run(True)
+    for a_, b_ in zip(oa, ob):
+        assert torch.equal(a_.mean, b_.mean) and torch.equal(a_.variance, b_.variance) and torch.equal(a_.sample, b_.sample)
+    assert torch.equal(oa[-1].elbo, ob[-1].elbo)
+    assert rel(dxb, dxa) < 1e-6
+    for n in ga:
+        assert rel(gb[n], ga[n]) < 2e-5, (n, rel(gb[n], ga[n]))
