@@ -383,6 +383,7 @@ def measure(args, wl, name, ctx, primary=True):
     model = make_model(wl, device)
     model.train()
     bucket = FlatGradBucket(gp_parameters(model), module=model)
+    peer_allreduce = bucket.enable_peer_allreduce() if (world > 1 and args.peer_allreduce) else False
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     nbuf = 3   # rotate inputs; an L2 flush is also issued between timed steps
     # the activations of a step sit back to back in one buffer (what a caller that wants ONE fused GP evaluation per
@@ -759,6 +760,8 @@ def measure(args, wl, name, ctx, primary=True):
                        "launch": graph_note,
                        "call_streams": call_streams is not None,
                        "calls_fused": fused,
+                       "allreduce": (None if world == 1 else "one-shot kernel over NVLink peer memory (CUDA IPC), rank-ordered sum"
+                                     if peer_allreduce else "NCCL all-reduce (AVG)"),
                        "regime": "R-exercise (SURVEY 8d)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pipeline": "pinned host inputs -> copy stream (step i + 1 in flight during step i) -> device "
@@ -791,6 +794,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
     ap.add_argument("--no-call-streams", dest="call_streams", action="store_false",
                     help="issue the GP calls of a step on one stream (default: one extra stream per additional call)")
+    ap.add_argument("--peer-allreduce", dest="peer_allreduce", action="store_true",
+                    help="N > 1: the library's one-shot all-reduce over NVLink peer memory instead of NCCL (measured: "
+                         "equal at 2 GPUs, slower than NCCL's in-switch reduction at 8)")
     ap.add_argument("--no-fuse-calls", dest="fuse_calls", action="store_false",
                     help="evaluate the GP once per activation (blur) instead of once per step (blur_segments)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "

@@ -76,6 +76,12 @@ SIGNATURES = {
         C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
         C.c_void_p]),
+    "gpblur_peer_comm_bytes": (C.c_size_t, [C.c_longlong]),
+    "gpblur_peer_alloc": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p]),
+    "gpblur_peer_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpblur_peer_close": (C.c_int, [C.c_void_p]),
+    "gpblur_peer_free": (C.c_int, [C.c_void_p]),
+    "gpblur_peer_allreduce": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
     "gpblur_svgp_param_stage_backward": (C.c_int, [
         C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
         C.c_void_p]),

@@ -218,6 +218,23 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
 int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
                        size_t out_bytes, int* mp, void* stream);
 
+/* ---- data-parallel exchange: one-shot all-reduce of the flat gradient bucket over NVLink peer memory -------------
+ * (one node, one process per GPU; replaces the all-reduce a torch DistributedDataParallel wrapper would issue for the
+ * GP parameters - the reference itself trains on one device.)  Every rank allocates one communication buffer of
+ * gpblur_peer_comm_bytes(n) with gpblur_peer_alloc, publishes the 64-byte IPC handle to its peers (any side channel:
+ * torch.distributed all_gather_object, MPI, ...), maps theirs with gpblur_peer_open, and calls gpblur_peer_allreduce
+ * once per step with the `world` pointers in RANK order (comm[rank] = its own buffer): bucket <- scale * sum over ranks,
+ * summed in rank order (bit-identical on every rank).  The kernel is self-synchronising (flags in peer memory, a
+ * device-resident step counter): it can be captured in a CUDA graph, and it traps instead of hanging if a peer never
+ * arrives.  `bucket` must be 16-byte aligned; world <= 16.  These two functions allocate / free device memory. */
+size_t gpblur_peer_comm_bytes(long long n);
+int gpblur_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int gpblur_peer_open(const unsigned char* handle64, void** ptr);
+int gpblur_peer_close(void* ptr);
+int gpblur_peer_free(void* ptr);
+int gpblur_peer_allreduce(float* bucket, long long n, int world, int rank, void* const* comm, float scale,
+                          void* stream);
+
 /* Developer probe: register a device buffer (>= 32 KB, zero-filled by the caller) that CTA 0 of the tensor-core
  * point kernels fills with clock64 event stamps (scripts/tc2_trace.py); NULL switches tracing off (default). */
 int gpblur_debug_set_trace(void* device_buffer);
