@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t bars[4];      // [0..1] mma_done (tcgen05.commit), [2..3] a_ready (256 producers)
   __shared__ uint32_t tmem_slot;
-  __shared__ float scs[4][KT], gms[4][KT];
+  __shared__ __align__(16) float scs[4][KT], gms[4][KT];
   __shared__ float ured[4][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,33 +134,44 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
 
     // the gathered operands of TWO slabs are in flight per thread (two register sets): with one, the global-load
     // latency of slab s + 1 was exposed between the split / store of consecutive slabs
+    // Addresses: n0 is a multiple of 32, so the 32 rows of a slab never cross a 128-point tile: element (n0 + k, col) of
+    // a tile-major matrix sits at slab_base(n0) + (col >> 2) * 512 + k * 4 (+ col & 3) - one 64-bit base per slab plus
+    // thread-constant offsets (the generic index cost ~15 integer instructions per load in an issue-bound loop).
+    const uint32_t a_off0 = (uint32_t)(((p0 + ar) >> 2) * 512 + (4 * acg + (lane & 3)) * 4);            // chunk acg
+    const uint32_t b_off_t = GRAM ? (uint32_t)(((q0 + bq) >> 2) * 512 + (4 * bcg + (lane & 3)) * 4) : 0u;
+    const bool b_col_ok = q0 + bq < a.vcols;
+    const size_t v_off = (size_t)(4 * bcg) * a.ldv + q0 + bq;                                            // W^T X: row 4 bcg
     auto prefetch = [&](Regs& rg, int s) {
       const long long n0 = r0 + (long long)s * KT;
+      const bool full = n0 + KT <= r1;
+      const float* ubase = a.U + (size_t)(n0 >> 7) * (size_t)a.MP * 128 + (size_t)(n0 & 127) * 4;
   #pragma unroll
       for (int i = 0; i < 2; ++i) {
         // rows n0 + 4 c .. + 3, column p0 + ar: this lane fetches row n0 + 4 c + (lane & 3) of its column piece
-        const int c = acg + 4 * i;
-        const long long n = n0 + 4 * c + (lane & 3);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < r1) v = *reinterpret_cast<const float4*>(a.U + tc_tiled_index(n, (p0 + ar) & ~3, a.MP));
+        if (full || n0 + 4 * (acg + 4 * i) + (lane & 3) < r1) v = *reinterpret_cast<const float4*>(ubase + a_off0 + i * 64);
         rg.a[i] = v;       // raw: the 4 x 4 transpose happens in produce(), two slabs later (a dependent shuffle here
                            // would stall the prefetch on its own HBM round trip)
       }
       if (TQ >= kProd || tid < TQ * BG) {
+        if (GRAM) {
+          const float* vbase = a.V + (size_t)(n0 >> 7) * (size_t)a.MP * 128 + (size_t)(n0 & 127) * 4;
   #pragma unroll
-        for (int i = 0; i < BCH; ++i) {
-          const int c = bcg + BG * i;
-          if (GRAM) {
-            const long long n = n0 + 4 * c + (lane & 3);
+          for (int i = 0; i < BCH; ++i) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < r1 && q0 + bq < a.vcols) v = *reinterpret_cast<const float4*>(a.V + tc_tiled_index(n, (q0 + bq) & ~3, a.MP));
+            if (b_col_ok && (full || n0 + 4 * (bcg + BG * i) + (lane & 3) < r1))
+              v = *reinterpret_cast<const float4*>(vbase + b_off_t + i * (BG * 16));
             rg.b[i] = v;   // raw (see above)
-          } else {
+          }
+        } else {
+          const float* vbase = a.V + (size_t)n0 * a.ldv + v_off;
+  #pragma unroll
+          for (int i = 0; i < BCH; ++i) {
             float v[4];
   #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const long long n = n0 + 4 * c + e;
-              v[e] = (n < r1 && q0 + bq < a.vcols) ? a.V[(size_t)n * a.ldv + q0 + bq] : 0.f;
+              const int k = 4 * (bcg + BG * i) + e;
+              v[e] = (b_col_ok && (full || n0 + k < r1)) ? vbase[(size_t)(4 * BG * i + e) * a.ldv] : 0.f;
             }
             rg.b[i] = make_float4(v[0], v[1], v[2], v[3]);
           }
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
     // per-row scales of slab s go through shared memory (4 buffers: staged two slabs ahead, before the producer
     // barrier of the iteration, which orders the write against the reads two iterations later)
     auto stage_scales = [&](int s) {
-      if (tid < KT) {
+      if (GRAM && tid < KT) {       // W^T X has neither a row scale nor weights for its column sums
         const long long n = r0 + (long long)s * KT + tid;
         scs[s & 3][tid] = (n < r1) ? (a.sc ? a.sc[n] : 1.f) : 0.f;
         gms[s & 3][tid] = (n < r1) ? (a.gm ? a.gm[n] : 1.f) : 0.f;
@@ -197,11 +208,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
         tc::split_tf32(av.z, h.z, l.z); tc::split_tf32(av.w, h.w, l.w);
         tc::tmem_st4(a_hi_t + 4 * c, h);
         tc::tmem_st4(a_lo_t + 4 * c, l);
-        {
-          usum = fmaf(gms[sb][4 * c + 0], av.x, usum);
-          usum = fmaf(gms[sb][4 * c + 1], av.y, usum);
-          usum = fmaf(gms[sb][4 * c + 2], av.z, usum);
-          usum = fmaf(gms[sb][4 * c + 3], av.w, usum);
+        if (GRAM) {
+          const float4 gw = *reinterpret_cast<const float4*>(&gms[sb][4 * c]);
+          usum = fmaf(gw.x, av.x, usum);
+          usum = fmaf(gw.y, av.y, usum);
+          usum = fmaf(gw.z, av.z, usum);
+          usum = fmaf(gw.w, av.w, usum);
+        } else {                     // plain column sums of W (rows beyond the split are zero)
+          usum += av.x; usum += av.y; usum += av.z; usum += av.w;
         }
       }
       if (TQ >= kProd || tid < TQ * BG) {
@@ -209,8 +223,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) tc_reduce_kernel(TcReduceArg
         for (int i = 0; i < BCH; ++i) {
           const int c = bcg + BG * i;
           float4 v = GRAM ? quad_transpose(rg.b[i], lane) : rg.b[i];
-          v.x *= scs[sb][4 * c + 0]; v.y *= scs[sb][4 * c + 1];
-          v.z *= scs[sb][4 * c + 2]; v.w *= scs[sb][4 * c + 3];
+          if (GRAM) {
+            const float4 sw = *reinterpret_cast<const float4*>(&scs[sb][4 * c]);
+            v.x *= sw.x; v.y *= sw.y; v.z *= sw.z; v.w *= sw.w;
+          }
           tc::store_split(b_hi, b_lo, tc::op_off<TQ>(bq, c), v);
         }
       }
