@@ -94,6 +94,9 @@ SIGNATURES = {
     "gpblur_elbo_backward": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
         C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpblur_elbo_backward_fused": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+        C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpblur_philox_bits": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_longlong, C.c_void_p, C.c_void_p]),
     "gpblur_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_longlong, C.c_void_p, C.c_void_p]),
     "gpblur_rsample_forward": (C.c_int, [

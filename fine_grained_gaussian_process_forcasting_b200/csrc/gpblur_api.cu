@@ -139,6 +139,67 @@ __global__ void elbo_bwd_kernel(const float* __restrict__ mean, const float* __r
   if (lane == 0) scratch[b] = ge * s;
 }
 
+// final reduction over the windows, fixed order (one block; volatile reads: the values come from other blocks)
+__device__ __forceinline__ void elbo_bwd_finish(const float* scratch, const float* g_elbo, const float* raw_noise,
+                                                float num_data, long long B, float* g_raw_noise, float* g_kl) {
+  __shared__ double r1[32], r2[32];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+    s1 += (double)*reinterpret_cast<const volatile float*>(scratch + b);
+    s2 += (double)g_elbo[b];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { r1[warp] = s1; r2[warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t1 += r1[i]; t2 += r2[i]; }
+    const double rn = (double)raw_noise[0];
+    if (g_raw_noise) g_raw_noise[0] = (float)(t1 * sigmoid64(rn));
+    if (g_kl) g_kl[0] = (float)(-t2 / (double)num_data);
+  }
+}
+
+// elbo_bwd_kernel + the final reduction in ONE launch: the block that takes the last ticket (a self-resetting
+// atomicInc on a caller-provided zeroed word) reduces the per-window partials - one graph node less per step.
+__global__ void elbo_bwd_fused_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                      const float* __restrict__ y, const float* __restrict__ raw_noise,
+                                      const float* __restrict__ g_elbo, float num_data, long long B, int L,
+                                      float* __restrict__ g_mean, float* __restrict__ g_var,
+                                      float* __restrict__ scratch, float* __restrict__ g_raw_noise,
+                                      float* __restrict__ g_kl, unsigned* __restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b < B) {
+    const float rn = raw_noise[0];
+    const float noise = (rn > 20.f ? rn : log1pf(expf(rn))) + kNoiseLower;
+    const float inv = 1.0f / noise;
+    const float ge = g_elbo[b] / (float)L;
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const size_t i = (size_t)b * L + l;
+      const float d = y[i] - mean[i];
+      g_mean[i] = ge * d * inv;
+      g_var[i] = -0.5f * ge * inv;
+      s += 0.5f * (fmaf(d, d, var[i]) * inv * inv - inv);
+    }
+    s = warp_sum(s);
+    if (lane == 0) scratch[b] = ge * s;
+  }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;     // wraps to 0: ready for the next launch
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  elbo_bwd_finish(scratch, g_elbo, raw_noise, num_data, B, g_raw_noise, g_kl);
+}
+
 __global__ void elbo_bwd_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ g_elbo,
                                        const float* __restrict__ raw_noise, float num_data, long long B,
                                        float* __restrict__ g_raw_noise, float* __restrict__ g_kl) {
@@ -486,6 +547,19 @@ int gpblur_elbo_forward(const float* mean, const float* var, const float* y, con
                                                                    elbo);
   note_launch();
   return check_launch("elbo_fwd");
+}
+
+int gpblur_elbo_backward_fused(const float* mean, const float* var, const float* y, const float* raw_noise,
+                               const float* g_elbo, float num_data, long long B, int L, float* g_mean, float* g_var,
+                               float* g_raw_noise, float* g_kl, float* scratch, unsigned* ticket, void* stream) {
+  if (B < 1 || L < 1 || !raw_noise || !ticket) return GPBLUR_EINVAL;
+  if (!mean || !var || !y || !g_elbo || !g_mean || !g_var || !scratch) return GPBLUR_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(ST_ELBO_BWD, st);
+  elbo_bwd_fused_kernel<<<ew_grid(B, 8), 256, 0, st>>>(mean, var, y, raw_noise, g_elbo, num_data, B, L, g_mean, g_var,
+                                                       scratch, g_raw_noise, g_kl, ticket);
+  note_launch();
+  return check_launch("elbo_bwd");
 }
 
 int gpblur_elbo_backward(const float* mean, const float* var, const float* y, const float* raw_noise,

@@ -158,6 +158,23 @@ def elbo_forward_raw(mean, var, y, raw_noise, kl, num_data: float):
     return elbo
 
 
+_TICKETS = {}
+
+
+def _next_ticket(dev) -> int:
+    """Device address of a zeroed 4-byte ticket word for a last-block-done kernel (a pool of 256 per device, handed out
+    round-robin; the kernels leave their word at 0)."""
+    key = (dev.type, dev.index)
+    ent = _TICKETS.get(key)
+    if ent is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("gpblur: run one eager step before capturing a CUDA graph (ticket pool not allocated)")
+        ent = [torch.zeros(256, device=dev, dtype=torch.int32), 0]
+        _TICKETS[key] = ent
+    ent[1] = (ent[1] + 1) % 256
+    return ent[0].data_ptr() + 4 * ent[1]
+
+
 def elbo_backward_raw(mean, var, y, raw_noise, g_elbo, num_data: float):
     _need_cuda(mean, var, y, raw_noise, g_elbo)
     B, L = mean.shape
@@ -168,9 +185,15 @@ def elbo_backward_raw(mean, var, y, raw_noise, g_elbo, num_data: float):
     g_kl = torch.empty(1, device=dev, dtype=torch.float32)
     scratch = torch.empty(max(B, 1), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().gpblur_elbo_backward(_ptr(mean), _ptr(var), _ptr(y), _ptr(raw_noise), _ptr(g_elbo),
-                                              float(num_data), B, L, _ptr(g_mean), _ptr(g_var), _ptr(g_noise),
-                                              _ptr(g_kl), _ptr(scratch), _stream())
+        if B >= 1:
+            # one launch: the block with the last ticket reduces; tickets rotate so that concurrent calls never share one
+            rc = _cabi.lib().gpblur_elbo_backward_fused(_ptr(mean), _ptr(var), _ptr(y), _ptr(raw_noise), _ptr(g_elbo),
+                                                        float(num_data), B, L, _ptr(g_mean), _ptr(g_var), _ptr(g_noise),
+                                                        _ptr(g_kl), _ptr(scratch), _next_ticket(dev), _stream())
+        else:
+            rc = _cabi.lib().gpblur_elbo_backward(_ptr(mean), _ptr(var), _ptr(y), _ptr(raw_noise), _ptr(g_elbo),
+                                                  float(num_data), B, L, _ptr(g_mean), _ptr(g_var), _ptr(g_noise),
+                                                  _ptr(g_kl), _ptr(scratch), _stream())
     _cabi.check(rc, "gpblur_elbo_backward")
     return g_mean, g_var, g_noise, g_kl
 
@@ -403,6 +426,20 @@ class _Fork:
             self.cur.wait_stream(st)
 
 
+_ZERO64 = {}
+
+
+def _zero64(dev):
+    """One float64 zero per device, created once (a fresh torch.zeros per step is a fill kernel - and a graph node)."""
+    key = (dev.type, dev.index)
+    z = _ZERO64.get(key)
+    if z is None:
+        z = torch.zeros((), device=dev, dtype=torch.float64)
+        if not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            _ZERO64[key] = z                  # (memory of a capture's private pool is not kept across captures)
+    return z
+
+
 class _ParamStageFunction(torch.autograd.Function):
     """Parameters -> (token, kl, info).  `token` is a float64 carrier whose GRADIENT is the stage gradient
     (include/gpblur.h): every per-point call that uses this stage returns its contribution as d/d token, autograd
@@ -453,7 +490,7 @@ class _ParamStageFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(info)
         G = stage_grad_doubles(D, M)
-        token = torch.zeros((), device=dev, dtype=torch.float64).expand((H, G) if batched else (G,))
+        token = _zero64(dev).expand((H, G) if batched else (G,))   # carrier of the stage gradient: never written
         return token, (kl if batched else kl.reshape(())), info
 
     @staticmethod

@@ -189,6 +189,13 @@ int gpblur_elbo_backward(const float* mean, const float* var, const float* y, co
                          float* g_var, float* g_raw_noise, float* g_kl, float* scratch,
                          void* stream);
 
+/* The same in ONE launch: the block that takes the last ticket does the final reduction.  `ticket`: a device word that
+ * is 0 before the first call; the kernel leaves it at 0 (concurrent calls need distinct words).  B >= 1. */
+int gpblur_elbo_backward_fused(const float* mean, const float* var, const float* y, const float* raw_noise,
+                               const float* g_elbo, float num_data, long long B, int L, float* g_mean,
+                               float* g_var, float* g_raw_noise, float* g_kl, float* scratch,
+                               unsigned* ticket, void* stream);
+
 /* Raw Philox4x32-10 words for elements offset .. offset+n-1 (bit-exactness probe): out [n, 4]. */
 int gpblur_philox_bits(uint64_t seed, uint64_t offset, uint32_t stream_id, long long n,
                        uint32_t* out, void* stream);
