@@ -225,6 +225,33 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
 int gpblur_debug_fetch(int which, long long N, int D, int M, const void* ws, void* out,
                        size_t out_bytes, int* mp, void* stream);
 
+/* ---- the steps on either side of the GP blur in one training step ----------
+ * blur application (replaces denoise_model_2.add_gp_noise's `x + self.proj_up(eps_gp.permute(1, 2, 0))`,
+ * /root/reference/denoising_model/denoise_model_2.py:36-38; proj_up = nn.Linear(1, d)):
+ *   out[n, :] = x[n, :] + mean[n] * w_up + b_up          x, out [N, D] row-major, mean [N], w_up, b_up [D]
+ * backward: g_out [N, D] -> g_mean [N], g_w [D], g_b [D] (the gradient of x is g_out itself).
+ * loss assembly (replaces /root/reference/forecast_denoising.py:84, 87-89, 102-104):
+ *   final[n] = h[n, :] . w_f + b_f                        h = rows (b, p) of a [B', P, D] view: h + b * h_bstride + p * D
+ *   scalars  = [loss, mse, mll_error]:  mse = mean_n (y[n] - final[n])^2,  mll_error = -mean_b elbo[b] (elbo [B]),
+ *              loss = mse + clip(lam, 0, 0.005) * mll_error            (y, elbo, lam nullable: their terms are 0)
+ * backward: g_final [N] (nullable), g_loss, g_mse (device scalars, nullable) -> g_h [N, D] (contiguous), g_w [D],
+ *   g_b [1], g_elbo [B], g_lam [1]; torch.clip passes the gradient of lam where 0 <= lam <= 0.005.
+ * `scratch`: gpblur_step_scratch_floats(D) floats; `ticket`: a zeroed device word the kernel leaves at 0. */
+size_t gpblur_step_scratch_floats(int D);
+int gpblur_blur_apply_forward(const float* x, const float* mean, const float* w_up, const float* b_up, long long N,
+                              int D, float* out, void* stream);
+int gpblur_blur_apply_backward(const float* g_out, const float* mean, const float* w_up, long long N, int D,
+                               float* g_mean, float* g_w, float* g_b, float* scratch, unsigned* ticket,
+                               void* stream);
+int gpblur_loss_forward(const float* h, long long h_bstride, int P, const float* w_f, const float* b_f, const float* y,
+                        const float* elbo, long long B, const float* lam, long long N, int D, float* final_out,
+                        float* scalars, float* scratch, unsigned* ticket, void* stream);
+int gpblur_loss_backward(const float* h, long long h_bstride, int P, const float* w_f, const float* y,
+                         const float* final_in, const float* scalars, const float* lam, const float* g_final,
+                         const float* g_loss, const float* g_mse, long long B, long long N, int D, float* g_h,
+                         float* g_w, float* g_b, float* g_elbo, float* g_lam, float* scratch, unsigned* ticket,
+                         void* stream);
+
 /* ---- data-parallel exchange: one-shot all-reduce of the flat gradient bucket over NVLink peer memory -------------
  * (one node, one process per GPU; replaces the all-reduce a torch DistributedDataParallel wrapper would issue for the
  * GP parameters - the reference itself trains on one device.)  Every rank allocates one communication buffer of

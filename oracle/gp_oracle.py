@@ -512,3 +512,25 @@ def make_inputs(B: int, L: int, D: int, seed: int, dtype=torch.float32, layernor
     g_mean = torch.randn(B, L, generator=g)
     g_var = torch.randn(B, L, generator=g)
     return x.to(dtype), y.to(dtype), g_mean.to(dtype), g_var.to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The steps on either side of the GP blur - plain torch, the reference's own ops.
+# ---------------------------------------------------------------------------------------------------------------------
+def blur_apply_reference(x: torch.Tensor, eps_gp: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """denoise_model_2.add_gp_noise, /root/reference/denoising_model/denoise_model_2.py:36-38:
+    ``eps_gp = self.proj_up(eps_gp.permute(1, 2, 0)); x_noisy = x + eps_gp`` with ``eps_gp`` [1, B, L] the blur mean
+    and ``proj_up = nn.Linear(1, d)`` (weight [d, 1], bias [d])."""
+    return x + torch.nn.functional.linear(eps_gp.permute(1, 2, 0), weight, bias)
+
+
+def forecast_loss_reference(h, weight, bias, y_true, elbo, lam):
+    """/root/reference/forecast_denoising.py:84, 87-89, 102-104: ``final_outputs = final_projection(h)`` (nn.Linear(d, 1)
+    on the last pred_len decoder states), ``mll_error = -mll(dist, y).mean()`` (``elbo`` = the [1, B] / [B] output of
+    DeepApproximateMLL(VariationalELBO(...)), see elbo_per_window), ``mse_loss = nn.MSELoss()(y_true, final_outputs)``,
+    ``loss = mse_loss + torch.clip(lam, min=0, max=0.005) * mll_error``.  -> (final_outputs, loss, mse_loss)."""
+    final = torch.nn.functional.linear(h, weight, bias)
+    mll_err = -elbo.mean() if elbo is not None else torch.zeros((), dtype=h.dtype)
+    mse = torch.nn.MSELoss()(y_true, final)
+    loss = mse + torch.clip(lam, min=0, max=0.005) * mll_err
+    return final, loss.reshape(()), mse
