@@ -730,11 +730,11 @@ def measure(args, wl, name, ctx, primary=True):
                   roof = {"bound": "tensor", "achieved": fl / per_launch_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                           "peak_note": "TF32 dense rate = 1/2 of the measured cuBLAS bf16 burst peak; 'achieved' counts "
                                        "ALGORITHMIC flops (a 3xTF32 kernel issues 3 MMAs per product, so its "
-                                       "ceiling is frac = 1/3; M <= 64 runs FP32 FFMA, peak ~74 TFLOP/s)"}
+                                       "ceiling is frac = 1/3; M <= 32 runs FP32 FFMA, peak ~74 TFLOP/s)"}
               roof["frac"] = roof["achieved"] / roof["peak"]
-              if roof["bound"] == "tensor" and M > 64 and dom in point_stages:
+              if roof["bound"] == "tensor" and M > 32 and dom in point_stages:
                   roof["frac_of_3xtf32_ceiling"] = 3.0 * roof["frac"]
-              if M <= 64 and dom in point_stages:     # FP32-FFMA path: CUDA-core bound long before HBM
+              if M <= 32 and dom in point_stages:     # FP32-FFMA path: CUDA-core bound long before HBM
                   roof["ffma_tflops_achieved"] = fl / per_launch_s / 1e12
                   roof["ffma_frac_of_74_tflops"] = roof["ffma_tflops_achieved"] / 74.0
               if dom in ("mm_fwd", "mm_bwd", "sg_reduce"):

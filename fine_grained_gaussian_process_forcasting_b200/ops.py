@@ -232,7 +232,7 @@ def rbf_covariance(x1: Tensor, x2: Tensor, raw_lengthscale: Tensor, raw_outputsc
 def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:
     """Test probe: 0 = L, 1 = Linv, 2 = Kzz + jitter (float64 [Mp, Mp]); 3 = A (float32 [N, Mp])."""
     mp = C.c_int(0)
-    Mp = 32 if M <= 32 else 64 if M <= 64 else 128 if M <= 128 else (M + 255) // 256 * 256
+    Mp = 32 if M <= 32 else 128 if M <= 128 else (M + 255) // 256 * 256
     if which == 4:
         out = torch.empty(32, device=ws.device, dtype=torch.int64)
     elif which in (3, 5):

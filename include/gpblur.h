@@ -252,6 +252,17 @@ int gpblur_loss_backward(const float* h, long long h_bstride, int P, const float
                          float* g_w, float* g_b, float* g_elbo, float* g_lam, float* scratch, unsigned* ticket,
                          void* stream);
 
+/* ---- window sampler on the device -------------------------------------------------
+ * Replaces the per-window host materialisation of /root/reference/Utils/base_train.py:67-97 (sample_train_val_test:
+ * one .iloc slice per sampled window) and the per-batch .to(device) of /root/reference/train.py:160-161.
+ * table [rows, F] fp32 row-major: the encoder-input columns of the (id, time)-ordered series, entities back to back;
+ * target [rows]: the target column; starts [B] int64: first table row of each window of T = time_steps rows
+ * (< 0: the window stays zero-filled, as the reference's pre-zeroed arrays do when max_samples exceeds the number of
+ * valid sampling locations).  Outputs: enc [B, n_enc, F] (`enc_inputs`), dec [B, T - n_enc - pred_len, F]
+ * (`dec_inputs`, may be NULL when empty), y [B, pred_len] (`outputs[:, -pred_len:, :]`).  Bit-exact copies. */
+int gpblur_window_gather(const float* table, const float* target, long long rows, int F, const long long* starts,
+                         long long B, int T, int n_enc, int pred_len, float* enc, float* dec, float* y, void* stream);
+
 /* ---- data-parallel exchange: one-shot all-reduce of the flat gradient bucket over NVLink peer memory -------------
  * (one node, one process per GPU; replaces the all-reduce a torch DistributedDataParallel wrapper would issue for the
  * GP parameters - the reference itself trains on one device.)  Every rank allocates one communication buffer of

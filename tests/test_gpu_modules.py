@@ -432,33 +432,37 @@ def test_anomaly_mode_and_concurrent_threads(cuda):
 
     def worker(k):
         try:
-            with gpcompat.num_likelihood_samples(1):
-                model = DeepGPp(D, 100 + k, num_inducing=M).to(cuda)
-                load_params(model, p)
-                for _ in range(3):
-                    xd = x.to(cuda).requires_grad_(True)
-                    m_enc, _ = model.predict(xd)                 # two calls on one stage, like the reference
-                    _, dist = model.predict(xd)
-                    mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
-                    loss = -mll(dist, y.to(cuda).unsqueeze(0)).mean() + m_enc.mean()
-                    model.zero_grad()
-                    loss.backward()
-                torch.cuda.synchronize()
-                g = model.hidden_layer.variational_strategy.inducing_points.grad
-                assert torch.isfinite(g).all() and torch.isfinite(xd.grad).all()
-                results[k] = (loss.item(), g.double().cpu())
+            model = DeepGPp(D, 100 + k, num_inducing=M).to(cuda)
+            load_params(model, p)
+            for _ in range(3):
+                xd = x.to(cuda).requires_grad_(True)
+                m_enc, _ = model.predict(xd)                 # two calls on one stage, like the reference
+                _, dist = model.predict(xd)
+                mll = gpcompat.DeepApproximateMLL(gpcompat.VariationalELBO(model.likelihood, model, D))
+                loss = -mll(dist, y.to(cuda).unsqueeze(0)).mean() + m_enc.mean()
+                model.zero_grad()
+                loss.backward()
+            torch.cuda.synchronize()
+            g = model.hidden_layer.variational_strategy.inducing_points.grad
+            assert torch.isfinite(g).all() and torch.isfinite(xd.grad).all()
+            results[k] = (loss.item(), g.double().cpu())
         except Exception as e:    # pragma: no cover
             errors.append(repr(e))
 
     # anomaly mode is a process-global switch (the reference flips it at import): set it around the threads, not
     # inside them, and restore it - a leaked anomaly mode would break CUDA-graph capture in later tests
+    # The same holds for num_likelihood_samples: like gpytorch's settings it is a PROCESS-wide value, and the reference
+    # enters it once around everything (train.py:20).  Entered per thread, the first thread to leave restored 10 while
+    # the others were still in their last step (valid, but S = 10 accumulates the gradients in another order: this
+    # test then failed about once in five runs).
     torch.autograd.set_detect_anomaly(True, check_nan=True)
     try:
-        threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        with gpcompat.num_likelihood_samples(1):
+            threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
     finally:
         torch.autograd.set_detect_anomaly(False)
     assert not errors, errors
