@@ -263,6 +263,24 @@ int gpblur_loss_backward(const float* h, long long h_bstride, int P, const float
 int gpblur_window_gather(const float* table, const float* target, long long rows, int F, const long long* starts,
                          long long B, int T, int n_enc, int pred_len, float* enc, float* dec, float* y, void* stream);
 
+/* ---- core of the ATA attention head ------------------------------------------------
+ * Replaces /root/reference/forecasting_models/ATA.py:53-65 (two topk(k = 1) poolings, einsum / sqrt(d_k), softmax,
+ * einsum) as called from /root/reference/modules/multi_head_attention.py:49-51.  The score matrix is rank one after
+ * the pooling; scores / attn [B, H, Lq, Lk] are never materialised.
+ *   qp [B, H, Lq, G], kp [B, H, Lk, G]  the multi-scale conv outputs as the reference reshapes them (G = 4 d_k),
+ *   v  element (b, h, j, e) at v + b v_sb + h v_sh + j v_sl + e (the [B, Lk, H, DV] memory of `v_s`), DV <= 64,
+ *   scale = 1 / sqrt(d_k);   ctx [B, Lq, H, DV] (= context.transpose(1, 2): what multi_head_attention.py:95 makes
+ *   contiguous);  saved for the backward: q_pool / q_arg / lse [B, H, Lq], k_pool / k_arg [B, H, Lk].
+ * backward: g_ctx [B, Lq, H, DV] -> g_qp, g_kp (pooled gradient at the arg-max element of each group, zeros
+ * elsewhere: topk's backward), g_v [B, Lk, H, DV].  16-byte aligned qp / kp / g_qp / g_kp when G % 4 == 0. */
+int gpblur_ata_forward(const float* qp, const float* kp, const float* v, long long v_sb, long long v_sh, long long v_sl,
+                       int B, int H, int Lq, int Lk, int G, int DV, float scale, float* ctx, float* q_pool,
+                       float* k_pool, int* q_arg, int* k_arg, float* lse, void* stream);
+int gpblur_ata_backward(const float* g_ctx, const float* ctx, const float* v, long long v_sb, long long v_sh,
+                        long long v_sl, const float* q_pool, const float* k_pool, const int* q_arg, const int* k_arg,
+                        const float* lse, int B, int H, int Lq, int Lk, int G, int DV, float scale, float* g_qp,
+                        float* g_kp, float* g_v, void* stream);
+
 /* ---- data-parallel exchange: one-shot all-reduce of the flat gradient bucket over NVLink peer memory -------------
  * (one node, one process per GPU; replaces the all-reduce a torch DistributedDataParallel wrapper would issue for the
  * GP parameters - the reference itself trains on one device.)  Every rank allocates one communication buffer of
