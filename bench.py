@@ -367,6 +367,10 @@ def run_ours(args, wl, name):
                 extra[other] = sub
         if rank == 0:
             line["workloads"] = extra
+            try:
+                line["next_rows"] = measure_next_rows(device, load_peaks())
+            except Exception as e:      # the headline line must survive a failure of the side measurements
+                line["next_rows"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -795,6 +799,139 @@ def measure(args, wl, name, ctx, primary=True):
                                             "counters of a window depend on its rank's offset)")
         return line
     return None
+
+
+# --------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rows on either side of the GP blur: each kernel timed alone (CUDA events per launch on the launching
+# stream, L2 flushed between launches, median), ALGORITHMIC bytes / time against the measured HBM peak, and the same
+# operation done the reference's way beside it (torch eager ops on the same GPU = the library baseline; host pandas
+# slicing for the sampler)
+# --------------------------------------------------------------------------------------------------
+def measure_next_rows(device, peaks, reps=12):
+    import numpy as np
+    from fine_grained_gaussian_process_forcasting_b200 import ATA as ata_mod
+    from fine_grained_gaussian_process_forcasting_b200 import base_train as bt
+    from fine_grained_gaussian_process_forcasting_b200 import step_ops
+    flush = torch.empty(L2_FLUSH_BYTES // 4, device=device)
+
+    def timed(fn):
+        # launches replayed from a CUDA graph (as the GP step is): the interval holds the kernels, not Python
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        del graph
+        return float(np.median(ts))
+
+    def row(t, by, **kw):
+        d = {"ms": t * 1e3, "algorithmic_bytes": int(by), "achieved_gbs": by / t / 1e9,
+             "hbm_frac": by / t / 1e9 / peaks["hbm_gbs"]}
+        d.update(kw)
+        return d
+
+    out = {"timing": "each operation captured once and replayed as a CUDA graph; CUDA events per replay, median of %d, "
+                     "%d MiB L2 flush before every replay" % (reps, L2_FLUSH_BYTES >> 20)}
+    g = torch.Generator(device=device).manual_seed(99)
+    # ---- rank 4: window gather, traffic shape (time_steps 240 = 192 + 24 + 24, F = 4), one epoch of 256-window batches
+    rows, F, T, ne, pl = 1 << 20, 4, 240, 192, 24
+    rs = np.random.RandomState(3)
+    nwin = 65536
+    ws = bt.WindowSet(rs.randn(rows, F).astype(np.float32), rs.randn(rows).astype(np.float32),
+                      rs.randint(0, rows - T, size=nwin).astype(np.int64), T, ne, pl, device=device)
+    per_win = ((T - pl) * F + pl) * 4 * 2                     # every gathered float is read once and written once
+    t_epoch = timed(lambda: ws.gather(0, nwin))
+    t_batch = timed(lambda: ws.gather(0, 256))
+    t0 = time.perf_counter()                                  # the reference's way: one slice + copy per window on the host
+    nh = 2048
+    enc = np.zeros((nh, ne, F)); dec = np.zeros((nh, T - ne - pl, F)); yy = np.zeros((nh, pl, 1))
+    for i, st in enumerate(ws.starts_host[:nh]):
+        enc[i] = ws.table_host[st:st + ne]; dec[i] = ws.table_host[st + ne:st + T - pl]; yy[i, :, 0] = ws.target_host[st + T - pl:st + T]
+    t_host = (time.perf_counter() - t0) / nh
+    out["window_gather"] = row(t_epoch, per_win * nwin, windows=nwin, windows_per_s=nwin / t_epoch,
+                               batch256_us=t_batch * 1e6,
+                               host_numpy_windows_per_s=1.0 / t_host,
+                               note="host figure: numpy slice + copy per window (the reference slices a pandas frame "
+                                    "per window, slower still) and excludes its per-batch .to(device)")
+    # ---- rank 1: blur application x + proj_up(mean), c2 shape
+    N, D = 256 * (192 + 24), 64
+    x = torch.randn(N, D, device=device, generator=g, requires_grad=True)
+    mean = torch.randn(N, device=device, generator=g, requires_grad=True)
+    up = torch.nn.Linear(1, D).to(device)
+    go = torch.randn(N, D, device=device, generator=g)
+
+    def fused_blur():
+        o = step_ops.blur_apply(x, mean, up.weight, up.bias)
+        torch.autograd.grad(o, (x, mean, up.weight, up.bias), go)
+
+    def eager_blur():
+        o = x + up(mean.unsqueeze(-1))
+        torch.autograd.grad(o, (x, mean, up.weight, up.bias), go)
+
+    by = N * D * 4 * 3 + N * 4 * 3                           # fwd: x in, out; bwd: g_out in (+ mean in / g_mean out)
+    out["blur_apply_fwd_bwd"] = row(timed(fused_blur), by, torch_eager_ms=timed(eager_blur) * 1e3)
+    # ---- rank 2: loss assembly (final projection + MSE + clipped-lambda ELBO term), decoder states of configs[1] and
+    # the same at 32 x the batch (the c2 shape is one launch latency: 6 144 rows)
+    for tag, Bl in (("loss_assembly_fwd_bwd", 256), ("loss_assembly_fwd_bwd_B8192", 8192)):
+        P = 24
+        hdec = torch.randn(Bl, 48, D, device=device, generator=g, requires_grad=True)
+        yt = torch.randn(Bl, P, 1, device=device, generator=g)
+        elbo = torch.randn(Bl, device=device, generator=g, requires_grad=True)
+        lam = torch.full((1,), 0.003, device=device, requires_grad=True)
+        fin = torch.nn.Linear(D, 1).to(device)
+
+        def fused_loss():
+            f, loss, mse = step_ops.forecast_loss(fin, hdec[:, -P:, :], yt, elbo, lam)
+            torch.autograd.grad(loss, (hdec, fin.weight, fin.bias, elbo, lam))
+
+        def eager_loss():                                      # forecast_denoising.py:84, 87-89, 102-104
+            f = fin(hdec[:, -P:, :])
+            mll_error = -elbo.mean()
+            mse = torch.nn.functional.mse_loss(yt, f)
+            loss = mse + torch.clip(lam, min=0, max=0.005) * mll_error
+            torch.autograd.grad(loss, (hdec, fin.weight, fin.bias, elbo, lam))
+
+        by = Bl * P * D * 4 * 3                                # h read forward and backward, g_h written
+        out[tag] = row(timed(fused_loss), by, torch_eager_ms=timed(eager_loss) * 1e3, rows=Bl * P)
+    # ---- rank 3: ATA core, encoder self-attention of configs[1] (b = 256, 8 heads, l = l_k = 192, d_k = d_v = 4)
+    b, h, l, dk = 256, 8, 192, 4
+    qp = torch.relu(torch.randn(b, h, l, 4 * dk, device=device, generator=g)).requires_grad_(True)
+    kp = torch.relu(torch.randn(b, h, l, 4 * dk, device=device, generator=g)).requires_grad_(True)
+    v = torch.randn(b, l, h, dk, device=device, generator=g).transpose(1, 2).requires_grad_(True)
+    gc = torch.randn(b, h, l, dk, device=device, generator=g)
+
+    def fused_ata():
+        c = ata_mod.ata_core(qp, kp, v, dk)[0]
+        torch.autograd.grad(c, (qp, kp, v), gc)
+
+    def eager_ata():                                          # ATA.py:56-65 verbatim
+        Q, _ = torch.topk(qp, dim=-1, k=1)
+        K, _ = torch.topk(kp, dim=-1, k=1)
+        scores = torch.einsum('bhqd,bhkd->bhqk', Q, K) / np.sqrt(dk)
+        attn = torch.softmax(scores, -1)
+        c = torch.einsum('bhqk,bhkd->bhqd', attn, v)
+        torch.autograd.grad(c, (qp, kp, v), gc)
+
+    by = (2 * b * h * l * 4 * dk * 2 + b * h * l * dk * 4) * 4    # q_proj, k_proj in + their gradients out; V, ctx, g_ctx, g_V
+    out["ata_core_fwd_bwd"] = row(timed(fused_ata), by, torch_eager_ms=timed(eager_ata) * 1e3,
+                                  attn_bytes_never_materialised=b * h * l * l * 4,
+                                  note="exp / FMA bound on the CUDA cores (2 x b h l l_k exp per step), not HBM bound")
+    return out
+
 
 
 def main():

@@ -60,13 +60,41 @@ __global__ void __launch_bounds__(kStepThreads) blur_apply_fwd_kernel(const floa
   const bool vec = (D & 3) == 0, on = d < D;
   const float4 w = on ? ld4(w_up, d, D, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 b = on ? ld4(b_up, d, D, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long n = (long long)blockIdx.x * rpi + rloc; n < N; n += (long long)gridDim.x * rpi) {
-    if (!on) continue;
-    const float m = mean[n];
-    const float4 xv = ld4(x + n * D, d, D, vec);
-    st4(out + n * D, d, D, vec,
-        make_float4(fmaf(m, w.x, xv.x + b.x), fmaf(m, w.y, xv.y + b.y), fmaf(m, w.z, xv.z + b.z), fmaf(m, w.w, xv.w + b.w)));
+  if (!on) return;
+  // four rows per thread and iteration: all their loads are issued before the first store (a single 16-byte load in
+  // flight per thread left the kernel latency-bound at ~0.7 TB/s)
+  constexpr int U = 8;
+  const long long stride = (long long)gridDim.x * rpi;
+  for (long long n0 = (long long)blockIdx.x * rpi + rloc; n0 < N; n0 += U * stride) {
+    float m[U];
+    float4 xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = n0 + u * stride;
+      if (n < N) { m[u] = mean[n]; xv[u] = ld4(x + n * D, d, D, vec); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = n0 + u * stride;
+      if (n < N)
+        st4(out + n * D, d, D, vec,
+            make_float4(fmaf(m[u], w.x, xv[u].x + b.x), fmaf(m[u], w.y, xv[u].y + b.y), fmaf(m[u], w.z, xv[u].z + b.z),
+                        fmaf(m[u], w.w, xv[u].w + b.w)));
+    }
   }
+}
+
+// Sum of one double per thread over the CTA in a FIXED tree order (bit-deterministic); valid in every thread.
+__device__ __forceinline__ double block_sum_fixed(double v) {
+  __shared__ double bs[kStepThreads];
+  __syncthreads();                       // a previous use of bs is over
+  bs[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = kStepThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) bs[threadIdx.x] += bs[threadIdx.x + o];
+    __syncthreads();
+  }
+  return bs[0];
 }
 
 // Shared tail of the reducing kernels: per-thread column partials (two float4 per thread: `a` and `b` sums of its 4
@@ -103,10 +131,21 @@ __device__ __forceinline__ bool column_totals(float4 sa, float4 sb, int tpr, int
   __threadfence();
   for (int i = threadIdx.x; i < 2 * Dp; i += kStepThreads) {
     const int which = i / Dp, c = i - which * Dp;
-    double t = 0.0;
-    for (unsigned g = 0; g < gridDim.x; ++g)
-      t += (double)*reinterpret_cast<const volatile float*>(partial + ((size_t)g * 2 + which) * Dp + c);
-    tot[which][c] = (float)t;
+    // four independent chains over g = 0, 4, 8, ... | 1, 5, ... | ... (fixed order), L2 loads (__ldcg: the partials were
+    // written by other CTAs and fenced), so that many loads are in flight: one serial chain of ~600 loads cost 20 us
+    const float* src = partial + (size_t)which * Dp + c;
+    const size_t gs = (size_t)2 * Dp;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    unsigned g = 0;
+#pragma unroll 4
+    for (; g + 4 <= gridDim.x; g += 4) {
+      t0 += (double)__ldcg(src + (size_t)g * gs);
+      t1 += (double)__ldcg(src + (size_t)(g + 1) * gs);
+      t2 += (double)__ldcg(src + (size_t)(g + 2) * gs);
+      t3 += (double)__ldcg(src + (size_t)(g + 3) * gs);
+    }
+    for (; g < gridDim.x; ++g) t0 += (double)__ldcg(src + (size_t)g * gs);
+    tot[which][c] = (float)((t0 + t1) + (t2 + t3));
   }
   __syncthreads();
   (void)D;
@@ -127,16 +166,28 @@ __global__ void __launch_bounds__(kStepThreads) blur_apply_bwd_kernel(const floa
   const float4 w = on ? ld4(w_up, d, D, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 sw = make_float4(0.f, 0.f, 0.f, 0.f), sb = sw;
   const long long n_iter = (N + rpi - 1) / rpi;
-  for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {      // whole row groups: shuffles stay convergent
-    const long long n = it * rpi + rloc;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    float m = 0.f;
-    if (n < N && on) { g = ld4(g_out + n * D, d, D, vec); m = mean[n]; }
-    float dot = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
-    dot = group_sum(dot, tpr);
-    if (n < N && sub == 0) g_mean[n] = dot;
-    sw.x = fmaf(m, g.x, sw.x); sw.y = fmaf(m, g.y, sw.y); sw.z = fmaf(m, g.z, sw.z); sw.w = fmaf(m, g.w, sw.w);
-    sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+  constexpr int U = 8;                                                 // loads of eight row groups in flight per thread
+  for (long long it0 = blockIdx.x; it0 < n_iter; it0 += (long long)U * gridDim.x) {   // whole row groups: shuffles stay convergent
+    float4 gu[U];
+    float mu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      gu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mu[u] = 0.f;
+      if (n < N && on) { gu[u] = ld4(g_out + n * D, d, D, vec); mu[u] = mean[n]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      const float4 g = gu[u];
+      const float m = mu[u];
+      float dot = g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+      dot = group_sum(dot, tpr);
+      if (n < N && sub == 0) g_mean[n] = dot;
+      sw.x = fmaf(m, g.x, sw.x); sw.y = fmaf(m, g.y, sw.y); sw.z = fmaf(m, g.z, sw.z); sw.w = fmaf(m, g.w, sw.w);
+      sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+    }
   }
   __shared__ float tot[2][128];
   if (!column_totals(sw, sb, tpr, D, partial, ticket, tot)) return;
@@ -162,27 +213,31 @@ __global__ void __launch_bounds__(kStepThreads) loss_fwd_kernel(const float* __r
   const float bf = b_f[0];
   float se = 0.f;
   const long long n_iter = (N + rpi - 1) / rpi;
-  for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    const long long n = it * rpi + rloc;
-    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N && on) hv = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
-    float dot = hv.x * w.x + hv.y * w.y + hv.z * w.z + hv.w * w.w;
-    dot = group_sum(dot, tpr);
-    if (n < N && sub == 0) {
-      const float f = dot + bf;
-      final_out[n] = f;
-      if (y) { const float e = y[n] - f; se = fmaf(e, e, se); }
+  constexpr int U = 8;                                                 // loads of eight row groups in flight per thread
+  for (long long it0 = blockIdx.x; it0 < n_iter; it0 += (long long)U * gridDim.x) {
+    float4 hu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      hu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < N && on) hu[u] = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      const float4 hv = hu[u];
+      float dot = hv.x * w.x + hv.y * w.y + hv.z * w.z + hv.w * w.w;
+      dot = group_sum(dot, tpr);
+      if (n < N && sub == 0) {
+        const float f = dot + bf;
+        final_out[n] = f;
+        if (y) { const float e = y[n] - f; se = fmaf(e, e, se); }
+      }
     }
   }
   // squared-error partial of the CTA (fixed order), then the last block finishes
-  __shared__ float sred[kStepThreads];
-  sred[threadIdx.x] = se;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < kStepThreads; ++i) t += sred[i];
-    partial[blockIdx.x] = t;
-  }
+  const double cta_se = block_sum_fixed((double)se);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (float)cta_se;
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -190,13 +245,17 @@ __global__ void __launch_bounds__(kStepThreads) loss_fwd_kernel(const float* __r
     last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!last || threadIdx.x != 0) return;
+  if (!last) return;
   __threadfence();
+  // the last block: all its threads sum strided subsets (fixed order), then the fixed tree
   double sse = 0.0;
-  for (unsigned g = 0; g < gridDim.x; ++g) sse += (double)*reinterpret_cast<const volatile float*>(partial + g);
+  for (unsigned g = threadIdx.x; g < gridDim.x; g += kStepThreads) sse += (double)__ldcg(partial + g);
+  sse = block_sum_fixed(sse);
   double es = 0.0;
   if (elbo)
-    for (long long b = 0; b < B; ++b) es += (double)elbo[b];
+    for (long long b = threadIdx.x; b < B; b += kStepThreads) es += (double)elbo[b];
+  es = block_sum_fixed(es);
+  if (threadIdx.x != 0) return;
   const double mse = y ? sse / (double)N : 0.0;
   const double mll_error = elbo ? -es / (double)B : 0.0;
   const float lm = lam ? lam[0] : 0.f;
@@ -230,15 +289,32 @@ __global__ void __launch_bounds__(kStepThreads) loss_bwd_kernel(const float* __r
   const float c2 = y ? (gl + gm) * 2.0f / (float)N : 0.f;
   float4 sw = make_float4(0.f, 0.f, 0.f, 0.f), sb = sw;
   const long long n_iter = (N + rpi - 1) / rpi;
-  for (long long it = blockIdx.x; it < n_iter; it += gridDim.x) {
-    const long long n = it * rpi + rloc;
-    if (n >= N || !on) continue;
-    float gf = g_final ? g_final[n] : 0.f;
-    if (y) gf = fmaf(c2, final_in[n] - y[n], gf);
-    const float4 hv = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
-    if (g_h) st4(g_h + n * D, d, D, vecw, make_float4(gf * w.x, gf * w.y, gf * w.z, gf * w.w));
-    sw.x = fmaf(gf, hv.x, sw.x); sw.y = fmaf(gf, hv.y, sw.y); sw.z = fmaf(gf, hv.z, sw.z); sw.w = fmaf(gf, hv.w, sw.w);
-    if (sub == 0) sb.x += gf;
+  constexpr int U = 8;                                                 // loads of eight row groups in flight per thread
+  for (long long it0 = blockIdx.x; it0 < n_iter; it0 += (long long)U * gridDim.x) {
+    float4 hu[U];
+    float gfu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      hu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gfu[u] = 0.f;
+      if (n < N && on) {
+        float gf = g_final ? g_final[n] : 0.f;
+        if (y) gf = fmaf(c2, final_in[n] - y[n], gf);
+        gfu[u] = gf;
+        hu[u] = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
+      if (n >= N || !on) continue;
+      const float gf = gfu[u];
+      const float4 hv = hu[u];
+      if (g_h) st4(g_h + n * D, d, D, vecw, make_float4(gf * w.x, gf * w.y, gf * w.z, gf * w.w));
+      sw.x = fmaf(gf, hv.x, sw.x); sw.y = fmaf(gf, hv.y, sw.y); sw.z = fmaf(gf, hv.z, sw.z); sw.w = fmaf(gf, hv.w, sw.w);
+      if (sub == 0) sb.x += gf;
+    }
   }
   // elbo / lam gradients: a few elements, block 0
   if (blockIdx.x == 0) {
@@ -259,7 +335,8 @@ int step_grid(long long N, int D) {
   while (tpr * 4 < D) tpr <<= 1;
   const int rpi = kStepThreads / tpr;
   long long g = (N + rpi - 1) / rpi;
-  const long long cap = 4 * 148;                 // 4 CTAs per SM: enough loads in flight to stream from HBM
+  const long long cap = 2 * 148;                 // 2 CTAs per SM x 8 row groups in flight per thread (~10 MB of loads in
+                                                 // flight); few CTAs keep the last block's pass over the partials short
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
