@@ -81,9 +81,20 @@ int num_sms() {
   return cache[dev];
 }
 
+// Tuning knobs (tile heights, GPBLUR_TC=-1): the environment is read ONCE per knob, not on every launch.  Callers
+// pass string literals: a handful of distinct pointers, cached in a small table.
 int tile_override(const char* env) {
+  static std::mutex mu;
+  static const char* names[8];
+  static int values[8];
+  static int n = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  for (int i = 0; i < n; ++i)
+    if (names[i] == env) return values[i];
   const char* v = getenv(env);
-  return v ? atoi(v) : 0;
+  const int val = v ? atoi(v) : 0;
+  if (n < 8) { names[n] = env; values[n] = val; ++n; }
+  return val;
 }
 
 int bwd_vector_partials(const WsLayout& L);

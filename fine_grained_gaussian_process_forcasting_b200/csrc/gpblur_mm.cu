@@ -1446,7 +1446,11 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   if (want < 8) want = 8;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
+#ifdef GPBLUR_TRACE   // developer builds only (scripts/mm_only.py, mm_step_probe.py): the kernel returns after a phase
   static const int dbg_stop = [] { const char* e = getenv("GPBLUR_MM_STOP"); return e ? atoi(e) : -1; }();
+#else
+  const int dbg_stop = -1;
+#endif
   unsigned* sync_words = reinterpret_cast<unsigned*>(ws_ptr<unsigned long long>(ws, L.stamps) + 14);   // 4 words
   MmFwdArgs args{p, L, ws, kl, info, extra_jitter, nullptr, dbg_stop, sync_words + 1};
   ProfScope ps(ST_MM_FWD, st);
