@@ -196,18 +196,36 @@ def sample_train_val_test(ddf, max_samples, time_steps, num_encoder_steps, pred_
 
 class DeviceWindowLoader:
     """What ``torch.utils.data.DataLoader(TensorDataset(enc, dec, y), batch_size, drop_last=True)`` yields
-    (base_train.py:149-151) - consecutive batches in sample order, the ragged tail dropped - gathered on the device."""
+    (base_train.py:149-151) - consecutive batches in sample order, the ragged tail dropped - gathered on the device.
 
-    def __init__(self, windows: WindowSet, batch_size: int, drop_last: bool = True):
+    ``shard=(rank, world)`` (keyword, data-parallel training): every rank walks the SAME global
+    batches and gathers only its contiguous slice of each (``distributed.shard_range``), so the union over the ranks is
+    exactly the single-device batch and the Philox / window indices stay global."""
+
+    def __init__(self, windows: WindowSet, batch_size: int, drop_last: bool = True, *, shard: Tuple[int, int] = (0, 1)):
         self.windows, self.batch_size, self.drop_last = windows, int(batch_size), bool(drop_last)
+        rank, world = int(shard[0]), int(shard[1])
+        if not 0 <= rank < world:
+            raise ValueError(f"shard {shard}: need 0 <= rank < world")
+        self.shard = (rank, world)
 
     def __len__(self) -> int:
         n = len(self.windows)
         return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
 
+    def batch_range(self, i: int) -> Tuple[int, int]:
+        """[lo, hi) of this rank's windows in global batch i."""
+        lo = i * self.batch_size
+        hi = min(len(self.windows), lo + self.batch_size)
+        rank, world = self.shard
+        n = hi - lo
+        base, extra = divmod(n, world)                    # the first `extra` ranks take one more window
+        start = lo + rank * base + min(rank, extra)
+        return start, start + base + (1 if rank < extra else 0)
+
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         for i in range(len(self)):
-            yield self.windows.gather(i * self.batch_size, (i + 1) * self.batch_size)
+            yield self.windows.gather(*self.batch_range(i))
 
 
 def sampled_windows(data, train_percent, max_samples, time_steps, num_encoder_steps, pred_len, column_definition,
@@ -234,13 +252,15 @@ def sampled_windows(data, train_percent, max_samples, time_steps, num_encoder_st
 
 
 def batch_sampled_data(data, train_percent, max_samples, time_steps, num_encoder_steps, pred_len, column_definition,
-                       batch_size, tgt_all=False, device: Optional[torch.device] = None):
+                       batch_size, tgt_all=False, device: Optional[torch.device] = None,
+                       shard: Tuple[int, int] = (0, 1)):
     """/root/reference/Utils/base_train.py:100-153: three loaders (train, valid, test) of ``batch_size`` windows,
-    ``drop_last=True``.  ``device`` (keyword, default: the current CUDA device) is where the tables live."""
+    ``drop_last=True``.  ``device`` (keyword, default: the current CUDA device) is where the tables live;
+    ``shard=(rank, world)``: this rank's slice of every global batch (see DeviceWindowLoader)."""
     if device is None:
         if not torch.cuda.is_available():
             raise RuntimeError("batch_sampled_data: no CUDA device (B200 / sm_100a); there is no CPU fallback")
         device = torch.device("cuda", torch.cuda.current_device())
     sets = sampled_windows(data, train_percent, max_samples, time_steps, num_encoder_steps, pred_len, column_definition,
                            tgt_all, device=device)
-    return tuple(DeviceWindowLoader(s, batch_size) for s in sets)
+    return tuple(DeviceWindowLoader(s, batch_size, shard=shard) for s in sets)

@@ -197,6 +197,18 @@ __global__ void __launch_bounds__(kStepThreads) blur_apply_bwd_kernel(const floa
   }
 }
 
+// offset of row n = (b, p) of a [B', P, D] view with batch stride h_bstride.  The 64-bit division cost ~150 instructions
+// per row (more than the rest of the row's work): rows are counted in 32 bits whenever they fit, and a contiguous view
+// needs no division at all.
+__device__ __forceinline__ long long row_offset(long long n, int P, long long h_bstride, int D, bool small) {
+  if (h_bstride == (long long)P * D) return n * D;
+  if (small) {
+    const unsigned q = (unsigned)n / (unsigned)P, r = (unsigned)n - q * (unsigned)P;
+    return (long long)q * h_bstride + (long long)r * D;
+  }
+  return (n / P) * h_bstride + (n % P) * (long long)D;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // final[n] = h[n, :] . w_f + b_f ; partial sums of (y - final)^2 ; the last block: mse, mll_error, loss
 __global__ void __launch_bounds__(kStepThreads) loss_fwd_kernel(const float* __restrict__ h, long long h_bstride, int P,
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(kStepThreads) loss_fwd_kernel(const float* __r
     for (int u = 0; u < U; ++u) {
       const long long n = (it0 + (long long)u * gridDim.x) * rpi + rloc;
       hu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < N && on) hu[u] = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
+      if (n < N && on) hu[u] = ld4(h + row_offset(n, P, h_bstride, D, N < (1ll << 31)), d, D, vec);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(kStepThreads) loss_bwd_kernel(const float* __r
         float gf = g_final ? g_final[n] : 0.f;
         if (y) gf = fmaf(c2, final_in[n] - y[n], gf);
         gfu[u] = gf;
-        hu[u] = ld4(h + (n / P) * h_bstride + (n % P) * (long long)D, d, D, vec);
+        hu[u] = ld4(h + row_offset(n, P, h_bstride, D, N < (1ll << 31)), d, D, vec);
       }
     }
 #pragma unroll

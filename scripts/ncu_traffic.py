@@ -16,7 +16,11 @@ def stage_of(name):
     return None
 def unit_scale(u):
     return {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-out = {}
+import os
+out = json.load(open("profiles/ncu_traffic.json")) if os.path.exists("profiles/ncu_traffic.json") else {}   # other workloads are kept
+for w_ in {a.split(":")[1] for a in sys.argv[1:]}:
+    out.pop(w_, None)
+fresh = set()
 for rep, workload in [a.split(":") for a in sys.argv[1:]]:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
@@ -28,9 +32,12 @@ for rep, workload in [a.split(":") for a in sys.argv[1:]]:
             continue
         b = float(row[ir]) * unit_scale(units[ir]) + float(row[iw]) * unit_scale(units[iw])
         ms = float(row[it]) * {"us": 1e-3, "ms": 1, "ns": 1e-6, "s": 1e3}.get(units[it], 1)
+        fresh.add(workload)
         d = out.setdefault(workload, {}).setdefault(st, {"bytes": 0.0, "ms": 0.0, "launches": 0, "kernel": row[ik][:80]})
         d["bytes"] += b; d["ms"] += ms; d["launches"] += 1
-for w in out.values():
+for wn, w in out.items():
+    if wn not in fresh:
+        continue
     for d in w.values():
         d["bytes_per_launch"] = d.pop("bytes") / d["launches"]
         d["ms_per_launch"] = d.pop("ms") / d["launches"]

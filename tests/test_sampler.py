@@ -92,6 +92,26 @@ def test_host_contract():
     assert ident.shape == (len(ws), c["time_steps"], 1) and ident.dtype == object
 
 
+def test_loader_shards_partition_every_batch():
+    """Data-parallel loaders: the ranks' slices of a global batch are disjoint, contiguous, in rank order and agree with
+    distributed.shard_range."""
+    from fine_grained_gaussian_process_forcasting_b200.distributed import shard_range
+    c = CASES["ragged"]
+    ws = quiet(BT.sampled_windows, make_frame(c), *args_of(c), column_definition())[0]
+    for world in (1, 2, 3, 8):
+        loaders = [BT.DeviceWindowLoader(ws, c["batch_size"], shard=(r, world)) for r in range(world)]
+        for i in range(len(loaders[0])):
+            pos = i * c["batch_size"]
+            for r, ld in enumerate(loaders):
+                lo, hi = ld.batch_range(i)
+                st, cnt = shard_range(c["batch_size"], r, world)
+                assert (lo, hi) == (i * c["batch_size"] + st, i * c["batch_size"] + st + cnt) and lo == pos
+                pos = hi
+            assert pos == (i + 1) * c["batch_size"]
+    with pytest.raises(ValueError):
+        BT.DeviceWindowLoader(ws, 4, shard=(2, 2))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.fixture
 def cuda():
