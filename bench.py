@@ -930,6 +930,40 @@ def measure_next_rows(device, peaks, reps=12):
     out["ata_core_fwd_bwd"] = row(timed(fused_ata), by, torch_eager_ms=timed(eager_ata) * 1e3,
                                   attn_bytes_never_materialised=b * h * l * l * 4,
                                   note="exp / FMA bound on the CUDA cores (2 x b h l l_k exp per step), not HBM bound")
+    # the whole head as its caller uses it (multi_head_attention.py:49-51: a NEW module per forward): wall clock per
+    # call incl. the host side, fresh construction + the reference's op sequence vs ATA.cached + the fused core
+    q_s = torch.randn(b, l, h, dk, device=device, generator=g).transpose(1, 2).requires_grad_(True)
+
+    def head_reference_style():
+        head = ata_mod.ATA(d_k=dk, device=device, h=h, seed=1234)
+        Qr, Kr = q_s.reshape(b, -1, l), q_s.reshape(b, -1, l)
+        Q_l = [head.conv_list_q[i](Qr) for i in range(4)]
+        K_l = [head.conv_list_k[i](Kr) for i in range(4)]
+        Q_p = torch.cat(Q_l, dim=0).reshape(b, h, l * 4, -1).reshape(b, h, l, -1)
+        K_p = torch.cat(K_l, dim=0).reshape(b, h, l * 4, -1).reshape(b, h, l, -1)
+        Q, _ = torch.topk(Q_p, dim=-1, k=1)
+        K, _ = torch.topk(K_p, dim=-1, k=1)
+        attn = torch.softmax(torch.einsum('bhqd,bhkd->bhqk', Q, K) / np.sqrt(dk), -1)
+        c = torch.einsum('bhqk,bhkd->bhqd', attn, q_s)
+        torch.autograd.grad(c, (q_s,), gc)
+
+    def head_ours():
+        c, _ = ata_mod.ATA.cached(d_k=dk, device=device, h=h, seed=1234)(Q=q_s, K=q_s, V=q_s)
+        torch.autograd.grad(c, (q_s,), gc)
+
+    def wall(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize(device)
+        return (time.perf_counter() - t0) / n
+
+    out["ata_head_fwd_bwd_wall"] = {"ms": wall(head_ours) * 1e3, "reference_style_ms": wall(head_reference_style) * 1e3,
+                                    "shape": "b=256 h=8 l=192 d_k=4 (d_model 32), self-attention",
+                                    "note": "convolutions / batch norm are cuDNN calls in both columns"}
     return out
 
 

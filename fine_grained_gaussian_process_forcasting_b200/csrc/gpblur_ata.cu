@@ -33,6 +33,12 @@ struct AtaArgs {
   const float* v;       // element (b, h, j, e) at v + b v_sb + h v_sh + j v_sl + e
   long long v_sb, v_sh, v_sl;
   int B, H, Lq, Lk, G, DV;
+  // nf > 0: qp / kp (and their gradients) are [B, nf * C, L] buffers - the output of ONE convolution that holds the
+  // reference's nf filter stacks as channel groups - instead of the reference's torch.cat(dim=0) of nf [B, C, L]
+  // tensors.  The kernel then reads group f0 of the cat order at its place in that buffer: block (filter i, batch j) of
+  // blk = C * L floats sits at (j * nf + i) * blk.  Requires blk % G == 0 (a group never straddles two blocks).
+  int nf;
+  long long blk_q, blk_k;
   float scale;          // 1 / sqrt(d_k)
   float* ctx;           // [B, Lq, H, DV]
   float* q_pool;        // [B, H, Lq]
@@ -46,6 +52,14 @@ struct AtaArgs {
   float* g_kp;          // [B, H, Lk, G]
   float* g_v;           // [B, Lk, H, DV]
 };
+
+// float offset of the group that starts at cat-order offset f0 (see AtaArgs::nf)
+__device__ __forceinline__ size_t group_offset(size_t f0, int nf, long long blk, int B) {
+  if (nf == 0) return f0;
+  const size_t block = f0 / (size_t)blk, rem = f0 - block * (size_t)blk;
+  const size_t i = block / (size_t)B, j = block - i * (size_t)B;
+  return (j * (size_t)nf + i) * (size_t)blk + rem;
+}
 
 // top-1 of a group of G floats (first maximum wins, as a sequential scan does)
 __device__ __forceinline__ float pool_group(const float* __restrict__ row, int G, int& arg) {
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(kAtaThreads) ata_fwd_kernel(AtaArgs a) {
   const int bh = blockIdx.x, b = bh / a.H, h = bh - b * a.H;
   for (int j = threadIdx.x; j < Lk; j += kAtaThreads) {
     int arg;
-    const float kv = pool_group(a.kp + ((size_t)bh * Lk + j) * G, G, arg);
+    const float kv = pool_group(a.kp + group_offset(((size_t)bh * Lk + j) * G, a.nf, a.blk_k, a.B), G, arg);
     ks[j] = kv;
     a.k_pool[(size_t)bh * Lk + j] = kv;
     a.k_arg[(size_t)bh * Lk + j] = arg;
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(kAtaThreads) ata_fwd_kernel(AtaArgs a) {
   __syncthreads();
   for (int i = threadIdx.x; i < Lq; i += kAtaThreads) {
     int arg;
-    const float q = pool_group(a.qp + ((size_t)bh * Lq + i) * G, G, arg);
+    const float q = pool_group(a.qp + group_offset(((size_t)bh * Lq + i) * G, a.nf, a.blk_q, a.B), G, arg);
     a.q_pool[(size_t)bh * Lq + i] = q;
     a.q_arg[(size_t)bh * Lq + i] = arg;
     const float aq = q * a.scale;
@@ -174,7 +188,8 @@ __global__ void __launch_bounds__(kAtaThreads) ata_bwd_kernel(AtaArgs a) {
       for (int e = 0; e < DVP; ++e) gp = fmaf(g[e], vs[j * DVP + e], gp);
       acc = fmaf(p * (gp - d), kj, acc);
     }
-    scatter_group(a.g_qp + ((size_t)bh * Lq + i) * G, G, a.q_arg[(size_t)bh * Lq + i], acc * a.scale);
+    scatter_group(a.g_qp + group_offset(((size_t)bh * Lq + i) * G, a.nf, a.blk_q, a.B), G, a.q_arg[(size_t)bh * Lq + i],
+                  acc * a.scale);
   }
   // phase 2: key / value side
   for (int j = threadIdx.x; j < Lk; j += kAtaThreads) {
@@ -195,7 +210,7 @@ __global__ void __launch_bounds__(kAtaThreads) ata_bwd_kernel(AtaArgs a) {
       }
       gk = fmaf(p * (gp - Ds[i]), aq, gk);
     }
-    scatter_group(a.g_kp + ((size_t)bh * Lk + j) * G, G, a.k_arg[(size_t)bh * Lk + j], gk);
+    scatter_group(a.g_kp + group_offset(((size_t)bh * Lk + j) * G, a.nf, a.blk_k, a.B), G, a.k_arg[(size_t)bh * Lk + j], gk);
     float* o = a.g_v + (((size_t)b * Lk + j) * a.H + h) * DV;
 #pragma unroll
     for (int e = 0; e < DVP; ++e)
@@ -244,33 +259,61 @@ bool bad_dims(int B, int H, int Lq, int Lk, int G, int DV) {
 
 using namespace gpblur;
 
-extern "C" int gpblur_ata_forward(const float* qp, const float* kp, const float* v, long long v_sb, long long v_sh,
-                                  long long v_sl, int B, int H, int Lq, int Lk, int G, int DV, float scale, float* ctx,
-                                  float* q_pool, float* k_pool, int* q_arg, int* k_arg, float* lse, void* stream) {
-  if (bad_dims(B, H, Lq, Lk, G, DV)) return GPBLUR_EINVAL;
+static bool bad_layout(int nf, int B, int H, int Lq, int Lk, int G) {
+  if (nf == 0) return false;
+  if (nf < 0 || G % nf != 0) return true;
+  const long long C = (long long)H * (G / nf);                  // channels of one filter stack = h * d_k
+  return (C * Lq) % G != 0 || (C * Lk) % G != 0;
+}
+
+extern "C" int gpblur_ata_forward_fused_stacks(const float* qp, const float* kp, const float* v, long long v_sb,
+                                               long long v_sh, long long v_sl, int B, int H, int Lq, int Lk, int G,
+                                               int DV, int nf, float scale, float* ctx, float* q_pool, float* k_pool,
+                                               int* q_arg, int* k_arg, float* lse, void* stream) {
+  if (bad_dims(B, H, Lq, Lk, G, DV) || bad_layout(nf, B, H, Lq, Lk, G)) return GPBLUR_EINVAL;
   if (B == 0) return GPBLUR_OK;
   if (!qp || !kp || !v || !ctx || !q_pool || !k_pool || !q_arg || !k_arg || !lse) return GPBLUR_EINVAL;
   if ((G & 3) == 0 && (((uintptr_t)qp | (uintptr_t)kp) & 15)) return GPBLUR_EINVAL;
   AtaArgs a{};
   a.qp = qp; a.kp = kp; a.v = v; a.v_sb = v_sb; a.v_sh = v_sh; a.v_sl = v_sl;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.G = G; a.DV = DV; a.scale = scale;
+  a.nf = nf;
+  if (nf) { a.blk_q = (long long)H * (G / nf) * Lq; a.blk_k = (long long)H * (G / nf) * Lk; }
   a.ctx = ctx; a.q_pool = q_pool; a.k_pool = k_pool; a.q_arg = q_arg; a.k_arg = k_arg; a.lse = lse;
   return dispatch(false, a, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int gpblur_ata_backward(const float* g_ctx, const float* ctx, const float* v, long long v_sb, long long v_sh,
-                                   long long v_sl, const float* q_pool, const float* k_pool, const int* q_arg,
-                                   const int* k_arg, const float* lse, int B, int H, int Lq, int Lk, int G, int DV,
-                                   float scale, float* g_qp, float* g_kp, float* g_v, void* stream) {
-  if (bad_dims(B, H, Lq, Lk, G, DV)) return GPBLUR_EINVAL;
+extern "C" int gpblur_ata_backward_fused_stacks(const float* g_ctx, const float* ctx, const float* v, long long v_sb,
+                                                long long v_sh, long long v_sl, const float* q_pool,
+                                                const float* k_pool, const int* q_arg, const int* k_arg,
+                                                const float* lse, int B, int H, int Lq, int Lk, int G, int DV, int nf,
+                                                float scale, float* g_qp, float* g_kp, float* g_v, void* stream) {
+  if (bad_dims(B, H, Lq, Lk, G, DV) || bad_layout(nf, B, H, Lq, Lk, G)) return GPBLUR_EINVAL;
   if (B == 0) return GPBLUR_OK;
   if (!g_ctx || !ctx || !v || !q_pool || !k_pool || !q_arg || !k_arg || !lse || !g_qp || !g_kp || !g_v) return GPBLUR_EINVAL;
   if ((G & 3) == 0 && (((uintptr_t)g_qp | (uintptr_t)g_kp) & 15)) return GPBLUR_EINVAL;
   AtaArgs a{};
   a.v = v; a.v_sb = v_sb; a.v_sh = v_sh; a.v_sl = v_sl;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.G = G; a.DV = DV; a.scale = scale;
+  a.nf = nf;
+  if (nf) { a.blk_q = (long long)H * (G / nf) * Lq; a.blk_k = (long long)H * (G / nf) * Lk; }
   a.ctx = const_cast<float*>(ctx); a.q_pool = const_cast<float*>(q_pool); a.k_pool = const_cast<float*>(k_pool);
   a.q_arg = const_cast<int*>(q_arg); a.k_arg = const_cast<int*>(k_arg); a.lse = const_cast<float*>(lse);
   a.g_ctx = g_ctx; a.g_qp = g_qp; a.g_kp = g_kp; a.g_v = g_v;
   return dispatch(true, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gpblur_ata_forward(const float* qp, const float* kp, const float* v, long long v_sb, long long v_sh,
+                                  long long v_sl, int B, int H, int Lq, int Lk, int G, int DV, float scale, float* ctx,
+                                  float* q_pool, float* k_pool, int* q_arg, int* k_arg, float* lse, void* stream) {
+  return gpblur_ata_forward_fused_stacks(qp, kp, v, v_sb, v_sh, v_sl, B, H, Lq, Lk, G, DV, 0, scale, ctx, q_pool, k_pool,
+                                         q_arg, k_arg, lse, stream);
+}
+
+extern "C" int gpblur_ata_backward(const float* g_ctx, const float* ctx, const float* v, long long v_sb, long long v_sh,
+                                   long long v_sl, const float* q_pool, const float* k_pool, const int* q_arg,
+                                   const int* k_arg, const float* lse, int B, int H, int Lq, int Lk, int G, int DV,
+                                   float scale, float* g_qp, float* g_kp, float* g_v, void* stream) {
+  return gpblur_ata_backward_fused_stacks(g_ctx, ctx, v, v_sb, v_sh, v_sl, q_pool, k_pool, q_arg, k_arg, lse, B, H, Lq, Lk,
+                                          G, DV, 0, scale, g_qp, g_kp, g_v, stream);
 }

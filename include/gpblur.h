@@ -280,6 +280,20 @@ int gpblur_ata_backward(const float* g_ctx, const float* ctx, const float* v, lo
                         long long v_sl, const float* q_pool, const float* k_pool, const int* q_arg, const int* k_arg,
                         const float* lse, int B, int H, int Lq, int Lk, int G, int DV, float scale, float* g_qp,
                         float* g_kp, float* g_v, void* stream);
+/* The same core for the head's conv stacks evaluated as ONE convolution (nf filter stacks as channel groups of a
+ * [B, nf * C, L] output, C = H * d_k) instead of nf convolutions + torch.cat(dim = 0) (ATA.py:50-54): qp / kp / g_qp /
+ * g_kp are [B, nf * C, Lq | Lk] buffers and every group is read / written at the place the cat would have put it, so
+ * the results equal the plain entry points on the concatenated tensor.  Needs (C * Lq) % G == 0 and (C * Lk) % G == 0. */
+int gpblur_ata_forward_fused_stacks(const float* qp, const float* kp, const float* v, long long v_sb, long long v_sh,
+                                    long long v_sl, int B, int H, int Lq, int Lk, int G, int DV, int nf, float scale,
+                                    float* ctx, float* q_pool, float* k_pool, int* q_arg, int* k_arg, float* lse,
+                                    void* stream);
+int gpblur_ata_backward_fused_stacks(const float* g_ctx, const float* ctx, const float* v, long long v_sb,
+                                     long long v_sh, long long v_sl, const float* q_pool, const float* k_pool,
+                                     const int* q_arg, const int* k_arg, const float* lse, int B, int H, int Lq, int Lk,
+                                     int G, int DV, int nf, float scale, float* g_qp, float* g_kp, float* g_v,
+                                     void* stream);
+
 
 /* ---- data-parallel exchange: one-shot all-reduce of the flat gradient bucket over NVLink peer memory -------------
  * (one node, one process per GPU; replaces the all-reduce a torch DistributedDataParallel wrapper would issue for the

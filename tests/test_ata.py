@@ -56,6 +56,27 @@ def test_module_mirror_on_host():
         head(x, x, x)                       # no CPU fallback
 
 
+def test_cached_head_replays_constructor_side_effects():
+    """ATA.cached: same weights as a fresh construction and the same generator states afterwards (torch, numpy,
+    random), on the first and on later calls; running statistics frozen, weights without gradient."""
+    import random
+    fresh = ATAmod.ATA(d_k=4, device="cpu", h=2, seed=99)
+    want = (torch.get_rng_state().clone(), np.random.get_state()[1].copy(), random.getstate())
+    ATAmod.ATA._cache.clear()
+    for _ in range(3):
+        torch.manual_seed(5); np.random.seed(5); random.seed(5)       # whatever the caller's generators held before
+        torch.randn(7)
+        head = ATAmod.ATA.cached(d_k=4, device="cpu", h=2, seed=99)
+        assert torch.equal(torch.get_rng_state(), want[0]) and np.array_equal(np.random.get_state()[1], want[1])
+        assert random.getstate() == want[2]
+        for (n1, a), (n2, b) in zip(fresh.state_dict().items(), head.state_dict().items()):
+            assert n1 == n2 and torch.equal(a, b)
+    assert head is ATAmod.ATA.cached(d_k=4, device="cpu", h=2, seed=99) and head.training
+    assert all(not q.requires_grad for q in head.parameters())
+    assert all(m.momentum == 0.0 for m in head.modules() if isinstance(m, torch.nn.BatchNorm1d))
+    assert ATAmod.ATA.cached(d_k=4, device="cpu", h=2, seed=100) is not head
+
+
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.fixture
 def cuda():
@@ -114,3 +135,50 @@ def test_fused_core_vs_fp64(cuda, b, h, l, lk, dk, dv):
     ctx2, _, _ = ATAmod.ata_core(qp, kp, v, dk)
     (ctx2 * gc).sum().backward()
     assert torch.equal(ctx2, got[0]) and torch.equal(qp.grad, got[1]) and torch.equal(kp.grad, got[2]) and torch.equal(v.grad, got[3])
+
+
+@pytest.mark.gpu
+def test_cached_head_equals_fresh_head_on_device(cuda, exact_convs):
+    """The cached instance, called repeatedly, gives what a freshly constructed head gives (multi_head_attention.py:49-51
+    builds one per forward): same context, same input gradients, same CUDA generator state afterwards."""
+    b, h, l, dk, seed = 4, 8, 24, 4, 321
+    g = torch.Generator().manual_seed(1)
+    Q, K, V = (torch.randn(b, l, h, dk, generator=g).transpose(1, 2).to(cuda).requires_grad_(True) for _ in range(3))
+    gc = torch.randn(b, h, l, dk, generator=g).to(cuda)
+    ATAmod.ATA._cache.clear()
+    for it in range(3):
+        fresh = ATAmod.ATA(d_k=dk, device=cuda, h=h, seed=seed)
+        state_fresh = torch.cuda.get_rng_state(cuda).clone()
+        c1, _ = fresh(Q=Q, K=K, V=V)
+        g1 = torch.autograd.grad(c1, (Q, K, V), gc)
+        torch.cuda.manual_seed(1000 + it)
+        head = ATAmod.ATA.cached(d_k=dk, device=cuda, h=h, seed=seed)
+        assert torch.equal(torch.cuda.get_rng_state(cuda), state_fresh)
+        c2, _ = head(Q=Q, K=K, V=V)
+        g2 = torch.autograd.grad(c2, (Q, K, V), gc)
+        # (the cached head evaluates the four stacks of a side as ONE 9-tap convolution: same arithmetic up to the
+        # summation order inside cuDNN)
+        assert rel(c2, c1) < TOL and all(rel(b_, a) < 10 * TOL for a, b_ in zip(g1, g2))
+        assert getattr(head, "_fused", False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,h,l,lk,dk", [(3, 8, 24, 40, 4), (2, 4, 7, 12, 8), (256, 8, 192, 192, 4)])
+def test_fused_stacks_layout_equals_cat_layout(cuda, b, h, l, lk, dk):
+    """The core on ONE [b, 4 C, l] convolution output (filter stacks as channel groups) is bit-identical to the core on
+    the reference's torch.cat(dim=0) + reshape of the four stacks, forward and backward."""
+    g = torch.Generator(device=cuda).manual_seed(l)
+    C, nf = h * dk, 4
+    yq = torch.relu(torch.randn(b, nf * C, l, device=cuda, generator=g)).requires_grad_(True)
+    yk = torch.relu(torch.randn(b, nf * C, lk, device=cuda, generator=g)).requires_grad_(True)
+    v = torch.randn(b, lk, h, dk, device=cuda, generator=g).transpose(1, 2).requires_grad_(True)
+    gc = torch.randn(b, h, l, dk, device=cuda, generator=g)
+    c1 = ATAmod.ata_core_fused_stacks(yq, yk, v, dk, nf)[0]
+    g1 = torch.autograd.grad(c1, (yq, yk, v), gc)
+
+    def cat_view(y, L):      # what ATA.py:50-59 builds: stacks [b, C, L] -> cat over the batch axis -> [b, h, L, 4 d_k]
+        return torch.cat([y[:, i * C:(i + 1) * C, :] for i in range(nf)], dim=0).reshape(b, h, L, -1)
+
+    c2 = ATAmod.ata_core(cat_view(yq, l), cat_view(yk, lk), v, dk)[0]
+    g2 = torch.autograd.grad(c2, (yq, yk, v), gc)
+    assert torch.equal(c1, c2) and all(torch.equal(a, b_) for a, b_ in zip(g1, g2))
