@@ -49,7 +49,7 @@ for _m in (64, 128, 256, 512, 1024):
     WORKLOADS[f"c5_m{_m}"] = dict(B=8192, calls=[24], D=64, M=_m,
                                   desc=f"configs[4]: inducing sweep point B=8192 L=24 D=64 M={_m}")
 WORKLOADS["c3"]["strong"] = True     # configs[2]: B = 1024 GLOBAL, batch-sharded (128 windows per GPU on 8)
-EXTRA_WORKLOADS = ["c1", "c3", "c5_m256", "c5_m1024"]
+EXTRA_WORKLOADS = ["c1", "c3", "c4", "c5_m64", "c5_m256", "c5_m1024"]
 WORKLOADS["c4"] = dict(B=2048, calls=[24], D=64, M=256, H=10,
                        desc="configs[3]: two-layer DeepGP blur B=2048 L=24 D=64 M=256, hidden width H=10 "
                             "(H independent GPs D->H, reparameterised sample, one GP H->1)")

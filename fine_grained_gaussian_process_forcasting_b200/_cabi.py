@@ -60,6 +60,12 @@ SIGNATURES = {
     "gpblur_svgp_param_stage_jitter": (C.c_int, [
         C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
         C.c_void_p]),
+    "gpblur_svgp_param_stage_shared_sms": (C.c_int, [
+        C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+        C.c_void_p]),
+    "gpblur_svgp_param_stage_backward_shared_sms": (C.c_int, [
+        C.POINTER(SvgpParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+        C.c_size_t, C.c_void_p]),
     "gpblur_svgp_point_forward": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

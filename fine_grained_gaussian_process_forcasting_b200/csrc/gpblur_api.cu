@@ -396,6 +396,27 @@ int gpblur_svgp_param_stage_jitter(const gpblur_svgp_params* p, int D, int M, do
   return launch_mm_forward(*p, L, stage, kl, info, (cudaStream_t)stream, extra_jitter);
 }
 
+int gpblur_svgp_param_stage_shared_sms(const gpblur_svgp_params* p, int D, int M, double extra_jitter, int max_ctas,
+                                       float* kl, int* info, void* stage, size_t stage_bytes, void* stream) {
+  int rc = validate(p, 0, D, M);
+  if (rc) return rc;
+  if (!stage || (reinterpret_cast<uintptr_t>(stage) & 255) || !(extra_jitter >= 0.0) || max_ctas < 0) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(0, D, M, 0);
+  if (stage_bytes < L.total) return GPBLUR_EWORKSPACE;
+  return launch_mm_forward(*p, L, stage, kl, info, (cudaStream_t)stream, extra_jitter, max_ctas);
+}
+
+int gpblur_svgp_param_stage_backward_shared_sms(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,
+                                                const float* g_kl, float* grad_bucket, int accumulate, int max_ctas,
+                                                void* stage, size_t stage_bytes, void* stream) {
+  int rc = validate(p, 0, D, M);
+  if (rc) return rc;
+  if (!stage_grad || !grad_bucket || !stage || (reinterpret_cast<uintptr_t>(stage) & 255) || max_ctas < 0) return GPBLUR_EINVAL;
+  const WsLayout L = make_layout(0, D, M, 0);
+  if (stage_bytes < L.total) return GPBLUR_EWORKSPACE;
+  return launch_mm_backward(*p, L, stage, stage_grad, g_kl, grad_bucket, (cudaStream_t)stream, accumulate ? 1 : 0, max_ctas);
+}
+
 int gpblur_svgp_point_forward(const void* param_stage, const float* x, long long N, int D, int M, float* mean,
                               float* var, float* sample, uint64_t seed, uint64_t offset, uint32_t stream_id,
                               const unsigned long long* offset_dev, int training, void* ws, size_t ws_bytes,

@@ -333,10 +333,10 @@ int tile_override(const char* env);   // 0 = heuristic, else forced tile height 
 
 // launchers implemented in the other translation units
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
-                      cudaStream_t st, double extra_jitter = 0.0);
+                      cudaStream_t st, double extra_jitter = 0.0, int max_ctas = 0);
 // stage: the parameter stage of the forward (its fp64 scratch regions are overwritten); sgrad: summed stage gradient
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
-                       const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate = 0);
+                       const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate = 0, int max_ctas = 0);
 // reduces the split partials left in `ws` by the point backward + N-reduction GEMMs into sgrad (fixed order, fp64)
 int launch_stage_grad_reduce(const WsLayout& L, const void* ws, double* sgrad, cudaStream_t st);
 int launch_point_forward(const WsLayout& L, void* ws, const float* x, float* mean, float* var,

@@ -1429,8 +1429,11 @@ int coop_grid(const void* func, int want, size_t smem) {
 
 }  // namespace
 
+// max_ctas > 0: an upper bound on the grid (>= 8): the H independent stages of a multi-output layer are launched on H
+// streams with 148 / H CTAs each so that they run CONCURRENTLY (a cooperative grid of ~130 CTAs owns the GPU alone; the
+// stage is a latency-bound chain, so ten stages side by side finish in little more than the time of one).
 int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, float* kl, int* info,
-                      cudaStream_t st, double extra_jitter) {
+                      cudaStream_t st, double extra_jitter, int max_ctas) {
   const size_t smem = sizeof(Tile) * 11 + kGemmScratchDoubles * sizeof(double);
   // per-DEVICE attribute: set on every launch (cheap) instead of a process-wide flag
   cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1443,6 +1446,7 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
     n_img = spb * NP * (NP + 1) / 2 + NPT * nsl - spt * NPT * (NPT - 1) / 2;
   }
   int want = nb * nb + nb + 3 * n_img;
+  if (max_ctas > 0 && want > max_ctas) want = max_ctas;
   if (want < 8) want = 8;
   if (want > 148) want = 148;
   const int grid = coop_grid((const void*)mm_forward_kernel, want, smem);
@@ -1470,7 +1474,7 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 }
 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
-                       const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate) {
+                       const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate, int max_ctas) {
   const int nb = L.MP / TB;
   // 16-row tiles while that still gives every SM at most two of them (one CTA for a single 32 x 32 block, with CTA
   // barriers instead of grid barriers, was tried: 29 us against 21 us on 8 CTAs - the elementwise phases want the threads)
@@ -1481,6 +1485,7 @@ int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* sta
   int want = (half ? 2 : 1) * nb * nb;
   const int dwant = (L.MP * L.DP + kThreads - 1) / kThreads;
   if (want < dwant) want = dwant;
+  if (max_ctas > 0 && want > max_ctas) want = max_ctas < 8 ? 8 : max_ctas;
   if (want > 148) want = 148;
   const int grid = coop_grid(func, want, smem);
   MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate, nullptr};

@@ -258,10 +258,11 @@ def stage_grad_doubles(D: int, M: int) -> int:
     return int(_cabi.lib().gpblur_svgp_stage_grad_doubles(D, M))
 
 
-def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None, extra_jitter: float = 0.0):
+def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None, extra_jitter: float = 0.0, max_ctas: int = 0):
     """Once-per-parameter-update M x M stage: -> (stage uint8 [param_stage_bytes], kl [1], info [1] int32).
     `out` = preallocated (stage, kl, info) (the call then only launches on the current stream).
-    `extra_jitter` is added to the diagonal of Kzz on top of the variational jitter (psd_safe_cholesky retries)."""
+    `extra_jitter` is added to the diagonal of Kzz on top of the variational jitter (psd_safe_cholesky retries).
+    `max_ctas` > 0 bounds the cooperative grid (stages of a multi-output layer running side by side, see _Fork)."""
     _need_cuda(Z, raw_ell, raw_os, m, s, w, b)
     M, D = Z.shape
     dev = Z.device
@@ -277,7 +278,10 @@ def param_stage_raw(Z, raw_ell, raw_os, m, s, w, b, out=None, extra_jitter: floa
         stage, kl, info = out
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(dev):
-        if extra_jitter:
+        if max_ctas:
+            rc = _cabi.lib().gpblur_svgp_param_stage_shared_sms(C.byref(p), D, M, float(extra_jitter), int(max_ctas),
+                                                                _ptr(kl), _ptr(info), _ptr(stage), stage.numel(), _stream())
+        elif extra_jitter:
             rc = _cabi.lib().gpblur_svgp_param_stage_jitter(C.byref(p), D, M, float(extra_jitter), _ptr(kl), _ptr(info),
                                                             _ptr(stage), stage.numel(), _stream())
         else:
@@ -368,7 +372,7 @@ def point_backward_segments_raw(x: Tensor, M: int, seg_sizes, g_means, g_vars, g
 
 
 def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl: Optional[Tensor], stage: Tensor,
-                             bucket: Optional[Tensor] = None, accumulate: bool = False):
+                             bucket: Optional[Tensor] = None, accumulate: bool = False, max_ctas: int = 0):
     """Summed stage gradient (+ g_kl) -> flat parameter-gradient bucket [M*D + 2M + 2D + 2] (`accumulate`: added to
     `bucket` instead of overwriting it)."""
     _need_cuda(Z, sgrad, stage, g_kl)
@@ -377,15 +381,33 @@ def param_stage_backward_raw(Z, raw_ell, raw_os, m, s, w, b, sgrad: Tensor, g_kl
         bucket = torch.empty(grad_bucket_floats(D, M), device=Z.device, dtype=torch.float32)
     p = _params_struct(Z, raw_ell, raw_os, m, s, w, b)
     with torch.cuda.device(Z.device):
-        rc = _cabi.lib().gpblur_svgp_param_stage_backward_acc(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
-                                                              int(accumulate), _ptr(stage), stage.numel(), _stream())
+        if max_ctas:
+            rc = _cabi.lib().gpblur_svgp_param_stage_backward_shared_sms(
+                C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket), int(accumulate), int(max_ctas), _ptr(stage),
+                stage.numel(), _stream())
+        else:
+            rc = _cabi.lib().gpblur_svgp_param_stage_backward_acc(C.byref(p), D, M, _ptr(sgrad), _ptr(g_kl), _ptr(bucket),
+                                                                  int(accumulate), _ptr(stage), stage.numel(), _stream())
     _cabi.check(rc, "gpblur_svgp_param_stage_backward")
     return bucket
 
 
 # ---- side streams: the M x M stages of the H independent GPs of a multi-output layer run concurrently ----
 _SIDE_STREAMS = {}
-N_SIDE_STREAMS = 4
+N_SIDE_STREAMS = 16
+_SM_COUNT = {}
+
+
+def _stage_cta_cap(dev, H: int) -> int:
+    """Grid bound of each of the H concurrent M x M stages of a multi-output layer: the SMs are shared out among the
+    stages that can be in flight at once (one per side stream), so that their cooperative grids are co-resident."""
+    if H <= 1:
+        return 0
+    key = (dev.type, dev.index)
+    sms = _SM_COUNT.get(key)
+    if sms is None:
+        sms = _SM_COUNT[key] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return max(8, sms // min(H, N_SIDE_STREAMS))
 
 
 def _side_streams(dev):
@@ -473,12 +495,13 @@ class _ParamStageFunction(torch.autograd.Function):
         kl = torch.empty(H, device=dev, dtype=torch.float32)
         info = torch.empty(H, device=dev, dtype=torch.int32)
         fork = _Fork(dev, H)
+        cap = _stage_cta_cap(dev, H)
         try:
             for h in range(H):
                 fork.enter(h)
                 param_stage_raw(Zc[h], ellc[h], osc[h], mc[h], sc[h], None if wc is None else wc[h % wc.shape[0]],
                                 bc[h % bc.shape[0]], out=(stage[h], kl[h:h + 1], info[h:h + 1]),
-                                extra_jitter=float(holder.get("extra_jitter", 0.0)))
+                                extra_jitter=float(holder.get("extra_jitter", 0.0)), max_ctas=cap)
         finally:
             fork.join()
         holder["stage"] = stage
@@ -522,12 +545,13 @@ class _ParamStageFunction(torch.autograd.Function):
             return (None,) * 8
         bucket = torch.empty(H, nb, device=dev, dtype=torch.float32)
         fork = _Fork(dev, H)
+        cap = _stage_cta_cap(dev, H)
         try:
             for h in range(H):
                 fork.enter(h)
                 param_stage_backward_raw(Zc[h], ellc[h], osc[h], mc[h], sc[h],
                                          None if wc is None else wc[h % wc.shape[0]], bc[h % bc.shape[0]], sgrad[h],
-                                         None if gk is None else gk[h:h + 1], stage[h], bucket=bucket[h])
+                                         None if gk is None else gk[h:h + 1], stage[h], bucket=bucket[h], max_ctas=cap)
         finally:
             fork.join()
         holder["consumed"] = True        # the graph behind this token is gone: the next forward rebuilds the stage

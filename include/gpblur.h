@@ -166,6 +166,15 @@ int gpblur_svgp_param_stage_backward_acc(const gpblur_svgp_params* p, int D, int
 int gpblur_svgp_param_stage_jitter(const gpblur_svgp_params* p, int D, int M, double extra_jitter, float* kl,
                                    int* info, void* stage, size_t stage_bytes, void* stream);
 
+/* The two M x M stage entry points with an upper bound `max_ctas` (0 = none, else >= 8) on the size of their cooperative
+ * grid.  A multi-output layer (/root/reference/denoising_model/DeepGP.py:21-26: H independent GPs) launches its H
+ * stages on H streams with (SM count / H) CTAs each, so that they run side by side instead of one after the other. */
+int gpblur_svgp_param_stage_shared_sms(const gpblur_svgp_params* p, int D, int M, double extra_jitter, int max_ctas,
+                                       float* kl, int* info, void* stage, size_t stage_bytes, void* stream);
+int gpblur_svgp_param_stage_backward_shared_sms(const gpblur_svgp_params* p, int D, int M, const double* stage_grad,
+                                                const float* g_kl, float* grad_bucket, int accumulate, int max_ctas,
+                                                void* stage, size_t stage_bytes, void* stream);
+
 /* `stage` is the buffer filled by gpblur_svgp_param_stage; its fp64 scratch regions are overwritten. */
 int gpblur_svgp_param_stage_backward(const gpblur_svgp_params* p, int D, int M,
                                      const double* stage_grad, const float* g_kl,
