@@ -197,7 +197,8 @@ class ScaleKernel(Kernel):
         return self.raw_outputscale_constraint.transform(self.raw_outputscale)
 
     def forward(self, x1, x2=None):
-        """Dense ScaleKernel(RBF) covariance by the CUDA kernel (no autograd)."""
+        """Dense ScaleKernel(RBF) covariance by the CUDA kernel, differentiable w.r.t. the inputs and both raw
+        hyper-parameters (hand-written backward: gpblur_rbf_covariance_backward)."""
         x2 = x1 if x2 is None else x2
         bk = self.base_kernel
         if not isinstance(bk, RBFKernel) or len(self.batch_shape):
@@ -205,8 +206,8 @@ class ScaleKernel(Kernel):
         lead = x1.shape[:-2]
         x1f = x1.reshape(-1, x1.shape[-2], x1.shape[-1])
         x2f = x2.reshape(-1, x2.shape[-2], x2.shape[-1])
-        ell = bk.raw_lengthscale.detach().reshape(-1)
-        outs = [ops.rbf_covariance(a, b, ell, self.raw_outputscale.detach().reshape(1), bk.ard_num_dims is not None)
+        same = x2 is x1
+        outs = [ops.rbf_covariance(a, a if same else b, bk.raw_lengthscale, self.raw_outputscale, bk.ard_num_dims is not None)
                 for a, b in zip(x1f, x2f)]
         return torch.stack(outs).reshape(*lead, x1.shape[-2], x2.shape[-2])
 
@@ -673,6 +674,29 @@ class DeepApproximateMLL(nn.Module):
         return self.base_mll(approximate_dist_f, target, **params).mean(0)
 
 
+class ExactMarginalLogLikelihood(nn.Module):
+    """gpytorch.mlls.ExactMarginalLogLikelihood for a Gaussian likelihood: ``mll(model(train_x), train_y)`` =
+    log N(y | mean, K + noise I) / n - the objective an ``ExactGPModel`` (GPModel.py:4-13) is trained with.  The
+    covariance comes from the CUDA kernel with its hand-written backward; the n x n factorisation is a library call
+    (cuSOLVER through torch.linalg), as gpytorch's is."""
+
+    def __init__(self, likelihood, model):
+        super().__init__()
+        object.__setattr__(self, "likelihood", likelihood)
+        object.__setattr__(self, "model", model)
+
+    def forward(self, function_dist, target, **params):
+        K = function_dist.covariance_matrix
+        n = K.shape[-1]
+        Kn = K + self.likelihood.noise * torch.eye(n, device=K.device, dtype=K.dtype)
+        Lc = torch.linalg.cholesky(Kn)
+        r = (target - function_dist.mean).unsqueeze(-1)
+        alpha = torch.cholesky_solve(r, Lc)
+        quad = (r * alpha).sum((-2, -1))
+        logdet = 2.0 * torch.diagonal(Lc, dim1=-2, dim2=-1).log().sum(-1)
+        return -0.5 * (quad + logdet + n * math.log(2 * math.pi)) / n
+
+
 # ------------------------------------------------------------------------------------------------
 # exact GP (GPModel.py)
 # ------------------------------------------------------------------------------------------------
@@ -700,7 +724,7 @@ class ExactGP(GP):
         n = xt.shape[-2]
         cov = full.covariance_matrix
         mean = full.mean
-        noise = self.likelihood.noise.detach()
+        noise = self.likelihood.noise
         Ktt = cov[..., :n, :n] + noise * torch.eye(n, device=cov.device, dtype=cov.dtype)
         Kst = cov[..., n:, :n]
         Kss = cov[..., n:, n:]

@@ -216,17 +216,63 @@ def philox_normal(seed: int, offset: int, n: int, stream_id: int = 0, device="cu
     return out
 
 
-def rbf_covariance(x1: Tensor, x2: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor, ard: bool) -> Tensor:
-    _need_cuda(x1, x2, raw_lengthscale, raw_outputscale)
-    x1 = _f32c(x1); x2 = _f32c(x2)
+def _rbf_covariance_raw(x1, x2, raw_lengthscale, raw_outputscale, ard: bool) -> Tensor:
     n1, D = x1.shape
     n2 = x2.shape[0]
     out = torch.empty(n1, n2, device=x1.device, dtype=torch.float32)
     with torch.cuda.device(x1.device):
-        rc = _cabi.lib().gpblur_rbf_covariance(_ptr(x1), _ptr(x2), n1, n2, D, _ptr(_f32c(raw_lengthscale)),
-                                               int(ard), _ptr(_f32c(raw_outputscale)), _ptr(out), _stream())
+        rc = _cabi.lib().gpblur_rbf_covariance(_ptr(x1), _ptr(x2), n1, n2, D, _ptr(raw_lengthscale),
+                                               int(ard), _ptr(raw_outputscale), _ptr(out), _stream())
     _cabi.check(rc, "gpblur_rbf_covariance")
     return out
+
+
+class _RbfCovFunction(torch.autograd.Function):
+    """Dense ScaleKernel(RBF) covariance with its hand-written backward (gpblur_rbf_covariance_backward): gradients of
+    the inputs, the raw lengthscale(s) and the raw outputscale."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, raw_lengthscale, raw_outputscale, ard):
+        same = x2 is x1
+        x1c, ellc, osc = _f32c(x1), _f32c(raw_lengthscale).reshape(-1), _f32c(raw_outputscale).reshape(-1)
+        x2c = x1c if same else _f32c(x2)
+        ctx.save_for_backward(x1c, x2c, ellc, osc)
+        ctx.meta = (bool(ard), same, raw_lengthscale.shape, raw_outputscale.shape)
+        return _rbf_covariance_raw(x1c, x2c, ellc, osc, ard)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x1, x2, ell, os_ = ctx.saved_tensors
+        ard, same, ell_shape, os_shape = ctx.meta
+        n1, D = x1.shape
+        n2 = x2.shape[0]
+        dev = x1.device
+        need = ctx.needs_input_grad
+        want_x1, want_x2 = need[0] or (same and need[1]), need[1] or (same and need[0])
+        g_x1 = torch.empty(n1, D, device=dev, dtype=torch.float32) if want_x1 else None
+        g_x2 = torch.empty(n2, D, device=dev, dtype=torch.float32) if want_x2 else None
+        g_ell = torch.empty(D if ard else 1, device=dev, dtype=torch.float32)
+        g_os = torch.empty(1, device=dev, dtype=torch.float32)
+        nbytes = int(_cabi.lib().gpblur_rbf_covariance_backward_scratch_bytes(n1, n2, D))
+        scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().gpblur_rbf_covariance_backward(_ptr(x1), _ptr(x2), n1, n2, D, _ptr(ell), int(ard), _ptr(os_),
+                                                            _ptr(_f32c(g_out)), _ptr(g_x1), _ptr(g_x2), _ptr(g_ell),
+                                                            _ptr(g_os), _ptr(scratch), nbytes, _stream())
+        _cabi.check(rc, "gpblur_rbf_covariance_backward")
+        if same:                       # K(x, x): the one tensor is both arguments
+            gx = g_x1 + g_x2 if (need[0] or need[1]) else None
+            return gx if need[0] else None, None, g_ell.reshape(ell_shape), g_os.reshape(os_shape), None
+        return (g_x1 if need[0] else None, g_x2 if need[1] else None, g_ell.reshape(ell_shape), g_os.reshape(os_shape),
+                None)
+
+
+def rbf_covariance(x1: Tensor, x2: Tensor, raw_lengthscale: Tensor, raw_outputscale: Tensor, ard: bool) -> Tensor:
+    """os * exp(-1/2 |(x1 - x2) / l|^2) [n1, n2]; differentiable w.r.t. x1, x2 and both raw hyper-parameters."""
+    _need_cuda(x1, x2, raw_lengthscale, raw_outputscale)
+    if raw_lengthscale.numel() != (x1.shape[-1] if ard else 1):
+        raise ValueError("rbf_covariance: raw_lengthscale must hold D values (ard) or one")
+    return _RbfCovFunction.apply(x1, x2, raw_lengthscale, raw_outputscale, bool(ard))
 
 
 def debug_fetch(which: int, N: int, D: int, M: int, ws: Tensor) -> Tensor:

@@ -227,6 +227,16 @@ int gpblur_rbf_covariance(const float* x1, const float* x2, long long n1, long l
                           const float* raw_lengthscale, int ard, const float* raw_outputscale,
                           float* out, void* stream);
 
+/* Backward of gpblur_rbf_covariance (what autograd computes through the kernel evaluation when the exact GP of
+ * /root/reference/denoising_model/GPModel.py:4-13 is trained): g_out [n1, n2] -> g_x1 [n1, D] (nullable), g_x2 [n2, D]
+ * (nullable; when x2 is the same tensor as x1 the caller adds the two), g_raw_lengthscale [D] (ard) or [1],
+ * g_raw_outputscale [1].  `scratch`: gpblur_rbf_covariance_backward_scratch_bytes(n1, n2, D) bytes, 256-byte aligned. */
+size_t gpblur_rbf_covariance_backward_scratch_bytes(long long n1, long long n2, int D);
+int gpblur_rbf_covariance_backward(const float* x1, const float* x2, long long n1, long long n2, int D,
+                                   const float* raw_lengthscale, int ard, const float* raw_outputscale,
+                                   const float* g_out, float* g_x1, float* g_x2, float* g_raw_lengthscale,
+                                   float* g_raw_outputscale, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Debug / test probes into the workspace of the last forward on (ws): copies device-to-device.
  * which: 0 = L (fp64 [Mp,Mp]), 1 = Linv (fp64 [Mp,Mp]), 2 = Kzz+jitter (fp64 [Mp,Mp]),
  *        3 = A (fp32 [N,Mp]), 4 = phase timestamps of the M x M kernels (uint64 ns [32]).

@@ -196,6 +196,35 @@ def test_exact_gp_model(cuda):
     assert rel(post.mean, pm) < 1e-4 and rel(post.covariance_matrix, pc) < 1e-4
 
 
+def test_exact_gp_model_trains(cuda):
+    """GPModel.py:4-13 trained the gpytorch way: loss = -ExactMarginalLogLikelihood(likelihood, model)(model(train_x),
+    train_y); gradients of the raw lengthscale / outputscale / noise / constant against fp64 autograd on the oracle."""
+    from fine_grained_gaussian_process_forcasting_b200.GPModel import ExactGPModel
+    from fine_grained_gaussian_process_forcasting_b200 import gpcompat
+    g = torch.Generator().manual_seed(4)
+    tx, ty = torch.randn(48, 6, generator=g), torch.randn(48, generator=g)
+    lik = gpcompat.GaussianLikelihood().to(cuda)
+    m = ExactGPModel(tx.to(cuda), ty.to(cuda), lik).to(cuda)
+    with torch.no_grad():
+        m.covar_module.base_kernel.raw_lengthscale.fill_(1.2)
+        m.covar_module.raw_outputscale.fill_(0.4)
+        m.mean_module.raw_constant.fill_(0.1)
+        lik.noise_covar.raw_noise.fill_(-1.0)
+    mll = gpcompat.ExactMarginalLogLikelihood(lik, m)
+    loss = -mll(m(tx.to(cuda)), ty.to(cuda))
+    loss.backward()
+    c, rl, ro, rn = (torch.tensor(v, dtype=torch.float64, requires_grad=True) for v in (0.1, 1.2, 0.4, -1.0))
+    mean_o, cov_o = O.exact_gp_prior(tx.double(), c, rl, ro)
+    Kn = cov_o + (O.softplus(rn) + 1e-4) * torch.eye(48, dtype=torch.float64)
+    want = -torch.distributions.MultivariateNormal(mean_o, covariance_matrix=Kn).log_prob(ty.double()) / 48
+    want.backward()
+    assert rel(loss, want) < 1e-5
+    assert rel(m.covar_module.base_kernel.raw_lengthscale.grad.reshape(()), rl.grad) < 1e-4
+    assert rel(m.covar_module.raw_outputscale.grad, ro.grad) < 1e-4
+    assert rel(lik.noise_covar.raw_noise.grad.reshape(()), rn.grad) < 1e-4
+    assert rel(m.mean_module.raw_constant.grad, c.grad) < 1e-4
+
+
 def test_shard_invariance_and_bit_exact_samples(cuda):
     """Size-independent property at a BASELINE size (C3: B=1024, L=24, D=64, M=128): running the batch in
     two shards with global Philox offsets reproduces the single-shot per-window outputs BIT-exactly."""

@@ -240,3 +240,31 @@ def test_rbf_covariance(cuda):
     want = O.rbf_scale_direct(x1.double(), x2.double(), O.softplus(raw_ell.double()), O.softplus(raw_os.double()))
     got = ops.rbf_covariance(x1.to(cuda), x2.to(cuda), raw_ell.to(cuda), raw_os.to(cuda), ard=False)
     assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("n1,n2,D,ard,same", [(37, 21, 5, False, False), (40, 40, 16, True, True), (130, 77, 64, True, False),
+                                               (9, 9, 3, False, True), (17, 33, 128, True, False)])
+def test_rbf_covariance_backward(cuda, n1, n2, D, ard, same):
+    """gpblur_rbf_covariance_backward against fp64 autograd through the oracle's direct-difference kernel: gradients of
+    both inputs (the SAME tensor on both sides for K(x, x)), raw lengthscale(s) and raw outputscale."""
+    from fine_grained_gaussian_process_forcasting_b200 import ops
+    g = torch.Generator().manual_seed(n1 * 7 + D)
+    x1 = torch.randn(n1, D, generator=g)
+    x2 = x1 if same else torch.randn(n2, D, generator=g)
+    raw_ell = 0.3 * torch.randn(D if ard else 1, generator=g) + (1.5 if D > 16 else 0.2)
+    raw_os = torch.tensor([-0.3])
+    G = torch.randn(n1, x2.shape[0], generator=g)
+    xa = x1.to(cuda).requires_grad_(True)
+    xb = xa if same else x2.to(cuda).requires_grad_(True)
+    ell_d, os_d = raw_ell.to(cuda).requires_grad_(True), raw_os.to(cuda).requires_grad_(True)
+    K = ops.rbf_covariance(xa, xb, ell_d, os_d, ard=ard)
+    (K * G.to(cuda)).sum().backward()
+    xa64 = x1.double().requires_grad_(True)
+    xb64 = xa64 if same else x2.double().requires_grad_(True)
+    ell64, os64 = raw_ell.double().requires_grad_(True), raw_os.double().requires_grad_(True)
+    K64 = O.rbf_scale_direct(xa64, xb64, O.softplus(ell64), O.softplus(os64))
+    (K64 * G.double()).sum().backward()
+    assert rel(K, K64) < 1e-5
+    assert rel(xa.grad, xa64.grad) < 2e-5 and rel(ell_d.grad, ell64.grad) < 2e-5 and rel(os_d.grad, os64.grad) < 2e-5
+    if not same:
+        assert rel(xb.grad, xb64.grad) < 2e-5
