@@ -467,7 +467,12 @@ def measure(args, wl, name, ctx, primary=True):
     def eager_step(i, xin, yin):
         for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
             ly.invalidate_param_stage()
-            ly._rng_offset = (i * world + rank) * B * sum(calls) * max(1, ly.output_dims or 1)   # global window index
+            # Philox counters by GLOBAL point index (and, for the H GPs of a multi-output layer, a stride of the global
+            # point count between them): the samples do not depend on the number of ranks
+            H_ = max(1, ly.output_dims or 1)
+            total = world * B * sum(calls)
+            ly._rng_offset = i * total * H_ + rank * B * sum(calls)
+            ly._rng_h_stride = total if H_ > 1 else None
         return step_body(xin, yin)
 
     def sync_all():
@@ -688,6 +693,7 @@ def measure(args, wl, name, ctx, primary=True):
             allreduce_in_step[0] = False
             for ly in layers:
                 ly.invalidate_param_stage()
+                ly._rng_offset, ly._rng_h_stride = 0, None      # step 0 on the concatenated batch: the same counters
             bucket.zero()
             outs, grads = [], []
             for c, L_ in enumerate(calls):
