@@ -1062,6 +1062,196 @@ __global__ void __launch_bounds__(kThreads) mm_forward_kernel(MmFwdArgs a) {
 }
 
 // ==================================================================================================
+// MP = 32 (M <= 32: configs[0]): the whole stage is ONE 32 x 32 block.  The general kernel above spends its time in
+// grid barriers and L2 round trips between phases that have nothing to parallelise here (measured at M = 32: 16 us
+// in-kernel warm, 26 us cold, 30 us with the cooperative launch around it), so this case gets ONE CTA that keeps
+// everything in shared memory: no grid barrier, a plain launch, and the hyper-parameter vectors / Z~ operands are
+// built by warps 1-7 WHILE warp 0 factorises.  Same arithmetic, same output regions of the stage.
+constexpr int kSmallZs = TB * (GPBLUR_MAX_D + 1);     // doubles: scaled inducing points [32][DP + 1]
+constexpr size_t kSmallFwdSmem = (size_t)(kSmallZs + 2 * TB * TLD + 2 * TB + GPBLUR_MAX_D) * sizeof(double) +
+                                 (size_t)(2 * GPBLUR_MAX_D + 2 * TB) * sizeof(float);
+
+__global__ void __launch_bounds__(kThreads) mm_small_forward_kernel(MmFwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Zs = reinterpret_cast<double*>(smem_raw);          // [32][DP + 1]  Z / ell (raw, not centred: differences)
+  double* Ks = Zs + kSmallZs;                                // [32][33]      Kzz + jitter, then L
+  double* Xs = Ks + TB * TLD;                                // [32][33]      L^-1
+  double* lcol = Xs + TB * TLD;                              // [64]
+  double* ie_s = lcol + 2 * TB;                              // [DP]          1 / ell (double)
+  float* cen_s = reinterpret_cast<float*>(ie_s + GPBLUR_MAX_D);   // [DP]  input centre (float, as the point kernels use it)
+  float* inv_s = cen_s + GPBLUR_MAX_D;                       // [DP]  1 / ell (float)
+  float* m_s = inv_s + GPBLUR_MAX_D;                         // [32]  variational mean
+  float* c_s = m_s + TB;                                     // [32]  s^2 - 1
+  __shared__ double os_s;
+
+  const WsLayout& L = a.L;
+  const int D = L.D, DP = L.DP, M = L.M, MP = L.MP;          // MP == 32
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ZP = DP + 1;                                     // pitch of Zs
+  float* hyp = ws_ptr<float>(a.ws, L.hyp);
+  double* hyp64 = ws_ptr<double>(a.ws, L.hyp64);
+  float* Zt = ws_ptr<float>(a.ws, L.Zt);
+  float* ZtT = ws_ptr<float>(a.ws, L.ZtT);
+  double* K64 = ws_ptr<double>(a.ws, L.K64);
+  double* L64 = ws_ptr<double>(a.ws, L.L64);
+  double* Li64 = ws_ptr<double>(a.ws, L.Linv64);
+  const float* Z = a.p.inducing_points;
+  unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps);
+  if (tid == 0) stamps[0] = global_ns();
+
+  // ---- per-dimension hyper-parameters and the input centre (threads = dimensions); outputscale; KL (warp 7) ----
+  if (tid < DP) {
+    const int d = tid;
+    float c = 0.f, e = 1.f, ie = 0.f, w = 0.f;
+    double ied = 0.0;
+    if (d < D) {
+      const double ell = softplus64((double)a.p.raw_lengthscale[d]);
+      double s = 0.0;
+      for (int m = 0; m < M; ++m) s += (double)Z[(size_t)m * D + d];
+      c = (float)(s / (double)M);
+      e = (float)ell;
+      ied = 1.0 / ell;
+      ie = (float)ied;
+      w = a.p.mean_weights ? (float)(ell * (double)a.p.mean_weights[d]) : 0.0f;
+    }
+    ws_ptr<float>(a.ws, L.center)[d] = c;
+    ws_ptr<float>(a.ws, L.ell)[d] = e;
+    ws_ptr<float>(a.ws, L.inv_ell)[d] = ie;
+    ws_ptr<float>(a.ws, L.wl)[d] = w;
+    cen_s[d] = c; inv_s[d] = ie; ie_s[d] = ied;
+  }
+  if (warp == 7) {
+    const double os = softplus64((double)a.p.raw_outputscale[0]);
+    double part = 0.0;
+    if (lane < M) {
+      const double mm = (double)a.p.variational_mean[lane], ss = (double)a.p.variational_stddev[lane];
+      part = ss * ss + mm * mm - 1.0 - log(ss * ss);
+    }
+    part = warp_sum(part);
+    if (lane == 0) {
+      os_s = os;
+      hyp[H_OS] = (float)os;
+      hyp[H_JIT] = kJitter;
+      hyp64[H_JIT] = (double)kJitter + a.extra_jitter;
+      hyp[H_KL] = (float)(0.5 * part);
+      hyp64[H_OS] = os;
+      hyp64[H_KL] = 0.5 * part;
+      if (a.kl) a.kl[0] = (float)(0.5 * part);
+      if (a.info) a.info[0] = 0;
+    }
+  }
+  if (tid < MP) {
+    const float mm = tid < M ? a.p.variational_mean[tid] : 0.f;
+    const float ss = tid < M ? a.p.variational_stddev[tid] : 1.f;
+    const float cc = tid < M ? ss * ss - 1.0f : 0.f;
+    ws_ptr<float>(a.ws, L.mvec)[tid] = mm;
+    ws_ptr<float>(a.ws, L.svec)[tid] = ss;
+    ws_ptr<float>(a.ws, L.cvec)[tid] = cc;
+    m_s[tid] = mm; c_s[tid] = cc;
+  }
+  __syncthreads();
+  // ---- Z / ell in double (rows m >= M and columns d >= D are zero) ----
+  for (int idx = tid; idx < MP * DP; idx += kThreads) {
+    const int m = idx / DP, d = idx - m * DP;
+    Zs[m * ZP + d] = (m < M && d < D) ? (double)Z[(size_t)m * D + d] * ie_s[d] : 0.0;
+  }
+  __syncthreads();
+  // ---- Kzz + jitter (direct differences, fp64), identity padding ----
+  {
+    const double os = os_s;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = warp + 8 * i, gj = lane;
+      double acc = 0.0;
+      for (int d = 0; d < DP; ++d) {
+        const double df = Zs[gi * ZP + d] - Zs[gj * ZP + d];
+        acc = fma(df, df, acc);
+      }
+      double kv;
+      if (gi < M && gj < M) kv = os * exp(-0.5 * acc) + (gi == gj ? (double)kJitter + a.extra_jitter : 0.0);
+      else kv = (gi == gj) ? 1.0 : 0.0;
+      K64[(size_t)gi * MP + gj] = kv;
+      Ks[gi * TLD + gj] = kv;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // ---- Cholesky + inverse of the one block (registers, one row per lane) ----
+    double arow[TB], xcol[TB];
+#pragma unroll
+    for (int c = 0; c < TB; ++c) arow[c] = Ks[lane * TLD + c];
+    chol32_inv_warp(arow, xcol, lane, lcol);
+#pragma unroll
+    for (int c = 0; c < TB; ++c) {
+      L64[(size_t)lane * MP + c] = arow[c];
+      Li64[(size_t)c * MP + lane] = xcol[c];            // xcol[r] = Linv[r][lane]
+      Xs[c * TLD + lane] = xcol[c];
+      Ks[lane * TLD + c] = arow[c];                     // L (row `lane` is this lane's own)
+    }
+    if (a.info) {
+      const double dg = Ks[lane * TLD + lane];          // (a dynamic index into arow would push it out of registers)
+      const unsigned badmask = __ballot_sync(0xffffffffu, !(dg > 0.0) || !(dg < 1e300));
+      if (badmask && lane == 0) a.info[0] = __ffs(badmask);
+    }
+  } else {
+    // ---- meanwhile: Z~ (centred, scaled; fp32 exactly as the point kernels evaluate it), |z~|^2, exponent offsets ----
+    const int t7 = tid - 32;
+    auto zt_of = [&](int m, int d) -> float {
+      return (m < M && d < D) ? (Z[(size_t)m * D + d] - cen_s[d]) * inv_s[d] : 0.f;
+    };
+    for (int idx = t7; idx < MP * DP; idx += kThreads - 32) {
+      const int m = idx / DP, d = idx - m * DP;
+      const float v = zt_of(m, d);
+      Zt[idx] = v;
+      ZtT[(size_t)d * MP + m] = v;
+    }
+    float* zn = ws_ptr<float>(a.ws, L.zn);
+    float* znc = ws_ptr<float>(a.ws, L.znc);
+    const float l2os = (float)(log(os_s) * 1.4426950408889634);
+    for (int j = warp - 1; j < MP; j += 7) {
+      float z2 = 0.f;
+      for (int d = lane; d < DP; d += 32) { const float v = zt_of(j, d); z2 = fmaf(v, v, z2); }
+      z2 = warp_sum(z2);
+      if (lane == 0) {
+        zn[j] = z2;
+        znc[j] = j < M ? fmaf(-0.72134752044448170f, z2, l2os) : -1e30f;
+      }
+    }
+    if (warp == 1) {
+      double sdot = 0.0;
+      if (a.p.mean_weights)
+        for (int d = lane; d < D; d += 32) sdot += (double)cen_s[d] * (double)a.p.mean_weights[d];
+      sdot = warp_sum(sdot);
+      if (lane == 0) hyp[H_CWB] = (float)(sdot + (double)a.p.mean_bias[0]);
+    }
+  }
+  __syncthreads();
+  // ---- fp32 operands of the point kernels and beta = Linv^T m ----
+  {
+    float* LinvT32 = ws_ptr<float>(a.ws, L.LinvT32);
+    float* LC32 = ws_ptr<float>(a.ws, L.LC32);
+    float* Linv32 = ws_ptr<float>(a.ws, L.Linv32);
+    float* LCT32 = ws_ptr<float>(a.ws, L.LCT32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      const float v = lane <= r ? (float)Xs[r * TLD + lane] : 0.f;       // Linv[r][lane]
+      LC32[(size_t)r * MP + lane] = v * c_s[r];
+      Linv32[(size_t)r * MP + lane] = v;
+      const float vt = r <= lane ? (float)Xs[lane * TLD + r] : 0.f;      // Linv[lane][r]
+      LinvT32[(size_t)r * MP + lane] = vt;
+      LCT32[(size_t)r * MP + lane] = vt * c_s[lane];
+    }
+    if (warp == 0) {
+      double t = 0.0;
+      for (int i = lane; i < M; ++i) t = fma(Xs[i * TLD + lane], (double)m_s[i], t);
+      ws_ptr<float>(a.ws, L.beta)[lane] = (float)t;
+    }
+  }
+  if (tid == 0) { stamps[1] = stamps[0]; stamps[7] = global_ns(); for (int k = 2; k < 7; ++k) stamps[k] = stamps[7]; stamps[13] = stamps[7]; }
+}
+
+// ==================================================================================================
 struct MmBwdArgs {
   gpblur_svgp_params p;
   WsLayout L;
@@ -1410,6 +1600,210 @@ __global__ void __launch_bounds__(kThreads) mm_backward_kernel(MmBwdArgs a) {
   (void)hyp;
 }
 
+// MP = 32: the backward of the one-block stage in ONE CTA (see mm_small_forward_kernel).  All operands (S, L, L^-1, Kzz,
+// Z~, W^T X: < 70 KB) are fetched into shared memory in one round trip; the chain of four 32 x 32 x 32 products, the
+// Kzz-path terms and the final bucket then run between CTA barriers instead of grid barriers + L2 round trips
+// (general kernel at M = 32: 23 us in-kernel, 45 us with the cooperative launch around it).
+constexpr size_t kSmallBwdSmem = (size_t)(6 * TB * TLD + 2 * TB * (GPBLUR_MAX_D + 1) + 6 * TB + GPBLUR_MAX_D + 8) * sizeof(double);
+
+__global__ void __launch_bounds__(kThreads) mm_small_backward_kernel(MmBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ss = reinterpret_cast<double*>(smem_raw);   // [32][33] S (stage gradient), later Wzz
+  double* Li = Ss + TB * TLD;                         // L^-1
+  double* Lm = Li + TB * TLD;                         // L
+  double* Kz = Lm + TB * TLD;                         // Kzz + jitter
+  double* Us = Kz + TB * TLD;                         // Lbar, then Tm
+  double* Ts = Us + TB * TLD;                         // Phi, then Kbar
+  double* Zd = Ts + TB * TLD;                         // [32][DP + 1] Z~ (double)
+  double* Wx = Zd + TB * (GPBLUR_MAX_D + 1);          // [32][DP + 1] W^T X (stage gradient)
+  double* u_s = Wx + TB * (GPBLUR_MAX_D + 1);         // [32]
+  double* beta_s = u_s + TB;                          // [32]
+  double* c_s = beta_s + TB;                          // [32]
+  double* cs_s = c_s + TB;                            // [32] colsum(W)
+  double* rz_s = cs_s + TB;                           // [32] row sums of Wzz
+  double* tcol = rz_s + TB;                           // [DP] column sums of the lengthscale terms
+
+  const WsLayout& L = a.L;
+  const int D = L.D, DP = L.DP, M = L.M, MP = L.MP;   // MP == 32
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ZP = DP + 1;
+  const double* hyp64 = ws_cptr<double>(a.ws, L.hyp64);
+  const float* inv_ell = ws_cptr<float>(a.ws, L.inv_ell);
+  const float* center = ws_cptr<float>(a.ws, L.center);
+  const float* Zt = ws_cptr<float>(a.ws, L.Zt);
+  const float* mvec = ws_cptr<float>(a.ws, L.mvec);
+  const float* cvec = ws_cptr<float>(a.ws, L.cvec);
+  const float* svec = ws_cptr<float>(a.ws, L.svec);
+  const float* beta = ws_cptr<float>(a.ws, L.beta);
+  const double* K64 = ws_cptr<double>(a.ws, L.K64);
+  const double* L64 = ws_cptr<double>(a.ws, L.L64);
+  const double* Li64 = ws_cptr<double>(a.ws, L.Linv64);
+  const double* u64 = a.sgrad;
+  const double* vec64 = a.sgrad + MP;
+  const double* S64 = vec64 + L.vec_len;
+  const double* WX64 = S64 + (size_t)MP * MP;
+  unsigned long long* stamps = ws_ptr<unsigned long long>(a.ws, L.stamps) + 16;
+  if (tid == 0) stamps[0] = global_ns();
+
+  // ---- one round trip: everything into shared memory ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp + 8 * i;
+    Ss[r * TLD + lane] = S64[(size_t)r * MP + lane];
+    Li[r * TLD + lane] = Li64[(size_t)r * MP + lane];
+    Lm[r * TLD + lane] = L64[(size_t)r * MP + lane];
+    Kz[r * TLD + lane] = K64[(size_t)r * MP + lane];
+  }
+  for (int idx = tid; idx < MP * DP; idx += kThreads) {
+    const int m = idx / DP, d = idx - m * DP;
+    Zd[m * ZP + d] = (double)Zt[idx];
+    Wx[m * ZP + d] = WX64[idx];
+  }
+  if (tid < MP) {
+    u_s[tid] = u64[tid];
+    beta_s[tid] = (double)beta[tid];
+    c_s[tid] = (double)cvec[tid];
+    cs_s[tid] = vec64[tid];
+  }
+  if (tid < DP) tcol[tid] = 0.0;
+  __syncthreads();
+
+  // out(r, lane) for r = warp + 8 i:  sum_k A(r, k) B(k, lane), A / B given as element functions of shared memory
+  // ---- phase 1: Lbar = -tril( beta u^T + 2 Linv^T diag(c) S ) -> Us ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp + 8 * i;
+    double acc = 0.0;
+    for (int k = 0; k < TB; ++k) acc = fma(Li[k * TLD + r] * c_s[k], Ss[k * TLD + lane], acc);
+    const double g = beta_s[r] * u_s[lane] + 2.0 * acc;
+    Us[r * TLD + lane] = (lane <= r) ? -g : 0.0;
+  }
+  __syncthreads();
+  // ---- phase 2: Phi( L^T Lbar ) -> Ts (lower, halved diagonal) ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp + 8 * i;
+    double acc = 0.0;
+    for (int k = 0; k < TB; ++k) acc = fma(Lm[k * TLD + r], Us[k * TLD + lane], acc);
+    Ts[r * TLD + lane] = lane > r ? 0.0 : (lane == r ? 0.5 * acc : acc);
+  }
+  __syncthreads();
+  // ---- phase 3: Tm = Phi Linv -> Us ----
+  {
+    double o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      double acc = 0.0;
+      for (int k = 0; k < TB; ++k) acc = fma(Ts[r * TLD + k], Li[k * TLD + lane], acc);
+      o[i] = acc;
+    }
+    __syncthreads();                       // (phase 2 results fully consumed before Us is overwritten - Us is not read
+#pragma unroll                             //  in phase 3, but keep the phases cleanly separated)
+    for (int i = 0; i < 4; ++i) Us[(warp + 8 * i) * TLD + lane] = o[i];
+  }
+  __syncthreads();
+  // ---- phase 4: Kbar = Linv^T Tm -> Ts (full) ----
+  {
+    double o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      double acc = 0.0;
+      for (int k = 0; k < TB; ++k) acc = fma(Li[k * TLD + r], Us[k * TLD + lane], acc);
+      o[i] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Ts[(warp + 8 * i) * TLD + lane] = o[i];
+  }
+  __syncthreads();
+  // ---- phase 5: Wzz = sym(Kbar) o (Kzz - jitter I) -> Ss ; row sums ----
+  {
+    const double zz_jitter = hyp64[H_JIT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      double v = 0.0;
+      if (r < M && lane < M) v = 0.5 * (Ts[r * TLD + lane] + Ts[lane * TLD + r]) * (Kz[r * TLD + lane] - (r == lane ? zz_jitter : 0.0));
+      Ss[r * TLD + lane] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < MP) {
+    double rz = 0.0;
+    for (int j = 0; j < TB; ++j) rz += Ss[tid * TLD + j];
+    rz_s[tid] = rz;
+  }
+  __syncthreads();
+  // (diag(S) of the stage gradient is needed in phase 7 and Ss now holds Wzz: it is re-read from global memory there)
+  // ---- phase 6: V = Wzz Z~ ; Kzz-path + a-space gradients of Z ; per-(i, d) lengthscale terms ----
+  for (int d0 = 0; d0 < DP; d0 += TB) {
+    const int d = d0 + lane;
+    double tsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      double V = 0.0;
+      for (int k = 0; k < TB; ++k) V = fma(Ss[r * TLD + k], Zd[k * ZP + d], V);
+      if (r < M && d < D) {
+        const double ie = (double)inv_ell[d], z = Zd[r * ZP + d], csum = cs_s[r], rz = rz_s[r];
+        const double wxt = (Wx[r * ZP + d] - csum * (double)center[d]) * ie;
+        const double dz = (wxt - csum * z) * ie + 2.0 * (V - rz * z) * ie;
+        GPBLUR_PUT(&a.bucket[(size_t)r * D + d], (float)dz);
+        tsum += -2.0 * z * wxt + csum * z * z + 2.0 * rz * z * z - 2.0 * z * V;
+      }
+    }
+    // column sums over the 32 rows: 8 warps x 4 rows each -> shared, added in warp order
+    __syncthreads();
+    double* part = Us;                     // [8][33] scratch (Us is free now)
+    part[warp * TLD + lane] = tsum;
+    __syncthreads();
+    if (warp == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += part[w8 * TLD + lane];
+      tcol[d] = t;
+    }
+    __syncthreads();
+  }
+  // ---- phase 7: final bucket ----
+  {
+    const double os = hyp64[H_OS];
+    const double gkl = a.g_kl ? (double)a.g_kl[0] : 0.0;
+    float* b_ell = a.bucket + (size_t)M * D;
+    float* b_os = b_ell + D;
+    float* b_m = b_os + 1;
+    float* b_s = b_m + M;
+    float* b_w = b_s + M;
+    float* b_b = b_w + D;
+    const double* q = vec64 + MP;
+    const double* wbar = vec64 + MP + DP;
+    const double* sc = vec64 + MP + 2 * DP;
+    if (tid < D) {
+      const double dell = (q[tid] + tcol[tid]) * (double)inv_ell[tid];
+      GPBLUR_PUT(&b_ell[tid], (float)(dell * sigmoid64((double)a.p.raw_lengthscale[tid])));
+      GPBLUR_PUT(&b_w[tid], a.p.mean_weights ? (float)wbar[tid] : 0.f);
+    }
+    if (tid >= 128 && tid < 128 + M) {
+      const int m = tid - 128;
+      const double mm = (double)mvec[m], ss = (double)svec[m];
+      GPBLUR_PUT(&b_m[m], (float)(u_s[m] + gkl * mm));
+      GPBLUR_PUT(&b_s[m], (float)(2.0 * ss * S64[(size_t)m * MP + m] + gkl * (ss - 1.0 / ss)));
+    }
+    if (warp == 7) {
+      double s = lane < M ? rz_s[lane] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) {
+        const double dos = (s + sc[VS_RSUM]) / os + sc[VS_GVAR];
+        GPBLUR_PUT(&b_os[0], (float)(dos * sigmoid64((double)a.p.raw_outputscale[0])));
+        GPBLUR_PUT(&b_b[0], (float)sc[VS_GMU]);
+      }
+    }
+  }
+  if (tid == 0) { const unsigned long long t = global_ns(); for (int k = 1; k < 9; ++k) stamps[k] = t; }
+}
+
 // Cooperative launches + cg grid.sync() by default.  GPBLUR_MM_COOP=0: plain launches + a counter barrier on a word
 // that a memset node zeroes before every launch - the kernels run equally fast, but each memset is one more graph node
 // (~3.5 us) on the critical path of a step.
@@ -1438,6 +1832,14 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
   // per-DEVICE attribute: set on every launch (cheap) instead of a process-wide flag
   cudaFuncSetAttribute(mm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nb = L.MP / TB;
+  if (nb == 1) {   // M <= 32: one CTA, no grid barrier, plain launch
+    cudaFuncSetAttribute(mm_small_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFwdSmem);
+    MmFwdArgs args{p, L, ws, kl, info, extra_jitter, nullptr, -1, nullptr};
+    ProfScope ps(ST_MM_FWD, st);
+    mm_small_forward_kernel<<<1, kThreads, kSmallFwdSmem, st>>>(args);
+    note_launch();
+    return check_launch("mm_small_forward");
+  }
   // CTA 0 (the factorisation chain) + workers, and enough CTAs that the final pass (fp32 tiles | operand images | beta
   // chunks) gives each of them one unit
   int n_img = 0;
@@ -1476,6 +1878,14 @@ int launch_mm_forward(const gpblur_svgp_params& p, const WsLayout& L, void* ws, 
 int launch_mm_backward(const gpblur_svgp_params& p, const WsLayout& L, void* stage, const double* sgrad,
                        const float* g_kl, float* grad_bucket, cudaStream_t st, int accumulate, int max_ctas) {
   const int nb = L.MP / TB;
+  if (nb == 1) {   // M <= 32: one CTA, everything in shared memory, plain launch
+    cudaFuncSetAttribute(mm_small_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallBwdSmem);
+    MmBwdArgs args{p, L, stage, sgrad, g_kl, grad_bucket, accumulate, nullptr};
+    ProfScope ps(ST_MM_BWD, st);
+    mm_small_backward_kernel<<<1, kThreads, kSmallBwdSmem, st>>>(args);
+    note_launch();
+    return check_launch("mm_small_backward");
+  }
   // 16-row tiles while that still gives every SM at most two of them (one CTA for a single 32 x 32 block, with CTA
   // barriers instead of grid barriers, was tried: 29 us against 21 us on 8 CTAs - the elementwise phases want the threads)
   const bool half = 2 * nb * nb <= 2 * 148;
