@@ -137,9 +137,11 @@ __host__ __device__ inline size_t tc_tiled_index(long long n, int m, int MP) {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 inline int choose_splits(long long N, int ntiles) {
-  // enough CTAs to fill ~2 waves of 148 SMs, each split at least 256 rows deep
+  // enough CTAs to fill ~2 waves of 148 SMs, each split at least 64 rows deep (FP32-FFMA path, M <= 32: a split walks
+  // its rows in 16-row slices behind a two-stage cp.async pipeline, ~0.8 us per slice - with 256-row splits the Gram of
+  // configs[0] (6 144 points) ran on 24 CTAs for 19 us)
   long long want = (2 * 148 + ntiles - 1) / ntiles;
-  long long maxs = (N + 255) / 256;
+  long long maxs = (N + 63) / 64;
   long long s = want < maxs ? want : maxs;
   if (s < 1) s = 1;
   if (s > kMaxSplits) s = kMaxSplits;
