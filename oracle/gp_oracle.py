@@ -18,7 +18,11 @@ therefore *restates the published gpytorch algorithm* at the reference's own cal
                                           /root/reference/train.py:20
 * exact GP model ........................ /root/reference/denoising_model/GPModel.py:4-13
 
-and pins itself with closed-form known-answer tests (tests/test_oracle.py) and fp64 gradcheck.
+and pins itself with closed-form known-answer tests (tests/test_oracle.py) and fp64 gradcheck.  One EXTERNAL anchor
+exists: tests/test_pin_sklearn.py checks both predictive restatements (and the exact GP) against scikit-learn's
+independent GaussianProcessRegressor - with m = L^-1 y_z, s = 0 the whitened SVGP predictive is an exact GP posterior -
+which fixes the ARD kernel, the outputscale, where the 1e-4 jitter goes, the whitening and the variance formula; the
+gpytorch-only conventions (variance clamp, ELBO scaling, first-call initialisation) remain restated from the source.
 
 gpytorch semantics restated (gpytorch >= 1.9, ``VariationalStrategy.forward`` whitened form):
   Kzz = os * exp(-1/2 |(z - z')/l|^2) + 1e-4 I         (settings.variational_cholesky_jitter, fp32)
