@@ -64,3 +64,29 @@ def test_exact_gp_oracle_against_sklearn():
     mean_s, cov_s = gpr.predict(sx.numpy(), return_cov=True)
     pm, pc = O.exact_gp_posterior(tx, ty, sx, c, rl, ro, rn)
     assert np.abs(pm.numpy() - (mean_s + float(c))).max() < 1e-9 and np.abs(pc.numpy() - cov_s).max() < 1e-9
+
+
+def test_elbo_terms_against_independent_implementations():
+    """KL(q(u) || p(u)) against torch.distributions' own closed form, and the expected log likelihood of
+    GaussianLikelihood.expected_log_prob against Gauss-Hermite quadrature of log N(y | f, noise) under f ~ N(mu, var)
+    (numpy's nodes): the two terms of forecast_denoising.py:87-89's ELBO, each pinned outside the restatement."""
+    g = torch.Generator().manual_seed(9)
+    M, B, L, num_data = 24, 3, 5, 32.0
+    p = O.clone_params(O.init_params_exercise(8, M, seed=5), torch.float64)
+    p["raw_noise"] = torch.tensor([0.3], dtype=torch.float64)
+    m, s = p["variational_mean"], p["variational_stddev"]
+    q = torch.distributions.MultivariateNormal(m, covariance_matrix=torch.diag(s * s))
+    prior = torch.distributions.MultivariateNormal(torch.zeros(M, dtype=torch.float64), torch.eye(M, dtype=torch.float64))
+    kl = O.kl_meanfield(p)
+    assert abs(float(kl) - float(torch.distributions.kl_divergence(q, prior))) < 1e-10
+    mu = torch.randn(B, L, generator=g, dtype=torch.float64)
+    var = torch.rand(B, L, generator=g, dtype=torch.float64) + 0.1
+    y = torch.randn(B, L, generator=g, dtype=torch.float64)
+    noise = O.noise_variance(p)
+    nodes, weights = np.polynomial.hermite.hermgauss(40)
+    f = mu.unsqueeze(-1) + torch.sqrt(2.0 * var).unsqueeze(-1) * torch.from_numpy(nodes)
+    logp = torch.distributions.Normal(f, float(noise.sqrt())).log_prob(y.unsqueeze(-1))
+    ell = (logp * torch.from_numpy(weights)).sum(-1) / np.sqrt(np.pi)             # E_q[log p(y | f)] per point
+    want = ell.mean(-1) - kl / num_data                                           # VariationalELBO: / L and KL / num_data
+    got = O.elbo_per_window(mu, var, y, noise, kl, num_data)
+    assert (got - want).abs().max() < 1e-10
