@@ -96,7 +96,7 @@ def bytes_per_window(L, D):
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock + throttle reasons DURING the timed region (NVML from a background thread, ~2 ms period;
+    """Samples SM clock + throttle reasons DURING the timed region (NVML from a background thread, ~1 ms period;
     falls back to one `nvidia-smi` query)."""
 
     def __init__(self, index: int):
@@ -107,30 +107,40 @@ class ClockSampler:
         self._stop = False
         self._thread = None
 
+    def _init(self):
+        """NVML set-up (import, nvmlInit, handle: tens of ms) - done by start() BEFORE the timed region, so that only
+        the cheap per-sample queries run beside it (initialising inside the sampling thread overlapped the first timed
+        steps with driver work and, at 20 steps, left a single sample)."""
+        import pynvml
+        pynvml.nvmlInit()
+        self._nv = pynvml
+        self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        self._names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                       "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                       "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                       "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        self._get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+
     def _run(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
             while not self._stop:
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                mask = int(get_reasons(h))
-                for nm, bit in names.items():
+                self.samples.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+                mask = int(self._get_reasons(self._h))
+                for nm, bit in self._names.items():
                     if mask & bit:
                         self.reasons.add(nm)
-                time.sleep(0.002)
+                time.sleep(0.001)
         except Exception:
             pass
 
     def start(self):
         import threading
+        try:
+            self._init()
+        except Exception:
+            return                                   # stop() falls back to one nvidia-smi query
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
@@ -462,7 +472,7 @@ def measure(args, wl, name, ctx, primary=True):
             bucket.all_reduce(average=True)               # NCCL AVG on the flat bucket: part of the captured step
         return elbo
 
-    allreduce_in_step = [True]
+    allreduce_in_step = [not args.allreduce_after_replay]
 
     def eager_step(i, xin, yin):
         for ly in layers:               # a real training step changes the parameters: recompute Kzz / Cholesky once
@@ -987,6 +997,8 @@ def main():
     ap.add_argument("--peer-allreduce", dest="peer_allreduce", action="store_true",
                     help="N > 1: the library's one-shot all-reduce over NVLink peer memory instead of NCCL (measured: "
                          "equal at 2 GPUs, slower than NCCL's in-switch reduction at 8)")
+    ap.add_argument("--allreduce-after-replay", action="store_true",
+                    help="N > 1: issue the NCCL all-reduce after the graph replay instead of capturing it in the step")
     ap.add_argument("--no-fuse-calls", dest="fuse_calls", action="store_false",
                     help="evaluate the GP once per activation (blur) instead of once per step (blur_segments)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the "
